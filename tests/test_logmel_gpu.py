@@ -1,0 +1,101 @@
+"""GPU parity of the log-mel kernel (through the C ABI) against the CPU oracle.
+Gate (BASELINE.json north_star): log-mel within 1e-4 relative in fp32.  The comparison is
+|got - want| <= 1e-4 * max(|want|, 1): relative where the log value is O(1) or larger, absolute 1e-4
+(= 1e-4 relative on the mel ENERGY) where log-mel passes through zero."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import logmel_ref as L
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def close(got, want):
+    assert got.shape == want.shape and got.dtype == np.float32
+    err = np.abs(got.astype(np.float64) - want) / np.maximum(np.abs(want), 1.0)
+    return float(err.max())
+
+
+@pytest.fixture(scope="module")
+def feat(built_lib):
+    assert torch.cuda.is_available()
+    from sed_crnn_b200 import feature
+    return feature
+
+
+@pytest.mark.parametrize("kind", ["mix", "noise", "chirp"])
+@pytest.mark.parametrize("n", [1, 1000, 1023, 1024, 1025, 2048, 2049, 4096, 44100, 2 * 44100 + 1, 1024 * 37])
+@pytest.mark.parametrize("pad_mode", ["constant", "reflect"])
+def test_mbe_parity_mono(feat, kind, n, pad_mode):
+    y = L.synth_clip(n % 97, n, 1, kind)[0]
+    want = L.mbe(y, pad_mode=pad_mode)
+    got = feat.mbe_device(torch.from_numpy(y).cuda(), pad_mode=pad_mode).cpu().numpy()
+    assert close(got, want) <= RTOL
+
+
+def test_drop_in_signature(feat):
+    y = L.synth_clip(11, 3 * 44100, 1, "mix")[0]
+    got = feat._mbe(y, feat.SR)
+    assert isinstance(got, np.ndarray) and got.shape == (1 + len(y) // 1024, 40)
+    assert close(got, L.mbe(y)) <= RTOL
+    assert (feat.SR, feat.NFFT, feat.HOP, feat.NB_MEL) == (44100, 2048, 1024, 40)
+
+
+@pytest.mark.parametrize("n_ch,n", [(2, 30001), (2, 30000), (3, 5000)])
+def test_multichannel_batch_layout(feat, n_ch, n):
+    clips = np.stack([L.synth_clip(20 + i, n, n_ch, "mix") for i in range(3)])
+    got = feat.mbe_device(torch.from_numpy(clips).cuda()).cpu().numpy()
+    assert got.shape == (3, 1 + n // 1024, n_ch * 40)
+    for i in range(3):
+        assert close(got[i], L.mbe_multichannel(clips[i])) <= RTOL
+
+
+def test_golden_fixture(feat, golden_dir):
+    g = np.load(os.path.join(golden_dir, "logmel_oracle.npz"))
+    for name in ("mix_1s", "noise_odd", "chirp_stereo", "short"):
+        for pm in ("constant", "reflect"):
+            got = feat.mbe_device(torch.from_numpy(g[name + "_pcm"]).cuda(), pad_mode=pm).cpu().numpy()
+            assert close(got, g[f"{name}_{pm}"]) <= RTOL, (name, pm)
+
+
+def test_other_sample_rate(feat):
+    y = L.synth_clip(5, 22050, 1, "noise")[0]
+    got = feat.mbe_device(torch.from_numpy(y).cuda(), sr=22050).cpu().numpy()
+    assert close(got, L.mbe(y, sr=22050)) <= RTOL
+
+
+def test_silence_and_errors(feat):
+    z = feat.mbe_device(torch.zeros(5000, device="cuda")).cpu().numpy()
+    assert np.all(np.isneginf(z))
+    with pytest.raises(ValueError):
+        feat._mbe(np.zeros(0, np.float32), 44100)
+    with pytest.raises(TypeError):
+        feat.mbe_device(torch.zeros(10))
+
+
+def test_full_size_properties(feat):
+    """BASELINE size (3-min stereo clip): size-independent checks -- frame-shift invariance (the same
+    audio delayed by one hop gives the same interior frames) and agreement with the oracle on a
+    strided sample of frames."""
+    n = 180 * 44100
+    rng = np.random.default_rng(0)
+    y = (0.1 * rng.standard_normal((2, n + 1024))).astype(np.float32)
+    d = torch.from_numpy(y).cuda()
+    a = feat.mbe_device(d[:, 1024:].contiguous())
+    b = feat.mbe_device(d[:, :n].contiguous())
+    assert a.shape == (7752, 80)
+    assert torch.equal(a[1:-2], b[2:-1])
+    idx = np.arange(0, 7752, 517)
+    want = L.mbe(y[1, 1024:])[idx]
+    assert close(a[:, 40:].cpu().numpy()[idx], want) <= RTOL
+
+
+def test_determinism(feat):
+    y = torch.from_numpy(L.synth_clip(1, 400000, 2, "mix")).cuda()
+    a = feat.mbe_device(y)
+    for _ in range(3):
+        assert torch.equal(a, feat.mbe_device(y))
