@@ -76,6 +76,103 @@ int    sedb200_logmel_host_f32(const float* pcm_host, int n_clips, int n_ch, lon
  * n_fft=2048, n_mels=40), feature.py:58) into a HOST buffer; for inspection / tests. */
 int    sedb200_mel_filterbank(int sr, float* out_host /* [40*1025] */);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * CRNN (conv blocks -> BiGRU stack -> per-frame dense -> logits), forward / loss / backward / Adam.
+ *
+ * Replaces the arithmetic of
+ *   crnn_lightning.py:41-73   TimePooledCRNN.forward          (Lightning variant)
+ *   sed.py:82-112             TimePooledCRNN.forward          (plain-torch variant)
+ *   crnn_lightning.py:27-35   FocalBCELoss.forward            sed.py:160 BCEWithLogitsLoss
+ *   loss.backward()           crnn_lightning.py:157-163 (Lightning), sed.py:137
+ *   clip_grad_norm_(1.0)+Adam train_lightning.py:50, crnn_lightning.py:195-197, sed.py:159
+ * for the hyper-parameters of train_constants.py:6-28 and of the BASELINE.json configs.
+ *
+ * Layouts
+ *   x        float32 [B][in_ch][H][W]  (NCHW, exactly what the reference feeds its Conv2d).
+ *            mode 0 ("fork",   crnn_lightning.py:66-70): H = mel, W = time; pooling (1,p) shrinks TIME;
+ *                     sequence axis = pooled W, features flattened as c*H + h.
+ *            mode 1 ("sednet", the BASELINE configs)   : H = time, W = mel; pooling (1,p) shrinks MEL;
+ *                     sequence axis = H, features flattened as c*W' + w.
+ *   logits   float32 [B][T][n_classes]
+ *   params   one flat float32 buffer; tensor i lives at offsets[i] (sedb200_crnn_param_layout), in
+ *            PyTorch's own shapes: conv weight [C][Cin][3][3], GRU weight_ih [3H][in] with gate order
+ *            r,z,n, Linear weight [out][in].  Order: per conv block {conv.weight, conv.bias, bn.weight,
+ *            bn.bias}; per GRU layer {w_ih[2 dirs], w_hh[2], b_ih[2], b_hh[2]}; per dense {weight, bias}.
+ *   bn_state float32: per conv block {running_mean[C], running_var[C]}, contiguous.
+ *   grads    same layout as params.
+ */
+#define SEDB200_MAX_CONV  4
+#define SEDB200_MAX_GRU   4
+#define SEDB200_MAX_DENSE 3
+
+#define SEDB200_LOSS_BCE   0           /* sed.py:160 */
+#define SEDB200_LOSS_FOCAL 1           /* crnn_lightning.py:27-35 */
+
+typedef struct sedb200_crnn_desc {
+    int   mode;                        /* 0 fork, 1 sednet */
+    int   in_ch, H, W;
+    int   n_conv, conv_ch;
+    int   pool[SEDB200_MAX_CONV];
+    int   n_gru;
+    int   gru_units[SEDB200_MAX_GRU];
+    int   n_dense;                     /* including the final n_classes layer */
+    int   dense_units[SEDB200_MAX_DENSE];
+    int   dense_relu;                  /* ReLU after every dense layer but the last (crnn_lightning.py:72) */
+    float dropout;                     /* crnn_lightning.py:52 / sed.py:92 */
+    int   dropout_each_block;          /* sed.py:107 applies it after every block */
+    float bn_eps, bn_momentum;         /* nn.BatchNorm2d defaults 1e-5 / 0.1 */
+} sedb200_crnn_desc;
+
+/* geometry helpers (host only, no GPU needed) */
+int    sedb200_crnn_validate(const sedb200_crnn_desc* d);
+int    sedb200_crnn_seq_len(const sedb200_crnn_desc* d);            /* T  */
+int    sedb200_crnn_flat(const sedb200_crnn_desc* d);               /* GRU-1 input width */
+int    sedb200_crnn_n_tensors(const sedb200_crnn_desc* d);
+long   sedb200_crnn_param_layout(const sedb200_crnn_desc* d, long* offsets /* [n_tensors] or NULL */);
+long   sedb200_crnn_bn_state_floats(const sedb200_crnn_desc* d);
+size_t sedb200_crnn_workspace_bytes(const sedb200_crnn_desc* d, int batch);
+
+/* Forward.  training != 0: batch-statistics BatchNorm (running stats in bn_state_dev are updated),
+ * dropout with the counter-based generator keyed by `seed`, activations saved in `ws_dev` for
+ * sedb200_crnn_backward.  training == 0: running statistics, no dropout. */
+int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params_dev, float* bn_state_dev,
+                         const float* x_dev, int batch, int training, unsigned long long seed,
+                         void* ws_dev, size_t ws_bytes, float* logits_dev, void* stream);
+
+/* Loss + its gradient in one pass over the logits.  loss_dev[0] = mean loss; probs_dev (optional) =
+ * sigmoid(logits) (crnn_lightning.py:98); dlogits_dev (optional) = d(mean loss)/d(logits) * grad_scale. */
+int sedb200_loss_fwd_bwd(int loss_kind, float alpha, float gamma, const float* logits_dev,
+                         const float* targets_dev, long n, float grad_scale, float* loss_dev,
+                         float* probs_dev, float* dlogits_dev, void* scratch_dev, size_t scratch_bytes,
+                         void* stream);
+size_t sedb200_loss_scratch_bytes(long n);
+
+/* Backward of the last training forward held in ws_dev: grads_dev (same layout as params) is
+ * OVERWRITTEN with d(loss)/d(params); dx_dev (optional, [B][in_ch][H][W]) receives d(loss)/d(x). */
+int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params_dev, const float* x_dev,
+                          int batch, unsigned long long seed, void* ws_dev, size_t ws_bytes,
+                          const float* dlogits_dev, float* grads_dev, float* dx_dev, void* stream);
+
+/* Global-norm clip (clip_grad_norm_ semantics: coef = min(1, max_norm/(norm+1e-6)); max_norm <= 0
+ * disables) followed by torch.optim.Adam with coupled L2 weight decay, over flat buffers.
+ * grad_prescale multiplies every gradient first (1/world_size after a sum all-reduce).
+ * gnorm_dev[0] receives the pre-clip global norm. */
+size_t sedb200_clip_adam_scratch_bytes(long n);
+int sedb200_clip_adam(float* params_dev, const float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev,
+                      long n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                      long step /* 1-based */, float max_norm, float grad_prescale, float* gnorm_dev,
+                      void* scratch_dev, size_t scratch_bytes, void* stream);
+
+/* sigmoid -> strict > 0.5 -> integer counts behind metrics.py:20-68 (crnn_lightning.py:112-126).
+ * probs/targets: float32 [n_rows][n_cls] (the [N,T,C] arrays flattened by utils.reshape_3Dto2D).
+ * counts_dev: 12 uint64 = {TP,Nsys,Nref,S,D,I} framewise, then the same six after block-max with
+ * `block` rows per block; ceil(n_rows/block) blocks feed TP/Nsys/Nref (metrics.py:50),
+ * floor(n_rows/block) blocks feed S/D/I and a second Nref stored in slot 12 (metrics.py:62).
+ * counts_dev therefore has 13 entries. */
+int sedb200_threshold_counts(const float* probs_dev, const float* targets_dev, long n_rows, int n_cls,
+                             int block, float threshold, unsigned long long* counts_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,7 +33,29 @@ SIGNATURES = {
     "sedb200_logmel_host_scratch": (_sz, [_i, _i, _l]),
     "sedb200_logmel_host_f32": (_i, [_p, _i, _i, _l, _i, _i, _p, _p, _sz, _p]),
     "sedb200_mel_filterbank": (_i, [_i, _p]),
+    "sedb200_crnn_validate": (_i, [_p]),
+    "sedb200_crnn_seq_len": (_i, [_p]),
+    "sedb200_crnn_flat": (_i, [_p]),
+    "sedb200_crnn_n_tensors": (_i, [_p]),
+    "sedb200_crnn_param_layout": (_l, [_p, _p]),
+    "sedb200_crnn_bn_state_floats": (_l, [_p]),
+    "sedb200_crnn_workspace_bytes": (_sz, [_p, _i]),
+    "sedb200_crnn_forward": (_i, [_p, _p, _p, _p, _i, _i, C.c_ulonglong, _p, _sz, _p, _p]),
+    "sedb200_loss_fwd_bwd": (_i, [_i, _f, _f, _p, _p, _l, _f, _p, _p, _p, _p, _sz, _p]),
+    "sedb200_loss_scratch_bytes": (_sz, [_l]),
+    "sedb200_crnn_backward": (_i, [_p, _p, _p, _i, C.c_ulonglong, _p, _sz, _p, _p, _p, _p]),
+    "sedb200_clip_adam_scratch_bytes": (_sz, [_l]),
+    "sedb200_clip_adam": (_i, [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _l, _f, _f, _p, _p, _sz, _p]),
+    "sedb200_threshold_counts": (_i, [_p, _p, _l, _i, _i, _f, _p, _p]),
 }
+
+
+class CrnnDesc(C.Structure):
+    """mirror of `sedb200_crnn_desc` (include/sedb200.h)"""
+    _fields_ = [("mode", _i), ("in_ch", _i), ("H", _i), ("W", _i), ("n_conv", _i), ("conv_ch", _i),
+                ("pool", _i * 4), ("n_gru", _i), ("gru_units", _i * 4), ("n_dense", _i),
+                ("dense_units", _i * 3), ("dense_relu", _i), ("dropout", _f), ("dropout_each_block", _i),
+                ("bn_eps", _f), ("bn_momentum", _f)]
 
 
 def header_symbols() -> list[str]:

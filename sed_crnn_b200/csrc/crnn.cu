@@ -1,0 +1,588 @@
+// crnn.cu -- CRNN forward / backward orchestration and the conv-block elementwise kernels.
+//
+// Reference arithmetic (see include/sedb200.h): crnn_lightning.py:41-73, sed.py:82-112.
+// Internal activation layout is channels-last [B][H][W][C]; the last conv block writes straight
+// into the GRU-ready [B][T][flat] layout (feature = c*F + f), which removes the reference's
+// permute+reshape copy (crnn_lightning.py:68-70).
+//
+// This file holds the fp32-exact path: contractions run through the functor GEMM of gemm_simt.cuh.
+#include "crnn_plan.cuh"
+#include "gemm_simt.cuh"
+#include "gru_scan.cuh"
+
+#include <algorithm>
+
+namespace sedb200 {
+namespace {
+
+// ----------------------------------------------------------------------------- GEMM operand functors
+struct RowMajor {                       // op(row, k) = p[row*ld + k]
+    static constexpr bool kContigK = true;
+    const float* p; long ld;
+    __device__ float operator()(int r, int k) const { return __ldg(p + (long)r * ld + k); }
+};
+struct ColMajor {                       // op(row, k) = p[k*ld + row]
+    static constexpr bool kContigK = false;
+    const float* p; long ld;
+    __device__ float operator()(int r, int k) const { return __ldg(p + (long)k * ld + r); }
+};
+
+// im2col view of a conv input with arbitrary strides (NCHW user input or channels-last activation):
+// A(m, k), m = (b,h,w), k = tap*Cin + ci
+struct ConvFwdA {
+    static constexpr bool kContigK = true;
+    const float* in; int H, W, Cin; long sB, sH, sW, sC;
+    __device__ float operator()(int m, int k) const {
+        const int w = m % W, t = m / W, h = t % H, b = t / H;
+        const int ci = k % Cin, tap = k / Cin, r = tap / 3, s = tap - 3 * r;
+        const int hh = h + r - 1, ww = w + s - 1;
+        if ((unsigned)hh >= (unsigned)H || (unsigned)ww >= (unsigned)W) return 0.0f;
+        return __ldg(in + b * sB + hh * sH + ww * sW + ci * sC);
+    }
+};
+struct ConvFwdB {                       // B(n, k) = weight[n][ci][tap]
+    static constexpr bool kContigK = false;
+    const float* w; int Cin;
+    __device__ float operator()(int n, int k) const {
+        const int ci = k % Cin, tap = k / Cin;
+        return __ldg(w + ((long)n * Cin + ci) * 9 + tap);
+    }
+};
+// dgrad: dIn(m=(b,h,w), ci) = sum_{tap,co} dY[b][h-r+1][w-s+1][co] * weight[co][ci][tap]
+struct ConvDgradA {                     // k = tap*C + co
+    static constexpr bool kContigK = true;
+    const float* dy; int H, W, C;
+    __device__ float operator()(int m, int k) const {
+        const int w = m % W, t = m / W, h = t % H, b = t / H;
+        const int co = k % C, tap = k / C, r = tap / 3, s = tap - 3 * r;
+        const int hh = h - r + 1, ww = w - s + 1;
+        if ((unsigned)hh >= (unsigned)H || (unsigned)ww >= (unsigned)W) return 0.0f;
+        return __ldg(dy + (((long)b * H + hh) * W + ww) * C + co);
+    }
+};
+struct ConvDgradB {                     // B(n=ci, k=(tap,co))
+    static constexpr bool kContigK = false;
+    const float* w; int Cin, C;
+    __device__ float operator()(int n, int k) const {
+        const int co = k % C, tap = k / C;
+        return __ldg(w + ((long)co * Cin + n) * 9 + tap);
+    }
+};
+// wgrad: dW(co, j=ci*9+tap) = sum_p dY[p][co] * In[p shifted by tap][ci]
+struct ConvWgradB {                     // B(n=j, k=p)
+    static constexpr bool kContigK = false;
+    const float* in; int H, W; long sB, sH, sW, sC;
+    __device__ float operator()(int n, int k) const {
+        const int ci = n / 9, tap = n - 9 * ci, r = tap / 3, s = tap - 3 * r;
+        const int w = k % W, t = k / W, h = t % H, b = t / H;
+        const int hh = h + r - 1, ww = w + s - 1;
+        if ((unsigned)hh >= (unsigned)H || (unsigned)ww >= (unsigned)W) return 0.0f;
+        return __ldg(in + b * sB + hh * sH + ww * sW + ci * sC);
+    }
+};
+// h_{t-1} of one GRU direction, as B(n=j, k=(b,t)) for dW_hh
+struct HPrevB {
+    static constexpr bool kContigK = false;
+    const float* out; int T, H, dir;
+    __device__ float operator()(int n, int k) const {
+        const int t = k % T;
+        const int tp = dir ? t + 1 : t - 1;
+        if (tp < 0 || tp >= T) return 0.0f;
+        return __ldg(out + ((long)(k - t + tp)) * 2 * H + dir * H + n);
+    }
+};
+
+struct EpiStore {                       // out[m*ld + n] = act(acc + bias[n])
+    float* out; long ld; const float* bias; int relu;
+    __device__ void operator()(int m, int n, float acc, int) const {
+        float v = acc + (bias ? __ldg(bias + n) : 0.0f);
+        if (relu) v = fmaxf(v, 0.0f);
+        out[(long)m * ld + n] = v;
+    }
+};
+struct EpiPartial {                     // part[z][m*ld + n] = acc
+    float* part; long mn, ld;
+    __device__ void operator()(int m, int n, float acc, int z) const { part[(long)z * mn + (long)m * ld + n] = acc; }
+};
+struct EpiReluMask {                    // out = act > 0 ? acc : 0   (gradient through a ReLU'd dense layer)
+    float* out; long ld; const float* act;
+    __device__ void operator()(int m, int n, float acc, int) const {
+        const long i = (long)m * ld + n;
+        out[i] = __ldg(act + i) > 0.0f ? acc : 0.0f;
+    }
+};
+struct EpiStrided {                     // dx in NCHW from m = (b,h,w), n = ci
+    float* out; int H, W; long sB, sH, sW, sC;
+    __device__ void operator()(int m, int n, float acc, int) const {
+        const int w = m % W, t = m / W, h = t % H, b = t / H;
+        out[b * sB + h * sH + w * sW + n * sC] = acc;
+    }
+};
+
+// ----------------------------------------------------------------------------- BatchNorm statistics
+// stat layout: [0,C) mean, [C,2C) invstd, [2C,3C) scale = gamma*invstd, [3C,4C) shift = beta - mean*scale
+__global__ void bn_finalize_train_kernel(const float* __restrict__ part, int nblk, int C, long n,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                         float eps, float momentum, float* __restrict__ running,
+                                         float* __restrict__ stat) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, ss = 0.0;
+    for (int k = 0; k < nblk; ++k) {
+        s += (double)part[((long)k * 2 + 0) * C + c];
+        ss += (double)part[((long)k * 2 + 1) * C + c];
+    }
+    const double mean = s / (double)n;
+    double var = ss / (double)n - mean * mean;          // biased (normalisation)
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * invstd;
+    stat[c] = (float)mean;
+    stat[C + c] = invstd;
+    stat[2 * C + c] = sc;
+    stat[3 * C + c] = beta[c] - (float)mean * sc;
+    const double unbiased = n > 1 ? var * (double)n / (double)(n - 1) : var;
+    running[c] = (1.0f - momentum) * running[c] + momentum * (float)mean;
+    running[C + c] = (1.0f - momentum) * running[C + c] + momentum * (float)unbiased;
+}
+
+__global__ void bn_finalize_eval_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                        float eps, const float* __restrict__ running, float* __restrict__ stat) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float mean = running[c];
+    const float invstd = 1.0f / sqrtf(running[C + c] + eps);
+    const float sc = gamma[c] * invstd;
+    stat[c] = mean;
+    stat[C + c] = invstd;
+    stat[2 * C + c] = sc;
+    stat[3 * C + c] = beta[c] - mean * sc;
+}
+
+// ----------------------------------------------------------------------------- dropout generator
+__device__ __forceinline__ float uniform01(unsigned long long seed, unsigned long long idx) {
+    unsigned long long x = seed + idx * 0x9E3779B97F4A7C15ull;
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return (float)(x >> 40) * (1.0f / 16777216.0f);
+}
+__host__ __device__ inline unsigned long long block_seed(unsigned long long seed, int block) {
+    return seed * 0x2545F4914F6CDD1Dull + (unsigned long long)(block + 1) * 0xD6E8FEB86659FD93ull;
+}
+
+struct PoolGeom {
+    int H, W, Wo, C, p;
+    long oB, oH, oW, oC;         // strides of the block OUTPUT (channels-last, or the [B][T][flat] layout)
+    float drop_p;                // 0 disables
+    unsigned long long seed;
+};
+
+// ----------------------------------------------------------------------------- BN + ReLU + max-pool(1,p) (+dropout)
+__global__ void __launch_bounds__(256)
+bn_relu_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ stat, float* __restrict__ out,
+                        long n_vec, PoolGeom g) {
+    const int C4 = g.C >> 2;
+    const float keep_scale = g.drop_p > 0.0f ? 1.0f / (1.0f - g.drop_p) : 1.0f;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        long t = i / C4;
+        const int wo = (int)(t % g.Wo); t /= g.Wo;
+        const int h = (int)(t % g.H);
+        const long b = t / g.H;
+        const int c = c4 * 4;
+        const float4 sc = *reinterpret_cast<const float4*>(stat + 2 * g.C + c);
+        const float4 sh = *reinterpret_cast<const float4*>(stat + 3 * g.C + c);
+        const float* src = y + (((b * g.H + h) * g.W) + (long)wo * g.p) * g.C + c;
+        float4 m = make_float4(0.0f, 0.0f, 0.0f, 0.0f);           // relu floor
+        for (int j = 0; j < g.p; ++j) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src + (long)j * g.C));
+            m.x = fmaxf(m.x, fmaf(v.x, sc.x, sh.x));
+            m.y = fmaxf(m.y, fmaf(v.y, sc.y, sh.y));
+            m.z = fmaxf(m.z, fmaf(v.z, sc.z, sh.z));
+            m.w = fmaxf(m.w, fmaf(v.w, sc.w, sh.w));
+        }
+        if (g.drop_p > 0.0f) {
+            const unsigned long long e = (unsigned long long)i * 4;
+            m.x = uniform01(g.seed, e + 0) >= g.drop_p ? m.x * keep_scale : 0.0f;
+            m.y = uniform01(g.seed, e + 1) >= g.drop_p ? m.y * keep_scale : 0.0f;
+            m.z = uniform01(g.seed, e + 2) >= g.drop_p ? m.z * keep_scale : 0.0f;
+            m.w = uniform01(g.seed, e + 3) >= g.drop_p ? m.w * keep_scale : 0.0f;
+        }
+        float* dst = out + b * g.oB + h * g.oH + wo * g.oW + c * g.oC;
+        if (g.oC == 1) {
+            *reinterpret_cast<float4*>(dst) = m;
+        } else {
+            dst[0] = m.x; dst[g.oC] = m.y; dst[2 * g.oC] = m.z; dst[3 * g.oC] = m.w;
+        }
+    }
+}
+
+// shared by the two backward passes: for one pooling window and 4 channels, recompute the winner and
+// return dz at the winner (0 elsewhere) plus the winner index.
+struct WindowGrad { float dz[4]; int arg[4]; };
+
+__device__ __forceinline__ WindowGrad window_grad(const float* __restrict__ src, const float* __restrict__ dA,
+                                                  const float4 sc, const float4 sh, const PoolGeom& g, long i) {
+    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    WindowGrad r;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r.arg[q] = 0;
+    for (int j = 0; j < g.p; ++j) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + (long)j * g.C));
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float z = fmaf(vv[q], scv[q], shv[q]);
+            if (z > best[q]) { best[q] = z; r.arg[q] = j; }      // first maximum wins (PyTorch max_pool2d)
+        }
+    }
+    const float keep_scale = g.drop_p > 0.0f ? 1.0f / (1.0f - g.drop_p) : 1.0f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float gq = __ldg(dA + q * g.oC);
+        if (g.drop_p > 0.0f)
+            gq = uniform01(g.seed, (unsigned long long)i * 4 + q) >= g.drop_p ? gq * keep_scale : 0.0f;
+        r.dz[q] = best[q] > 0.0f ? gq : 0.0f;                       // ReLU gate
+    }
+    return r;
+}
+
+// pass 1: per-channel sum(dz) and sum(dz * xhat); part layout [nblk][2][C]
+__global__ void __launch_bounds__(256)
+bn_pool_bwd_sums_kernel(const float* __restrict__ y, const float* __restrict__ stat, const float* __restrict__ dA,
+                        long n_pix, PoolGeom g, float* __restrict__ part) {
+    __shared__ float4 s1[256], s2[256];
+    const int C4 = g.C >> 2, rows = 256 / C4;
+    const int c4 = threadIdx.x % C4, prow = threadIdx.x / C4;
+    const int c = c4 * 4;
+    const float4 sc = *reinterpret_cast<const float4*>(stat + 2 * g.C + c);
+    const float4 sh = *reinterpret_cast<const float4*>(stat + 3 * g.C + c);
+    const float4 mu = *reinterpret_cast<const float4*>(stat + c);
+    const float4 is = *reinterpret_cast<const float4*>(stat + g.C + c);
+    const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, isv[4] = {is.x, is.y, is.z, is.w};
+    float a[4] = {0, 0, 0, 0}, bsum[4] = {0, 0, 0, 0};
+    for (long pix = (long)blockIdx.x * rows + prow; pix < n_pix; pix += (long)gridDim.x * rows) {
+        long t = pix;
+        const int wo = (int)(t % g.Wo); t /= g.Wo;
+        const int h = (int)(t % g.H);
+        const long b = t / g.H;
+        const float* src = y + (((b * g.H + h) * g.W) + (long)wo * g.p) * g.C + c;
+        const float* da = dA + b * g.oB + h * g.oH + wo * g.oW + c * g.oC;
+        const WindowGrad wg = window_grad(src, da, sc, sh, g, pix * C4 + c4);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float xh = (__ldg(src + (long)wg.arg[q] * g.C + q) - muv[q]) * isv[q];
+            a[q] += wg.dz[q];
+            bsum[q] = fmaf(wg.dz[q], xh, bsum[q]);
+        }
+    }
+    s1[threadIdx.x] = make_float4(a[0], a[1], a[2], a[3]);
+    s2[threadIdx.x] = make_float4(bsum[0], bsum[1], bsum[2], bsum[3]);
+    __syncthreads();
+    if (prow == 0) {
+        float4 ta = make_float4(0, 0, 0, 0), tb = make_float4(0, 0, 0, 0);
+        for (int r = 0; r < rows; ++r) {
+            const float4 u = s1[r * C4 + c4], v = s2[r * C4 + c4];
+            ta.x += u.x; ta.y += u.y; ta.z += u.z; ta.w += u.w;
+            tb.x += v.x; tb.y += v.y; tb.z += v.z; tb.w += v.w;
+        }
+        *reinterpret_cast<float4*>(part + ((long)blockIdx.x * 2 + 0) * g.C + c) = ta;
+        *reinterpret_cast<float4*>(part + ((long)blockIdx.x * 2 + 1) * g.C + c) = tb;
+    }
+}
+
+// reduce pass-1 partials: d(beta) = sum dz, d(gamma) = sum dz*xhat; bnsum = {mean dz, mean dz*xhat}
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nblk, int C, long n,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       float* __restrict__ bnsum) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, sx = 0.0;
+    for (int k = 0; k < nblk; ++k) {
+        s += (double)part[((long)k * 2 + 0) * C + c];
+        sx += (double)part[((long)k * 2 + 1) * C + c];
+    }
+    dbeta[c] = (float)s;
+    dgamma[c] = (float)sx;
+    bnsum[c] = (float)(s / (double)n);
+    bnsum[C + c] = (float)(sx / (double)n);
+}
+
+// pass 2: dy = scale * (dz - mean(dz) - xhat * mean(dz*xhat)) for EVERY conv output element
+__global__ void __launch_bounds__(256)
+bn_pool_bwd_dy_kernel(const float* __restrict__ y, const float* __restrict__ stat, const float* __restrict__ dA,
+                      const float* __restrict__ bnsum, long n_vec, PoolGeom g, float* __restrict__ dy) {
+    const int C4 = g.C >> 2;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        long t = i / C4;
+        const int wo = (int)(t % g.Wo); t /= g.Wo;
+        const int h = (int)(t % g.H);
+        const long b = t / g.H;
+        const int c = c4 * 4;
+        const float4 sc = *reinterpret_cast<const float4*>(stat + 2 * g.C + c);
+        const float4 sh = *reinterpret_cast<const float4*>(stat + 3 * g.C + c);
+        const float4 mu = *reinterpret_cast<const float4*>(stat + c);
+        const float4 is = *reinterpret_cast<const float4*>(stat + g.C + c);
+        const float4 k1 = *reinterpret_cast<const float4*>(bnsum + c);
+        const float4 k2 = *reinterpret_cast<const float4*>(bnsum + g.C + c);
+        const long row = ((b * g.H + h) * g.W) + (long)wo * g.p;
+        const float* src = y + row * g.C + c;
+        const float* da = dA + b * g.oB + h * g.oH + wo * g.oW + c * g.oC;
+        const WindowGrad wg = window_grad(src, da, sc, sh, g, i);
+        // the last window of a row also owns the columns the floor-mode pooling drops
+        const int span = (wo == g.Wo - 1) ? g.W - wo * g.p : g.p;
+        for (int j = 0; j < span; ++j) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src + (long)j * g.C));
+            float4 o;
+            o.x = sc.x * ((wg.arg[0] == j && j < g.p ? wg.dz[0] : 0.0f) - k1.x - (v.x - mu.x) * is.x * k2.x);
+            o.y = sc.y * ((wg.arg[1] == j && j < g.p ? wg.dz[1] : 0.0f) - k1.y - (v.y - mu.y) * is.y * k2.y);
+            o.z = sc.z * ((wg.arg[2] == j && j < g.p ? wg.dz[2] : 0.0f) - k1.z - (v.z - mu.z) * is.z * k2.z);
+            o.w = sc.w * ((wg.arg[3] == j && j < g.p ? wg.dz[3] : 0.0f) - k1.w - (v.w - mu.w) * is.w * k2.w);
+            *reinterpret_cast<float4*>(dy + (row + j) * g.C + c) = o;
+        }
+    }
+}
+
+inline int ew_blocks(long n) { return (int)std::min<long>((n + 255) / 256, 148L * 16); }
+
+PoolGeom pool_geom(const Plan& P, const sedb200_crnn_desc* d, int i, int training, unsigned long long seed) {
+    PoolGeom g;
+    g.H = P.H; g.W = P.win[i]; g.Wo = P.wout[i]; g.C = P.C; g.p = P.pool[i];
+    const bool last = (i == P.n_conv - 1);
+    if (!last) {
+        g.oC = 1; g.oW = P.C; g.oH = (long)g.Wo * P.C; g.oB = (long)P.H * g.Wo * P.C;
+    } else if (d->mode == 0) {          // [B][T=wo][c*H + h]
+        g.oB = (long)P.T * P.flat; g.oW = P.flat; g.oC = P.H; g.oH = 1;
+    } else {                            // [B][T=h][c*Wo + wo]
+        g.oB = (long)P.T * P.flat; g.oH = P.flat; g.oC = g.Wo; g.oW = 1;
+    }
+    const bool drop = training && d->dropout > 0.0f && (d->dropout_each_block || last);
+    g.drop_p = drop ? d->dropout : 0.0f;
+    g.seed = block_seed(seed, i);
+    return g;
+}
+
+struct InStrides { long sB, sH, sW, sC; };
+InStrides in_strides(const Plan& P, const sedb200_crnn_desc* d, int i) {
+    if (i == 0) return {(long)d->in_ch * P.H * P.win[0], (long)P.win[0], 1L, (long)P.H * P.win[0]};   // NCHW
+    return {(long)P.H * P.win[i] * P.C, (long)P.win[i] * P.C, (long)P.C, 1L};                          // NHWC
+}
+
+inline float* wsf(void* ws, size_t off) { return reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + off); }
+
+}  // namespace
+}  // namespace sedb200
+
+using namespace sedb200;
+
+extern "C" {
+
+int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float* bn_state, const float* x,
+                         int batch, int training, unsigned long long seed, void* ws, size_t ws_bytes,
+                         float* logits, void* stream) {
+    Plan P;
+    int rc = make_plan(d, batch, &P);
+    if (rc) return rc;
+    SED_REQUIRE(batch >= 1, SEDB200_EINVAL, "crnn_forward: batch %d", batch);
+    SED_REQUIRE(params && bn_state && x && ws && logits, SEDB200_EINVAL, "crnn_forward: null buffer");
+    SED_REQUIRE(ws_bytes >= P.ws_bytes, SEDB200_EWORKSPACE, "crnn_forward: workspace %zu < %zu bytes", ws_bytes, P.ws_bytes);
+    rc = require_sm100();
+    if (rc) return rc;
+    cudaStream_t st = as_stream(stream);
+    const long B = batch;
+
+    // ---- conv blocks
+    for (int i = 0; i < P.n_conv; ++i) {
+        const float* in = i == 0 ? x : wsf(ws, P.act[i - 1]);
+        const InStrides s = in_strides(P, d, i);
+        const int M = (int)(B * P.H * P.win[i]), K = 9 * P.cin[i];
+        float* y = wsf(ws, P.y[i]);
+        rc = gemm_simt(M, P.C, K, 1, ConvFwdA{in, P.H, P.win[i], P.cin[i], s.sB, s.sH, s.sW, s.sC},
+                       ConvFwdB{params + P.conv_w[i], P.cin[i]}, EpiStore{y, P.C, params + P.conv_b[i], 0}, st);
+        if (rc) return rc;
+        float* stat = wsf(ws, P.stat[i]);
+        float* running = bn_state + 2L * i * P.C;
+        if (training) {
+            int nblk = 0;
+            rc = colsum_partials(y, M, P.C, wsf(ws, P.part), &nblk, st);
+            if (rc) return rc;
+            bn_finalize_train_kernel<<<(P.C + 127) / 128, 128, 0, st>>>(
+                wsf(ws, P.part), nblk, P.C, (long)M, params + P.bn_w[i], params + P.bn_b[i], d->bn_eps,
+                d->bn_momentum, running, stat);
+        } else {
+            bn_finalize_eval_kernel<<<(P.C + 127) / 128, 128, 0, st>>>(P.C, params + P.bn_w[i], params + P.bn_b[i],
+                                                                       d->bn_eps, running, stat);
+        }
+        SED_CUDA_OK(cudaGetLastError());
+        const PoolGeom g = pool_geom(P, d, i, training, seed);
+        const long n_vec = B * P.H * P.wout[i] * (P.C / 4);
+        bn_relu_pool_fwd_kernel<<<ew_blocks(n_vec), 256, 0, st>>>(y, stat, wsf(ws, P.act[i]), n_vec, g);
+        SED_CUDA_OK(cudaGetLastError());
+    }
+
+    // ---- BiGRU stack
+    const int BT = (int)(B * P.T);
+    const float* seq = wsf(ws, P.act[P.n_conv - 1]);
+    for (int l = 0; l < P.n_gru; ++l) {
+        const int h = P.gh[l], in = P.gin[l];
+        float* gi = wsf(ws, P.gi[l]);
+        rc = gemm_simt(BT, 6 * h, in, 1, RowMajor{seq, in}, RowMajor{params + P.wih[l], in},
+                       EpiStore{gi, 6L * h, params + P.bih[l], 0}, st);
+        if (rc) return rc;
+        rc = gru_scan_forward(gi, params + P.whh[l], params + P.bhh[l], wsf(ws, P.gout[l]), wsf(ws, P.gates[l]),
+                              batch, P.T, h, st);
+        if (rc) return rc;
+        seq = wsf(ws, P.gout[l]);
+    }
+
+    // ---- per-frame dense head
+    for (int j = 0; j < P.n_dense; ++j) {
+        const bool last = (j == P.n_dense - 1);
+        float* out = last ? logits : wsf(ws, P.hid[j]);
+        rc = gemm_simt(BT, P.dout[j], P.din[j], 1, RowMajor{seq, P.din[j]}, RowMajor{params + P.dn_w[j], P.din[j]},
+                       EpiStore{out, P.dout[j], params + P.dn_b[j], (!last && d->dense_relu) ? 1 : 0}, st);
+        if (rc) return rc;
+        seq = out;
+    }
+    return SEDB200_OK;
+}
+
+int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const float* x, int batch,
+                          unsigned long long seed, void* ws, size_t ws_bytes, const float* dlogits,
+                          float* grads, float* dx, void* stream) {
+    Plan P;
+    int rc = make_plan(d, batch, &P);
+    if (rc) return rc;
+    SED_REQUIRE(batch >= 1, SEDB200_EINVAL, "crnn_backward: batch %d", batch);
+    SED_REQUIRE(params && x && ws && dlogits && grads, SEDB200_EINVAL, "crnn_backward: null buffer");
+    SED_REQUIRE(ws_bytes >= P.ws_bytes, SEDB200_EWORKSPACE, "crnn_backward: workspace %zu < %zu bytes", ws_bytes, P.ws_bytes);
+    rc = require_sm100();
+    if (rc) return rc;
+    cudaStream_t st = as_stream(stream);
+    const long B = batch;
+    const int BT = (int)(B * P.T);
+    float* part = wsf(ws, P.part);
+    const int kSplit = 32;
+
+    // zero the alignment padding of the gradient buffer once (tensors themselves are fully overwritten)
+    SED_CUDA_OK(cudaMemsetAsync(grads, 0, (size_t)P.n_params * 4, st));
+
+    // ---- dense head
+    const float* dout = dlogits;
+    for (int j = P.n_dense - 1; j >= 0; --j) {
+        const float* in = j == 0 ? wsf(ws, P.gout[P.n_gru - 1]) : wsf(ws, P.hid[j - 1]);
+        const int N = P.dout[j], D = P.din[j];
+        // dW[n][k] = sum_m dout[m][n] * in[m][k]
+        const int sp = gemm_simt_splits(BT, kSplit);
+        rc = gemm_simt(N, D, BT, kSplit, ColMajor{dout, N}, ColMajor{in, D}, EpiPartial{part, (long)N * D, D}, st);
+        if (rc) return rc;
+        rc = reduce_partials(part, grads + P.dn_w[j], (long)N * D, sp, st);
+        if (rc) return rc;
+        rc = colsum(dout, BT, N, grads + P.dn_b[j], part, st);
+        if (rc) return rc;
+        // d(in)[m][k] = sum_n dout[m][n] * W[n][k]   (through the previous layer's ReLU if any)
+        float* din = j == 0 ? wsf(ws, P.dseq[0]) : wsf(ws, P.dhid[(j - 1) & 1]);
+        if (j > 0 && d->dense_relu)
+            rc = gemm_simt(BT, D, N, 1, RowMajor{dout, N}, ColMajor{params + P.dn_w[j], D},
+                           EpiReluMask{din, D, wsf(ws, P.hid[j - 1])}, st);
+        else
+            rc = gemm_simt(BT, D, N, 1, RowMajor{dout, N}, ColMajor{params + P.dn_w[j], D},
+                           EpiStore{din, D, nullptr, 0}, st);
+        if (rc) return rc;
+        dout = din;
+    }
+
+    // ---- BiGRU stack (dout = grad wrt the layer's output, in dseq[cur])
+    int cur = 0;
+    for (int l = P.n_gru - 1; l >= 0; --l) {
+        const int h = P.gh[l], in = P.gin[l];
+        const float* xin = l == 0 ? wsf(ws, P.act[P.n_conv - 1]) : wsf(ws, P.gout[l - 1]);
+        float* dgi = wsf(ws, P.dgi);
+        float* dgh = wsf(ws, P.dgh);
+        rc = gru_scan_backward(wsf(ws, P.dseq[cur]), wsf(ws, P.gout[l]), wsf(ws, P.gates[l]), params + P.whh[l],
+                               dgi, dgh, batch, P.T, h, st);
+        if (rc) return rc;
+        // biases
+        rc = colsum(dgi, BT, 6 * h, grads + P.bih[l], part, st);
+        if (rc) return rc;
+        rc = colsum(dgh, BT, 6 * h, grads + P.bhh[l], part, st);
+        if (rc) return rc;
+        // dW_ih[n6][k] = sum_m dgi[m][n6] * xin[m][k]
+        int sp = gemm_simt_splits(BT, kSplit);
+        rc = gemm_simt(6 * h, in, BT, kSplit, ColMajor{dgi, 6L * h}, ColMajor{xin, in},
+                       EpiPartial{part, 6L * h * in, in}, st);
+        if (rc) return rc;
+        rc = reduce_partials(part, grads + P.wih[l], 6L * h * in, sp, st);
+        if (rc) return rc;
+        // dW_hh[dir][r][j] = sum_(b,t) dgh[b,t,dir,r] * h_prev[b,t,dir,j]
+        for (int dir = 0; dir < 2; ++dir) {
+            rc = gemm_simt(3 * h, h, BT, kSplit, ColMajor{dgh + dir * 3 * h, 6L * h},
+                           HPrevB{wsf(ws, P.gout[l]), P.T, h, dir}, EpiPartial{part, 3L * h * h, h}, st);
+            if (rc) return rc;
+            rc = reduce_partials(part, grads + P.whh[l] + (long)dir * 3 * h * h, 3L * h * h, sp, st);
+            if (rc) return rc;
+        }
+        // d(xin)[m][k] = sum_n6 dgi[m][n6] * W_ih[n6][k]
+        float* dxin = wsf(ws, P.dseq[cur ^ 1]);
+        rc = gemm_simt(BT, in, 6 * h, 1, RowMajor{dgi, 6L * h}, ColMajor{params + P.wih[l], in},
+                       EpiStore{dxin, in, nullptr, 0}, st);
+        if (rc) return rc;
+        cur ^= 1;
+    }
+
+    // ---- conv blocks (dA = grad wrt block output; for the last block it is dseq[cur] in [B][T][flat])
+    const float* dA = wsf(ws, P.dseq[cur]);
+    for (int i = P.n_conv - 1; i >= 0; --i) {
+        const PoolGeom g = pool_geom(P, d, i, 1, seed);
+        const float* y = wsf(ws, P.y[i]);
+        const float* stat = wsf(ws, P.stat[i]);
+        const long n_pix_out = B * P.H * P.wout[i];
+        const long n_elem = B * P.H * P.win[i];                 // BN population per channel
+        const int rows = 256 / (P.C / 4);
+        const int nblk = (int)std::min<long>((n_pix_out + rows - 1) / rows, 592);
+        bn_pool_bwd_sums_kernel<<<nblk, 256, 0, st>>>(y, stat, dA, n_pix_out, g, part);
+        SED_CUDA_OK(cudaGetLastError());
+        float* bnsum = wsf(ws, P.bnsum);
+        bn_bwd_finalize_kernel<<<(P.C + 127) / 128, 128, 0, st>>>(part, nblk, P.C, n_elem, grads + P.bn_w[i],
+                                                                 grads + P.bn_b[i], bnsum);
+        SED_CUDA_OK(cudaGetLastError());
+        float* dy = wsf(ws, P.dy);
+        const long n_vec = n_pix_out * (P.C / 4);
+        bn_pool_bwd_dy_kernel<<<ew_blocks(n_vec), 256, 0, st>>>(y, stat, dA, bnsum, n_vec, g, dy);
+        SED_CUDA_OK(cudaGetLastError());
+
+        const float* in = i == 0 ? x : wsf(ws, P.act[i - 1]);
+        const InStrides s = in_strides(P, d, i);
+        const int M = (int)n_elem, J = P.cin[i] * 9;
+        // conv bias grad = column sums of dy
+        rc = colsum(dy, M, P.C, grads + P.conv_b[i], part, st);
+        if (rc) return rc;
+        // wgrad
+        const int want = std::max(1, std::min(64, M / 2048));
+        const int sp = gemm_simt_splits(M, want);
+        rc = gemm_simt(P.C, J, M, want, ColMajor{dy, P.C}, ConvWgradB{in, P.H, P.win[i], s.sB, s.sH, s.sW, s.sC},
+                       EpiPartial{part, (long)P.C * J, J}, st);
+        if (rc) return rc;
+        rc = reduce_partials(part, grads + P.conv_w[i], (long)P.C * J, sp, st);
+        if (rc) return rc;
+        // dgrad
+        if (i > 0) {
+            float* dprev = wsf(ws, P.dact[i & 1]);
+            rc = gemm_simt(M, P.cin[i], 9 * P.C, 1, ConvDgradA{dy, P.H, P.win[i], P.C},
+                           ConvDgradB{params + P.conv_w[i], P.cin[i], P.C}, EpiStore{dprev, P.cin[i], nullptr, 0}, st);
+            if (rc) return rc;
+            dA = dprev;
+        } else if (dx) {
+            rc = gemm_simt(M, P.cin[0], 9 * P.C, 1, ConvDgradA{dy, P.H, P.win[0], P.C},
+                           ConvDgradB{params + P.conv_w[0], P.cin[0], P.C},
+                           EpiStrided{dx, P.H, P.win[0], s.sB, s.sH, s.sW, s.sC}, st);
+            if (rc) return rc;
+        }
+    }
+    return SEDB200_OK;
+}
+
+}  // extern "C"

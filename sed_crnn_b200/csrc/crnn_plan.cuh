@@ -1,0 +1,34 @@
+// crnn_plan.cuh -- geometry, flat-parameter layout and workspace carve-up of one CRNN configuration.
+#pragma once
+#include "common.cuh"
+
+namespace sedb200 {
+
+struct Plan {
+    int B = 0;
+    // conv stack
+    int n_conv = 0, C = 0, H = 0;
+    int cin[SEDB200_MAX_CONV], win[SEDB200_MAX_CONV], wout[SEDB200_MAX_CONV], pool[SEDB200_MAX_CONV];
+    // sequence part
+    int T = 0, flat = 0;
+    int n_gru = 0, gin[SEDB200_MAX_GRU], gh[SEDB200_MAX_GRU];
+    int n_dense = 0, din[SEDB200_MAX_DENSE], dout[SEDB200_MAX_DENSE];
+    // flat parameter offsets (floats)
+    long conv_w[SEDB200_MAX_CONV], conv_b[SEDB200_MAX_CONV], bn_w[SEDB200_MAX_CONV], bn_b[SEDB200_MAX_CONV];
+    long wih[SEDB200_MAX_GRU], whh[SEDB200_MAX_GRU], bih[SEDB200_MAX_GRU], bhh[SEDB200_MAX_GRU];
+    long dn_w[SEDB200_MAX_DENSE], dn_b[SEDB200_MAX_DENSE];
+    long n_params = 0;
+    int n_tensors = 0;
+    // workspace offsets (bytes); valid when B > 0
+    size_t y[SEDB200_MAX_CONV], stat[SEDB200_MAX_CONV], act[SEDB200_MAX_CONV];   // act[i] = output of block i
+    size_t gi[SEDB200_MAX_GRU], gout[SEDB200_MAX_GRU], gates[SEDB200_MAX_GRU];
+    size_t hid[SEDB200_MAX_DENSE];
+    size_t dy, dact[2], dseq[2], dgi, dgh, dhid[2], part, bnsum;
+    size_t part_floats = 0;
+    size_t ws_bytes = 0;
+};
+
+// Fills `p` from `d` (and the workspace part when batch > 0).  Returns SEDB200_OK or an error code.
+int make_plan(const sedb200_crnn_desc* d, int batch, Plan* p);
+
+}  // namespace sedb200

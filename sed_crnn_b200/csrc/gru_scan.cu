@@ -1,0 +1,184 @@
+// gru_scan.cu -- persistent recurrent scans of the bidirectional GRU.
+//
+// Reference: nn.GRU(bidirectional=True, batch_first=True), crnn_lightning.py:61-62,71 / sed.py:101,111
+//   r = sigmoid(gi_r + gh_r)   z = sigmoid(gi_z + gh_z)   n = tanh(gi_n + r * gh_n)
+//   h' = (1 - z) * n + z * h ,  gh = W_hh h + b_hh ,  h_0 = 0
+//
+// One CTA owns (direction, tile of kBT batch rows) for all T steps: W_hh stays resident in shared
+// memory (transposed so that the 3H row-dot-products read it conflict-free), the hidden state lives
+// in shared memory, and gi for step t+1 is prefetched into registers while step t computes.
+#include "gru_scan.cuh"
+
+#include <algorithm>
+
+namespace sedb200 {
+namespace {
+
+constexpr int kBT = 4;      // batch rows per CTA
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void gru_scan_fwd_kernel(const float* __restrict__ gi, const float* __restrict__ whh,
+                                    const float* __restrict__ bhh, float* __restrict__ out,
+                                    float* __restrict__ gates, int B, int T, int H) {
+    extern __shared__ __align__(16) float sm[];
+    const int H3 = 3 * H;
+    float* Wt = sm;                       // [H][3H]   Wt[k*3H + r] = W[r][k]
+    float* h_s = Wt + (size_t)H * H3;     // [kBT][H]
+    float* gh_s = h_s + kBT * H;          // [kBT][3H]
+    const int dir = blockIdx.y, b0 = blockIdx.x * kBT, tid = threadIdx.x;
+    const float* W = whh + (size_t)dir * H3 * H;
+    for (int i = tid; i < H3 * H; i += blockDim.x) {
+        const int r = i / H, k = i - r * H;
+        Wt[k * H3 + r] = __ldg(W + i);
+    }
+    for (int i = tid; i < kBT * H; i += blockDim.x) h_s[i] = 0.0f;
+    const float bias = tid < H3 ? __ldg(bhh + dir * H3 + tid) : 0.0f;
+    // gate-phase role of this thread
+    const int gi_item = tid / H, gj = tid - gi_item * H;
+    const bool gate_thread = tid < kBT * H && (b0 + gi_item) < B;
+    const long gb = b0 + gi_item;
+    float nr = 0, nz = 0, nn = 0;
+    auto load_gi = [&](int t) {
+        const float* g = gi + ((gb * T + t) * 2 + dir) * H3;
+        nr = __ldg(g + gj); nz = __ldg(g + H + gj); nn = __ldg(g + 2 * H + gj);
+    };
+    if (gate_thread) load_gi(dir ? T - 1 : 0);
+    __syncthreads();
+
+    for (int step = 0; step < T; ++step) {
+        const int t = dir ? T - 1 - step : step;
+        const float cr = nr, cz = nz, cn = nn;
+        if (gate_thread && step + 1 < T) load_gi(dir ? t - 1 : t + 1);
+        // phase 1: gh[item][r] = b_hh[r] + sum_k W[r][k] h[item][k]
+        if (tid < H3) {
+            float acc[kBT];
+#pragma unroll
+            for (int i = 0; i < kBT; ++i) acc[i] = bias;
+            for (int k = 0; k < H; k += 4) {
+                const float w0 = Wt[(k + 0) * H3 + tid], w1 = Wt[(k + 1) * H3 + tid];
+                const float w2 = Wt[(k + 2) * H3 + tid], w3 = Wt[(k + 3) * H3 + tid];
+#pragma unroll
+                for (int i = 0; i < kBT; ++i) {
+                    const float4 hv = *reinterpret_cast<const float4*>(h_s + i * H + k);
+                    acc[i] = fmaf(w0, hv.x, acc[i]);
+                    acc[i] = fmaf(w1, hv.y, acc[i]);
+                    acc[i] = fmaf(w2, hv.z, acc[i]);
+                    acc[i] = fmaf(w3, hv.w, acc[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kBT; ++i) gh_s[i * H3 + tid] = acc[i];
+        }
+        __syncthreads();
+        // phase 2: gates and the new hidden state
+        if (gate_thread) {
+            const float* gh = gh_s + gi_item * H3;
+            const float r = sigmoidf_(cr + gh[gj]);
+            const float z = sigmoidf_(cz + gh[H + gj]);
+            const float q = gh[2 * H + gj];
+            const float n = tanhf(fmaf(r, q, cn));
+            const float hp = h_s[gi_item * H + gj];
+            const float hn = fmaf(z, hp - n, n);                 // (1-z)*n + z*h
+            h_s[gi_item * H + gj] = hn;
+            out[(gb * T + t) * 2 * H + dir * H + gj] = hn;
+            float* gs = gates + ((gb * T + t) * 2 + dir) * 4 * H;
+            gs[gj] = r; gs[H + gj] = z; gs[2 * H + gj] = n; gs[3 * H + gj] = q;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void gru_scan_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                    const float* __restrict__ gates, const float* __restrict__ whh,
+                                    float* __restrict__ dgi, float* __restrict__ dgh, int B, int T, int H) {
+    extern __shared__ __align__(16) float sm[];
+    const int H3 = 3 * H;
+    float* W_s = sm;                      // [3H][H]
+    float* dg_s = W_s + (size_t)H3 * H;   // [kBT][3H]
+    const int dir = blockIdx.y, b0 = blockIdx.x * kBT, tid = threadIdx.x;
+    const float* W = whh + (size_t)dir * H3 * H;
+    for (int i = tid; i < H3 * H; i += blockDim.x) W_s[i] = __ldg(W + i);
+    const int item = tid / H, j = tid - item * H;
+    const bool active = tid < kBT * H && (b0 + item) < B;
+    const long b = b0 + item;
+    float dh = 0.0f;
+    float n_do = 0, n_r = 0, n_z = 0, n_n = 0, n_q = 0, n_hp = 0;
+    auto load_step = [&](int t) {
+        n_do = __ldg(dout + (b * T + t) * 2 * H + dir * H + j);
+        const float* gs = gates + ((b * T + t) * 2 + dir) * 4 * H;
+        n_r = __ldg(gs + j); n_z = __ldg(gs + H + j); n_n = __ldg(gs + 2 * H + j); n_q = __ldg(gs + 3 * H + j);
+        const int tp = dir ? t + 1 : t - 1;
+        n_hp = (tp >= 0 && tp < T) ? __ldg(out + (b * T + tp) * 2 * H + dir * H + j) : 0.0f;
+    };
+    if (active) load_step(dir ? 0 : T - 1);
+    __syncthreads();
+
+    for (int step = 0; step < T; ++step) {
+        const int t = dir ? step : T - 1 - step;             // reverse of the forward order
+        const float c_do = n_do, r = n_r, z = n_z, n = n_n, q = n_q, hp = n_hp;
+        if (active && step + 1 < T) load_step(dir ? t + 1 : t - 1);
+        float direct = 0.0f;
+        if (active) {
+            const float dht = c_do + dh;
+            const float dn = dht * (1.0f - z);
+            const float dz = dht * (hp - n);
+            direct = dht * z;
+            const float dan = dn * (1.0f - n * n);
+            const float dar = dan * q * r * (1.0f - r);
+            const float daz = dz * z * (1.0f - z);
+            const float dq = dan * r;
+            const long o = ((b * T + t) * 2 + dir) * H3;
+            dgi[o + j] = dar; dgi[o + H + j] = daz; dgi[o + 2 * H + j] = dan;
+            dgh[o + j] = dar; dgh[o + H + j] = daz; dgh[o + 2 * H + j] = dq;
+            float* ds = dg_s + item * H3;
+            ds[j] = dar; ds[H + j] = daz; ds[2 * H + j] = dq;
+        }
+        __syncthreads();
+        if (active) {
+            const float* ds = dg_s + item * H3;
+            float acc = direct;
+            for (int rr = 0; rr < H3; rr += 4) {
+                const float4 dv = *reinterpret_cast<const float4*>(ds + rr);
+                acc = fmaf(W_s[(rr + 0) * H + j], dv.x, acc);
+                acc = fmaf(W_s[(rr + 1) * H + j], dv.y, acc);
+                acc = fmaf(W_s[(rr + 2) * H + j], dv.z, acc);
+                acc = fmaf(W_s[(rr + 3) * H + j], dv.w, acc);
+            }
+            dh = acc;
+        }
+        __syncthreads();
+    }
+}
+
+inline int round32(int v) { return (v + 31) / 32 * 32; }
+
+}  // namespace
+
+int gru_scan_forward(const float* gi, const float* whh, const float* bhh, float* out, float* gates, int B, int T,
+                     int H, cudaStream_t st) {
+    const int threads = round32(std::max(3 * H, kBT * H));
+    SED_REQUIRE(threads <= 1024 && H % 4 == 0, SEDB200_ESHAPE, "gru_scan: H=%d unsupported", H);
+    const size_t smem = ((size_t)3 * H * H + kBT * H + kBT * 3 * H) * 4;
+    SED_CUDA_OK(cudaFuncSetAttribute(gru_scan_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SED_REQUIRE(smem <= 227 * 1024, SEDB200_ESHAPE, "gru_scan: H=%d needs %zu B shared memory", H, smem);
+    dim3 grid((B + kBT - 1) / kBT, 2);
+    gru_scan_fwd_kernel<<<grid, threads, smem, st>>>(gi, whh, bhh, out, gates, B, T, H);
+    SED_CUDA_OK(cudaGetLastError());
+    return SEDB200_OK;
+}
+
+int gru_scan_backward(const float* dout, const float* out, const float* gates, const float* whh, float* dgi,
+                      float* dgh, int B, int T, int H, cudaStream_t st) {
+    const int threads = round32(kBT * H);
+    SED_REQUIRE(threads <= 1024 && H % 4 == 0, SEDB200_ESHAPE, "gru_scan: H=%d unsupported", H);
+    const size_t smem = ((size_t)3 * H * H + kBT * 3 * H) * 4;
+    SED_CUDA_OK(cudaFuncSetAttribute(gru_scan_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SED_REQUIRE(smem <= 227 * 1024, SEDB200_ESHAPE, "gru_scan: H=%d needs %zu B shared memory", H, smem);
+    dim3 grid((B + kBT - 1) / kBT, 2);
+    gru_scan_bwd_kernel<<<grid, threads, smem, st>>>(dout, out, gates, whh, dgi, dgh, B, T, H);
+    SED_CUDA_OK(cudaGetLastError());
+    return SEDB200_OK;
+}
+
+}  // namespace sedb200

@@ -1,0 +1,228 @@
+// head_optim.cu -- loss (+gradient) on the logits, clip + Adam over flat buffers, and the integer
+// counting behind the segment metrics.
+//
+// Reference arithmetic:
+//   FocalBCELoss            crnn_lightning.py:27-35 (EPS crnn_lightning.py:21)
+//   BCEWithLogitsLoss       sed.py:160
+//   clip_grad_norm_(1.0)    train_lightning.py:50   (coef = max_norm / (norm + 1e-6), clamped to 1)
+//   Adam(lr, wd)            crnn_lightning.py:195-197, sed.py:159 (coupled L2: g += wd * p)
+//   threshold + metrics     crnn_lightning.py:112-126, metrics.py:20-68
+#include "common.cuh"
+#include <algorithm>
+#include <cmath>
+
+namespace sedb200 {
+namespace {
+
+constexpr int kRedBlocks = 592;
+
+__device__ __forceinline__ float block_sum_256(float v, float* sh) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    float t = 0.0f;
+    if (threadIdx.x == 0)
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+    return t;                                    // valid on thread 0
+}
+
+__global__ void __launch_bounds__(256)
+loss_kernel(int kind, float alpha, float gamma, const float* __restrict__ logits, const float* __restrict__ targets,
+            long n, float gscale, float* __restrict__ probs, float* __restrict__ dlogits, float* __restrict__ part) {
+    __shared__ float sh[8];
+    float acc = 0.0f;
+    const float inv_n = 1.0f / (float)n;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const float l = __ldg(logits + i), t = __ldg(targets + i);
+        const float p = 1.0f / (1.0f + expf(-l));
+        float loss, dl;
+        if (kind == SEDB200_LOSS_FOCAL) {
+            const bool pos = (t == 1.0f);
+            const float pt = pos ? p : 1.0f - p;
+            const float om = 1.0f - pt;
+            const float lg = logf(pt + 1e-12f);
+            const float pw = powf(om, gamma);
+            loss = -alpha * pw * lg;
+            // d loss / d pt = alpha * gamma * om^(gamma-1) * lg - alpha * om^gamma / (pt + eps)
+            const float pw1 = (gamma == 2.0f) ? om : powf(om, gamma - 1.0f);
+            const float dpt = alpha * gamma * pw1 * lg - alpha * pw / (pt + 1e-12f);
+            dl = dpt * (pos ? 1.0f : -1.0f) * p * (1.0f - p);
+        } else {
+            loss = fmaxf(l, 0.0f) - l * t + log1pf(expf(-fabsf(l)));
+            dl = p - t;
+        }
+        acc += loss;
+        if (probs) probs[i] = p;
+        if (dlogits) dlogits[i] = dl * inv_n * gscale;
+    }
+    const float tot = block_sum_256(acc, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = tot;
+}
+
+__global__ void loss_final_kernel(const float* __restrict__ part, int nblk, long n, float* __restrict__ loss) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < nblk; ++i) s += (double)part[i];
+        loss[0] = (float)(s / (double)n);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const float* __restrict__ g, long n, float prescale, float* __restrict__ part) {
+    __shared__ float sh[8];
+    float acc = 0.0f;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const float v = __ldg(g + i) * prescale;
+        acc = fmaf(v, v, acc);
+    }
+    const float tot = block_sum_256(acc, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = tot;
+}
+
+__global__ void gnorm_final_kernel(const float* __restrict__ part, int nblk, float* __restrict__ gnorm) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < nblk; ++i) s += (double)part[i];
+        gnorm[0] = (float)sqrt(s);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
+            float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float max_norm,
+            float prescale, const float* __restrict__ gnorm) {
+    float coef = prescale;
+    if (max_norm > 0.0f) {
+        const float c = max_norm / (gnorm[0] + 1e-6f);
+        coef *= fminf(c, 1.0f);
+    }
+    const float step_size = lr / bc1;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const float w = p[i];
+        float grad = g[i] * coef;
+        grad = fmaf(wd, w, grad);
+        const float mi = m[i] + (1.0f - b1) * (grad - m[i]);                 // torch: lerp_(grad, 1-beta1)
+        const float vi = fmaf(b2, v[i], (1.0f - b2) * grad * grad);
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = w - step_size * (mi / denom);
+    }
+}
+
+// ---- threshold + counts.  counts: [0..5] frame TP,Nsys,Nref,S,D,I ; [6..11] block ; [12] block Nref (floor blocks)
+__global__ void __launch_bounds__(256)
+frame_counts_kernel(const float* __restrict__ probs, const float* __restrict__ targets, long n_rows, int n_cls,
+                    float thr, unsigned long long* __restrict__ counts) {
+    unsigned long long tp = 0, nsys = 0, nref = 0, S = 0, D = 0, I = 0;
+    for (long r = (long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (long)gridDim.x * blockDim.x) {
+        int fp = 0, fn = 0;
+        for (int c = 0; c < n_cls; ++c) {
+            const bool o = __ldg(probs + r * n_cls + c) > thr;
+            const bool t = __ldg(targets + r * n_cls + c) == 1.0f;
+            tp += (o && t); nsys += o; nref += t;
+            fp += (o && !t); fn += (!o && t);
+        }
+        S += min(fp, fn); D += max(0, fn - fp); I += max(0, fp - fn);
+    }
+    atomicAdd(counts + 0, tp); atomicAdd(counts + 1, nsys); atomicAdd(counts + 2, nref);
+    atomicAdd(counts + 3, S); atomicAdd(counts + 4, D); atomicAdd(counts + 5, I);
+}
+
+__global__ void __launch_bounds__(256)
+block_counts_kernel(const float* __restrict__ probs, const float* __restrict__ targets, long n_rows, int n_cls,
+                    int block, float thr, unsigned long long* __restrict__ counts) {
+    const long n_ceil = (n_rows + block - 1) / block, n_floor = n_rows / block;
+    unsigned long long tp = 0, nsys = 0, nref = 0, S = 0, D = 0, I = 0, nref_er = 0;
+    for (long bi = (long)blockIdx.x * blockDim.x + threadIdx.x; bi < n_ceil; bi += (long)gridDim.x * blockDim.x) {
+        const long r0 = bi * block, r1 = min(n_rows, r0 + block);
+        int fp = 0, fn = 0, nr = 0;
+        for (int c = 0; c < n_cls; ++c) {
+            bool o = false, t = false;
+            for (long r = r0; r < r1; ++r) {
+                o |= __ldg(probs + r * n_cls + c) > thr;
+                t |= __ldg(targets + r * n_cls + c) == 1.0f;
+            }
+            tp += (o && t); nsys += o; nref += t; nr += t;
+            fp += (o && !t); fn += (!o && t);
+        }
+        if (bi < n_floor) { S += min(fp, fn); D += max(0, fn - fp); I += max(0, fp - fn); nref_er += nr; }
+    }
+    atomicAdd(counts + 6, tp); atomicAdd(counts + 7, nsys); atomicAdd(counts + 8, nref);
+    atomicAdd(counts + 9, S); atomicAdd(counts + 10, D); atomicAdd(counts + 11, I);
+    atomicAdd(counts + 12, nref_er);
+}
+
+inline int red_blocks(long n) { return (int)std::max<long>(1, std::min<long>((n + 255) / 256, kRedBlocks)); }
+
+}  // namespace
+}  // namespace sedb200
+
+using namespace sedb200;
+
+extern "C" {
+
+size_t sedb200_loss_scratch_bytes(long n) { (void)n; return (size_t)kRedBlocks * 4; }
+
+int sedb200_loss_fwd_bwd(int kind, float alpha, float gamma, const float* logits, const float* targets, long n,
+                         float grad_scale, float* loss, float* probs, float* dlogits, void* scratch,
+                         size_t scratch_bytes, void* stream) {
+    SED_REQUIRE(kind == SEDB200_LOSS_BCE || kind == SEDB200_LOSS_FOCAL, SEDB200_EINVAL, "loss: kind %d", kind);
+    SED_REQUIRE(n >= 1 && logits && targets && loss && scratch, SEDB200_EINVAL, "loss: bad argument");
+    SED_REQUIRE(scratch_bytes >= sedb200_loss_scratch_bytes(n), SEDB200_EWORKSPACE, "loss: scratch too small");
+    int rc = require_sm100();
+    if (rc) return rc;
+    cudaStream_t st = as_stream(stream);
+    const int nb = red_blocks(n);
+    float* part = reinterpret_cast<float*>(scratch);
+    loss_kernel<<<nb, 256, 0, st>>>(kind, alpha, gamma, logits, targets, n, grad_scale, probs, dlogits, part);
+    SED_CUDA_OK(cudaGetLastError());
+    loss_final_kernel<<<1, 32, 0, st>>>(part, nb, n, loss);
+    SED_CUDA_OK(cudaGetLastError());
+    return SEDB200_OK;
+}
+
+size_t sedb200_clip_adam_scratch_bytes(long n) { (void)n; return (size_t)kRedBlocks * 4; }
+
+int sedb200_clip_adam(float* params, const float* grads, float* m, float* v, long n, float lr, float b1, float b2,
+                      float eps, float wd, long step, float max_norm, float prescale, float* gnorm, void* scratch,
+                      size_t scratch_bytes, void* stream) {
+    SED_REQUIRE(n >= 1 && params && grads && m && v && gnorm && scratch, SEDB200_EINVAL, "clip_adam: bad argument");
+    SED_REQUIRE(step >= 1, SEDB200_EINVAL, "clip_adam: step %ld (1-based)", step);
+    SED_REQUIRE(scratch_bytes >= sedb200_clip_adam_scratch_bytes(n), SEDB200_EWORKSPACE, "clip_adam: scratch too small");
+    int rc = require_sm100();
+    if (rc) return rc;
+    cudaStream_t st = as_stream(stream);
+    const int nb = red_blocks(n);
+    float* part = reinterpret_cast<float*>(scratch);
+    sumsq_kernel<<<nb, 256, 0, st>>>(grads, n, prescale, part);
+    SED_CUDA_OK(cudaGetLastError());
+    gnorm_final_kernel<<<1, 32, 0, st>>>(part, nb, gnorm);
+    SED_CUDA_OK(cudaGetLastError());
+    const double bc1 = 1.0 - std::pow((double)b1, (double)step);
+    const double bc2 = 1.0 - std::pow((double)b2, (double)step);
+    adam_kernel<<<nb, 256, 0, st>>>(params, grads, m, v, n, lr, b1, b2, eps, wd, (float)bc1, (float)std::sqrt(bc2),
+                                    max_norm, prescale, gnorm);
+    SED_CUDA_OK(cudaGetLastError());
+    return SEDB200_OK;
+}
+
+int sedb200_threshold_counts(const float* probs, const float* targets, long n_rows, int n_cls, int block,
+                             float threshold, unsigned long long* counts, void* stream) {
+    SED_REQUIRE(n_rows >= 0 && n_cls >= 1 && block >= 1 && counts, SEDB200_EINVAL, "threshold_counts: bad argument");
+    int rc = require_sm100();
+    if (rc) return rc;
+    cudaStream_t st = as_stream(stream);
+    SED_CUDA_OK(cudaMemsetAsync(counts, 0, 13 * sizeof(unsigned long long), st));
+    if (n_rows == 0) return SEDB200_OK;
+    SED_REQUIRE(probs && targets, SEDB200_EINVAL, "threshold_counts: null buffer");
+    frame_counts_kernel<<<red_blocks(n_rows), 256, 0, st>>>(probs, targets, n_rows, n_cls, threshold, counts);
+    SED_CUDA_OK(cudaGetLastError());
+    const long nblk = (n_rows + block - 1) / block;
+    block_counts_kernel<<<red_blocks(nblk), 256, 0, st>>>(probs, targets, n_rows, n_cls, block, threshold, counts);
+    SED_CUDA_OK(cudaGetLastError());
+    return SEDB200_OK;
+}
+
+}  // extern "C"

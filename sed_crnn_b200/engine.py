@@ -1,0 +1,220 @@
+"""CRNNEngine -- the B200 training / inference engine behind the drop-in modules.
+
+Owns the flat parameter / gradient / Adam-state buffers and the activation workspace (all PyTorch
+tensors: PyTorch is the allocator and the stream provider, nothing more) and drives libsedb200.so:
+
+    forward -> loss(+dlogits) -> backward -> [NCCL all-reduce of the flat gradient] -> clip + Adam
+
+which is the arithmetic of crnn_lightning.py:157-163 + train_lightning.py:50 + crnn_lightning.py:195-197
+(Lightning variant) or sed.py:134-137,159 (plain-torch variant).  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .config import CRNNConfig
+
+LOSS_KINDS = {"bce": 0, "focal": 1}
+
+
+class CRNNEngine:
+    def __init__(self, cfg: CRNNConfig, device="cuda", *, loss="focal", alpha=0.25, gamma=2.0,
+                 lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, clip=1.0, seed=0,
+                 process_group=None):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("CRNNEngine runs on a CUDA device only (no CPU fallback)")
+        self.L = _lib.lib()
+        self.desc = cfg.desc()
+        _lib.check(self.L.sedb200_crnn_validate(C.byref(self.desc)))
+        self.loss_kind, self.alpha, self.gamma = LOSS_KINDS[loss], float(alpha), float(gamma)
+        self.lr, self.betas, self.eps, self.weight_decay = float(lr), tuple(betas), float(eps), float(weight_decay)
+        self.clip = float(clip) if clip else 0.0
+        self.seed, self.step_count = int(seed), 0
+        self.pg = process_group
+        self.specs = cfg.tensor_specs()
+        n = cfg.n_param_floats()
+        kw = dict(dtype=torch.float32, device=self.device)
+        self.params = torch.zeros(n, **kw)
+        self.grads = torch.zeros(n, **kw)
+        self.exp_avg = torch.zeros(n, **kw)
+        self.exp_avg_sq = torch.zeros(n, **kw)
+        nb = int(self.L.sedb200_crnn_bn_state_floats(C.byref(self.desc)))
+        self.bn_state = torch.zeros(nb, **kw)
+        c = cfg.conv_ch
+        for i in range(len(cfg.pool)):
+            self.bn_state[2 * i * c + c: 2 * (i + 1) * c] = 1.0          # running_var = 1
+        self.num_batches_tracked = 0
+        self._scratch = torch.zeros(4096, **kw)
+        self._scalars = torch.zeros(4, **kw)                              # loss, gnorm
+        self._counts = torch.zeros(13, dtype=torch.int64, device=self.device)
+        self._ws = None
+        self._ws_batch = 0
+        self._bufs = {}
+
+    # ------------------------------------------------------------------ parameters
+    def views(self, flat: torch.Tensor | None = None) -> dict[str, torch.Tensor]:
+        flat = self.params if flat is None else flat
+        out = {}
+        for name, shape, off in self.specs:
+            n = 1
+            for s in shape:
+                n *= s
+            out[name] = flat[off:off + n].view(shape)
+        return out
+
+    def bn_views(self) -> dict[str, torch.Tensor]:
+        c, out = self.cfg.conv_ch, {}
+        for i in range(len(self.cfg.pool)):
+            out[f"bn{i}.running_mean"] = self.bn_state[2 * i * c: 2 * i * c + c]
+            out[f"bn{i}.running_var"] = self.bn_state[2 * i * c + c: 2 * (i + 1) * c]
+        return out
+
+    @torch.no_grad()
+    def load_named(self, tensors: dict) -> None:
+        """Copy tensors given under canonical names.  GRU tensors may be given per direction as
+        `gru{i}.f.w_ih` / `gru{i}.r.w_ih` (the oracle's naming) or stacked as `gru{i}.w_ih`."""
+        v = self.views()
+        v.update(self.bn_views())
+        for name, t in tensors.items():
+            t = torch.as_tensor(t)
+            parts = name.split(".")
+            if len(parts) == 3 and parts[1] in ("f", "r"):
+                dst = v[f"{parts[0]}.{parts[2]}"][0 if parts[1] == "f" else 1]
+            else:
+                dst = v[name]
+            dst.copy_(t.to(self.device, torch.float32).reshape(dst.shape))
+
+    def reset_optimizer(self) -> None:
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        self.step_count = 0
+
+    # ------------------------------------------------------------------ plumbing
+    def _workspace(self, batch: int):
+        if self._ws is None or self._ws_batch != batch:
+            nbytes = int(self.L.sedb200_crnn_workspace_bytes(C.byref(self.desc), batch))
+            if nbytes == 0:
+                _lib.check(self.L.sedb200_crnn_validate(C.byref(self.desc)))
+                raise _lib.Sedb200Error(_lib.ESHAPE, f"batch {batch} not supported")
+            self._ws = None
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._ws_batch = batch
+        return self._ws
+
+    def _buf(self, key, shape):
+        b = self._bufs.get(key)
+        if b is None or tuple(b.shape) != tuple(shape):
+            b = torch.empty(shape, dtype=torch.float32, device=self.device)
+            self._bufs[key] = b
+        return b
+
+    def _check_x(self, x):
+        if not (x.is_cuda and x.dtype == torch.float32):
+            raise TypeError("x must be a CUDA float32 tensor")
+        want = self.cfg.input_shape(x.shape[0])
+        if tuple(x.shape) != want:
+            raise ValueError(f"x has shape {tuple(x.shape)}, config expects {want}")
+        return x.contiguous()
+
+    # ------------------------------------------------------------------ compute
+    def forward(self, x: torch.Tensor, training: bool = False, logits: torch.Tensor | None = None) -> torch.Tensor:
+        x = self._check_x(x)
+        B = x.shape[0]
+        ws = self._workspace(B)
+        if logits is None:
+            logits = self._buf(("logits", B), self.cfg.target_shape(B))
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.sedb200_crnn_forward(
+                C.byref(self.desc), self.params.data_ptr(), self.bn_state.data_ptr(), x.data_ptr(), B,
+                int(training), self.seed + self.step_count, ws.data_ptr(), ws.numel(), logits.data_ptr(),
+                _lib.current_stream_ptr()))
+        if training:
+            self.num_batches_tracked += 1
+        return logits
+
+    def loss_and_grad(self, logits, targets, grad_scale: float = 1.0, want_grad: bool = True):
+        """-> (loss [device scalar view], probs, dlogits)"""
+        n = logits.numel()
+        targets = targets.contiguous()
+        if targets.shape != logits.shape or targets.dtype != torch.float32 or not targets.is_cuda:
+            raise ValueError("targets must be CUDA float32 with the logits' shape")
+        probs = self._buf(("probs", tuple(logits.shape)), logits.shape)
+        dlog = self._buf(("dlogits", tuple(logits.shape)), logits.shape) if want_grad else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.sedb200_loss_fwd_bwd(
+                self.loss_kind, self.alpha, self.gamma, logits.data_ptr(), targets.data_ptr(), n, float(grad_scale),
+                self._scalars.data_ptr(), probs.data_ptr(), dlog.data_ptr() if want_grad else None,
+                self._scratch.data_ptr(), self._scratch.numel() * 4, _lib.current_stream_ptr()))
+        return self._scalars[0], probs, dlog
+
+    def backward(self, x, dlogits, dx: torch.Tensor | None = None) -> torch.Tensor:
+        x = self._check_x(x)
+        B = x.shape[0]
+        ws = self._workspace(B)
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.sedb200_crnn_backward(
+                C.byref(self.desc), self.params.data_ptr(), x.data_ptr(), B, self.seed + self.step_count,
+                ws.data_ptr(), ws.numel(), dlogits.data_ptr(), self.grads.data_ptr(),
+                dx.data_ptr() if dx is not None else None, _lib.current_stream_ptr()))
+        return self.grads
+
+    def optimizer_step(self, world_size: int = 1) -> torch.Tensor:
+        """clip (global norm) + Adam on the flat buffers; returns the pre-clip gradient norm (device scalar)."""
+        self.step_count += 1
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.sedb200_clip_adam(
+                self.params.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                self.params.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                self.step_count, self.clip, 1.0 / world_size, self._scalars[1:].data_ptr(),
+                self._scratch.data_ptr(), self._scratch.numel() * 4, _lib.current_stream_ptr()))
+        return self._scalars[1]
+
+    def train_step(self, x: torch.Tensor, y: torch.Tensor):
+        """One optimisation step on device-resident (x, y).  Returns (loss, probs) as device tensors
+        (views of engine-owned buffers, valid until the next call)."""
+        logits = self.forward(x, training=True)
+        loss, probs, dlog = self.loss_and_grad(logits, y)
+        self.backward(x, dlog)
+        world = 1
+        if self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            import torch.distributed as dist
+            world = dist.get_world_size(self.pg)
+            if world > 1:
+                dist.all_reduce(self.grads, group=self.pg)           # sum; 1/world folded into clip_adam
+        self.optimizer_step(world)
+        return loss, probs
+
+    @torch.no_grad()
+    def predict_proba(self, x: torch.Tensor, training_bn: bool = False) -> torch.Tensor:
+        logits = self.forward(x, training=False) if not training_bn else self._forward_train_noupdate(x)
+        return torch.sigmoid_(logits.clone())
+
+    def _forward_train_noupdate(self, x):
+        """train-mode BatchNorm forward that leaves running stats / counters untouched (parity checks)."""
+        keep, nbt = self.bn_state.clone(), self.num_batches_tracked
+        drop = self.desc.dropout
+        self.desc.dropout = 0.0
+        try:
+            out = self.forward(x, training=True)
+        finally:
+            self.desc.dropout = drop
+            self.bn_state.copy_(keep)
+            self.num_batches_tracked = nbt
+        return out
+
+    # ------------------------------------------------------------------ metrics on device
+    def threshold_counts(self, probs: torch.Tensor, targets: torch.Tensor, block: int, threshold: float = 0.5):
+        """13 integer counts behind metrics.py (see sedb200.h); probs/targets [..., n_cls] CUDA float32."""
+        n_cls = probs.shape[-1]
+        p2 = probs.reshape(-1, n_cls).contiguous()
+        t2 = targets.reshape(-1, n_cls).contiguous().to(torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.sedb200_threshold_counts(p2.data_ptr(), t2.data_ptr(), p2.shape[0], n_cls, int(block),
+                                                       float(threshold), self._counts.data_ptr(),
+                                                       _lib.current_stream_ptr()))
+        return self._counts

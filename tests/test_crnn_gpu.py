@@ -1,0 +1,202 @@
+"""GPU parity of the CRNN engine (through the C ABI) against the CPU oracle and the golden fixtures
+written from the reference's own modules.
+
+Gates (BASELINE.json north_star): per-frame probabilities within 1e-3 after one training step;
+thresholded frame decisions and segment ER/F1 bit-exact."""
+import os
+from dataclasses import replace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import crnn_ref as R
+from oracle import metrics_ref as M
+
+pytestmark = pytest.mark.gpu
+PROB_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def pkg(built_lib):
+    assert torch.cuda.is_available()
+    from sed_crnn_b200 import config, engine
+    return config, engine
+
+
+def make_pair(pkg, preset, overrides, loss, wd, clip, seed=0):
+    config, engine = pkg
+    rcfg = dict(R.PRESETS[preset]); rcfg.update(overrides)
+    torch.manual_seed(seed)
+    ref = R.RefCRNN(**rcfg)
+    cfg = replace(config.PRESETS[preset], dropout=0.0, **overrides)
+    eng = engine.CRNNEngine(cfg, loss=loss, weight_decay=wd, clip=clip)
+    eng.load_named({k: v.detach() for k, v in ref.canonical_named_params()})
+    return rcfg, ref, cfg, eng
+
+
+CASES = [
+    ("fork", {}, 128, "focal", 1e-4, 1.0),
+    ("fork", {}, 5, "bce", 0.0, None),
+    ("sedpy", {"conv_ch": 32}, 16, "bce", 0.0, None),
+    ("c1", {"seq_len": 32}, 6, "bce", 1e-4, 1.0),
+    ("c2", {"seq_len": 24, "conv_ch": 64}, 3, "focal", 1e-4, 1.0),
+    ("c5", {"seq_len": 16, "conv_ch": 32, "gru_units": (64, 16, 8)}, 2, "bce", 1e-4, 1.0),
+]
+
+
+@pytest.mark.parametrize("preset,ov,batch,loss,wd,clip", CASES)
+def test_one_training_step_matches_oracle(pkg, preset, ov, batch, loss, wd, clip):
+    torch.set_num_threads(8)
+    rcfg, ref, cfg, eng = make_pair(pkg, preset, ov, loss, wd, clip)
+    x, y = R.synth_batch(rcfg, batch, seed=3)
+    xd, yd = x.cuda(), y.cuda()
+    # --- reference step
+    opt = R.make_adam(ref, 1e-3, wd)
+    ref.train()
+    logits_ref = ref(x)
+    loss_ref = R.loss_fn(loss)(logits_ref, y)
+    opt.zero_grad(); loss_ref.backward()
+    gref = {k: p.grad.detach().clone() for k, p in ref.canonical_named_params()}
+    gn_ref = torch.nn.utils.clip_grad_norm_(ref.parameters(), clip if clip else 1e30)
+    opt.step()
+    with torch.no_grad():
+        p1_ref = torch.sigmoid(ref(x))
+    # --- engine step, piece by piece
+    logits = eng.forward(xd, training=True)
+    np.testing.assert_allclose(logits.cpu().numpy(), logits_ref.detach().numpy(), rtol=0, atol=2e-5)
+    l, probs, dlog = eng.loss_and_grad(logits, yd)
+    assert abs(l.item() - loss_ref.item()) <= 2e-6 + 1e-5 * abs(loss_ref.item())
+    eng.backward(xd, dlog)
+    gv = eng.views(eng.grads)
+    for name, g in gref.items():
+        parts = name.split(".")
+        got = gv[f"{parts[0]}.{parts[2]}"][0 if parts[1] == "f" else 1] if parts[1] in ("f", "r") else gv[name]
+        scale = max(g.abs().max().item(), 1e-6)
+        if name.startswith("conv") and name.endswith("bias"):
+            assert got.abs().max().item() <= 1e-4 * max(1.0, scale)      # true gradient is 0 (BN follows)
+            continue
+        err = (got.cpu() - g).abs().max().item() / scale
+        assert err <= 2e-3, (name, err)
+    gn = eng.optimizer_step()
+    assert abs(gn.item() - gn_ref.item()) <= 1e-4 * gn_ref.item()
+    p1 = eng.predict_proba(xd, training_bn=True).cpu()
+    perr = (p1 - p1_ref).abs().max().item()
+    assert perr <= PROB_TOL, perr
+    if wd > 0:           # with wd=0 conv-bias updates are sign(noise)*lr: skip weight compare
+        for (name, pref) in ref.canonical_named_params():
+            parts = name.split(".")
+            v = eng.views()
+            got = v[f"{parts[0]}.{parts[2]}"][0 if parts[1] == "f" else 1] if parts[1] in ("f", "r") else v[name]
+            assert (got.cpu() - pref.detach()).abs().max().item() <= 2.1e-3, name
+    # --- decisions + metrics bit-exact (frames inside the tolerance margin must not exist)
+    margin = (p1_ref - 0.5).abs()
+    safe = margin > 2 * perr + 1e-7
+    assert torch.equal((p1 > 0.5)[safe], (p1_ref > 0.5)[safe])
+    if bool(safe.all()):
+        O, T = (p1.numpy() > 0.5), y.numpy()
+        Oref = (p1_ref.numpy() > 0.5)
+        for blk in (5, 43):
+            assert M.f1_overall_1sec(O, T, blk) == M.f1_overall_1sec(Oref, T, blk)
+            assert M.er_overall_1sec(O, T, blk) == M.er_overall_1sec(Oref, T, blk)
+
+
+def test_eval_mode_uses_running_stats(pkg):
+    rcfg, ref, cfg, eng = make_pair(pkg, "fork", {}, "focal", 1e-4, 1.0)
+    x, y = R.synth_batch(rcfg, 16, seed=5)
+    ref.train()
+    for _ in range(2):
+        ref(x)
+        eng.forward(x.cuda(), training=True)
+    ref.eval()
+    with torch.no_grad():
+        want = ref(x)
+    got = eng.forward(x.cuda(), training=False).cpu()
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=0, atol=2e-5)
+    bn = eng.bn_views()
+    np.testing.assert_allclose(bn["bn0.running_mean"].cpu().numpy(), ref.bns[0].running_mean.numpy(), atol=1e-6)
+    np.testing.assert_allclose(bn["bn2.running_var"].cpu().numpy(), ref.bns[2].running_var.numpy(), rtol=1e-5)
+
+
+LIGHTNING_KEYS = {
+    **{f"conv_stack.{4 * i}.{p}": f"conv{i}.{p}" for i in range(3) for p in ("weight", "bias")},
+    **{f"conv_stack.{4 * i + 1}.{p}": f"bn{i}.{p}" for i in range(3) for p in ("weight", "bias")},
+    **{f"gru{i + 1}.{a}_l0{sfx}": f"gru{i}.{tag}.{b}" for i in range(2)
+       for sfx, tag in (("", "f"), ("_reverse", "r"))
+       for a, b in (("weight_ih", "w_ih"), ("weight_hh", "w_hh"), ("bias_ih", "b_ih"), ("bias_hh", "b_hh"))},
+    "d1.weight": "dense0.weight", "d1.bias": "dense0.bias", "d2.weight": "dense1.weight", "d2.bias": "dense1.bias",
+}
+
+
+def test_golden_fixture_from_reference_lightning(pkg, golden_dir):
+    """Weights, batch and results produced by the UNMODIFIED crnn_lightning.TimePooledCRNN +
+    FocalBCELoss + clip(1.0) + Adam(wd 1e-4) (oracle/make_golden.py)."""
+    config, engine = pkg
+    g = np.load(os.path.join(golden_dir, "crnn_fork_lightning.npz"))
+    eng = engine.CRNNEngine(replace(config.FORK, dropout=0.0), loss="focal", weight_decay=1e-4, clip=1.0)
+    eng.load_named({ck: g["w." + rk] for rk, ck in LIGHTNING_KEYS.items()})
+    x, y = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["y"]).cuda()
+    logits = eng.forward(x, training=True)
+    np.testing.assert_allclose(logits.cpu().numpy(), g["logits0"], rtol=0, atol=2e-5)
+    loss, probs, dlog = eng.loss_and_grad(logits, y)
+    assert abs(loss.item() - float(g["loss0"])) < 1e-6
+    eng.backward(x, dlog)
+    gn = eng.optimizer_step()
+    assert abs(gn.item() - float(g["gnorm"])) < 1e-4 * float(g["gnorm"])
+    p1 = eng.predict_proba(x, training_bn=True).cpu().numpy()
+    assert np.abs(p1 - g["probs1"]).max() <= PROB_TOL
+    assert np.array_equal(p1 > 0.5, g["probs1"] > 0.5)
+    v = eng.views()
+    for rk, ck in LIGHTNING_KEYS.items():
+        parts = ck.split(".")
+        got = v[f"{parts[0]}.{parts[2]}"][0 if parts[1] == "f" else 1] if parts[1] in ("f", "r") else v[ck]
+        assert np.abs(got.cpu().numpy() - g["w1." + rk]).max() <= 2.1e-3, rk
+
+
+def test_train_step_api_and_determinism(pkg):
+    config, engine = pkg
+    cfg = replace(config.C1, seq_len=32)
+    outs = []
+    for _ in range(2):
+        torch.manual_seed(0)
+        ref = R.RefCRNN(**{**R.PRESETS["c1"], "seq_len": 32})
+        eng = engine.CRNNEngine(cfg, loss="bce", seed=7)           # dropout 0.5 active
+        eng.load_named({k: v.detach() for k, v in ref.canonical_named_params()})
+        x, y = R.synth_batch({**R.PRESETS["c1"], "seq_len": 32}, 8, seed=1)
+        for _ in range(3):
+            loss, probs = eng.train_step(x.cuda(), y.cuda())
+        outs.append((loss.item(), probs.clone(), eng.params.clone()))
+    assert outs[0][0] == outs[1][0] and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    assert np.isfinite(outs[0][0])
+
+
+def test_loss_known_answers(pkg, golden_dir):
+    config, engine = pkg
+    g = np.load(os.path.join(golden_dir, "loss_kat.npz"))
+    lo = torch.from_numpy(g["logits"]).cuda().view(4, 8, 1)
+    t = torch.from_numpy(g["targets"]).cuda().view(4, 8, 1)
+    for kind, kw, key in (("focal", {}, "focal_mean"), ("focal", dict(alpha=.5, gamma=1.), "focal_a5_g1"), ("bce", {}, "bce_mean")):
+        eng = engine.CRNNEngine(config.FORK, loss=kind, **kw)
+        loss, probs, dlog = eng.loss_and_grad(lo, t)
+        assert abs(loss.item() - float(g[key])) < 2e-7
+        lref = torch.from_numpy(g["logits"]).requires_grad_(True)
+        tt = torch.from_numpy(g["targets"])
+        (R.focal_bce(lref, tt, kw.get("alpha", .25), kw.get("gamma", 2.)) if kind == "focal" else R.bce_logits(lref, tt)).backward()
+        np.testing.assert_allclose(dlog.cpu().numpy().ravel(), lref.grad.numpy(), rtol=1e-4, atol=1e-8)
+        np.testing.assert_allclose(probs.cpu().numpy().ravel(), torch.sigmoid(lref).detach().numpy(), atol=1e-7)
+
+
+def test_threshold_counts_match_metrics(pkg, golden_dir):
+    config, engine = pkg
+    eng = engine.CRNNEngine(config.FORK)
+    g = np.load(os.path.join(golden_dir, "metrics_kat.npz"))
+    for n in g["names"]:
+        O, T, blk, want = g[f"{n}_O"], g[f"{n}_T"], int(g[f"{n}_block"]), g[f"{n}_out"]
+        probs = torch.from_numpy(np.where(O.astype(bool), 0.9, 0.1).astype(np.float32)).cuda()
+        c = eng.threshold_counts(probs, torch.from_numpy(T.astype(np.float32)).cuda(), blk).cpu().numpy()
+        fr = dict(zip(("TP", "Nsys", "Nref", "S", "D", "I"), c[:6].tolist()))
+        assert fr == M.frame_counts(O, T), n
+        from sed_crnn_b200 import metrics as PM
+        with np.errstate(all="ignore"):
+            got = np.array(PM.scores_from_counts(c))
+        assert np.array_equal(got, want, equal_nan=True), (n, got, want)
