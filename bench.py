@@ -1,0 +1,406 @@
+#!/usr/bin/env python3
+"""bench.py -- CRNN train frames/sec (BASELINE.json metric) on N B200s, plus the log-mel leg.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" = one full training step of the hot path on one synthetic batch: forward + loss + backward
++ [NCCL all-reduce of the flat gradient] + global-norm clip + Adam.  Workload at N=1 is BASELINE.json
+configs[1] (binaural SEDnet, seq_len 256, batch 128); at N>1 the per-GPU batch stays 128 (weak
+scaling; N=8 is configs[3]'s global batch 1024).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "CRNN train frames/sec"
+UNIT = "frames/s"
+PER_GPU_BATCH = 128
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=float(p["hbm_gbs"]), tf_burst=float(p["bf16_tflops"]),
+                    tf_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), src="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------------------ FLOP model
+def crnn_flops(cfg, batch):
+    """Algorithmic FLOPs of one training step, SURVEY.md 8(d) convention: 2*M*K*N per contraction,
+    backward = dgrad + wgrad, no dgrad for conv1, elementwise work excluded."""
+    H, W = cfg.H, cfg.W
+    fwd = 0.0
+    per = {}
+    cin, w = cfg.in_ch, W
+    for i, p in enumerate(cfg.pool):
+        f = 2.0 * batch * H * w * 9 * cin * cfg.conv_ch
+        per[f"conv{i}"] = f
+        fwd += f
+        w //= p
+        cin = cfg.conv_ch
+    T, gin = cfg.seq_len_out, cfg.flat
+    for i, h in enumerate(cfg.gru_units):
+        per[f"gru{i}.proj"] = 2.0 * batch * T * gin * 6 * h
+        per[f"gru{i}.rec"] = 2.0 * batch * T * h * 6 * h
+        fwd += per[f"gru{i}.proj"] + per[f"gru{i}.rec"]
+        gin = 2 * h
+    for i, u in enumerate(list(cfg.dense_units) + [cfg.n_classes]):
+        per[f"dense{i}"] = 2.0 * batch * T * gin * u
+        fwd += per[f"dense{i}"]
+        gin = u
+    total = 3.0 * fwd - per["conv0"]
+    return total, per
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # median over the busiest half of the samples (the sampler also sees idle gaps around the region)
+        busy = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path on this box's host cores: the CRNN oracle is the
+    same stock torch.nn modules the reference instantiates (crnn_lightning.py:41-73), the trainer step is
+    forward + loss + backward + clip + Adam (oracle/crnn_ref.py).  /root/reference does not exist on the
+    GPU box, so this is cpu_baseline.kind = "port"."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import crnn_ref as R
+    preset = dict(R.PRESETS[args.config])
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_b = args.ref_batch
+    model = R.RefCRNN(**preset, dropout=0.5, dropout_each_block=True) if args.config != "fork" else R.RefCRNN(**preset, dropout=0.4)
+    opt = R.make_adam(model, 1e-3, 1e-4)
+    x, y = R.synth_batch(preset, sample_b, seed=0)
+    for _ in range(max(1, min(args.warmup, 2))):
+        R.train_step(model, opt, x, y, "bce", 1.0)
+    steps = max(1, min(args.steps, 8))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        R.train_step(model, opt, x, y, "bce", 1.0)
+    dt = (time.perf_counter() - t0) / steps
+    T = preset["seq_len"]
+    val = sample_b * T / dt
+    sample = (f"{steps} timed steps (of --steps {args.steps}) at batch {sample_b} of the {args.config} config "
+              f"(full batch {PER_GPU_BATCH}), torch-CPU fp32, {torch.get_num_threads()} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, args.gpus), "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_name(config, n):
+    base = {"c2": "binaural (2-ch, 80-band) SEDnet DCASE2017 task3 CRNN train step, seq_len 256, 128 filters, "
+                  "pool [5,2,2] over mel, 2xBiGRU(32), dense 16, 6 classes",
+            "c1": "mono SEDnet CRNN train step, seq_len 256, 128 filters, pool [5,2,2], 2xBiGRU(32), 6 classes",
+            "c5": "long-context CRNN train step, seq_len 2048, 256 filters, 3xBiGRU(128), 16 classes",
+            "fork": "fork-default CRNN (train_constants.py) train step", "sedpy": "sed.py CRNN train step"}[config]
+    return f"{base}; batch {PER_GPU_BATCH}/GPU x {n} GPU = global batch {PER_GPU_BATCH * n}"
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def parse_prof(L):
+    import ctypes as C
+    buf = C.create_string_buffer(1 << 16)
+    L.sedb200_prof_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, ms, cnt = line.split()
+        out[name] = (float(ms), int(cnt))
+    return out
+
+
+def logmel_leg(torch, feature, L, pk, rank):
+    """BASELINE configs[2] leg: bulk log-mel of 3-min stereo clips resident in HBM (kernel-only, CUDA
+    events) and end-to-end through feature.mbe_batch-style host buffers."""
+    n_clips, S = 32, 180 * 44100
+    x = torch.empty(n_clips, 2, S, device="cuda").normal_(0, 0.1)            # 2.03 GB > L2
+    out = torch.empty(n_clips, feature.n_frames(S), 80, device="cuda")
+    for _ in range(3):
+        feature.mbe_device(x, out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 10
+    e0.record()
+    for _ in range(iters):
+        feature.mbe_device(x, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    alg_bytes = x.numel() * 4 + out.numel() * 4
+    gbs = alg_bytes / ms / 1e6
+    # e2e: pinned host PCM -> device -> kernel -> host log-mel, 4 clips per call
+    hb = torch.empty(4, 2, S).normal_(0, 0.1).pin_memory()
+    ho = torch.empty(4, feature.n_frames(S), 80).pin_memory()
+    for _ in range(2):
+        feature.mbe_device(hb.cuda(non_blocking=True), out=out[:4]); ho.copy_(out[:4], non_blocking=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        d = hb.cuda(non_blocking=True)
+        feature.mbe_device(d, out=out[:4])
+        ho.copy_(out[:4], non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / reps
+    del x
+    return {
+        "workload": f"{n_clips} synthetic 3-min stereo clips resident in HBM (2.03 GB in, > L2), kernel-only",
+        "audio_s_per_s": n_clips * 180.0 / (ms * 1e-3), "frames_per_s": n_clips * 2 * feature.n_frames(S) / (ms * 1e-3),
+        "ms_per_launch": ms, "ten_k_clips_s_est": 10000 / n_clips * ms * 1e-3,
+        "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                     "traffic": None, "peak_source": pk["src"]},
+        "e2e": {"audio_s_per_s": 4 * 180.0 / e2e_s, "h2d_bytes_per_call": hb.numel() * 4,
+                "d2h_bytes_per_call": ho.numel() * 4},
+    }
+
+
+def cpu_baselines(args, torch):
+    """Reference CPU path beside the GPU number (rank 0, N=1 only; bounded samples)."""
+    from oracle import crnn_ref as R, logmel_ref
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    preset = dict(R.PRESETS[args.config])
+    b = args.ref_batch
+    model = R.RefCRNN(**preset, dropout=0.5, dropout_each_block=True)
+    opt = R.make_adam(model, 1e-3, 1e-4)
+    x, y = R.synth_batch(preset, b, seed=0)
+    R.train_step(model, opt, x, y, "bce", 1.0)
+    t0 = time.perf_counter()
+    n = 2
+    for _ in range(n):
+        R.train_step(model, opt, x, y, "bce", 1.0)
+    dt = (time.perf_counter() - t0) / n
+    val = b * preset["seq_len"] / dt
+    clip = logmel_ref.synth_clip(0, 180 * 44100, 1, "noise")[0]
+    t0 = time.perf_counter()
+    logmel_ref.mbe(clip)
+    lm = 180.0 / (time.perf_counter() - t0)
+    return {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"oracle/crnn_ref.py (stock torch.nn, the modules the reference instantiates) on torch-CPU fp32, "
+                      f"{torch.get_num_threads()} threads: 1 warm-up + {n} timed steps at batch {b} of the same config "
+                      f"(full batch {PER_GPU_BATCH}); log-mel oracle (numpy/scipy float64 FFT, librosa semantics), "
+                      f"one 3-min mono clip, single process",
+            "logmel_audio_s_per_s": lm}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: libsedb200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from sed_crnn_b200 import _lib, config, engine, feature
+    L = _lib.lib()
+    _lib.check(L.sedb200_device_check(-1))
+    pk = peaks()
+    cfg = config.PRESETS[args.config]
+    B = PER_GPU_BATCH
+    eng = engine.CRNNEngine(cfg, loss="bce", lr=1e-3, weight_decay=1e-4, clip=1.0, seed=1234 + rank)
+    eng.init_default(seed=0)                         # identical weights on every rank
+
+    gx = torch.Generator().manual_seed(100 + rank)
+    n_in = 4                                         # rotate a few distinct batches
+    xs_h = [torch.randn(cfg.input_shape(B), generator=gx).pin_memory() for _ in range(n_in)]
+    ys_h = [(torch.rand(cfg.target_shape(B), generator=gx) < 0.2).float().pin_memory() for _ in range(n_in)]
+    xs = [t.cuda() for t in xs_h]
+    ys = [t.cuda() for t in ys_h]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for i in range(max(args.warmup, 3)):
+        eng.train_step(xs[i % n_in], ys[i % n_in])
+    barrier()
+
+    # ---- timed region: device-resident inputs
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = L.sedb200_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        loss, _ = eng.train_step(xs[i % n_in], ys[i % n_in])
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = L.sedb200_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    frames_per_step = B * cfg.seq_len * world
+    value = frames_per_step / (ms_step * 1e-3)
+    final_loss = loss.item()
+
+    # ---- end-to-end: pinned host batch -> H2D -> step -> D2H loss, every step
+    xd, yd = torch.empty_like(xs[0]), torch.empty_like(ys[0])
+    loss_h = torch.empty(1).pin_memory()
+    for i in range(2):
+        xd.copy_(xs_h[i % n_in], non_blocking=True); yd.copy_(ys_h[i % n_in], non_blocking=True)
+        l, _ = eng.train_step(xd, yd); loss_h.copy_(l.reshape(1), non_blocking=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        xd.copy_(xs_h[i % n_in], non_blocking=True)
+        yd.copy_(ys_h[i % n_in], non_blocking=True)
+        l, _ = eng.train_step(xd, yd)
+        loss_h.copy_(l.reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the caller reads the loss every step (sed.py:138)
+    e1.record()
+    barrier()
+    t2 = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = frames_per_step / (t2.item() / args.steps * 1e-3)
+
+    # ---- phase breakdown (extra instrumented steps, CUDA events on the launching stream)
+    L.sedb200_prof_enable(1)
+    prof_steps = 3
+    for i in range(prof_steps):
+        eng.train_step(xs[i % n_in], ys[i % n_in])
+    torch.cuda.synchronize()
+    prof = parse_prof(L)
+    L.sedb200_prof_enable(0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    total_flops, per = crnn_flops(cfg, B)
+    phases = {k: v[0] / prof_steps for k, v in prof.items()}
+    # dominant kernel = the conv contraction phase with the largest share of the step
+    conv_phases = {k: v for k, v in phases.items() if k.startswith("conv")}
+    dom = max(conv_phases, key=conv_phases.get)
+    blk = dom.split(".")[0]
+    dom_flops = per[blk]                              # fwd, dgrad and wgrad of a block each cost per[blk]
+    dom_ms = phases[dom] / (prof[dom][1] / prof_steps)
+    ach = dom_flops / (dom_ms * 1e-3) / 1e12
+    roof = {"bound": "tensor", "kernel": f"gemm_simt_kernel<{dom}> (fp32 CUDA-core functor GEMM)",
+            "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
+            "traffic": None, "peak_source": pk["src"] + " (sustained bf16)",
+            "algorithmic_flops_per_launch": dom_flops, "ms_per_launch": dom_ms,
+            "share_of_step": phases[dom] / sum(phases.values()),
+            "whole_step": {"algorithmic_tflops": total_flops / (ms_step * 1e-3) / 1e12,
+                           "frac": total_flops / (ms_step * 1e-3) / 1e12 / pk["tf_sustained"]}}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, world), "per_gpu_batch": B, "global_batch": B * world,
+                   "seq_len": cfg.seq_len, "parallelism": f"dp{world}", "l2": "per-step working set (>1 GB of "
+                   "activations) exceeds the 126 MB L2; 4 input batches rotated", "loss": "bce", "optimizer":
+                   "clip 1.0 + Adam(1e-3, wd 1e-4)", "dropout": cfg.dropout, "final_loss": final_loss},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT,
+                "h2d_bytes_per_step": (xs_h[0].numel() + ys_h[0].numel()) * 4 * world, "d2h_bytes_per_step": 4 * world},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "phases_ms": {k: round(v, 4) for k, v in phases.items()},
+    }
+    if world == 1:
+        line["cpu_baseline"] = cpu_baselines(args, torch)
+        if not args.no_logmel:
+            line["logmel"] = logmel_leg(torch, feature, L, pk, rank)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c5", "fork", "sedpy"])
+    ap.add_argument("--ref-batch", type=int, default=16, help="CPU-baseline sample batch")
+    ap.add_argument("--no-logmel", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under it
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), __file__] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -48,6 +48,13 @@ int         sedb200_version(void);
 const char* sedb200_last_error(void);
 /* SEDB200_OK if `device` (or the current device when -1) is sm_100; SEDB200_EARCH otherwise. */
 int         sedb200_device_check(int device);
+/* number of CUDA kernels this library has launched in this process (for the bench's gpu_launches). */
+long        sedb200_launch_count(void);
+/* Phase profiler: when enabled, every phase of the CRNN calls is bracketed by CUDA events on the
+ * launching stream.  sedb200_prof_report synchronises those events and writes one line per phase,
+ * "<name> <total_ms> <count>\n", into buf.  sedb200_prof_enable (on or off) clears the record. */
+int         sedb200_prof_enable(int on);
+int         sedb200_prof_report(char* buf, size_t buf_bytes);
 
 /* ------------------------------------------------------------------------------------------------
  * Log-mel front end.   Replaces  feature._mbe(y, sr)  (/root/reference/feature.py:55-59):

@@ -28,6 +28,9 @@ SIGNATURES = {
     "sedb200_version": (_i, []),
     "sedb200_last_error": (C.c_char_p, []),
     "sedb200_device_check": (_i, [_i]),
+    "sedb200_launch_count": (_l, []),
+    "sedb200_prof_enable": (_i, [_i]),
+    "sedb200_prof_report": (_i, [C.c_char_p, _sz]),
     "sedb200_logmel_frames": (_l, [_l]),
     "sedb200_logmel_f32": (_i, [_p, _i, _i, _l, _i, _i, _p, _p]),
     "sedb200_logmel_host_scratch": (_sz, [_i, _i, _l]),

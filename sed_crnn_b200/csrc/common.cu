@@ -1,6 +1,10 @@
 // common.cu -- error plumbing, device checks, version.
 #include "common.cuh"
+#include <atomic>
+#include <map>
 #include <mutex>
+#include <string>
+#include <vector>
 
 namespace sedb200 {
 
@@ -52,6 +56,34 @@ int require_sm100() {
     return SEDB200_OK;
 }
 
+namespace {
+std::atomic<long> g_launches{0};
+std::atomic<bool> g_prof{false};
+struct ProfRec { std::string name; cudaEvent_t a, b; };
+std::vector<ProfRec> g_recs;
+std::vector<size_t> g_open;          // stack of scopes whose end event is not recorded yet
+std::mutex g_prof_mu;
+}  // namespace
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool prof_on() { return g_prof.load(std::memory_order_relaxed); }
+void prof_begin(const char* name, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfRec r;
+    r.name = name;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    g_open.push_back(g_recs.size());
+    g_recs.push_back(r);
+}
+void prof_end(cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (g_open.empty()) return;
+    cudaEventRecord(g_recs[g_open.back()].b, st);
+    g_open.pop_back();
+}
+
 int sm_count() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
@@ -67,6 +99,40 @@ extern "C" {
 int sedb200_version(void) { return SEDB200_VERSION; }
 
 const char* sedb200_last_error(void) { return sedb200::err_buf(); }
+
+long sedb200_launch_count(void) { return sedb200::g_launches.load(); }
+
+int sedb200_prof_enable(int on) {
+    std::lock_guard<std::mutex> lk(sedb200::g_prof_mu);
+    for (auto& r : sedb200::g_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    sedb200::g_recs.clear();
+    sedb200::g_open.clear();
+    sedb200::g_prof.store(on != 0);
+    return SEDB200_OK;
+}
+
+int sedb200_prof_report(char* buf, size_t n) {
+    if (!buf || n == 0) return sedb200::fail(SEDB200_EINVAL, "prof_report: no buffer");
+    std::lock_guard<std::mutex> lk(sedb200::g_prof_mu);
+    std::map<std::string, std::pair<double, long>> acc;
+    std::vector<std::string> order;
+    for (auto& r : sedb200::g_recs) {
+        if (cudaEventSynchronize(r.b) != cudaSuccess) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+        if (!acc.count(r.name)) order.push_back(r.name);
+        acc[r.name].first += ms;
+        acc[r.name].second += 1;
+    }
+    size_t o = 0;
+    buf[0] = 0;
+    for (auto& k : order) {
+        int w = snprintf(buf + o, n - o, "%s %.6f %ld\n", k.c_str(), acc[k].first, acc[k].second);
+        if (w < 0 || (size_t)w >= n - o) break;
+        o += (size_t)w;
+    }
+    return SEDB200_OK;
+}
 
 int sedb200_device_check(int device) {
     if (device >= 0) {

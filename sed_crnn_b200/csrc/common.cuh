@@ -25,6 +25,25 @@ int   fail(int code, const char* fmt, ...);
         if (!(cond)) return ::sedb200::fail((code), __VA_ARGS__);     \
     } while (0)
 
+// every kernel launch goes through this: counts the launch and surfaces launch errors
+void count_launch();
+#define SED_POST_LAUNCH()                        \
+    do {                                         \
+        ::sedb200::count_launch();               \
+        SED_CUDA_OK(cudaGetLastError());         \
+    } while (0)
+
+// optional phase profiler (sedb200_prof_enable): CUDA events on the launching stream around a phase
+bool prof_on();
+void prof_begin(const char* name, cudaStream_t st);
+void prof_end(cudaStream_t st);
+struct ProfScope {
+    cudaStream_t st; bool on;
+    ProfScope(const char* name, cudaStream_t s) : st(s), on(prof_on()) { if (on) prof_begin(name, st); }
+    ~ProfScope() { if (on) prof_end(st); }
+};
+#define SED_PROF(name_literal, stream) ::sedb200::ProfScope _sed_prof(name_literal, stream)
+
 // 0 if the current device is compute capability 10.x, else SEDB200_EARCH (message set).
 int  require_sm100();
 int  sm_count();

@@ -400,11 +400,14 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
         const InStrides s = in_strides(P, d, i);
         const int M = (int)(B * P.H * P.win[i]), K = 9 * P.cin[i];
         float* y = wsf(ws, P.y[i]);
+{ char _nm[40]; snprintf(_nm, sizeof _nm, "conv%d.fwd", i); SED_PROF(_nm, st);
         rc = gemm_simt(M, P.C, K, 1, ConvFwdA{in, P.H, P.win[i], P.cin[i], s.sB, s.sH, s.sW, s.sC},
                        ConvFwdB{params + P.conv_w[i], P.cin[i]}, EpiStore{y, P.C, params + P.conv_b[i], 0}, st);
         if (rc) return rc;
+}
         float* stat = wsf(ws, P.stat[i]);
         float* running = bn_state + 2L * i * P.C;
+{ char _nm[40]; snprintf(_nm, sizeof _nm, "bn%d.stats", i); SED_PROF(_nm, st);
         if (training) {
             int nblk = 0;
             rc = colsum_partials(y, M, P.C, wsf(ws, P.part), &nblk, st);
@@ -416,11 +419,14 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
             bn_finalize_eval_kernel<<<(P.C + 127) / 128, 128, 0, st>>>(P.C, params + P.bn_w[i], params + P.bn_b[i],
                                                                        d->bn_eps, running, stat);
         }
-        SED_CUDA_OK(cudaGetLastError());
+        SED_POST_LAUNCH();
+}
         const PoolGeom g = pool_geom(P, d, i, training, seed);
         const long n_vec = B * P.H * P.wout[i] * (P.C / 4);
+{ char _nm[40]; snprintf(_nm, sizeof _nm, "pool%d.fwd", i); SED_PROF(_nm, st);
         bn_relu_pool_fwd_kernel<<<ew_blocks(n_vec), 256, 0, st>>>(y, stat, wsf(ws, P.act[i]), n_vec, g);
-        SED_CUDA_OK(cudaGetLastError());
+        SED_POST_LAUNCH();
+}
     }
 
     // ---- BiGRU stack
@@ -429,12 +435,16 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
     for (int l = 0; l < P.n_gru; ++l) {
         const int h = P.gh[l], in = P.gin[l];
         float* gi = wsf(ws, P.gi[l]);
+{ char _nm[40]; snprintf(_nm, sizeof _nm, "gru%d.proj", l); SED_PROF(_nm, st);
         rc = gemm_simt(BT, 6 * h, in, 1, RowMajor{seq, in}, RowMajor{params + P.wih[l], in},
                        EpiStore{gi, 6L * h, params + P.bih[l], 0}, st);
         if (rc) return rc;
+}
+{ char _nm[40]; snprintf(_nm, sizeof _nm, "gru%d.scan_fwd", l); SED_PROF(_nm, st);
         rc = gru_scan_forward(gi, params + P.whh[l], params + P.bhh[l], wsf(ws, P.gout[l]), wsf(ws, P.gates[l]),
                               batch, P.T, h, st);
         if (rc) return rc;
+}
         seq = wsf(ws, P.gout[l]);
     }
 
@@ -442,9 +452,11 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
     for (int j = 0; j < P.n_dense; ++j) {
         const bool last = (j == P.n_dense - 1);
         float* out = last ? logits : wsf(ws, P.hid[j]);
+{ char _nm[40]; snprintf(_nm, sizeof _nm, "dense%d.fwd", j); SED_PROF(_nm, st);
         rc = gemm_simt(BT, P.dout[j], P.din[j], 1, RowMajor{seq, P.din[j]}, RowMajor{params + P.dn_w[j], P.din[j]},
                        EpiStore{out, P.dout[j], params + P.dn_b[j], (!last && d->dense_relu) ? 1 : 0}, st);
         if (rc) return rc;
+}
         seq = out;
     }
     return SEDB200_OK;
@@ -502,9 +514,11 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         const float* xin = l == 0 ? wsf(ws, P.act[P.n_conv - 1]) : wsf(ws, P.gout[l - 1]);
         float* dgi = wsf(ws, P.dgi);
         float* dgh = wsf(ws, P.dgh);
+{ char _nm[40]; snprintf(_nm, sizeof _nm, "gru%d.scan_bwd", l); SED_PROF(_nm, st);
         rc = gru_scan_backward(wsf(ws, P.dseq[cur]), wsf(ws, P.gout[l]), wsf(ws, P.gates[l]), params + P.whh[l],
                                dgi, dgh, batch, P.T, h, st);
         if (rc) return rc;
+}
         // biases
         rc = colsum(dgi, BT, 6 * h, grads + P.bih[l], part, st);
         if (rc) return rc;
@@ -543,16 +557,20 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         const long n_elem = B * P.H * P.win[i];                 // BN population per channel
         const int rows = 256 / (P.C / 4);
         const int nblk = (int)std::min<long>((n_pix_out + rows - 1) / rows, 592);
+{ char _nm[40]; snprintf(_nm, sizeof _nm, "pool%d.bwd_sums", i); SED_PROF(_nm, st);
         bn_pool_bwd_sums_kernel<<<nblk, 256, 0, st>>>(y, stat, dA, n_pix_out, g, part);
-        SED_CUDA_OK(cudaGetLastError());
+        SED_POST_LAUNCH();
+}
         float* bnsum = wsf(ws, P.bnsum);
         bn_bwd_finalize_kernel<<<(P.C + 127) / 128, 128, 0, st>>>(part, nblk, P.C, n_elem, grads + P.bn_w[i],
                                                                  grads + P.bn_b[i], bnsum);
-        SED_CUDA_OK(cudaGetLastError());
+        SED_POST_LAUNCH();
         float* dy = wsf(ws, P.dy);
         const long n_vec = n_pix_out * (P.C / 4);
+{ char _nm[40]; snprintf(_nm, sizeof _nm, "pool%d.bwd_dy", i); SED_PROF(_nm, st);
         bn_pool_bwd_dy_kernel<<<ew_blocks(n_vec), 256, 0, st>>>(y, stat, dA, bnsum, n_vec, g, dy);
-        SED_CUDA_OK(cudaGetLastError());
+        SED_POST_LAUNCH();
+}
 
         const float* in = i == 0 ? x : wsf(ws, P.act[i - 1]);
         const InStrides s = in_strides(P, d, i);
@@ -563,17 +581,21 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         // wgrad
         const int want = std::max(1, std::min(64, M / 2048));
         const int sp = gemm_simt_splits(M, want);
+{ char _nm[40]; snprintf(_nm, sizeof _nm, "conv%d.wgrad", i); SED_PROF(_nm, st);
         rc = gemm_simt(P.C, J, M, want, ColMajor{dy, P.C}, ConvWgradB{in, P.H, P.win[i], s.sB, s.sH, s.sW, s.sC},
                        EpiPartial{part, (long)P.C * J, J}, st);
         if (rc) return rc;
         rc = reduce_partials(part, grads + P.conv_w[i], (long)P.C * J, sp, st);
         if (rc) return rc;
+}
         // dgrad
         if (i > 0) {
             float* dprev = wsf(ws, P.dact[i & 1]);
+{ char _nm[40]; snprintf(_nm, sizeof _nm, "conv%d.dgrad", i); SED_PROF(_nm, st);
             rc = gemm_simt(M, P.cin[i], 9 * P.C, 1, ConvDgradA{dy, P.H, P.win[i], P.C},
                            ConvDgradB{params + P.conv_w[i], P.cin[i], P.C}, EpiStore{dprev, P.cin[i], nullptr, 0}, st);
             if (rc) return rc;
+}
             dA = dprev;
         } else if (dx) {
             rc = gemm_simt(M, P.cin[0], 9 * P.C, 1, ConvDgradA{dy, P.H, P.win[0], P.C},

@@ -130,7 +130,7 @@ inline int gemm_simt(int M, int N, int K, int splits, AOp A, BOp B, Epi epi, cud
     splits = K > 0 ? (K + k_slice - 1) / k_slice : 1;
     dim3 grid((M + GBM - 1) / GBM, (N + GBN - 1) / GBN, splits);
     gemm_simt_kernel<AOp, BOp, Epi><<<grid, GTHREADS, 0, st>>>(M, N, K, k_slice, A, B, epi);
-    SED_CUDA_OK(cudaGetLastError());
+    SED_POST_LAUNCH();
     return SEDB200_OK;
 }
 

@@ -164,7 +164,7 @@ int gru_scan_forward(const float* gi, const float* whh, const float* bhh, float*
     SED_REQUIRE(smem <= 227 * 1024, SEDB200_ESHAPE, "gru_scan: H=%d needs %zu B shared memory", H, smem);
     dim3 grid((B + kBT - 1) / kBT, 2);
     gru_scan_fwd_kernel<<<grid, threads, smem, st>>>(gi, whh, bhh, out, gates, B, T, H);
-    SED_CUDA_OK(cudaGetLastError());
+    SED_POST_LAUNCH();
     return SEDB200_OK;
 }
 
@@ -177,7 +177,7 @@ int gru_scan_backward(const float* dout, const float* out, const float* gates, c
     SED_REQUIRE(smem <= 227 * 1024, SEDB200_ESHAPE, "gru_scan: H=%d needs %zu B shared memory", H, smem);
     dim3 grid((B + kBT - 1) / kBT, 2);
     gru_scan_bwd_kernel<<<grid, threads, smem, st>>>(dout, out, gates, whh, dgi, dgh, B, T, H);
-    SED_CUDA_OK(cudaGetLastError());
+    SED_POST_LAUNCH();
     return SEDB200_OK;
 }
 

@@ -177,9 +177,9 @@ int sedb200_loss_fwd_bwd(int kind, float alpha, float gamma, const float* logits
     const int nb = red_blocks(n);
     float* part = reinterpret_cast<float*>(scratch);
     loss_kernel<<<nb, 256, 0, st>>>(kind, alpha, gamma, logits, targets, n, grad_scale, probs, dlogits, part);
-    SED_CUDA_OK(cudaGetLastError());
+    SED_POST_LAUNCH();
     loss_final_kernel<<<1, 32, 0, st>>>(part, nb, n, loss);
-    SED_CUDA_OK(cudaGetLastError());
+    SED_POST_LAUNCH();
     return SEDB200_OK;
 }
 
@@ -197,14 +197,14 @@ int sedb200_clip_adam(float* params, const float* grads, float* m, float* v, lon
     const int nb = red_blocks(n);
     float* part = reinterpret_cast<float*>(scratch);
     sumsq_kernel<<<nb, 256, 0, st>>>(grads, n, prescale, part);
-    SED_CUDA_OK(cudaGetLastError());
+    SED_POST_LAUNCH();
     gnorm_final_kernel<<<1, 32, 0, st>>>(part, nb, gnorm);
-    SED_CUDA_OK(cudaGetLastError());
+    SED_POST_LAUNCH();
     const double bc1 = 1.0 - std::pow((double)b1, (double)step);
     const double bc2 = 1.0 - std::pow((double)b2, (double)step);
     adam_kernel<<<nb, 256, 0, st>>>(params, grads, m, v, n, lr, b1, b2, eps, wd, (float)bc1, (float)std::sqrt(bc2),
                                     max_norm, prescale, gnorm);
-    SED_CUDA_OK(cudaGetLastError());
+    SED_POST_LAUNCH();
     return SEDB200_OK;
 }
 
@@ -218,10 +218,10 @@ int sedb200_threshold_counts(const float* probs, const float* targets, long n_ro
     if (n_rows == 0) return SEDB200_OK;
     SED_REQUIRE(probs && targets, SEDB200_EINVAL, "threshold_counts: null buffer");
     frame_counts_kernel<<<red_blocks(n_rows), 256, 0, st>>>(probs, targets, n_rows, n_cls, threshold, counts);
-    SED_CUDA_OK(cudaGetLastError());
+    SED_POST_LAUNCH();
     const long nblk = (n_rows + block - 1) / block;
     block_counts_kernel<<<red_blocks(nblk), 256, 0, st>>>(probs, targets, n_rows, n_cls, block, threshold, counts);
-    SED_CUDA_OK(cudaGetLastError());
+    SED_POST_LAUNCH();
     return SEDB200_OK;
 }
 

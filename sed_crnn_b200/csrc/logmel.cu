@@ -411,7 +411,7 @@ int sedb200_logmel_f32(const float* pcm_dev, int n_clips, int n_ch, long n_sampl
     const int grid = (int)std::min<long>(want, sm_count());
     logmel_kernel<<<grid, kWarps * 32, kSmemBytes, st>>>(pcm_dev, out_dev, n_ch, n_samples, (int)nfr, total,
                                                          pad_mode, tab);
-    SED_CUDA_OK(cudaGetLastError());
+    SED_POST_LAUNCH();
     return SEDB200_OK;
 }
 

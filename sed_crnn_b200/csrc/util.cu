@@ -18,7 +18,7 @@ int reduce_partials(const float* part, float* out, long n, int splits, cudaStrea
     if (n <= 0) return SEDB200_OK;
     const int blocks = (int)std::min<long>((n + 255) / 256, 1184);
     reduce_partials_kernel<<<blocks, 256, 0, st>>>(part, out, n, splits);
-    SED_CUDA_OK(cudaGetLastError());
+    SED_POST_LAUNCH();
     return SEDB200_OK;
 }
 
@@ -92,7 +92,7 @@ int colsum_partials(const float* X, long rows, int cols, float* part, int* nblk_
     const int nb = colsum_blocks(rows);
     const long rpb = (rows + nb - 1) / nb;
     colsum2_kernel<<<nb, 256, 0, st>>>(X, rows, cols, rpb, part);
-    SED_CUDA_OK(cudaGetLastError());
+    SED_POST_LAUNCH();
     *nblk_out = nb;
     return SEDB200_OK;
 }
@@ -102,7 +102,7 @@ int colsum(const float* X, long rows, int cols, float* out, float* scratch, cuda
     int rc = colsum_partials(X, rows, cols, scratch, &nb, st);
     if (rc) return rc;
     colsum_final_kernel<<<(cols + 127) / 128, 128, 0, st>>>(scratch, nb, cols, out, nullptr);
-    SED_CUDA_OK(cudaGetLastError());
+    SED_POST_LAUNCH();
     return SEDB200_OK;
 }
 

@@ -89,6 +89,26 @@ class CRNNEngine:
                 dst = v[name]
             dst.copy_(t.to(self.device, torch.float32).reshape(dst.shape))
 
+    @torch.no_grad()
+    def init_default(self, seed: int = 0) -> None:
+        """PyTorch-default-style random init (uniform +-1/sqrt(fan_in); BatchNorm weight 1 / bias 0),
+        drawn on the host from `seed` so that every rank gets identical weights."""
+        g = torch.Generator().manual_seed(seed)
+        host, fan = {}, 1
+        for name, shape, _ in self.specs:
+            layer, leaf = name.split(".")
+            if layer.startswith("bn"):
+                host[name] = torch.ones(shape) if leaf == "weight" else torch.zeros(shape)
+                continue
+            if layer.startswith("conv") and leaf == "weight":
+                fan = shape[1] * 9
+            elif layer.startswith("gru"):
+                fan = shape[1] // 3                                   # nn.GRU: 1/sqrt(hidden_size) for all
+            elif layer.startswith("dense") and leaf == "weight":
+                fan = shape[1]
+            host[name] = (torch.rand(shape, generator=g) * 2 - 1) / (fan ** 0.5)
+        self.load_named(host)
+
     def reset_optimizer(self) -> None:
         self.exp_avg.zero_()
         self.exp_avg_sq.zero_()
