@@ -370,7 +370,8 @@ def run_ours(args, rank, world, local_rank):
         "phases_ms": {k: round(v, 4) for k, v in phases.items()},
     }
     if world == 1:
-        line["cpu_baseline"] = cpu_baselines(args, torch)
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baselines(args, torch)
         if not args.no_logmel:
             line["logmel"] = logmel_leg(torch, feature, L, pk, rank)
     print(json.dumps(line))
@@ -387,6 +388,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=["c1", "c2", "c5", "fork", "sedpy"])
     ap.add_argument("--ref-batch", type=int, default=16, help="CPU-baseline sample batch")
     ap.add_argument("--no-logmel", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU-baseline leg (profiling runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
