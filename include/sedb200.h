@@ -180,6 +180,17 @@ int sedb200_clip_adam(float* params_dev, const float* grads_dev, float* exp_avg_
 int sedb200_threshold_counts(const float* probs_dev, const float* targets_dev, long n_rows, int n_cls,
                              int block, float threshold, unsigned long long* counts_dev, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Tensor-core building block, exposed for unit tests: one 3x3 / pad 1 convolution (nn.Conv2d(.., 3,
+ * padding=1), crnn_lightning.py:47) or its data gradient on channels-last fp32 tensors, computed on
+ * tcgen05 with the 3-term bf16 split.  in [B][H][W][Cin] -> out [B][H][W][Cout] (dgrad: in = dY
+ * [B][H][W][Cout] -> out = dX [B][H][W][Cin]); weight in PyTorch layout [Cout][Cin][3][3].
+ * Supported: K channels % 64 == 0, N channels % 128 == 0, W a divisor of 128. */
+size_t sedb200_conv3x3_tc_scratch_bytes(int B, int H, int W, int Cin, int Cout);
+int    sedb200_conv3x3_tc(const float* in_dev, const float* weight_dev, const float* bias_dev, float* out_dev,
+                          int B, int H, int W, int Cin, int Cout, int dgrad, void* scratch_dev,
+                          size_t scratch_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

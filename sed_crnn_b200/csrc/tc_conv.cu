@@ -1,0 +1,321 @@
+// tc_conv.cu -- 3x3 convolutions as implicit GEMMs on the 5th-generation tensor cores (tcgen05 + TMEM),
+// operands staged by TMA, fp32-grade accuracy through a 3-term bf16 split.
+//
+// Reference call sites: nn.Conv2d(.., 3, padding=1) in crnn_lightning.py:47 / sed.py:88 and their
+// autograd backward (dgrad / wgrad).
+//
+// Why split precision: the parity gate (probabilities within 1e-3 after one Adam step) is not met by
+// single-pass bf16 (2-3e-3) nor TF32 (1.2e-3) operands -- Adam's first step moves every weight by
+// lr*sign(g), so operand rounding in the gradients is amplified (DESIGN.md "precision").  Every fp32
+// operand x is therefore carried as two bf16 planes  x = hi + lo  (hi = bf16(x), lo = bf16(x - hi),
+// 16 mantissa bits together) and each product runs as three MMAs into the same fp32 TMEM accumulator:
+//     A*B ~= A_hi*B_hi + A_hi*B_lo + A_lo*B_hi            (the dropped lo*lo term is ~2^-18 relative)
+//
+// Forward / dgrad kernel (K-major operands):
+//   M = 128 output pixels of one image (Ht = 128/W rows x W columns), N = 128 output channels,
+//   K = 9 taps x Cin, walked as K-blocks of one tap x 64 channels.  For a tap (r,s) the A tile is the
+//   SAME NHWC box shifted by (r-1, s-1): a 4-D TMA load {64 c, W, Ht, 1} at coordinates
+//   (c0, s-1, h0+r-1, b); out-of-image rows/columns are zero-filled by the TMA unit, which is exactly
+//   the conv padding.  No im2col buffer ever exists.
+//   Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
+//   warps 4-7 = epilogue (tcgen05.ld -> +bias -> fp32 NHWC store).  Two TMEM accumulator buffers so the
+//   epilogue of tile i overlaps the MMAs of tile i+1; 3-stage smem ring (64 KB per stage).
+//   dgrad is the same kernel on dY with the weights flipped and transposed beforehand.
+#include "tc_umma.cuh"
+#include "tc_conv.cuh"
+
+#include <algorithm>
+#include <mutex>
+
+namespace sedb200 {
+
+// ---------------------------------------------------------------------------------- tensor-map encode
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box) {
+    using Fn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                            const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                            CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static Fn fn = nullptr;
+    static std::mutex mu;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!fn) {
+            void* p = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            SED_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+            SED_REQUIRE(p && q == cudaDriverEntryPointSuccess, SEDB200_ECUDA, "cuTensorMapEncodeTiled not available");
+            fn = reinterpret_cast<Fn>(p);
+        }
+    }
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                    strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SED_REQUIRE(r == CUDA_SUCCESS, SEDB200_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return SEDB200_OK;
+}
+
+namespace {
+using namespace umma;
+
+constexpr int kStages = 3;
+constexpr int kTileM = 128, kTileN = 128, kBlockK = 64;
+constexpr int kTileBytes = kTileM * kBlockK * 2;                 // 16 KB: one bf16 operand tile
+constexpr int kStageBytes = 4 * kTileBytes;                      // A_hi, A_lo, B_hi, B_lo
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kThreads = 256;
+constexpr uint32_t kTmemCols = 256;                              // two 128-column accumulators
+
+struct ConvTcParams {
+    int B, H, W, Ht, tiles_per_img, n_tiles_n, total_tiles, kchunks, n_total;
+    float* out;              // [B*H*W][out_ld] fp32
+    const float* bias;       // [n_total] or null
+    long out_ld;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+               const ConvTcParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* full = bars;                    // [kStages]  TMA -> MMA
+    uint64_t* empty = bars + kStages;         // [kStages]  MMA -> TMA
+    uint64_t* tfull = bars + 2 * kStages;     // [2]        MMA -> epilogue
+    uint64_t* tempty = bars + 2 * kStages + 2;// [2]        epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int n_kb = 9 * p.kchunks;
+
+    if (warp == 0 && lane == 0) {
+        // ================= TMA producer =================
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
+            const int b = mt / p.tiles_per_img, h0 = (mt % p.tiles_per_img) * p.Ht;
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int tap = kb / p.kchunks, c0 = (kb % p.kchunks) * kBlockK;
+                const int r = tap / 3, s = tap - 3 * r;
+                mbar_wait(empty + stage, phase ^ 1);
+                unsigned char* st = smem + stage * kStageBytes;
+                mbar_expect_tx(full + stage, kStageBytes);
+                tma_load_4d(st, &tmA_hi, full + stage, c0, s - 1, h0 + r - 1, b);
+                tma_load_4d(st + kTileBytes, &tmA_lo, full + stage, c0, s - 1, h0 + r - 1, b);
+                tma_load_2d(st + 2 * kTileBytes, &tmB_hi, full + stage, c0, tap * p.n_total + nt * kTileN);
+                tma_load_2d(st + 3 * kTileBytes, &tmB_lo, full + stage, c0, tap * p.n_total + nt * kTileN);
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ================= MMA issuer =================
+        constexpr uint32_t idesc = idesc_bf16(kTileM, kTileN, 0, 0);
+        int stage = 0; uint32_t phase = 0;
+        int buf = 0; uint32_t bphase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            mbar_wait(tempty + buf, bphase ^ 1);
+            tc_fence_after();
+            const uint32_t d = tmem_base + buf * kTileN;
+            for (int kb = 0; kb < n_kb; ++kb) {
+                mbar_wait(full + stage, phase);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem + stage * kStageBytes);
+                const uint32_t a_lo = a_hi + kTileBytes, b_hi = a_hi + 2 * kTileBytes, b_lo = a_hi + 3 * kTileBytes;
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                    const uint64_t dah = smem_desc_sw128(a_hi + k * 32, 16, 1024), dal = smem_desc_sw128(a_lo + k * 32, 16, 1024);
+                    const uint64_t dbh = smem_desc_sw128(b_hi + k * 32, 16, 1024), dbl = smem_desc_sw128(b_lo + k * 32, 16, 1024);
+                    mma_bf16(d, dah, dbh, idesc, (kb | k) != 0);
+                    mma_bf16(d, dah, dbl, idesc, 1);
+                    mma_bf16(d, dal, dbh, idesc, 1);
+                }
+                mma_commit(empty + stage);                 // smem slot reusable once these MMAs retire
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+            mma_commit(tfull + buf);                       // accumulator complete
+            if (++buf == 2) { buf = 0; bphase ^= 1; }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue (4 warps, one TMEM sub-partition each) =================
+        const int q = warp - 4;                            // == warp % 4
+        int buf = 0; uint32_t bphase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
+            const int b = mt / p.tiles_per_img, h0 = (mt % p.tiles_per_img) * p.Ht;
+            mbar_wait(tfull + buf, bphase);
+            tc_fence_after();
+            const int row = q * 32 + lane;
+            const bool valid = (h0 + row / p.W) < p.H;
+            float* dst = p.out + (((long)b * p.H + h0) * p.W + row) * p.out_ld + nt * kTileN;
+#pragma unroll 1
+            for (int cc = 0; cc < kTileN / 32; ++cc) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * kTileN + cc * 32, v);
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        if (p.bias) {
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nt * kTileN + cc * 32 + j));
+                            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                        }
+                        *reinterpret_cast<float4*>(dst + cc * 32 + j) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty + buf);
+            if (++buf == 2) { buf = 0; bphase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------------- operand preparation
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// fp32 [n] -> bf16 hi/lo planes
+__global__ void __launch_bounds__(256)
+split_planes_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long n4) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+        __nv_bfloat16 h[4], l[4];
+        split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+        reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<uint2*>(h);
+        reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<uint2*>(l);
+    }
+}
+
+// conv weight [Cout][Cin][3][3] fp32 -> B-operand planes [9][N][K] bf16 (K contiguous)
+//   fwd  : N = Cout, K = Cin, plane[tap][co][ci] = w[co][ci][tap]
+//   dgrad: N = Cin,  K = Cout, plane[tap][ci][co] = w[co][ci][8 - tap]      (flipped taps)
+__global__ void __launch_bounds__(256)
+weight_planes_kernel(const float* __restrict__ w, int Cout, int Cin, int dgrad, __nv_bfloat16* __restrict__ hi,
+                     __nv_bfloat16* __restrict__ lo) {
+    const long n = 9L * Cout * Cin;
+    const int N = dgrad ? Cin : Cout, K = dgrad ? Cout : Cin;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % K);
+        const int nn = (int)((i / K) % N);
+        const int tap = (int)(i / ((long)K * N));
+        const int co = dgrad ? k : nn, ci = dgrad ? nn : k, t = dgrad ? 8 - tap : tap;
+        split_bf16(__ldg(w + ((long)co * Cin + ci) * 9 + t), hi[i], lo[i]);
+    }
+}
+
+}  // namespace
+
+size_t conv_tc_scratch_bytes(int B, int H, int W, int Cin, int Cout) {
+    const size_t act = (size_t)B * H * W * Cin * 2;      // one bf16 plane of the input
+    const size_t wp = (size_t)9 * Cout * Cin * 2;
+    return 2 * ((act + 1023) & ~(size_t)1023) + 2 * ((wp + 1023) & ~(size_t)1023);
+}
+
+bool conv_tc_supported(int H, int W, int Cin, int Cout) {
+    return Cin % 64 == 0 && Cout % 128 == 0 && W >= 1 && W <= 128 && (128 % W) == 0 && H >= 1;
+}
+
+int conv_tc_forward(const float* in, const float* w, const float* bias, float* out, int B, int H, int W, int Cin,
+                    int Cout, int dgrad, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+    // dgrad: `in` is dY [B,H,W,Cout]; the result is dX [B,H,W,Cin]
+    const int Kc = dgrad ? Cout : Cin, Nc = dgrad ? Cin : Cout;
+    SED_REQUIRE(conv_tc_supported(H, W, Kc, Nc), SEDB200_ESHAPE, "conv_tc: shape H=%d W=%d K=%d N=%d unsupported", H, W, Kc, Nc);
+    SED_REQUIRE(scratch_bytes >= conv_tc_scratch_bytes(B, H, W, Kc, Nc), SEDB200_EWORKSPACE, "conv_tc: scratch too small");
+    const size_t act = ((size_t)B * H * W * Kc * 2 + 1023) & ~(size_t)1023;
+    const size_t wp = ((size_t)9 * Nc * Kc * 2 + 1023) & ~(size_t)1023;
+    char* s = reinterpret_cast<char*>(scratch);
+    __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(s);
+    __nv_bfloat16* a_lo = reinterpret_cast<__nv_bfloat16*>(s + act);
+    __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(s + 2 * act);
+    __nv_bfloat16* w_lo = reinterpret_cast<__nv_bfloat16*>(s + 2 * act + wp);
+
+    const long n4 = (long)B * H * W * Kc / 4;
+    split_planes_kernel<<<(int)std::min<long>((n4 + 255) / 256, 148L * 8), 256, 0, st>>>(in, a_hi, a_lo, n4);
+    SED_POST_LAUNCH();
+    weight_planes_kernel<<<(int)std::min<long>((9L * Cout * Cin + 255) / 256, 1184), 256, 0, st>>>(w, Cout, Cin, dgrad, w_hi, w_lo);
+    SED_POST_LAUNCH();
+
+    const int Ht = kTileM / W;
+    CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+    {
+        const uint64_t dims[4] = {(uint64_t)Kc, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+        const uint64_t strides[3] = {(uint64_t)Kc * 2, (uint64_t)W * Kc * 2, (uint64_t)H * W * Kc * 2};
+        const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)W, (uint32_t)Ht, 1};
+        int rc = encode_tmap_bf16(&tmA_hi, a_hi, 4, dims, strides, box);
+        if (rc) return rc;
+        rc = encode_tmap_bf16(&tmA_lo, a_lo, 4, dims, strides, box);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)Kc, (uint64_t)9 * Nc};
+        const uint64_t strides[1] = {(uint64_t)Kc * 2};
+        const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)kTileN};
+        int rc = encode_tmap_bf16(&tmB_hi, w_hi, 2, dims, strides, box);
+        if (rc) return rc;
+        rc = encode_tmap_bf16(&tmB_lo, w_lo, 2, dims, strides, box);
+        if (rc) return rc;
+    }
+    ConvTcParams p;
+    p.B = B; p.H = H; p.W = W; p.Ht = Ht;
+    p.tiles_per_img = (H + Ht - 1) / Ht;
+    p.n_tiles_n = Nc / kTileN;
+    p.total_tiles = B * p.tiles_per_img * p.n_tiles_n;
+    p.kchunks = Kc / kBlockK;
+    p.n_total = Nc;
+    p.out = out; p.bias = bias; p.out_ld = Nc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SED_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        attr_done = true;
+    }
+    const int grid = std::min(p.total_tiles, sm_count());
+    conv_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+    SED_POST_LAUNCH();
+    return SEDB200_OK;
+}
+
+}  // namespace sedb200
+
+using namespace sedb200;
+
+extern "C" {
+
+size_t sedb200_conv3x3_tc_scratch_bytes(int B, int H, int W, int Cin, int Cout) {
+    return std::max(conv_tc_scratch_bytes(B, H, W, Cin, Cout), conv_tc_scratch_bytes(B, H, W, Cout, Cin));
+}
+
+int sedb200_conv3x3_tc(const float* in_dev, const float* weight_dev, const float* bias_dev, float* out_dev, int B,
+                       int H, int W, int Cin, int Cout, int dgrad, void* scratch_dev, size_t scratch_bytes,
+                       void* stream) {
+    SED_REQUIRE(in_dev && weight_dev && out_dev && scratch_dev, SEDB200_EINVAL, "conv3x3_tc: null buffer");
+    SED_REQUIRE(B >= 1, SEDB200_EINVAL, "conv3x3_tc: batch %d", B);
+    int rc = require_sm100();
+    if (rc) return rc;
+    return conv_tc_forward(in_dev, weight_dev, bias_dev, out_dev, B, H, W, Cin, Cout, dgrad, scratch_dev,
+                           scratch_bytes, as_stream(stream));
+}
+
+}  // extern "C"

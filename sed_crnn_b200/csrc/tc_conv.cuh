@@ -1,0 +1,16 @@
+// tc_conv.cuh -- tensor-core (tcgen05) 3x3 convolution entry points used by the CRNN orchestration.
+#pragma once
+#include "common.cuh"
+
+namespace sedb200 {
+
+// shapes the tcgen05 path covers: K channels % 64 == 0, N channels % 128 == 0, W a divisor of 128
+bool conv_tc_supported(int H, int W, int Kc, int Nc);
+size_t conv_tc_scratch_bytes(int B, int H, int W, int Kc, int Nc);
+
+// dgrad == 0: out[B,H,W,Cout] = conv3x3(in[B,H,W,Cin], w[Cout][Cin][3][3]) + bias      (channels-last fp32)
+// dgrad == 1: out[B,H,W,Cin]  = conv3x3_transposed(in = dY[B,H,W,Cout], w)             (bias ignored: pass null)
+int conv_tc_forward(const float* in, const float* w, const float* bias, float* out, int B, int H, int W, int Cin,
+                    int Cout, int dgrad, void* scratch, size_t scratch_bytes, cudaStream_t st);
+
+}  // namespace sedb200
