@@ -129,6 +129,8 @@ typedef struct sedb200_crnn_desc {
     float dropout;                     /* crnn_lightning.py:52 / sed.py:92 */
     int   dropout_each_block;          /* sed.py:107 applies it after every block */
     float bn_eps, bn_momentum;         /* nn.BatchNorm2d defaults 1e-5 / 0.1 */
+    int   tensor_cores;                /* 1: conv contractions on tcgen05 (3-term bf16 split, fp32-grade) wherever the
+                                          shape allows (channels % 128 == 0, W | 128); 0: fp32 CUDA cores everywhere */
 } sedb200_crnn_desc;
 
 /* geometry helpers (host only, no GPU needed) */
@@ -190,6 +192,11 @@ size_t sedb200_conv3x3_tc_scratch_bytes(int B, int H, int W, int Cin, int Cout);
 int    sedb200_conv3x3_tc(const float* in_dev, const float* weight_dev, const float* bias_dev, float* out_dev,
                           int B, int H, int W, int Cin, int Cout, int dgrad, void* scratch_dev,
                           size_t scratch_bytes, void* stream);
+/* weight gradient of the same convolution: dw [Cout][Cin][3][3] from dy [B][H][W][Cout] and in
+ * [B][H][W][Cin].  Supported: Cin % 128 == 0, Cout % 128 == 0, W a divisor of 32. */
+size_t sedb200_conv3x3_wgrad_tc_scratch_bytes(int B, int H, int W, int Cin, int Cout);
+int    sedb200_conv3x3_wgrad_tc(const float* dy_dev, const float* in_dev, float* dw_dev, int B, int H, int W,
+                                int Cin, int Cout, void* scratch_dev, size_t scratch_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -51,6 +51,8 @@ SIGNATURES = {
     "sedb200_clip_adam": (_i, [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _l, _f, _f, _p, _p, _sz, _p]),
     "sedb200_threshold_counts": (_i, [_p, _p, _l, _i, _i, _f, _p, _p]),
     "sedb200_conv3x3_tc_scratch_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "sedb200_conv3x3_wgrad_tc_scratch_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "sedb200_conv3x3_wgrad_tc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),
     "sedb200_conv3x3_tc": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _sz, _p]),
 }
 
@@ -60,7 +62,7 @@ class CrnnDesc(C.Structure):
     _fields_ = [("mode", _i), ("in_ch", _i), ("H", _i), ("W", _i), ("n_conv", _i), ("conv_ch", _i),
                 ("pool", _i * 4), ("n_gru", _i), ("gru_units", _i * 4), ("n_dense", _i),
                 ("dense_units", _i * 3), ("dense_relu", _i), ("dropout", _f), ("dropout_each_block", _i),
-                ("bn_eps", _f), ("bn_momentum", _f)]
+                ("bn_eps", _f), ("bn_momentum", _f), ("tensor_cores", _i)]
 
 
 def header_symbols() -> list[str]:

@@ -29,6 +29,7 @@ class CRNNConfig:
     dropout_each_block: bool = False       # sed.py:107 -> True
     bn_eps: float = 1e-5
     bn_momentum: float = 0.1
+    tensor_cores: bool = True              # conv contractions on tcgen05 (3-term bf16 split) where the shape allows
 
     # ---- geometry
     @property
@@ -74,6 +75,7 @@ class CRNNConfig:
         d.dropout = float(self.dropout)
         d.dropout_each_block = int(self.dropout_each_block)
         d.bn_eps, d.bn_momentum = float(self.bn_eps), float(self.bn_momentum)
+        d.tensor_cores = int(self.tensor_cores)
         return d
 
     # ---- flat-parameter layout (canonical tensor names, shapes and offsets)

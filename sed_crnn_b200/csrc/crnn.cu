@@ -9,6 +9,7 @@
 #include "crnn_plan.cuh"
 #include "gemm_simt.cuh"
 #include "gru_scan.cuh"
+#include "tc_conv.cuh"
 
 #include <algorithm>
 
@@ -401,8 +402,12 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
         const int M = (int)(B * P.H * P.win[i]), K = 9 * P.cin[i];
         float* y = wsf(ws, P.y[i]);
 { char _nm[40]; snprintf(_nm, sizeof _nm, "conv%d.fwd", i); SED_PROF(_nm, st);
-        rc = gemm_simt(M, P.C, K, 1, ConvFwdA{in, P.H, P.win[i], P.cin[i], s.sB, s.sH, s.sW, s.sC},
-                       ConvFwdB{params + P.conv_w[i], P.cin[i]}, EpiStore{y, P.C, params + P.conv_b[i], 0}, st);
+        if (i > 0 && d->tensor_cores && conv_tc_supported(P.H, P.win[i], P.cin[i], P.C))
+            rc = conv_tc_forward(in, params + P.conv_w[i], params + P.conv_b[i], y, batch, P.H, P.win[i], P.cin[i], P.C,
+                                 0, wsf(ws, P.tc), P.tc_bytes, st);
+        else
+            rc = gemm_simt(M, P.C, K, 1, ConvFwdA{in, P.H, P.win[i], P.cin[i], s.sB, s.sH, s.sW, s.sC},
+                           ConvFwdB{params + P.conv_w[i], P.cin[i]}, EpiStore{y, P.C, params + P.conv_b[i], 0}, st);
         if (rc) return rc;
 }
         float* stat = wsf(ws, P.stat[i]);
@@ -582,18 +587,27 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         const int want = std::max(1, std::min(64, M / 2048));
         const int sp = gemm_simt_splits(M, want);
 { char _nm[40]; snprintf(_nm, sizeof _nm, "conv%d.wgrad", i); SED_PROF(_nm, st);
+        if (i > 0 && d->tensor_cores && wgrad_tc_supported(P.H, P.win[i], P.cin[i], P.C)) {
+            rc = wgrad_tc(dy, in, grads + P.conv_w[i], batch, P.H, P.win[i], P.cin[i], P.C, wsf(ws, P.tc), P.tc_bytes, st);
+            if (rc) return rc;
+        } else {
         rc = gemm_simt(P.C, J, M, want, ColMajor{dy, P.C}, ConvWgradB{in, P.H, P.win[i], s.sB, s.sH, s.sW, s.sC},
                        EpiPartial{part, (long)P.C * J, J}, st);
         if (rc) return rc;
         rc = reduce_partials(part, grads + P.conv_w[i], (long)P.C * J, sp, st);
         if (rc) return rc;
+        }
 }
         // dgrad
         if (i > 0) {
             float* dprev = wsf(ws, P.dact[i & 1]);
 { char _nm[40]; snprintf(_nm, sizeof _nm, "conv%d.dgrad", i); SED_PROF(_nm, st);
-            rc = gemm_simt(M, P.cin[i], 9 * P.C, 1, ConvDgradA{dy, P.H, P.win[i], P.C},
-                           ConvDgradB{params + P.conv_w[i], P.cin[i], P.C}, EpiStore{dprev, P.cin[i], nullptr, 0}, st);
+            if (d->tensor_cores && conv_tc_supported(P.H, P.win[i], P.C, P.cin[i]))
+                rc = conv_tc_forward(dy, params + P.conv_w[i], nullptr, dprev, batch, P.H, P.win[i], P.cin[i], P.C, 1,
+                                     wsf(ws, P.tc), P.tc_bytes, st);
+            else
+                rc = gemm_simt(M, P.cin[i], 9 * P.C, 1, ConvDgradA{dy, P.H, P.win[i], P.C},
+                               ConvDgradB{params + P.conv_w[i], P.cin[i], P.C}, EpiStore{dprev, P.cin[i], nullptr, 0}, st);
             if (rc) return rc;
 }
             dA = dprev;

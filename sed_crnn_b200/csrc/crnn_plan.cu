@@ -1,6 +1,7 @@
 // crnn_plan.cu -- host-side geometry / layout helpers of the CRNN C ABI (no GPU needed).
 #include "crnn_plan.cuh"
 #include "gemm_simt.cuh"
+#include "tc_conv.cuh"
 
 #include <algorithm>
 
@@ -131,6 +132,16 @@ int make_plan(const sedb200_crnn_desc* d, int batch, Plan* p) {
     for (int j = 0; j < P.n_dense; ++j) part = std::max(part, 64L * P.dout[j] * P.din[j]);
     P.part_floats = (size_t)part;
     P.part = take(part);
+    // tensor-core scratch: bf16 operand planes + wgrad split-K partials
+    size_t tc = 0;
+    if (d->tensor_cores)
+        for (int i = 1; i < P.n_conv; ++i) {
+            if (conv_tc_supported(P.H, P.win[i], P.cin[i], P.C)) tc = std::max(tc, conv_tc_scratch_bytes(batch, P.H, P.win[i], P.cin[i], P.C));
+            if (conv_tc_supported(P.H, P.win[i], P.C, P.cin[i])) tc = std::max(tc, conv_tc_scratch_bytes(batch, P.H, P.win[i], P.C, P.cin[i]));
+            if (wgrad_tc_supported(P.H, P.win[i], P.cin[i], P.C)) tc = std::max(tc, wgrad_tc_scratch_bytes(batch, P.H, P.win[i], P.cin[i], P.C));
+        }
+    P.tc_bytes = tc;
+    P.tc = take((long)(tc / 4) + 64);
     P.ws_bytes = o;
     return SEDB200_OK;
 }

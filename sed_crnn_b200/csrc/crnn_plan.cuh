@@ -23,7 +23,8 @@ struct Plan {
     size_t y[SEDB200_MAX_CONV], stat[SEDB200_MAX_CONV], act[SEDB200_MAX_CONV];   // act[i] = output of block i
     size_t gi[SEDB200_MAX_GRU], gout[SEDB200_MAX_GRU], gates[SEDB200_MAX_GRU];
     size_t hid[SEDB200_MAX_DENSE];
-    size_t dy, dact[2], dseq[2], dgi, dgh, dhid[2], part, bnsum;
+    size_t dy, dact[2], dseq[2], dgi, dgh, dhid[2], part, bnsum, tc;
+    size_t tc_bytes = 0;
     size_t part_floats = 0;
     size_t ws_bytes = 0;
 };

@@ -226,6 +226,155 @@ weight_planes_kernel(const float* __restrict__ w, int Cout, int Cin, int dgrad, 
     }
 }
 
+
+// ====================================================================================== wgrad
+// dW[co][ci][tap] = sum_p dY[p][co] * In[p + shift(tap)][ci]
+//
+// One GEMM per tap with the PIXEL index as K: both operands are "MN-major" (for a fixed pixel the
+// 64 channels are contiguous), which tcgen05 consumes directly from the same NHWC planes -- no
+// transposes.  A K-block is 32 pixels (Hk = 32/W image rows): dY box {64 co, W, Hk, 1} and, per tap,
+// the In box shifted by the tap (TMA zero-fill = padding).  A CTA owns (co-tile, ci-tile, tap row r,
+// K-slice): the three taps (r, 0..2) share every dY tile and accumulate into three 128-column TMEM
+// accumulators.  Per-slice partials are reduced afterwards in a fixed order (deterministic).
+constexpr int kWgKp = 32;                                   // pixels per K-block
+constexpr int kWgBox = kWgKp * 128;                         // 4 KB: one {64 ch x 32 px} bf16 box
+constexpr int kWgABytes = 4 * kWgBox;                       // dY: 2 channel halves x (hi, lo)
+constexpr int kWgBBytes = 4 * kWgBox;                       // In (one tap): 2 channel halves x (hi, lo)
+constexpr int kWgStageBytes = kWgABytes + 3 * kWgBBytes;    // 64 KB
+constexpr int kWgSmemBytes = kStages * kWgStageBytes + 1024 + 256;
+constexpr uint32_t kWgTmemCols = 512;
+
+struct WgradTcParams {
+    int B, H, W, Hk, hblocks_per_img, total_kblocks, n_mt, n_nt, slices;
+    float* part;             // [slices][9][Cout][Cin]
+    int Cout, Cin;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
+                const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
+                const WgradTcParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kWgStageBytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kStages;
+    uint64_t* tfull = bars + 2 * kStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmY_hi); prefetch_tmap(&tmY_lo); prefetch_tmap(&tmX_hi); prefetch_tmap(&tmX_lo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, kWgTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // work item of this CTA
+    int w = blockIdx.x;
+    const int slice = w % p.slices; w /= p.slices;
+    const int r = w % 3; w /= 3;
+    const int nt = w % p.n_nt, mt = w / p.n_nt;
+    const int kb_per = (p.total_kblocks + p.slices - 1) / p.slices;
+    const int kb0 = slice * kb_per, kb1 = min(p.total_kblocks, kb0 + kb_per);
+
+    if (warp == 0 && lane == 0) {
+        int stage = 0; uint32_t phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            const int b = kb / p.hblocks_per_img, h0 = (kb % p.hblocks_per_img) * p.Hk;
+            mbar_wait(empty + stage, phase ^ 1);
+            unsigned char* st = smem + stage * kWgStageBytes;
+            mbar_expect_tx(full + stage, kWgStageBytes);
+            for (int half = 0; half < 2; ++half) {
+                tma_load_4d(st + half * kWgBox, &tmY_hi, full + stage, mt * 128 + half * 64, 0, h0, b);
+                tma_load_4d(st + (2 + half) * kWgBox, &tmY_lo, full + stage, mt * 128 + half * 64, 0, h0, b);
+            }
+            for (int s = 0; s < 3; ++s) {
+                unsigned char* bt = st + kWgABytes + s * kWgBBytes;
+                for (int half = 0; half < 2; ++half) {
+                    tma_load_4d(bt + half * kWgBox, &tmX_hi, full + stage, nt * 128 + half * 64, s - 1, h0 + r - 1, b);
+                    tma_load_4d(bt + (2 + half) * kWgBox, &tmX_lo, full + stage, nt * 128 + half * 64, s - 1, h0 + r - 1, b);
+                }
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1 && lane == 0) {
+        constexpr uint32_t idesc = idesc_bf16(128, 128, 1, 1);      // both operands MN-major
+        int stage = 0; uint32_t phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(full + stage, phase);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(smem + stage * kWgStageBytes), a_lo = a_hi + 2 * kWgBox;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const uint32_t b_hi = a_hi + kWgABytes + s * kWgBBytes, b_lo = b_hi + 2 * kWgBox;
+                const uint32_t d = tmem_base + s * 128;
+#pragma unroll
+                for (int k = 0; k < kWgKp / 16; ++k) {
+                    const uint64_t dah = smem_desc_sw128(a_hi + k * 2048, kWgBox, 1024), dal = smem_desc_sw128(a_lo + k * 2048, kWgBox, 1024);
+                    const uint64_t dbh = smem_desc_sw128(b_hi + k * 2048, kWgBox, 1024), dbl = smem_desc_sw128(b_lo + k * 2048, kWgBox, 1024);
+                    mma_bf16(d, dah, dbh, idesc, (kb != kb0 || k != 0));
+                    mma_bf16(d, dah, dbl, idesc, 1);
+                    mma_bf16(d, dal, dbh, idesc, 1);
+                }
+            }
+            mma_commit(empty + stage);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        mma_commit(tfull);
+    } else if (warp >= 4) {
+        const int q = warp - 4;
+        const int co = mt * 128 + q * 32 + lane;
+        if (kb1 > kb0) {
+            mbar_wait(tfull, 0);
+            tc_fence_after();
+        }
+        for (int s = 0; s < 3; ++s) {
+            float* dst = p.part + (((long)slice * 9 + (r * 3 + s)) * p.Cout + co) * p.Cin + nt * 128;
+#pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) {
+                float v[32];
+                if (kb1 > kb0) {
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + s * 128 + cc * 32, v);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(dst + cc * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kWgTmemCols);
+    }
+}
+
+// dW[co][ci][tap] = sum_slice part[slice][tap][co][ci]
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ part, int slices, int Cout, int Cin, float* __restrict__ dw) {
+    const long n = 9L * Cout * Cin;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % Cin);
+        const int co = (int)((i / Cin) % Cout);
+        const int tap = (int)(i / ((long)Cin * Cout));
+        float acc = 0.0f;
+        for (int z = 0; z < slices; ++z) acc += __ldg(part + (long)z * n + i);
+        dw[((long)co * Cin + ci) * 9 + tap] = acc;
+    }
+}
+
 }  // namespace
 
 size_t conv_tc_scratch_bytes(int B, int H, int W, int Cin, int Cout) {
@@ -297,6 +446,82 @@ int conv_tc_forward(const float* in, const float* w, const float* bias, float* o
     return SEDB200_OK;
 }
 
+
+bool wgrad_tc_supported(int H, int W, int Cin, int Cout) {
+    return Cin % 128 == 0 && Cout % 128 == 0 && W >= 1 && W <= 32 && (32 % W) == 0 && H >= 1;
+}
+
+static int wgrad_slices(int Cin, int Cout) {
+    const int items = (Cout / 128) * (Cin / 128) * 3;
+    return std::max(1, sm_count() / items);
+}
+
+size_t wgrad_tc_scratch_bytes(int B, int H, int W, int Cin, int Cout) {
+    const size_t px = (size_t)B * H * W;
+    const size_t planes = 2 * ((px * Cout * 2 + 1023) & ~(size_t)1023) + 2 * ((px * Cin * 2 + 1023) & ~(size_t)1023);
+    return planes + (size_t)wgrad_slices(Cin, Cout) * 9 * Cout * Cin * 4;
+}
+
+// dw[Cout][Cin][3][3] = wgrad(dy[B,H,W,Cout], in[B,H,W,Cin]); if the bf16 planes already exist they can be
+// passed in (null -> they are produced here from the fp32 tensors)
+int wgrad_tc(const float* dy, const float* in, float* dw, int B, int H, int W, int Cin, int Cout, void* scratch,
+             size_t scratch_bytes, cudaStream_t st) {
+    SED_REQUIRE(wgrad_tc_supported(H, W, Cin, Cout), SEDB200_ESHAPE, "wgrad_tc: shape H=%d W=%d Cin=%d Cout=%d unsupported", H, W, Cin, Cout);
+    SED_REQUIRE(scratch_bytes >= wgrad_tc_scratch_bytes(B, H, W, Cin, Cout), SEDB200_EWORKSPACE, "wgrad_tc: scratch too small");
+    const size_t px = (size_t)B * H * W;
+    const size_t ysz = (px * Cout * 2 + 1023) & ~(size_t)1023, xsz = (px * Cin * 2 + 1023) & ~(size_t)1023;
+    char* s = reinterpret_cast<char*>(scratch);
+    __nv_bfloat16* y_hi = reinterpret_cast<__nv_bfloat16*>(s);
+    __nv_bfloat16* y_lo = reinterpret_cast<__nv_bfloat16*>(s + ysz);
+    __nv_bfloat16* x_hi = reinterpret_cast<__nv_bfloat16*>(s + 2 * ysz);
+    __nv_bfloat16* x_lo = reinterpret_cast<__nv_bfloat16*>(s + 2 * ysz + xsz);
+    float* part = reinterpret_cast<float*>(s + 2 * ysz + 2 * xsz);
+    long n4 = (long)px * Cout / 4;
+    split_planes_kernel<<<(int)std::min<long>((n4 + 255) / 256, 148L * 8), 256, 0, st>>>(dy, y_hi, y_lo, n4);
+    SED_POST_LAUNCH();
+    n4 = (long)px * Cin / 4;
+    split_planes_kernel<<<(int)std::min<long>((n4 + 255) / 256, 148L * 8), 256, 0, st>>>(in, x_hi, x_lo, n4);
+    SED_POST_LAUNCH();
+
+    const int Hk = kWgKp / W;
+    CUtensorMap tmY_hi, tmY_lo, tmX_hi, tmX_lo;
+    const uint32_t box[4] = {64, (uint32_t)W, (uint32_t)Hk, 1};
+    {
+        const uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+        const uint64_t strides[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
+        int rc = encode_tmap_bf16(&tmY_hi, y_hi, 4, dims, strides, box);
+        if (rc) return rc;
+        rc = encode_tmap_bf16(&tmY_lo, y_lo, 4, dims, strides, box);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+        const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+        int rc = encode_tmap_bf16(&tmX_hi, x_hi, 4, dims, strides, box);
+        if (rc) return rc;
+        rc = encode_tmap_bf16(&tmX_lo, x_lo, 4, dims, strides, box);
+        if (rc) return rc;
+    }
+    WgradTcParams p;
+    p.B = B; p.H = H; p.W = W; p.Hk = Hk;
+    p.hblocks_per_img = (H + Hk - 1) / Hk;
+    p.total_kblocks = B * p.hblocks_per_img;
+    p.n_mt = Cout / 128; p.n_nt = Cin / 128;
+    p.slices = std::min(wgrad_slices(Cin, Cout), p.total_kblocks);
+    p.part = part; p.Cout = Cout; p.Cin = Cin;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SED_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
+        attr_done = true;
+    }
+    const int grid = p.n_mt * p.n_nt * 3 * p.slices;
+    wgrad_tc_kernel<<<grid, kThreads, kWgSmemBytes, st>>>(tmY_hi, tmY_lo, tmX_hi, tmX_lo, p);
+    SED_POST_LAUNCH();
+    wgrad_reduce_kernel<<<(int)std::min<long>((9L * Cout * Cin + 255) / 256, 1184), 256, 0, st>>>(part, p.slices, Cout, Cin, dw);
+    SED_POST_LAUNCH();
+    return SEDB200_OK;
+}
+
 }  // namespace sedb200
 
 using namespace sedb200;
@@ -316,6 +541,19 @@ int sedb200_conv3x3_tc(const float* in_dev, const float* weight_dev, const float
     if (rc) return rc;
     return conv_tc_forward(in_dev, weight_dev, bias_dev, out_dev, B, H, W, Cin, Cout, dgrad, scratch_dev,
                            scratch_bytes, as_stream(stream));
+}
+
+size_t sedb200_conv3x3_wgrad_tc_scratch_bytes(int B, int H, int W, int Cin, int Cout) {
+    return wgrad_tc_scratch_bytes(B, H, W, Cin, Cout);
+}
+
+int sedb200_conv3x3_wgrad_tc(const float* dy_dev, const float* in_dev, float* dw_dev, int B, int H, int W, int Cin,
+                             int Cout, void* scratch_dev, size_t scratch_bytes, void* stream) {
+    SED_REQUIRE(dy_dev && in_dev && dw_dev && scratch_dev, SEDB200_EINVAL, "conv3x3_wgrad_tc: null buffer");
+    SED_REQUIRE(B >= 1, SEDB200_EINVAL, "conv3x3_wgrad_tc: batch %d", B);
+    int rc = require_sm100();
+    if (rc) return rc;
+    return wgrad_tc(dy_dev, in_dev, dw_dev, B, H, W, Cin, Cout, scratch_dev, scratch_bytes, as_stream(stream));
 }
 
 }  // extern "C"

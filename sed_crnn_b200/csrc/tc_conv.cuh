@@ -13,4 +13,11 @@ size_t conv_tc_scratch_bytes(int B, int H, int W, int Kc, int Nc);
 int conv_tc_forward(const float* in, const float* w, const float* bias, float* out, int B, int H, int W, int Cin,
                     int Cout, int dgrad, void* scratch, size_t scratch_bytes, cudaStream_t st);
 
+// dw[Cout][Cin][3][3] = sum over pixels of dy[B,H,W,Cout] (x) shifted in[B,H,W,Cin]
+// shapes: Cin % 128 == 0, Cout % 128 == 0, W a divisor of 32
+bool wgrad_tc_supported(int H, int W, int Cin, int Cout);
+size_t wgrad_tc_scratch_bytes(int B, int H, int W, int Cin, int Cout);
+int wgrad_tc(const float* dy, const float* in, float* dw, int B, int H, int W, int Cin, int Cout, void* scratch,
+             size_t scratch_bytes, cudaStream_t st);
+
 }  // namespace sedb200

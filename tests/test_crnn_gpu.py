@@ -201,3 +201,23 @@ def test_threshold_counts_match_metrics(pkg, golden_dir):
         with np.errstate(all="ignore"):
             got = np.array(PM.scores_from_counts(c))
         assert np.array_equal(got, want, equal_nan=True), (n, got, want)
+
+
+def test_tensor_core_and_fp32_paths_agree(pkg):
+    """conv contractions on tcgen05 (3-term bf16 split) vs the fp32 CUDA-core path: same step, ~1e-5."""
+    config, engine = pkg
+    outs = {}
+    for tc in (False, True):
+        rcfg = {**R.PRESETS["c2"], "seq_len": 32}
+        torch.manual_seed(0)
+        ref = R.RefCRNN(**rcfg)
+        eng = engine.CRNNEngine(replace(config.C2, seq_len=32, dropout=0.0, tensor_cores=tc), loss="bce")
+        eng.load_named({k: v.detach() for k, v in ref.canonical_named_params()})
+        x, y = R.synth_batch(rcfg, 8, seed=2)
+        logits = eng.forward(x.cuda(), training=True).clone()
+        loss, probs, dlog = eng.loss_and_grad(logits, y.cuda())
+        eng.backward(x.cuda(), dlog)
+        outs[tc] = (logits, eng.grads.clone())
+    assert (outs[True][0] - outs[False][0]).abs().max().item() < 2e-5
+    g0, g1 = outs[False][1], outs[True][1]
+    assert (g1 - g0).abs().max().item() <= 1e-4 * g0.abs().max().item()

@@ -56,3 +56,25 @@ def test_dgrad_matches_autograd(L, B, H, W, Cin, Cout):
     got = run_tc(L, dy.permute(0, 2, 3, 1).contiguous().cuda(), w.cuda(), None, True).cpu().double()
     err = (got - want).abs().max().item() / want.abs().max().item()
     assert err < 2e-5, err
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 32, 8, 128, 128), (3, 10, 16, 128, 128), (2, 16, 4, 256, 128),
+                                            (1, 5, 32, 128, 256), (7, 64, 8, 128, 128)])
+def test_wgrad_matches_autograd(L, B, H, W, Cin, Cout):
+    from sed_crnn_b200 import _lib
+    g = torch.Generator().manual_seed(11 + H)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.zeros(Cout, Cin, 3, 3, dtype=torch.float64, requires_grad=True)
+    dy = torch.randn(B, Cout, H, W, generator=g)
+    F.conv2d(x.double(), w, None, padding=1).backward(dy.double())
+    want = w.grad
+    dw = torch.empty(Cout, Cin, 3, 3, device="cuda")
+    nbytes = L.sedb200_conv3x3_wgrad_tc_scratch_bytes(B, H, W, Cin, Cout)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    xd = x.permute(0, 2, 3, 1).contiguous().cuda()
+    dyd = dy.permute(0, 2, 3, 1).contiguous().cuda()
+    _lib.check(L.sedb200_conv3x3_wgrad_tc(dyd.data_ptr(), xd.data_ptr(), dw.data_ptr(), B, H, W, Cin, Cout,
+                                          scratch.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    err = (dw.cpu().double() - want).abs().max().item() / want.abs().max().item()
+    assert err < 2e-5, err
