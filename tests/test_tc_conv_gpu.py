@@ -33,7 +33,8 @@ def run_tc(L, x_nhwc, w, bias, dgrad):
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 32, 8, 64, 128), (1, 40, 32, 128, 128), (3, 16, 4, 128, 128),
-                                            (2, 7, 16, 64, 256), (5, 256, 8, 128, 128), (1, 3, 128, 64, 128)])
+                                            (2, 7, 16, 64, 256), (5, 256, 8, 128, 128), (1, 3, 128, 64, 128),
+                                            (21, 256, 8, 64, 128)])          # 336 tiles: > 2 per CTA
 def test_forward_matches_float64_conv(L, B, H, W, Cin, Cout):
     g = torch.Generator().manual_seed(B * 1000 + H)
     x = torch.randn(B, Cin, H, W, generator=g)
