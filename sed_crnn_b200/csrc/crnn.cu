@@ -122,17 +122,35 @@ struct EpiStrided {                     // dx in NCHW from m = (b,h,w), n = ci
 
 // ----------------------------------------------------------------------------- BatchNorm statistics
 // stat layout: [0,C) mean, [C,2C) invstd, [2C,3C) scale = gamma*invstd, [3C,4C) shift = beta - mean*scale
+// deterministic warp-per-channel reduction of the per-block partials [nblk][2][C] (fixed lane
+// assignment + fixed shuffle tree => bit-reproducible)
+__device__ __forceinline__ void reduce_pair(const float* __restrict__ part, int nblk, int C, int c, double& s,
+                                            double& ss) {
+    const int lane = threadIdx.x & 31;
+    double a = 0.0, b = 0.0;
+    for (int k = lane; k < nblk; k += 32) {
+        a += (double)__ldg(part + ((long)k * 2 + 0) * C + c);
+        b += (double)__ldg(part + ((long)k * 2 + 1) * C + c);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    s = a;
+    ss = b;
+}
+
+// one warp per channel
 __global__ void bn_finalize_train_kernel(const float* __restrict__ part, int nblk, int C, long n,
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                          float eps, float momentum, float* __restrict__ running,
                                          float* __restrict__ stat) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (c >= C) return;
-    double s = 0.0, ss = 0.0;
-    for (int k = 0; k < nblk; ++k) {
-        s += (double)part[((long)k * 2 + 0) * C + c];
-        ss += (double)part[((long)k * 2 + 1) * C + c];
-    }
+    double s, ss;
+    reduce_pair(part, nblk, C, c, s, ss);
+    if ((threadIdx.x & 31) != 0) return;
     const double mean = s / (double)n;
     double var = ss / (double)n - mean * mean;          // biased (normalisation)
     if (var < 0.0) var = 0.0;
@@ -298,13 +316,11 @@ bn_pool_bwd_sums_kernel(const float* __restrict__ y, const float* __restrict__ s
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nblk, int C, long n,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        float* __restrict__ bnsum) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per channel
     if (c >= C) return;
-    double s = 0.0, sx = 0.0;
-    for (int k = 0; k < nblk; ++k) {
-        s += (double)part[((long)k * 2 + 0) * C + c];
-        sx += (double)part[((long)k * 2 + 1) * C + c];
-    }
+    double s, sx;
+    reduce_pair(part, nblk, C, c, s, sx);
+    if ((threadIdx.x & 31) != 0) return;
     dbeta[c] = (float)s;
     dgamma[c] = (float)sx;
     bnsum[c] = (float)(s / (double)n);
@@ -346,6 +362,172 @@ bn_pool_bwd_dy_kernel(const float* __restrict__ y, const float* __restrict__ sta
         }
     }
 }
+
+
+// ----------------------------------------------------------------------------- first conv block, direct
+// conv block 0 has K = 9*Cin = 9 or 18: a degenerate GEMM whose cost is the 4 B x B*H*W*C activation it
+// produces, not its FLOPs.  Two direct fp32 kernels keep that tensor's HBM traffic at the minimum:
+//   forward : conv + bias -> y0 (one write) with the BatchNorm statistics accumulated on the fly
+//   backward: BN/ReLU/pool backward recomputed from y0 and consumed IN REGISTERS by the weight-gradient
+//             accumulation -- dy0 is never written (conv 0 needs no data gradient).
+// Thread mapping: lane <-> 4 consecutive output channels (weights / dW live in registers for the whole
+// kernel), warp <-> one image row, block <-> 8 rows; the input rows (with zero halo) sit in shared memory
+// and are read as warp-wide broadcasts; every y0 access is a 512 B coalesced row of 128 channels.
+constexpr int kC0Rows = 8;
+
+template <int CIN>
+__device__ __forceinline__ void load_x_rows(const float* __restrict__ x, float* xs, int b, int h0, int H, int W) {
+    const int Wp = W + 2;
+    for (int idx = threadIdx.x; idx < CIN * (kC0Rows + 2) * Wp; idx += blockDim.x) {
+        const int cc = idx % Wp, rr = (idx / Wp) % (kC0Rows + 2), ci = idx / (Wp * (kC0Rows + 2));
+        const int hh = h0 - 1 + rr, ww = cc - 1;
+        xs[idx] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(x + (((long)b * CIN + ci) * H + hh) * W + ww) : 0.0f;
+    }
+}
+
+template <int CIN>
+__global__ void __launch_bounds__(256)
+conv0_fwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                       float* __restrict__ y, int H, int W, int C, float* __restrict__ part) {
+    extern __shared__ float xs[];                         // [CIN][10][W+2]
+    __shared__ float red[kC0Rows][2][128];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y, h0 = blockIdx.x * kC0Rows, c = blockIdx.z * 128 + lane * 4, Wp = W + 2;
+    load_x_rows<CIN>(x, xs, b, h0, H, W);
+    float wr[4][CIN * 9], bs[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        bs[q] = __ldg(bias + c + q);
+#pragma unroll
+        for (int k = 0; k < CIN * 9; ++k) wr[q][k] = __ldg(w + (long)(c + q) * CIN * 9 + k);
+    }
+    __syncthreads();
+    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    const int h = h0 + warp;
+    if (h < H) {
+        float* yrow = y + ((long)b * H + h) * W * C + c;
+        for (int ww = 0; ww < W; ++ww) {
+            float acc[4] = {bs[0], bs[1], bs[2], bs[3]};
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        const float xv = xs[(ci * (kC0Rows + 2) + warp + r) * Wp + ww + t];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[q] = fmaf(wr[q][ci * 9 + r * 3 + t], xv, acc[q]);
+                    }
+            *reinterpret_cast<float4*>(yrow + (long)ww * C) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { s1[q] += acc[q]; s2[q] = fmaf(acc[q], acc[q], s2[q]); }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { red[warp][0][lane * 4 + q] = s1[q]; red[warp][1][lane * 4 + q] = s2[q]; }
+    __syncthreads();
+    {
+        const int which = threadIdx.x >> 7, ch = threadIdx.x & 127;
+        float t = 0.0f;
+#pragma unroll
+        for (int r = 0; r < kC0Rows; ++r) t += red[r][which][ch];
+        const long blk = (long)blockIdx.y * gridDim.x + blockIdx.x;
+        part[(blk * 2 + which) * C + blockIdx.z * 128 + ch] = t;
+    }
+}
+
+// part layout: [nblk][CIN*9 + 1][C]   (slot CIN*9 = bias gradient)
+template <int CIN>
+__global__ void __launch_bounds__(256)
+conv0_bwd_fused_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ stat,
+                       const float* __restrict__ dA, const float* __restrict__ bnsum, PoolGeom g,
+                       float* __restrict__ part) {
+    extern __shared__ float xs[];
+    __shared__ float red[kC0Rows][128];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y, h0 = blockIdx.x * kC0Rows, c4 = blockIdx.z * 32 + lane, c = c4 * 4, Wp = g.W + 2;
+    const int C4 = g.C >> 2;
+    load_x_rows<CIN>(x, xs, b, h0, g.H, g.W);
+    const float4 sc = *reinterpret_cast<const float4*>(stat + 2 * g.C + c);
+    const float4 sh = *reinterpret_cast<const float4*>(stat + 3 * g.C + c);
+    const float4 mu = *reinterpret_cast<const float4*>(stat + c);
+    const float4 is = *reinterpret_cast<const float4*>(stat + g.C + c);
+    const float4 k1 = *reinterpret_cast<const float4*>(bnsum + c);
+    const float4 k2 = *reinterpret_cast<const float4*>(bnsum + g.C + c);
+    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, muv[4] = {mu.x, mu.y, mu.z, mu.w};
+    const float isv[4] = {is.x, is.y, is.z, is.w}, k1v[4] = {k1.x, k1.y, k1.z, k1.w}, k2v[4] = {k2.x, k2.y, k2.z, k2.w};
+    float dw[4][CIN * 9 + 1];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int k = 0; k <= CIN * 9; ++k) dw[q][k] = 0.0f;
+    __syncthreads();
+    const int h = h0 + warp;
+    if (h < g.H) {
+        for (int wo = 0; wo < g.Wo; ++wo) {
+            const long row = (((long)b * g.H + h) * g.W) + (long)wo * g.p;
+            const float* src = y + row * g.C + c;
+            const float* da = dA + (long)b * g.oB + (long)h * g.oH + (long)wo * g.oW + (long)c * g.oC;
+            const long i = (((long)b * g.H + h) * g.Wo + wo) * C4 + c4;
+            const WindowGrad wg = window_grad(src, da, sc, sh, g, i);
+            const int span = (wo == g.Wo - 1) ? g.W - wo * g.p : g.p;
+            for (int j = 0; j < span; ++j) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src + (long)j * g.C));
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+                float dyv[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    dyv[q] = scv[q] * ((wg.arg[q] == j && j < g.p ? wg.dz[q] : 0.0f) - k1v[q] - (vv[q] - muv[q]) * isv[q] * k2v[q]);
+                const int ww = wo * g.p + j;
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int t = 0; t < 3; ++t) {
+                            const float xv = xs[(ci * (kC0Rows + 2) + warp + r) * Wp + ww + t];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) dw[q][ci * 9 + r * 3 + t] = fmaf(dyv[q], xv, dw[q][ci * 9 + r * 3 + t]);
+                        }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) dw[q][CIN * 9] += dyv[q];
+            }
+        }
+    }
+    const long blk = (long)blockIdx.y * gridDim.x + blockIdx.x;
+#pragma unroll
+    for (int k = 0; k <= CIN * 9; ++k) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) red[warp][lane * 4 + q] = dw[q][k];
+        __syncthreads();
+        if (threadIdx.x < 128) {
+            float t = 0.0f;
+#pragma unroll
+            for (int r = 0; r < kC0Rows; ++r) t += red[r][threadIdx.x];
+            part[(blk * (CIN * 9 + 1) + k) * g.C + blockIdx.z * 128 + threadIdx.x] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// dW[c][j] = sum_blk part[blk][j][c] (j < J), db[c] = sum_blk part[blk][J][c]; one warp per output
+__global__ void conv0_bwd_reduce_kernel(const float* __restrict__ part, int nblk, int J, int C,
+                                        float* __restrict__ dw, float* __restrict__ db) {
+    const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (o >= (J + 1) * C) return;
+    const int j = o / C, c = o - j * C;
+    double a = 0.0;
+    for (int k = lane; k < nblk; k += 32) a += (double)__ldg(part + ((long)k * (J + 1) + j) * C + c);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+    if (lane == 0) {
+        if (j < J) dw[(long)c * J + j] = (float)a;
+        else db[c] = (float)a;
+    }
+}
+
+inline bool conv0_direct_ok(int cin, int C) { return (cin == 1 || cin == 2) && C % 128 == 0; }
+inline long conv0_blocks(int B, int H) { return (long)B * ((H + kC0Rows - 1) / kC0Rows); }
 
 inline int ew_blocks(long n) { return (int)std::min<long>((n + 255) / 256, 148L * 16); }
 
@@ -401,23 +583,37 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
         const InStrides s = in_strides(P, d, i);
         const int M = (int)(B * P.H * P.win[i]), K = 9 * P.cin[i];
         float* y = wsf(ws, P.y[i]);
-{ char _nm[40]; snprintf(_nm, sizeof _nm, "conv%d.fwd", i); SED_PROF(_nm, st);
-        if (i > 0 && d->tensor_cores && conv_tc_supported(P.H, P.win[i], P.cin[i], P.C))
-            rc = conv_tc_forward(in, params + P.conv_w[i], params + P.conv_b[i], y, batch, P.H, P.win[i], P.cin[i], P.C,
-                                 0, wsf(ws, P.tc), P.tc_bytes, st);
-        else
-            rc = gemm_simt(M, P.C, K, 1, ConvFwdA{in, P.H, P.win[i], P.cin[i], s.sB, s.sH, s.sW, s.sC},
-                           ConvFwdB{params + P.conv_w[i], P.cin[i]}, EpiStore{y, P.C, params + P.conv_b[i], 0}, st);
-        if (rc) return rc;
-}
         float* stat = wsf(ws, P.stat[i]);
         float* running = bn_state + 2L * i * P.C;
-{ char _nm[40]; snprintf(_nm, sizeof _nm, "bn%d.stats", i); SED_PROF(_nm, st);
-        if (training) {
-            int nblk = 0;
-            rc = colsum_partials(y, M, P.C, wsf(ws, P.part), &nblk, st);
+        const bool direct0 = (i == 0) && conv0_direct_ok(P.cin[0], P.C);
+        int nblk = 0;
+        { char _nm[40]; snprintf(_nm, sizeof _nm, "conv%d.fwd", i); SED_PROF(_nm, st);
+        if (direct0) {
+            const dim3 grid((P.H + kC0Rows - 1) / kC0Rows, batch, P.C / 128);
+            const size_t sm = (size_t)P.cin[0] * (kC0Rows + 2) * (P.win[0] + 2) * 4;
+            if (P.cin[0] == 1)
+                conv0_fwd_stats_kernel<1><<<grid, 256, sm, st>>>(x, params + P.conv_w[0], params + P.conv_b[0], y, P.H, P.win[0], P.C, wsf(ws, P.part));
+            else
+                conv0_fwd_stats_kernel<2><<<grid, 256, sm, st>>>(x, params + P.conv_w[0], params + P.conv_b[0], y, P.H, P.win[0], P.C, wsf(ws, P.part));
+            SED_POST_LAUNCH();
+            nblk = (int)(grid.x * grid.y);
+        } else if (i > 0 && d->tensor_cores && conv_tc_supported(P.H, P.win[i], P.cin[i], P.C)) {
+            rc = conv_tc_forward(in, params + P.conv_w[i], params + P.conv_b[i], y, batch, P.H, P.win[i], P.cin[i], P.C,
+                                 0, wsf(ws, P.tc), P.tc_bytes, st);
             if (rc) return rc;
-            bn_finalize_train_kernel<<<(P.C + 127) / 128, 128, 0, st>>>(
+        } else {
+            rc = gemm_simt(M, P.C, K, 1, ConvFwdA{in, P.H, P.win[i], P.cin[i], s.sB, s.sH, s.sW, s.sC},
+                           ConvFwdB{params + P.conv_w[i], P.cin[i]}, EpiStore{y, P.C, params + P.conv_b[i], 0}, st);
+            if (rc) return rc;
+        }
+        }
+        { char _nm[40]; snprintf(_nm, sizeof _nm, "bn%d.stats", i); SED_PROF(_nm, st);
+        if (training) {
+            if (!direct0) {
+                rc = colsum_partials(y, M, P.C, wsf(ws, P.part), &nblk, st);
+                if (rc) return rc;
+            }
+            bn_finalize_train_kernel<<<(P.C * 32 + 255) / 256, 256, 0, st>>>(
                 wsf(ws, P.part), nblk, P.C, (long)M, params + P.bn_w[i], params + P.bn_b[i], d->bn_eps,
                 d->bn_momentum, running, stat);
         } else {
@@ -425,7 +621,7 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
                                                                        d->bn_eps, running, stat);
         }
         SED_POST_LAUNCH();
-}
+        }
         const PoolGeom g = pool_geom(P, d, i, training, seed);
         const long n_vec = B * P.H * P.wout[i] * (P.C / 4);
 { char _nm[40]; snprintf(_nm, sizeof _nm, "pool%d.fwd", i); SED_PROF(_nm, st);
@@ -561,15 +757,31 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         const long n_pix_out = B * P.H * P.wout[i];
         const long n_elem = B * P.H * P.win[i];                 // BN population per channel
         const int rows = 256 / (P.C / 4);
-        const int nblk = (int)std::min<long>((n_pix_out + rows - 1) / rows, 592);
+        const int nblk = (int)std::min<long>((n_pix_out + rows - 1) / rows, 148L * 16);
 { char _nm[40]; snprintf(_nm, sizeof _nm, "pool%d.bwd_sums", i); SED_PROF(_nm, st);
         bn_pool_bwd_sums_kernel<<<nblk, 256, 0, st>>>(y, stat, dA, n_pix_out, g, part);
         SED_POST_LAUNCH();
 }
         float* bnsum = wsf(ws, P.bnsum);
-        bn_bwd_finalize_kernel<<<(P.C + 127) / 128, 128, 0, st>>>(part, nblk, P.C, n_elem, grads + P.bn_w[i],
+        bn_bwd_finalize_kernel<<<(P.C * 32 + 255) / 256, 256, 0, st>>>(part, nblk, P.C, n_elem, grads + P.bn_w[i],
                                                                  grads + P.bn_b[i], bnsum);
         SED_POST_LAUNCH();
+        if (i == 0 && !dx && conv0_direct_ok(P.cin[0], P.C)) {
+            // fused BN/ReLU/pool backward + weight/bias gradient: dy0 is never materialised
+            SED_PROF("conv0.bwd_fused", st);
+            const dim3 grid((P.H + kC0Rows - 1) / kC0Rows, batch, P.C / 128);
+            const size_t sm = (size_t)P.cin[0] * (kC0Rows + 2) * (P.win[0] + 2) * 4;
+            const int J = P.cin[0] * 9;
+            if (P.cin[0] == 1)
+                conv0_bwd_fused_kernel<1><<<grid, 256, sm, st>>>(x, y, stat, dA, bnsum, g, part);
+            else
+                conv0_bwd_fused_kernel<2><<<grid, 256, sm, st>>>(x, y, stat, dA, bnsum, g, part);
+            SED_POST_LAUNCH();
+            conv0_bwd_reduce_kernel<<<((J + 1) * P.C * 32 + 255) / 256, 256, 0, st>>>(
+                part, (int)(grid.x * grid.y), J, P.C, grads + P.conv_w[0], grads + P.conv_b[0]);
+            SED_POST_LAUNCH();
+            break;
+        }
         float* dy = wsf(ws, P.dy);
         const long n_vec = n_pix_out * (P.C / 4);
 { char _nm[40]; snprintf(_nm, sizeof _nm, "pool%d.bwd_dy", i); SED_PROF(_nm, st);

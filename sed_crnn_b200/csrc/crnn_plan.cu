@@ -130,6 +130,8 @@ int make_plan(const sedb200_crnn_desc* d, int batch, Plan* p) {
     for (int l = 0; l < P.n_gru; ++l)
         part = std::max(part, 64L * 6 * P.gh[l] * std::max(P.gin[l], P.gh[l]));
     for (int j = 0; j < P.n_dense; ++j) part = std::max(part, 64L * P.dout[j] * P.din[j]);
+    part = std::max(part, B * ((P.H + 7) / 8) * (long)std::max(2, P.cin[0] * 9 + 1) * P.C);   // direct block-0 partials
+    part = std::max(part, 148L * 16 * 2 * P.C);                                                 // BN backward sums
     P.part_floats = (size_t)part;
     P.part = take(part);
     // tensor-core scratch: bf16 operand planes + wgrad split-K partials
