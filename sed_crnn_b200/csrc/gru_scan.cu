@@ -151,16 +151,187 @@ __global__ void gru_scan_bwd_kernel(const float* __restrict__ dout, const float*
     }
 }
 
+
+// ------------------------------------------------------------------------------ H <= 32: warp-resident scans
+// One sub-warp of H lanes owns one (direction, batch row): lane j keeps row j of each W_hh gate block
+// (3H registers) and its own h[j]; the matvec broadcasts h[k] with warp shuffles, so a step has no
+// shared memory and no block barrier -- only the dependent FMA chains.  B*2 independent sub-warps run in
+// parallel; gi for the next step is prefetched into registers.
+constexpr int kCh = 8;          // time steps of operands held in registers ahead of the recurrence
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+
+template <int H>
+__global__ void __launch_bounds__(128)
+gru_scan_fwd_warp_kernel(const float* __restrict__ gi, const float* __restrict__ whh, const float* __restrict__ bhh,
+                         float* __restrict__ out, float* __restrict__ gates, int B, int T) {
+    constexpr int IPW = 32 / H, H3 = 3 * H;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dir = blockIdx.y, j = lane % H;
+    const long b = ((long)blockIdx.x * 4 + warp) * IPW + lane / H;
+    const bool act = b < B;
+    const float* W = whh + (size_t)dir * H3 * H;
+    float w[3][H], bias[3];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+        bias[g] = __ldg(bhh + dir * H3 + g * H + j);
+#pragma unroll
+        for (int k = 0; k < H; ++k) w[g][k] = __ldg(W + (g * H + j) * H + k);
+    }
+    // gi is consumed kCh steps at a time from registers while the next kCh steps are already in flight
+    // (a one-step prefetch leaves every step exposed to a full L2/HBM round trip)
+    float h = 0.0f;
+    float cur[kCh][3], nxt[kCh][3];
+    auto load_chunk = [&](float (&dst)[kCh][3], int step0) {
+#pragma unroll
+        for (int s = 0; s < kCh; ++s) {
+            const int step = step0 + s;
+            if (act && step < T) {
+                const int t = dir ? T - 1 - step : step;
+                const float* g = gi + ((b * T + t) * 2 + dir) * H3;
+                dst[s][0] = __ldg(g + j); dst[s][1] = __ldg(g + H + j); dst[s][2] = __ldg(g + 2 * H + j);
+            } else {
+                dst[s][0] = dst[s][1] = dst[s][2] = 0.0f;
+            }
+        }
+    };
+    load_chunk(cur, 0);
+    for (int step0 = 0; step0 < T; step0 += kCh) {
+        load_chunk(nxt, step0 + kCh);
+#pragma unroll
+        for (int s = 0; s < kCh; ++s) {
+            const int step = step0 + s;
+            if (step >= T) break;
+            const int t = dir ? T - 1 - step : step;
+            float a0 = bias[0], a1 = bias[1], a2 = bias[2];
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+                const float hk = __shfl_sync(0xffffffffu, h, k, H);
+                a0 = fmaf(w[0][k], hk, a0);
+                a1 = fmaf(w[1][k], hk, a1);
+                a2 = fmaf(w[2][k], hk, a2);
+            }
+            const float r = fast_sigmoid(cur[s][0] + a0);
+            const float z = fast_sigmoid(cur[s][1] + a1);
+            const float n = fast_tanh(fmaf(r, a2, cur[s][2]));
+            h = fmaf(z, h - n, n);
+            if (act) {
+                out[(b * T + t) * 2 * H + dir * H + j] = h;
+                float* gs = gates + ((b * T + t) * 2 + dir) * 4 * H;
+                gs[j] = r; gs[H + j] = z; gs[2 * H + j] = n; gs[3 * H + j] = a2;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < kCh; ++s) { cur[s][0] = nxt[s][0]; cur[s][1] = nxt[s][1]; cur[s][2] = nxt[s][2]; }
+    }
+}
+
+template <int H>
+__global__ void __launch_bounds__(128)
+gru_scan_bwd_warp_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                         const float* __restrict__ gates, const float* __restrict__ whh, float* __restrict__ dgi,
+                         float* __restrict__ dgh, int B, int T) {
+    constexpr int IPW = 32 / H, H3 = 3 * H;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dir = blockIdx.y, j = lane % H;
+    const long b = ((long)blockIdx.x * 4 + warp) * IPW + lane / H;
+    const bool act = b < B;
+    const float* W = whh + (size_t)dir * H3 * H;
+    float wc[3][H];                                   // column j of each gate block: W[g*H + k][j]
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+        for (int k = 0; k < H; ++k) wc[g][k] = __ldg(W + (g * H + k) * H + j);
+    float dh = 0.0f;
+    float cur[kCh][6], nxt[kCh][6];                   // dout, r, z, n, q, h_prev
+    auto load_chunk = [&](float (&dst)[kCh][6], int step0) {
+#pragma unroll
+        for (int s = 0; s < kCh; ++s) {
+            const int step = step0 + s;
+            if (act && step < T) {
+                const int t = dir ? step : T - 1 - step;
+                dst[s][0] = __ldg(dout + (b * T + t) * 2 * H + dir * H + j);
+                const float* gs = gates + ((b * T + t) * 2 + dir) * 4 * H;
+                dst[s][1] = __ldg(gs + j); dst[s][2] = __ldg(gs + H + j);
+                dst[s][3] = __ldg(gs + 2 * H + j); dst[s][4] = __ldg(gs + 3 * H + j);
+                const int tp = dir ? t + 1 : t - 1;
+                dst[s][5] = (tp >= 0 && tp < T) ? __ldg(out + (b * T + tp) * 2 * H + dir * H + j) : 0.0f;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) dst[s][q] = 0.0f;
+            }
+        }
+    };
+    load_chunk(cur, 0);
+    for (int step0 = 0; step0 < T; step0 += kCh) {
+        load_chunk(nxt, step0 + kCh);
+#pragma unroll
+        for (int s = 0; s < kCh; ++s) {
+            const int step = step0 + s;
+            if (step >= T) break;
+            const int t = dir ? step : T - 1 - step;             // reverse of the forward order
+            const float c_do = cur[s][0], r = cur[s][1], z = cur[s][2], n = cur[s][3], q = cur[s][4], hp = cur[s][5];
+            const float dht = c_do + dh;
+            const float dn = dht * (1.0f - z);
+            const float dz = dht * (hp - n);
+            const float dan = dn * (1.0f - n * n);
+            const float dar = dan * q * r * (1.0f - r);
+            const float daz = dz * z * (1.0f - z);
+            const float dq = dan * r;
+            if (act) {
+                const long o = ((b * T + t) * 2 + dir) * H3;
+                dgi[o + j] = dar; dgi[o + H + j] = daz; dgi[o + 2 * H + j] = dan;
+                dgh[o + j] = dar; dgh[o + H + j] = daz; dgh[o + 2 * H + j] = dq;
+            }
+            float acc = dht * z;
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+                acc = fmaf(wc[0][k], __shfl_sync(0xffffffffu, dar, k, H), acc);
+                acc = fmaf(wc[1][k], __shfl_sync(0xffffffffu, daz, k, H), acc);
+                acc = fmaf(wc[2][k], __shfl_sync(0xffffffffu, dq, k, H), acc);
+            }
+            dh = acc;
+        }
+#pragma unroll
+        for (int s = 0; s < kCh; ++s)
+#pragma unroll
+            for (int q = 0; q < 6; ++q) cur[s][q] = nxt[s][q];
+    }
+}
+
+template <int H>
+int launch_warp_fwd(const float* gi, const float* whh, const float* bhh, float* out, float* gates, int B, int T,
+                    cudaStream_t st) {
+    constexpr int per_block = 4 * (32 / H);
+    dim3 grid((B + per_block - 1) / per_block, 2);
+    gru_scan_fwd_warp_kernel<H><<<grid, 128, 0, st>>>(gi, whh, bhh, out, gates, B, T);
+    SED_POST_LAUNCH();
+    return SEDB200_OK;
+}
+template <int H>
+int launch_warp_bwd(const float* dout, const float* out, const float* gates, const float* whh, float* dgi,
+                    float* dgh, int B, int T, cudaStream_t st) {
+    constexpr int per_block = 4 * (32 / H);
+    dim3 grid((B + per_block - 1) / per_block, 2);
+    gru_scan_bwd_warp_kernel<H><<<grid, 128, 0, st>>>(dout, out, gates, whh, dgi, dgh, B, T);
+    SED_POST_LAUNCH();
+    return SEDB200_OK;
+}
+
 inline int round32(int v) { return (v + 31) / 32 * 32; }
 
 }  // namespace
 
 int gru_scan_forward(const float* gi, const float* whh, const float* bhh, float* out, float* gates, int B, int T,
                      int H, cudaStream_t st) {
+    if (H == 32) return launch_warp_fwd<32>(gi, whh, bhh, out, gates, B, T, st);
+    if (H == 16) return launch_warp_fwd<16>(gi, whh, bhh, out, gates, B, T, st);
+    if (H == 8) return launch_warp_fwd<8>(gi, whh, bhh, out, gates, B, T, st);
     const int threads = round32(std::max(3 * H, kBT * H));
     SED_REQUIRE(threads <= 1024 && H % 4 == 0, SEDB200_ESHAPE, "gru_scan: H=%d unsupported", H);
     const size_t smem = ((size_t)3 * H * H + kBT * H + kBT * 3 * H) * 4;
-    SED_CUDA_OK(cudaFuncSetAttribute(gru_scan_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    static bool attr_f = false;
+    if (!attr_f) { SED_CUDA_OK(cudaFuncSetAttribute(gru_scan_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_f = true; }
     SED_REQUIRE(smem <= 227 * 1024, SEDB200_ESHAPE, "gru_scan: H=%d needs %zu B shared memory", H, smem);
     dim3 grid((B + kBT - 1) / kBT, 2);
     gru_scan_fwd_kernel<<<grid, threads, smem, st>>>(gi, whh, bhh, out, gates, B, T, H);
@@ -170,10 +341,14 @@ int gru_scan_forward(const float* gi, const float* whh, const float* bhh, float*
 
 int gru_scan_backward(const float* dout, const float* out, const float* gates, const float* whh, float* dgi,
                       float* dgh, int B, int T, int H, cudaStream_t st) {
+    if (H == 32) return launch_warp_bwd<32>(dout, out, gates, whh, dgi, dgh, B, T, st);
+    if (H == 16) return launch_warp_bwd<16>(dout, out, gates, whh, dgi, dgh, B, T, st);
+    if (H == 8) return launch_warp_bwd<8>(dout, out, gates, whh, dgi, dgh, B, T, st);
     const int threads = round32(kBT * H);
     SED_REQUIRE(threads <= 1024 && H % 4 == 0, SEDB200_ESHAPE, "gru_scan: H=%d unsupported", H);
     const size_t smem = ((size_t)3 * H * H + kBT * 3 * H) * 4;
-    SED_CUDA_OK(cudaFuncSetAttribute(gru_scan_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    static bool attr_b = false;
+    if (!attr_b) { SED_CUDA_OK(cudaFuncSetAttribute(gru_scan_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_b = true; }
     SED_REQUIRE(smem <= 227 * 1024, SEDB200_ESHAPE, "gru_scan: H=%d needs %zu B shared memory", H, smem);
     dim3 grid((B + kBT - 1) / kBT, 2);
     gru_scan_bwd_kernel<<<grid, threads, smem, st>>>(dout, out, gates, whh, dgi, dgh, B, T, H);

@@ -176,6 +176,7 @@ int sedb200_loss_fwd_bwd(int kind, float alpha, float gamma, const float* logits
     cudaStream_t st = as_stream(stream);
     const int nb = red_blocks(n);
     float* part = reinterpret_cast<float*>(scratch);
+    SED_PROF("loss", st);
     loss_kernel<<<nb, 256, 0, st>>>(kind, alpha, gamma, logits, targets, n, grad_scale, probs, dlogits, part);
     SED_POST_LAUNCH();
     loss_final_kernel<<<1, 32, 0, st>>>(part, nb, n, loss);
@@ -196,6 +197,7 @@ int sedb200_clip_adam(float* params, const float* grads, float* m, float* v, lon
     cudaStream_t st = as_stream(stream);
     const int nb = red_blocks(n);
     float* part = reinterpret_cast<float*>(scratch);
+    SED_PROF("clip_adam", st);
     sumsq_kernel<<<nb, 256, 0, st>>>(grads, n, prescale, part);
     SED_POST_LAUNCH();
     gnorm_final_kernel<<<1, 32, 0, st>>>(part, nb, gnorm);

@@ -65,17 +65,25 @@ colsum2_kernel(const float* __restrict__ X, long rows, int cols, long rows_per_b
     }
 }
 
+// one warp per column: fixed lane assignment + fixed shuffle tree (deterministic)
 __global__ void colsum_final_kernel(const float* __restrict__ part, int nblk, int cols, float* __restrict__ out,
                                     float* __restrict__ out_sq) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= cols) return;
     double a = 0.0, b = 0.0;
-    for (int k = 0; k < nblk; ++k) {
-        a += (double)part[((long)k * 2 + 0) * cols + c];
-        b += (double)part[((long)k * 2 + 1) * cols + c];
+    for (int k = lane; k < nblk; k += 32) {
+        a += (double)__ldg(part + ((long)k * 2 + 0) * cols + c);
+        b += (double)__ldg(part + ((long)k * 2 + 1) * cols + c);
     }
-    if (out) out[c] = (float)a;
-    if (out_sq) out_sq[c] = (float)b;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+        if (out) out[c] = (float)a;
+        if (out_sq) out_sq[c] = (float)b;
+    }
 }
 }  // namespace
 
@@ -101,7 +109,7 @@ int colsum(const float* X, long rows, int cols, float* out, float* scratch, cuda
     int nb = 0;
     int rc = colsum_partials(X, rows, cols, scratch, &nb, st);
     if (rc) return rc;
-    colsum_final_kernel<<<(cols + 127) / 128, 128, 0, st>>>(scratch, nb, cols, out, nullptr);
+    colsum_final_kernel<<<(cols * 32 + 255) / 256, 256, 0, st>>>(scratch, nb, cols, out, nullptr);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }
