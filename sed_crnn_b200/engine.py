@@ -55,6 +55,7 @@ class CRNNEngine:
         self._ws = None
         self._ws_batch = 0
         self._bufs = {}
+        self._last_seed = self.seed
 
     # ------------------------------------------------------------------ parameters
     def views(self, flat: torch.Tensor | None = None) -> dict[str, torch.Tensor]:
@@ -142,8 +143,10 @@ class CRNNEngine:
         return x.contiguous()
 
     # ------------------------------------------------------------------ compute
-    def forward(self, x: torch.Tensor, training: bool = False, logits: torch.Tensor | None = None) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, training: bool = False, logits: torch.Tensor | None = None,
+                seed: int | None = None) -> torch.Tensor:
         x = self._check_x(x)
+        self._last_seed = self.seed + self.step_count if seed is None else int(seed)
         B = x.shape[0]
         ws = self._workspace(B)
         if logits is None:
@@ -151,7 +154,7 @@ class CRNNEngine:
         with torch.cuda.device(self.device):
             _lib.check(self.L.sedb200_crnn_forward(
                 C.byref(self.desc), self.params.data_ptr(), self.bn_state.data_ptr(), x.data_ptr(), B,
-                int(training), self.seed + self.step_count, ws.data_ptr(), ws.numel(), logits.data_ptr(),
+                int(training), self._last_seed, ws.data_ptr(), ws.numel(), logits.data_ptr(),
                 _lib.current_stream_ptr()))
         if training:
             self.num_batches_tracked += 1
@@ -178,7 +181,7 @@ class CRNNEngine:
         ws = self._workspace(B)
         with torch.cuda.device(self.device):
             _lib.check(self.L.sedb200_crnn_backward(
-                C.byref(self.desc), self.params.data_ptr(), x.data_ptr(), B, self.seed + self.step_count,
+                C.byref(self.desc), self.params.data_ptr(), x.data_ptr(), B, self._last_seed,
                 ws.data_ptr(), ws.numel(), dlogits.data_ptr(), self.grads.data_ptr(),
                 dx.data_ptr() if dx is not None else None, _lib.current_stream_ptr()))
         return self.grads
