@@ -203,12 +203,9 @@ class CRNNEngine:
         logits = self.forward(x, training=True)
         loss, probs, dlog = self.loss_and_grad(logits, y)
         self.backward(x, dlog)
-        world = 1
-        if self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            import torch.distributed as dist
-            world = dist.get_world_size(self.pg)
-            if world > 1:
-                dist.all_reduce(self.grads, group=self.pg)           # sum; 1/world folded into clip_adam
+        from . import parallel
+        scale = parallel.allreduce_sum_(self.grads, self.pg)         # sum; 1/world folded into clip_adam
+        world = round(1.0 / scale)
         self.optimizer_step(world)
         return loss, probs
 
