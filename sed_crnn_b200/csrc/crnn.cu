@@ -529,6 +529,22 @@ __global__ void conv0_bwd_reduce_kernel(const float* __restrict__ part, int nblk
 inline bool conv0_direct_ok(int cin, int C) { return (cin == 1 || cin == 2) && C % 128 == 0; }
 inline long conv0_blocks(int B, int H) { return (long)B * ((H + kC0Rows - 1) / kC0Rows); }
 
+// part_b [B][2][n6] -> dbih[n6], dbhh[n6]  (fixed-order sum over B)
+__global__ void reduce_bias_partials_kernel(const float* __restrict__ part_b, float* __restrict__ dbih,
+                                            float* __restrict__ dbhh, int n6, int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * n6) return;
+    float acc = 0.0f;
+    for (int b = 0; b < B; ++b) acc += __ldg(part_b + (long)b * 2 * n6 + i);
+    if (i < n6) dbih[i] = acc;
+    else dbhh[i - n6] = acc;
+}
+inline int reduce_bias_partials(const float* part_b, float* dbih, float* dbhh, int n6, int B, cudaStream_t st) {
+    reduce_bias_partials_kernel<<<(2 * n6 + 127) / 128, 128, 0, st>>>(part_b, dbih, dbhh, n6, B);
+    SED_POST_LAUNCH();
+    return SEDB200_OK;
+}
+
 inline int ew_blocks(long n) { return (int)std::min<long>((n + 255) / 256, 148L * 16); }
 
 PoolGeom pool_geom(const Plan& P, const sedb200_crnn_desc* d, int i, int training, unsigned long long seed) {
@@ -716,17 +732,35 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         const float* xin = l == 0 ? wsf(ws, P.act[P.n_conv - 1]) : wsf(ws, P.gout[l - 1]);
         float* dgi = wsf(ws, P.dgi);
         float* dgh = wsf(ws, P.dgh);
+        const bool fusedg = gru_scan_fused_param_grads(h);
+        float* part_w = part;                                      // [B][2][3h][h]
+        float* part_b = part + (size_t)B * 6 * h * h;              // [B][2][2][3h]
 { char _nm[40]; snprintf(_nm, sizeof _nm, "gru%d.scan_bwd", l); SED_PROF(_nm, st);
         rc = gru_scan_backward(wsf(ws, P.dseq[cur]), wsf(ws, P.gout[l]), wsf(ws, P.gates[l]), params + P.whh[l],
-                               dgi, dgh, batch, P.T, h, st);
+                               dgi, dgh, part_w, part_b, batch, P.T, h, st);
         if (rc) return rc;
 }
         char _nm2[40]; snprintf(_nm2, sizeof _nm2, "gru%d.bwd_gemms", l); SED_PROF(_nm2, st);
-        // biases
-        rc = colsum(dgi, BT, 6 * h, grads + P.bih[l], part, st);
-        if (rc) return rc;
-        rc = colsum(dgh, BT, 6 * h, grads + P.bhh[l], part, st);
-        if (rc) return rc;
+        if (fusedg) {
+            // the scan left per-batch-row partials of dW_hh and of both bias gradients: fixed-order sum over B
+            rc = reduce_partials(part_w, grads + P.whh[l], 6L * h * h, batch, st);
+            if (rc) return rc;
+            rc = reduce_bias_partials(part_b, grads + P.bih[l], grads + P.bhh[l], 6 * h, batch, st);
+            if (rc) return rc;
+        } else {
+            rc = colsum(dgi, BT, 6 * h, grads + P.bih[l], part, st);
+            if (rc) return rc;
+            rc = colsum(dgh, BT, 6 * h, grads + P.bhh[l], part, st);
+            if (rc) return rc;
+            for (int dir = 0; dir < 2; ++dir) {
+                const int spw = gemm_simt_splits(BT, kSplit);
+                rc = gemm_simt(3 * h, h, BT, kSplit, ColMajor{dgh + dir * 3 * h, 6L * h},
+                               HPrevB{wsf(ws, P.gout[l]), P.T, h, dir}, EpiPartial{part, 3L * h * h, h}, st);
+                if (rc) return rc;
+                rc = reduce_partials(part, grads + P.whh[l] + (long)dir * 3 * h * h, 3L * h * h, spw, st);
+                if (rc) return rc;
+            }
+        }
         // dW_ih[n6][k] = sum_m dgi[m][n6] * xin[m][k]
         int sp = gemm_simt_splits(BT, kSplit);
         rc = gemm_simt(6 * h, in, BT, kSplit, ColMajor{dgi, 6L * h}, ColMajor{xin, in},
@@ -734,14 +768,6 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         if (rc) return rc;
         rc = reduce_partials(part, grads + P.wih[l], 6L * h * in, sp, st);
         if (rc) return rc;
-        // dW_hh[dir][r][j] = sum_(b,t) dgh[b,t,dir,r] * h_prev[b,t,dir,j]
-        for (int dir = 0; dir < 2; ++dir) {
-            rc = gemm_simt(3 * h, h, BT, kSplit, ColMajor{dgh + dir * 3 * h, 6L * h},
-                           HPrevB{wsf(ws, P.gout[l]), P.T, h, dir}, EpiPartial{part, 3L * h * h, h}, st);
-            if (rc) return rc;
-            rc = reduce_partials(part, grads + P.whh[l] + (long)dir * 3 * h * h, 3L * h * h, sp, st);
-            if (rc) return rc;
-        }
         // d(xin)[m][k] = sum_n6 dgi[m][n6] * W_ih[n6][k]
         float* dxin = wsf(ws, P.dseq[cur ^ 1]);
         rc = gemm_simt(BT, in, 6 * h, 1, RowMajor{dgi, 6L * h}, ColMajor{params + P.wih[l], in},

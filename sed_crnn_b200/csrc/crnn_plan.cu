@@ -127,8 +127,10 @@ int make_plan(const sedb200_crnn_desc* d, int batch, Plan* p) {
     long part = colsum_scratch_floats(B * P.H * P.win[0], std::max({P.C, 6 * 128, 1024}));
     for (int i = 0; i < P.n_conv; ++i)
         part = std::max(part, 64L * P.C * P.cin[i] * 9);                // wgrad: <= 64 K-slices
-    for (int l = 0; l < P.n_gru; ++l)
+    for (int l = 0; l < P.n_gru; ++l) {
         part = std::max(part, 64L * 6 * P.gh[l] * std::max(P.gin[l], P.gh[l]));
+        part = std::max(part, B * (6L * P.gh[l] * P.gh[l] + 12L * P.gh[l]));         // per-row dW_hh / bias partials
+    }
     for (int j = 0; j < P.n_dense; ++j) part = std::max(part, 64L * P.dout[j] * P.din[j]);
     part = std::max(part, B * ((P.H + 7) / 8) * (long)std::max(2, P.cin[0] * 9 + 1) * P.C);   // direct block-0 partials
     part = std::max(part, 148L * 16 * 2 * P.C);                                                 // BN backward sums

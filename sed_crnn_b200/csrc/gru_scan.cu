@@ -157,7 +157,8 @@ __global__ void gru_scan_bwd_kernel(const float* __restrict__ dout, const float*
 // (3H registers) and its own h[j]; the matvec broadcasts h[k] with warp shuffles, so a step has no
 // shared memory and no block barrier -- only the dependent FMA chains.  B*2 independent sub-warps run in
 // parallel; gi for the next step is prefetched into registers.
-constexpr int kCh = 8;          // time steps of operands held in registers ahead of the recurrence
+constexpr int kCh = 8;          // time steps of operands held in registers ahead of the recurrence (forward)
+constexpr int kChB = 4;         // same, backward scan (it also keeps 3H gradient accumulators per lane)
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 
@@ -226,27 +227,36 @@ gru_scan_fwd_warp_kernel(const float* __restrict__ gi, const float* __restrict__
     }
 }
 
+// Backward scan.  Besides dgi / dgh it accumulates, per (batch row, direction) and entirely in registers,
+// the recurrent weight gradient dW_hh = sum_t dgh_t (x) h_{t-1} and both bias gradients, so no separate
+// reduction GEMM over the B*T rows is needed afterwards (the per-row partials are summed over B by a
+// fixed-order reduce).  W_hh columns are read from shared memory (conflict-free, lane j <-> column j).
 template <int H>
 __global__ void __launch_bounds__(128)
 gru_scan_bwd_warp_kernel(const float* __restrict__ dout, const float* __restrict__ out,
                          const float* __restrict__ gates, const float* __restrict__ whh, float* __restrict__ dgi,
-                         float* __restrict__ dgh, int B, int T) {
+                         float* __restrict__ dgh, float* __restrict__ part_w, float* __restrict__ part_b, int B,
+                         int T) {
     constexpr int IPW = 32 / H, H3 = 3 * H;
+    __shared__ float Ws[H3 * H];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y, j = lane % H;
     const long b = ((long)blockIdx.x * 4 + warp) * IPW + lane / H;
     const bool act = b < B;
     const float* W = whh + (size_t)dir * H3 * H;
-    float wc[3][H];                                   // column j of each gate block: W[g*H + k][j]
+    for (int i = threadIdx.x; i < H3 * H; i += blockDim.x) Ws[i] = __ldg(W + i);
+    __syncthreads();
+    float dwa[3][H];                                  // dW_hh[g*H + j][k]
 #pragma unroll
     for (int g = 0; g < 3; ++g)
 #pragma unroll
-        for (int k = 0; k < H; ++k) wc[g][k] = __ldg(W + (g * H + k) * H + j);
+        for (int k = 0; k < H; ++k) dwa[g][k] = 0.0f;
+    float sb_r = 0, sb_z = 0, sb_n = 0, sb_q = 0;     // bias-gradient sums over t
     float dh = 0.0f;
-    float cur[kCh][6], nxt[kCh][6];                   // dout, r, z, n, q, h_prev
-    auto load_chunk = [&](float (&dst)[kCh][6], int step0) {
+    float cur[kChB][6], nxt[kChB][6];                   // dout, r, z, n, q, h_prev
+    auto load_chunk = [&](float (&dst)[kChB][6], int step0) {
 #pragma unroll
-        for (int s = 0; s < kCh; ++s) {
+        for (int s = 0; s < kChB; ++s) {
             const int step = step0 + s;
             if (act && step < T) {
                 const int t = dir ? step : T - 1 - step;
@@ -263,10 +273,10 @@ gru_scan_bwd_warp_kernel(const float* __restrict__ dout, const float* __restrict
         }
     };
     load_chunk(cur, 0);
-    for (int step0 = 0; step0 < T; step0 += kCh) {
-        load_chunk(nxt, step0 + kCh);
+    for (int step0 = 0; step0 < T; step0 += kChB) {
+        load_chunk(nxt, step0 + kChB);
 #pragma unroll
-        for (int s = 0; s < kCh; ++s) {
+        for (int s = 0; s < kChB; ++s) {
             const int step = step0 + s;
             if (step >= T) break;
             const int t = dir ? step : T - 1 - step;             // reverse of the forward order
@@ -283,19 +293,35 @@ gru_scan_bwd_warp_kernel(const float* __restrict__ dout, const float* __restrict
                 dgi[o + j] = dar; dgi[o + H + j] = daz; dgi[o + 2 * H + j] = dan;
                 dgh[o + j] = dar; dgh[o + H + j] = daz; dgh[o + 2 * H + j] = dq;
             }
-            float acc = dht * z;
+            sb_r += dar; sb_z += daz; sb_n += dan; sb_q += dq;
+            float a0 = dht * z, a1 = 0.0f, a2 = 0.0f;
 #pragma unroll
             for (int k = 0; k < H; ++k) {
-                acc = fmaf(wc[0][k], __shfl_sync(0xffffffffu, dar, k, H), acc);
-                acc = fmaf(wc[1][k], __shfl_sync(0xffffffffu, daz, k, H), acc);
-                acc = fmaf(wc[2][k], __shfl_sync(0xffffffffu, dq, k, H), acc);
+                a0 = fmaf(Ws[k * H + j], __shfl_sync(0xffffffffu, dar, k, H), a0);
+                a1 = fmaf(Ws[(H + k) * H + j], __shfl_sync(0xffffffffu, daz, k, H), a1);
+                a2 = fmaf(Ws[(2 * H + k) * H + j], __shfl_sync(0xffffffffu, dq, k, H), a2);
+                const float hk = __shfl_sync(0xffffffffu, hp, k, H);
+                dwa[0][k] = fmaf(dar, hk, dwa[0][k]);
+                dwa[1][k] = fmaf(daz, hk, dwa[1][k]);
+                dwa[2][k] = fmaf(dq, hk, dwa[2][k]);
             }
-            dh = acc;
+            dh = a0 + a1 + a2;
         }
 #pragma unroll
-        for (int s = 0; s < kCh; ++s)
+        for (int s = 0; s < kChB; ++s)
 #pragma unroll
             for (int q = 0; q < 6; ++q) cur[s][q] = nxt[s][q];
+    }
+    if (act) {
+        float* pw = part_w + ((b * 2 + dir) * H3) * H;               // [B][2][3H][H]
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+#pragma unroll
+            for (int k = 0; k < H; k += 4)
+                *reinterpret_cast<float4*>(pw + (g * H + j) * H + k) = make_float4(dwa[g][k], dwa[g][k + 1], dwa[g][k + 2], dwa[g][k + 3]);
+        float* pb = part_b + (b * 2) * 2 * H3;                        // [B][ih|hh][2][3H]
+        pb[dir * H3 + j] = sb_r; pb[dir * H3 + H + j] = sb_z; pb[dir * H3 + 2 * H + j] = sb_n;
+        pb[2 * H3 + dir * H3 + j] = sb_r; pb[2 * H3 + dir * H3 + H + j] = sb_z; pb[2 * H3 + dir * H3 + 2 * H + j] = sb_q;
     }
 }
 
@@ -310,10 +336,10 @@ int launch_warp_fwd(const float* gi, const float* whh, const float* bhh, float* 
 }
 template <int H>
 int launch_warp_bwd(const float* dout, const float* out, const float* gates, const float* whh, float* dgi,
-                    float* dgh, int B, int T, cudaStream_t st) {
+                    float* dgh, float* part_w, float* part_b, int B, int T, cudaStream_t st) {
     constexpr int per_block = 4 * (32 / H);
     dim3 grid((B + per_block - 1) / per_block, 2);
-    gru_scan_bwd_warp_kernel<H><<<grid, 128, 0, st>>>(dout, out, gates, whh, dgi, dgh, B, T);
+    gru_scan_bwd_warp_kernel<H><<<grid, 128, 0, st>>>(dout, out, gates, whh, dgi, dgh, part_w, part_b, B, T);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }
@@ -339,11 +365,13 @@ int gru_scan_forward(const float* gi, const float* whh, const float* bhh, float*
     return SEDB200_OK;
 }
 
+bool gru_scan_fused_param_grads(int H) { return H == 32 || H == 16 || H == 8; }
+
 int gru_scan_backward(const float* dout, const float* out, const float* gates, const float* whh, float* dgi,
-                      float* dgh, int B, int T, int H, cudaStream_t st) {
-    if (H == 32) return launch_warp_bwd<32>(dout, out, gates, whh, dgi, dgh, B, T, st);
-    if (H == 16) return launch_warp_bwd<16>(dout, out, gates, whh, dgi, dgh, B, T, st);
-    if (H == 8) return launch_warp_bwd<8>(dout, out, gates, whh, dgi, dgh, B, T, st);
+                      float* dgh, float* part_w, float* part_b, int B, int T, int H, cudaStream_t st) {
+    if (H == 32) return launch_warp_bwd<32>(dout, out, gates, whh, dgi, dgh, part_w, part_b, B, T, st);
+    if (H == 16) return launch_warp_bwd<16>(dout, out, gates, whh, dgi, dgh, part_w, part_b, B, T, st);
+    if (H == 8) return launch_warp_bwd<8>(dout, out, gates, whh, dgi, dgh, part_w, part_b, B, T, st);
     const int threads = round32(kBT * H);
     SED_REQUIRE(threads <= 1024 && H % 4 == 0, SEDB200_ESHAPE, "gru_scan: H=%d unsupported", H);
     const size_t smem = ((size_t)3 * H * H + kBT * 3 * H) * 4;
