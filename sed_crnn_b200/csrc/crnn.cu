@@ -268,6 +268,95 @@ __device__ __forceinline__ WindowGrad window_grad(const float* __restrict__ src,
     return r;
 }
 
+
+// Compile-time pool width: the P conv outputs of a window are loaded first (P independent 16 B loads in
+// flight per thread), then evaluated from registers -- no second trip to memory for the winner.
+template <int P>
+__device__ __forceinline__ void load_window(const float* __restrict__ src, int C, float4 (&v)[P]) {
+#pragma unroll
+    for (int j = 0; j < P; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(src + (long)j * C));
+}
+__device__ __forceinline__ void load_dA(const float* __restrict__ da, long oC, float (&g)[4]) {
+    if (oC == 1) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(da));
+        g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) g[q] = __ldg(da + q * oC);
+    }
+}
+template <int P>
+__device__ __forceinline__ void eval_window(const float4 (&v)[P], const float (&scv)[4], const float (&shv)[4],
+                                            float (&gq)[4], const PoolGeom& g, long i, float (&dz)[4], int (&arg)[4],
+                                            float (&yarg)[4]) {
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { arg[q] = 0; yarg[q] = 0.0f; }
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const float vv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float z = fmaf(vv[q], scv[q], shv[q]);
+            if (z > best[q]) { best[q] = z; arg[q] = j; yarg[q] = vv[q]; }
+        }
+    }
+    const float keep_scale = g.drop_p > 0.0f ? 1.0f / (1.0f - g.drop_p) : 1.0f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float t = gq[q];
+        if (g.drop_p > 0.0f) t = uniform01(g.seed, (unsigned long long)i * 4 + q) >= g.drop_p ? t * keep_scale : 0.0f;
+        dz[q] = best[q] > 0.0f ? t : 0.0f;
+    }
+}
+
+template <int P>
+__global__ void __launch_bounds__(256)
+bn_pool_bwd_sums_t_kernel(const float* __restrict__ y, const float* __restrict__ stat, const float* __restrict__ dA,
+                          long n_pix, PoolGeom g, float* __restrict__ part) {
+    __shared__ float4 s1[256], s2[256];
+    const int C4 = g.C >> 2, rows = 256 / C4;
+    const int c4 = threadIdx.x % C4, prow = threadIdx.x / C4;
+    const int c = c4 * 4;
+    const float4 sc = *reinterpret_cast<const float4*>(stat + 2 * g.C + c);
+    const float4 sh = *reinterpret_cast<const float4*>(stat + 3 * g.C + c);
+    const float4 mu = *reinterpret_cast<const float4*>(stat + c);
+    const float4 is = *reinterpret_cast<const float4*>(stat + g.C + c);
+    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+    const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, isv[4] = {is.x, is.y, is.z, is.w};
+    float a[4] = {0, 0, 0, 0}, bsum[4] = {0, 0, 0, 0};
+    for (long pix = (long)blockIdx.x * rows + prow; pix < n_pix; pix += (long)gridDim.x * rows) {
+        long t = pix;
+        const int wo = (int)(t % g.Wo); t /= g.Wo;
+        const int h = (int)(t % g.H);
+        const long b = t / g.H;
+        float4 v[P];
+        float gq[4], dz[4], yarg[4];
+        int arg[4];
+        load_window<P>(y + (((b * g.H + h) * g.W) + (long)wo * P) * g.C + c, g.C, v);
+        load_dA(dA + b * g.oB + h * g.oH + wo * g.oW + c * g.oC, g.oC, gq);
+        eval_window<P>(v, scv, shv, gq, g, pix * C4 + c4, dz, arg, yarg);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            a[q] += dz[q];
+            bsum[q] = fmaf(dz[q], (yarg[q] - muv[q]) * isv[q], bsum[q]);
+        }
+    }
+    s1[threadIdx.x] = make_float4(a[0], a[1], a[2], a[3]);
+    s2[threadIdx.x] = make_float4(bsum[0], bsum[1], bsum[2], bsum[3]);
+    __syncthreads();
+    if (prow == 0) {
+        float4 ta = make_float4(0, 0, 0, 0), tb = make_float4(0, 0, 0, 0);
+        for (int r = 0; r < rows; ++r) {
+            const float4 u = s1[r * C4 + c4], w = s2[r * C4 + c4];
+            ta.x += u.x; ta.y += u.y; ta.z += u.z; ta.w += u.w;
+            tb.x += w.x; tb.y += w.y; tb.z += w.z; tb.w += w.w;
+        }
+        *reinterpret_cast<float4*>(part + ((long)blockIdx.x * 2 + 0) * g.C + c) = ta;
+        *reinterpret_cast<float4*>(part + ((long)blockIdx.x * 2 + 1) * g.C + c) = tb;
+    }
+}
+
 // pass 1: per-channel sum(dz) and sum(dz * xhat); part layout [nblk][2][C]
 __global__ void __launch_bounds__(256)
 bn_pool_bwd_sums_kernel(const float* __restrict__ y, const float* __restrict__ stat, const float* __restrict__ dA,
@@ -492,6 +581,95 @@ conv0_bwd_fused_kernel(const float* __restrict__ x, const float* __restrict__ y,
 #pragma unroll
                 for (int q = 0; q < 4; ++q) dw[q][CIN * 9] += dyv[q];
             }
+        }
+    }
+    const long blk = (long)blockIdx.y * gridDim.x + blockIdx.x;
+#pragma unroll
+    for (int k = 0; k <= CIN * 9; ++k) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) red[warp][lane * 4 + q] = dw[q][k];
+        __syncthreads();
+        if (threadIdx.x < 128) {
+            float t = 0.0f;
+#pragma unroll
+            for (int r = 0; r < kC0Rows; ++r) t += red[r][threadIdx.x];
+            part[(blk * (CIN * 9 + 1) + k) * g.C + blockIdx.z * 128 + threadIdx.x] = t;
+        }
+        __syncthreads();
+    }
+}
+
+
+// Same as conv0_bwd_fused_kernel with the pool width P known at compile time and W == Wo*P: the P conv
+// outputs of the NEXT window are already in flight while the current window is being consumed.
+template <int CIN, int P>
+__global__ void __launch_bounds__(256)
+conv0_bwd_fused_t_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ stat,
+                         const float* __restrict__ dA, const float* __restrict__ bnsum, PoolGeom g,
+                         float* __restrict__ part) {
+    extern __shared__ float xs[];
+    __shared__ float red[kC0Rows][128];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y, h0 = blockIdx.x * kC0Rows, c4 = blockIdx.z * 32 + lane, c = c4 * 4, Wp = g.W + 2;
+    const int C4 = g.C >> 2;
+    load_x_rows<CIN>(x, xs, b, h0, g.H, g.W);
+    const float4 sc = *reinterpret_cast<const float4*>(stat + 2 * g.C + c);
+    const float4 sh = *reinterpret_cast<const float4*>(stat + 3 * g.C + c);
+    const float4 mu = *reinterpret_cast<const float4*>(stat + c);
+    const float4 is = *reinterpret_cast<const float4*>(stat + g.C + c);
+    const float4 k1 = *reinterpret_cast<const float4*>(bnsum + c);
+    const float4 k2 = *reinterpret_cast<const float4*>(bnsum + g.C + c);
+    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+    // dy = scale*dz - A - B*y   with  A = scale*(k1 - mu*is*k2),  B = scale*is*k2
+    const float Bc[4] = {sc.x * is.x * k2.x, sc.y * is.y * k2.y, sc.z * is.z * k2.z, sc.w * is.w * k2.w};
+    const float Ac[4] = {sc.x * k1.x - mu.x * Bc[0], sc.y * k1.y - mu.y * Bc[1], sc.z * k1.z - mu.z * Bc[2],
+                         sc.w * k1.w - mu.w * Bc[3]};
+    float dw[4][CIN * 9 + 1];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int k = 0; k <= CIN * 9; ++k) dw[q][k] = 0.0f;
+    __syncthreads();
+    const int h = h0 + warp;
+    if (h < g.H) {
+        const float* yrow = y + (((long)b * g.H + h) * g.W) * g.C + c;
+        const float* darow = dA + (long)b * g.oB + (long)h * g.oH + (long)c * g.oC;
+        float4 v[P], vn[P];
+        float gq[4], gn[4];
+        load_window<P>(yrow, g.C, v);
+        load_dA(darow, g.oC, gq);
+        for (int wo = 0; wo < g.Wo; ++wo) {
+            if (wo + 1 < g.Wo) {
+                load_window<P>(yrow + (long)(wo + 1) * P * g.C, g.C, vn);
+                load_dA(darow + (long)(wo + 1) * g.oW, g.oC, gn);
+            }
+            float dz[4], yarg[4];
+            int arg[4];
+            eval_window<P>(v, scv, shv, gq, g, (((long)b * g.H + h) * g.Wo + wo) * C4 + c4, dz, arg, yarg);
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const float vv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                float dyv[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) dyv[q] = fmaf(-Bc[q], vv[q], (arg[q] == j ? scv[q] * dz[q] : 0.0f) - Ac[q]);
+                const int ww = wo * P + j;
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int t = 0; t < 3; ++t) {
+                            const float xv = xs[(ci * (kC0Rows + 2) + warp + r) * Wp + ww + t];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) dw[q][ci * 9 + r * 3 + t] = fmaf(dyv[q], xv, dw[q][ci * 9 + r * 3 + t]);
+                        }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) dw[q][CIN * 9] += dyv[q];
+            }
+#pragma unroll
+            for (int j = 0; j < P; ++j) v[j] = vn[j];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) gq[q] = gn[q];
         }
     }
     const long blk = (long)blockIdx.y * gridDim.x + blockIdx.x;
@@ -787,7 +965,9 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         const int rows = 256 / (P.C / 4);
         const int nblk = (int)std::min<long>((n_pix_out + rows - 1) / rows, 148L * 16);
 { char _nm[40]; snprintf(_nm, sizeof _nm, "pool%d.bwd_sums", i); SED_PROF(_nm, st);
-        bn_pool_bwd_sums_kernel<<<nblk, 256, 0, st>>>(y, stat, dA, n_pix_out, g, part);
+        if (g.p == 5) bn_pool_bwd_sums_t_kernel<5><<<nblk, 256, 0, st>>>(y, stat, dA, n_pix_out, g, part);
+        else if (g.p == 2) bn_pool_bwd_sums_t_kernel<2><<<nblk, 256, 0, st>>>(y, stat, dA, n_pix_out, g, part);
+        else bn_pool_bwd_sums_kernel<<<nblk, 256, 0, st>>>(y, stat, dA, n_pix_out, g, part);
         SED_POST_LAUNCH();
 }
         float* bnsum = wsf(ws, P.bnsum);
@@ -800,7 +980,12 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
             const dim3 grid((P.H + kC0Rows - 1) / kC0Rows, batch, P.C / 128);
             const size_t sm = (size_t)P.cin[0] * (kC0Rows + 2) * (P.win[0] + 2) * 4;
             const int J = P.cin[0] * 9;
-            if (P.cin[0] == 1)
+            const bool exact = (g.W == g.Wo * g.p);
+            if (exact && g.p == 5 && P.cin[0] == 1) conv0_bwd_fused_t_kernel<1, 5><<<grid, 256, sm, st>>>(x, y, stat, dA, bnsum, g, part);
+            else if (exact && g.p == 5 && P.cin[0] == 2) conv0_bwd_fused_t_kernel<2, 5><<<grid, 256, sm, st>>>(x, y, stat, dA, bnsum, g, part);
+            else if (exact && g.p == 2 && P.cin[0] == 1) conv0_bwd_fused_t_kernel<1, 2><<<grid, 256, sm, st>>>(x, y, stat, dA, bnsum, g, part);
+            else if (exact && g.p == 2 && P.cin[0] == 2) conv0_bwd_fused_t_kernel<2, 2><<<grid, 256, sm, st>>>(x, y, stat, dA, bnsum, g, part);
+            else if (P.cin[0] == 1)
                 conv0_bwd_fused_kernel<1><<<grid, 256, sm, st>>>(x, y, stat, dA, bnsum, g, part);
             else
                 conv0_bwd_fused_kernel<2><<<grid, 256, sm, st>>>(x, y, stat, dA, bnsum, g, part);
