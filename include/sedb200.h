@@ -198,6 +198,15 @@ size_t sedb200_conv3x3_wgrad_tc_scratch_bytes(int B, int H, int W, int Cin, int 
 int    sedb200_conv3x3_wgrad_tc(const float* dy_dev, const float* in_dev, float* dw_dev, int B, int H, int W,
                                 int Cin, int Cout, void* scratch_dev, size_t scratch_bytes, void* stream);
 
+/* Plain GEMM on tcgen05 with the same 3-term bf16 split (unit-test entry for the kernel behind the GRU input
+ * projections, crnn_lightning.py:61-62 / sed.py:101, and their gradients):
+ *   out[M][N] (+bias[N]) = sum_k A(m,k) * B(n,k),   a_mn / b_mn: 0 = operand stored [rows][K], 1 = stored [K][rows].
+ * split_k != 0 splits K over the SMs and reduces the partials in a fixed order.  M, N, K multiples of 8. */
+size_t sedb200_gemm_tc_scratch_bytes(int M, int N, int K);
+int    sedb200_gemm_tc(const float* a_dev, int a_mn, const float* b_dev, int b_mn, int M, int N, int K,
+                       const float* bias_dev, float* out_dev, int split_k, void* scratch_dev, size_t scratch_bytes,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

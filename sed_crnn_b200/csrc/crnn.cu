@@ -10,6 +10,7 @@
 #include "gemm_simt.cuh"
 #include "gru_scan.cuh"
 #include "tc_conv.cuh"
+#include "tc_gemm.cuh"
 
 #include <algorithm>
 
@@ -831,8 +832,20 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
         const int h = P.gh[l], in = P.gin[l];
         float* gi = wsf(ws, P.gi[l]);
 { char _nm[40]; snprintf(_nm, sizeof _nm, "gru%d.proj", l); SED_PROF(_nm, st);
-        rc = gemm_simt(BT, 6 * h, in, 1, RowMajor{seq, in}, RowMajor{params + P.wih[l], in},
-                       EpiStore{gi, 6L * h, params + P.bih[l], 0}, st);
+        if (P.gru_tc[l]) {
+            // tcgen05: X planes are kept for the backward dW_ih, W_ih planes are rebuilt every step (tiny)
+            const size_t xpb = ((size_t)BT * in * 2 + 1023) & ~(size_t)1023, wpb = ((size_t)6 * h * in * 2 + 1023) & ~(size_t)1023;
+            char* xp = reinterpret_cast<char*>(ws) + P.gxp[l];
+            char* wp = reinterpret_cast<char*>(ws) + P.tc;
+            rc = split_planes(seq, xp, xp + xpb, (long)BT * in, st);
+            if (rc) return rc;
+            rc = split_planes(params + P.wih[l], wp, wp + wpb, 6L * h * in, st);
+            if (rc) return rc;
+            rc = gemm_tc(xp, xp + xpb, 0, wp, wp + wpb, 0, BT, 6 * h, in, params + P.bih[l], gi, 6L * h, 0, nullptr, st);
+        } else {
+            rc = gemm_simt(BT, 6 * h, in, 1, RowMajor{seq, in}, RowMajor{params + P.wih[l], in},
+                           EpiStore{gi, 6L * h, params + P.bih[l], 0}, st);
+        }
         if (rc) return rc;
 }
 { char _nm[40]; snprintf(_nm, sizeof _nm, "gru%d.scan_fwd", l); SED_PROF(_nm, st);
@@ -939,6 +952,25 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
                 if (rc) return rc;
             }
         }
+        float* dxin = wsf(ws, P.dseq[cur ^ 1]);
+        if (P.gru_tc[l]) {
+            const size_t xpb = ((size_t)BT * in * 2 + 1023) & ~(size_t)1023, wpb = ((size_t)6 * h * in * 2 + 1023) & ~(size_t)1023;
+            const size_t gpb = ((size_t)BT * 6 * h * 2 + 1023) & ~(size_t)1023;
+            char* xp = reinterpret_cast<char*>(ws) + P.gxp[l];
+            char* gp = reinterpret_cast<char*>(ws) + P.tc;
+            char* wp = gp + 2 * gpb;
+            float* tpart = reinterpret_cast<float*>(wp + 2 * wpb);
+            rc = split_planes(dgi, gp, gp + gpb, (long)BT * 6 * h, st);
+            if (rc) return rc;
+            rc = split_planes(params + P.wih[l], wp, wp + wpb, 6L * h * in, st);
+            if (rc) return rc;
+            // dW_ih[n6][k] = sum_m dgi[m][n6] * xin[m][k]        (both operands stored [B*T][.]: MN-major)
+            rc = gemm_tc(gp, gp + gpb, 1, xp, xp + xpb, 1, 6 * h, in, BT, nullptr, grads + P.wih[l], in, 1, tpart, st);
+            if (rc) return rc;
+            // d(xin)[m][k] = sum_n6 dgi[m][n6] * W_ih[n6][k]    (W_ih stored [n6][k] = [K][N]: MN-major)
+            rc = gemm_tc(gp, gp + gpb, 0, wp, wp + wpb, 1, BT, in, 6 * h, nullptr, dxin, in, 0, nullptr, st);
+            if (rc) return rc;
+        } else {
         // dW_ih[n6][k] = sum_m dgi[m][n6] * xin[m][k]
         int sp = gemm_simt_splits(BT, kSplit);
         rc = gemm_simt(6 * h, in, BT, kSplit, ColMajor{dgi, 6L * h}, ColMajor{xin, in},
@@ -946,11 +978,10 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         if (rc) return rc;
         rc = reduce_partials(part, grads + P.wih[l], 6L * h * in, sp, st);
         if (rc) return rc;
-        // d(xin)[m][k] = sum_n6 dgi[m][n6] * W_ih[n6][k]
-        float* dxin = wsf(ws, P.dseq[cur ^ 1]);
         rc = gemm_simt(BT, in, 6 * h, 1, RowMajor{dgi, 6L * h}, ColMajor{params + P.wih[l], in},
                        EpiStore{dxin, in, nullptr, 0}, st);
         if (rc) return rc;
+        }
         cur ^= 1;
     }
 

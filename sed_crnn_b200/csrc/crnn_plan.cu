@@ -2,6 +2,7 @@
 #include "crnn_plan.cuh"
 #include "gemm_simt.cuh"
 #include "tc_conv.cuh"
+#include "tc_gemm.cuh"
 
 #include <algorithm>
 
@@ -144,6 +145,16 @@ int make_plan(const sedb200_crnn_desc* d, int batch, Plan* p) {
             if (conv_tc_supported(P.H, P.win[i], P.C, P.cin[i])) tc = std::max(tc, conv_tc_scratch_bytes(batch, P.H, P.win[i], P.C, P.cin[i]));
             if (wgrad_tc_supported(P.H, P.win[i], P.cin[i], P.C)) tc = std::max(tc, wgrad_tc_scratch_bytes(batch, P.H, P.win[i], P.cin[i], P.C));
         }
+    auto plane = [](long n) { return ((size_t)n * 2 + 1023) & ~(size_t)1023; };
+    for (int l = 0; l < P.n_gru; ++l) {
+        const int h6 = 6 * P.gh[l], in = P.gin[l];
+        P.gru_tc[l] = d->tensor_cores && BT >= 1024 && gemm_tc_supported((int)BT, h6, in) && gemm_tc_supported(h6, in, (int)BT) &&
+                      gemm_tc_supported((int)BT, in, h6);
+        P.gxp[l] = 0;
+        if (!P.gru_tc[l]) continue;
+        P.gxp[l] = take((long)(2 * plane(BT * in) / 4));
+        tc = std::max(tc, 2 * plane(BT * h6) + 2 * plane((long)h6 * in) + (size_t)sm_count() * h6 * in * 4 + 4096);
+    }
     P.tc_bytes = tc;
     P.tc = take((long)(tc / 4) + 64);
     P.ws_bytes = o;

@@ -22,6 +22,8 @@ struct Plan {
     // workspace offsets (bytes); valid when B > 0
     size_t y[SEDB200_MAX_CONV], stat[SEDB200_MAX_CONV], act[SEDB200_MAX_CONV];   // act[i] = output of block i
     size_t gi[SEDB200_MAX_GRU], gout[SEDB200_MAX_GRU], gates[SEDB200_MAX_GRU];
+    size_t gxp[SEDB200_MAX_GRU];              // bf16 hi/lo planes of each GRU layer's input (tensor-core path)
+    bool gru_tc[SEDB200_MAX_GRU];
     size_t hid[SEDB200_MAX_DENSE];
     size_t dy, dact[2], dseq[2], dgi, dgh, dhid[2], part, bnsum, tc;
     size_t tc_bytes = 0;
