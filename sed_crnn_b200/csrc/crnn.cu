@@ -718,6 +718,13 @@ __global__ void reduce_bias_partials_kernel(const float* __restrict__ part_b, fl
     if (i < n6) dbih[i] = acc;
     else dbhh[i - n6] = acc;
 }
+// whh[dir][r][j] = full[dir*3h + r][dir*h + j],  full is [6h][2h]
+__global__ void extract_whh_kernel(const float* __restrict__ full, int h, float* __restrict__ whh) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 6 * h * h) return;
+    const int j = i % h, r = (i / h) % (3 * h), dir = i / (3 * h * h);
+    whh[i] = full[(long)(dir * 3 * h + r) * 2 * h + dir * h + j];
+}
 inline int reduce_bias_partials(const float* part_b, float* dbih, float* dbhh, int n6, int B, cudaStream_t st) {
     reduce_bias_partials_kernel<<<(2 * n6 + 127) / 128, 128, 0, st>>>(part_b, dbih, dbhh, n6, B);
     SED_POST_LAUNCH();
@@ -933,9 +940,7 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
 }
         char _nm2[40]; snprintf(_nm2, sizeof _nm2, "gru%d.bwd_gemms", l); SED_PROF(_nm2, st);
         if (fusedg) {
-            // the scan left per-batch-row partials of dW_hh and of both bias gradients: fixed-order sum over B
-            rc = reduce_partials(part_w, grads + P.whh[l], 6L * h * h, batch, st);
-            if (rc) return rc;
+            // the scan left per-batch-row partials of both bias gradients: fixed-order sum over B
             rc = reduce_bias_partials(part_b, grads + P.bih[l], grads + P.bhh[l], 6 * h, batch, st);
             if (rc) return rc;
         } else {
@@ -943,6 +948,24 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
             if (rc) return rc;
             rc = colsum(dgh, BT, 6 * h, grads + P.bhh[l], part, st);
             if (rc) return rc;
+        }
+        if (P.gru_tc[l] && gemm_tc_supported(6 * h, 2 * h, BT)) {
+            // dW_hh on tcgen05: [6h][2h] = dgh^T (B*T x 6h) . h_prev (B*T x 2h); the two diagonal blocks are
+            // the per-direction gradients (the off-diagonal blocks are discarded)
+            const size_t gpb = ((size_t)BT * 6 * h * 2 + 1023) & ~(size_t)1023, hpb = ((size_t)BT * 2 * h * 2 + 1023) & ~(size_t)1023;
+            char* gp = reinterpret_cast<char*>(ws) + P.tc;
+            char* hp = gp + 2 * gpb;
+            float* tmp = reinterpret_cast<float*>(hp + 2 * hpb);
+            float* tpart = tmp + 12 * h * h + 64;
+            rc = split_planes(dgh, gp, gp + gpb, (long)BT * 6 * h, st);
+            if (rc) return rc;
+            rc = hprev_planes(wsf(ws, P.gout[l]), hp, hp + hpb, BT, P.T, h, st);
+            if (rc) return rc;
+            rc = gemm_tc(gp, gp + gpb, 1, hp, hp + hpb, 1, 6 * h, 2 * h, BT, nullptr, tmp, 2 * h, 1, tpart, st);
+            if (rc) return rc;
+            extract_whh_kernel<<<(6 * h * h + 255) / 256, 256, 0, st>>>(tmp, h, grads + P.whh[l]);
+            SED_POST_LAUNCH();
+        } else {
             for (int dir = 0; dir < 2; ++dir) {
                 const int spw = gemm_simt_splits(BT, kSplit);
                 rc = gemm_simt(3 * h, h, BT, kSplit, ColMajor{dgh + dir * 3 * h, 6L * h},

@@ -154,6 +154,7 @@ int make_plan(const sedb200_crnn_desc* d, int batch, Plan* p) {
         if (!P.gru_tc[l]) continue;
         P.gxp[l] = take((long)(2 * plane(BT * in) / 4));
         tc = std::max(tc, 2 * plane(BT * h6) + 2 * plane((long)h6 * in) + (size_t)sm_count() * h6 * in * 4 + 4096);
+        tc = std::max(tc, 2 * plane(BT * h6) + 2 * plane(BT * 2L * P.gh[l]) + ((size_t)sm_count() + 1) * h6 * 2 * P.gh[l] * 4 + 8192);
     }
     P.tc_bytes = tc;
     P.tc = take((long)(tc / 4) + 64);

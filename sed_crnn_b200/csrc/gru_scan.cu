@@ -158,7 +158,7 @@ __global__ void gru_scan_bwd_kernel(const float* __restrict__ dout, const float*
 // shared memory and no block barrier -- only the dependent FMA chains.  B*2 independent sub-warps run in
 // parallel; gi for the next step is prefetched into registers.
 constexpr int kCh = 8;          // time steps of operands held in registers ahead of the recurrence (forward)
-constexpr int kChB = 4;         // same, backward scan (it also keeps 3H gradient accumulators per lane)
+constexpr int kChB = 8;         // same, backward scan
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 
@@ -227,10 +227,10 @@ gru_scan_fwd_warp_kernel(const float* __restrict__ gi, const float* __restrict__
     }
 }
 
-// Backward scan.  Besides dgi / dgh it accumulates, per (batch row, direction) and entirely in registers,
-// the recurrent weight gradient dW_hh = sum_t dgh_t (x) h_{t-1} and both bias gradients, so no separate
-// reduction GEMM over the B*T rows is needed afterwards (the per-row partials are summed over B by a
-// fixed-order reduce).  W_hh columns are read from shared memory (conflict-free, lane j <-> column j).
+// Backward scan.  Besides dgi / dgh it accumulates both bias gradients per (batch row, direction) in
+// registers (summed over B afterwards in a fixed order).  dW_hh = sum_(b,t) dgh (x) h_{t-1} has no
+// sequential dependency and is left to a tensor-core GEMM.  W_hh columns are read from shared memory
+// (conflict-free, lane j <-> column j).
 template <int H>
 __global__ void __launch_bounds__(128)
 gru_scan_bwd_warp_kernel(const float* __restrict__ dout, const float* __restrict__ out,
@@ -246,11 +246,6 @@ gru_scan_bwd_warp_kernel(const float* __restrict__ dout, const float* __restrict
     const float* W = whh + (size_t)dir * H3 * H;
     for (int i = threadIdx.x; i < H3 * H; i += blockDim.x) Ws[i] = __ldg(W + i);
     __syncthreads();
-    float dwa[3][H];                                  // dW_hh[g*H + j][k]
-#pragma unroll
-    for (int g = 0; g < 3; ++g)
-#pragma unroll
-        for (int k = 0; k < H; ++k) dwa[g][k] = 0.0f;
     float sb_r = 0, sb_z = 0, sb_n = 0, sb_q = 0;     // bias-gradient sums over t
     float dh = 0.0f;
     float cur[kChB][6], nxt[kChB][6];                   // dout, r, z, n, q, h_prev
@@ -300,10 +295,6 @@ gru_scan_bwd_warp_kernel(const float* __restrict__ dout, const float* __restrict
                 a0 = fmaf(Ws[k * H + j], __shfl_sync(0xffffffffu, dar, k, H), a0);
                 a1 = fmaf(Ws[(H + k) * H + j], __shfl_sync(0xffffffffu, daz, k, H), a1);
                 a2 = fmaf(Ws[(2 * H + k) * H + j], __shfl_sync(0xffffffffu, dq, k, H), a2);
-                const float hk = __shfl_sync(0xffffffffu, hp, k, H);
-                dwa[0][k] = fmaf(dar, hk, dwa[0][k]);
-                dwa[1][k] = fmaf(daz, hk, dwa[1][k]);
-                dwa[2][k] = fmaf(dq, hk, dwa[2][k]);
             }
             dh = a0 + a1 + a2;
         }
@@ -313,12 +304,6 @@ gru_scan_bwd_warp_kernel(const float* __restrict__ dout, const float* __restrict
             for (int q = 0; q < 6; ++q) cur[s][q] = nxt[s][q];
     }
     if (act) {
-        float* pw = part_w + ((b * 2 + dir) * H3) * H;               // [B][2][3H][H]
-#pragma unroll
-        for (int g = 0; g < 3; ++g)
-#pragma unroll
-            for (int k = 0; k < H; k += 4)
-                *reinterpret_cast<float4*>(pw + (g * H + j) * H + k) = make_float4(dwa[g][k], dwa[g][k + 1], dwa[g][k + 2], dwa[g][k + 3]);
         float* pb = part_b + (b * 2) * 2 * H3;                        // [B][ih|hh][2][3H]
         pb[dir * H3 + j] = sb_r; pb[dir * H3 + H + j] = sb_z; pb[dir * H3 + 2 * H + j] = sb_n;
         pb[2 * H3 + dir * H3 + j] = sb_r; pb[2 * H3 + dir * H3 + H + j] = sb_z; pb[2 * H3 + dir * H3 + 2 * H + j] = sb_q;

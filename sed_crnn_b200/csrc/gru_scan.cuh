@@ -16,7 +16,7 @@ int gru_scan_forward(const float* gi, const float* whh, const float* bhh, float*
 // dgh   [B][T][2][3H] gradient w.r.t. W_hh h_{t-1} + b_hh
 // When gru_scan_fused_param_grads(H) the scan also writes per-batch-row partial sums that the caller
 // reduces over B in a fixed order:
-//   part_w [B][2][3H][H]   contribution of row b to dW_hh
+//   part_w                 unused (kept for ABI stability; dW_hh comes from a GEMM over dgh and h_{t-1})
 //   part_b [B][2][2][3H]   contribution of row b to db_ih ([.][0]) and db_hh ([.][1])
 // otherwise part_w / part_b are untouched and the caller derives those gradients from dgi / dgh.
 bool gru_scan_fused_param_grads(int H);
