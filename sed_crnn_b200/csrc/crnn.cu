@@ -708,6 +708,67 @@ __global__ void conv0_bwd_reduce_kernel(const float* __restrict__ part, int nblk
 inline bool conv0_direct_ok(int cin, int C) { return (cin == 1 || cin == 2) && C % 128 == 0; }
 inline long conv0_blocks(int B, int H) { return (long)B * ((H + kC0Rows - 1) / kC0Rows); }
 
+
+// ----------------------------------------------------------------------------- small dense layers, backward
+// The per-frame dense head is tiny (e.g. 64 -> 16 -> 6): one kernel per layer produces d(input) for its 128
+// rows and the block's partial dW / db; a second one sums the partials in a fixed order.
+constexpr int kDbRows = 128;
+__global__ void __launch_bounds__(256)
+dense_bwd_small_kernel(const float* __restrict__ dout, const float* __restrict__ in, const float* __restrict__ W,
+                       const float* __restrict__ relu_act /* activation of the producing layer or null */,
+                       int rows, int N, int D, float* __restrict__ din, float* __restrict__ part) {
+    extern __shared__ float sm[];
+    float* s_do = sm;                       // [128][N]
+    float* s_in = s_do + kDbRows * N;       // [128][D+1]
+    float* s_w = s_in + kDbRows * (D + 1);  // [N][D]
+    const int r0 = blockIdx.x * kDbRows, nr = min(kDbRows, rows - r0), Dp = D + 1;
+    for (int i = threadIdx.x; i < kDbRows * N; i += 256) s_do[i] = (i / N) < nr ? __ldg(dout + (long)r0 * N + i) : 0.0f;
+    for (int i = threadIdx.x; i < kDbRows * D; i += 256) {
+        const int r = i / D, k = i - r * D;
+        s_in[r * Dp + k] = r < nr ? __ldg(in + (long)r0 * D + i) : 0.0f;
+    }
+    for (int i = threadIdx.x; i < N * D; i += 256) s_w[i] = __ldg(W + i);
+    __syncthreads();
+    // d(in)[r][k] = sum_n dout[r][n] W[n][k]
+    if (din) {
+        for (int i = threadIdx.x; i < nr * D; i += 256) {
+            const int r = i / D, k = i - r * D;
+            float acc = 0.0f;
+            for (int n = 0; n < N; ++n) acc = fmaf(s_do[r * N + n], s_w[n * D + k], acc);
+            if (relu_act && !(__ldg(relu_act + (long)(r0 + r) * D + k) > 0.0f)) acc = 0.0f;
+            din[(long)(r0 + r) * D + k] = acc;
+        }
+    }
+    // partial dW[n][k] = sum_r dout[r][n] in[r][k];  partial db[n] = sum_r dout[r][n]
+    float* pb = part + (long)blockIdx.x * (N * D + N);
+    for (int i = threadIdx.x; i < N * D; i += 256) {
+        const int n = i / D, k = i - n * D;
+        float acc = 0.0f;
+        for (int r = 0; r < kDbRows; ++r) acc = fmaf(s_do[r * N + n], s_in[r * Dp + k], acc);
+        pb[i] = acc;
+    }
+    for (int n = threadIdx.x; n < N; n += 256) {
+        float acc = 0.0f;
+        for (int r = 0; r < kDbRows; ++r) acc += s_do[r * N + n];
+        pb[N * D + n] = acc;
+    }
+}
+__global__ void dense_bwd_reduce_kernel(const float* __restrict__ part, int nblk, int ND, int N,
+                                        float* __restrict__ dw, float* __restrict__ db) {
+    const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (o >= ND + N) return;
+    double a = 0.0;
+    for (int k = lane; k < nblk; k += 32) a += (double)__ldg(part + (long)k * (ND + N) + o);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+    if (lane == 0) {
+        if (o < ND) dw[o] = (float)a;
+        else db[o - ND] = (float)a;
+    }
+}
+inline size_t dense_small_smem(int N, int D) { return ((size_t)kDbRows * N + (size_t)kDbRows * (D + 1) + (size_t)N * D) * 4; }
+inline bool dense_small_ok(int N, int D) { return dense_small_smem(N, D) <= 160 * 1024; }
+
 // part_b [B][2][n6] -> dbih[n6], dbhh[n6]  (fixed-order sum over B)
 __global__ void reduce_bias_partials_kernel(const float* __restrict__ part_b, float* __restrict__ dbih,
                                             float* __restrict__ dbhh, int n6, int B) {
@@ -903,6 +964,20 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         char _nm[40]; snprintf(_nm, sizeof _nm, "dense%d.bwd", j); SED_PROF(_nm, st);
         const float* in = j == 0 ? wsf(ws, P.gout[P.n_gru - 1]) : wsf(ws, P.hid[j - 1]);
         const int N = P.dout[j], D = P.din[j];
+        float* din = j == 0 ? wsf(ws, P.dseq[0]) : wsf(ws, P.dhid[(j - 1) & 1]);
+        const float* mask = (j > 0 && d->dense_relu) ? wsf(ws, P.hid[j - 1]) : nullptr;
+        if (dense_small_ok(N, D)) {
+            static bool attr_done = false;
+            if (!attr_done) {
+                SED_CUDA_OK(cudaFuncSetAttribute(dense_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+                attr_done = true;
+            }
+            const int nblk = (BT + kDbRows - 1) / kDbRows;
+            dense_bwd_small_kernel<<<nblk, 256, dense_small_smem(N, D), st>>>(dout, in, params + P.dn_w[j], mask, BT, N, D, din, part);
+            SED_POST_LAUNCH();
+            dense_bwd_reduce_kernel<<<((N * D + N) * 32 + 255) / 256, 256, 0, st>>>(part, nblk, N * D, N, grads + P.dn_w[j], grads + P.dn_b[j]);
+            SED_POST_LAUNCH();
+        } else {
         // dW[n][k] = sum_m dout[m][n] * in[m][k]
         const int sp = gemm_simt_splits(BT, kSplit);
         rc = gemm_simt(N, D, BT, kSplit, ColMajor{dout, N}, ColMajor{in, D}, EpiPartial{part, (long)N * D, D}, st);
@@ -912,14 +987,14 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         rc = colsum(dout, BT, N, grads + P.dn_b[j], part, st);
         if (rc) return rc;
         // d(in)[m][k] = sum_n dout[m][n] * W[n][k]   (through the previous layer's ReLU if any)
-        float* din = j == 0 ? wsf(ws, P.dseq[0]) : wsf(ws, P.dhid[(j - 1) & 1]);
-        if (j > 0 && d->dense_relu)
+        if (mask)
             rc = gemm_simt(BT, D, N, 1, RowMajor{dout, N}, ColMajor{params + P.dn_w[j], D},
-                           EpiReluMask{din, D, wsf(ws, P.hid[j - 1])}, st);
+                           EpiReluMask{din, D, mask}, st);
         else
             rc = gemm_simt(BT, D, N, 1, RowMajor{dout, N}, ColMajor{params + P.dn_w[j], D},
                            EpiStore{din, D, nullptr, 0}, st);
         if (rc) return rc;
+        }
         dout = din;
     }
 

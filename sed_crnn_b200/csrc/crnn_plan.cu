@@ -132,7 +132,10 @@ int make_plan(const sedb200_crnn_desc* d, int batch, Plan* p) {
         part = std::max(part, 64L * 6 * P.gh[l] * std::max(P.gin[l], P.gh[l]));
         part = std::max(part, B * (6L * P.gh[l] * P.gh[l] + 12L * P.gh[l]));         // per-row dW_hh / bias partials
     }
-    for (int j = 0; j < P.n_dense; ++j) part = std::max(part, 64L * P.dout[j] * P.din[j]);
+    for (int j = 0; j < P.n_dense; ++j) {
+        part = std::max(part, 64L * P.dout[j] * P.din[j]);
+        part = std::max(part, ((BT + 127) / 128) * ((long)P.dout[j] * P.din[j] + P.dout[j]));     // per-block dW/db partials
+    }
     part = std::max(part, B * ((P.H + 7) / 8) * (long)std::max(2, P.cin[0] * 9 + 1) * P.C);   // direct block-0 partials
     part = std::max(part, 148L * 16 * 2 * P.C);                                                 // BN backward sums
     P.part_floats = (size_t)part;
