@@ -6,6 +6,7 @@
 // permute+reshape copy (crnn_lightning.py:68-70).
 //
 // This file holds the fp32-exact path: contractions run through the functor GEMM of gemm_simt.cuh.
+#include <cuda_bf16.h>
 #include "crnn_plan.cuh"
 #include "gemm_simt.cuh"
 #include "gru_scan.cuh"
@@ -191,6 +192,20 @@ __host__ __device__ inline unsigned long long block_seed(unsigned long long seed
     return seed * 0x2545F4914F6CDD1Dull + (unsigned long long)(block + 1) * 0xD6E8FEB86659FD93ull;
 }
 
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): the tensor-core operand format (tc_conv.cu)
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long i4,
+                                              const float4 v) {
+    __nv_bfloat16 h[4], l[4];
+    const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        h[q] = __float2bfloat16_rn(f[q]);
+        l[q] = __float2bfloat16_rn(f[q] - __bfloat162float(h[q]));
+    }
+    reinterpret_cast<uint2*>(hi)[i4] = *reinterpret_cast<uint2*>(h);
+    reinterpret_cast<uint2*>(lo)[i4] = *reinterpret_cast<uint2*>(l);
+}
+
 struct PoolGeom {
     int H, W, Wo, C, p;
     long oB, oH, oW, oC;         // strides of the block OUTPUT (channels-last, or the [B][T][flat] layout)
@@ -201,7 +216,7 @@ struct PoolGeom {
 // ----------------------------------------------------------------------------- BN + ReLU + max-pool(1,p) (+dropout)
 __global__ void __launch_bounds__(256)
 bn_relu_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ stat, float* __restrict__ out,
-                        long n_vec, PoolGeom g) {
+                        __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long n_vec, PoolGeom g) {
     const int C4 = g.C >> 2;
     const float keep_scale = g.drop_p > 0.0f ? 1.0f / (1.0f - g.drop_p) : 1.0f;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long)gridDim.x * blockDim.x) {
@@ -229,11 +244,14 @@ bn_relu_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ s
             m.z = uniform01(g.seed, e + 2) >= g.drop_p ? m.z * keep_scale : 0.0f;
             m.w = uniform01(g.seed, e + 3) >= g.drop_p ? m.w * keep_scale : 0.0f;
         }
-        float* dst = out + b * g.oB + h * g.oH + wo * g.oW + c * g.oC;
-        if (g.oC == 1) {
-            *reinterpret_cast<float4*>(dst) = m;
-        } else {
-            dst[0] = m.x; dst[g.oC] = m.y; dst[2 * g.oC] = m.z; dst[3 * g.oC] = m.w;
+        if (out_hi) store_planes4(out_hi, out_lo, i, m);        // channels-last planes: element index == 4*i
+        if (out) {
+            float* dst = out + b * g.oB + h * g.oH + wo * g.oW + c * g.oC;
+            if (g.oC == 1) {
+                *reinterpret_cast<float4*>(dst) = m;
+            } else {
+                dst[0] = m.x; dst[g.oC] = m.y; dst[2 * g.oC] = m.z; dst[3 * g.oC] = m.w;
+            }
         }
     }
 }
@@ -420,7 +438,8 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nblk,
 // pass 2: dy = scale * (dz - mean(dz) - xhat * mean(dz*xhat)) for EVERY conv output element
 __global__ void __launch_bounds__(256)
 bn_pool_bwd_dy_kernel(const float* __restrict__ y, const float* __restrict__ stat, const float* __restrict__ dA,
-                      const float* __restrict__ bnsum, long n_vec, PoolGeom g, float* __restrict__ dy) {
+                      const float* __restrict__ bnsum, long n_vec, PoolGeom g, float* __restrict__ dy,
+                      __nv_bfloat16* __restrict__ dy_hi, __nv_bfloat16* __restrict__ dy_lo) {
     const int C4 = g.C >> 2;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long)gridDim.x * blockDim.x) {
         const int c4 = (int)(i % C4);
@@ -448,7 +467,8 @@ bn_pool_bwd_dy_kernel(const float* __restrict__ y, const float* __restrict__ sta
             o.y = sc.y * ((wg.arg[1] == j && j < g.p ? wg.dz[1] : 0.0f) - k1.y - (v.y - mu.y) * is.y * k2.y);
             o.z = sc.z * ((wg.arg[2] == j && j < g.p ? wg.dz[2] : 0.0f) - k1.z - (v.z - mu.z) * is.z * k2.z);
             o.w = sc.w * ((wg.arg[3] == j && j < g.p ? wg.dz[3] : 0.0f) - k1.w - (v.w - mu.w) * is.w * k2.w);
-            *reinterpret_cast<float4*>(dy + (row + j) * g.C + c) = o;
+            if (dy) *reinterpret_cast<float4*>(dy + (row + j) * g.C + c) = o;
+            if (dy_hi) store_planes4(dy_hi, dy_lo, ((row + j) * g.C + c) >> 2, o);
         }
     }
 }
@@ -860,6 +880,15 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
                 conv0_fwd_stats_kernel<2><<<grid, 256, sm, st>>>(x, params + P.conv_w[0], params + P.conv_b[0], y, P.H, P.win[0], P.C, wsf(ws, P.part));
             SED_POST_LAUNCH();
             nblk = (int)(grid.x * grid.y);
+        } else if (P.conv_tc_all[i]) {
+            // plane-native: input planes were written by the previous block's pool kernel; BatchNorm partial sums
+            // come out of the conv epilogue
+            const char* ap = reinterpret_cast<const char*>(ws) + P.actp[i - 1];
+            rc = conv_tc_planes(ap, ap + P.act_plane_bytes[i - 1], params + P.conv_w[i], params + P.conv_b[i], y,
+                                training ? wsf(ws, P.part) : nullptr, batch, P.H, P.win[i], P.cin[i], P.C, 0,
+                                wsf(ws, P.tc), st);
+            if (rc) return rc;
+            nblk = conv_tc_stat_tiles(batch, P.H, P.win[i]);
         } else if (i > 0 && d->tensor_cores && conv_tc_supported(P.H, P.win[i], P.cin[i], P.C)) {
             rc = conv_tc_forward(in, params + P.conv_w[i], params + P.conv_b[i], y, batch, P.H, P.win[i], P.cin[i], P.C,
                                  0, wsf(ws, P.tc), P.tc_bytes, st);
@@ -872,7 +901,7 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
         }
         { char _nm[40]; snprintf(_nm, sizeof _nm, "bn%d.stats", i); SED_PROF(_nm, st);
         if (training) {
-            if (!direct0) {
+            if (!direct0 && !P.conv_tc_all[i]) {
                 rc = colsum_partials(y, M, P.C, wsf(ws, P.part), &nblk, st);
                 if (rc) return rc;
             }
@@ -888,7 +917,14 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
         const PoolGeom g = pool_geom(P, d, i, training, seed);
         const long n_vec = B * P.H * P.wout[i] * (P.C / 4);
 { char _nm[40]; snprintf(_nm, sizeof _nm, "pool%d.fwd", i); SED_PROF(_nm, st);
-        bn_relu_pool_fwd_kernel<<<ew_blocks(n_vec), 256, 0, st>>>(y, stat, wsf(ws, P.act[i]), n_vec, g);
+        {
+            // the consumer decides the format: a plane-native conv wants bf16 hi/lo planes only, the GRU wants the
+            // fp32 sequence (plus planes of it when its projection runs on tcgen05), everything else fp32
+            const bool to_planes = (i + 1 < P.n_conv) && P.conv_tc_all[i + 1];
+            __nv_bfloat16* ph = to_planes ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(ws) + P.actp[i]) : nullptr;
+            __nv_bfloat16* pl = to_planes ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(ws) + P.actp[i] + P.act_plane_bytes[i]) : nullptr;
+            bn_relu_pool_fwd_kernel<<<ew_blocks(n_vec), 256, 0, st>>>(y, stat, to_planes ? nullptr : wsf(ws, P.act[i]), ph, pl, n_vec, g);
+        }
         SED_POST_LAUNCH();
 }
     }
@@ -1126,8 +1162,10 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         }
         float* dy = wsf(ws, P.dy);
         const long n_vec = n_pix_out * (P.C / 4);
+        __nv_bfloat16* dyh = P.conv_tc_all[i] ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(ws) + P.dyp) : nullptr;
+        __nv_bfloat16* dyl = P.conv_tc_all[i] ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(ws) + P.dyp + P.dy_plane_bytes) : nullptr;
 { char _nm[40]; snprintf(_nm, sizeof _nm, "pool%d.bwd_dy", i); SED_PROF(_nm, st);
-        bn_pool_bwd_dy_kernel<<<ew_blocks(n_vec), 256, 0, st>>>(y, stat, dA, bnsum, n_vec, g, dy);
+        bn_pool_bwd_dy_kernel<<<ew_blocks(n_vec), 256, 0, st>>>(y, stat, dA, bnsum, n_vec, g, P.conv_tc_all[i] ? nullptr : dy, dyh, dyl);
         SED_POST_LAUNCH();
 }
 
@@ -1141,7 +1179,13 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         const int want = std::max(1, std::min(64, M / 2048));
         const int sp = gemm_simt_splits(M, want);
 { char _nm[40]; snprintf(_nm, sizeof _nm, "conv%d.wgrad", i); SED_PROF(_nm, st);
-        if (i > 0 && d->tensor_cores && wgrad_tc_supported(P.H, P.win[i], P.cin[i], P.C)) {
+        if (P.conv_tc_all[i]) {
+            const char* xp = reinterpret_cast<const char*>(ws) + P.actp[i - 1];
+            float* wpart = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + P.tc + conv_tc_weight_scratch_bytes(P.cin[i], P.C));
+            rc = wgrad_tc_planes(dyh, dyl, xp, xp + P.act_plane_bytes[i - 1], grads + P.conv_w[i], batch, P.H, P.win[i],
+                                 P.cin[i], P.C, wpart, st);
+            if (rc) return rc;
+        } else if (i > 0 && d->tensor_cores && wgrad_tc_supported(P.H, P.win[i], P.cin[i], P.C)) {
             rc = wgrad_tc(dy, in, grads + P.conv_w[i], batch, P.H, P.win[i], P.cin[i], P.C, wsf(ws, P.tc), P.tc_bytes, st);
             if (rc) return rc;
         } else {
@@ -1156,7 +1200,10 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         if (i > 0) {
             float* dprev = wsf(ws, P.dact[i & 1]);
 { char _nm[40]; snprintf(_nm, sizeof _nm, "conv%d.dgrad", i); SED_PROF(_nm, st);
-            if (d->tensor_cores && conv_tc_supported(P.H, P.win[i], P.C, P.cin[i]))
+            if (P.conv_tc_all[i])
+                rc = conv_tc_planes(dyh, dyl, params + P.conv_w[i], nullptr, dprev, nullptr, batch, P.H, P.win[i],
+                                    P.cin[i], P.C, 1, wsf(ws, P.tc), st);
+            else if (d->tensor_cores && conv_tc_supported(P.H, P.win[i], P.C, P.cin[i]))
                 rc = conv_tc_forward(dy, params + P.conv_w[i], nullptr, dprev, batch, P.H, P.win[i], P.cin[i], P.C, 1,
                                      wsf(ws, P.tc), P.tc_bytes, st);
             else

@@ -137,18 +137,37 @@ int make_plan(const sedb200_crnn_desc* d, int batch, Plan* p) {
         part = std::max(part, ((BT + 127) / 128) * ((long)P.dout[j] * P.din[j] + P.dout[j]));     // per-block dW/db partials
     }
     part = std::max(part, B * ((P.H + 7) / 8) * (long)std::max(2, P.cin[0] * 9 + 1) * P.C);   // direct block-0 partials
-    part = std::max(part, 148L * 16 * 2 * P.C);                                                 // BN backward sums
+    part = std::max(part, 148L * 16 * 2 * P.C);
+    for (int i = 1; i < P.n_conv; ++i) part = std::max(part, 2L * P.C * B * ((P.H * P.win[i] + 127) / 128 + 1));   // conv-epilogue BN partials                                                 // BN backward sums
     P.part_floats = (size_t)part;
     P.part = take(part);
+    // plane-native tensor-core blocks
+    auto plane = [](long n) { return ((size_t)n * 2 + 1023) & ~(size_t)1023; };
+    size_t dyp_bytes = 0;
+    for (int i = 0; i < P.n_conv; ++i) { P.conv_tc_all[i] = false; P.actp[i] = 0; P.act_plane_bytes[i] = 0; }
+    for (int i = 1; i < P.n_conv; ++i)
+        P.conv_tc_all[i] = d->tensor_cores && conv_tc_supported(P.H, P.win[i], P.cin[i], P.C) &&
+                           conv_tc_supported(P.H, P.win[i], P.C, P.cin[i]) && wgrad_tc_supported(P.H, P.win[i], P.cin[i], P.C);
+    for (int i = 0; i + 1 < P.n_conv; ++i)
+        if (P.conv_tc_all[i + 1]) {
+            P.act_plane_bytes[i] = plane(B * P.H * P.wout[i] * P.C);
+            P.actp[i] = take((long)(2 * P.act_plane_bytes[i] / 4));
+        }
+    for (int i = 1; i < P.n_conv; ++i)
+        if (P.conv_tc_all[i]) dyp_bytes = std::max(dyp_bytes, plane(B * P.H * P.win[i] * P.C));
+    P.dy_plane_bytes = dyp_bytes;
+    P.dyp = take((long)(2 * dyp_bytes / 4) + 64);
     // tensor-core scratch: bf16 operand planes + wgrad split-K partials
     size_t tc = 0;
+    for (int i = 1; i < P.n_conv; ++i)
+        if (P.conv_tc_all[i])
+            tc = std::max(tc, conv_tc_weight_scratch_bytes(P.cin[i], P.C) + wgrad_tc_part_bytes(P.cin[i], P.C) + 4096);
     if (d->tensor_cores)
         for (int i = 1; i < P.n_conv; ++i) {
             if (conv_tc_supported(P.H, P.win[i], P.cin[i], P.C)) tc = std::max(tc, conv_tc_scratch_bytes(batch, P.H, P.win[i], P.cin[i], P.C));
             if (conv_tc_supported(P.H, P.win[i], P.C, P.cin[i])) tc = std::max(tc, conv_tc_scratch_bytes(batch, P.H, P.win[i], P.C, P.cin[i]));
             if (wgrad_tc_supported(P.H, P.win[i], P.cin[i], P.C)) tc = std::max(tc, wgrad_tc_scratch_bytes(batch, P.H, P.win[i], P.cin[i], P.C));
         }
-    auto plane = [](long n) { return ((size_t)n * 2 + 1023) & ~(size_t)1023; };
     for (int l = 0; l < P.n_gru; ++l) {
         const int h6 = 6 * P.gh[l], in = P.gin[l];
         P.gru_tc[l] = d->tensor_cores && BT >= 1024 && gemm_tc_supported((int)BT, h6, in) && gemm_tc_supported(h6, in, (int)BT) &&

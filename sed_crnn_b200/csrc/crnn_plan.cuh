@@ -26,6 +26,12 @@ struct Plan {
     bool gru_tc[SEDB200_MAX_GRU];
     size_t hid[SEDB200_MAX_DENSE];
     size_t dy, dact[2], dseq[2], dgi, dgh, dhid[2], part, bnsum, tc;
+    // plane-native tensor-core flow: block i (>= 1) runs fwd, dgrad and wgrad on tcgen05 and exchanges
+    // bf16 hi/lo planes with its neighbours instead of fp32 tensors
+    bool conv_tc_all[SEDB200_MAX_CONV];
+    size_t actp[SEDB200_MAX_CONV];            // planes of block i's OUTPUT (2 x plane, when block i+1 is plane-native)
+    size_t dyp;                               // planes of dy (largest plane-native block)
+    size_t act_plane_bytes[SEDB200_MAX_CONV], dy_plane_bytes;
     size_t tc_bytes = 0;
     size_t part_floats = 0;
     size_t ws_bytes = 0;

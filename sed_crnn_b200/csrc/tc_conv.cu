@@ -62,7 +62,7 @@ constexpr int kStages = 3;
 constexpr int kTileM = 128, kTileN = 128, kBlockK = 64;
 constexpr int kTileBytes = kTileM * kBlockK * 2;                 // 16 KB: one bf16 operand tile
 constexpr int kStageBytes = 4 * kTileBytes;                      // A_hi, A_lo, B_hi, B_lo
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 4096 /*BN-stat staging*/;
 constexpr int kThreads = 256;
 constexpr uint32_t kTmemCols = 256;                              // two 128-column accumulators
 
@@ -71,6 +71,7 @@ struct ConvTcParams {
     float* out;              // [B*H*W][out_ld] fp32
     const float* bias;       // [n_total] or null
     long out_ld;
+    float* stats;            // null, or per-M-tile partial BatchNorm sums [m_tiles][2][n_total] (sum, sum of squares)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -85,6 +86,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint64_t* tfull = bars + 2 * kStages;     // [2]        MMA -> epilogue
     uint64_t* tempty = bars + 2 * kStages + 2;// [2]        epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    float* stat_s = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);     // [4 warps][2][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -165,17 +167,48 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             for (int cc = 0; cc < kTileN / 32; ++cc) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * kTileN + cc * 32, v);
-                if (valid) {
+                if (p.bias) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        if (p.bias) {
-                            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nt * kTileN + cc * 32 + j));
-                            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-                        }
-                        *reinterpret_cast<float4*>(dst + cc * 32 + j) = o;
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nt * kTileN + cc * 32 + j));
+                        v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
                     }
                 }
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(dst + cc * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+                if (p.stats) {
+                    // per-column sum / sum of squares over this warp's 32 rows: butterfly reduce-scatter, after which
+                    // lane L holds column cc*32 + L
+                    float s1[32], s2[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { s1[j] = valid ? v[j] : 0.0f; s2[j] = s1[j] * s1[j]; }
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int i = 0; i < off; ++i) {
+                            const float k1 = up ? s1[i + off] : s1[i], g1 = up ? s1[i] : s1[i + off];
+                            const float k2 = up ? s2[i + off] : s2[i], g2 = up ? s2[i] : s2[i + off];
+                            s1[i] = k1 + __shfl_xor_sync(0xffffffffu, g1, off);
+                            s2[i] = k2 + __shfl_xor_sync(0xffffffffu, g2, off);
+                        }
+                    }
+                    stat_s[(q * 2 + 0) * 128 + cc * 32 + lane] = s1[0];
+                    stat_s[(q * 2 + 1) * 128 + cc * 32 + lane] = s2[0];
+                }
+            }
+            if (p.stats) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int e = (warp - 4) * 32 + lane;                      // column of the tile
+                float a = 0.0f, b2 = 0.0f;
+#pragma unroll
+                for (int w4 = 0; w4 < 4; ++w4) { a += stat_s[(w4 * 2 + 0) * 128 + e]; b2 += stat_s[(w4 * 2 + 1) * 128 + e]; }
+                p.stats[((long)mt * 2 + 0) * p.n_total + nt * kTileN + e] = a;
+                p.stats[((long)mt * 2 + 1) * p.n_total + nt * kTileN + e] = b2;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
             }
             tc_fence_before();
             __syncwarp();
@@ -387,23 +420,16 @@ bool conv_tc_supported(int H, int W, int Cin, int Cout) {
     return Cin % 64 == 0 && Cout % 128 == 0 && W >= 1 && W <= 128 && (128 % W) == 0 && H >= 1;
 }
 
-int conv_tc_forward(const float* in, const float* w, const float* bias, float* out, int B, int H, int W, int Cin,
-                    int Cout, int dgrad, void* scratch, size_t scratch_bytes, cudaStream_t st) {
-    // dgrad: `in` is dY [B,H,W,Cout]; the result is dX [B,H,W,Cin]
+size_t conv_tc_weight_scratch_bytes(int Cin, int Cout) { return 2 * (((size_t)9 * Cout * Cin * 2 + 1023) & ~(size_t)1023); }
+
+// activation planes given ([B][H][W][Kc] bf16 hi / lo); weight planes are rebuilt into wscratch (tiny)
+int conv_tc_planes(const void* a_hi, const void* a_lo, const float* w, const float* bias, float* out, float* stats,
+                   int B, int H, int W, int Cin, int Cout, int dgrad, void* wscratch, cudaStream_t st) {
     const int Kc = dgrad ? Cout : Cin, Nc = dgrad ? Cin : Cout;
     SED_REQUIRE(conv_tc_supported(H, W, Kc, Nc), SEDB200_ESHAPE, "conv_tc: shape H=%d W=%d K=%d N=%d unsupported", H, W, Kc, Nc);
-    SED_REQUIRE(scratch_bytes >= conv_tc_scratch_bytes(B, H, W, Kc, Nc), SEDB200_EWORKSPACE, "conv_tc: scratch too small");
-    const size_t act = ((size_t)B * H * W * Kc * 2 + 1023) & ~(size_t)1023;
     const size_t wp = ((size_t)9 * Nc * Kc * 2 + 1023) & ~(size_t)1023;
-    char* s = reinterpret_cast<char*>(scratch);
-    __nv_bfloat16* a_hi = reinterpret_cast<__nv_bfloat16*>(s);
-    __nv_bfloat16* a_lo = reinterpret_cast<__nv_bfloat16*>(s + act);
-    __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(s + 2 * act);
-    __nv_bfloat16* w_lo = reinterpret_cast<__nv_bfloat16*>(s + 2 * act + wp);
-
-    const long n4 = (long)B * H * W * Kc / 4;
-    split_planes_kernel<<<(int)std::min<long>((n4 + 255) / 256, 148L * 8), 256, 0, st>>>(in, a_hi, a_lo, n4);
-    SED_POST_LAUNCH();
+    __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(wscratch);
+    __nv_bfloat16* w_lo = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(wscratch) + wp);
     weight_planes_kernel<<<(int)std::min<long>((9L * Cout * Cin + 255) / 256, 1184), 256, 0, st>>>(w, Cout, Cin, dgrad, w_hi, w_lo);
     SED_POST_LAUNCH();
 
@@ -434,7 +460,7 @@ int conv_tc_forward(const float* in, const float* w, const float* bias, float* o
     p.total_tiles = B * p.tiles_per_img * p.n_tiles_n;
     p.kchunks = Kc / kBlockK;
     p.n_total = Nc;
-    p.out = out; p.bias = bias; p.out_ld = Nc;
+    p.out = out; p.bias = bias; p.out_ld = Nc; p.stats = stats;
     static bool attr_done = false;
     if (!attr_done) {
         SED_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -444,6 +470,23 @@ int conv_tc_forward(const float* in, const float* w, const float* bias, float* o
     conv_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
     SED_POST_LAUNCH();
     return SEDB200_OK;
+}
+
+int conv_tc_stat_tiles(int B, int H, int W) { return B * ((H + kTileM / W - 1) / (kTileM / W)); }
+
+int conv_tc_forward(const float* in, const float* w, const float* bias, float* out, int B, int H, int W, int Cin,
+                    int Cout, int dgrad, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+    // dgrad: `in` is dY [B,H,W,Cout]; the result is dX [B,H,W,Cin]
+    const int Kc = dgrad ? Cout : Cin, Nc = dgrad ? Cin : Cout;
+    SED_REQUIRE(conv_tc_supported(H, W, Kc, Nc), SEDB200_ESHAPE, "conv_tc: shape H=%d W=%d K=%d N=%d unsupported", H, W, Kc, Nc);
+    SED_REQUIRE(scratch_bytes >= conv_tc_scratch_bytes(B, H, W, Kc, Nc), SEDB200_EWORKSPACE, "conv_tc: scratch too small");
+    const size_t act = ((size_t)B * H * W * Kc * 2 + 1023) & ~(size_t)1023;
+    char* s = reinterpret_cast<char*>(scratch);
+    const long n4 = (long)B * H * W * Kc / 4;
+    split_planes_kernel<<<(int)std::min<long>((n4 + 255) / 256, 148L * 8), 256, 0, st>>>(
+        in, reinterpret_cast<__nv_bfloat16*>(s), reinterpret_cast<__nv_bfloat16*>(s + act), n4);
+    SED_POST_LAUNCH();
+    return conv_tc_planes(s, s + act, w, bias, out, nullptr, B, H, W, Cin, Cout, dgrad, s + 2 * act, st);
 }
 
 
@@ -464,25 +507,12 @@ size_t wgrad_tc_scratch_bytes(int B, int H, int W, int Cin, int Cout) {
 
 // dw[Cout][Cin][3][3] = wgrad(dy[B,H,W,Cout], in[B,H,W,Cin]); if the bf16 planes already exist they can be
 // passed in (null -> they are produced here from the fp32 tensors)
-int wgrad_tc(const float* dy, const float* in, float* dw, int B, int H, int W, int Cin, int Cout, void* scratch,
-             size_t scratch_bytes, cudaStream_t st) {
-    SED_REQUIRE(wgrad_tc_supported(H, W, Cin, Cout), SEDB200_ESHAPE, "wgrad_tc: shape H=%d W=%d Cin=%d Cout=%d unsupported", H, W, Cin, Cout);
-    SED_REQUIRE(scratch_bytes >= wgrad_tc_scratch_bytes(B, H, W, Cin, Cout), SEDB200_EWORKSPACE, "wgrad_tc: scratch too small");
-    const size_t px = (size_t)B * H * W;
-    const size_t ysz = (px * Cout * 2 + 1023) & ~(size_t)1023, xsz = (px * Cin * 2 + 1023) & ~(size_t)1023;
-    char* s = reinterpret_cast<char*>(scratch);
-    __nv_bfloat16* y_hi = reinterpret_cast<__nv_bfloat16*>(s);
-    __nv_bfloat16* y_lo = reinterpret_cast<__nv_bfloat16*>(s + ysz);
-    __nv_bfloat16* x_hi = reinterpret_cast<__nv_bfloat16*>(s + 2 * ysz);
-    __nv_bfloat16* x_lo = reinterpret_cast<__nv_bfloat16*>(s + 2 * ysz + xsz);
-    float* part = reinterpret_cast<float*>(s + 2 * ysz + 2 * xsz);
-    long n4 = (long)px * Cout / 4;
-    split_planes_kernel<<<(int)std::min<long>((n4 + 255) / 256, 148L * 8), 256, 0, st>>>(dy, y_hi, y_lo, n4);
-    SED_POST_LAUNCH();
-    n4 = (long)px * Cin / 4;
-    split_planes_kernel<<<(int)std::min<long>((n4 + 255) / 256, 148L * 8), 256, 0, st>>>(in, x_hi, x_lo, n4);
-    SED_POST_LAUNCH();
+size_t wgrad_tc_part_bytes(int Cin, int Cout) { return (size_t)wgrad_slices(Cin, Cout) * 9 * Cout * Cin * 4; }
 
+// planes given: dY [B][H][W][Cout] and In [B][H][W][Cin] as bf16 hi / lo
+int wgrad_tc_planes(const void* y_hi, const void* y_lo, const void* x_hi, const void* x_lo, float* dw, int B, int H,
+                    int W, int Cin, int Cout, float* part, cudaStream_t st) {
+    SED_REQUIRE(wgrad_tc_supported(H, W, Cin, Cout), SEDB200_ESHAPE, "wgrad_tc: shape H=%d W=%d Cin=%d Cout=%d unsupported", H, W, Cin, Cout);
     const int Hk = kWgKp / W;
     CUtensorMap tmY_hi, tmY_lo, tmX_hi, tmX_lo;
     const uint32_t box[4] = {64, (uint32_t)W, (uint32_t)Hk, 1};
@@ -520,6 +550,26 @@ int wgrad_tc(const float* dy, const float* in, float* dw, int B, int H, int W, i
     wgrad_reduce_kernel<<<(int)std::min<long>((9L * Cout * Cin + 255) / 256, 1184), 256, 0, st>>>(part, p.slices, Cout, Cin, dw);
     SED_POST_LAUNCH();
     return SEDB200_OK;
+}
+
+// dw[Cout][Cin][3][3] = wgrad(dy[B,H,W,Cout], in[B,H,W,Cin]) from fp32 tensors (planes are produced here)
+int wgrad_tc(const float* dy, const float* in, float* dw, int B, int H, int W, int Cin, int Cout, void* scratch,
+             size_t scratch_bytes, cudaStream_t st) {
+    SED_REQUIRE(wgrad_tc_supported(H, W, Cin, Cout), SEDB200_ESHAPE, "wgrad_tc: shape H=%d W=%d Cin=%d Cout=%d unsupported", H, W, Cin, Cout);
+    SED_REQUIRE(scratch_bytes >= wgrad_tc_scratch_bytes(B, H, W, Cin, Cout), SEDB200_EWORKSPACE, "wgrad_tc: scratch too small");
+    const size_t px = (size_t)B * H * W;
+    const size_t ysz = (px * Cout * 2 + 1023) & ~(size_t)1023, xsz = (px * Cin * 2 + 1023) & ~(size_t)1023;
+    char* s = reinterpret_cast<char*>(scratch);
+    long n4 = (long)px * Cout / 4;
+    split_planes_kernel<<<(int)std::min<long>((n4 + 255) / 256, 148L * 8), 256, 0, st>>>(
+        dy, reinterpret_cast<__nv_bfloat16*>(s), reinterpret_cast<__nv_bfloat16*>(s + ysz), n4);
+    SED_POST_LAUNCH();
+    n4 = (long)px * Cin / 4;
+    split_planes_kernel<<<(int)std::min<long>((n4 + 255) / 256, 148L * 8), 256, 0, st>>>(
+        in, reinterpret_cast<__nv_bfloat16*>(s + 2 * ysz), reinterpret_cast<__nv_bfloat16*>(s + 2 * ysz + xsz), n4);
+    SED_POST_LAUNCH();
+    return wgrad_tc_planes(s, s + ysz, s + 2 * ysz, s + 2 * ysz + xsz, dw, B, H, W, Cin, Cout,
+                           reinterpret_cast<float*>(s + 2 * ysz + 2 * xsz), st);
 }
 
 }  // namespace sedb200

@@ -20,4 +20,14 @@ size_t wgrad_tc_scratch_bytes(int B, int H, int W, int Cin, int Cout);
 int wgrad_tc(const float* dy, const float* in, float* dw, int B, int H, int W, int Cin, int Cout, void* scratch,
              size_t scratch_bytes, cudaStream_t st);
 
+// ---- plane-native variants: the activation / gradient tensors already exist as bf16 hi / lo planes
+size_t conv_tc_weight_scratch_bytes(int Cin, int Cout);
+// stats (optional): per-M-tile partial BatchNorm sums [conv_tc_stat_tiles()][2][Cout] of the conv output (+bias)
+int conv_tc_stat_tiles(int B, int H, int W);
+int conv_tc_planes(const void* a_hi, const void* a_lo, const float* w, const float* bias, float* out, float* stats,
+                   int B, int H, int W, int Cin, int Cout, int dgrad, void* wscratch, cudaStream_t st);
+size_t wgrad_tc_part_bytes(int Cin, int Cout);
+int wgrad_tc_planes(const void* y_hi, const void* y_lo, const void* x_hi, const void* x_lo, float* dw, int B, int H,
+                    int W, int Cin, int Cout, float* part, cudaStream_t st);
+
 }  // namespace sedb200
