@@ -504,20 +504,22 @@ conv0_fwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ w,
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y, h0 = blockIdx.x * kC0Rows, c = blockIdx.z * 128 + lane * 4, Wp = W + 2;
     load_x_rows<CIN>(x, xs, b, h0, H, W);
-    float wr[4][CIN * 9], bs[4];
+    // weights as channel pairs: one packed fma.f32x2 updates two output channels (halves the FMA issue slots)
+    float2 wr[2][CIN * 9], bs[2];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        bs[q] = __ldg(bias + c + q);
+    for (int q = 0; q < 2; ++q) {
+        bs[q] = make_float2(__ldg(bias + c + 2 * q), __ldg(bias + c + 2 * q + 1));
 #pragma unroll
-        for (int k = 0; k < CIN * 9; ++k) wr[q][k] = __ldg(w + (long)(c + q) * CIN * 9 + k);
+        for (int k = 0; k < CIN * 9; ++k)
+            wr[q][k] = make_float2(__ldg(w + (long)(c + 2 * q) * CIN * 9 + k), __ldg(w + (long)(c + 2 * q + 1) * CIN * 9 + k));
     }
     __syncthreads();
-    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    float2 s1[2] = {make_float2(0, 0), make_float2(0, 0)}, s2[2] = {make_float2(0, 0), make_float2(0, 0)};
     const int h = h0 + warp;
     if (h < H) {
         float* yrow = y + ((long)b * H + h) * W * C + c;
         for (int ww = 0; ww < W; ++ww) {
-            float acc[4] = {bs[0], bs[1], bs[2], bs[3]};
+            float2 acc[2] = {bs[0], bs[1]};
 #pragma unroll
             for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
@@ -525,16 +527,20 @@ conv0_fwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ w,
 #pragma unroll
                     for (int t = 0; t < 3; ++t) {
                         const float xv = xs[(ci * (kC0Rows + 2) + warp + r) * Wp + ww + t];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) acc[q] = fmaf(wr[q][ci * 9 + r * 3 + t], xv, acc[q]);
+                        const float2 x2 = make_float2(xv, xv);
+                        acc[0] = __ffma2_rn(wr[0][ci * 9 + r * 3 + t], x2, acc[0]);
+                        acc[1] = __ffma2_rn(wr[1][ci * 9 + r * 3 + t], x2, acc[1]);
                     }
-            *reinterpret_cast<float4*>(yrow + (long)ww * C) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            *reinterpret_cast<float4*>(yrow + (long)ww * C) = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { s1[q] += acc[q]; s2[q] = fmaf(acc[q], acc[q], s2[q]); }
+            for (int q = 0; q < 2; ++q) { s1[q] = __fadd2_rn(s1[q], acc[q]); s2[q] = __ffma2_rn(acc[q], acc[q], s2[q]); }
         }
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { red[warp][0][lane * 4 + q] = s1[q]; red[warp][1][lane * 4 + q] = s2[q]; }
+    for (int q = 0; q < 2; ++q) {
+        red[warp][0][lane * 4 + 2 * q] = s1[q].x; red[warp][0][lane * 4 + 2 * q + 1] = s1[q].y;
+        red[warp][1][lane * 4 + 2 * q] = s2[q].x; red[warp][1][lane * 4 + 2 * q + 1] = s2[q].y;
+    }
     __syncthreads();
     {
         const int which = threadIdx.x >> 7, ch = threadIdx.x & 127;
@@ -621,19 +627,21 @@ conv0_bwd_fused_kernel(const float* __restrict__ x, const float* __restrict__ y,
 }
 
 
-// Same as conv0_bwd_fused_kernel with the pool width P known at compile time and W == Wo*P: the P conv
-// outputs of the NEXT window are already in flight while the current window is being consumed.
+// Same as conv0_bwd_fused_kernel with the pool width P known at compile time and W == Wo*P, PERSISTENT: a block
+// walks row groups (8 image rows each) with a stride of gridDim.x, keeps its dW / db accumulators in registers
+// across all of them and reduces once at the end (gridDim.x partials instead of one per row group).  The input
+// rows of the next group are fetched into the second shared buffer while the current group is consumed, and
+// the P conv outputs of the next pooling window are in flight while the current window is processed.
 template <int CIN, int P>
 __global__ void __launch_bounds__(256)
 conv0_bwd_fused_t_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ stat,
-                         const float* __restrict__ dA, const float* __restrict__ bnsum, PoolGeom g,
-                         float* __restrict__ part) {
-    extern __shared__ float xs[];
+                         const float* __restrict__ dA, const float* __restrict__ bnsum, PoolGeom g, int groups_per_img,
+                         int n_groups, float* __restrict__ part) {
+    extern __shared__ float xs_all[];                 // 2 x [CIN][10][W+2]
     __shared__ float red[kC0Rows][128];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.y, h0 = blockIdx.x * kC0Rows, c4 = blockIdx.z * 32 + lane, c = c4 * 4, Wp = g.W + 2;
-    const int C4 = g.C >> 2;
-    load_x_rows<CIN>(x, xs, b, h0, g.H, g.W);
+    const int c4 = blockIdx.y * 32 + lane, c = c4 * 4, Wp = g.W + 2;
+    const int C4 = g.C >> 2, xsz = CIN * (kC0Rows + 2) * Wp;
     const float4 sc = *reinterpret_cast<const float4*>(stat + 2 * g.C + c);
     const float4 sh = *reinterpret_cast<const float4*>(stat + 3 * g.C + c);
     const float4 mu = *reinterpret_cast<const float4*>(stat + c);
@@ -645,65 +653,77 @@ conv0_bwd_fused_t_kernel(const float* __restrict__ x, const float* __restrict__ 
     const float Bc[4] = {sc.x * is.x * k2.x, sc.y * is.y * k2.y, sc.z * is.z * k2.z, sc.w * is.w * k2.w};
     const float Ac[4] = {sc.x * k1.x - mu.x * Bc[0], sc.y * k1.y - mu.y * Bc[1], sc.z * k1.z - mu.z * Bc[2],
                          sc.w * k1.w - mu.w * Bc[3]};
-    float dw[4][CIN * 9 + 1];
+    float2 dw[2][CIN * 9 + 1];                        // channel pairs: packed fma.f32x2
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+    for (int q = 0; q < 2; ++q)
 #pragma unroll
-        for (int k = 0; k <= CIN * 9; ++k) dw[q][k] = 0.0f;
+        for (int k = 0; k <= CIN * 9; ++k) dw[q][k] = make_float2(0.0f, 0.0f);
+
+    int grp = blockIdx.x, buf = 0;
+    if (grp < n_groups) load_x_rows<CIN>(x, xs_all, grp / groups_per_img, (grp % groups_per_img) * kC0Rows, g.H, g.W);
     __syncthreads();
-    const int h = h0 + warp;
-    if (h < g.H) {
-        const float* yrow = y + (((long)b * g.H + h) * g.W) * g.C + c;
-        const float* darow = dA + (long)b * g.oB + (long)h * g.oH + (long)c * g.oC;
-        float4 v[P], vn[P];
-        float gq[4], gn[4];
-        load_window<P>(yrow, g.C, v);
-        load_dA(darow, g.oC, gq);
-        for (int wo = 0; wo < g.Wo; ++wo) {
-            if (wo + 1 < g.Wo) {
-                load_window<P>(yrow + (long)(wo + 1) * P * g.C, g.C, vn);
-                load_dA(darow + (long)(wo + 1) * g.oW, g.oC, gn);
+    for (; grp < n_groups; grp += gridDim.x, buf ^= 1) {
+        const float* xs = xs_all + buf * xsz;
+        const int b = grp / groups_per_img, h0 = (grp % groups_per_img) * kC0Rows;
+        const int nxt = grp + gridDim.x;
+        if (nxt < n_groups)                           // next group's input rows -> the other buffer
+            load_x_rows<CIN>(x, xs_all + (buf ^ 1) * xsz, nxt / groups_per_img, (nxt % groups_per_img) * kC0Rows, g.H, g.W);
+        const int h = h0 + warp;
+        if (h < g.H) {
+            const float* yrow = y + (((long)b * g.H + h) * g.W) * g.C + c;
+            const float* darow = dA + (long)b * g.oB + (long)h * g.oH + (long)c * g.oC;
+            float4 v[P], vn[P];
+            float gq[4], gn[4];
+            load_window<P>(yrow, g.C, v);
+            load_dA(darow, g.oC, gq);
+            for (int wo = 0; wo < g.Wo; ++wo) {
+                if (wo + 1 < g.Wo) {
+                    load_window<P>(yrow + (long)(wo + 1) * P * g.C, g.C, vn);
+                    load_dA(darow + (long)(wo + 1) * g.oW, g.oC, gn);
+                }
+                float dz[4], yarg[4];
+                int arg[4];
+                eval_window<P>(v, scv, shv, gq, g, (((long)b * g.H + h) * g.Wo + wo) * C4 + c4, dz, arg, yarg);
+#pragma unroll
+                for (int j = 0; j < P; ++j) {
+                    const float vv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                    float dyv[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) dyv[q] = fmaf(-Bc[q], vv[q], (arg[q] == j ? scv[q] * dz[q] : 0.0f) - Ac[q]);
+                    const int ww = wo * P + j;
+                    const float2 d01 = make_float2(dyv[0], dyv[1]), d23 = make_float2(dyv[2], dyv[3]);
+#pragma unroll
+                    for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+                        for (int r = 0; r < 3; ++r)
+#pragma unroll
+                            for (int t = 0; t < 3; ++t) {
+                                const float xv = xs[(ci * (kC0Rows + 2) + warp + r) * Wp + ww + t];
+                                const float2 x2 = make_float2(xv, xv);
+                                dw[0][ci * 9 + r * 3 + t] = __ffma2_rn(d01, x2, dw[0][ci * 9 + r * 3 + t]);
+                                dw[1][ci * 9 + r * 3 + t] = __ffma2_rn(d23, x2, dw[1][ci * 9 + r * 3 + t]);
+                            }
+                    dw[0][CIN * 9] = __fadd2_rn(dw[0][CIN * 9], d01);
+                    dw[1][CIN * 9] = __fadd2_rn(dw[1][CIN * 9], d23);
+                }
+#pragma unroll
+                for (int j = 0; j < P; ++j) v[j] = vn[j];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) gq[q] = gn[q];
             }
-            float dz[4], yarg[4];
-            int arg[4];
-            eval_window<P>(v, scv, shv, gq, g, (((long)b * g.H + h) * g.Wo + wo) * C4 + c4, dz, arg, yarg);
-#pragma unroll
-            for (int j = 0; j < P; ++j) {
-                const float vv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-                float dyv[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) dyv[q] = fmaf(-Bc[q], vv[q], (arg[q] == j ? scv[q] * dz[q] : 0.0f) - Ac[q]);
-                const int ww = wo * P + j;
-#pragma unroll
-                for (int ci = 0; ci < CIN; ++ci)
-#pragma unroll
-                    for (int r = 0; r < 3; ++r)
-#pragma unroll
-                        for (int t = 0; t < 3; ++t) {
-                            const float xv = xs[(ci * (kC0Rows + 2) + warp + r) * Wp + ww + t];
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) dw[q][ci * 9 + r * 3 + t] = fmaf(dyv[q], xv, dw[q][ci * 9 + r * 3 + t]);
-                        }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) dw[q][CIN * 9] += dyv[q];
-            }
-#pragma unroll
-            for (int j = 0; j < P; ++j) v[j] = vn[j];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) gq[q] = gn[q];
         }
+        __syncthreads();                              // everyone is done with xs[buf]; xs[buf^1] is complete
     }
-    const long blk = (long)blockIdx.y * gridDim.x + blockIdx.x;
 #pragma unroll
     for (int k = 0; k <= CIN * 9; ++k) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) red[warp][lane * 4 + q] = dw[q][k];
+        red[warp][lane * 4 + 0] = dw[0][k].x; red[warp][lane * 4 + 1] = dw[0][k].y;
+        red[warp][lane * 4 + 2] = dw[1][k].x; red[warp][lane * 4 + 3] = dw[1][k].y;
         __syncthreads();
         if (threadIdx.x < 128) {
             float t = 0.0f;
 #pragma unroll
             for (int r = 0; r < kC0Rows; ++r) t += red[r][threadIdx.x];
-            part[(blk * (CIN * 9 + 1) + k) * g.C + blockIdx.z * 128 + threadIdx.x] = t;
+            part[((long)blockIdx.x * (CIN * 9 + 1) + k) * g.C + blockIdx.y * 128 + threadIdx.x] = t;
         }
         __syncthreads();
     }
@@ -1145,18 +1165,23 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
             const dim3 grid((P.H + kC0Rows - 1) / kC0Rows, batch, P.C / 128);
             const size_t sm = (size_t)P.cin[0] * (kC0Rows + 2) * (P.win[0] + 2) * 4;
             const int J = P.cin[0] * 9;
-            const bool exact = (g.W == g.Wo * g.p);
-            if (exact && g.p == 5 && P.cin[0] == 1) conv0_bwd_fused_t_kernel<1, 5><<<grid, 256, sm, st>>>(x, y, stat, dA, bnsum, g, part);
-            else if (exact && g.p == 5 && P.cin[0] == 2) conv0_bwd_fused_t_kernel<2, 5><<<grid, 256, sm, st>>>(x, y, stat, dA, bnsum, g, part);
-            else if (exact && g.p == 2 && P.cin[0] == 1) conv0_bwd_fused_t_kernel<1, 2><<<grid, 256, sm, st>>>(x, y, stat, dA, bnsum, g, part);
-            else if (exact && g.p == 2 && P.cin[0] == 2) conv0_bwd_fused_t_kernel<2, 2><<<grid, 256, sm, st>>>(x, y, stat, dA, bnsum, g, part);
-            else if (P.cin[0] == 1)
+            const bool exact = (g.W == g.Wo * g.p) && (g.p == 5 || g.p == 2);
+            int nparts = (int)(grid.x * grid.y);
+            if (exact) {
+                const int gpi = (P.H + kC0Rows - 1) / kC0Rows, n_groups = gpi * batch;
+                const dim3 pgrid(std::min(n_groups, sm_count()), P.C / 128);
+                nparts = (int)pgrid.x;
+                if (g.p == 5 && P.cin[0] == 1) conv0_bwd_fused_t_kernel<1, 5><<<pgrid, 256, 2 * sm, st>>>(x, y, stat, dA, bnsum, g, gpi, n_groups, part);
+                else if (g.p == 5) conv0_bwd_fused_t_kernel<2, 5><<<pgrid, 256, 2 * sm, st>>>(x, y, stat, dA, bnsum, g, gpi, n_groups, part);
+                else if (P.cin[0] == 1) conv0_bwd_fused_t_kernel<1, 2><<<pgrid, 256, 2 * sm, st>>>(x, y, stat, dA, bnsum, g, gpi, n_groups, part);
+                else conv0_bwd_fused_t_kernel<2, 2><<<pgrid, 256, 2 * sm, st>>>(x, y, stat, dA, bnsum, g, gpi, n_groups, part);
+            } else if (P.cin[0] == 1)
                 conv0_bwd_fused_kernel<1><<<grid, 256, sm, st>>>(x, y, stat, dA, bnsum, g, part);
             else
                 conv0_bwd_fused_kernel<2><<<grid, 256, sm, st>>>(x, y, stat, dA, bnsum, g, part);
             SED_POST_LAUNCH();
             conv0_bwd_reduce_kernel<<<((J + 1) * P.C * 32 + 255) / 256, 256, 0, st>>>(
-                part, (int)(grid.x * grid.y), J, P.C, grads + P.conv_w[0], grads + P.conv_b[0]);
+                part, nparts, J, P.C, grads + P.conv_w[0], grads + P.conv_b[0]);
             SED_POST_LAUNCH();
             break;
         }
