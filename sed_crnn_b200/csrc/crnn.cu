@@ -495,15 +495,17 @@ __device__ __forceinline__ void load_x_rows(const float* __restrict__ x, float* 
     }
 }
 
+// persistent: a block walks row groups (8 image rows) with stride gridDim.x, BatchNorm partial sums stay in
+// registers across groups (one partial per block), next group's input rows are fetched while computing
 template <int CIN>
 __global__ void __launch_bounds__(256)
 conv0_fwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                       float* __restrict__ y, int H, int W, int C, float* __restrict__ part) {
-    extern __shared__ float xs[];                         // [CIN][10][W+2]
+                       float* __restrict__ y, int H, int W, int C, int groups_per_img, int n_groups,
+                       float* __restrict__ part) {
+    extern __shared__ float xs_all[];                     // 2 x [CIN][10][W+2]
     __shared__ float red[kC0Rows][2][128];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.y, h0 = blockIdx.x * kC0Rows, c = blockIdx.z * 128 + lane * 4, Wp = W + 2;
-    load_x_rows<CIN>(x, xs, b, h0, H, W);
+    const int c = blockIdx.y * 128 + lane * 4, Wp = W + 2, xsz = CIN * (kC0Rows + 2) * Wp;
     // weights as channel pairs: one packed fma.f32x2 updates two output channels (halves the FMA issue slots)
     float2 wr[2][CIN * 9], bs[2];
 #pragma unroll
@@ -513,28 +515,38 @@ conv0_fwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ w,
         for (int k = 0; k < CIN * 9; ++k)
             wr[q][k] = make_float2(__ldg(w + (long)(c + 2 * q) * CIN * 9 + k), __ldg(w + (long)(c + 2 * q + 1) * CIN * 9 + k));
     }
-    __syncthreads();
     float2 s1[2] = {make_float2(0, 0), make_float2(0, 0)}, s2[2] = {make_float2(0, 0), make_float2(0, 0)};
-    const int h = h0 + warp;
-    if (h < H) {
-        float* yrow = y + ((long)b * H + h) * W * C + c;
-        for (int ww = 0; ww < W; ++ww) {
-            float2 acc[2] = {bs[0], bs[1]};
+    int grp = blockIdx.x, buf = 0;
+    if (grp < n_groups) load_x_rows<CIN>(x, xs_all, grp / groups_per_img, (grp % groups_per_img) * kC0Rows, H, W);
+    __syncthreads();
+    for (; grp < n_groups; grp += gridDim.x, buf ^= 1) {
+        const float* xs = xs_all + buf * xsz;
+        const int b = grp / groups_per_img, h0 = (grp % groups_per_img) * kC0Rows;
+        const int nxt = grp + gridDim.x;
+        if (nxt < n_groups)
+            load_x_rows<CIN>(x, xs_all + (buf ^ 1) * xsz, nxt / groups_per_img, (nxt % groups_per_img) * kC0Rows, H, W);
+        const int h = h0 + warp;
+        if (h < H) {
+            float* yrow = y + ((long)b * H + h) * W * C + c;
+            for (int ww = 0; ww < W; ++ww) {
+                float2 acc[2] = {bs[0], bs[1]};
 #pragma unroll
-            for (int ci = 0; ci < CIN; ++ci)
+                for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
-                for (int r = 0; r < 3; ++r)
+                    for (int r = 0; r < 3; ++r)
 #pragma unroll
-                    for (int t = 0; t < 3; ++t) {
-                        const float xv = xs[(ci * (kC0Rows + 2) + warp + r) * Wp + ww + t];
-                        const float2 x2 = make_float2(xv, xv);
-                        acc[0] = __ffma2_rn(wr[0][ci * 9 + r * 3 + t], x2, acc[0]);
-                        acc[1] = __ffma2_rn(wr[1][ci * 9 + r * 3 + t], x2, acc[1]);
-                    }
-            *reinterpret_cast<float4*>(yrow + (long)ww * C) = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+                        for (int t = 0; t < 3; ++t) {
+                            const float xv = xs[(ci * (kC0Rows + 2) + warp + r) * Wp + ww + t];
+                            const float2 x2 = make_float2(xv, xv);
+                            acc[0] = __ffma2_rn(wr[0][ci * 9 + r * 3 + t], x2, acc[0]);
+                            acc[1] = __ffma2_rn(wr[1][ci * 9 + r * 3 + t], x2, acc[1]);
+                        }
+                *reinterpret_cast<float4*>(yrow + (long)ww * C) = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
 #pragma unroll
-            for (int q = 0; q < 2; ++q) { s1[q] = __fadd2_rn(s1[q], acc[q]); s2[q] = __ffma2_rn(acc[q], acc[q], s2[q]); }
+                for (int q = 0; q < 2; ++q) { s1[q] = __fadd2_rn(s1[q], acc[q]); s2[q] = __ffma2_rn(acc[q], acc[q], s2[q]); }
+            }
         }
+        __syncthreads();
     }
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -547,8 +559,7 @@ conv0_fwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ w,
         float t = 0.0f;
 #pragma unroll
         for (int r = 0; r < kC0Rows; ++r) t += red[r][which][ch];
-        const long blk = (long)blockIdx.y * gridDim.x + blockIdx.x;
-        part[(blk * 2 + which) * C + blockIdx.z * 128 + ch] = t;
+        part[((long)blockIdx.x * 2 + which) * C + blockIdx.y * 128 + ch] = t;
     }
 }
 
@@ -892,14 +903,15 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
         int nblk = 0;
         { char _nm[40]; snprintf(_nm, sizeof _nm, "conv%d.fwd", i); SED_PROF(_nm, st);
         if (direct0) {
-            const dim3 grid((P.H + kC0Rows - 1) / kC0Rows, batch, P.C / 128);
-            const size_t sm = (size_t)P.cin[0] * (kC0Rows + 2) * (P.win[0] + 2) * 4;
+            const int gpi = (P.H + kC0Rows - 1) / kC0Rows, n_groups = gpi * batch;
+            const dim3 grid(std::min(n_groups, 2 * sm_count()), P.C / 128);
+            const size_t sm = 2 * (size_t)P.cin[0] * (kC0Rows + 2) * (P.win[0] + 2) * 4;
             if (P.cin[0] == 1)
-                conv0_fwd_stats_kernel<1><<<grid, 256, sm, st>>>(x, params + P.conv_w[0], params + P.conv_b[0], y, P.H, P.win[0], P.C, wsf(ws, P.part));
+                conv0_fwd_stats_kernel<1><<<grid, 256, sm, st>>>(x, params + P.conv_w[0], params + P.conv_b[0], y, P.H, P.win[0], P.C, gpi, n_groups, wsf(ws, P.part));
             else
-                conv0_fwd_stats_kernel<2><<<grid, 256, sm, st>>>(x, params + P.conv_w[0], params + P.conv_b[0], y, P.H, P.win[0], P.C, wsf(ws, P.part));
+                conv0_fwd_stats_kernel<2><<<grid, 256, sm, st>>>(x, params + P.conv_w[0], params + P.conv_b[0], y, P.H, P.win[0], P.C, gpi, n_groups, wsf(ws, P.part));
             SED_POST_LAUNCH();
-            nblk = (int)(grid.x * grid.y);
+            nblk = (int)grid.x;
         } else if (P.conv_tc_all[i]) {
             // plane-native: input planes were written by the previous block's pool kernel; BatchNorm partial sums
             // come out of the conv epilogue
