@@ -104,7 +104,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -112,15 +112,27 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def wait_first(self, timeout=5.0):
+        """block until nvidia-smi has delivered its first sample (its start-up takes ~1 s)"""
+        t0 = time.perf_counter()
+        while not self.rows and time.perf_counter() - t0 < timeout and self.proc is not None:
+            time.sleep(0.02)
+
+    def mark(self):
+        return time.perf_counter()
+
+    def stop(self, t_begin=None, t_end=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        rows = [r for (t, r) in self.rows if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end)]
+        if not rows:
+            rows = [r for (_, r) in self.rows]
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -132,10 +144,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        # median over the busiest half of the samples (the sampler also sees idle gaps around the region)
-        busy = sm[len(sm) // 2:] if sm else []
-        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm), "window": "timed + end-to-end regions, 20 ms period"}
 
 
 # ------------------------------------------------------------------------------------------ reference arm
@@ -306,6 +316,7 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_first()
     for i in range(max(args.warmup, 3)):
         eng.train_step(xs[i % n_in], ys[i % n_in])
     barrier()
@@ -314,6 +325,7 @@ def run_ours(args, rank, world, local_rank):
     l0 = L.sedb200_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_clk0 = sampler.mark()
     e0.record()
     for i in range(args.steps):
         loss, _ = eng.train_step(xs[i % n_in], ys[i % n_in])
@@ -349,7 +361,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = frames_per_step / (t2.item() / args.steps * 1e-3)
-    clocks = sampler.stop() if rank == 0 else None          # sampled over warm-up + timed + e2e regions
+    clocks = sampler.stop(t_clk0, sampler.mark()) if rank == 0 else None
 
     # ---- phase breakdown (extra instrumented steps, CUDA events on the launching stream)
     L.sedb200_prof_enable(1)

@@ -235,3 +235,22 @@ def test_tensor_core_and_fp32_paths_agree(pkg):
     assert (outs[True][0] - outs[False][0]).abs().max().item() < 2e-5
     g0, g1 = outs[False][1], outs[True][1]
     assert (g1 - g0).norm().item() <= 2e-2 * g0.norm().item()
+
+
+def test_c5_shape_with_128_unit_gru(pkg):
+    """BASELINE configs[4] geometry at reduced batch/length: 256 filters (two 128-channel tensor-core N tiles)
+    and 3 x BiGRU(128) (shared-memory-resident W_hh scan)."""
+    rcfg, ref, cfg, eng = make_pair(pkg, "c5", {"seq_len": 32}, "bce", 1e-4, 1.0)
+    x, y = R.synth_batch(rcfg, 2, seed=9)
+    opt = R.make_adam(ref, 1e-3, 1e-4)
+    loss_ref, logits_ref, gn_ref = R.train_step(ref, opt, x, y, "bce", 1.0)
+    logits = eng.forward(x.cuda(), training=True)
+    np.testing.assert_allclose(logits.cpu().numpy(), logits_ref.numpy(), rtol=0, atol=5e-5)
+    loss, probs, dlog = eng.loss_and_grad(logits, y.cuda())
+    eng.backward(x.cuda(), dlog)
+    gn = eng.optimizer_step()
+    assert abs(gn.item() - gn_ref.item()) <= 2e-3 * gn_ref.item()
+    with torch.no_grad():
+        p1_ref = torch.sigmoid(ref(x))
+    p1 = eng.predict_proba(x.cuda(), training_bn=True).cpu()
+    assert (p1 - p1_ref).abs().max().item() <= PROB_TOL
