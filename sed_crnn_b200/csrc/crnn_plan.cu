@@ -86,8 +86,8 @@ int make_plan(const sedb200_crnn_desc* d, int batch, Plan* p) {
 
     // ---- workspace
     const long B = batch;
-    SED_REQUIRE(B * P.H * (long)P.win[0] * P.C < (1L << 31), SEDB200_ESHAPE,
-                "crnn: batch %d makes the largest activation exceed 2^31 elements", batch);
+    SED_REQUIRE(B * P.H * (long)P.win[0] < (1L << 31) / 16, SEDB200_ESHAPE,
+                "crnn: batch %d makes the pixel count of the first block exceed 2^27", batch);
     size_t o = 0;
     auto take = [&](long floats) { size_t at = o; o += (size_t)align_up(floats * 4, 256); return at; };
     long max_y = 0, max_act = 0;

@@ -121,7 +121,7 @@ class CRNNEngine:
             nbytes = int(self.L.sedb200_crnn_workspace_bytes(C.byref(self.desc), batch))
             if nbytes == 0:
                 _lib.check(self.L.sedb200_crnn_validate(C.byref(self.desc)))
-                raise _lib.Sedb200Error(_lib.ESHAPE, f"batch {batch} not supported")
+                raise _lib.Sedb200Error(_lib.ESHAPE, f"batch {batch}: " + self.L.sedb200_last_error().decode(errors="replace"))
             self._ws = None
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             self._ws_batch = batch

@@ -254,3 +254,35 @@ def test_c5_shape_with_128_unit_gru(pkg):
         p1_ref = torch.sigmoid(ref(x))
     p1 = eng.predict_proba(x.cuda(), training_bn=True).cpu()
     assert (p1 - p1_ref).abs().max().item() <= PROB_TOL
+
+
+def test_full_size_c2_properties(pkg):
+    """BASELINE configs[1] at its full size (batch 128, T 256) -- too slow for the CPU oracle, so checked through
+    size-independent properties: (1) bit-exact run-to-run determinism of a training step, (2) eval-mode forward
+    of the full batch == the two half batches run separately (per-sample independence outside train-mode BN),
+    (3) the gradient of one step equals the mean of the two half-batch gradients when BatchNorm statistics are
+    frozen is not testable (train-mode BN), so instead: the loss goes down over a few steps on a fixed batch."""
+    config, engine = pkg
+    cfg = config.C2
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(cfg.input_shape(128), generator=g).cuda()
+    y = (torch.rand(cfg.target_shape(128), generator=g) < 0.2).float().cuda()
+    runs = []
+    for _ in range(2):
+        eng = engine.CRNNEngine(cfg, loss="bce", seed=3)
+        eng.init_default(0)
+        losses = [eng.train_step(x, y)[0].item() for _ in range(4)]
+        runs.append((losses, eng.params.clone(), eng.bn_state.clone()))
+    assert runs[0][0] == runs[1][0]
+    assert torch.equal(runs[0][1], runs[1][1]) and torch.equal(runs[0][2], runs[1][2])
+    assert runs[0][0][-1] < runs[0][0][0] and all(np.isfinite(runs[0][0]))
+    full = eng.forward(x, training=False).clone()
+    lo = eng.forward(x[:64].contiguous(), training=False).clone()
+    hi = eng.forward(x[64:].contiguous(), training=False).clone()
+    assert torch.equal(full, torch.cat([lo, hi]))
+    probs = torch.sigmoid(full)
+    c = eng.threshold_counts(probs, y, 43).cpu().numpy()
+    O = (probs.cpu().numpy() > 0.5)
+    from sed_crnn_b200 import metrics as PM
+    got = PM.scores_from_counts(c)
+    assert got[2] == M.f1_overall_1sec(O, y.cpu().numpy(), 43) and got[3] == M.er_overall_1sec(O, y.cpu().numpy(), 43)
