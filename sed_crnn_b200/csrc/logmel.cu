@@ -38,17 +38,18 @@ constexpr int kM = kNfft / 2;            // complex FFT length 1024
 constexpr int kWarps = 16;               // warps (= frames in flight) per CTA
 constexpr int kBinStride = 33;           // bins walked per lane in the mel stage
 constexpr int kMaxSlots = 192;
+constexpr int kMaxTerms = 16;            // max lanes contributing to one mel band
 
 // Constant tables, built on the host in double precision, one copy per (device, sr).
 struct LogmelTables {
     float2 tw1[32 * 32];        // [a][t] = exp(-2 pi i t a / 1024)
     float  win[kNfft];          // periodic Hann
     float2 tw2[kM / 2 + 8];     // exp(-2 pi i k / 2048), k = 0..512
-    float2 binw[kBins + 7];     // per bin: weight for band binband[f] and binband[f]+1
-    unsigned char binband[kBins + 7];
-    short slotbase[kMel + 1];   // first partial-sum slot of each band
-    short firstlane[kMel + 1];  // first lane that contributes to each band
-    short count[kMel + 1];      // number of partial sums of each band
+    float2 binw[kBinStride * 32];   // per bin: weights for band binband[f] and binband[f]+1; the SIGN BIT of .y says
+                                    // "the band index steps up at this bin" (weights are >= 0); zero padded
+    unsigned char gather[(kMel + 1) * kMaxTerms];   // per band: the partial-sum slots to add, in lane order
+    unsigned char count[kMel + 1 + 7];              // number of partial sums of each band
+    unsigned char lanebase[32];                     // first slot of each lane (its bands take consecutive slots)
 };
 static_assert(sizeof(LogmelTables) % 16 == 0, "tables are copied as uint4");
 
@@ -57,8 +58,10 @@ constexpr int kPartBytes = kMaxSlots * 4;              // per-warp mel partial s
 constexpr int kSmemBytes = sizeof(LogmelTables) + kWarps * (kBufBytes + kPartBytes);
 
 // ------------------------------------------------------------------------------ device: FFT-32
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// complex add / subtract as ONE packed fp32x2 instruction each (sm_100 add.f32x2 / fma.f32x2): the (re, im)
+// pair of a float2 is exactly the register pair the packed pipe wants
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }
 // (a + ib)(c - is)
 __device__ __forceinline__ float2 cmul_conjtw(float2 d, float c, float s) {
     return make_float2(fmaf(d.y, s, d.x * c), fmaf(-d.x, s, d.y * c));
@@ -211,7 +214,7 @@ logmel_kernel(const float* __restrict__ pcm, float* __restrict__ out, int n_ch, 
             for (int m = 0; m < 16; ++m) {
                 const int k = lane + 32 * m;
                 const float2 w = tab.tw2[k];                                     // (cos, -sin)
-                const float2 e = make_float2(zk[m].x + zp[m].x, zk[m].y - zp[m].y);   // 2E
+                const float2 e = __ffma2_rn(zp[m], make_float2(1.0f, -1.0f), zk[m]);   // 2E = (zk.x+zp.x, zk.y-zp.y)
                 const float2 o = make_float2(zk[m].y + zp[m].y, zp[m].x - zk[m].x);   // 2O
                 const float2 t = cmul(o, w);                                     // 2 W^k O
                 const float2 xa = cadd(e, t), xb2 = csub(e, t);
@@ -222,28 +225,28 @@ logmel_kernel(const float* __restrict__ pcm, float* __restrict__ out, int n_ch, 
         }
         __syncwarp();
 
-        // ---- mel projection: each lane walks 33 consecutive bins, emitting one partial sum per
-        //      band it crosses into a statically assigned slot (deterministic summation order)
+        // ---- mel projection: each lane walks 33 consecutive bins with two running sums (band cur, cur+1); when
+        //      the band index steps up (static flag stored in the weight's sign bit) the finished sum goes to the
+        //      lane's next slot.  No data-dependent loop, fully unrolled, deterministic summation order.
         {
             const int f0 = lane * kBinStride;
-            const int f1 = min(f0 + kBinStride, kBins);
-            int cur = tab.binband[f0];
+            int k = tab.lanebase[lane];
             float a0 = 0.0f, a1 = 0.0f;
-            for (int f = f0; f < f1; ++f) {
-                const int b = tab.binband[f];
-                while (b > cur) {
-                    part[tab.slotbase[cur] + lane - tab.firstlane[cur]] = a0;
+#pragma unroll
+            for (int i = 0; i < kBinStride; ++i) {
+                const int f = f0 + i;
+                const float2 w = tab.binw[f];
+                const float p = f < kBins ? P[f] : 0.0f;
+                if (i > 0 && (__float_as_uint(w.y) >> 31)) {
+                    part[k++] = a0;
                     a0 = a1;
                     a1 = 0.0f;
-                    ++cur;
                 }
-                const float p = P[f];
-                const float2 w = tab.binw[f];
                 a0 = fmaf(w.x, p, a0);
-                a1 = fmaf(w.y, p, a1);
+                a1 = fmaf(fabsf(w.y), p, a1);
             }
-            part[tab.slotbase[cur] + lane - tab.firstlane[cur]] = a0;
-            part[tab.slotbase[cur + 1] + lane - tab.firstlane[cur + 1]] = a1;
+            part[k] = a0;
+            part[k + 1] = a1;
         }
         __syncwarp();
         {
@@ -254,9 +257,9 @@ logmel_kernel(const float* __restrict__ pcm, float* __restrict__ out, int n_ch, 
             for (int r = 0; r < 2; ++r) {
                 const int b = lane + 32 * r;
                 if (b < kMel) {
-                    const int base = tab.slotbase[b], n = tab.count[b];
+                    const int n = tab.count[b];
                     float acc = 0.0f;
-                    for (int i = 0; i < n; ++i) acc += part[base + i];
+                    for (int i = 0; i < n; ++i) acc += part[tab.gather[b * kMaxTerms + i]];
                     o[b] = logf(acc);
                 }
             }
@@ -314,7 +317,9 @@ int build_tables(int sr, LogmelTables& t) {
     std::vector<float> fb;
     build_mel(sr, fb);
     int prev = 0;
-    for (int f = 0; f < kBins; ++f) {
+    unsigned char band[kBinStride * 32];
+    for (int f = 0; f < kBinStride * 32; ++f) {
+        if (f >= kBins) { band[f] = (unsigned char)prev; t.binw[f] = make_float2(0.0f, 0.0f); continue; }
         int first = -1, last = -1;
         for (int b = 0; b < kMel; ++b)
             if (fb[(size_t)b * kBins + f] != 0.0f) {
@@ -322,34 +327,35 @@ int build_tables(int sr, LogmelTables& t) {
                 last = b;
             }
         if (first < 0) first = last = prev;
-        if (last > first + 1 || first < prev)
-            return fail(SEDB200_ESHAPE, "mel filterbank for sr=%d is not a 2-band-per-bin bank (bin %d)", sr, f);
-        t.binband[f] = (unsigned char)first;
-        t.binw[f] = make_float2(fb[(size_t)first * kBins + f],
-                                first + 1 < kMel ? fb[(size_t)(first + 1) * kBins + f] : 0.0f);
+        if (last > first + 1 || first < prev || first > prev + 1)
+            return fail(SEDB200_ESHAPE, "mel filterbank for sr=%d: bin %d does not fit the 2-bands-per-bin walk", sr, f);
+        band[f] = (unsigned char)first;
+        float w1 = first + 1 < kMel ? fb[(size_t)(first + 1) * kBins + f] : 0.0f;
+        if (first > prev) w1 = -w1;                       // sign bit = "band index steps up here" (-0.0f works too)
+        if (first > prev && w1 == 0.0f) w1 = -0.0f;
+        t.binw[f] = make_float2(fb[(size_t)first * kBins + f], w1);
         prev = first;
     }
-    // which lanes touch which bands -> slot layout
-    int lo_lane[kMel + 1], hi_lane[kMel + 1];
-    for (int b = 0; b <= kMel; ++b) lo_lane[b] = 1 << 20, hi_lane[b] = -1;
+    // slots: lane l covers bands [band[f0], band[f_last] + 1], one slot each, consecutive
+    int bmin[32], bmax[32], slots = 0;
     for (int l = 0; l < 32; ++l) {
         const int f0 = l * kBinStride, f1 = std::min(f0 + kBinStride, kBins);
         if (f0 >= kBins) return fail(SEDB200_ESHAPE, "bin walk layout broken");
-        const int b0 = t.binband[f0], b1 = t.binband[f1 - 1] + 1;
-        for (int b = b0; b <= b1; ++b) {
-            lo_lane[b] = std::min(lo_lane[b], l);
-            hi_lane[b] = std::max(hi_lane[b], l);
-        }
+        bmin[l] = band[f0];
+        bmax[l] = band[f1 - 1] + 1;
+        t.lanebase[l] = (unsigned char)slots;
+        slots += bmax[l] - bmin[l] + 1;
     }
-    int slots = 0;
+    if (slots > kMaxSlots || slots > 255) return fail(SEDB200_ESHAPE, "mel partial-sum slots %d too many", slots);
     for (int b = 0; b <= kMel; ++b) {
-        if (hi_lane[b] < 0) { lo_lane[b] = 0; hi_lane[b] = -1; }
-        t.slotbase[b] = (short)slots;
-        t.firstlane[b] = (short)lo_lane[b];
-        t.count[b] = (short)(hi_lane[b] - lo_lane[b] + 1);
-        slots += t.count[b];
+        int n = 0;
+        for (int l = 0; l < 32; ++l)
+            if (b >= bmin[l] && b <= bmax[l]) {
+                if (n >= kMaxTerms) return fail(SEDB200_ESHAPE, "mel band %d has more than %d partial sums", b, kMaxTerms);
+                t.gather[b * kMaxTerms + n++] = (unsigned char)(t.lanebase[l] + b - bmin[l]);
+            }
+        t.count[b] = (unsigned char)n;
     }
-    if (slots > kMaxSlots) return fail(SEDB200_ESHAPE, "mel partial-sum slots %d > %d", slots, kMaxSlots);
     return SEDB200_OK;
 }
 
