@@ -79,6 +79,17 @@ int    sedb200_logmel_host_f32(const float* pcm_host, int n_clips, int n_ch, lon
                                int sr, int pad_mode, float* out_host,
                                void* scratch_dev, size_t scratch_bytes, void* stream);
 
+/* Per-bin standardisation -- the step between the two halves of the hot path (feature.py:127-129:
+ * sklearn.preprocessing.StandardScaler().fit_transform(X_train) / .transform(X_test)).
+ * fit:   mean[c], var[c] (population variance), scale[c] = sqrt(var) (1.0 for constant columns) of x [rows][cols],
+ *        accumulated deterministically, float64 results (sklearn's mean_ / var_ / scale_ dtypes).
+ * apply: out = (x - mean) / scale, float32. */
+size_t sedb200_standardize_scratch_bytes(long rows, int cols);
+int    sedb200_standardize_fit(const float* x_dev, long rows, int cols, double* mean_dev, double* var_dev,
+                               double* scale_dev, void* scratch_dev, size_t scratch_bytes, void* stream);
+int    sedb200_standardize_apply(const float* x_dev, long rows, int cols, const double* mean_dev,
+                                 const double* scale_dev, float* out_dev, void* stream);
+
 /* Copy of the float32 [40][1025] mel filterbank the kernel uses (== librosa.filters.mel(sr=sr,
  * n_fft=2048, n_mels=40), feature.py:58) into a HOST buffer; for inspection / tests. */
 int    sedb200_mel_filterbank(int sr, float* out_host /* [40*1025] */);

@@ -114,4 +114,82 @@ int colsum(const float* X, long rows, int cols, float* out, float* scratch, cuda
     return SEDB200_OK;
 }
 
+
+// ---------------------------------------------------------------- per-bin standardisation (feature.py:127-129)
+namespace {
+// one warp per column: mean, population variance, scale (= sqrt(var), 1.0 for constant columns) in float64
+__global__ void standardize_final_kernel(const float* __restrict__ part, int nblk, int cols, long rows,
+                                         double* __restrict__ mean, double* __restrict__ var,
+                                         double* __restrict__ scale) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= cols) return;
+    double a = 0.0, b = 0.0;
+    for (int k = lane; k < nblk; k += 32) {
+        a += (double)__ldg(part + ((long)k * 2 + 0) * cols + c);
+        b += (double)__ldg(part + ((long)k * 2 + 1) * cols + c);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+        const double m = a / (double)rows;
+        double v = b / (double)rows - m * m;
+        if (v < 0.0) v = 0.0;
+        mean[c] = m;
+        var[c] = v;
+        // sklearn _handle_zeros_in_scale: (near-)constant features keep scale 1
+        scale[c] = (v <= 10.0 * 2.220446049250313e-16 * (m * m + 1e-300) || v == 0.0) ? 1.0 : sqrt(v);
+    }
+}
+__global__ void __launch_bounds__(256)
+standardize_apply_kernel(const float* __restrict__ X, long n, int cols, const double* __restrict__ mean,
+                         const double* __restrict__ scale, float* __restrict__ out) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cols);
+        out[i] = (float)((float)((double)__ldg(X + i) - mean[c]) / scale[c]);      // two roundings, like numpy in-place ops
+    }
+}
+}  // namespace
+
 }  // namespace sedb200
+
+using namespace sedb200;
+
+extern "C" {
+
+size_t sedb200_standardize_scratch_bytes(long rows, int cols) { return (size_t)colsum_scratch_floats(rows, cols) * 4; }
+
+int sedb200_standardize_fit(const float* x_dev, long rows, int cols, double* mean_dev, double* var_dev,
+                            double* scale_dev, void* scratch_dev, size_t scratch_bytes, void* stream) {
+    SED_REQUIRE(x_dev && mean_dev && var_dev && scale_dev && scratch_dev, SEDB200_EINVAL, "standardize_fit: null buffer");
+    SED_REQUIRE(rows >= 1 && cols >= 1, SEDB200_EINVAL, "standardize_fit: rows=%ld cols=%d", rows, cols);
+    SED_REQUIRE(scratch_bytes >= sedb200_standardize_scratch_bytes(rows, cols), SEDB200_EWORKSPACE, "standardize_fit: scratch too small");
+    int rc = require_sm100();
+    if (rc) return rc;
+    cudaStream_t st = as_stream(stream);
+    int nb = 0;
+    rc = colsum_partials(x_dev, rows, cols, reinterpret_cast<float*>(scratch_dev), &nb, st);
+    if (rc) return rc;
+    standardize_final_kernel<<<(cols * 32 + 255) / 256, 256, 0, st>>>(reinterpret_cast<float*>(scratch_dev), nb, cols, rows,
+                                                                    mean_dev, var_dev, scale_dev);
+    SED_POST_LAUNCH();
+    return SEDB200_OK;
+}
+
+int sedb200_standardize_apply(const float* x_dev, long rows, int cols, const double* mean_dev, const double* scale_dev,
+                              float* out_dev, void* stream) {
+    SED_REQUIRE(x_dev && mean_dev && scale_dev && out_dev, SEDB200_EINVAL, "standardize_apply: null buffer");
+    SED_REQUIRE(rows >= 0 && cols >= 1, SEDB200_EINVAL, "standardize_apply: rows=%ld cols=%d", rows, cols);
+    if (rows == 0) return SEDB200_OK;
+    int rc = require_sm100();
+    if (rc) return rc;
+    const long n = rows * cols;
+    standardize_apply_kernel<<<(int)std::min<long>((n + 255) / 256, 148L * 16), 256, 0, as_stream(stream)>>>(
+        x_dev, n, cols, mean_dev, scale_dev, out_dev);
+    SED_POST_LAUNCH();
+    return SEDB200_OK;
+}
+
+}  // extern "C"

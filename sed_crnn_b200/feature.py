@@ -90,3 +90,59 @@ def mel_filterbank(sr: int = SR) -> np.ndarray:
     out = np.empty((NB_MEL, NFFT // 2 + 1), dtype=np.float32)
     _lib.check(_lib.lib().sedb200_mel_filterbank(int(sr), out.ctypes.data))
     return out
+
+
+class StandardScaler:
+    """Drop-in for the `sklearn.preprocessing.StandardScaler` calls of feature.py:127-129 (fit on the training
+    frames, apply to both splits), computed on the GPU: deterministic per-bin sum / sum of squares reduction,
+    float64 statistics (`mean_`, `var_`, `scale_`, `n_samples_seen_`), float32 output.  Accepts CUDA tensors
+    (returns CUDA tensors) or numpy arrays (returns numpy)."""
+
+    def __init__(self):
+        self.mean_ = self.var_ = self.scale_ = None
+        self.n_samples_seen_ = 0
+        self._dev = None
+
+    @staticmethod
+    def _to_dev(X):
+        if isinstance(X, torch.Tensor):
+            if not X.is_cuda:
+                raise TypeError("StandardScaler needs CUDA tensors or numpy arrays (no CPU fallback)")
+            return X.contiguous().float(), False
+        return torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32)).cuda(), True
+
+    def fit(self, X):
+        x, _ = self._to_dev(X)
+        if x.dim() != 2 or x.shape[0] < 1:
+            raise ValueError("expected a non-empty 2-D array [frames, features]")
+        rows, cols = x.shape
+        L = _lib.lib()
+        stats = torch.empty(3, cols, dtype=torch.float64, device=x.device)
+        nbytes = int(L.sedb200_standardize_scratch_bytes(rows, cols))
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(L.sedb200_standardize_fit(x.data_ptr(), rows, cols, stats[0].data_ptr(), stats[1].data_ptr(),
+                                                 stats[2].data_ptr(), scratch.data_ptr(), nbytes,
+                                                 _lib.current_stream_ptr()))
+        self._dev = stats
+        host = stats.cpu().numpy()
+        self.mean_, self.var_, self.scale_ = host[0], host[1], host[2]
+        self.n_samples_seen_ = rows
+        return self
+
+    def transform(self, X):
+        if self._dev is None:
+            raise RuntimeError("StandardScaler.transform called before fit")
+        x, was_numpy = self._to_dev(X)
+        if x.dim() != 2 or x.shape[1] != self._dev.shape[1]:
+            raise ValueError("feature count differs from the fitted data")
+        stats = self._dev.to(x.device)
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().sedb200_standardize_apply(x.data_ptr(), x.shape[0], x.shape[1], stats[0].data_ptr(),
+                                                            stats[2].data_ptr(), out.data_ptr(),
+                                                            _lib.current_stream_ptr()))
+        return out.cpu().numpy() if was_numpy else out
+
+    def fit_transform(self, X):
+        return self.fit(X).transform(X)

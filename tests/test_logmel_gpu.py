@@ -105,3 +105,24 @@ def test_determinism(feat):
     a = feat.mbe_device(y)
     for _ in range(3):
         assert torch.equal(a, feat.mbe_device(y))
+
+
+def test_standard_scaler_matches_sklearn(feat):
+    """feature.py:127-129: StandardScaler fit on train frames, applied to train and test."""
+    sk = pytest.importorskip("sklearn.preprocessing")
+    rng = np.random.default_rng(3)
+    Xtr = (rng.standard_normal((20011, 40)) * rng.uniform(0.5, 3, 40) + rng.uniform(-8, 2, 40)).astype(np.float32)
+    Xtr[:, 7] = 1.25                                     # constant column -> scale 1
+    Xte = (rng.standard_normal((999, 40)) * 2 - 3).astype(np.float32)
+    ref = sk.StandardScaler()
+    want_tr, want_te = ref.fit_transform(Xtr.copy()), ref.transform(Xte.copy())
+    mine = feat.StandardScaler()
+    got_tr, got_te = mine.fit_transform(Xtr), mine.transform(Xte)
+    np.testing.assert_allclose(mine.mean_, ref.mean_, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(mine.var_, ref.var_, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(mine.scale_, ref.scale_, rtol=1e-5)
+    assert mine.n_samples_seen_ == 20011 and got_tr.dtype == np.float32
+    np.testing.assert_allclose(got_tr, want_tr, rtol=0, atol=2e-5)
+    np.testing.assert_allclose(got_te, want_te, rtol=0, atol=2e-5)
+    d = mine.transform(torch.from_numpy(Xte).cuda())
+    assert d.is_cuda and torch.equal(d.cpu(), torch.from_numpy(got_te))
