@@ -124,13 +124,13 @@ struct EpiStrided {                     // dx in NCHW from m = (b,h,w), n = ci
 
 // ----------------------------------------------------------------------------- BatchNorm statistics
 // stat layout: [0,C) mean, [C,2C) invstd, [2C,3C) scale = gamma*invstd, [3C,4C) shift = beta - mean*scale
-// deterministic warp-per-channel reduction of the per-block partials [nblk][2][C] (fixed lane
-// assignment + fixed shuffle tree => bit-reproducible)
+// deterministic block-per-channel reduction of the per-block partials [nblk][2][C]: fixed thread assignment,
+// fixed shuffle tree, fixed cross-warp order => bit-reproducible.  blockDim.x == 128.
 __device__ __forceinline__ void reduce_pair(const float* __restrict__ part, int nblk, int C, int c, double& s,
                                             double& ss) {
-    const int lane = threadIdx.x & 31;
+    __shared__ double sh[2][4];
     double a = 0.0, b = 0.0;
-    for (int k = lane; k < nblk; k += 32) {
+    for (int k = threadIdx.x; k < nblk; k += 128) {
         a += (double)__ldg(part + ((long)k * 2 + 0) * C + c);
         b += (double)__ldg(part + ((long)k * 2 + 1) * C + c);
     }
@@ -139,20 +139,22 @@ __device__ __forceinline__ void reduce_pair(const float* __restrict__ part, int 
         a += __shfl_xor_sync(0xffffffffu, a, o);
         b += __shfl_xor_sync(0xffffffffu, b, o);
     }
-    s = a;
-    ss = b;
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a; sh[1][threadIdx.x >> 5] = b; }
+    __syncthreads();
+    s = sh[0][0] + sh[0][1] + sh[0][2] + sh[0][3];
+    ss = sh[1][0] + sh[1][1] + sh[1][2] + sh[1][3];
 }
 
-// one warp per channel
-__global__ void bn_finalize_train_kernel(const float* __restrict__ part, int nblk, int C, long n,
+// one 128-thread block per channel
+__global__ void __launch_bounds__(128)
+bn_finalize_train_kernel(const float* __restrict__ part, int nblk, int C, long n,
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                          float eps, float momentum, float* __restrict__ running,
                                          float* __restrict__ stat) {
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (c >= C) return;
+    const int c = blockIdx.x;
     double s, ss;
     reduce_pair(part, nblk, C, c, s, ss);
-    if ((threadIdx.x & 31) != 0) return;
+    if (threadIdx.x != 0) return;
     const double mean = s / (double)n;
     double var = ss / (double)n - mean * mean;          // biased (normalisation)
     if (var < 0.0) var = 0.0;
@@ -421,14 +423,14 @@ bn_pool_bwd_sums_kernel(const float* __restrict__ y, const float* __restrict__ s
 }
 
 // reduce pass-1 partials: d(beta) = sum dz, d(gamma) = sum dz*xhat; bnsum = {mean dz, mean dz*xhat}
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int nblk, int C, long n,
+__global__ void __launch_bounds__(128)
+bn_bwd_finalize_kernel(const float* __restrict__ part, int nblk, int C, long n,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        float* __restrict__ bnsum) {
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per channel
-    if (c >= C) return;
+    const int c = blockIdx.x;                                        // one block per channel
     double s, sx;
     reduce_pair(part, nblk, C, c, s, sx);
-    if ((threadIdx.x & 31) != 0) return;
+    if (threadIdx.x != 0) return;
     dbeta[c] = (float)s;
     dgamma[c] = (float)sx;
     bnsum[c] = (float)(s / (double)n);
@@ -937,7 +939,7 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
                 rc = colsum_partials(y, M, P.C, wsf(ws, P.part), &nblk, st);
                 if (rc) return rc;
             }
-            bn_finalize_train_kernel<<<(P.C * 32 + 255) / 256, 256, 0, st>>>(
+            bn_finalize_train_kernel<<<P.C, 128, 0, st>>>(
                 wsf(ws, P.part), nblk, P.C, (long)M, params + P.bn_w[i], params + P.bn_b[i], d->bn_eps,
                 d->bn_momentum, running, stat);
         } else {
@@ -1168,7 +1170,7 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         SED_POST_LAUNCH();
 }
         float* bnsum = wsf(ws, P.bnsum);
-        bn_bwd_finalize_kernel<<<(P.C * 32 + 255) / 256, 256, 0, st>>>(part, nblk, P.C, n_elem, grads + P.bn_w[i],
+        bn_bwd_finalize_kernel<<<P.C, 128, 0, st>>>(part, nblk, P.C, n_elem, grads + P.bn_w[i],
                                                                  grads + P.bn_b[i], bnsum);
         SED_POST_LAUNCH();
         if (i == 0 && !dx && conv0_direct_ok(P.cin[0], P.C)) {

@@ -289,14 +289,17 @@ gru_scan_bwd_warp_kernel(const float* __restrict__ dout, const float* __restrict
                 dgh[o + j] = dar; dgh[o + H + j] = daz; dgh[o + 2 * H + j] = dq;
             }
             sb_r += dar; sb_z += daz; sb_n += dan; sb_q += dq;
-            float a0 = dht * z, a1 = 0.0f, a2 = 0.0f;
+            float a0 = dht * z, a1 = 0.0f, a2 = 0.0f, b0 = 0.0f, b1 = 0.0f, b2 = 0.0f;
 #pragma unroll
-            for (int k = 0; k < H; ++k) {
+            for (int k = 0; k < H; k += 2) {
                 a0 = fmaf(Ws[k * H + j], __shfl_sync(0xffffffffu, dar, k, H), a0);
                 a1 = fmaf(Ws[(H + k) * H + j], __shfl_sync(0xffffffffu, daz, k, H), a1);
                 a2 = fmaf(Ws[(2 * H + k) * H + j], __shfl_sync(0xffffffffu, dq, k, H), a2);
+                b0 = fmaf(Ws[(k + 1) * H + j], __shfl_sync(0xffffffffu, dar, k + 1, H), b0);
+                b1 = fmaf(Ws[(H + k + 1) * H + j], __shfl_sync(0xffffffffu, daz, k + 1, H), b1);
+                b2 = fmaf(Ws[(2 * H + k + 1) * H + j], __shfl_sync(0xffffffffu, dq, k + 1, H), b2);
             }
-            dh = a0 + a1 + a2;
+            dh = (a0 + b0) + (a1 + b1) + (a2 + b2);
         }
 #pragma unroll
         for (int s = 0; s < kChB; ++s)

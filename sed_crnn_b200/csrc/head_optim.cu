@@ -60,12 +60,17 @@ loss_kernel(int kind, float alpha, float gamma, const float* __restrict__ logits
     if (threadIdx.x == 0) part[blockIdx.x] = tot;
 }
 
+// one warp: fixed lane assignment + fixed shuffle tree (deterministic)
+__device__ __forceinline__ double warp_total(const float* __restrict__ part, int nblk) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nblk; i += 32) s += (double)part[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
 __global__ void loss_final_kernel(const float* __restrict__ part, int nblk, long n, float* __restrict__ loss) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double s = 0.0;
-        for (int i = 0; i < nblk; ++i) s += (double)part[i];
-        loss[0] = (float)(s / (double)n);
-    }
+    const double s = warp_total(part, nblk);
+    if (threadIdx.x == 0) loss[0] = (float)(s / (double)n);
 }
 
 __global__ void __launch_bounds__(256)
@@ -81,11 +86,8 @@ sumsq_kernel(const float* __restrict__ g, long n, float prescale, float* __restr
 }
 
 __global__ void gnorm_final_kernel(const float* __restrict__ part, int nblk, float* __restrict__ gnorm) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double s = 0.0;
-        for (int i = 0; i < nblk; ++i) s += (double)part[i];
-        gnorm[0] = (float)sqrt(s);
-    }
+    const double s = warp_total(part, nblk);
+    if (threadIdx.x == 0) gnorm[0] = (float)sqrt(s);
 }
 
 __global__ void __launch_bounds__(256)
