@@ -341,20 +341,26 @@ def run_ours(args, rank, world, local_rank):
     value = frames_per_step / (ms_step * 1e-3)
     final_loss = loss.item()
 
-    # ---- end-to-end: pinned host batch -> H2D -> step -> D2H loss, every step
-    xd, yd = torch.empty_like(xs[0]), torch.empty_like(ys[0])
+    # ---- end-to-end through the public API with HOST batches: every step copies its pinned host batch to the
+    #      device (parallel.DevicePrefetcher: batch i+1 is copied on a side stream while batch i trains, the way
+    #      DataLoader(pin_memory=True) is meant to be used) and reads the loss back to the host (sed.py:138)
+    from sed_crnn_b200.parallel import DevicePrefetcher
     loss_h = torch.empty(1).pin_memory()
-    for i in range(2):
-        xd.copy_(xs_h[i % n_in], non_blocking=True); yd.copy_(ys_h[i % n_in], non_blocking=True)
-        l, _ = eng.train_step(xd, yd); loss_h.copy_(l.reshape(1), non_blocking=True)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        xd.copy_(xs_h[i % n_in], non_blocking=True)
-        yd.copy_(ys_h[i % n_in], non_blocking=True)
+
+    def host_batches(n):
+        for i in range(n):
+            yield xs_h[i % n_in], ys_h[i % n_in]
+
+    for xd, yd, k in DevicePrefetcher(host_batches(2)):
         l, _ = eng.train_step(xd, yd)
+    barrier()
+    pf = DevicePrefetcher(host_batches(args.steps))
+    e0.record()
+    for xd, yd, k in pf:
+        l, _ = eng.train_step(xd, yd)
+        pf.release(k)
         loss_h.copy_(l.reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()          # the caller reads the loss every step (sed.py:138)
+        torch.cuda.current_stream().synchronize()          # the caller reads the loss every step
     e1.record()
     barrier()
     t2 = torch.tensor([e0.elapsed_time(e1)], device="cuda")

@@ -56,3 +56,56 @@ def broadcast_(flat: torch.Tensor, src: int = 0, group=None) -> None:
     _, world = world_info(group)
     if world > 1:
         dist.broadcast(flat, src=src, group=group)
+
+
+class DevicePrefetcher:
+    """Iterate over (x, y) HOST batches (pinned, as the reference's DataLoader(pin_memory=True) yields them,
+    decorte_datamodule.py:130-137) and hand out DEVICE batches, copying batch i+1 on a side stream while batch i
+    is being trained on.  Two device buffer pairs are rotated; the consumer stream waits on the copy event, and
+    the copy stream waits until the consumer has finished with the buffer it is about to overwrite."""
+
+    def __init__(self, batches, device="cuda"):
+        self.it = iter(batches)
+        self.device = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.bufs = [None, None]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.freed = [torch.cuda.Event(), torch.cuda.Event()]
+        self.slot = 0
+        self.pending = None
+        self._enqueue()
+
+    def _enqueue(self):
+        try:
+            x, y = next(self.it)
+        except StopIteration:
+            self.pending = None
+            return
+        k = self.slot
+        if self.bufs[k] is None or self.bufs[k][0].shape != x.shape or self.bufs[k][1].shape != y.shape:
+            self.bufs[k] = (torch.empty(x.shape, dtype=x.dtype, device=self.device),
+                            torch.empty(y.shape, dtype=y.dtype, device=self.device))
+        else:
+            self.copy_stream.wait_event(self.freed[k])
+        with torch.cuda.stream(self.copy_stream):
+            self.bufs[k][0].copy_(x, non_blocking=True)
+            self.bufs[k][1].copy_(y, non_blocking=True)
+            self.ready[k].record(self.copy_stream)
+        self.pending = k
+        self.slot ^= 1
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self.pending is None:
+            raise StopIteration
+        k = self.pending
+        torch.cuda.current_stream(self.device).wait_event(self.ready[k])
+        out = self.bufs[k]
+        self._enqueue()                       # start copying the following batch right away
+        return out[0], out[1], k
+
+    def release(self, k: int) -> None:
+        """call after the work that reads buffer pair k has been enqueued on the current stream"""
+        self.freed[k].record(torch.cuda.current_stream(self.device))

@@ -135,3 +135,18 @@ def test_cpu_call_fails_loudly(mods):
     m = cl.TimePooledCRNN()
     with pytest.raises(RuntimeError, match="CUDA"):
         m(torch.zeros(2, 1, 40, 64))
+
+
+def test_device_prefetcher_orders_and_overlaps(mods):
+    from sed_crnn_b200.parallel import DevicePrefetcher
+    g = torch.Generator().manual_seed(0)
+    host = [(torch.randn(8, 1, 40, 64, generator=g).pin_memory(), torch.rand(8, 8, 1, generator=g).pin_memory())
+            for _ in range(5)]
+    seen = []
+    pf = DevicePrefetcher(iter(host))
+    for x, y, k in pf:
+        seen.append((x.clone(), y.clone()))
+        pf.release(k)
+    assert len(seen) == 5
+    for (xh, yh), (xd, yd) in zip(host, seen):
+        assert torch.equal(xd.cpu(), xh) and torch.equal(yd.cpu(), yh)
