@@ -208,15 +208,19 @@ def parse_prof(L):
     return out
 
 
-def logmel_leg(torch, feature, L, pk, rank):
-    """BASELINE configs[2] leg: bulk log-mel of 3-min stereo clips resident in HBM (kernel-only, CUDA
-    events) and end-to-end through feature.mbe_batch-style host buffers."""
+def logmel_leg(torch, feature, L, pk, rank, world=1, dist=None):
+    """BASELINE configs[2] leg: bulk log-mel of 3-min stereo clips.  Clips shard by index across ranks with NO
+    collective (parallel.clip_ids_for_rank); every rank keeps `n_clips` synthetic clips resident in HBM
+    (kernel-only, CUDA events, max over ranks) and rank 0 also measures the host-buffer path."""
     n_clips, S = 32, 180 * 44100
-    x = torch.empty(n_clips, 2, S, device="cuda").normal_(0, 0.1)            # 2.03 GB > L2
+    g = torch.Generator(device="cuda").manual_seed(1000 + rank)
+    x = torch.empty(n_clips, 2, S, device="cuda").normal_(0, 0.1, generator=g)            # 2.03 GB > L2
     out = torch.empty(n_clips, feature.n_frames(S), 80, device="cuda")
     for _ in range(3):
         feature.mbe_device(x, out=out)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     iters = 10
     e0.record()
@@ -224,33 +228,42 @@ def logmel_leg(torch, feature, L, pk, rank):
         feature.mbe_device(x, out=out)
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
+    t = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
     alg_bytes = x.numel() * 4 + out.numel() * 4
     gbs = alg_bytes / ms / 1e6
-    # e2e: pinned host PCM -> device -> kernel -> host log-mel, 4 clips per call
-    hb = torch.empty(4, 2, S).normal_(0, 0.1).pin_memory()
-    ho = torch.empty(4, feature.n_frames(S), 80).pin_memory()
-    for _ in range(2):
-        feature.mbe_device(hb.cuda(non_blocking=True), out=out[:4]); ho.copy_(out[:4], non_blocking=True)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    reps = 5
-    for _ in range(reps):
-        d = hb.cuda(non_blocking=True)
-        feature.mbe_device(d, out=out[:4])
-        ho.copy_(out[:4], non_blocking=True)
-        torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / reps
-    del x
-    return {
-        "workload": f"{n_clips} synthetic 3-min stereo clips resident in HBM (2.03 GB in, > L2), kernel-only",
-        "audio_s_per_s": n_clips * 180.0 / (ms * 1e-3), "frames_per_s": n_clips * 2 * feature.n_frames(S) / (ms * 1e-3),
-        "ms_per_launch": ms, "ten_k_clips_s_est": 10000 / n_clips * ms * 1e-3,
-        "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
-                     "traffic": None, "peak_source": pk["src"]},
-        "e2e": {"audio_s_per_s": 4 * 180.0 / e2e_s, "h2d_bytes_per_call": hb.numel() * 4,
-                "d2h_bytes_per_call": ho.numel() * 4},
+    res = {
+        "workload": f"{n_clips} synthetic 3-min stereo clips per GPU resident in HBM (2.03 GB in, > L2), kernel-only, "
+                    f"{world} GPU(s), clips sharded by index, no collective",
+        "audio_s_per_s": world * n_clips * 180.0 / (ms * 1e-3),
+        "frames_per_s": world * n_clips * 2 * feature.n_frames(S) / (ms * 1e-3),
+        "ms_per_launch": ms, "ten_k_clips_s_est": 10000 / (n_clips * world) * ms * 1e-3,
+        "roofline": {"bound": "hbm", "kernel": "logmel_kernel", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
+                     "frac": gbs / pk["hbm"], "traffic": 528320256 * n_clips / 8, "per_gpu": True,
+                     "peak_source": pk["src"],
+                     "traffic_source": "profiles/r01_logmel_full.ncu-rep (8 clips: 508.5 MB read + 19.8 MB written), scaled"},
     }
+    if rank == 0:
+        # e2e: pinned host PCM -> device -> kernel -> host log-mel, 4 clips per call
+        hb = torch.empty(4, 2, S).normal_(0, 0.1).pin_memory()
+        ho = torch.empty(4, feature.n_frames(S), 80).pin_memory()
+        for _ in range(2):
+            feature.mbe_device(hb.cuda(non_blocking=True), out=out[:4]); ho.copy_(out[:4], non_blocking=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            d = hb.cuda(non_blocking=True)
+            feature.mbe_device(d, out=out[:4])
+            ho.copy_(out[:4], non_blocking=True)
+            torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / reps
+        res["e2e"] = {"audio_s_per_s": 4 * 180.0 / e2e_s, "h2d_bytes_per_call": hb.numel() * 4,
+                      "d2h_bytes_per_call": ho.numel() * 4, "note": "one rank, PCIe-bound"}
+    del x
+    return res
 
 
 def cpu_baselines(args, torch):
@@ -378,6 +391,9 @@ def run_ours(args, rank, world, local_rank):
     prof = parse_prof(L)
     L.sedb200_prof_enable(0)
 
+    lm = None
+    if not args.no_logmel:
+        lm = logmel_leg(torch, feature, L, pk, rank, world, dist if world > 1 else None)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -437,8 +453,8 @@ def run_ours(args, rank, world, local_rank):
     if world == 1:
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baselines(args, torch)
-        if not args.no_logmel:
-            line["logmel"] = logmel_leg(torch, feature, L, pk, rank)
+    if lm is not None:
+        line["logmel"] = lm
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -313,6 +313,170 @@ gru_scan_bwd_warp_kernel(const float* __restrict__ dout, const float* __restrict
     }
 }
 
+
+// ------------------------------------------------------------------------------ H = 64 / 128: K-split scans
+// W_hh no longer fits one lane per unit, so each hidden unit is served by FOUR adjacent lanes that each keep a
+// quarter of the unit's three W_hh rows in registers (3*H/4 values) and reduce with two xor-shuffles; the CTA
+// (4*H threads) owns kSplitBT batch rows of one direction, the hidden state is double-buffered in shared memory
+// (one block barrier per step).  Lane `ks` of a unit's quad also does the gate math of batch row `ks`.
+constexpr int kSplitBT = 2;
+
+template <int H>
+__global__ void __launch_bounds__(4 * H, 1)
+gru_scan_fwd_split_kernel(const float* __restrict__ gi, const float* __restrict__ whh, const float* __restrict__ bhh,
+                          float* __restrict__ out, float* __restrict__ gates, int B, int T) {
+    constexpr int KS = H / 4, H3 = 3 * H, HP = H + 16;          // HP: row pitch with 4 floats of padding per K-slice
+    __shared__ __align__(16) float h_s[2][kSplitBT][HP];
+    const int tid = threadIdx.x, ks = tid & 3, j = tid >> 2;
+    const int dir = blockIdx.y, b0 = blockIdx.x * kSplitBT;
+    const float* W = whh + (size_t)dir * H3 * H;
+    float w[3][KS];
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+        for (int kk = 0; kk < KS; ++kk) w[g][kk] = __ldg(W + (size_t)(g * H + j) * H + ks * KS + kk);
+    float bias[3];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) bias[g] = __ldg(bhh + dir * H3 + g * H + j);
+    for (int i = tid; i < 2 * kSplitBT * HP; i += blockDim.x) (&h_s[0][0][0])[i] = 0.0f;
+    const bool gate = ks < kSplitBT && (b0 + ks) < B;            // this lane finishes unit j of batch row b0 + ks
+    const long b = b0 + ks;
+    float hprev = 0.0f, nr = 0, nz = 0, nn = 0;
+    auto load_gi = [&](int t) {
+        const float* g = gi + ((b * T + t) * 2 + dir) * H3;
+        nr = __ldg(g + j); nz = __ldg(g + H + j); nn = __ldg(g + 2 * H + j);
+    };
+    if (gate) load_gi(dir ? T - 1 : 0);
+    __syncthreads();
+    int cur = 0;
+    for (int step = 0; step < T; ++step) {
+        const int t = dir ? T - 1 - step : step;
+        const float cr = nr, cz = nz, cn = nn;
+        if (gate && step + 1 < T) load_gi(dir ? t - 1 : t + 1);
+        float acc[kSplitBT][3];
+#pragma unroll
+        for (int r = 0; r < kSplitBT; ++r) acc[r][0] = acc[r][1] = acc[r][2] = 0.0f;
+#pragma unroll
+        for (int kk = 0; kk < KS; kk += 4) {
+#pragma unroll
+            for (int r = 0; r < kSplitBT; ++r) {
+                const float4 hv = *reinterpret_cast<const float4*>(&h_s[cur][r][ks * (KS + 4) + kk]);
+#pragma unroll
+                for (int g = 0; g < 3; ++g) {
+                    acc[r][g] = fmaf(w[g][kk + 0], hv.x, acc[r][g]);
+                    acc[r][g] = fmaf(w[g][kk + 1], hv.y, acc[r][g]);
+                    acc[r][g] = fmaf(w[g][kk + 2], hv.z, acc[r][g]);
+                    acc[r][g] = fmaf(w[g][kk + 3], hv.w, acc[r][g]);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kSplitBT; ++r)
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                acc[r][g] += __shfl_xor_sync(0xffffffffu, acc[r][g], 1);
+                acc[r][g] += __shfl_xor_sync(0xffffffffu, acc[r][g], 2);
+            }
+        if (gate) {
+            const float g0 = (ks == 0 ? acc[0][0] : acc[1][0]) + bias[0];
+            const float g1 = (ks == 0 ? acc[0][1] : acc[1][1]) + bias[1];
+            const float g2 = (ks == 0 ? acc[0][2] : acc[1][2]) + bias[2];
+            const float r = fast_sigmoid(cr + g0);
+            const float z = fast_sigmoid(cz + g1);
+            const float n = fast_tanh(fmaf(r, g2, cn));
+            hprev = fmaf(z, hprev - n, n);
+            h_s[cur ^ 1][ks][j + 4 * (j / KS)] = hprev;
+            out[(b * T + t) * 2 * H + dir * H + j] = hprev;
+            float* gs = gates + ((b * T + t) * 2 + dir) * 4 * H;
+            gs[j] = r; gs[H + j] = z; gs[2 * H + j] = n; gs[3 * H + j] = g2;
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+}
+
+template <int H>
+__global__ void __launch_bounds__(4 * H, 1)
+gru_scan_bwd_split_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                          const float* __restrict__ gates, const float* __restrict__ whh, float* __restrict__ dgi,
+                          float* __restrict__ dgh, float* __restrict__ part_b, int B, int T) {
+    constexpr int H3 = 3 * H, RS = H3 / 4, DP = H3 + 16;        // RS rows of W_hh per K-slice; padded pitch
+    __shared__ __align__(16) float dg_s[2][kSplitBT][DP];
+    const int tid = threadIdx.x, ks = tid & 3, j = tid >> 2;
+    const int dir = blockIdx.y, b0 = blockIdx.x * kSplitBT;
+    const float* W = whh + (size_t)dir * H3 * H;
+    float wc[RS];                                               // W_hh[ks*RS + i][j]
+#pragma unroll
+    for (int i = 0; i < RS; ++i) wc[i] = __ldg(W + (size_t)(ks * RS + i) * H + j);
+    const bool gate = ks < kSplitBT && (b0 + ks) < B;
+    const long b = b0 + ks;
+    float dh = 0.0f, sb_r = 0, sb_z = 0, sb_n = 0, sb_q = 0;
+    float n_do = 0, n_r = 0, n_z = 0, n_n = 0, n_q = 0, n_hp = 0;
+    auto load_step = [&](int t) {
+        n_do = __ldg(dout + (b * T + t) * 2 * H + dir * H + j);
+        const float* gs = gates + ((b * T + t) * 2 + dir) * 4 * H;
+        n_r = __ldg(gs + j); n_z = __ldg(gs + H + j); n_n = __ldg(gs + 2 * H + j); n_q = __ldg(gs + 3 * H + j);
+        const int tp = dir ? t + 1 : t - 1;
+        n_hp = (tp >= 0 && tp < T) ? __ldg(out + (b * T + tp) * 2 * H + dir * H + j) : 0.0f;
+    };
+    if (gate) load_step(dir ? 0 : T - 1);
+    for (int i = tid; i < 2 * kSplitBT * DP; i += blockDim.x) (&dg_s[0][0][0])[i] = 0.0f;
+    __syncthreads();
+    // slot of gradient element e (0..3H-1) inside the padded row: 4 floats of padding per K-slice
+    auto pad = [&](int e) { return e + 4 * (e / RS); };
+    int cur = 0;
+    for (int step = 0; step < T; ++step) {
+        const int t = dir ? step : T - 1 - step;
+        float direct = 0.0f;
+        if (gate) {
+            const float c_do = n_do, r = n_r, z = n_z, n = n_n, q = n_q, hp = n_hp;
+            if (step + 1 < T) load_step(dir ? t + 1 : t - 1);
+            const float dht = c_do + dh;
+            const float dn = dht * (1.0f - z);
+            const float dz = dht * (hp - n);
+            direct = dht * z;
+            const float dan = dn * (1.0f - n * n);
+            const float dar = dan * q * r * (1.0f - r);
+            const float daz = dz * z * (1.0f - z);
+            const float dq = dan * r;
+            const long o = ((b * T + t) * 2 + dir) * H3;
+            dgi[o + j] = dar; dgi[o + H + j] = daz; dgi[o + 2 * H + j] = dan;
+            dgh[o + j] = dar; dgh[o + H + j] = daz; dgh[o + 2 * H + j] = dq;
+            sb_r += dar; sb_z += daz; sb_n += dan; sb_q += dq;
+            dg_s[cur][ks][pad(j)] = dar;
+            dg_s[cur][ks][pad(H + j)] = daz;
+            dg_s[cur][ks][pad(2 * H + j)] = dq;
+        }
+        __syncthreads();
+        float acc[kSplitBT];
+#pragma unroll
+        for (int r = 0; r < kSplitBT; ++r) acc[r] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < RS; i += 4) {
+#pragma unroll
+            for (int r = 0; r < kSplitBT; ++r) {
+                const float4 dv = *reinterpret_cast<const float4*>(&dg_s[cur][r][ks * (RS + 4) + i]);
+                acc[r] = fmaf(wc[i + 0], dv.x, acc[r]);
+                acc[r] = fmaf(wc[i + 1], dv.y, acc[r]);
+                acc[r] = fmaf(wc[i + 2], dv.z, acc[r]);
+                acc[r] = fmaf(wc[i + 3], dv.w, acc[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kSplitBT; ++r) {
+            acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 1);
+            acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 2);
+        }
+        if (gate) dh = direct + (ks == 0 ? acc[0] : acc[1]);
+        cur ^= 1;
+    }
+    if (gate) {
+        float* pb = part_b + (b * 2) * 2 * H3;                  // [B][ih|hh][2][3H]
+        pb[dir * H3 + j] = sb_r; pb[dir * H3 + H + j] = sb_z; pb[dir * H3 + 2 * H + j] = sb_n;
+        pb[2 * H3 + dir * H3 + j] = sb_r; pb[2 * H3 + dir * H3 + H + j] = sb_z; pb[2 * H3 + dir * H3 + 2 * H + j] = sb_q;
+    }
+}
+
 template <int H>
 int launch_warp_fwd(const float* gi, const float* whh, const float* bhh, float* out, float* gates, int B, int T,
                     cudaStream_t st) {
@@ -341,6 +505,13 @@ int gru_scan_forward(const float* gi, const float* whh, const float* bhh, float*
     if (H == 32) return launch_warp_fwd<32>(gi, whh, bhh, out, gates, B, T, st);
     if (H == 16) return launch_warp_fwd<16>(gi, whh, bhh, out, gates, B, T, st);
     if (H == 8) return launch_warp_fwd<8>(gi, whh, bhh, out, gates, B, T, st);
+    if (H == 128 || H == 64) {
+        dim3 grid((B + kSplitBT - 1) / kSplitBT, 2);
+        if (H == 128) gru_scan_fwd_split_kernel<128><<<grid, 512, 0, st>>>(gi, whh, bhh, out, gates, B, T);
+        else gru_scan_fwd_split_kernel<64><<<grid, 256, 0, st>>>(gi, whh, bhh, out, gates, B, T);
+        SED_POST_LAUNCH();
+        return SEDB200_OK;
+    }
     const int threads = round32(std::max(3 * H, kBT * H));
     SED_REQUIRE(threads <= 1024 && H % 4 == 0, SEDB200_ESHAPE, "gru_scan: H=%d unsupported", H);
     const size_t smem = ((size_t)3 * H * H + kBT * H + kBT * 3 * H) * 4;
@@ -353,13 +524,20 @@ int gru_scan_forward(const float* gi, const float* whh, const float* bhh, float*
     return SEDB200_OK;
 }
 
-bool gru_scan_fused_param_grads(int H) { return H == 32 || H == 16 || H == 8; }
+bool gru_scan_fused_param_grads(int H) { return H == 128 || H == 64 || H == 32 || H == 16 || H == 8; }
 
 int gru_scan_backward(const float* dout, const float* out, const float* gates, const float* whh, float* dgi,
                       float* dgh, float* part_w, float* part_b, int B, int T, int H, cudaStream_t st) {
     if (H == 32) return launch_warp_bwd<32>(dout, out, gates, whh, dgi, dgh, part_w, part_b, B, T, st);
     if (H == 16) return launch_warp_bwd<16>(dout, out, gates, whh, dgi, dgh, part_w, part_b, B, T, st);
     if (H == 8) return launch_warp_bwd<8>(dout, out, gates, whh, dgi, dgh, part_w, part_b, B, T, st);
+    if (H == 128 || H == 64) {
+        dim3 grid((B + kSplitBT - 1) / kSplitBT, 2);
+        if (H == 128) gru_scan_bwd_split_kernel<128><<<grid, 512, 0, st>>>(dout, out, gates, whh, dgi, dgh, part_b, B, T);
+        else gru_scan_bwd_split_kernel<64><<<grid, 256, 0, st>>>(dout, out, gates, whh, dgi, dgh, part_b, B, T);
+        SED_POST_LAUNCH();
+        return SEDB200_OK;
+    }
     const int threads = round32(kBT * H);
     SED_REQUIRE(threads <= 1024 && H % 4 == 0, SEDB200_ESHAPE, "gru_scan: H=%d unsupported", H);
     const size_t smem = ((size_t)3 * H * H + kBT * 3 * H) * 4;
