@@ -194,6 +194,30 @@ int sedb200_threshold_counts(const float* probs_dev, const float* targets_dev, l
                              int block, float threshold, unsigned long long* counts_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Window sampler: HitWindowDataset.__getitem__ for a whole batch (decorte_datamodule.py:88-111, sed.py:72-76).
+ * The fold's feature matrix mel_dev [n_frames][n_ch*n_feat] and label matrix lab_dev [n_frames][n_lab] stay in
+ * HBM; per step only the window starts (and SpecAugment offsets) are uploaded.
+ *   layout 0 (fork, crnn_lightning.py:66):  x[b][c][f][t] = mel[starts[b]+t][c*n_feat+f]   -> [batch][n_ch][n_feat][seq_in]
+ *   layout 1 (SEDnet, time-major):          x[b][c][t][f] = same element                    -> [batch][n_ch][seq_in][n_feat]
+ *   y[b][j][k] = max_{p < seq_in/seq_out} lab[starts[b] + j*seq_in/seq_out + p][k]          (decorte_datamodule.py:101)
+ * SpecAugment (decorte_datamodule.py:39-49): for each of n_masks masks, frames [tmask[b][i], +time_mask_w) and mel
+ * bins [fmask[b][i], +freq_mask_w) are zeroed; an offset < 0 disables that mask; tmask_dev / fmask_dev may be NULL.
+ * y_dev may be NULL (features only). */
+int sedb200_window_batch_f32(const float* mel_dev, const float* lab_dev, long n_frames, int n_ch, int n_feat,
+                             int n_lab, const long* starts_dev, int batch, int seq_in, int seq_out,
+                             const int* tmask_dev, const int* fmask_dev, int n_masks, int time_mask_w,
+                             int freq_mask_w, int layout, float* x_dev, float* y_dev, void* stream);
+/* _find_clean_negatives (decorte_datamodule.py:19-23, sed.py:48-52): flag_dev[s] = 1 iff none of the frames
+ * [s, s+seq_in) has lab[.][0] == 1, for s in [0, n_frames-seq_in]. */
+int sedb200_clean_negatives(const float* lab_dev, long n_frames, int n_lab, int seq_in, unsigned char* flag_dev,
+                            void* stream);
+/* Label rasterisation (feature.py:89-93): for every event i, lab[s:e][col] = 1.0 with
+ * s = int(floor(start_s[i]*sr/hop)), e = int(ceil(end_s[i]*sr/hop)) and Python slice clamping.  lab_dev
+ * [n_frames][n_lab] is NOT cleared by the call (feature.py:88 zero-fills it first). */
+int sedb200_rasterize_labels(const double* start_s_dev, const double* end_s_dev, int n_events, int sr, int hop,
+                             long n_frames, int n_lab, int col, float* lab_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Tensor-core building block, exposed for unit tests: one 3x3 / pad 1 convolution (nn.Conv2d(.., 3,
  * padding=1), crnn_lightning.py:47) or its data gradient on channels-last fp32 tensors, computed on
  * tcgen05 with the 3-term bf16 split.  in [B][H][W][Cin] -> out [B][H][W][Cout] (dgrad: in = dY

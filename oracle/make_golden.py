@@ -11,6 +11,7 @@ Fixtures written (all small, committed):
   crnn_fork_lightning.npz  crnn_lightning.TimePooledCRNN: weights, batch, logits, loss, grads,
                            and probabilities after one clip(1.0)+Adam(wd 1e-4) step
   crnn_fork_sedpy.npz      sed.TimePooledCRNN(conv_channels=32): same, BCE, Adam(wd 0), no clip
+  window_sampler.npz       decorte_datamodule.HitWindowDataset (plain + SpecAugment) items, _find_clean_negatives
   logmel_oracle.npz        NOT from the reference (librosa absent): frozen output of
                            oracle/logmel_ref.py, a regression anchor only (parity unpinned)
 """
@@ -139,9 +140,41 @@ def logmel_anchor():
     print("logmel_oracle:", {k: v.shape for k, v in out.items() if "_pcm" not in k})
 
 
+def window_sampler():
+    """HitWindowDataset of the UNMODIFIED reference decorte_datamodule.py under fixed seeds."""
+    import random
+    dm = ref_import.load("decorte_datamodule")
+    rng = np.random.default_rng(11)
+    n = 900
+    mel = rng.standard_normal((n, 40)).astype(np.float32)
+    lab = np.zeros((n, 1), np.float32)
+    for a, b in ((70, 75), (200, 203), (204, 260), (500, 501), (880, 900)):
+        lab[a:b, 0] = 1.0
+    out = dict(mel=mel, lab=lab, neg_starts=np.asarray(dm._find_clean_negatives(lab), dtype=np.int64))
+    idx = np.arange(24)
+    for name, aug in (("plain", False), ("aug", True)):
+        random.seed(5)
+        np.random.seed(6)
+        ds = dm.HitWindowDataset(mel, lab, augment=aug)
+        items = [ds[int(i)] for i in idx]
+        out[f"{name}_x"] = np.stack([it[0].numpy() for it in items])
+        out[f"{name}_y"] = np.stack([it[1].numpy() for it in items])
+        out[f"{name}_len"] = np.int64(len(ds))
+        out[f"{name}_pos_frames"] = np.asarray(ds.pos_frames, dtype=np.int64)
+    out["idx"] = idx
+    out["seeds"] = np.array([5, 6])
+    np.savez_compressed(os.path.join(OUT, "window_sampler.npz"), **out)
+    print("window_sampler:", out["plain_x"].shape, out["plain_y"].shape, "neg starts", out["neg_starts"].size,
+          "masked zeros", int((out["aug_x"] == 0).sum()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--only-window" in sys.argv:
+        window_sampler()
+        sys.exit(0)
     metrics_kat()
     loss_kat()
     crnn_fork()
     logmel_anchor()
+    window_sampler()

@@ -53,6 +53,9 @@ SIGNATURES = {
     "sedb200_clip_adam_scratch_bytes": (_sz, [_l]),
     "sedb200_clip_adam": (_i, [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _l, _f, _f, _p, _p, _sz, _p]),
     "sedb200_threshold_counts": (_i, [_p, _p, _l, _i, _i, _f, _p, _p]),
+    "sedb200_window_batch_f32": (_i, [_p, _p, _l, _i, _i, _i, _p, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "sedb200_clean_negatives": (_i, [_p, _l, _i, _i, _p, _p]),
+    "sedb200_rasterize_labels": (_i, [_p, _p, _i, _i, _i, _l, _i, _i, _p, _p]),
     "sedb200_conv3x3_tc_scratch_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "sedb200_conv3x3_wgrad_tc_scratch_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "sedb200_conv3x3_wgrad_tc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),

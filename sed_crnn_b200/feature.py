@@ -92,6 +92,26 @@ def mel_filterbank(sr: int = SR) -> np.ndarray:
     return out
 
 
+def rasterize_labels(starts_s, ends_s, n_frames: int, sr: int = SR, hop: int = HOP,
+                     out: torch.Tensor | None = None, col: int = 0) -> torch.Tensor:
+    """feature.py:88-93 on the device: frame labels [n_frames, 1] (CUDA float32) from event start / end times in
+    seconds, `lbl[floor(start*SR/HOP) : ceil(end*SR/HOP), 0] = 1.0` with Python slice clamping."""
+    a = torch.as_tensor(np.asarray(starts_s, dtype=np.float64)).reshape(-1)
+    b = torch.as_tensor(np.asarray(ends_s, dtype=np.float64)).reshape(-1)
+    if a.numel() != b.numel():
+        raise ValueError("starts and ends differ in length")
+    if out is None:
+        out = torch.zeros(n_frames, 1, dtype=torch.float32, device="cuda")
+    elif not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.shape[0] == n_frames):
+        raise ValueError("out must be a contiguous CUDA float32 [n_frames, n_lab] tensor")
+    ev = torch.stack([a, b]).to(out.device).contiguous()
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.lib().sedb200_rasterize_labels(ev[0].data_ptr(), ev[1].data_ptr(), a.numel(), int(sr), int(hop),
+                                                       n_frames, out.shape[1], col, out.data_ptr(),
+                                                       _lib.current_stream_ptr()))
+    return out
+
+
 class StandardScaler:
     """Drop-in for the `sklearn.preprocessing.StandardScaler` calls of feature.py:127-129 (fit on the training
     frames, apply to both splits), computed on the GPU: deterministic per-bin sum / sum of squares reduction,
