@@ -8,7 +8,10 @@
 //     -> twiddle W_1024^(lane*a), transpose via smem }   (one shared-memory exchange)
 //     -> 32-point DFT in registers over lane         }
 //     -> real-FFT untangle of bins (k, 1024-k), |X|^2                    feature.py:57
-//     -> sparse mel projection (<= 2 bands per bin), deterministic order feature.py:58-59
+//        (each lane keeps its own half of every pair in registers; only the partner half crosses shared memory)
+//     -> mel projection: the triangular filters are linear in the bin index between band edges, so each lane
+//        only accumulates (sum P, sum i*P) per band-edge segment of its 33 bins -- no per-bin weight loads --
+//        and 40 bands are closed with <= 8 (A, B) coefficient pairs each, fixed order   feature.py:58-59
 //     -> logf, 160 B coalesced store per (frame, channel)                feature.py:59
 //
 // The frame never touches HBM between the PCM load and the 40 output floats, so algorithmic HBM
@@ -37,25 +40,29 @@ constexpr int kMel = SEDB200_NMEL;       // 40
 constexpr int kM = kNfft / 2;            // complex FFT length 1024
 constexpr int kWarps = 16;               // warps (= frames in flight) per CTA
 constexpr int kBinStride = 33;           // bins walked per lane in the mel stage
-constexpr int kMaxSlots = 192;
-constexpr int kMaxTerms = 16;            // max lanes contributing to one mel band
+constexpr int kMaxSlots = 96;            // (lane, segment) partial sums
+constexpr int kMaxTerms = 12;            // max partial sums feeding one mel band
+constexpr int kBandsRound1 = 32;         // bands kMel-32 .. kMel-1 are closed by lanes 0..31, the rest in a second round
 
 // Constant tables, built on the host in double precision, one copy per (device, sr).
 struct LogmelTables {
     float2 tw1[32 * 32];        // [a][t] = exp(-2 pi i t a / 1024)
-    float  win[kNfft];          // periodic Hann
+    float  win[kNfft / 2];      // first half of the periodic Hann window; w[n + 1024] = 1 - w[n]
     float2 tw2[kM / 2 + 8];     // exp(-2 pi i k / 2048), k = 0..512
-    float2 binw[kBinStride * 32];   // per bin: weights for band binband[f] and binband[f]+1; the SIGN BIT of .y says
-                                    // "the band index steps up at this bin" (weights are >= 0); zero padded
-    unsigned char gather[(kMel + 1) * kMaxTerms];   // per band: the partial-sum slots to add, in lane order
-    unsigned char count[kMel + 1 + 7];              // number of partial sums of each band
-    unsigned char lanebase[32];                     // first slot of each lane (its bands take consecutive slots)
+    float2 coef[kMel * kMaxTerms];          // per band: (A, B) of each partial sum: band += A * S0 + B * S1
+    unsigned long long lanemask[32];        // bit i: the band-edge segment steps up at the lane's i-th bin
+    unsigned char gslot[kMel * kMaxTerms];  // per band: the partial-sum slot of each term (padding: slot 0, A = B = 0)
+    unsigned char lanebase[32];             // first slot of each lane (its segments take consecutive slots)
+    int terms_round1, terms_round2;         // loop trip counts of the two closing rounds
+    int pad_[2];
 };
 static_assert(sizeof(LogmelTables) % 16 == 0, "tables are copied as uint4");
 
 constexpr int kBufBytes = 32 * 33 * 8;                 // per-warp exchange buffer (8448 B)
-constexpr int kPartBytes = kMaxSlots * 4;              // per-warp mel partial sums
+constexpr int kExchBytes = 512 * 8;                    // untangle exchange: Z[512..1023]; P starts behind it
+constexpr int kPartBytes = kMaxSlots * 8;              // per-warp mel partial sums (S0, S1)
 constexpr int kSmemBytes = sizeof(LogmelTables) + kWarps * (kBufBytes + kPartBytes);
+static_assert(kExchBytes + kBinStride * 32 * 4 <= kBufBytes, "P (33 x 32 floats) must fit behind the exchange half");
 
 // ------------------------------------------------------------------------------ device: FFT-32
 // complex add / subtract as ONE packed fp32x2 instruction each (sm_100 add.f32x2 / fma.f32x2): the (re, im)
@@ -135,8 +142,8 @@ logmel_kernel(const float* __restrict__ pcm, float* __restrict__ out, int n_ch, 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float2* buf = reinterpret_cast<float2*>(smem + sizeof(LogmelTables) + warp * kBufBytes);
-    float* part = reinterpret_cast<float*>(smem + sizeof(LogmelTables) + kWarps * kBufBytes + warp * kPartBytes);
-    float* P = reinterpret_cast<float*>(buf);
+    float2* part = reinterpret_cast<float2*>(smem + sizeof(LogmelTables) + kWarps * kBufBytes + warp * kPartBytes);
+    float* P = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(buf) + kExchBytes);   // power spectrum, 33 x 32
 
     for (long q = (long)blockIdx.x * kWarps + warp; q < total_frames; q += (long)gridDim.x * kWarps) {
         const int frame = (int)(q % n_frames);
@@ -171,12 +178,13 @@ logmel_kernel(const float* __restrict__ pcm, float* __restrict__ out, int n_ch, 
             __syncwarp();
         }
         {
+            // periodic Hann: w[n + 1024] = 1 - w[n], so v[j + 16] (sample n + 1024) takes x - x * w[n]
             const float2* w2 = reinterpret_cast<const float2*>(tab.win);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 16; ++j) {
                 const float2 w = w2[lane + 32 * j];
-                v[j].x *= w.x;
-                v[j].y *= w.y;
+                v[j] = __fmul2_rn(v[j], w);
+                v[j + 16] = __ffma2_rn(make_float2(-v[j + 16].x, -v[j + 16].y), w, v[j + 16]);
             }
         }
 
@@ -193,75 +201,94 @@ logmel_kernel(const float* __restrict__ pcm, float* __restrict__ out, int n_ch, 
         for (int t = 0; t < 32; ++t) v[t] = buf[t * 33 + lane];
         __syncwarp();
 
-        // ---- stage 2: DFT over t; lane a now owns Z[a + 32 b]
+        // ---- stage 2: DFT over t; lane a now owns Z[a + 32 b] (register v[i] holds b = bitrev5(i)).
+        //      Bins k and 1024-k are untangled together by the lane that owns the one with b < 16; its partner
+        //      (lane (32 - a) % 32, b' >= 16) passes the other half through shared memory: ex[k - 512] = Z[k].
         fft32(v);
+        float2* ex = buf;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) buf[lane + 32 * bitrev5(i)] = v[i];
+        for (int i = 1; i < 32; i += 2) ex[lane + 32 * (bitrev5(i) - 16)] = v[i];
         __syncwarp();
 
-        // ---- real-FFT untangle + power spectrum; bins k and 1024-k are produced together
+        // ---- real-FFT untangle + power spectrum
         {
-            float2 zk[16], zp[16];
 #pragma unroll
             for (int m = 0; m < 16; ++m) {
                 const int k = lane + 32 * m;
-                zk[m] = buf[k];
-                zp[m] = buf[(kM - k) & (kM - 1)];
-            }
-            const float2 zmid = buf[kM / 2];
-            __syncwarp();
-#pragma unroll
-            for (int m = 0; m < 16; ++m) {
-                const int k = lane + 32 * m;
+                const float2 zk = v[bitrev5(m)];
+                float2 zp = ex[(m == 0 && lane == 0) ? 0 : 512 - k];
+                if (m == 0 && lane == 0) zp = zk;                                // k = 0 pairs with itself
                 const float2 w = tab.tw2[k];                                     // (cos, -sin)
-                const float2 e = __ffma2_rn(zp[m], make_float2(1.0f, -1.0f), zk[m]);   // 2E = (zk.x+zp.x, zk.y-zp.y)
-                const float2 o = make_float2(zk[m].y + zp[m].y, zp[m].x - zk[m].x);   // 2O
+                const float2 e = __ffma2_rn(zp, make_float2(1.0f, -1.0f), zk);   // 2E = (zk.x+zp.x, zk.y-zp.y)
+                const float2 o = make_float2(zk.y + zp.y, zp.x - zk.x);          // 2O
                 const float2 t = cmul(o, w);                                     // 2 W^k O
                 const float2 xa = cadd(e, t), xb2 = csub(e, t);
                 P[k] = 0.25f * fmaf(xa.x, xa.x, xa.y * xa.y);
                 P[kM - k] = 0.25f * fmaf(xb2.x, xb2.x, xb2.y * xb2.y);
             }
-            if (lane == 0) P[kM / 2] = fmaf(zmid.x, zmid.x, zmid.y * zmid.y);
+            const float2 zmid = ex[0];                                           // Z[512]
+            P[lane == 0 ? kM / 2 : kM + lane] = lane == 0 ? fmaf(zmid.x, zmid.x, zmid.y * zmid.y) : 0.0f;
         }
         __syncwarp();
 
-        // ---- mel projection: each lane walks 33 consecutive bins with two running sums (band cur, cur+1); when
-        //      the band index steps up (static flag stored in the weight's sign bit) the finished sum goes to the
-        //      lane's next slot.  No data-dependent loop, fully unrolled, deterministic summation order.
+        // ---- mel projection, part 1: each lane walks 33 consecutive bins.  Between two band edges every
+        //      triangular weight is linear in the bin index, so the lane only keeps S0 = sum P and S1 = sum i*P of
+        //      the current edge-to-edge segment; when the segment steps up (static per-lane bit mask) the pair goes
+        //      to the lane's next slot.  No weight loads, no data-dependent control flow, fixed summation order.
         {
-            const int f0 = lane * kBinStride;
-            int k = tab.lanebase[lane];
-            float a0 = 0.0f, a1 = 0.0f;
+            const float* Pl = P + lane * kBinStride;
+            const unsigned long long msk = tab.lanemask[lane];
+            const unsigned mlo = (unsigned)msk, mhi = (unsigned)(msk >> 32);
+            unsigned slot = (unsigned)__cvta_generic_to_shared(part + tab.lanebase[lane]);
+            float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
             for (int i = 0; i < kBinStride; ++i) {
-                const int f = f0 + i;
-                const float2 w = tab.binw[f];
-                const float p = f < kBins ? P[f] : 0.0f;
-                if (i > 0 && (__float_as_uint(w.y) >> 31)) {
-                    part[k++] = a0;
-                    a0 = a1;
-                    a1 = 0.0f;
+                const float p = Pl[i];
+                if (i > 0) {
+                    // one predicate per bin; store / advance / reset are predicated, nothing branches
+                    asm volatile(
+                        "{\n\t.reg .pred q;\n\t"
+                        "setp.ne.u32 q, %3, 0;\n\t"
+                        "@q st.shared.v2.f32 [%0], {%1, %2};\n\t"
+                        "@q add.u32 %0, %0, 8;\n\t"
+                        "@q mov.f32 %1, 0f00000000;\n\t"
+                        "@q mov.f32 %2, 0f00000000;\n\t}"
+                        : "+r"(slot), "+f"(s0), "+f"(s1)
+                        : "r"((i < 32 ? mlo : mhi) & (1u << (i & 31)))
+                        : "memory");
                 }
-                a0 = fmaf(w.x, p, a0);
-                a1 = fmaf(fabsf(w.y), p, a1);
+                s0 += p;
+                s1 = fmaf((float)i, p, s1);
             }
-            part[k] = a0;
-            part[k + 1] = a1;
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(slot), "f"(s0), "f"(s1) : "memory");
         }
         __syncwarp();
+        // ---- part 2: close the bands.  band = sum over its partial sums of A * S0 + B * S1 (<= 8 terms at 44.1 kHz)
         {
             const long clip = cc / n_ch;
             const int ch = (int)(cc % n_ch);
             float* o = out + ((clip * n_frames + frame) * n_ch + ch) * kMel;
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int b = lane + 32 * r;
-                if (b < kMel) {
-                    const int n = tab.count[b];
-                    float acc = 0.0f;
-                    for (int i = 0; i < n; ++i) acc += part[tab.gather[b * kMaxTerms + i]];
-                    o[b] = logf(acc);
+            {
+                const int b = kMel - kBandsRound1 + lane;
+                float acc = 0.0f;
+                for (int i = 0; i < tab.terms_round1; ++i) {
+                    const float2 c = tab.coef[b * kMaxTerms + i];
+                    const float2 sv = part[tab.gslot[b * kMaxTerms + i]];
+                    acc = fmaf(c.x, sv.x, acc);
+                    acc = fmaf(c.y, sv.y, acc);
                 }
+                o[b] = logf(acc);
+            }
+            if (lane < kMel - kBandsRound1) {
+                const int b = lane;
+                float acc = 0.0f;
+                for (int i = 0; i < tab.terms_round2; ++i) {
+                    const float2 c = tab.coef[b * kMaxTerms + i];
+                    const float2 sv = part[tab.gslot[b * kMaxTerms + i]];
+                    acc = fmaf(c.x, sv.x, acc);
+                    acc = fmaf(c.y, sv.y, acc);
+                }
+                o[b] = logf(acc);
             }
         }
         __syncwarp();
@@ -280,13 +307,19 @@ double mel_to_hz(double m) {
     return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m;
 }
 
-// librosa.filters.mel(sr, n_fft=2048, n_mels=40): Slaney scale, slaney norm, float32 [40][1025]
-void build_mel(int sr, std::vector<float>& fb) {
-    fb.assign((size_t)kMel * kBins, 0.0f);
-    std::vector<double> mel_f(kMel + 2), fftf(kBins);
+// band-edge frequencies mel_f[0 .. kMel+1] of librosa.filters.mel (Slaney scale, fmin 0, fmax sr/2)
+void mel_edges(int sr, std::vector<double>& mel_f) {
+    mel_f.resize(kMel + 2);
     const double lo = hz_to_mel(0.0), hi = hz_to_mel(sr / 2.0);
     const double step = (hi - lo) / (kMel + 1);
     for (int i = 0; i < kMel + 2; ++i) mel_f[i] = mel_to_hz(i == kMel + 1 ? hi : lo + step * i);
+}
+
+// librosa.filters.mel(sr, n_fft=2048, n_mels=40): Slaney scale, slaney norm, float32 [40][1025]
+void build_mel(int sr, std::vector<float>& fb) {
+    fb.assign((size_t)kMel * kBins, 0.0f);
+    std::vector<double> mel_f, fftf(kBins);
+    mel_edges(sr, mel_f);
     const double val = 1.0 / (kNfft * (1.0 / sr));
     for (int k = 0; k < kBins; ++k) fftf[k] = k * val;
     for (int i = 0; i < kMel; ++i) {
@@ -309,52 +342,73 @@ int build_tables(int sr, LogmelTables& t) {
             const double ang = -two_pi * (double)(l * a) / kM;
             t.tw1[a * 32 + l] = make_float2((float)std::cos(ang), (float)std::sin(ang));
         }
-    for (int n = 0; n < kNfft; ++n) t.win[n] = (float)(0.5 - 0.5 * std::cos(two_pi * n / kNfft));
+    for (int n = 0; n < kNfft / 2; ++n) t.win[n] = (float)(0.5 - 0.5 * std::cos(two_pi * n / kNfft));
     for (int k = 0; k <= kM / 2; ++k) {
         const double ang = -two_pi * (double)k / kNfft;
         t.tw2[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
     }
-    std::vector<float> fb;
-    build_mel(sr, fb);
-    int prev = 0;
-    unsigned char band[kBinStride * 32];
+    // Mel projection tables.  Segment j = [mel_f[j], mel_f[j+1]) holds the bins whose weight into band j rises
+    // linearly, enorm_j (f - mel_f[j]) / D_j, and whose weight into band j-1 falls linearly,
+    // enorm_{j-1} (mel_f[j+1] - f) / D_j  (the two branches of librosa's min(lower, upper) ramp).
+    std::vector<double> mel_f;
+    mel_edges(sr, mel_f);
+    const double df = (double)sr / kNfft;
+    int seg[kBinStride * 32];
     for (int f = 0; f < kBinStride * 32; ++f) {
-        if (f >= kBins) { band[f] = (unsigned char)prev; t.binw[f] = make_float2(0.0f, 0.0f); continue; }
-        int first = -1, last = -1;
-        for (int b = 0; b < kMel; ++b)
-            if (fb[(size_t)b * kBins + f] != 0.0f) {
-                if (first < 0) first = b;
-                last = b;
-            }
-        if (first < 0) first = last = prev;
-        if (last > first + 1 || first < prev || first > prev + 1)
-            return fail(SEDB200_ESHAPE, "mel filterbank for sr=%d: bin %d does not fit the 2-bands-per-bin walk", sr, f);
-        band[f] = (unsigned char)first;
-        float w1 = first + 1 < kMel ? fb[(size_t)(first + 1) * kBins + f] : 0.0f;
-        if (first > prev) w1 = -w1;                       // sign bit = "band index steps up here" (-0.0f works too)
-        if (first > prev && w1 == 0.0f) w1 = -0.0f;
-        t.binw[f] = make_float2(fb[(size_t)first * kBins + f], w1);
-        prev = first;
+        const double fr = std::min(f, kBins - 1) * df;
+        int j = 0;
+        while (j < kMel && fr >= mel_f[j + 1]) ++j;
+        seg[f] = j;                                        // 0 .. kMel
     }
-    // slots: lane l covers bands [band[f0], band[f_last] + 1], one slot each, consecutive
-    int bmin[32], bmax[32], slots = 0;
+    int slots = 0;
+    int slot_lane[kMaxSlots], slot_seg[kMaxSlots];
     for (int l = 0; l < 32; ++l) {
-        const int f0 = l * kBinStride, f1 = std::min(f0 + kBinStride, kBins);
+        const int f0 = l * kBinStride;
         if (f0 >= kBins) return fail(SEDB200_ESHAPE, "bin walk layout broken");
-        bmin[l] = band[f0];
-        bmax[l] = band[f1 - 1] + 1;
         t.lanebase[l] = (unsigned char)slots;
-        slots += bmax[l] - bmin[l] + 1;
-    }
-    if (slots > kMaxSlots || slots > 255) return fail(SEDB200_ESHAPE, "mel partial-sum slots %d too many", slots);
-    for (int b = 0; b <= kMel; ++b) {
-        int n = 0;
-        for (int l = 0; l < 32; ++l)
-            if (b >= bmin[l] && b <= bmax[l]) {
-                if (n >= kMaxTerms) return fail(SEDB200_ESHAPE, "mel band %d has more than %d partial sums", b, kMaxTerms);
-                t.gather[b * kMaxTerms + n++] = (unsigned char)(t.lanebase[l] + b - bmin[l]);
+        unsigned long long m = 0;
+        for (int i = 0; i < kBinStride; ++i) {
+            if (i > 0 && seg[f0 + i] != seg[f0 + i - 1]) {
+                if (seg[f0 + i] != seg[f0 + i - 1] + 1)
+                    return fail(SEDB200_ESHAPE, "mel filterbank for sr=%d: a band edge segment holds no bin", sr);
+                m |= 1ull << i;
             }
-        t.count[b] = (unsigned char)n;
+            if (i == 0 || (m >> i) & 1) {
+                if (slots >= kMaxSlots) return fail(SEDB200_ESHAPE, "mel partial-sum slots exceed %d", kMaxSlots);
+                slot_lane[slots] = l;
+                slot_seg[slots] = seg[f0 + i];
+                ++slots;
+            }
+        }
+        t.lanemask[l] = m;
+    }
+    int n_terms[kMel] = {0};
+    auto add_term = [&](int band, int slot, double A, double B) -> int {
+        if (n_terms[band] >= kMaxTerms)
+            return fail(SEDB200_ESHAPE, "mel band %d has more than %d partial sums", band, kMaxTerms);
+        t.gslot[band * kMaxTerms + n_terms[band]] = (unsigned char)slot;
+        t.coef[band * kMaxTerms + n_terms[band]] = make_float2((float)A, (float)B);
+        ++n_terms[band];
+        return SEDB200_OK;
+    };
+    for (int s = 0; s < slots; ++s) {
+        const int j = slot_seg[s];
+        const double f0 = slot_lane[s] * kBinStride * df, D = mel_f[j + 1] - mel_f[j];
+        if (j <= kMel - 1) {                               // rising edge of band j
+            const double en = 2.0 / (mel_f[j + 2] - mel_f[j]);
+            int rc = add_term(j, s, en * (f0 - mel_f[j]) / D, en * df / D);
+            if (rc) return rc;
+        }
+        if (j >= 1) {                                      // falling edge of band j - 1
+            const double en = 2.0 / (mel_f[j + 1] - mel_f[j - 1]);
+            int rc = add_term(j - 1, s, en * (mel_f[j + 1] - f0) / D, -en * df / D);
+            if (rc) return rc;
+        }
+    }
+    t.terms_round1 = t.terms_round2 = 0;
+    for (int b = 0; b < kMel; ++b) {
+        int& r = b >= kMel - kBandsRound1 ? t.terms_round1 : t.terms_round2;
+        r = std::max(r, n_terms[b]);
     }
     return SEDB200_OK;
 }
