@@ -69,12 +69,14 @@ static_assert(kExchBytes + kBinStride * 32 * 4 <= kBufBytes, "P (33 x 32 floats)
 // pair of a float2 is exactly the register pair the packed pipe wants
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a); }
+// Complex products as TWO packed instructions: d * (c, c), then (swapped, sign-flipped d) * (s, s) added on top --
+// the swap / negate of the halves is an operand modifier of the packed pipe (F32x2.LO_HI.NP in SASS), not a MOV.
 // (a + ib)(c - is)
 __device__ __forceinline__ float2 cmul_conjtw(float2 d, float c, float s) {
-    return make_float2(fmaf(d.y, s, d.x * c), fmaf(-d.x, s, d.y * c));
+    return __ffma2_rn(make_float2(d.y, -d.x), make_float2(s, s), __fmul2_rn(d, make_float2(c, c)));
 }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-    return make_float2(fmaf(-a.y, b.y, a.x * b.x), fmaf(a.x, b.y, a.y * b.x));
+    return __ffma2_rn(make_float2(-a.y, a.x), make_float2(b.y, b.y), __fmul2_rn(a, make_float2(b.x, b.x)));
 }
 
 // d * W_32^m, W_32 = exp(-2 pi i / 32), m a compile-time constant after unrolling.
@@ -89,8 +91,9 @@ __device__ __forceinline__ float2 mul_w32(float2 d, int m) {
                              0.70710678118654752f, 0.55557023301960218f, 0.38268343236508978f, 0.19509032201612825f};
     if (m == 0) return d;
     if (m == 8) return make_float2(d.y, -d.x);
-    if (m == 4) return make_float2((d.x + d.y) * 0.70710678118654752f, (d.y - d.x) * 0.70710678118654752f);
-    if (m == 12) return make_float2((d.y - d.x) * 0.70710678118654752f, -(d.x + d.y) * 0.70710678118654752f);
+    constexpr float h = 0.70710678118654752f;
+    if (m == 4) return __fmul2_rn(__fadd2_rn(d, make_float2(d.y, -d.x)), make_float2(h, h));
+    if (m == 12) return __fmul2_rn(__fadd2_rn(make_float2(-d.x, -d.y), make_float2(d.y, -d.x)), make_float2(h, h));
     return cmul_conjtw(d, C[m], S[m]);
 }
 
@@ -145,9 +148,18 @@ logmel_kernel(const float* __restrict__ pcm, float* __restrict__ out, int n_ch, 
     float2* part = reinterpret_cast<float2*>(smem + sizeof(LogmelTables) + kWarps * kBufBytes + warp * kPartBytes);
     float* P = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(buf) + kExchBytes);   // power spectrum, 33 x 32
 
-    for (long q = (long)blockIdx.x * kWarps + warp; q < total_frames; q += (long)gridDim.x * kWarps) {
-        const int frame = (int)(q % n_frames);
-        const long cc = q / n_frames;                      // clip * n_ch + ch
+    // (clip*n_ch + ch, frame) of this warp's first frame, then advanced by the grid stride without any division
+    const long q0 = (long)blockIdx.x * kWarps + warp;
+    const long stride = (long)gridDim.x * kWarps;
+    long cc = q0 / n_frames;                               // clip * n_ch + ch
+    int frame = (int)(q0 - cc * n_frames);
+    const long stride_cc = stride / n_frames;
+    const int stride_fr = (int)(stride - stride_cc * n_frames);
+    for (long q = q0; q < total_frames; q += stride, cc += stride_cc, frame += stride_fr) {
+        if (frame >= n_frames) {
+            frame -= n_frames;
+            ++cc;
+        }
         const float* __restrict__ xb = pcm + cc * S;
         const long start = (long)(frame - 1) * kHop;       // first sample of the frame (may be < 0)
 
@@ -223,11 +235,11 @@ logmel_kernel(const float* __restrict__ pcm, float* __restrict__ out, int n_ch, 
                 const float2 o = make_float2(zk.y + zp.y, zp.x - zk.x);          // 2O
                 const float2 t = cmul(o, w);                                     // 2 W^k O
                 const float2 xa = cadd(e, t), xb2 = csub(e, t);
-                P[k] = 0.25f * fmaf(xa.x, xa.x, xa.y * xa.y);
-                P[kM - k] = 0.25f * fmaf(xb2.x, xb2.x, xb2.y * xb2.y);
+                P[k] = fmaf(xa.x, xa.x, xa.y * xa.y);                           // 4 |X[k]|^2: the 1/4 lives in the
+                P[kM - k] = fmaf(xb2.x, xb2.x, xb2.y * xb2.y);                  // mel coefficients
             }
             const float2 zmid = ex[0];                                           // Z[512]
-            P[lane == 0 ? kM / 2 : kM + lane] = lane == 0 ? fmaf(zmid.x, zmid.x, zmid.y * zmid.y) : 0.0f;
+            P[lane == 0 ? kM / 2 : kM + lane] = lane == 0 ? 4.0f * fmaf(zmid.x, zmid.x, zmid.y * zmid.y) : 0.0f;
         }
         __syncwarp();
 
@@ -265,9 +277,9 @@ logmel_kernel(const float* __restrict__ pcm, float* __restrict__ out, int n_ch, 
         __syncwarp();
         // ---- part 2: close the bands.  band = sum over its partial sums of A * S0 + B * S1 (<= 8 terms at 44.1 kHz)
         {
-            const long clip = cc / n_ch;
-            const int ch = (int)(cc % n_ch);
-            float* o = out + ((clip * n_frames + frame) * n_ch + ch) * kMel;
+            const unsigned clip = (unsigned)cc / (unsigned)n_ch;       // cc < 2^31 (checked by the launcher)
+            const int ch = (int)((unsigned)cc - clip * (unsigned)n_ch);
+            float* o = out + (((long)clip * n_frames + frame) * n_ch + ch) * kMel;
             {
                 const int b = kMel - kBandsRound1 + lane;
                 float acc = 0.0f;
@@ -387,7 +399,7 @@ int build_tables(int sr, LogmelTables& t) {
         if (n_terms[band] >= kMaxTerms)
             return fail(SEDB200_ESHAPE, "mel band %d has more than %d partial sums", band, kMaxTerms);
         t.gslot[band * kMaxTerms + n_terms[band]] = (unsigned char)slot;
-        t.coef[band * kMaxTerms + n_terms[band]] = make_float2((float)A, (float)B);
+        t.coef[band * kMaxTerms + n_terms[band]] = make_float2((float)(0.25 * A), (float)(0.25 * B));   // P holds 4|X|^2
         ++n_terms[band];
         return SEDB200_OK;
     };
@@ -466,6 +478,7 @@ int sedb200_logmel_f32(const float* pcm_dev, int n_clips, int n_ch, long n_sampl
     if (rc) return rc;
     const long nfr = sedb200_logmel_frames(n_samples);
     SED_REQUIRE(nfr < (1L << 31), SEDB200_ESHAPE, "logmel: %ld frames per clip", nfr);
+    SED_REQUIRE((long)n_clips * n_ch < (1L << 31), SEDB200_ESHAPE, "logmel: %ld channel-clips", (long)n_clips * n_ch);
     const long total = (long)n_clips * n_ch * nfr;
     const long want = (total + kWarps - 1) / kWarps;
     const int grid = (int)std::min<long>(want, sm_count());
