@@ -202,11 +202,18 @@ logmel_kernel(const float* __restrict__ pcm, float* __restrict__ out, int n_ch, 
 
         // ---- stage 1: DFT over j, twiddle, transpose through shared memory
         fft32(v);
+        {
+            // twiddles W_1024^(lane*a): every fourth one comes from the table, the three after it by multiplying with
+            // W_1024^lane (two packed instructions instead of a shared-memory load -- this kernel is bound by the
+            // shared-memory pipe, not by issue)
+            const float2 w1 = tab.tw1[32 + lane];
+            float2 tw = w1;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const int a = bitrev5(i);
-            const float2 t = (a == 0) ? v[i] : cmul(v[i], tab.tw1[a * 32 + lane]);
-            buf[lane * 33 + a] = t;
+            for (int a = 0; a < 32; ++a) {
+                const int i = bitrev5(a);
+                if (a > 1) tw = (a % 4 == 0) ? tab.tw1[a * 32 + lane] : cmul(tw, w1);
+                buf[lane * 33 + a] = (a == 0) ? v[i] : cmul(v[i], tw);
+            }
         }
         __syncwarp();
 #pragma unroll
@@ -224,16 +231,19 @@ logmel_kernel(const float* __restrict__ pcm, float* __restrict__ out, int n_ch, 
 
         // ---- real-FFT untangle + power spectrum
         {
+            constexpr float kC64[16] = {1.0f, 0.99518472667219693f, 0.98078528040323043f, 0.95694033573220882f, 0.92387953251128674f, 0.88192126434835505f, 0.83146961230254524f, 0.77301045336273699f, 0.70710678118654757f, 0.63439328416364549f, 0.55557023301960229f, 0.47139673682599781f, 0.38268343236508984f, 0.29028467725446233f, 0.19509032201612833f, 0.09801714032956077f};
+            constexpr float kS64[16] = {0.0f, 0.098017140329560604f, 0.19509032201612825f, 0.29028467725446233f, 0.38268343236508978f, 0.47139673682599764f, 0.55557023301960218f, 0.63439328416364549f, 0.70710678118654746f, 0.77301045336273699f, 0.83146961230254524f, 0.88192126434835494f, 0.92387953251128674f, 0.95694033573220894f, 0.98078528040323043f, 0.99518472667219682f};
+            const float2 wl = tab.tw2[lane];                                     // W_2048^lane = (cos, -sin)
 #pragma unroll
             for (int m = 0; m < 16; ++m) {
                 const int k = lane + 32 * m;
                 const float2 zk = v[bitrev5(m)];
                 float2 zp = ex[(m == 0 && lane == 0) ? 0 : 512 - k];
                 if (m == 0 && lane == 0) zp = zk;                                // k = 0 pairs with itself
-                const float2 w = tab.tw2[k];                                     // (cos, -sin)
                 const float2 e = __ffma2_rn(zp, make_float2(1.0f, -1.0f), zk);   // 2E = (zk.x+zp.x, zk.y-zp.y)
                 const float2 o = make_float2(zk.y + zp.y, zp.x - zk.x);          // 2O
-                const float2 t = cmul(o, w);                                     // 2 W^k O
+                // W_2048^k = W_2048^lane * W_64^m: per-lane factor from the table, per-m factor an immediate
+                const float2 t = cmul(m == 0 ? o : cmul_conjtw(o, kC64[m], kS64[m]), wl);   // 2 W^k O
                 const float2 xa = cadd(e, t), xb2 = csub(e, t);
                 P[k] = fmaf(xa.x, xa.x, xa.y * xa.y);                           // 4 |X[k]|^2: the 1/4 lives in the
                 P[kM - k] = fmaf(xb2.x, xb2.x, xb2.y * xb2.y);                  // mel coefficients
