@@ -184,6 +184,33 @@ int sedb200_clip_adam(float* params_dev, const float* grads_dev, float* exp_avg_
                       long step /* 1-based */, float max_norm, float grad_prescale, float* gnorm_dev,
                       void* scratch_dev, size_t scratch_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Data-parallel exchange step as ONE kernel over NVLink peer memory (single node, one process per GPU):
+ * sum all-reduce of the flat gradient buffers of all ranks + global-norm clip + Adam, replacing
+ * `dist.all_reduce(grads)` followed by sedb200_clip_adam (train_lightning.py:50, crnn_lightning.py:195-197).
+ *
+ * Each rank allocates one exchange region (sedb200_p2p_region_alloc: cudaMalloc + CUDA IPC handle -- the one place
+ * the library allocates, because IPC needs a whole cudaMalloc allocation), sends the 64-byte handle to its peers
+ * (any transport: torch.distributed.all_gather_object) and maps theirs (sedb200_p2p_region_open).  Region layout:
+ * flag row + status word in the first 1024 B, then two gradient buffers selected by `seq & 1`; a rank's backward
+ * pass for exchange number `seq` must write its gradients at region + sedb200_p2p_grad_offset_bytes(n, seq & 1).
+ * `seq` starts at 1 and increases by exactly 1 per call on every rank; `step` is Adam's bias-correction step.
+ * reduced_dev [n] receives the summed gradients; results are bit-identical on all ranks (fixed rank order).
+ * sedb200_p2p_status reads back the region's status word: non-zero = a peer did not publish within ~2 s. */
+size_t sedb200_p2p_region_bytes(long n);
+long   sedb200_p2p_grad_offset_bytes(long n, int parity);
+int    sedb200_p2p_region_alloc(size_t bytes, void** region_dev, unsigned char* ipc_handle /* [64] */);
+int    sedb200_p2p_region_open(const unsigned char* ipc_handle /* [64] */, void** region_dev);
+int    sedb200_p2p_region_close(void* region_dev);
+int    sedb200_p2p_region_free(void* region_dev);
+int    sedb200_p2p_status(const void* region_dev, unsigned int* status_host);
+size_t sedb200_p2p_scratch_bytes(void);
+int    sedb200_p2p_allreduce_clip_adam(void* const* regions_host /* [world], rank order */, int world, int rank, long n,
+                                       long seq, long step, float* params_dev, float* exp_avg_dev,
+                                       float* exp_avg_sq_dev, float* reduced_dev, float lr, float beta1, float beta2,
+                                       float eps, float weight_decay, float max_norm, float grad_prescale,
+                                       float* gnorm_dev, void* scratch_dev, size_t scratch_bytes, void* stream);
+
 /* sigmoid -> strict > 0.5 -> integer counts behind metrics.py:20-68 (crnn_lightning.py:112-126).
  * probs/targets: float32 [n_rows][n_cls] (the [N,T,C] arrays flattened by utils.reshape_3Dto2D).
  * counts_dev: 12 uint64 = {TP,Nsys,Nref,S,D,I} framewise, then the same six after block-max with

@@ -23,7 +23,7 @@ LOSS_KINDS = {"bce": 0, "focal": 1}
 class CRNNEngine:
     def __init__(self, cfg: CRNNConfig, device="cuda", *, loss="focal", alpha=0.25, gamma=2.0,
                  lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, clip=1.0, seed=0,
-                 process_group=None):
+                 process_group=None, grad_exchange: str = "nccl"):
         self.cfg = cfg
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -56,6 +56,14 @@ class CRNNEngine:
         self._ws_batch = 0
         self._bufs = {}
         self._last_seed = self.seed
+        # "nccl": dist.all_reduce + clip_adam kernels;  "p2p": one fused kernel over NVLink peer memory
+        if grad_exchange not in ("nccl", "p2p"):
+            raise ValueError("grad_exchange must be 'nccl' or 'p2p'")
+        self.xch = None
+        if grad_exchange == "p2p":
+            from . import parallel
+            self.xch = parallel.P2PGradExchange(n, self.device, process_group)
+            self.grads = self.xch.next_grad_buffer()
 
     # ------------------------------------------------------------------ parameters
     def views(self, flat: torch.Tensor | None = None) -> dict[str, torch.Tensor]:
@@ -202,6 +210,14 @@ class CRNNEngine:
         (views of engine-owned buffers, valid until the next call)."""
         logits = self.forward(x, training=True)
         loss, probs, dlog = self.loss_and_grad(logits, y)
+        if self.xch is not None:
+            self.grads = self.xch.next_grad_buffer()                  # this step's half of the exchange region
+            self.backward(x, dlog)
+            self.step_count += 1
+            self.grads = self.xch.allreduce_clip_adam(
+                self.params, self.exp_avg, self.exp_avg_sq, step=self.step_count, lr=self.lr, betas=self.betas,
+                eps=self.eps, weight_decay=self.weight_decay, clip=self.clip, gnorm_out=self._scalars[1:])
+            return loss, probs
         self.backward(x, dlog)
         from . import parallel
         scale = parallel.allreduce_sum_(self.grads, self.pg)         # sum; 1/world folded into clip_adam

@@ -58,6 +58,95 @@ def broadcast_(flat: torch.Tensor, src: int = 0, group=None) -> None:
         dist.broadcast(flat, src=src, group=group)
 
 
+class _RawCudaArray:
+    """`__cuda_array_interface__` view of library-owned device memory, so torch can wrap it without a copy."""
+
+    def __init__(self, ptr: int, n_floats: int):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class P2PGradExchange:
+    """The data-parallel exchange step over NVLink peer memory (single node): every rank's backward pass writes
+    its flat gradients into a CUDA-IPC-shared region; ONE kernel (`sedb200_p2p_allreduce_clip_adam`) then sums the
+    buffers of all ranks with peer loads, clips and applies Adam -- no NCCL call on the data path, sums bit-identical
+    on every rank.  `torch.distributed` is used once, at construction, to swap the 64-byte IPC handles."""
+
+    def __init__(self, n_floats: int, device, group=None):
+        import ctypes as C
+        from . import _lib
+        self.L, self.C = _lib.lib(), C
+        self.check = _lib.check
+        self.device = torch.device(device)
+        self.rank, self.world = world_info(group)
+        self.n = int(n_floats)
+        if self.n % 4:
+            raise ValueError("flat parameter count must be a multiple of 4 floats")
+        if self.world > 16:
+            raise ValueError("P2PGradExchange supports up to 16 ranks on one node")
+        nbytes = int(self.L.sedb200_p2p_region_bytes(self.n))
+        with torch.cuda.device(self.device):
+            ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+            self.check(self.L.sedb200_p2p_region_alloc(nbytes, C.byref(ptr), handle))
+            self.own = ptr.value
+            handles = [bytes(handle)]
+            if self.world > 1:
+                gathered = [None] * self.world
+                dist.all_gather_object(gathered, (bytes(handle), torch.cuda.current_device()), group=group)
+                handles = [g[0] for g in gathered]
+            self.regions = []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self.regions.append(self.own)
+                    continue
+                q = C.c_void_p()
+                self.check(self.L.sedb200_p2p_region_open((C.c_ubyte * 64).from_buffer_copy(h), C.byref(q)))
+                self.regions.append(q.value)
+            torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=group)                  # every region is zeroed and mapped before the first flag
+        self.table = (C.c_void_p * self.world)(*self.regions)
+        self.grad_bufs = [
+            torch.as_tensor(_RawCudaArray(self.own + int(self.L.sedb200_p2p_grad_offset_bytes(self.n, par)), self.n),
+                            device=self.device) for par in (0, 1)]
+        self.reduced = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+        self.scratch = torch.zeros(int(self.L.sedb200_p2p_scratch_bytes()) // 4, dtype=torch.float32,
+                                   device=self.device)
+        self.seq = 0
+
+    def next_grad_buffer(self) -> torch.Tensor:
+        """The buffer the NEXT exchange will read on every rank: backward must write its gradients here."""
+        return self.grad_bufs[(self.seq + 1) & 1]
+
+    def allreduce_clip_adam(self, params, exp_avg, exp_avg_sq, *, step, lr, betas, eps, weight_decay, clip, gnorm_out):
+        self.seq += 1
+        with torch.cuda.device(self.device):
+            self.check(self.L.sedb200_p2p_allreduce_clip_adam(
+                self.table, self.world, self.rank, self.n, self.seq, int(step), params.data_ptr(), exp_avg.data_ptr(),
+                exp_avg_sq.data_ptr(), self.reduced.data_ptr(), float(lr), float(betas[0]), float(betas[1]),
+                float(eps), float(weight_decay), float(clip), 1.0 / self.world, gnorm_out.data_ptr(),
+                self.scratch.data_ptr(), self.scratch.numel() * 4, torch.cuda.current_stream().cuda_stream))
+        return self.reduced
+
+    def status(self) -> int:
+        """0 = healthy; non-zero = some peer failed to publish its gradients within the kernel's spin bound."""
+        v = self.C.c_uint(0)
+        with torch.cuda.device(self.device):
+            self.check(self.L.sedb200_p2p_status(self.own, self.C.byref(v)))
+        return int(v.value)
+
+    def close(self) -> None:
+        if getattr(self, "own", None) is None:
+            return
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            for r, q in enumerate(self.regions):
+                if r != self.rank:
+                    self.L.sedb200_p2p_region_close(q)
+            self.grad_bufs = []
+            self.L.sedb200_p2p_region_free(self.own)
+        self.own = None
+
+
 class DevicePrefetcher:
     """Iterate over (x, y) HOST batches (pinned, as the reference's DataLoader(pin_memory=True) yields them,
     decorte_datamodule.py:130-137) and hand out DEVICE batches, copying batch i+1 on a side stream while batch i

@@ -1,0 +1,58 @@
+"""Fused peer-memory all-reduce + clip + Adam kernel (sedb200_p2p_allreduce_clip_adam).
+
+Single GPU (world = 1: the exchange region is local, same kernel, same flag protocol) against the plain
+sedb200_clip_adam path; the two-rank NVLink run lives in tools/mgpu_check.py (needs `gpurun --gpus 2`)."""
+from dataclasses import replace
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _engines(**kw):
+    from sed_crnn_b200 import config, engine
+    cfg = replace(config.PRESETS["c2"], seq_len=32, dropout=0.0)
+    a = engine.CRNNEngine(cfg, loss="bce", **kw)
+    b = engine.CRNNEngine(cfg, loss="bce", grad_exchange="p2p", **kw)
+    a.init_default(3)
+    b.init_default(3)
+    return cfg, a, b
+
+
+@pytest.mark.parametrize("clip", [1.0, 0.0])
+def test_p2p_world1_matches_clip_adam(built_lib, clip):
+    cfg, a, b = _engines(clip=clip, weight_decay=1e-4)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for step in range(4):
+        x = torch.randn(cfg.input_shape(8), device="cuda", generator=g)
+        y = (torch.rand(cfg.target_shape(8), device="cuda", generator=g) < 0.2).float()
+        la, _ = a.train_step(x, y)
+        lb, _ = b.train_step(x, y)
+        assert torch.equal(la, lb)
+        # the summed gradient IS the local gradient at world 1; the norm is folded in a different (fixed) order,
+        # so the clip coefficient may differ in its last bit
+        assert torch.equal(a.grads, b.grads)
+        assert torch.allclose(a._scalars[1], b._scalars[1], rtol=1e-6, atol=0)
+        assert torch.allclose(a.params, b.params, rtol=0, atol=2e-7), (a.params - b.params).abs().max()
+        assert torch.allclose(a.exp_avg_sq, b.exp_avg_sq, rtol=1e-5, atol=1e-12)
+    assert b.xch.status() == 0 and b.xch.seq == 4
+    # the two halves of the exchange region alternate
+    assert b.xch.next_grad_buffer().data_ptr() != b.grads.data_ptr()
+    b.xch.close()
+
+
+def test_p2p_rejects_bad_arguments(built_lib):
+    import ctypes as C
+    from sed_crnn_b200 import _lib
+    L = _lib.lib()
+    assert L.sedb200_p2p_region_bytes(0) == 0
+    assert L.sedb200_p2p_region_bytes(1024) >= 1024 + 2 * 4096
+    assert L.sedb200_p2p_grad_offset_bytes(1024, 1) - L.sedb200_p2p_grad_offset_bytes(1024, 0) == 4096
+    tab = (C.c_void_p * 1)(None)
+    rc = L.sedb200_p2p_allreduce_clip_adam(tab, 1, 0, 1024, 1, 1, None, None, None, None, 1e-3, .9, .999, 1e-8, 0., 1.,
+                                           1., None, None, 0, None)
+    assert rc == _lib.EINVAL
+    rc = L.sedb200_p2p_allreduce_clip_adam(tab, 17, 0, 1024, 1, 1, None, None, None, None, 1e-3, .9, .999, 1e-8, 0.,
+                                           1., 1., None, None, 0, None)
+    assert rc == _lib.EINVAL
