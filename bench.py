@@ -309,7 +309,18 @@ def run_ours(args, rank, world, local_rank):
     pk = peaks()
     cfg = config.PRESETS[args.config]
     B = PER_GPU_BATCH
-    eng = engine.CRNNEngine(cfg, loss="bce", lr=1e-3, weight_decay=1e-4, clip=1.0, seed=1234 + rank)
+    # gradient exchange: the fused NVLink peer-memory kernel when there is more than one rank ("auto"); if its
+    # set-up fails (agreed on by all ranks) the run uses NCCL and SAYS so in config.grad_exchange
+    gx_mode, gx_note = ("nccl" if world == 1 else "p2p") if args.grad_exchange == "auto" else args.grad_exchange, None
+    try:
+        eng = engine.CRNNEngine(cfg, loss="bce", lr=1e-3, weight_decay=1e-4, clip=1.0, seed=1234 + rank,
+                                grad_exchange=gx_mode)
+    except RuntimeError as e:
+        if gx_mode != "p2p" or args.grad_exchange == "p2p":
+            raise
+        gx_mode, gx_note = "nccl", f"p2p set-up failed: {e}"
+        sys.stderr.write(f"[bench] rank {rank}: {gx_note}; using NCCL\n")
+        eng = engine.CRNNEngine(cfg, loss="bce", lr=1e-3, weight_decay=1e-4, clip=1.0, seed=1234 + rank)
     eng.init_default(seed=0)                         # identical weights on every rank
 
     gx = torch.Generator().manual_seed(100 + rank)
@@ -442,7 +453,10 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": workload_name(args.config, world), "per_gpu_batch": B, "global_batch": B * world,
                    "seq_len": cfg.seq_len, "parallelism": f"dp{world}", "l2": "per-step working set (>1 GB of "
                    "activations) exceeds the 126 MB L2; 4 input batches rotated", "loss": "bce", "optimizer":
-                   "clip 1.0 + Adam(1e-3, wd 1e-4)", "dropout": cfg.dropout, "final_loss": final_loss},
+                   "clip 1.0 + Adam(1e-3, wd 1e-4)", "dropout": cfg.dropout, "final_loss": final_loss,
+                   "grad_exchange": {"nccl": "none (1 GPU)" if world == 1 else "NCCL all-reduce + clip/Adam kernels",
+                                     "p2p": "one fused kernel: NVLink peer-memory all-reduce + clip + Adam"}[gx_mode],
+                   **({"grad_exchange_note": gx_note} if gx_note else {})},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT,
                 "h2d_bytes_per_step": (xs_h[0].numel() + ys_h[0].numel()) * 4 * world, "d2h_bytes_per_step": 4 * world},
@@ -468,6 +482,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=["c1", "c2", "c5", "fork", "sedpy"])
     ap.add_argument("--ref-batch", type=int, default=16, help="CPU-baseline sample batch")
+    ap.add_argument("--grad-exchange", default="auto", choices=["auto", "nccl", "p2p"])
     ap.add_argument("--no-logmel", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU-baseline leg (profiling runs)")
     args = ap.parse_args()

@@ -84,26 +84,43 @@ class P2PGradExchange:
         if self.world > 16:
             raise ValueError("P2PGradExchange supports up to 16 ranks on one node")
         nbytes = int(self.L.sedb200_p2p_region_bytes(self.n))
+        # Set-up must fail on ALL ranks or on none (a rank that raised between two collectives would hang the
+        # others), so errors are collected and agreed on with one MIN all-reduce at the end.
+        err = None
+        self.own, self.regions = None, []
         with torch.cuda.device(self.device):
             ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
-            self.check(self.L.sedb200_p2p_region_alloc(nbytes, C.byref(ptr), handle))
-            self.own = ptr.value
-            handles = [bytes(handle)]
+            try:
+                self.check(self.L.sedb200_p2p_region_alloc(nbytes, C.byref(ptr), handle))
+                self.own = ptr.value
+            except Exception as e:                                    # noqa: BLE001
+                err = e
+            handles = [bytes(handle) if err is None else None]
             if self.world > 1:
                 gathered = [None] * self.world
-                dist.all_gather_object(gathered, (bytes(handle), torch.cuda.current_device()), group=group)
-                handles = [g[0] for g in gathered]
-            self.regions = []
+                dist.all_gather_object(gathered, handles[0], group=group)
+                handles = gathered
             for r, h in enumerate(handles):
-                if r == self.rank:
-                    self.regions.append(self.own)
+                if r == self.rank or err is not None or h is None:
+                    self.regions.append(self.own if r == self.rank else None)
                     continue
                 q = C.c_void_p()
-                self.check(self.L.sedb200_p2p_region_open((C.c_ubyte * 64).from_buffer_copy(h), C.byref(q)))
-                self.regions.append(q.value)
+                try:
+                    self.check(self.L.sedb200_p2p_region_open((C.c_ubyte * 64).from_buffer_copy(h), C.byref(q)))
+                    self.regions.append(q.value)
+                except Exception as e:                                # noqa: BLE001
+                    err = e
+                    self.regions.append(None)
             torch.cuda.synchronize()
-        if self.world > 1:
-            dist.barrier(group=group)                  # every region is zeroed and mapped before the first flag
+            if self.world > 1:
+                ok = torch.tensor([0 if (err is not None or any(q is None for q in self.regions)) else 1],
+                                  device=self.device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)   # also: every region zeroed + mapped
+                if ok.item() == 0 and err is None:
+                    err = RuntimeError("a peer rank could not set up its NVLink exchange region")
+        if err is not None:
+            self.close()
+            raise RuntimeError(f"P2PGradExchange set-up failed on rank {self.rank}: {err}") from err
         self.table = (C.c_void_p * self.world)(*self.regions)
         self.grad_bufs = [
             torch.as_tensor(_RawCudaArray(self.own + int(self.L.sedb200_p2p_grad_offset_bytes(self.n, par)), self.n),
@@ -140,7 +157,7 @@ class P2PGradExchange:
         with torch.cuda.device(self.device):
             torch.cuda.synchronize()
             for r, q in enumerate(self.regions):
-                if r != self.rank:
+                if r != self.rank and q is not None:
                     self.L.sedb200_p2p_region_close(q)
             self.grad_bufs = []
             self.L.sedb200_p2p_region_free(self.own)
