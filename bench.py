@@ -98,13 +98,13 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index=0, period_ms=50):
+        self.index, self.rows, self.proc, self.period_ms = index, [], None, int(period_ms)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE,
+                                          "-i", str(self.index), "-lms", str(self.period_ms)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -130,8 +130,10 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         rows = [r for (t, r) in self.rows if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end)]
-        if not rows:
-            rows = [r for (_, r) in self.rows]
+        window = f"timed + end-to-end regions, {self.period_ms} ms period"
+        if len(rows) < 2:                       # region shorter than two sampling periods: add the warm-up steps
+            rows = [r for (_, r) in self.rows]  # (same kernels, same load; the sampler starts just before them)
+            window = f"warm-up + timed + end-to-end regions, {self.period_ms} ms period"
         for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
@@ -145,7 +147,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm), "window": "timed + end-to-end regions, 20 ms period"}
+                "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------ reference arm
@@ -337,7 +339,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # ---- warm-up (the clock sampler starts here so that it is running well before the timed region)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, args.clock_period_ms)
     if rank == 0:
         sampler.start()
         sampler.wait_first()
@@ -375,12 +377,14 @@ def run_ours(args, rank, world, local_rank):
         for i in range(n):
             yield xs_h[i % n_in], ys_h[i % n_in]
 
-    for xd, yd, k in DevicePrefetcher(host_batches(2)):
-        l, _ = eng.train_step(xd, yd)
-    barrier()
-    pf = DevicePrefetcher(host_batches(args.steps))
-    e0.record()
-    for xd, yd, k in pf:
+    # one pipeline for warm-up and timed steps: 3 untimed steps bring the copy stream, the pinned buffers and the
+    # caching allocator to steady state, then exactly args.steps steps are timed
+    e2e_warm = 3
+    pf = DevicePrefetcher(host_batches(e2e_warm + args.steps))
+    for n_done, (xd, yd, k) in enumerate(pf):
+        if n_done == e2e_warm:
+            barrier()
+            e0.record()
         l, _ = eng.train_step(xd, yd)
         pf.release(k)
         loss_h.copy_(l.reshape(1), non_blocking=True)
@@ -483,6 +487,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=["c1", "c2", "c5", "fork", "sedpy"])
     ap.add_argument("--ref-batch", type=int, default=16, help="CPU-baseline sample batch")
     ap.add_argument("--grad-exchange", default="auto", choices=["auto", "nccl", "p2p"])
+    ap.add_argument("--clock-period-ms", type=int, default=50, help="nvidia-smi sampling period during the run")
     ap.add_argument("--no-logmel", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU-baseline leg (profiling runs)")
     args = ap.parse_args()
