@@ -314,6 +314,197 @@ gru_scan_bwd_warp_kernel(const float* __restrict__ dout, const float* __restrict
 }
 
 
+// ------------------------------------------------------------------------------ H = 32: broadcast-through-smem scans
+// Same ownership as the warp-resident kernels (one warp per (direction, batch row), lane j <-> hidden unit j, its
+// W_hh rows / columns in registers), but the vector every lane needs (h, or the three gate gradients) is written
+// to a double-buffered shared row and read back as broadcast LDS.128 -- 8 loads instead of 32 dependent-latency
+// shuffles per 32 values -- and the dot products run as packed fma.f32x2 on (k, k+1) pairs in two / four
+// independent chains.  With one warp per SM sub-partition the step time IS the dependent-instruction latency,
+// so this is what sets the speed of the whole scan.
+constexpr int kChF32 = 8, kChB32 = 6;
+
+// REV is the scan direction as a compile-time constant: every per-step address is then `base + immediate`, and the
+// integer work per step drops to two pointer bumps per chunk.
+template <bool REV>
+__device__ __forceinline__ void gru_fwd_bcast32_body(const float* __restrict__ gi, const float* __restrict__ whh,
+                                                     const float* __restrict__ bhh, float* __restrict__ out,
+                                                     float* __restrict__ gates, int T, long b, float (*h_s)[32]) {
+    constexpr int H = 32, H3 = 96, dir = REV ? 1 : 0;
+    constexpr long sGi = 2 * H3, sOut = 2 * H, sGs = 2 * 4 * H;            // floats per time step
+    constexpr long dGi = REV ? -sGi : sGi, dOut = REV ? -sOut : sOut, dGs = REV ? -sGs : sGs;
+    const int j = threadIdx.x & 31;
+    const float* W = whh + (size_t)dir * H3 * H;
+    float2 w2[3][H / 2];
+    float bias[3];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+        bias[g] = __ldg(bhh + dir * H3 + g * H + j);
+#pragma unroll
+        for (int k = 0; k < H / 2; ++k) w2[g][k] = __ldg(reinterpret_cast<const float2*>(W + (g * H + j) * H) + k);
+    }
+    const long t0 = REV ? T - 1 : 0;
+    const float* gp = gi + ((b * T + t0) * 2 + dir) * H3 + j;               // this lane's gi of the current chunk
+    float* op = out + (b * T + t0) * sOut + dir * H + j;
+    float* sp = gates + ((b * T + t0) * 2 + dir) * 4 * H + j;
+    float h = 0.0f;
+    float cur[kChF32][3], nxt[kChF32][3];
+    auto load_chunk = [&](float (&dst)[kChF32][3], const float* g, int step0) {
+#pragma unroll
+        for (int s = 0; s < kChF32; ++s) {
+            if (step0 + s < T) {
+                dst[s][0] = __ldg(g + s * dGi); dst[s][1] = __ldg(g + s * dGi + H); dst[s][2] = __ldg(g + s * dGi + 2 * H);
+            } else {
+                dst[s][0] = dst[s][1] = dst[s][2] = 0.0f;
+            }
+        }
+    };
+    load_chunk(cur, gp, 0);
+    int buf = 0;
+    for (int step0 = 0; step0 < T; step0 += kChF32) {
+        gp += kChF32 * dGi;
+        load_chunk(nxt, gp, step0 + kChF32);
+#pragma unroll
+        for (int s = 0; s < kChF32; ++s) {
+            if (step0 + s >= T) break;
+            h_s[buf * 4][j] = h;
+            __syncwarp();
+            const float4* hv4 = reinterpret_cast<const float4*>(h_s[buf * 4]);
+            buf ^= 1;
+            float2 acc[3][2];
+#pragma unroll
+            for (int g = 0; g < 3; ++g) acc[g][0] = acc[g][1] = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int i = 0; i < H / 4; ++i) {
+                const float4 hv = hv4[i];
+#pragma unroll
+                for (int g = 0; g < 3; ++g) {
+                    acc[g][0] = __ffma2_rn(w2[g][2 * i], make_float2(hv.x, hv.y), acc[g][0]);
+                    acc[g][1] = __ffma2_rn(w2[g][2 * i + 1], make_float2(hv.z, hv.w), acc[g][1]);
+                }
+            }
+            const float a0 = bias[0] + ((acc[0][0].x + acc[0][0].y) + (acc[0][1].x + acc[0][1].y));
+            const float a1 = bias[1] + ((acc[1][0].x + acc[1][0].y) + (acc[1][1].x + acc[1][1].y));
+            const float a2 = bias[2] + ((acc[2][0].x + acc[2][0].y) + (acc[2][1].x + acc[2][1].y));
+            const float r = fast_sigmoid(cur[s][0] + a0);
+            const float z = fast_sigmoid(cur[s][1] + a1);
+            const float n = fast_tanh(fmaf(r, a2, cur[s][2]));
+            h = fmaf(z, h - n, n);
+            op[s * dOut] = h;
+            sp[s * dGs] = r; sp[s * dGs + H] = z; sp[s * dGs + 2 * H] = n; sp[s * dGs + 3 * H] = a2;
+        }
+        op += kChF32 * dOut;
+        sp += kChF32 * dGs;
+#pragma unroll
+        for (int s = 0; s < kChF32; ++s) { cur[s][0] = nxt[s][0]; cur[s][1] = nxt[s][1]; cur[s][2] = nxt[s][2]; }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+gru_scan_fwd_bcast32_kernel(const float* __restrict__ gi, const float* __restrict__ whh, const float* __restrict__ bhh,
+                            float* __restrict__ out, float* __restrict__ gates, int B, int T) {
+    __shared__ __align__(16) float h_s[2 * 4][32];          // [buffer][warp] rows; a warp uses rows warp and 4 + warp
+    const int warp = threadIdx.x >> 5;
+    const long b = (long)blockIdx.x * 4 + warp;
+    if (b >= B) return;                                     // warps are independent: no block-level barrier below
+    if (blockIdx.y == 0) gru_fwd_bcast32_body<false>(gi, whh, bhh, out, gates, T, b, h_s + warp);
+    else gru_fwd_bcast32_body<true>(gi, whh, bhh, out, gates, T, b, h_s + warp);
+}
+
+template <bool REV>
+__device__ __forceinline__ void gru_bwd_bcast32_body(const float* __restrict__ dout, const float* __restrict__ out,
+                                                     const float* __restrict__ gates, const float* __restrict__ whh,
+                                                     float* __restrict__ dgi, float* __restrict__ dgh,
+                                                     float* __restrict__ part_b, int T, long b, float (*dg_s)[96]) {
+    // REV = the FORWARD direction of this GRU half; the backward scan walks time the other way
+    constexpr int H = 32, H3 = 96, dir = REV ? 1 : 0;
+    constexpr long sOut = 2 * H, sGs = 2 * 4 * H, sDg = 2 * H3;
+    constexpr long dOut = REV ? sOut : -sOut, dGs = REV ? sGs : -sGs, dDg = REV ? sDg : -sDg;
+    const int j = threadIdx.x & 31;
+    const float* W = whh + (size_t)dir * H3 * H;
+    float2 wc[H3 / 2];                                          // (W_hh[e][j], W_hh[e+1][j]) for even e
+#pragma unroll
+    for (int e = 0; e < H3 / 2; ++e) wc[e] = make_float2(__ldg(W + (2 * e) * H + j), __ldg(W + (2 * e + 1) * H + j));
+    const long t0 = REV ? 0 : T - 1;
+    const float* dp = dout + (b * T + t0) * sOut + dir * H + j;
+    const float* hp_ = out + (b * T + t0) * sOut + dir * H + j;         // h_prev of step t is out[t -/+ 1]
+    const float* gsp = gates + ((b * T + t0) * 2 + dir) * 4 * H + j;
+    float* gip = dgi + ((b * T + t0) * 2 + dir) * H3 + j;
+    float* ghp = dgh + ((b * T + t0) * 2 + dir) * H3 + j;
+    float sb_r = 0, sb_z = 0, sb_n = 0, sb_q = 0;
+    float dh = 0.0f;
+    float cur[kChB32][6], nxt[kChB32][6];                       // dout, r, z, n, q, h_prev
+    auto load_chunk = [&](float (&dst)[kChB32][6], const float* d, const float* hpp, const float* gs, int step0) {
+#pragma unroll
+        for (int s = 0; s < kChB32; ++s) {
+            if (step0 + s < T) {
+                dst[s][0] = __ldg(d + s * dOut);
+                dst[s][1] = __ldg(gs + s * dGs); dst[s][2] = __ldg(gs + s * dGs + H);
+                dst[s][3] = __ldg(gs + s * dGs + 2 * H); dst[s][4] = __ldg(gs + s * dGs + 3 * H);
+                dst[s][5] = (step0 + s + 1 < T) ? __ldg(hpp + (s + 1) * dOut) : 0.0f;   // forward-previous step
+            } else {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) dst[s][q] = 0.0f;
+            }
+        }
+    };
+    load_chunk(cur, dp, hp_, gsp, 0);
+    int buf = 0;
+    for (int step0 = 0; step0 < T; step0 += kChB32) {
+        dp += kChB32 * dOut; hp_ += kChB32 * dOut; gsp += kChB32 * dGs;
+        load_chunk(nxt, dp, hp_, gsp, step0 + kChB32);
+#pragma unroll
+        for (int s = 0; s < kChB32; ++s) {
+            if (step0 + s >= T) break;
+            const float c_do = cur[s][0], r = cur[s][1], z = cur[s][2], n = cur[s][3], q = cur[s][4], hp = cur[s][5];
+            const float dht = c_do + dh;
+            const float dn = dht * (1.0f - z);
+            const float dz = dht * (hp - n);
+            const float dan = dn * (1.0f - n * n);
+            const float dar = dan * q * r * (1.0f - r);
+            const float daz = dz * z * (1.0f - z);
+            const float dq = dan * r;
+            float* ds = dg_s[buf * 4];
+            ds[j] = dar; ds[H + j] = daz; ds[2 * H + j] = dq;
+            __syncwarp();
+            gip[s * dDg] = dar; gip[s * dDg + H] = daz; gip[s * dDg + 2 * H] = dan;
+            ghp[s * dDg] = dar; ghp[s * dDg + H] = daz; ghp[s * dDg + 2 * H] = dq;
+            sb_r += dar; sb_z += daz; sb_n += dan; sb_q += dq;
+            const float4* dv4 = reinterpret_cast<const float4*>(ds);
+            buf ^= 1;
+            float2 acc[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[c] = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int i = 0; i < H3 / 4; ++i) {
+                const float4 dv = dv4[i];
+                acc[(2 * i) & 3] = __ffma2_rn(wc[2 * i], make_float2(dv.x, dv.y), acc[(2 * i) & 3]);
+                acc[(2 * i + 1) & 3] = __ffma2_rn(wc[2 * i + 1], make_float2(dv.z, dv.w), acc[(2 * i + 1) & 3]);
+            }
+            dh = fmaf(dht, z, ((acc[0].x + acc[0].y) + (acc[1].x + acc[1].y)) + ((acc[2].x + acc[2].y) + (acc[3].x + acc[3].y)));
+        }
+        gip += kChB32 * dDg; ghp += kChB32 * dDg;
+#pragma unroll
+        for (int s = 0; s < kChB32; ++s)
+#pragma unroll
+            for (int q = 0; q < 6; ++q) cur[s][q] = nxt[s][q];
+    }
+    float* pb = part_b + (b * 2) * 2 * H3;                        // [B][ih|hh][2][3H]
+    pb[dir * H3 + j] = sb_r; pb[dir * H3 + H + j] = sb_z; pb[dir * H3 + 2 * H + j] = sb_n;
+    pb[2 * H3 + dir * H3 + j] = sb_r; pb[2 * H3 + dir * H3 + H + j] = sb_z; pb[2 * H3 + dir * H3 + 2 * H + j] = sb_q;
+}
+
+__global__ void __launch_bounds__(128)
+gru_scan_bwd_bcast32_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                            const float* __restrict__ gates, const float* __restrict__ whh, float* __restrict__ dgi,
+                            float* __restrict__ dgh, float* __restrict__ part_b, int B, int T) {
+    __shared__ __align__(16) float dg_s[2 * 4][96];
+    const int warp = threadIdx.x >> 5;
+    const long b = (long)blockIdx.x * 4 + warp;
+    if (b >= B) return;
+    if (blockIdx.y == 0) gru_bwd_bcast32_body<false>(dout, out, gates, whh, dgi, dgh, part_b, T, b, dg_s + warp);
+    else gru_bwd_bcast32_body<true>(dout, out, gates, whh, dgi, dgh, part_b, T, b, dg_s + warp);
+}
+
 // ------------------------------------------------------------------------------ H = 64 / 128: K-split scans
 // W_hh no longer fits one lane per unit, so each hidden unit is served by FOUR adjacent lanes that each keep a
 // quarter of the unit's three W_hh rows in registers (3*H/4 values) and reduce with two xor-shuffles; the CTA
@@ -502,7 +693,11 @@ inline int round32(int v) { return (v + 31) / 32 * 32; }
 
 int gru_scan_forward(const float* gi, const float* whh, const float* bhh, float* out, float* gates, int B, int T,
                      int H, cudaStream_t st) {
-    if (H == 32) return launch_warp_fwd<32>(gi, whh, bhh, out, gates, B, T, st);
+    if (H == 32) {
+        gru_scan_fwd_bcast32_kernel<<<dim3((B + 3) / 4, 2), 128, 0, st>>>(gi, whh, bhh, out, gates, B, T);
+        SED_POST_LAUNCH();
+        return SEDB200_OK;
+    }
     if (H == 16) return launch_warp_fwd<16>(gi, whh, bhh, out, gates, B, T, st);
     if (H == 8) return launch_warp_fwd<8>(gi, whh, bhh, out, gates, B, T, st);
     if (H == 128 || H == 64) {
@@ -528,7 +723,11 @@ bool gru_scan_fused_param_grads(int H) { return H == 128 || H == 64 || H == 32 |
 
 int gru_scan_backward(const float* dout, const float* out, const float* gates, const float* whh, float* dgi,
                       float* dgh, float* part_w, float* part_b, int B, int T, int H, cudaStream_t st) {
-    if (H == 32) return launch_warp_bwd<32>(dout, out, gates, whh, dgi, dgh, part_w, part_b, B, T, st);
+    if (H == 32) {
+        gru_scan_bwd_bcast32_kernel<<<dim3((B + 3) / 4, 2), 128, 0, st>>>(dout, out, gates, whh, dgi, dgh, part_b, B, T);
+        SED_POST_LAUNCH();
+        return SEDB200_OK;
+    }
     if (H == 16) return launch_warp_bwd<16>(dout, out, gates, whh, dgi, dgh, part_w, part_b, B, T, st);
     if (H == 8) return launch_warp_bwd<8>(dout, out, gates, whh, dgi, dgh, part_w, part_b, B, T, st);
     if (H == 128 || H == 64) {
