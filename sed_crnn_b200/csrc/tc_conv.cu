@@ -62,7 +62,9 @@ constexpr int kStages = 3;
 constexpr int kTileM = 128, kTileN = 128, kBlockK = 64;
 constexpr int kTileBytes = kTileM * kBlockK * 2;                 // 16 KB: one bf16 operand tile
 constexpr int kStageBytes = 4 * kTileBytes;                      // A_hi, A_lo, B_hi, B_lo
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 4096 /*BN-stat staging*/;
+constexpr int kEpiPitch = 36;                                    // floats per staged row: LDS/STS.128 conflict-free
+constexpr int kEpiBytes = 4 * 32 * kEpiPitch * 4;                // one 32 x 32 staging tile per epilogue warp
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 4096 /*BN-stat staging*/ + kEpiBytes;
 constexpr int kThreads = 256;
 constexpr uint32_t kTmemCols = 256;                              // two 128-column accumulators
 
@@ -87,6 +89,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint64_t* tempty = bars + 2 * kStages + 2;// [2]        epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
     float* stat_s = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);     // [4 warps][2][128]
+    float* epi_stage = stat_s + 1024;                                                 // [4 warps][32][kEpiPitch]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -160,45 +163,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const int b = mt / p.tiles_per_img, h0 = (mt % p.tiles_per_img) * p.Ht;
             mbar_wait(tfull + buf, bphase);
             tc_fence_after();
-            const int row = q * 32 + lane;
-            const bool valid = (h0 + row / p.W) < p.H;
-            float* dst = p.out + (((long)b * p.H + h0) * p.W + row) * p.out_ld + nt * kTileN;
+            // TMEM hands every lane one output ROW (pixel); each 32 x 32 chunk goes through a per-warp staging tile so
+            // that one store instruction writes four full 128 B channel segments (instead of 16 B pieces of 32 pixels),
+            // and the BatchNorm column sums are plain conflict-free column reads of the same tile.
+            float* dst0 = p.out + (((long)b * p.H + h0) * p.W + q * 32) * p.out_ld + nt * kTileN;
+            float* stg = epi_stage + q * (32 * kEpiPitch);
+            const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
 #pragma unroll 1
             for (int cc = 0; cc < kTileN / 32; ++cc) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * kTileN + cc * 32, v);
-                if (p.bias) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nt * kTileN + cc * 32 + j));
-                        v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
-                    }
-                }
-                if (valid) {
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(stg + lane * kEpiPitch + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                __syncwarp();
+                float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + nt * kTileN + cc * 32 + sub_c));
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(dst + cc * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                for (int r = 0; r < 32; r += 4) {
+                    float4 o = *reinterpret_cast<const float4*>(stg + (r + sub_r) * kEpiPitch + sub_c);
+                    o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                    if ((h0 + (q * 32 + r + sub_r) / p.W) < p.H)
+                        *reinterpret_cast<float4*>(dst0 + (long)(r + sub_r) * p.out_ld + cc * 32 + sub_c) = o;
                 }
                 if (p.stats) {
-                    // per-column sum / sum of squares over this warp's 32 rows: butterfly reduce-scatter, after which
-                    // lane L holds column cc*32 + L
-                    float s1[32], s2[32];
+                    // lane L: sum / sum of squares of column cc*32 + L over this warp's 32 rows, fixed order
+                    const float bl = p.bias ? __ldg(p.bias + nt * kTileN + cc * 32 + lane) : 0.0f;
+                    float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { s1[j] = valid ? v[j] : 0.0f; s2[j] = s1[j] * s1[j]; }
-#pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) {
-                        const bool up = (lane & off) != 0;
-#pragma unroll
-                        for (int i = 0; i < off; ++i) {
-                            const float k1 = up ? s1[i + off] : s1[i], g1 = up ? s1[i] : s1[i + off];
-                            const float k2 = up ? s2[i + off] : s2[i], g2 = up ? s2[i] : s2[i + off];
-                            s1[i] = k1 + __shfl_xor_sync(0xffffffffu, g1, off);
-                            s2[i] = k2 + __shfl_xor_sync(0xffffffffu, g2, off);
-                        }
+                    for (int r = 0; r < 32; ++r) {
+                        const float x = stg[r * kEpiPitch + lane] + bl;
+                        if ((h0 + (q * 32 + r) / p.W) < p.H) { s1 += x; s2 = fmaf(x, x, s2); }
                     }
-                    stat_s[(q * 2 + 0) * 128 + cc * 32 + lane] = s1[0];
-                    stat_s[(q * 2 + 1) * 128 + cc * 32 + lane] = s2[0];
+                    stat_s[(q * 2 + 0) * 128 + cc * 32 + lane] = s1;
+                    stat_s[(q * 2 + 1) * 128 + cc * 32 + lane] = s2;
                 }
+                __syncwarp();
             }
             if (p.stats) {
                 asm volatile("bar.sync 1, 128;" ::: "memory");

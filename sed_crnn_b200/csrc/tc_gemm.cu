@@ -23,7 +23,9 @@ constexpr int kStages = 3;
 constexpr int kTile = 128, kBlockK = 64;
 constexpr int kTileBytes = kTile * kBlockK * 2;          // 16 KB
 constexpr int kStageBytes = 4 * kTileBytes;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+constexpr int kEpiPitch = 36;                            // floats per staged row: 16 B aligned, conflict-free as LDS/STS.128
+constexpr int kEpiBytes = 4 * 32 * kEpiPitch * 4;        // one 32 x 32 staging tile per epilogue warp
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kEpiBytes;
 constexpr int kThreads = 256;
 constexpr uint32_t kTmemCols = 256;
 
@@ -61,6 +63,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint64_t* tfull = bars + 2 * kStages;
     uint64_t* tempty = bars + 2 * kStages + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    float* epi_stage = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -145,12 +148,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 mbar_wait(tfull + buf, bphase);
                 tc_fence_after();
             }
-            const int row = mt * kTile + q * 32 + lane;
-            const bool rvalid = row < p.M;
-            float* dst = p.slices == 1 ? p.out + (long)row * p.out_ld
-                                       : p.out + ((long)slice * p.M + row) * p.N;
+            // TMEM hands every lane one ROW of the tile; storing that directly would scatter 16 B pieces over 32 rows
+            // per instruction.  Each 32 x 32 chunk is transposed through a per-warp staging tile instead, so that one
+            // store instruction writes four full 128 B row segments.
+            const int row0 = mt * kTile + q * 32;
+            float* dst0 = p.slices == 1 ? p.out + (long)row0 * p.out_ld : p.out + ((long)slice * p.M + row0) * p.N;
+            const long ld = p.slices == 1 ? p.out_ld : (long)p.N;
+            float* stg = epi_stage + q * (32 * kEpiPitch);
+            const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
 #pragma unroll 1
             for (int cc = 0; cc < kTile / 32; ++cc) {
+                const int col0 = nt * kTile + cc * 32;
+                if (col0 >= p.N) break;                     // tile columns beyond N (N % 4 == 0)
                 float v[32];
                 if (has) {
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * kTile + cc * 32, v);
@@ -158,20 +167,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = 0.0f;
                 }
-                if (rvalid) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const int col = nt * kTile + cc * 32 + j;
-                        if (col < p.N) {                    // N % 4 == 0
-                            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                            if (p.bias) {
-                                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                                o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-                            }
-                            *reinterpret_cast<float4*>(dst + col) = o;
-                        }
-                    }
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(stg + lane * kEpiPitch + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                __syncwarp();
+                const int col = col0 + sub_c;
+                float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias && col < p.N) bb = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+#pragma unroll
+                for (int r = 0; r < 32; r += 4) {
+                    float4 o = *reinterpret_cast<const float4*>(stg + (r + sub_r) * kEpiPitch + sub_c);
+                    o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                    if (row0 + r + sub_r < p.M && col < p.N)
+                        *reinterpret_cast<float4*>(dst0 + (long)(r + sub_r) * ld + col) = o;
                 }
+                __syncwarp();
             }
             if (has) {
                 tc_fence_before();
