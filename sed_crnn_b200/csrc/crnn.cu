@@ -476,6 +476,51 @@ bn_pool_bwd_dy_kernel(const float* __restrict__ y, const float* __restrict__ sta
 }
 
 
+// Same pass with a compile-time pool width that divides W (no floor-dropped columns): the P conv outputs of a
+// window are loaded once, the winner is found in registers, and the pixel index uses 32-bit arithmetic.
+//   dy = scale*dz[winner] - A - Bc*y   with   Bc = scale*invstd*k2,  A = scale*k1 - mean*Bc
+template <int P>
+__global__ void __launch_bounds__(256)
+bn_pool_bwd_dy_t_kernel(const float* __restrict__ y, const float* __restrict__ stat, const float* __restrict__ dA,
+                        const float* __restrict__ bnsum, unsigned n_pix, PoolGeom g, float* __restrict__ dy,
+                        __nv_bfloat16* __restrict__ dy_hi, __nv_bfloat16* __restrict__ dy_lo) {
+    const int C4 = g.C >> 2, rows = 256 / C4;
+    const int c4 = threadIdx.x % C4, prow = threadIdx.x / C4, c = c4 * 4;
+    const float4 sc = *reinterpret_cast<const float4*>(stat + 2 * g.C + c);
+    const float4 sh = *reinterpret_cast<const float4*>(stat + 3 * g.C + c);
+    const float4 mu = *reinterpret_cast<const float4*>(stat + c);
+    const float4 is = *reinterpret_cast<const float4*>(stat + g.C + c);
+    const float4 k1 = *reinterpret_cast<const float4*>(bnsum + c);
+    const float4 k2 = *reinterpret_cast<const float4*>(bnsum + g.C + c);
+    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+    const float Bc[4] = {sc.x * is.x * k2.x, sc.y * is.y * k2.y, sc.z * is.z * k2.z, sc.w * is.w * k2.w};
+    const float Ac[4] = {sc.x * k1.x - mu.x * Bc[0], sc.y * k1.y - mu.y * Bc[1], sc.z * k1.z - mu.z * Bc[2],
+                         sc.w * k1.w - mu.w * Bc[3]};
+    const unsigned Wo = (unsigned)g.Wo, H = (unsigned)g.H;
+    for (unsigned pix = blockIdx.x * rows + prow; pix < n_pix; pix += gridDim.x * rows) {
+        const unsigned t = pix / Wo, wo = pix - t * Wo;
+        const unsigned b = t / H, h = t - b * H;
+        const long row = ((long)b * g.H + h) * g.W + (long)wo * P;
+        float4 v[P];
+        float gq[4], dz[4], yarg[4];
+        int arg[4];
+        load_window<P>(y + row * g.C + c, g.C, v);
+        load_dA(dA + (long)b * g.oB + (long)h * g.oH + (long)wo * g.oW + (long)c * g.oC, g.oC, gq);
+        eval_window<P>(v, scv, shv, gq, g, (long)pix * C4 + c4, dz, arg, yarg);
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            const float vv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+            float o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[q] = fmaf(-Bc[q], vv[q], (arg[q] == j ? scv[q] * dz[q] : 0.0f) - Ac[q]);
+            const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
+            if (dy) *reinterpret_cast<float4*>(dy + (row + j) * g.C + c) = o4;
+            if (dy_hi) store_planes4(dy_hi, dy_lo, ((row + j) * g.C + c) >> 2, o4);
+        }
+    }
+}
+
+
 // ----------------------------------------------------------------------------- first conv block, direct
 // conv block 0 has K = 9*Cin = 9 or 18: a degenerate GEMM whose cost is the 4 B x B*H*W*C activation it
 // produces, not its FLOPs.  Two direct fp32 kernels keep that tensor's HBM traffic at the minimum:
@@ -1204,7 +1249,14 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         __nv_bfloat16* dyh = P.conv_tc_all[i] ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(ws) + P.dyp) : nullptr;
         __nv_bfloat16* dyl = P.conv_tc_all[i] ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(ws) + P.dyp + P.dy_plane_bytes) : nullptr;
 { char _nm[40]; snprintf(_nm, sizeof _nm, "pool%d.bwd_dy", i); SED_PROF(_nm, st);
-        bn_pool_bwd_dy_kernel<<<ew_blocks(n_vec), 256, 0, st>>>(y, stat, dA, bnsum, n_vec, g, P.conv_tc_all[i] ? nullptr : dy, dyh, dyl);
+        float* dyf = P.conv_tc_all[i] ? nullptr : dy;
+        const bool exact_t = g.W == g.Wo * g.p && (g.p == 5 || g.p == 2) && 256 % (P.C / 4) == 0 && n_pix_out < (1L << 31);
+        if (exact_t && g.p == 5)
+            bn_pool_bwd_dy_t_kernel<5><<<nblk, 256, 0, st>>>(y, stat, dA, bnsum, (unsigned)n_pix_out, g, dyf, dyh, dyl);
+        else if (exact_t)
+            bn_pool_bwd_dy_t_kernel<2><<<nblk, 256, 0, st>>>(y, stat, dA, bnsum, (unsigned)n_pix_out, g, dyf, dyh, dyl);
+        else
+            bn_pool_bwd_dy_kernel<<<ew_blocks(n_vec), 256, 0, st>>>(y, stat, dA, bnsum, n_vec, g, dyf, dyh, dyl);
         SED_POST_LAUNCH();
 }
 
