@@ -258,6 +258,54 @@ bn_relu_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ s
     }
 }
 
+// Same kernel with a compile-time pool width and 32-bit index arithmetic (the P loads of a window are all in flight
+// before the first max; no 64-bit divisions per element).
+template <int P>
+__global__ void __launch_bounds__(256)
+bn_relu_pool_fwd_t_kernel(const float* __restrict__ y, const float* __restrict__ stat, float* __restrict__ out,
+                          __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, unsigned n_pix,
+                          PoolGeom g) {
+    const int C4 = g.C >> 2, rows = 256 / C4;
+    const int c4 = threadIdx.x % C4, prow = threadIdx.x / C4, c = c4 * 4;
+    const float4 sc = *reinterpret_cast<const float4*>(stat + 2 * g.C + c);
+    const float4 sh = *reinterpret_cast<const float4*>(stat + 3 * g.C + c);
+    const float keep_scale = g.drop_p > 0.0f ? 1.0f / (1.0f - g.drop_p) : 1.0f;
+    const unsigned Wo = (unsigned)g.Wo, H = (unsigned)g.H;
+    for (unsigned pix = blockIdx.x * rows + prow; pix < n_pix; pix += gridDim.x * rows) {
+        const unsigned t = pix / Wo, wo = pix - t * Wo;
+        const unsigned b = t / H, h = t - b * H;
+        float4 v[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j)
+            v[j] = __ldg(reinterpret_cast<const float4*>(y + ((((long)b * g.H + h) * g.W) + (long)wo * P + j) * g.C + c));
+        float4 m = make_float4(0.0f, 0.0f, 0.0f, 0.0f);           // relu floor
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            m.x = fmaxf(m.x, fmaf(v[j].x, sc.x, sh.x));
+            m.y = fmaxf(m.y, fmaf(v[j].y, sc.y, sh.y));
+            m.z = fmaxf(m.z, fmaf(v[j].z, sc.z, sh.z));
+            m.w = fmaxf(m.w, fmaf(v[j].w, sc.w, sh.w));
+        }
+        const long i = (long)pix * C4 + c4;                        // same element numbering as the generic kernel
+        if (g.drop_p > 0.0f) {
+            const unsigned long long e = (unsigned long long)i * 4;
+            m.x = uniform01(g.seed, e + 0) >= g.drop_p ? m.x * keep_scale : 0.0f;
+            m.y = uniform01(g.seed, e + 1) >= g.drop_p ? m.y * keep_scale : 0.0f;
+            m.z = uniform01(g.seed, e + 2) >= g.drop_p ? m.z * keep_scale : 0.0f;
+            m.w = uniform01(g.seed, e + 3) >= g.drop_p ? m.w * keep_scale : 0.0f;
+        }
+        if (out_hi) store_planes4(out_hi, out_lo, i, m);
+        if (out) {
+            float* dst = out + (long)b * g.oB + (long)h * g.oH + (long)wo * g.oW + (long)c * g.oC;
+            if (g.oC == 1) {
+                *reinterpret_cast<float4*>(dst) = m;
+            } else {
+                dst[0] = m.x; dst[g.oC] = m.y; dst[2 * g.oC] = m.z; dst[3 * g.oC] = m.w;
+            }
+        }
+    }
+}
+
 // shared by the two backward passes: for one pooling window and 4 channels, recompute the winner and
 // return dz at the winner (0 elsewhere) plus the winner index.
 struct WindowGrad { float dz[4]; int arg[4]; };
@@ -346,17 +394,16 @@ bn_pool_bwd_sums_t_kernel(const float* __restrict__ y, const float* __restrict__
     const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
     const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, isv[4] = {is.x, is.y, is.z, is.w};
     float a[4] = {0, 0, 0, 0}, bsum[4] = {0, 0, 0, 0};
-    for (long pix = (long)blockIdx.x * rows + prow; pix < n_pix; pix += (long)gridDim.x * rows) {
-        long t = pix;
-        const int wo = (int)(t % g.Wo); t /= g.Wo;
-        const int h = (int)(t % g.H);
-        const long b = t / g.H;
+    const unsigned Wo = (unsigned)g.Wo, H = (unsigned)g.H, npx = (unsigned)n_pix;     // n_pix < 2^31 (launcher)
+    for (unsigned pix = blockIdx.x * rows + prow; pix < npx; pix += gridDim.x * rows) {
+        const unsigned t = pix / Wo, wo = pix - t * Wo;
+        const unsigned b = t / H, h = t - b * H;
         float4 v[P];
         float gq[4], dz[4], yarg[4];
         int arg[4];
-        load_window<P>(y + (((b * g.H + h) * g.W) + (long)wo * P) * g.C + c, g.C, v);
-        load_dA(dA + b * g.oB + h * g.oH + wo * g.oW + c * g.oC, g.oC, gq);
-        eval_window<P>(v, scv, shv, gq, g, pix * C4 + c4, dz, arg, yarg);
+        load_window<P>(y + ((((long)b * g.H + h) * g.W) + (long)wo * P) * g.C + c, g.C, v);
+        load_dA(dA + (long)b * g.oB + (long)h * g.oH + (long)wo * g.oW + (long)c * g.oC, g.oC, gq);
+        eval_window<P>(v, scv, shv, gq, g, (long)pix * C4 + c4, dz, arg, yarg);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             a[q] += dz[q];
@@ -1002,7 +1049,15 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
             const bool to_planes = (i + 1 < P.n_conv) && P.conv_tc_all[i + 1];
             __nv_bfloat16* ph = to_planes ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(ws) + P.actp[i]) : nullptr;
             __nv_bfloat16* pl = to_planes ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(ws) + P.actp[i] + P.act_plane_bytes[i]) : nullptr;
-            bn_relu_pool_fwd_kernel<<<ew_blocks(n_vec), 256, 0, st>>>(y, stat, to_planes ? nullptr : wsf(ws, P.act[i]), ph, pl, n_vec, g);
+            float* of = to_planes ? nullptr : wsf(ws, P.act[i]);
+            const int C4 = P.C / 4;
+            const long n_pix = n_vec / C4;
+            const bool fast = (g.p == 5 || g.p == 2) && 256 % C4 == 0 && n_pix < (1L << 31);
+            const int prow = 256 / C4;
+            const int nb = (int)std::min<long>((n_pix + prow - 1) / prow, 148L * 16);
+            if (fast && g.p == 5) bn_relu_pool_fwd_t_kernel<5><<<nb, 256, 0, st>>>(y, stat, of, ph, pl, (unsigned)n_pix, g);
+            else if (fast) bn_relu_pool_fwd_t_kernel<2><<<nb, 256, 0, st>>>(y, stat, of, ph, pl, (unsigned)n_pix, g);
+            else bn_relu_pool_fwd_kernel<<<ew_blocks(n_vec), 256, 0, st>>>(y, stat, of, ph, pl, n_vec, g);
         }
         SED_POST_LAUNCH();
 }
@@ -1209,8 +1264,9 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         const int rows = 256 / (P.C / 4);
         const int nblk = (int)std::min<long>((n_pix_out + rows - 1) / rows, 148L * 16);
 { char _nm[40]; snprintf(_nm, sizeof _nm, "pool%d.bwd_sums", i); SED_PROF(_nm, st);
-        if (g.p == 5) bn_pool_bwd_sums_t_kernel<5><<<nblk, 256, 0, st>>>(y, stat, dA, n_pix_out, g, part);
-        else if (g.p == 2) bn_pool_bwd_sums_t_kernel<2><<<nblk, 256, 0, st>>>(y, stat, dA, n_pix_out, g, part);
+        const bool idx32 = n_pix_out < (1L << 31);
+        if (g.p == 5 && idx32) bn_pool_bwd_sums_t_kernel<5><<<nblk, 256, 0, st>>>(y, stat, dA, n_pix_out, g, part);
+        else if (g.p == 2 && idx32) bn_pool_bwd_sums_t_kernel<2><<<nblk, 256, 0, st>>>(y, stat, dA, n_pix_out, g, part);
         else bn_pool_bwd_sums_kernel<<<nblk, 256, 0, st>>>(y, stat, dA, n_pix_out, g, part);
         SED_POST_LAUNCH();
 }
