@@ -183,12 +183,24 @@ __global__ void bn_finalize_eval_kernel(int C, const float* __restrict__ gamma, 
 }
 
 // ----------------------------------------------------------------------------- dropout generator
-__device__ __forceinline__ float uniform01(unsigned long long seed, unsigned long long idx) {
+// One 64-bit hash (splitmix64 finaliser) per group of FOUR consecutive elements; element q of the group keeps its
+// value iff the q-th 16-bit field of the hash is >= p * 65536.  Forward and backward kernels all go through
+// dropout_keep4(seed, group index), so they agree on the mask without storing it.
+__device__ __forceinline__ unsigned long long hash64(unsigned long long seed, unsigned long long idx) {
     unsigned long long x = seed + idx * 0x9E3779B97F4A7C15ull;
     x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
     x ^= x >> 27; x *= 0x94D049BB133111EBull;
     x ^= x >> 31;
-    return (float)(x >> 40) * (1.0f / 16777216.0f);
+    return x;
+}
+struct Keep4 { bool k[4]; };
+__device__ __forceinline__ Keep4 dropout_keep4(unsigned long long seed, unsigned long long group, float p) {
+    const unsigned long long x = hash64(seed, group);
+    const unsigned thr = (unsigned)(p * 65536.0f);
+    Keep4 r;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r.k[q] = (unsigned)((x >> (16 * q)) & 0xFFFFu) >= thr;
+    return r;
 }
 __host__ __device__ inline unsigned long long block_seed(unsigned long long seed, int block) {
     return seed * 0x2545F4914F6CDD1Dull + (unsigned long long)(block + 1) * 0xD6E8FEB86659FD93ull;
@@ -240,11 +252,11 @@ bn_relu_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ s
             m.w = fmaxf(m.w, fmaf(v.w, sc.w, sh.w));
         }
         if (g.drop_p > 0.0f) {
-            const unsigned long long e = (unsigned long long)i * 4;
-            m.x = uniform01(g.seed, e + 0) >= g.drop_p ? m.x * keep_scale : 0.0f;
-            m.y = uniform01(g.seed, e + 1) >= g.drop_p ? m.y * keep_scale : 0.0f;
-            m.z = uniform01(g.seed, e + 2) >= g.drop_p ? m.z * keep_scale : 0.0f;
-            m.w = uniform01(g.seed, e + 3) >= g.drop_p ? m.w * keep_scale : 0.0f;
+            const Keep4 kp = dropout_keep4(g.seed, (unsigned long long)i, g.drop_p);
+            m.x = kp.k[0] ? m.x * keep_scale : 0.0f;
+            m.y = kp.k[1] ? m.y * keep_scale : 0.0f;
+            m.z = kp.k[2] ? m.z * keep_scale : 0.0f;
+            m.w = kp.k[3] ? m.w * keep_scale : 0.0f;
         }
         if (out_hi) store_planes4(out_hi, out_lo, i, m);        // channels-last planes: element index == 4*i
         if (out) {
@@ -288,11 +300,11 @@ bn_relu_pool_fwd_t_kernel(const float* __restrict__ y, const float* __restrict__
         }
         const long i = (long)pix * C4 + c4;                        // same element numbering as the generic kernel
         if (g.drop_p > 0.0f) {
-            const unsigned long long e = (unsigned long long)i * 4;
-            m.x = uniform01(g.seed, e + 0) >= g.drop_p ? m.x * keep_scale : 0.0f;
-            m.y = uniform01(g.seed, e + 1) >= g.drop_p ? m.y * keep_scale : 0.0f;
-            m.z = uniform01(g.seed, e + 2) >= g.drop_p ? m.z * keep_scale : 0.0f;
-            m.w = uniform01(g.seed, e + 3) >= g.drop_p ? m.w * keep_scale : 0.0f;
+            const Keep4 kp = dropout_keep4(g.seed, (unsigned long long)i, g.drop_p);
+            m.x = kp.k[0] ? m.x * keep_scale : 0.0f;
+            m.y = kp.k[1] ? m.y * keep_scale : 0.0f;
+            m.z = kp.k[2] ? m.z * keep_scale : 0.0f;
+            m.w = kp.k[3] ? m.w * keep_scale : 0.0f;
         }
         if (out_hi) store_planes4(out_hi, out_lo, i, m);
         if (out) {
@@ -327,11 +339,12 @@ __device__ __forceinline__ WindowGrad window_grad(const float* __restrict__ src,
         }
     }
     const float keep_scale = g.drop_p > 0.0f ? 1.0f / (1.0f - g.drop_p) : 1.0f;
+    Keep4 kp;
+    if (g.drop_p > 0.0f) kp = dropout_keep4(g.seed, (unsigned long long)i, g.drop_p);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         float gq = __ldg(dA + q * g.oC);
-        if (g.drop_p > 0.0f)
-            gq = uniform01(g.seed, (unsigned long long)i * 4 + q) >= g.drop_p ? gq * keep_scale : 0.0f;
+        if (g.drop_p > 0.0f) gq = kp.k[q] ? gq * keep_scale : 0.0f;
         r.dz[q] = best[q] > 0.0f ? gq : 0.0f;                       // ReLU gate
     }
     return r;
@@ -371,10 +384,12 @@ __device__ __forceinline__ void eval_window(const float4 (&v)[P], const float (&
         }
     }
     const float keep_scale = g.drop_p > 0.0f ? 1.0f / (1.0f - g.drop_p) : 1.0f;
+    Keep4 kp;
+    if (g.drop_p > 0.0f) kp = dropout_keep4(g.seed, (unsigned long long)i, g.drop_p);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         float t = gq[q];
-        if (g.drop_p > 0.0f) t = uniform01(g.seed, (unsigned long long)i * 4 + q) >= g.drop_p ? t * keep_scale : 0.0f;
+        if (g.drop_p > 0.0f) t = kp.k[q] ? t * keep_scale : 0.0f;
         dz[q] = best[q] > 0.0f ? t : 0.0f;
     }
 }
@@ -408,6 +423,73 @@ bn_pool_bwd_sums_t_kernel(const float* __restrict__ y, const float* __restrict__
         for (int q = 0; q < 4; ++q) {
             a[q] += dz[q];
             bsum[q] = fmaf(dz[q], (yarg[q] - muv[q]) * isv[q], bsum[q]);
+        }
+    }
+    s1[threadIdx.x] = make_float4(a[0], a[1], a[2], a[3]);
+    s2[threadIdx.x] = make_float4(bsum[0], bsum[1], bsum[2], bsum[3]);
+    __syncthreads();
+    if (prow == 0) {
+        float4 ta = make_float4(0, 0, 0, 0), tb = make_float4(0, 0, 0, 0);
+        for (int r = 0; r < rows; ++r) {
+            const float4 u = s1[r * C4 + c4], w = s2[r * C4 + c4];
+            ta.x += u.x; ta.y += u.y; ta.z += u.z; ta.w += u.w;
+            tb.x += w.x; tb.y += w.y; tb.z += w.z; tb.w += w.w;
+        }
+        *reinterpret_cast<float4*>(part + ((long)blockIdx.x * 2 + 0) * g.C + c) = ta;
+        *reinterpret_cast<float4*>(part + ((long)blockIdx.x * 2 + 1) * g.C + c) = tb;
+    }
+}
+
+// pass 1 from the block OUTPUT instead of the conv output: the saved activation a = dropout(relu(max_window(bn(y))))
+// already says everything the two sums need -- a > 0 <=> the window's winner passed the ReLU and was kept by the
+// dropout, in which case dz = dA * keep_scale and xhat(winner) = (a / keep_scale - beta) / gamma.  Reads
+// |a| + |dA| (1/p-th of the conv output each) instead of the whole conv output, and needs neither the window
+// search nor the dropout generator.  `act` (fp32, block-output strides) or its bf16 hi/lo planes (channels-last).
+__global__ void __launch_bounds__(256)
+bn_bwd_sums_act_kernel(const float* __restrict__ act, const __nv_bfloat16* __restrict__ act_hi,
+                       const __nv_bfloat16* __restrict__ act_lo, const float* __restrict__ stat,
+                       const float* __restrict__ dA, unsigned n_pix, PoolGeom g, float* __restrict__ part) {
+    __shared__ float4 s1[256], s2[256];
+    const int C4 = g.C >> 2, rows = 256 / C4;
+    const int c4 = threadIdx.x % C4, prow = threadIdx.x / C4, c = c4 * 4;
+    const float4 sc = *reinterpret_cast<const float4*>(stat + 2 * g.C + c);
+    const float4 sh = *reinterpret_cast<const float4*>(stat + 3 * g.C + c);
+    const float4 mu = *reinterpret_cast<const float4*>(stat + c);
+    const float4 is = *reinterpret_cast<const float4*>(stat + g.C + c);
+    // xhat = (z - sh) * (invstd / sc) - mean * invstd   (z = sc * y + sh);  sc == 0 (gamma == 0) carries no information
+    const float shv[4] = {sh.x, sh.y, sh.z, sh.w};
+    const float rs[4] = {sc.x != 0.f ? is.x / sc.x : 0.f, sc.y != 0.f ? is.y / sc.y : 0.f,
+                         sc.z != 0.f ? is.z / sc.z : 0.f, sc.w != 0.f ? is.w / sc.w : 0.f};
+    const float mis[4] = {mu.x * is.x, mu.y * is.y, mu.z * is.z, mu.w * is.w};
+    const float keep_scale = g.drop_p > 0.0f ? 1.0f / (1.0f - g.drop_p) : 1.0f;
+    const float inv_keep = g.drop_p > 0.0f ? 1.0f - g.drop_p : 1.0f;
+    const unsigned Wo = (unsigned)g.Wo, H = (unsigned)g.H;
+    float a[4] = {0, 0, 0, 0}, bsum[4] = {0, 0, 0, 0};
+    for (unsigned pix = blockIdx.x * rows + prow; pix < n_pix; pix += gridDim.x * rows) {
+        const unsigned t = pix / Wo, wo = pix - t * Wo;
+        const unsigned b = t / H, h = t - b * H;
+        const long off = (long)b * g.oB + (long)h * g.oH + (long)wo * g.oW + (long)c * g.oC;
+        float av[4], gq[4];
+        if (act) {
+            load_dA(act + off, g.oC, av);
+        } else {
+            const long i4 = (long)pix * C4 + c4;
+            const uint2 hb = __ldg(reinterpret_cast<const uint2*>(act_hi) + i4);
+            const uint2 lb = __ldg(reinterpret_cast<const uint2*>(act_lo) + i4);
+            const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(&hb);
+            const __nv_bfloat16* lp = reinterpret_cast<const __nv_bfloat16*>(&lb);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) av[q] = __bfloat162float(hp[q]) + __bfloat162float(lp[q]);
+        }
+        load_dA(dA + off, g.oC, gq);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (av[q] > 0.0f) {
+                const float dz = gq[q] * keep_scale;
+                const float xh = fmaf(av[q] * inv_keep - shv[q], rs[q], -mis[q]);
+                a[q] += dz;
+                bsum[q] = fmaf(dz, xh, bsum[q]);
+            }
         }
     }
     s1[threadIdx.x] = make_float4(a[0], a[1], a[2], a[3]);
@@ -1265,7 +1347,15 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         const int nblk = (int)std::min<long>((n_pix_out + rows - 1) / rows, 148L * 16);
 { char _nm[40]; snprintf(_nm, sizeof _nm, "pool%d.bwd_sums", i); SED_PROF(_nm, st);
         const bool idx32 = n_pix_out < (1L << 31);
-        if (g.p == 5 && idx32) bn_pool_bwd_sums_t_kernel<5><<<nblk, 256, 0, st>>>(y, stat, dA, n_pix_out, g, part);
+        const bool planes_out = (i + 1 < P.n_conv) && P.conv_tc_all[i + 1];      // what the forward pass stored
+        if (idx32 && 256 % (P.C / 4) == 0) {
+            const char* ap = reinterpret_cast<const char*>(ws) + P.actp[i];
+            bn_bwd_sums_act_kernel<<<nblk, 256, 0, st>>>(
+                planes_out ? nullptr : wsf(ws, P.act[i]),
+                planes_out ? reinterpret_cast<const __nv_bfloat16*>(ap) : nullptr,
+                planes_out ? reinterpret_cast<const __nv_bfloat16*>(ap + P.act_plane_bytes[i]) : nullptr, stat, dA,
+                (unsigned)n_pix_out, g, part);
+        } else if (g.p == 5 && idx32) bn_pool_bwd_sums_t_kernel<5><<<nblk, 256, 0, st>>>(y, stat, dA, n_pix_out, g, part);
         else if (g.p == 2 && idx32) bn_pool_bwd_sums_t_kernel<2><<<nblk, 256, 0, st>>>(y, stat, dA, n_pix_out, g, part);
         else bn_pool_bwd_sums_kernel<<<nblk, 256, 0, st>>>(y, stat, dA, n_pix_out, g, part);
         SED_POST_LAUNCH();
