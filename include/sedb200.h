@@ -168,8 +168,24 @@ int sedb200_loss_fwd_bwd(int loss_kind, float alpha, float gamma, const float* l
                          void* stream);
 size_t sedb200_loss_scratch_bytes(long n);
 
+/* Fused per-frame head (crnn_lightning.py:63-64,72-73 + the loss): for models with exactly two dense layers
+ * (sedb200_crnn_head_supported != 0), ONE kernel computes relu(d1) -> d2 -> sigmoid -> loss from the GRU output saved
+ * in ws_dev and the whole backward of that head.  Call order for a training step:
+ *   sedb200_crnn_forward(..., logits_dev = NULL)       conv blocks + GRU stack only
+ *   sedb200_crnn_head_fwd_bwd(...)                      zero-fills grads_dev, writes the dense gradients, loss_dev[0],
+ *                                                       probs_dev / logits_dev (optional), d(GRU output) into ws_dev
+ *   sedb200_crnn_backward(..., dlogits_dev = NULL)      GRU stack + conv blocks
+ * Same arithmetic as forward + sedb200_loss_fwd_bwd + backward (summation order of the loss / weight-gradient
+ * partials differs). */
+int sedb200_crnn_head_supported(const sedb200_crnn_desc* d);
+int sedb200_crnn_head_fwd_bwd(const sedb200_crnn_desc* d, const float* params_dev, int batch, void* ws_dev,
+                              size_t ws_bytes, const float* targets_dev, int loss_kind, float alpha, float gamma,
+                              float grad_scale, float* logits_dev, float* probs_dev, float* loss_dev,
+                              float* grads_dev, void* stream);
+
 /* Backward of the last training forward held in ws_dev: grads_dev (same layout as params) is
- * OVERWRITTEN with d(loss)/d(params); dx_dev (optional, [B][in_ch][H][W]) receives d(loss)/d(x). */
+ * OVERWRITTEN with d(loss)/d(params); dx_dev (optional, [B][in_ch][H][W]) receives d(loss)/d(x).
+ * dlogits_dev == NULL: continue after sedb200_crnn_head_fwd_bwd (see above). */
 int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params_dev, const float* x_dev,
                           int batch, unsigned long long seed, void* ws_dev, size_t ws_bytes,
                           const float* dlogits_dev, float* grads_dev, float* dx_dev, void* stream);

@@ -49,6 +49,8 @@ SIGNATURES = {
     "sedb200_crnn_forward": (_i, [_p, _p, _p, _p, _i, _i, C.c_ulonglong, _p, _sz, _p, _p]),
     "sedb200_loss_fwd_bwd": (_i, [_i, _f, _f, _p, _p, _l, _f, _p, _p, _p, _p, _sz, _p]),
     "sedb200_loss_scratch_bytes": (_sz, [_l]),
+    "sedb200_crnn_head_supported": (_i, [_p]),
+    "sedb200_crnn_head_fwd_bwd": (_i, [_p, _p, _i, _p, _sz, _p, _i, _f, _f, _f, _p, _p, _p, _p, _p]),
     "sedb200_crnn_backward": (_i, [_p, _p, _p, _i, C.c_ulonglong, _p, _sz, _p, _p, _p, _p]),
     "sedb200_clip_adam_scratch_bytes": (_sz, [_l]),
     "sedb200_clip_adam": (_i, [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _l, _f, _f, _p, _p, _sz, _p]),

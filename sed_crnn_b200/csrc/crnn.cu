@@ -1106,7 +1106,7 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
     int rc = make_plan(d, batch, &P);
     if (rc) return rc;
     SED_REQUIRE(batch >= 1, SEDB200_EINVAL, "crnn_forward: batch %d", batch);
-    SED_REQUIRE(params && bn_state && x && ws && logits, SEDB200_EINVAL, "crnn_forward: null buffer");
+    SED_REQUIRE(params && bn_state && x && ws, SEDB200_EINVAL, "crnn_forward: null buffer");
     SED_REQUIRE(ws_bytes >= P.ws_bytes, SEDB200_EWORKSPACE, "crnn_forward: workspace %zu < %zu bytes", ws_bytes, P.ws_bytes);
     rc = require_sm100();
     if (rc) return rc;
@@ -1222,8 +1222,8 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
         seq = wsf(ws, P.gout[l]);
     }
 
-    // ---- per-frame dense head
-    for (int j = 0; j < P.n_dense; ++j) {
+    // ---- per-frame dense head (skipped when the caller runs the fused head, sedb200_crnn_head_fwd_bwd)
+    for (int j = 0; logits && j < P.n_dense; ++j) {
         const bool last = (j == P.n_dense - 1);
         float* out = last ? logits : wsf(ws, P.hid[j]);
 { char _nm[40]; snprintf(_nm, sizeof _nm, "dense%d.fwd", j); SED_PROF(_nm, st);
@@ -1236,6 +1236,30 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
     return SEDB200_OK;
 }
 
+int sedb200_crnn_head_supported(const sedb200_crnn_desc* d) {
+    Plan P;
+    if (make_plan(d, 0, &P)) return 0;
+    return head_fused_supported(P) ? 1 : 0;
+}
+
+int sedb200_crnn_head_fwd_bwd(const sedb200_crnn_desc* d, const float* params, int batch, void* ws, size_t ws_bytes,
+                              const float* targets, int loss_kind, float alpha, float gamma, float grad_scale,
+                              float* logits, float* probs, float* loss, float* grads, void* stream) {
+    Plan P;
+    int rc = make_plan(d, batch, &P);
+    if (rc) return rc;
+    SED_REQUIRE(batch >= 1 && params && ws && targets && loss && grads, SEDB200_EINVAL, "crnn_head_fwd_bwd: bad argument");
+    SED_REQUIRE(loss_kind == SEDB200_LOSS_BCE || loss_kind == SEDB200_LOSS_FOCAL, SEDB200_EINVAL, "crnn_head_fwd_bwd: loss kind %d", loss_kind);
+    SED_REQUIRE(ws_bytes >= P.ws_bytes, SEDB200_EWORKSPACE, "crnn_head_fwd_bwd: workspace %zu < %zu bytes", ws_bytes, P.ws_bytes);
+    SED_REQUIRE(head_fused_supported(P), SEDB200_ESHAPE, "crnn_head_fwd_bwd: needs exactly two small dense layers");
+    rc = require_sm100();
+    if (rc) return rc;
+    cudaStream_t st = as_stream(stream);
+    SED_CUDA_OK(cudaMemsetAsync(grads, 0, (size_t)P.n_params * 4, st));
+    return head_fused_run(P, d, params, batch, wsf(ws, P.gout[P.n_gru - 1]), targets, loss_kind, alpha, gamma, grad_scale,
+                          logits, probs, loss, wsf(ws, P.dseq[0]), grads, wsf(ws, P.part), st);
+}
+
 int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const float* x, int batch,
                           unsigned long long seed, void* ws, size_t ws_bytes, const float* dlogits,
                           float* grads, float* dx, void* stream) {
@@ -1243,7 +1267,7 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
     int rc = make_plan(d, batch, &P);
     if (rc) return rc;
     SED_REQUIRE(batch >= 1, SEDB200_EINVAL, "crnn_backward: batch %d", batch);
-    SED_REQUIRE(params && x && ws && dlogits && grads, SEDB200_EINVAL, "crnn_backward: null buffer");
+    SED_REQUIRE(params && x && ws && grads, SEDB200_EINVAL, "crnn_backward: null buffer");
     SED_REQUIRE(ws_bytes >= P.ws_bytes, SEDB200_EWORKSPACE, "crnn_backward: workspace %zu < %zu bytes", ws_bytes, P.ws_bytes);
     rc = require_sm100();
     if (rc) return rc;
@@ -1253,12 +1277,13 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
     float* part = wsf(ws, P.part);
     const int kSplit = 48;
 
-    // zero the alignment padding of the gradient buffer once (tensors themselves are fully overwritten)
-    SED_CUDA_OK(cudaMemsetAsync(grads, 0, (size_t)P.n_params * 4, st));
+    // zero the alignment padding of the gradient buffer once (tensors themselves are fully overwritten); with
+    // dlogits == NULL the fused head has done that, written the dense gradients and left d(gru output) in dseq[0]
+    if (dlogits) SED_CUDA_OK(cudaMemsetAsync(grads, 0, (size_t)P.n_params * 4, st));
 
     // ---- dense head
     const float* dout = dlogits;
-    for (int j = P.n_dense - 1; j >= 0; --j) {
+    for (int j = P.n_dense - 1; dlogits && j >= 0; --j) {
         char _nm[40]; snprintf(_nm, sizeof _nm, "dense%d.bwd", j); SED_PROF(_nm, st);
         const float* in = j == 0 ? wsf(ws, P.gout[P.n_gru - 1]) : wsf(ws, P.hid[j - 1]);
         const int N = P.dout[j], D = P.din[j];

@@ -37,6 +37,13 @@ struct Plan {
     size_t ws_bytes = 0;
 };
 
+// Fused dense head (head_fused.cu): d1 -> relu -> d2 -> sigmoid -> loss and the whole backward of it in one kernel.
+bool   head_fused_supported(const Plan& P);
+size_t head_fused_part_floats(const Plan& P, int batch);
+int    head_fused_run(const Plan& P, const sedb200_crnn_desc* d, const float* params, int batch, const float* x,
+                      const float* targets, int loss_kind, float alpha, float gamma, float grad_scale, float* logits,
+                      float* probs, float* loss, float* dx, float* grads, float* part, cudaStream_t st);
+
 // Fills `p` from `d` (and the workspace part when batch > 0).  Returns SEDB200_OK or an error code.
 int make_plan(const sedb200_crnn_desc* d, int batch, Plan* p);
 

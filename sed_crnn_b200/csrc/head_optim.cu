@@ -8,6 +8,7 @@
 //   Adam(lr, wd)            crnn_lightning.py:195-197, sed.py:159 (coupled L2: g += wd * p)
 //   threshold + metrics     crnn_lightning.py:112-126, metrics.py:20-68
 #include "common.cuh"
+#include "loss_math.cuh"
 #include <algorithm>
 #include <cmath>
 
@@ -35,23 +36,8 @@ loss_kernel(int kind, float alpha, float gamma, const float* __restrict__ logits
     const float inv_n = 1.0f / (float)n;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
         const float l = __ldg(logits + i), t = __ldg(targets + i);
-        const float p = 1.0f / (1.0f + expf(-l));
-        float loss, dl;
-        if (kind == SEDB200_LOSS_FOCAL) {
-            const bool pos = (t == 1.0f);
-            const float pt = pos ? p : 1.0f - p;
-            const float om = 1.0f - pt;
-            const float lg = logf(pt + 1e-12f);
-            const float pw = powf(om, gamma);
-            loss = -alpha * pw * lg;
-            // d loss / d pt = alpha * gamma * om^(gamma-1) * lg - alpha * om^gamma / (pt + eps)
-            const float pw1 = (gamma == 2.0f) ? om : powf(om, gamma - 1.0f);
-            const float dpt = alpha * gamma * pw1 * lg - alpha * pw / (pt + 1e-12f);
-            dl = dpt * (pos ? 1.0f : -1.0f) * p * (1.0f - p);
-        } else {
-            loss = fmaxf(l, 0.0f) - l * t + log1pf(expf(-fabsf(l)));
-            dl = p - t;
-        }
+        float p, loss, dl;
+        loss_elem(kind, alpha, gamma, l, t, p, loss, dl);
         acc += loss;
         if (probs) probs[i] = p;
         if (dlogits) dlogits[i] = dl * inv_n * gscale;

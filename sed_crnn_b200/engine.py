@@ -59,6 +59,8 @@ class CRNNEngine:
         # "nccl": dist.all_reduce + clip_adam kernels;  "p2p": one fused kernel over NVLink peer memory
         if grad_exchange not in ("nccl", "p2p"):
             raise ValueError("grad_exchange must be 'nccl' or 'p2p'")
+        # two-layer dense heads run as one fused forward + loss + backward kernel inside train_step
+        self.fused_head = bool(self.L.sedb200_crnn_head_supported(C.byref(self.desc)))
         self.xch = None
         if grad_exchange == "p2p":
             from . import parallel
@@ -152,18 +154,19 @@ class CRNNEngine:
 
     # ------------------------------------------------------------------ compute
     def forward(self, x: torch.Tensor, training: bool = False, logits: torch.Tensor | None = None,
-                seed: int | None = None) -> torch.Tensor:
+                seed: int | None = None, skip_head: bool = False) -> torch.Tensor:
+        """`skip_head`: stop after the GRU stack (the fused head kernel takes over); returns None."""
         x = self._check_x(x)
         self._last_seed = self.seed + self.step_count if seed is None else int(seed)
         B = x.shape[0]
         ws = self._workspace(B)
-        if logits is None:
+        if logits is None and not skip_head:
             logits = self._buf(("logits", B), self.cfg.target_shape(B))
         with torch.cuda.device(self.device):
             _lib.check(self.L.sedb200_crnn_forward(
                 C.byref(self.desc), self.params.data_ptr(), self.bn_state.data_ptr(), x.data_ptr(), B,
-                int(training), self._last_seed, ws.data_ptr(), ws.numel(), logits.data_ptr(),
-                _lib.current_stream_ptr()))
+                int(training), self._last_seed, ws.data_ptr(), ws.numel(),
+                None if skip_head else logits.data_ptr(), _lib.current_stream_ptr()))
         if training:
             self.num_batches_tracked += 1
         return logits
@@ -183,14 +186,31 @@ class CRNNEngine:
                 self._scratch.data_ptr(), self._scratch.numel() * 4, _lib.current_stream_ptr()))
         return self._scalars[0], probs, dlog
 
+    def head_forward_backward(self, batch: int, targets: torch.Tensor):
+        """Fused dense head: logits, probabilities, loss and the head's whole backward in one kernel (needs a
+        preceding `forward(..., skip_head=True)`; `backward(x, None)` continues).  -> (loss, probs, logits)"""
+        shape = self.cfg.target_shape(batch)
+        targets = targets.contiguous()
+        if tuple(targets.shape) != tuple(shape) or targets.dtype != torch.float32 or not targets.is_cuda:
+            raise ValueError("targets must be CUDA float32 with the logits' shape")
+        logits, probs = self._buf(("logits", batch), shape), self._buf(("probs", tuple(shape)), shape)
+        ws = self._workspace(batch)
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.sedb200_crnn_head_fwd_bwd(
+                C.byref(self.desc), self.params.data_ptr(), batch, ws.data_ptr(), ws.numel(), targets.data_ptr(),
+                self.loss_kind, self.alpha, self.gamma, 1.0, logits.data_ptr(), probs.data_ptr(),
+                self._scalars.data_ptr(), self.grads.data_ptr(), _lib.current_stream_ptr()))
+        return self._scalars[0], probs, logits
+
     def backward(self, x, dlogits, dx: torch.Tensor | None = None) -> torch.Tensor:
+        """`dlogits=None`: continue after `head_forward_backward`."""
         x = self._check_x(x)
         B = x.shape[0]
         ws = self._workspace(B)
         with torch.cuda.device(self.device):
             _lib.check(self.L.sedb200_crnn_backward(
                 C.byref(self.desc), self.params.data_ptr(), x.data_ptr(), B, self._last_seed,
-                ws.data_ptr(), ws.numel(), dlogits.data_ptr(), self.grads.data_ptr(),
+                ws.data_ptr(), ws.numel(), dlogits.data_ptr() if dlogits is not None else None, self.grads.data_ptr(),
                 dx.data_ptr() if dx is not None else None, _lib.current_stream_ptr()))
         return self.grads
 
@@ -208,10 +228,16 @@ class CRNNEngine:
     def train_step(self, x: torch.Tensor, y: torch.Tensor):
         """One optimisation step on device-resident (x, y).  Returns (loss, probs) as device tensors
         (views of engine-owned buffers, valid until the next call)."""
-        logits = self.forward(x, training=True)
-        loss, probs, dlog = self.loss_and_grad(logits, y)
         if self.xch is not None:
             self.grads = self.xch.next_grad_buffer()                  # this step's half of the exchange region
+        if self.fused_head:
+            self.forward(x, training=True, skip_head=True)
+            loss, probs, _ = self.head_forward_backward(x.shape[0], y)
+            dlog = None
+        else:
+            logits = self.forward(x, training=True)
+            loss, probs, dlog = self.loss_and_grad(logits, y)
+        if self.xch is not None:
             self.backward(x, dlog)
             self.step_count += 1
             self.grads = self.xch.allreduce_clip_adam(

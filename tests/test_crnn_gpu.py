@@ -286,3 +286,35 @@ def test_full_size_c2_properties(pkg):
     from sed_crnn_b200 import metrics as PM
     got = PM.scores_from_counts(c)
     assert got[2] == M.f1_overall_1sec(O, y.cpu().numpy(), 43) and got[3] == M.er_overall_1sec(O, y.cpu().numpy(), 43)
+
+
+@pytest.mark.parametrize("preset,loss", [("c2", "bce"), ("fork", "focal"), ("c1", "focal")])
+def test_fused_head_matches_unfused_path(pkg, preset, loss):
+    """train_step's fused dense head (one kernel: d1 -> relu -> d2 -> sigmoid -> loss -> backward) against the same
+    step run through forward + sedb200_loss_fwd_bwd + backward (eight launches for the head)."""
+    config, engine = pkg
+    cfg = replace(config.PRESETS[preset], dropout=0.0, **({"seq_len": 32} if preset != "fork" else {}))
+    a = engine.CRNNEngine(cfg, loss=loss, weight_decay=1e-4, clip=1.0)
+    b = engine.CRNNEngine(cfg, loss=loss, weight_decay=1e-4, clip=1.0)
+    assert b.fused_head
+    a.init_default(11)
+    b.init_default(11)
+    a.fused_head = False
+    g = torch.Generator(device="cuda").manual_seed(2)
+    B = 5                                                  # rows = 5 * T: not a multiple of the 128-row block
+    for it in range(2):
+        x = torch.randn(cfg.input_shape(B), device="cuda", generator=g)
+        y = (torch.rand(cfg.target_shape(B), device="cuda", generator=g) < 0.3).float()
+        la, pa = a.train_step(x, y)
+        lb, pb = b.train_step(x, y)
+        assert abs(la.item() - lb.item()) <= 1e-6 * max(1.0, abs(la.item()))
+        assert torch.allclose(pa, pb, rtol=0, atol=2e-6)
+        scale = a.grads.abs().max().item()
+        # first step: identical weights, only summation orders differ.  Second step: the weights already differ
+        # where Adam amplified gradient noise (see below), which the 3-term tensor-core convs echo at ~1e-5
+        assert (a.grads - b.grads).abs().max().item() <= (5e-6 if it == 0 else 2e-4) * scale
+        # Adam turns a gradient that is pure rounding noise (conv biases under BatchNorm) into +-lr: compare the
+        # weights only where the gradient is above the noise
+        if it == 0:
+            solid = a.grads.abs() > 1e-3 * scale
+            assert torch.allclose(a.params[solid], b.params[solid], rtol=0, atol=2e-5)
