@@ -494,14 +494,28 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
-    if world != args.gpus and world == 1 and args.gpus > 1:
+    if args.impl != "reference" and world != args.gpus and world == 1 and args.gpus > 1:
         # launched without torchrun: re-exec under it
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), __file__] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    # stdout carries exactly ONE line, the JSON result: anything a library prints there (NCCL's version banner, a
+    # stray warning) is sent to stderr by pointing fd 1 at fd 2 for the whole run; the result goes to the saved fd
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global print
+    _print = print
+
+    def print(*a, **k):                                    # noqa: A001 -- every result line of this file
+        if k.get("file") not in (None, sys.stdout):
+            return _print(*a, **k)
+        sys.stdout.flush()
+        os.write(real_stdout, (" ".join(str(x) for x in a) + "\n").encode())
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
     run_ours(args, rank, world, local_rank)
 
 
