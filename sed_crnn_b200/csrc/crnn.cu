@@ -1225,8 +1225,10 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
         if (rc) return rc;
 }
 { char _nm[40]; snprintf(_nm, sizeof _nm, "gru%d.scan_fwd", l); SED_PROF(_nm, st);
+        char* hpl = reinterpret_cast<char*>(ws) + P.hpp[l];
         rc = gru_scan_forward(gi, params + P.whh[l], params + P.bhh[l], wsf(ws, P.gout[l]), wsf(ws, P.gates[l]),
-                              batch, P.T, h, st);
+                              batch, P.T, h, st, (training && P.gru_planes[l]) ? hpl : nullptr,
+                              (training && P.gru_planes[l]) ? hpl + P.hp_plane_bytes[l] : nullptr);
         if (rc) return rc;
 }
         seq = wsf(ws, P.gout[l]);
@@ -1341,9 +1343,11 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         const bool fusedg = gru_scan_fused_param_grads(h);
         float* part_w = part;                                      // [B][2][3h][h]
         float* part_b = part + (size_t)B * 6 * h * h;              // [B][2][2][3h]
+        char* dgpl = reinterpret_cast<char*>(ws) + P.dgp;       // {dgi_hi, dgi_lo, dgh_hi, dgh_lo} when the scan emits planes
+        void* planes[4] = {dgpl, dgpl + P.dg_plane_bytes, dgpl + 2 * P.dg_plane_bytes, dgpl + 3 * P.dg_plane_bytes};
 { char _nm[40]; snprintf(_nm, sizeof _nm, "gru%d.scan_bwd", l); SED_PROF(_nm, st);
         rc = gru_scan_backward(wsf(ws, P.dseq[cur]), wsf(ws, P.gout[l]), wsf(ws, P.gates[l]), params + P.whh[l],
-                               dgi, dgh, part_w, part_b, batch, P.T, h, st);
+                               dgi, dgh, part_w, part_b, batch, P.T, h, st, P.gru_planes[l] ? planes : nullptr);
         if (rc) return rc;
 }
         char _nm2[40]; snprintf(_nm2, sizeof _nm2, "gru%d.bwd_gemms", l); SED_PROF(_nm2, st);
@@ -1365,11 +1369,17 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
             char* hp = gp + 2 * gpb;
             float* tmp = reinterpret_cast<float*>(hp + 2 * hpb);
             float* tpart = tmp + 12 * h * h + 64;
-            rc = split_planes(dgh, gp, gp + gpb, (long)BT * 6 * h, st);
-            if (rc) return rc;
-            rc = hprev_planes(wsf(ws, P.gout[l]), hp, hp + hpb, BT, P.T, h, st);
-            if (rc) return rc;
-            rc = gemm_tc(gp, gp + gpb, 1, hp, hp + hpb, 1, 6 * h, 2 * h, BT, nullptr, tmp, 2 * h, 1, tpart, st);
+            const char *gh_hi = gp, *gh_lo = gp + gpb, *hp_hi = hp, *hp_lo = hp + hpb;
+            if (P.gru_planes[l]) {                          // both operands were written by the scans themselves
+                gh_hi = dgpl + 2 * P.dg_plane_bytes; gh_lo = dgpl + 3 * P.dg_plane_bytes;
+                hp_hi = reinterpret_cast<char*>(ws) + P.hpp[l]; hp_lo = hp_hi + P.hp_plane_bytes[l];
+            } else {
+                rc = split_planes(dgh, gp, gp + gpb, (long)BT * 6 * h, st);
+                if (rc) return rc;
+                rc = hprev_planes(wsf(ws, P.gout[l]), hp, hp + hpb, BT, P.T, h, st);
+                if (rc) return rc;
+            }
+            rc = gemm_tc(gh_hi, gh_lo, 1, hp_hi, hp_lo, 1, 6 * h, 2 * h, BT, nullptr, tmp, 2 * h, 1, tpart, st);
             if (rc) return rc;
             extract_whh_kernel<<<(6 * h * h + 255) / 256, 256, 0, st>>>(tmp, h, grads + P.whh[l]);
             SED_POST_LAUNCH();
@@ -1391,15 +1401,20 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
             char* gp = reinterpret_cast<char*>(ws) + P.tc;
             char* wp = gp + 2 * gpb;
             float* tpart = reinterpret_cast<float*>(wp + 2 * wpb);
-            rc = split_planes(dgi, gp, gp + gpb, (long)BT * 6 * h, st);
-            if (rc) return rc;
+            const char *gi_hi = gp, *gi_lo = gp + gpb;
+            if (P.gru_planes[l]) {
+                gi_hi = dgpl; gi_lo = dgpl + P.dg_plane_bytes;
+            } else {
+                rc = split_planes(dgi, gp, gp + gpb, (long)BT * 6 * h, st);
+                if (rc) return rc;
+            }
             rc = split_planes(params + P.wih[l], wp, wp + wpb, 6L * h * in, st);
             if (rc) return rc;
             // dW_ih[n6][k] = sum_m dgi[m][n6] * xin[m][k]        (both operands stored [B*T][.]: MN-major)
-            rc = gemm_tc(gp, gp + gpb, 1, xp, xp + xpb, 1, 6 * h, in, BT, nullptr, grads + P.wih[l], in, 1, tpart, st);
+            rc = gemm_tc(gi_hi, gi_lo, 1, xp, xp + xpb, 1, 6 * h, in, BT, nullptr, grads + P.wih[l], in, 1, tpart, st);
             if (rc) return rc;
             // d(xin)[m][k] = sum_n6 dgi[m][n6] * W_ih[n6][k]    (W_ih stored [n6][k] = [K][N]: MN-major)
-            rc = gemm_tc(gp, gp + gpb, 0, wp, wp + wpb, 1, BT, in, 6 * h, nullptr, dxin, in, 0, nullptr, st);
+            rc = gemm_tc(gi_hi, gi_lo, 0, wp, wp + wpb, 1, BT, in, 6 * h, nullptr, dxin, in, 0, nullptr, st);
             if (rc) return rc;
         } else {
         // dW_ih[n6][k] = sum_m dgi[m][n6] * xin[m][k]

@@ -1,5 +1,6 @@
 // crnn_plan.cu -- host-side geometry / layout helpers of the CRNN C ABI (no GPU needed).
 #include "crnn_plan.cuh"
+#include "gru_scan.cuh"
 #include "gemm_simt.cuh"
 #include "tc_conv.cuh"
 #include "tc_gemm.cuh"
@@ -179,6 +180,17 @@ int make_plan(const sedb200_crnn_desc* d, int batch, Plan* p) {
         tc = std::max(tc, 2 * plane(BT * h6) + 2 * plane((long)h6 * in) + (size_t)sm_count() * h6 * in * 4 + 4096);
         tc = std::max(tc, 2 * plane(BT * h6) + 2 * plane(BT * 2L * P.gh[l]) + ((size_t)sm_count() + 1) * h6 * 2 * P.gh[l] * 4 + 8192);
     }
+    P.dg_plane_bytes = 0;
+    for (int l = 0; l < P.n_gru; ++l) {
+        P.gru_planes[l] = P.gru_tc[l] && gru_scan_emits_planes(P.gh[l]) && gemm_tc_supported(6 * P.gh[l], 2 * P.gh[l], (int)BT);
+        P.hpp[l] = 0;
+        P.hp_plane_bytes[l] = 0;
+        if (!P.gru_planes[l]) continue;
+        P.hp_plane_bytes[l] = plane(BT * 2L * P.gh[l]);
+        P.hpp[l] = take((long)(2 * P.hp_plane_bytes[l] / 4));
+        P.dg_plane_bytes = std::max(P.dg_plane_bytes, plane(BT * 6L * P.gh[l]));
+    }
+    P.dgp = P.dg_plane_bytes ? take((long)(4 * P.dg_plane_bytes / 4)) : 0;
     P.tc_bytes = tc;
     P.tc = take((long)(tc / 4) + 64);
     P.ws_bytes = o;

@@ -24,6 +24,11 @@ struct Plan {
     size_t gi[SEDB200_MAX_GRU], gout[SEDB200_MAX_GRU], gates[SEDB200_MAX_GRU];
     size_t gxp[SEDB200_MAX_GRU];              // bf16 hi/lo planes of each GRU layer's input (tensor-core path)
     bool gru_tc[SEDB200_MAX_GRU];
+    // scans that write their tensor-core operands themselves (H = 32): h_{t-1} planes per layer (forward scan,
+    // kept until the backward pass) and the dgi / dgh planes of the layer being back-propagated
+    bool gru_planes[SEDB200_MAX_GRU];
+    size_t hpp[SEDB200_MAX_GRU], dgp;
+    size_t hp_plane_bytes[SEDB200_MAX_GRU], dg_plane_bytes;
     size_t hid[SEDB200_MAX_DENSE];
     size_t dy, dact[2], dseq[2], dgi, dgh, dhid[2], part, bnsum, tc;
     // plane-native tensor-core flow: block i (>= 1) runs fwd, dgrad and wgrad on tcgen05 and exchanges

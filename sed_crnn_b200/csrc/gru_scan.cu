@@ -9,6 +9,8 @@
 // in shared memory, and gi for step t+1 is prefetched into registers while step t computes.
 #include "gru_scan.cuh"
 
+#include <cuda_bf16.h>
+
 #include <algorithm>
 
 namespace sedb200 {
@@ -323,12 +325,20 @@ gru_scan_bwd_warp_kernel(const float* __restrict__ dout, const float* __restrict
 // so this is what sets the speed of the whole scan.
 constexpr int kChF32 = 8, kChB32 = 6;
 
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): the tensor-core operand format (tc_gemm.cu)
+__device__ __forceinline__ void store_plane(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long i, float x) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+}
+
 // REV is the scan direction as a compile-time constant: every per-step address is then `base + immediate`, and the
 // integer work per step drops to two pointer bumps per chunk.
 template <bool REV>
 __device__ __forceinline__ void gru_fwd_bcast32_body(const float* __restrict__ gi, const float* __restrict__ whh,
                                                      const float* __restrict__ bhh, float* __restrict__ out,
-                                                     float* __restrict__ gates, int T, long b, float (*h_s)[32]) {
+                                                     float* __restrict__ gates, int T, long b, float (*h_s)[32],
+                                                     __nv_bfloat16* __restrict__ hp_hi, __nv_bfloat16* __restrict__ hp_lo) {
     constexpr int H = 32, H3 = 96, dir = REV ? 1 : 0;
     constexpr long sGi = 2 * H3, sOut = 2 * H, sGs = 2 * 4 * H;            // floats per time step
     constexpr long dGi = REV ? -sGi : sGi, dOut = REV ? -sOut : sOut, dGs = REV ? -sGs : sGs;
@@ -346,6 +356,10 @@ __device__ __forceinline__ void gru_fwd_bcast32_body(const float* __restrict__ g
     const float* gp = gi + ((b * T + t0) * 2 + dir) * H3 + j;               // this lane's gi of the current chunk
     float* op = out + (b * T + t0) * sOut + dir * H + j;
     float* sp = gates + ((b * T + t0) * 2 + dir) * 4 * H + j;
+    // h_prev planes: h_t belongs to the row of the step that CONSUMES it (t+1 forward, t-1 reverse); the first
+    // step's own row holds h_0 = 0
+    long hrow = hp_hi ? ((b * T + t0) * 2 * H + dir * H + j) : 0;
+    if (hp_hi) store_plane(hp_hi, hp_lo, hrow, 0.0f);
     float h = 0.0f;
     float cur[kChF32][3], nxt[kChF32][3];
     auto load_chunk = [&](float (&dst)[kChF32][3], const float* g, int step0) {
@@ -391,7 +405,9 @@ __device__ __forceinline__ void gru_fwd_bcast32_body(const float* __restrict__ g
             h = fmaf(z, h - n, n);
             op[s * dOut] = h;
             sp[s * dGs] = r; sp[s * dGs + H] = z; sp[s * dGs + 2 * H] = n; sp[s * dGs + 3 * H] = a2;
+            if (hp_hi && step0 + s + 1 < T) store_plane(hp_hi, hp_lo, hrow + (s + 1) * dOut, h);
         }
+        hrow += kChF32 * dOut;
         op += kChF32 * dOut;
         sp += kChF32 * dGs;
 #pragma unroll
@@ -401,20 +417,23 @@ __device__ __forceinline__ void gru_fwd_bcast32_body(const float* __restrict__ g
 
 __global__ void __launch_bounds__(128)
 gru_scan_fwd_bcast32_kernel(const float* __restrict__ gi, const float* __restrict__ whh, const float* __restrict__ bhh,
-                            float* __restrict__ out, float* __restrict__ gates, int B, int T) {
+                            float* __restrict__ out, float* __restrict__ gates, int B, int T,
+                            __nv_bfloat16* __restrict__ hp_hi, __nv_bfloat16* __restrict__ hp_lo) {
     __shared__ __align__(16) float h_s[2 * 4][32];          // [buffer][warp] rows; a warp uses rows warp and 4 + warp
     const int warp = threadIdx.x >> 5;
     const long b = (long)blockIdx.x * 4 + warp;
     if (b >= B) return;                                     // warps are independent: no block-level barrier below
-    if (blockIdx.y == 0) gru_fwd_bcast32_body<false>(gi, whh, bhh, out, gates, T, b, h_s + warp);
-    else gru_fwd_bcast32_body<true>(gi, whh, bhh, out, gates, T, b, h_s + warp);
+    if (blockIdx.y == 0) gru_fwd_bcast32_body<false>(gi, whh, bhh, out, gates, T, b, h_s + warp, hp_hi, hp_lo);
+    else gru_fwd_bcast32_body<true>(gi, whh, bhh, out, gates, T, b, h_s + warp, hp_hi, hp_lo);
 }
 
 template <bool REV>
 __device__ __forceinline__ void gru_bwd_bcast32_body(const float* __restrict__ dout, const float* __restrict__ out,
                                                      const float* __restrict__ gates, const float* __restrict__ whh,
                                                      float* __restrict__ dgi, float* __restrict__ dgh,
-                                                     float* __restrict__ part_b, int T, long b, float (*dg_s)[96]) {
+                                                     float* __restrict__ part_b, int T, long b, float (*dg_s)[96],
+                                                     __nv_bfloat16* __restrict__ gi_hi, __nv_bfloat16* __restrict__ gi_lo,
+                                                     __nv_bfloat16* __restrict__ gh_hi, __nv_bfloat16* __restrict__ gh_lo) {
     // REV = the FORWARD direction of this GRU half; the backward scan walks time the other way
     constexpr int H = 32, H3 = 96, dir = REV ? 1 : 0;
     constexpr long sOut = 2 * H, sGs = 2 * 4 * H, sDg = 2 * H3;
@@ -430,6 +449,7 @@ __device__ __forceinline__ void gru_bwd_bcast32_body(const float* __restrict__ d
     const float* gsp = gates + ((b * T + t0) * 2 + dir) * 4 * H + j;
     float* gip = dgi + ((b * T + t0) * 2 + dir) * H3 + j;
     float* ghp = dgh + ((b * T + t0) * 2 + dir) * H3 + j;
+    long prow = ((b * T + t0) * 2 + dir) * H3 + j;              // same element index in the bf16 planes
     float sb_r = 0, sb_z = 0, sb_n = 0, sb_q = 0;
     float dh = 0.0f;
     float cur[kChB32][6], nxt[kChB32][6];                       // dout, r, z, n, q, h_prev
@@ -466,8 +486,14 @@ __device__ __forceinline__ void gru_bwd_bcast32_body(const float* __restrict__ d
             float* ds = dg_s[buf * 4];
             ds[j] = dar; ds[H + j] = daz; ds[2 * H + j] = dq;
             __syncwarp();
-            gip[s * dDg] = dar; gip[s * dDg + H] = daz; gip[s * dDg + 2 * H] = dan;
-            ghp[s * dDg] = dar; ghp[s * dDg + H] = daz; ghp[s * dDg + 2 * H] = dq;
+            if (gi_hi) {
+                const long o = prow + s * dDg;
+                store_plane(gi_hi, gi_lo, o, dar); store_plane(gi_hi, gi_lo, o + H, daz); store_plane(gi_hi, gi_lo, o + 2 * H, dan);
+                store_plane(gh_hi, gh_lo, o, dar); store_plane(gh_hi, gh_lo, o + H, daz); store_plane(gh_hi, gh_lo, o + 2 * H, dq);
+            } else {
+                gip[s * dDg] = dar; gip[s * dDg + H] = daz; gip[s * dDg + 2 * H] = dan;
+                ghp[s * dDg] = dar; ghp[s * dDg + H] = daz; ghp[s * dDg + 2 * H] = dq;
+            }
             sb_r += dar; sb_z += daz; sb_n += dan; sb_q += dq;
             const float4* dv4 = reinterpret_cast<const float4*>(ds);
             buf ^= 1;
@@ -482,7 +508,7 @@ __device__ __forceinline__ void gru_bwd_bcast32_body(const float* __restrict__ d
             }
             dh = fmaf(dht, z, ((acc[0].x + acc[0].y) + (acc[1].x + acc[1].y)) + ((acc[2].x + acc[2].y) + (acc[3].x + acc[3].y)));
         }
-        gip += kChB32 * dDg; ghp += kChB32 * dDg;
+        gip += kChB32 * dDg; ghp += kChB32 * dDg; prow += kChB32 * dDg;
 #pragma unroll
         for (int s = 0; s < kChB32; ++s)
 #pragma unroll
@@ -496,13 +522,15 @@ __device__ __forceinline__ void gru_bwd_bcast32_body(const float* __restrict__ d
 __global__ void __launch_bounds__(128)
 gru_scan_bwd_bcast32_kernel(const float* __restrict__ dout, const float* __restrict__ out,
                             const float* __restrict__ gates, const float* __restrict__ whh, float* __restrict__ dgi,
-                            float* __restrict__ dgh, float* __restrict__ part_b, int B, int T) {
+                            float* __restrict__ dgh, float* __restrict__ part_b, int B, int T,
+                            __nv_bfloat16* __restrict__ gi_hi, __nv_bfloat16* __restrict__ gi_lo,
+                            __nv_bfloat16* __restrict__ gh_hi, __nv_bfloat16* __restrict__ gh_lo) {
     __shared__ __align__(16) float dg_s[2 * 4][96];
     const int warp = threadIdx.x >> 5;
     const long b = (long)blockIdx.x * 4 + warp;
     if (b >= B) return;
-    if (blockIdx.y == 0) gru_bwd_bcast32_body<false>(dout, out, gates, whh, dgi, dgh, part_b, T, b, dg_s + warp);
-    else gru_bwd_bcast32_body<true>(dout, out, gates, whh, dgi, dgh, part_b, T, b, dg_s + warp);
+    if (blockIdx.y == 0) gru_bwd_bcast32_body<false>(dout, out, gates, whh, dgi, dgh, part_b, T, b, dg_s + warp, gi_hi, gi_lo, gh_hi, gh_lo);
+    else gru_bwd_bcast32_body<true>(dout, out, gates, whh, dgi, dgh, part_b, T, b, dg_s + warp, gi_hi, gi_lo, gh_hi, gh_lo);
 }
 
 // ------------------------------------------------------------------------------ H = 64 / 128: K-split scans
@@ -691,10 +719,14 @@ inline int round32(int v) { return (v + 31) / 32 * 32; }
 
 }  // namespace
 
+bool gru_scan_emits_planes(int H) { return H == 32; }
+
 int gru_scan_forward(const float* gi, const float* whh, const float* bhh, float* out, float* gates, int B, int T,
-                     int H, cudaStream_t st) {
+                     int H, cudaStream_t st, void* hprev_hi, void* hprev_lo) {
+    SED_REQUIRE(!hprev_hi || gru_scan_emits_planes(H), SEDB200_ESHAPE, "gru_scan: h_prev planes need H = 32 (H = %d)", H);
     if (H == 32) {
-        gru_scan_fwd_bcast32_kernel<<<dim3((B + 3) / 4, 2), 128, 0, st>>>(gi, whh, bhh, out, gates, B, T);
+        gru_scan_fwd_bcast32_kernel<<<dim3((B + 3) / 4, 2), 128, 0, st>>>(
+            gi, whh, bhh, out, gates, B, T, reinterpret_cast<__nv_bfloat16*>(hprev_hi), reinterpret_cast<__nv_bfloat16*>(hprev_lo));
         SED_POST_LAUNCH();
         return SEDB200_OK;
     }
@@ -722,9 +754,14 @@ int gru_scan_forward(const float* gi, const float* whh, const float* bhh, float*
 bool gru_scan_fused_param_grads(int H) { return H == 128 || H == 64 || H == 32 || H == 16 || H == 8; }
 
 int gru_scan_backward(const float* dout, const float* out, const float* gates, const float* whh, float* dgi,
-                      float* dgh, float* part_w, float* part_b, int B, int T, int H, cudaStream_t st) {
+                      float* dgh, float* part_w, float* part_b, int B, int T, int H, cudaStream_t st,
+                      void* const* planes) {
+    SED_REQUIRE(!planes || gru_scan_emits_planes(H), SEDB200_ESHAPE, "gru_scan: gradient planes need H = 32 (H = %d)", H);
     if (H == 32) {
-        gru_scan_bwd_bcast32_kernel<<<dim3((B + 3) / 4, 2), 128, 0, st>>>(dout, out, gates, whh, dgi, dgh, part_b, B, T);
+        __nv_bfloat16* pl[4] = {nullptr, nullptr, nullptr, nullptr};
+        if (planes) for (int i = 0; i < 4; ++i) pl[i] = reinterpret_cast<__nv_bfloat16*>(planes[i]);
+        gru_scan_bwd_bcast32_kernel<<<dim3((B + 3) / 4, 2), 128, 0, st>>>(dout, out, gates, whh, dgi, dgh, part_b, B, T,
+                                                                           pl[0], pl[1], pl[2], pl[3]);
         SED_POST_LAUNCH();
         return SEDB200_OK;
     }
