@@ -332,16 +332,31 @@ __device__ __forceinline__ void store_plane(__nv_bfloat16* __restrict__ hi, __nv
     lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
 }
 
+// Producer / consumer hand-off between a scan warp and its helper warp through hardware named barriers (PTX
+// bar.arrive + bar.sync, 64 participants): a blocked warp costs no issue slots, unlike a spin on a flag.
+// None of these carries a "memory" clobber on purpose: volatile asm statements keep their order among themselves
+// (barrier -> slot stores -> barrier), which is all the hand-off needs, while the compiler stays free to schedule the
+// recurrence's own loads and FMAs around them -- with a clobber the hand-off would sit in the critical path.
+__device__ __forceinline__ void bar_sync64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id)); }
+__device__ __forceinline__ void bar_arrive64(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id)); }
+__device__ __forceinline__ void ring_st(float* p, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "f"(v));
+}
+__device__ __forceinline__ float ring_ld(const float* p) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+}
+
 // REV is the scan direction as a compile-time constant: every per-step address is then `base + immediate`, and the
 // integer work per step drops to two pointer bumps per chunk.
 template <bool REV>
 __device__ __forceinline__ void gru_fwd_bcast32_body(const float* __restrict__ gi, const float* __restrict__ whh,
-                                                     const float* __restrict__ bhh, float* __restrict__ out,
-                                                     float* __restrict__ gates, int T, long b, float (*h_s)[32],
-                                                     __nv_bfloat16* __restrict__ hp_hi, __nv_bfloat16* __restrict__ hp_lo) {
+                                                     const float* __restrict__ bhh, int T, long b, float (*h_s)[32],
+                                                     float (*ring)[32], int ready_id, int free_id) {
     constexpr int H = 32, H3 = 96, dir = REV ? 1 : 0;
-    constexpr long sGi = 2 * H3, sOut = 2 * H, sGs = 2 * 4 * H;            // floats per time step
-    constexpr long dGi = REV ? -sGi : sGi, dOut = REV ? -sOut : sOut, dGs = REV ? -sGs : sGs;
+    constexpr long sGi = 2 * H3;                                           // floats per time step
+    constexpr long dGi = REV ? -sGi : sGi;
     const int j = threadIdx.x & 31;
     const float* W = whh + (size_t)dir * H3 * H;
     float2 w2[3][H / 2];
@@ -354,12 +369,6 @@ __device__ __forceinline__ void gru_fwd_bcast32_body(const float* __restrict__ g
     }
     const long t0 = REV ? T - 1 : 0;
     const float* gp = gi + ((b * T + t0) * 2 + dir) * H3 + j;               // this lane's gi of the current chunk
-    float* op = out + (b * T + t0) * sOut + dir * H + j;
-    float* sp = gates + ((b * T + t0) * 2 + dir) * 4 * H + j;
-    // h_prev planes: h_t belongs to the row of the step that CONSUMES it (t+1 forward, t-1 reverse); the first
-    // step's own row holds h_0 = 0
-    long hrow = hp_hi ? ((b * T + t0) * 2 * H + dir * H + j) : 0;
-    if (hp_hi) store_plane(hp_hi, hp_lo, hrow, 0.0f);
     float h = 0.0f;
     float cur[kChF32][3], nxt[kChF32][3];
     auto load_chunk = [&](float (&dst)[kChF32][3], const float* g, int step0) {
@@ -403,41 +412,76 @@ __device__ __forceinline__ void gru_fwd_bcast32_body(const float* __restrict__ g
             const float z = fast_sigmoid(cur[s][1] + a1);
             const float n = fast_tanh(fmaf(r, a2, cur[s][2]));
             h = fmaf(z, h - n, n);
-            op[s * dOut] = h;
-            sp[s * dGs] = r; sp[s * dGs + H] = z; sp[s * dGs + 2 * H] = n; sp[s * dGs + 3 * H] = a2;
-            if (hp_hi && step0 + s + 1 < T) store_plane(hp_hi, hp_lo, hrow + (s + 1) * dOut, h);
+            // hand the step's results to the helper warp, which does every global store of the scan
+            if (step0 + s > 0) bar_sync64(free_id);
+            ring_st(&ring[0][j], r); ring_st(&ring[1][j], z); ring_st(&ring[2][j], n); ring_st(&ring[3][j], a2);
+            ring_st(&ring[4][j], h);
+            bar_arrive64(ready_id);
         }
-        hrow += kChF32 * dOut;
-        op += kChF32 * dOut;
-        sp += kChF32 * dGs;
 #pragma unroll
         for (int s = 0; s < kChF32; ++s) { cur[s][0] = nxt[s][0]; cur[s][1] = nxt[s][1]; cur[s][2] = nxt[s][2]; }
     }
 }
 
-__global__ void __launch_bounds__(128)
+// Helper warp of the forward scan: takes (r, z, n, q, h) of each step from the pair's shared-memory slot and writes
+// the layer output, the saved gates and (optionally) the h_{t-1} planes -- the scan warp itself never touches HBM
+// on the output side, so its dependent-instruction chain is only the recurrence.
+template <bool REV>
+__device__ __forceinline__ void gru_fwd_bcast32_helper(float* __restrict__ out, float* __restrict__ gates, int T, long b,
+                                                       const float (*ring)[32], int ready_id, int free_id,
+                                                       __nv_bfloat16* __restrict__ hp_hi, __nv_bfloat16* __restrict__ hp_lo) {
+    constexpr int H = 32, dir = REV ? 1 : 0;
+    constexpr long sOut = 2 * H, sGs = 2 * 4 * H;
+    constexpr long dOut = REV ? -sOut : sOut, dGs = REV ? -sGs : sGs;
+    const int j = threadIdx.x & 31;
+    const long t0 = REV ? T - 1 : 0;
+    float* op = out + (b * T + t0) * sOut + dir * H + j;
+    float* sp = gates + ((b * T + t0) * 2 + dir) * 4 * H + j;
+    // h_prev planes: h_t belongs to the row of the step that CONSUMES it (t+1 forward, t-1 reverse); the first
+    // step's own row holds h_0 = 0
+    long hrow = (b * T + t0) * 2 * H + dir * H + j;
+    if (hp_hi) store_plane(hp_hi, hp_lo, hrow, 0.0f);
+    for (int step = 0; step < T; ++step) {
+        bar_sync64(ready_id);
+        const float r = ring_ld(&ring[0][j]), z = ring_ld(&ring[1][j]), n = ring_ld(&ring[2][j]);
+        const float q = ring_ld(&ring[3][j]), h = ring_ld(&ring[4][j]);
+        if (step + 1 < T) bar_arrive64(free_id);
+        *op = h;
+        sp[0] = r; sp[H] = z; sp[2 * H] = n; sp[3 * H] = q;
+        op += dOut; sp += dGs; hrow += dOut;
+        if (hp_hi && step + 1 < T) store_plane(hp_hi, hp_lo, hrow, h);
+    }
+}
+
+__global__ void __launch_bounds__(256)
 gru_scan_fwd_bcast32_kernel(const float* __restrict__ gi, const float* __restrict__ whh, const float* __restrict__ bhh,
                             float* __restrict__ out, float* __restrict__ gates, int B, int T,
                             __nv_bfloat16* __restrict__ hp_hi, __nv_bfloat16* __restrict__ hp_lo) {
-    __shared__ __align__(16) float h_s[2 * 4][32];          // [buffer][warp] rows; a warp uses rows warp and 4 + warp
-    const int warp = threadIdx.x >> 5;
-    const long b = (long)blockIdx.x * 4 + warp;
-    if (b >= B) return;                                     // warps are independent: no block-level barrier below
-    if (blockIdx.y == 0) gru_fwd_bcast32_body<false>(gi, whh, bhh, out, gates, T, b, h_s + warp, hp_hi, hp_lo);
-    else gru_fwd_bcast32_body<true>(gi, whh, bhh, out, gates, T, b, h_s + warp, hp_hi, hp_lo);
+    __shared__ __align__(16) float h_s[2 * 4][32];          // [buffer][pair] rows; a pair uses rows pair and 4 + pair
+    __shared__ float ring[4][5][32];                        // per pair: r, z, n, q, h of the step being handed over
+    const int warp = threadIdx.x >> 5, pair = warp & 3;
+    const bool helper = warp >= 4;
+    const long b = (long)blockIdx.x * 4 + pair;
+    if (b >= B) return;                                     // pairs are independent: no block-level barrier below
+    const int ready_id = 1 + 2 * pair, free_id = 2 + 2 * pair;
+    if (!helper) {
+        if (blockIdx.y == 0) gru_fwd_bcast32_body<false>(gi, whh, bhh, T, b, h_s + pair, ring[pair], ready_id, free_id);
+        else gru_fwd_bcast32_body<true>(gi, whh, bhh, T, b, h_s + pair, ring[pair], ready_id, free_id);
+    } else {
+        if (blockIdx.y == 0) gru_fwd_bcast32_helper<false>(out, gates, T, b, ring[pair], ready_id, free_id, hp_hi, hp_lo);
+        else gru_fwd_bcast32_helper<true>(out, gates, T, b, ring[pair], ready_id, free_id, hp_hi, hp_lo);
+    }
 }
 
 template <bool REV>
 __device__ __forceinline__ void gru_bwd_bcast32_body(const float* __restrict__ dout, const float* __restrict__ out,
                                                      const float* __restrict__ gates, const float* __restrict__ whh,
-                                                     float* __restrict__ dgi, float* __restrict__ dgh,
                                                      float* __restrict__ part_b, int T, long b, float (*dg_s)[96],
-                                                     __nv_bfloat16* __restrict__ gi_hi, __nv_bfloat16* __restrict__ gi_lo,
-                                                     __nv_bfloat16* __restrict__ gh_hi, __nv_bfloat16* __restrict__ gh_lo) {
+                                                     float (*ring)[32], int ready_id, int free_id) {
     // REV = the FORWARD direction of this GRU half; the backward scan walks time the other way
     constexpr int H = 32, H3 = 96, dir = REV ? 1 : 0;
-    constexpr long sOut = 2 * H, sGs = 2 * 4 * H, sDg = 2 * H3;
-    constexpr long dOut = REV ? sOut : -sOut, dGs = REV ? sGs : -sGs, dDg = REV ? sDg : -sDg;
+    constexpr long sOut = 2 * H, sGs = 2 * 4 * H;
+    constexpr long dOut = REV ? sOut : -sOut, dGs = REV ? sGs : -sGs;
     const int j = threadIdx.x & 31;
     const float* W = whh + (size_t)dir * H3 * H;
     float2 wc[H3 / 2];                                          // (W_hh[e][j], W_hh[e+1][j]) for even e
@@ -447,9 +491,6 @@ __device__ __forceinline__ void gru_bwd_bcast32_body(const float* __restrict__ d
     const float* dp = dout + (b * T + t0) * sOut + dir * H + j;
     const float* hp_ = out + (b * T + t0) * sOut + dir * H + j;         // h_prev of step t is out[t -/+ 1]
     const float* gsp = gates + ((b * T + t0) * 2 + dir) * 4 * H + j;
-    float* gip = dgi + ((b * T + t0) * 2 + dir) * H3 + j;
-    float* ghp = dgh + ((b * T + t0) * 2 + dir) * H3 + j;
-    long prow = ((b * T + t0) * 2 + dir) * H3 + j;              // same element index in the bf16 planes
     float sb_r = 0, sb_z = 0, sb_n = 0, sb_q = 0;
     float dh = 0.0f;
     float cur[kChB32][6], nxt[kChB32][6];                       // dout, r, z, n, q, h_prev
@@ -486,14 +527,10 @@ __device__ __forceinline__ void gru_bwd_bcast32_body(const float* __restrict__ d
             float* ds = dg_s[buf * 4];
             ds[j] = dar; ds[H + j] = daz; ds[2 * H + j] = dq;
             __syncwarp();
-            if (gi_hi) {
-                const long o = prow + s * dDg;
-                store_plane(gi_hi, gi_lo, o, dar); store_plane(gi_hi, gi_lo, o + H, daz); store_plane(gi_hi, gi_lo, o + 2 * H, dan);
-                store_plane(gh_hi, gh_lo, o, dar); store_plane(gh_hi, gh_lo, o + H, daz); store_plane(gh_hi, gh_lo, o + 2 * H, dq);
-            } else {
-                gip[s * dDg] = dar; gip[s * dDg + H] = daz; gip[s * dDg + 2 * H] = dan;
-                ghp[s * dDg] = dar; ghp[s * dDg + H] = daz; ghp[s * dDg + 2 * H] = dq;
-            }
+            // the helper warp turns these four values into the dgi / dgh stores (fp32 or bf16 planes)
+            if (step0 + s > 0) bar_sync64(free_id);
+            ring_st(&ring[0][j], dar); ring_st(&ring[1][j], daz); ring_st(&ring[2][j], dan); ring_st(&ring[3][j], dq);
+            bar_arrive64(ready_id);
             sb_r += dar; sb_z += daz; sb_n += dan; sb_q += dq;
             const float4* dv4 = reinterpret_cast<const float4*>(ds);
             buf ^= 1;
@@ -508,7 +545,6 @@ __device__ __forceinline__ void gru_bwd_bcast32_body(const float* __restrict__ d
             }
             dh = fmaf(dht, z, ((acc[0].x + acc[0].y) + (acc[1].x + acc[1].y)) + ((acc[2].x + acc[2].y) + (acc[3].x + acc[3].y)));
         }
-        gip += kChB32 * dDg; ghp += kChB32 * dDg; prow += kChB32 * dDg;
 #pragma unroll
         for (int s = 0; s < kChB32; ++s)
 #pragma unroll
@@ -519,18 +555,54 @@ __device__ __forceinline__ void gru_bwd_bcast32_body(const float* __restrict__ d
     pb[2 * H3 + dir * H3 + j] = sb_r; pb[2 * H3 + dir * H3 + H + j] = sb_z; pb[2 * H3 + dir * H3 + 2 * H + j] = sb_q;
 }
 
-__global__ void __launch_bounds__(128)
+// Helper warp of the backward scan: dgi = (dar, daz, dan), dgh = (dar, daz, dq) of each step, as fp32 or as the bf16
+// hi/lo planes the tensor-core GEMMs consume.
+template <bool REV>
+__device__ __forceinline__ void gru_bwd_bcast32_helper(float* __restrict__ dgi, float* __restrict__ dgh, int T, long b,
+                                                       const float (*ring)[32], int ready_id, int free_id,
+                                                       __nv_bfloat16* __restrict__ gi_hi, __nv_bfloat16* __restrict__ gi_lo,
+                                                       __nv_bfloat16* __restrict__ gh_hi, __nv_bfloat16* __restrict__ gh_lo) {
+    constexpr int H = 32, H3 = 96, dir = REV ? 1 : 0;
+    constexpr long sDg = 2 * H3, dDg = REV ? sDg : -sDg;
+    const int j = threadIdx.x & 31;
+    const long t0 = REV ? 0 : T - 1;
+    long o = ((b * T + t0) * 2 + dir) * H3 + j;                 // element index in dgi / dgh and in their planes
+    for (int step = 0; step < T; ++step) {
+        bar_sync64(ready_id);
+        const float dar = ring_ld(&ring[0][j]), daz = ring_ld(&ring[1][j]), dan = ring_ld(&ring[2][j]);
+        const float dq = ring_ld(&ring[3][j]);
+        if (step + 1 < T) bar_arrive64(free_id);
+        if (gi_hi) {
+            store_plane(gi_hi, gi_lo, o, dar); store_plane(gi_hi, gi_lo, o + H, daz); store_plane(gi_hi, gi_lo, o + 2 * H, dan);
+            store_plane(gh_hi, gh_lo, o, dar); store_plane(gh_hi, gh_lo, o + H, daz); store_plane(gh_hi, gh_lo, o + 2 * H, dq);
+        } else {
+            dgi[o] = dar; dgi[o + H] = daz; dgi[o + 2 * H] = dan;
+            dgh[o] = dar; dgh[o + H] = daz; dgh[o + 2 * H] = dq;
+        }
+        o += dDg;
+    }
+}
+
+__global__ void __launch_bounds__(256)
 gru_scan_bwd_bcast32_kernel(const float* __restrict__ dout, const float* __restrict__ out,
                             const float* __restrict__ gates, const float* __restrict__ whh, float* __restrict__ dgi,
                             float* __restrict__ dgh, float* __restrict__ part_b, int B, int T,
                             __nv_bfloat16* __restrict__ gi_hi, __nv_bfloat16* __restrict__ gi_lo,
                             __nv_bfloat16* __restrict__ gh_hi, __nv_bfloat16* __restrict__ gh_lo) {
     __shared__ __align__(16) float dg_s[2 * 4][96];
-    const int warp = threadIdx.x >> 5;
-    const long b = (long)blockIdx.x * 4 + warp;
+    __shared__ float ring[4][4][32];                        // per pair: dar, daz, dan, dq of the step being handed over
+    const int warp = threadIdx.x >> 5, pair = warp & 3;
+    const bool helper = warp >= 4;
+    const long b = (long)blockIdx.x * 4 + pair;
     if (b >= B) return;
-    if (blockIdx.y == 0) gru_bwd_bcast32_body<false>(dout, out, gates, whh, dgi, dgh, part_b, T, b, dg_s + warp, gi_hi, gi_lo, gh_hi, gh_lo);
-    else gru_bwd_bcast32_body<true>(dout, out, gates, whh, dgi, dgh, part_b, T, b, dg_s + warp, gi_hi, gi_lo, gh_hi, gh_lo);
+    const int ready_id = 1 + 2 * pair, free_id = 2 + 2 * pair;
+    if (!helper) {
+        if (blockIdx.y == 0) gru_bwd_bcast32_body<false>(dout, out, gates, whh, part_b, T, b, dg_s + pair, ring[pair], ready_id, free_id);
+        else gru_bwd_bcast32_body<true>(dout, out, gates, whh, part_b, T, b, dg_s + pair, ring[pair], ready_id, free_id);
+    } else {
+        if (blockIdx.y == 0) gru_bwd_bcast32_helper<false>(dgi, dgh, T, b, ring[pair], ready_id, free_id, gi_hi, gi_lo, gh_hi, gh_lo);
+        else gru_bwd_bcast32_helper<true>(dgi, dgh, T, b, ring[pair], ready_id, free_id, gi_hi, gi_lo, gh_hi, gh_lo);
+    }
 }
 
 // ------------------------------------------------------------------------------ H = 64 / 128: K-split scans
@@ -725,7 +797,7 @@ int gru_scan_forward(const float* gi, const float* whh, const float* bhh, float*
                      int H, cudaStream_t st, void* hprev_hi, void* hprev_lo) {
     SED_REQUIRE(!hprev_hi || gru_scan_emits_planes(H), SEDB200_ESHAPE, "gru_scan: h_prev planes need H = 32 (H = %d)", H);
     if (H == 32) {
-        gru_scan_fwd_bcast32_kernel<<<dim3((B + 3) / 4, 2), 128, 0, st>>>(
+        gru_scan_fwd_bcast32_kernel<<<dim3((B + 3) / 4, 2), 256, 0, st>>>(
             gi, whh, bhh, out, gates, B, T, reinterpret_cast<__nv_bfloat16*>(hprev_hi), reinterpret_cast<__nv_bfloat16*>(hprev_lo));
         SED_POST_LAUNCH();
         return SEDB200_OK;
@@ -760,7 +832,7 @@ int gru_scan_backward(const float* dout, const float* out, const float* gates, c
     if (H == 32) {
         __nv_bfloat16* pl[4] = {nullptr, nullptr, nullptr, nullptr};
         if (planes) for (int i = 0; i < 4; ++i) pl[i] = reinterpret_cast<__nv_bfloat16*>(planes[i]);
-        gru_scan_bwd_bcast32_kernel<<<dim3((B + 3) / 4, 2), 128, 0, st>>>(dout, out, gates, whh, dgi, dgh, part_b, B, T,
+        gru_scan_bwd_bcast32_kernel<<<dim3((B + 3) / 4, 2), 256, 0, st>>>(dout, out, gates, whh, dgi, dgh, part_b, B, T,
                                                                            pl[0], pl[1], pl[2], pl[3]);
         SED_POST_LAUNCH();
         return SEDB200_OK;
