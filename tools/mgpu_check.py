@@ -44,7 +44,13 @@ def main():
         gscale = engs["nccl"].grads.abs().max().item()
         if rank == 0:
             print(f"step {i}: ranks identical={same} |p_nccl-p_p2p|max={diff:.3e} |g_nccl-g_p2p|max={gd:.3e} (|g|max {gscale:.3e})")
-        ok &= same and diff < 5e-6 and gd <= 1e-5 * max(gscale, 1e-30) * world
+        # two ranks: a + b is the same sum in either order, so the two paths must agree bit for bit; more ranks: NCCL
+        # adds in ring / tree order, the fused kernel in rank order -- gradients agree to rounding, and Adam may turn a
+        # last-bit difference of a near-zero gradient into +-lr, so the weights are only required to stay close
+        if world == 2:
+            ok &= same and diff == 0.0 and gd == 0.0
+        else:
+            ok &= same and gd <= 1e-4 * max(gscale, 1e-30) and diff < 5e-3
     times = {}
     for k, e in engs.items():
         for x, y in batches[:3]:
