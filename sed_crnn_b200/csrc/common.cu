@@ -57,6 +57,22 @@ int require_sm100() {
 }
 
 namespace {
+std::mutex g_smem_mu;
+std::map<std::pair<int, const void*>, int> g_smem_set;     // (device, kernel) -> bytes already granted
+}  // namespace
+
+int ensure_dyn_smem(const void* func, int bytes) {
+    int dev = 0;
+    SED_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_smem_mu);
+    auto it = g_smem_set.find({dev, func});
+    if (it != g_smem_set.end() && it->second >= bytes) return SEDB200_OK;
+    SED_CUDA_OK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    g_smem_set[{dev, func}] = bytes;
+    return SEDB200_OK;
+}
+
+namespace {
 std::atomic<long> g_launches{0};
 std::atomic<bool> g_prof{false};
 struct ProfRec { std::string name; cudaEvent_t a, b; };

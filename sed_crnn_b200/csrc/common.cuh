@@ -47,6 +47,9 @@ struct ProfScope {
 // 0 if the current device is compute capability 10.x, else SEDB200_EARCH (message set).
 int  require_sm100();
 int  sm_count();
+// cudaFuncSetAttribute(func, MaxDynamicSharedMemorySize, bytes) once per (device, kernel): the attribute belongs to
+// the device's context, so a process that drives several GPUs must set it on each of them.  Thread-safe.
+int  ensure_dyn_smem(const void* func, int bytes);
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -1302,11 +1302,8 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         float* din = j == 0 ? wsf(ws, P.dseq[0]) : wsf(ws, P.dhid[(j - 1) & 1]);
         const float* mask = (j > 0 && d->dense_relu) ? wsf(ws, P.hid[j - 1]) : nullptr;
         if (dense_small_ok(N, D)) {
-            static bool attr_done = false;
-            if (!attr_done) {
-                SED_CUDA_OK(cudaFuncSetAttribute(dense_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-                attr_done = true;
-            }
+            rc = ensure_dyn_smem((const void*)dense_bwd_small_kernel, 160 * 1024);
+            if (rc) return rc;
             const int nblk = (BT + kDbRows - 1) / kDbRows;
             dense_bwd_small_kernel<<<nblk, 256, dense_small_smem(N, D), st>>>(dout, in, params + P.dn_w[j], mask, BT, N, D, din, part);
             SED_POST_LAUNCH();

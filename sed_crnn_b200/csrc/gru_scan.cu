@@ -814,8 +814,7 @@ int gru_scan_forward(const float* gi, const float* whh, const float* bhh, float*
     const int threads = round32(std::max(3 * H, kBT * H));
     SED_REQUIRE(threads <= 1024 && H % 4 == 0, SEDB200_ESHAPE, "gru_scan: H=%d unsupported", H);
     const size_t smem = ((size_t)3 * H * H + kBT * H + kBT * 3 * H) * 4;
-    static bool attr_f = false;
-    if (!attr_f) { SED_CUDA_OK(cudaFuncSetAttribute(gru_scan_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_f = true; }
+    { const int rc = ensure_dyn_smem((const void*)gru_scan_fwd_kernel, 227 * 1024); if (rc) return rc; }
     SED_REQUIRE(smem <= 227 * 1024, SEDB200_ESHAPE, "gru_scan: H=%d needs %zu B shared memory", H, smem);
     dim3 grid((B + kBT - 1) / kBT, 2);
     gru_scan_fwd_kernel<<<grid, threads, smem, st>>>(gi, whh, bhh, out, gates, B, T, H);
@@ -849,8 +848,7 @@ int gru_scan_backward(const float* dout, const float* out, const float* gates, c
     const int threads = round32(kBT * H);
     SED_REQUIRE(threads <= 1024 && H % 4 == 0, SEDB200_ESHAPE, "gru_scan: H=%d unsupported", H);
     const size_t smem = ((size_t)3 * H * H + kBT * 3 * H) * 4;
-    static bool attr_b = false;
-    if (!attr_b) { SED_CUDA_OK(cudaFuncSetAttribute(gru_scan_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_b = true; }
+    { const int rc = ensure_dyn_smem((const void*)gru_scan_bwd_kernel, 227 * 1024); if (rc) return rc; }
     SED_REQUIRE(smem <= 227 * 1024, SEDB200_ESHAPE, "gru_scan: H=%d needs %zu B shared memory", H, smem);
     dim3 grid((B + kBT - 1) / kBT, 2);
     gru_scan_bwd_kernel<<<grid, threads, smem, st>>>(dout, out, gates, whh, dgi, dgh, B, T, H);

@@ -200,8 +200,6 @@ __global__ void head_reduce_kernel(const float* __restrict__ part, int nblk, Hea
     loss[0] = (float)(a / (double)n_elems);
 }
 
-bool g_attr_done = false;
-
 }  // namespace
 
 bool head_fused_supported(const Plan& P) {
@@ -223,9 +221,9 @@ int head_fused_run(const Plan& P, const sedb200_crnn_desc* d, const float* param
     const long n_elems = (long)rows * hd.N1;
     const int nblk = (rows + kRows - 1) / kRows;
     const size_t smem = head_smem_floats(hd.D, hd.N0, hd.N1) * 4;
-    if (!g_attr_done) {
-        SED_CUDA_OK(cudaFuncSetAttribute(head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        g_attr_done = true;
+    {
+        const int rc = ensure_dyn_smem((const void*)head_fused_kernel, 200 * 1024);
+        if (rc) return rc;
     }
     SED_PROF("head.fused", st);
     head_fused_kernel<<<nblk, kThreads, smem, st>>>(x, params + P.dn_w[0], params + P.dn_b[0], params + P.dn_w[1],

@@ -437,7 +437,6 @@ int build_tables(int sr, LogmelTables& t) {
 
 std::mutex g_tab_mu;
 std::map<std::pair<int, int>, LogmelTables*> g_tabs;   // (device, sr) -> device copy
-bool g_attr_set[64] = {false};
 
 int get_tables(int sr, cudaStream_t stream, const LogmelTables** out) {
     int dev = 0;
@@ -453,10 +452,6 @@ int get_tables(int sr, cudaStream_t stream, const LogmelTables** out) {
         SED_CUDA_OK(cudaMemcpyAsync(d, &host, sizeof(LogmelTables), cudaMemcpyHostToDevice, stream));
         SED_CUDA_OK(cudaStreamSynchronize(stream));   // one-off; later calls are fully asynchronous
         it = g_tabs.emplace(std::make_pair(dev, sr), d).first;
-    }
-    if (dev < 64 && !g_attr_set[dev]) {
-        SED_CUDA_OK(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        g_attr_set[dev] = true;
     }
     *out = it->second;
     return SEDB200_OK;
@@ -492,6 +487,8 @@ int sedb200_logmel_f32(const float* pcm_dev, int n_clips, int n_ch, long n_sampl
     const long total = (long)n_clips * n_ch * nfr;
     const long want = (total + kWarps - 1) / kWarps;
     const int grid = (int)std::min<long>(want, sm_count());
+    rc = ensure_dyn_smem((const void*)logmel_kernel, kSmemBytes);
+    if (rc) return rc;
     logmel_kernel<<<grid, kWarps * 32, kSmemBytes, st>>>(pcm_dev, out_dev, n_ch, n_samples, (int)nfr, total,
                                                          pad_mode, tab);
     SED_POST_LAUNCH();

@@ -461,11 +461,7 @@ int conv_tc_planes(const void* a_hi, const void* a_lo, const float* w, const flo
     p.kchunks = Kc / kBlockK;
     p.n_total = Nc;
     p.out = out; p.bias = bias; p.out_ld = Nc; p.stats = stats;
-    static bool attr_done = false;
-    if (!attr_done) {
-        SED_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        attr_done = true;
-    }
+    { const int rc = ensure_dyn_smem((const void*)conv_tc_kernel, kSmemBytes); if (rc) return rc; }
     const int grid = std::min(p.total_tiles, sm_count());
     conv_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
     SED_POST_LAUNCH();
@@ -539,11 +535,7 @@ int wgrad_tc_planes(const void* y_hi, const void* y_lo, const void* x_hi, const 
     p.n_mt = Cout / 128; p.n_nt = Cin / 128;
     p.slices = std::min(wgrad_slices(Cin, Cout), p.total_kblocks);
     p.part = part; p.Cout = Cout; p.Cin = Cin;
-    static bool attr_done = false;
-    if (!attr_done) {
-        SED_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
-        attr_done = true;
-    }
+    { const int rc = ensure_dyn_smem((const void*)wgrad_tc_kernel, kWgSmemBytes); if (rc) return rc; }
     const int grid = p.n_mt * p.n_nt * 3 * p.slices;
     wgrad_tc_kernel<<<grid, kThreads, kWgSmemBytes, st>>>(tmY_hi, tmY_lo, tmX_hi, tmX_lo, p);
     SED_POST_LAUNCH();

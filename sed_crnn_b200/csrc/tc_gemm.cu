@@ -234,11 +234,7 @@ inline size_t plane_bytes(long rows, long cols) { return ((size_t)rows * cols * 
 template <bool A_MN, bool B_MN>
 int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
            const GemmTcParams& p, cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        SED_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        attr_done = true;
-    }
+    { const int rc = ensure_dyn_smem((const void*)gemm_tc_kernel<A_MN, B_MN>, kSmemBytes); if (rc) return rc; }
     const int grid = std::min(p.n_items, sm_count());
     gemm_tc_kernel<A_MN, B_MN><<<grid, kThreads, kSmemBytes, st>>>(a_hi, a_lo, b_hi, b_lo, p);
     SED_POST_LAUNCH();
