@@ -768,6 +768,145 @@ gru_scan_bwd_split_kernel(const float* __restrict__ dout, const float* __restric
     }
 }
 
+// ------------------------------------------------------------------------------ H = 128: register-tiled backward scan
+constexpr int kOpDepth = 6;             // cp.async ring slots (operands are requested kOpDepth - 1 steps ahead)
+__device__ __forceinline__ void cp_async4(unsigned smem_addr, const float* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// The K-split kernel above reads 96 gradient words per thread per row and step: 393 KB of shared-memory traffic per
+// step and SM, which is what bounds it (3,072 LSU cycles per step against 768 FMA-pipe cycles).  Here a thread owns an
+// 8 (hidden units) x 12 (gate-gradient slice) tile of W_hh -- still 96 registers -- so each loaded word feeds 8
+// FMAs: 6 LDS.128 per step instead of 48.  The two batch rows of a block are interleaved in shared memory and travel
+// together through packed fma.f32x2 (weight as the scalar operand), and the 32 slices of a hidden unit are folded
+// with a reduce-scatter over the warp (18 shuffles per step).  Direction is a template constant.
+template <bool REV>
+__device__ __forceinline__ void gru_bwd_tile128_body(const float* __restrict__ dout, const float* __restrict__ out,
+                                                     const float* __restrict__ gates, const float* __restrict__ whh,
+                                                     float* __restrict__ dgi, float* __restrict__ dgh,
+                                                     float* __restrict__ part_b, int B, int T, float (*dg_s)[384][2],
+                                                     float (*ops)[6][128][2]) {
+    constexpr int H = 128, H3 = 384, dir = REV ? 1 : 0;
+    constexpr long sOut = 2 * H, sGs = 2 * 4 * H, sDg = 2 * H3;           // floats per time step
+    constexpr long dOut = REV ? sOut : -sOut, dGs = REV ? sGs : -sGs, dDg = REV ? sDg : -sDg;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* W = whh + (size_t)dir * H3 * H;
+    float w[8][12];                                           // W_hh[12*lane + ee][8*warp + jj]
+#pragma unroll
+    for (int ee = 0; ee < 12; ++ee)
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) w[jj][ee] = __ldg(W + (size_t)(12 * lane + ee) * H + 8 * warp + jj);
+    // after the reduce-scatter lane L holds hidden unit 8*warp + ((L >> 2) & 7) of both rows; lanes with (L & 3) < 2
+    // finish (row L & 3, that unit): gate derivatives, outputs, next step's shared vector
+    const int j = 8 * warp + ((lane >> 2) & 7), r = lane & 3;
+    const long b = (long)blockIdx.x * 2 + r;
+    const bool gate = r < 2 && b < B;
+    const long t0 = REV ? 0 : T - 1;
+    // element indices as 32-bit integers (the launcher checks the tensors have < 2^31 elements): one register each
+    // instead of five 64-bit pointers -- the kernel sits exactly at the 128-register limit of a 512-thread block
+    int io = (int)((b * T + t0) * sOut + dir * H + j);                     // into dout / out
+    int ig = (int)(((b * T + t0) * 2 + dir) * 4 * H + j);                  // into gates
+    int id = (int)(((b * T + t0) * 2 + dir) * H3 + j);                     // into dgi / dgh
+    float dh = 0.0f, sb_r = 0, sb_z = 0, sb_n = 0, sb_q = 0;
+    // The six per-step operands of a gate thread travel global -> shared with cp.async, kOpDepth - 1 steps ahead of
+    // their use: no registers are held for data in flight (there are none to spare), and a step no longer waits a
+    // DRAM round trip for operands requested only one step earlier.
+    float* my_ops = &ops[0][0][(lane >> 2) + 8 * warp][r & 1];          // [slot][operand][unit][row]
+    const unsigned ops_addr = (unsigned)__cvta_generic_to_shared(my_ops);
+    constexpr unsigned kOpStride = 128 * 2 * 4, kSlotStride = 6 * kOpStride;     // bytes
+    auto issue = [&](int step) {                              // operands of `step`; io / ig point at that step
+        if (gate && step < T) {
+            const unsigned d = ops_addr + (unsigned)(step % kOpDepth) * kSlotStride;
+            cp_async4(d, dout + io);
+            cp_async4(d + kOpStride, gates + ig);
+            cp_async4(d + 2 * kOpStride, gates + ig + H);
+            cp_async4(d + 3 * kOpStride, gates + ig + 2 * H);
+            cp_async4(d + 4 * kOpStride, gates + ig + 3 * H);
+            if (step + 1 < T) cp_async4(d + 5 * kOpStride, out + io + dOut);     // forward-previous hidden state
+            io += (int)dOut; ig += (int)dGs;
+        }
+        cp_async_commit();
+    };
+#pragma unroll 1
+    for (int p = 0; p < kOpDepth - 1; ++p) issue(p);
+    for (int i = threadIdx.x; i < 2 * H3 * 2; i += blockDim.x) (&dg_s[0][0][0])[i] = 0.0f;
+    __syncthreads();
+    int cur = 0;
+    for (int step = 0; step < T; ++step) {
+        issue(step + kOpDepth - 1);
+        cp_async_wait<kOpDepth - 1>();                        // this step's operands have landed
+        float direct = 0.0f;
+        if (gate) {
+            const float* o = my_ops + (size_t)(step % kOpDepth) * (kSlotStride / 4);
+            const float c_do = o[0], rr = o[kOpStride / 4], z = o[2 * (kOpStride / 4)], n = o[3 * (kOpStride / 4)];
+            const float q = o[4 * (kOpStride / 4)], hp = step + 1 < T ? o[5 * (kOpStride / 4)] : 0.0f;
+            const float dht = c_do + dh;
+            const float dn = dht * (1.0f - z);
+            const float dz = dht * (hp - n);
+            direct = dht * z;
+            const float dan = dn * (1.0f - n * n);
+            const float dar = dan * q * rr * (1.0f - rr);
+            const float daz = dz * z * (1.0f - z);
+            const float dq = dan * rr;
+            dgi[id] = dar; dgi[id + H] = daz; dgi[id + 2 * H] = dan;
+            dgh[id] = dar; dgh[id + H] = daz; dgh[id + 2 * H] = dq;
+            id += (int)dDg;
+            sb_r += dar; sb_z += daz; sb_n += dan; sb_q += dq;
+            dg_s[cur][j][r] = dar;
+            dg_s[cur][H + j][r] = daz;
+            dg_s[cur][2 * H + j][r] = dq;
+        }
+        __syncthreads();
+        // dh[j] (both rows) += sum over this lane's 12 gradient words
+        float2 acc[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) acc[jj] = make_float2(0.0f, 0.0f);
+        const float4* dv = reinterpret_cast<const float4*>(&dg_s[cur][12 * lane][0]);
+#pragma unroll
+        for (int q4 = 0; q4 < 6; ++q4) {
+            const float4 d4 = dv[q4];                          // (e, row0), (e, row1), (e+1, row0), (e+1, row1)
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                acc[jj] = __ffma2_rn(make_float2(w[jj][2 * q4], w[jj][2 * q4]), make_float2(d4.x, d4.y), acc[jj]);
+                acc[jj] = __ffma2_rn(make_float2(w[jj][2 * q4 + 1], w[jj][2 * q4 + 1]), make_float2(d4.z, d4.w), acc[jj]);
+            }
+        }
+        // reduce-scatter over the 32 slices: 8 -> 4 -> 2 -> 1 values per lane, then two butterflies
+#pragma unroll
+        for (int half = 4, off = 16; half >= 1; half >>= 1, off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+                const float2 send = up ? acc[i] : acc[i + half], keep = up ? acc[i + half] : acc[i];
+                acc[i].x = keep.x + __shfl_xor_sync(0xffffffffu, send.x, off);
+                acc[i].y = keep.y + __shfl_xor_sync(0xffffffffu, send.y, off);
+            }
+        }
+        acc[0].x += __shfl_xor_sync(0xffffffffu, acc[0].x, 2); acc[0].y += __shfl_xor_sync(0xffffffffu, acc[0].y, 2);
+        acc[0].x += __shfl_xor_sync(0xffffffffu, acc[0].x, 1); acc[0].y += __shfl_xor_sync(0xffffffffu, acc[0].y, 1);
+        if (gate) dh = direct + (r == 0 ? acc[0].x : acc[0].y);
+        cur ^= 1;
+    }
+    if (gate) {
+        float* pb = part_b + (b * 2) * 2 * H3;                  // [B][ih|hh][2][3H]
+        pb[dir * H3 + j] = sb_r; pb[dir * H3 + H + j] = sb_z; pb[dir * H3 + 2 * H + j] = sb_n;
+        pb[2 * H3 + dir * H3 + j] = sb_r; pb[2 * H3 + dir * H3 + H + j] = sb_z; pb[2 * H3 + dir * H3 + 2 * H + j] = sb_q;
+    }
+}
+
+__global__ void __launch_bounds__(512, 1)
+gru_scan_bwd_tile128_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                            const float* __restrict__ gates, const float* __restrict__ whh, float* __restrict__ dgi,
+                            float* __restrict__ dgh, float* __restrict__ part_b, int B, int T) {
+    __shared__ __align__(16) float dg_s[2][384][2];           // [buffer][gradient word][row]
+    __shared__ float ops[kOpDepth][6][128][2];                // cp.async ring of the gate threads' operands
+    if (blockIdx.y == 0) gru_bwd_tile128_body<false>(dout, out, gates, whh, dgi, dgh, part_b, B, T, dg_s, ops);
+    else gru_bwd_tile128_body<true>(dout, out, gates, whh, dgi, dgh, part_b, B, T, dg_s, ops);
+}
+
 template <int H>
 int launch_warp_fwd(const float* gi, const float* whh, const float* bhh, float* out, float* gates, int B, int T,
                     cudaStream_t st) {
@@ -840,7 +979,7 @@ int gru_scan_backward(const float* dout, const float* out, const float* gates, c
     if (H == 8) return launch_warp_bwd<8>(dout, out, gates, whh, dgi, dgh, part_w, part_b, B, T, st);
     if (H == 128 || H == 64) {
         dim3 grid((B + kSplitBT - 1) / kSplitBT, 2);
-        if (H == 128) gru_scan_bwd_split_kernel<128><<<grid, 512, 0, st>>>(dout, out, gates, whh, dgi, dgh, part_b, B, T);
+        if (H == 128) gru_scan_bwd_tile128_kernel<<<grid, 512, 0, st>>>(dout, out, gates, whh, dgi, dgh, part_b, B, T);
         else gru_scan_bwd_split_kernel<64><<<grid, 256, 0, st>>>(dout, out, gates, whh, dgi, dgh, part_b, B, T);
         SED_POST_LAUNCH();
         return SEDB200_OK;
