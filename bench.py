@@ -268,6 +268,39 @@ def logmel_leg(torch, feature, L, pk, rank, world=1, dist=None):
     return res
 
 
+def other_configs_leg(torch, config, engine, main_config):
+    """The BASELINE configs that are not the bench line (parity-test cases), timed for reference on one GPU:
+    device-resident batches, CUDA events, 3 warm-up + 5 timed steps each.  Informational only."""
+    out = {}
+    for name, B in (("c1", 128), ("c5", 128)):
+        if name == main_config:
+            continue
+        try:
+            cfg = config.PRESETS[name]
+            eng = engine.CRNNEngine(cfg, loss="bce", lr=1e-3, weight_decay=1e-4, clip=1.0, seed=99)
+            eng.init_default(seed=0)
+            g = torch.Generator(device="cuda").manual_seed(5)
+            x = torch.randn(cfg.input_shape(B), device="cuda", generator=g)
+            y = (torch.rand(cfg.target_shape(B), device="cuda", generator=g) < 0.2).float()
+            for _ in range(3):
+                eng.train_step(x, y)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                eng.train_step(x, y)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            out[name] = {"workload": workload_name(name, 1), "per_gpu_batch": B, "seq_len": cfg.seq_len, "ms_per_step": ms,
+                         "frames_per_s": B * cfg.seq_len / (ms * 1e-3)}
+            del eng, x, y
+            torch.cuda.empty_cache()
+        except Exception as e:                                  # noqa: BLE001 -- informational leg must not sink the run
+            out[name] = {"error": str(e)[:200]}
+    return out
+
+
 def cpu_baselines(args, torch):
     """Reference CPU path beside the GPU number (rank 0, N=1 only; bounded samples)."""
     from oracle import crnn_ref as R, logmel_ref
@@ -471,6 +504,8 @@ def run_ours(args, rank, world, local_rank):
     if world == 1:
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baselines(args, torch)
+        if not args.no_other_configs:
+            line["other_configs"] = other_configs_leg(torch, config, engine, args.config)
     if lm is not None:
         line["logmel"] = lm
     print(json.dumps(line))
@@ -489,6 +524,7 @@ def main():
     ap.add_argument("--grad-exchange", default="auto", choices=["auto", "nccl", "p2p"])
     ap.add_argument("--clock-period-ms", type=int, default=50, help="nvidia-smi sampling period during the run")
     ap.add_argument("--no-logmel", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the C1 / C5 reference timings (N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU-baseline leg (profiling runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
