@@ -907,6 +907,129 @@ gru_scan_bwd_tile128_kernel(const float* __restrict__ dout, const float* __restr
     else gru_bwd_tile128_body<true>(dout, out, gates, whh, dgi, dgh, part_b, B, T, dg_s, ops);
 }
 
+// ------------------------------------------------------------------------------ H = 128: register-tiled forward scan
+// Thread tile: 3 gates x 2 hidden units x 16 k (96 weights): 8 LDS.128 per step instead of 16, rows paired in
+// fma.f32x2, the 8 k-slices of a unit pair folded with a reduce-scatter (18 shuffles), gi through a cp.async ring.
+template <bool REV>
+__device__ __forceinline__ void gru_fwd_tile128_body(const float* __restrict__ gi, const float* __restrict__ whh,
+                                                     const float* __restrict__ bhh, float* __restrict__ out,
+                                                     float* __restrict__ gates, int B, int T, float (*h_s)[128][2],
+                                                     float (*ops)[3][128][2]) {
+    constexpr int H = 128, H3 = 384, dir = REV ? 1 : 0;
+    constexpr long sGi = 2 * H3, sOut = 2 * H, sGs = 2 * 4 * H;
+    constexpr long dGi = REV ? -sGi : sGi, dOut = REV ? -sOut : sOut, dGs = REV ? -sGs : sGs;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int up = lane >> 3, ks = lane & 7;                  // unit pair of the warp, k slice
+    const int j0 = 8 * warp + 2 * up;
+    const float* W = whh + (size_t)dir * H3 * H;
+    float w[3][2][16];                                        // W_hh[g*H + j0 + u][k], k = 2*(ks + 8*i) + {0, 1}
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float2 t = __ldg(reinterpret_cast<const float2*>(W + (size_t)(g * H + j0 + u) * H + 2 * (ks + 8 * i)));
+                w[g][u][2 * i] = t.x;
+                w[g][u][2 * i + 1] = t.y;
+            }
+    // after the reduce-scatter, lanes with bit 2 == u hold the three gate sums of unit j0 + u (both rows); of those,
+    // lanes with (lane & 3) < 2 finish (row lane & 3, that unit)
+    const int j = j0 + ((lane >> 2) & 1), r = lane & 3;
+    const long b = (long)blockIdx.x * 2 + r;
+    const bool gate = r < 2 && b < B;
+    const long t0 = REV ? T - 1 : 0;
+    int ig = (int)(((b * T + t0) * 2 + dir) * H3 + j);        // into gi
+    int io = (int)((b * T + t0) * sOut + dir * H + j);        // into out
+    int is = (int)(((b * T + t0) * 2 + dir) * 4 * H + j);     // into gates
+    float bias[3] = {0.f, 0.f, 0.f};
+    if (gate) {
+#pragma unroll
+        for (int g = 0; g < 3; ++g) bias[g] = __ldg(bhh + dir * H3 + g * H + j);
+    }
+    float* my_ops = &ops[0][0][j][r & 1];
+    const unsigned ops_addr = (unsigned)__cvta_generic_to_shared(my_ops);
+    constexpr unsigned kOpStride = 128 * 2 * 4, kSlotStride = 3 * kOpStride;
+    auto issue = [&](int step) {
+        if (gate && step < T) {
+            const unsigned d = ops_addr + (unsigned)(step % kOpDepth) * kSlotStride;
+            cp_async4(d, gi + ig);
+            cp_async4(d + kOpStride, gi + ig + H);
+            cp_async4(d + 2 * kOpStride, gi + ig + 2 * H);
+            ig += (int)dGi;
+        }
+        cp_async_commit();
+    };
+#pragma unroll 1
+    for (int p = 0; p < kOpDepth - 1; ++p) issue(p);
+    for (int i = threadIdx.x; i < 2 * H * 2; i += blockDim.x) (&h_s[0][0][0])[i] = 0.0f;
+    float hprev = 0.0f;
+    __syncthreads();
+    int cur = 0;
+    for (int step = 0; step < T; ++step) {
+        issue(step + kOpDepth - 1);
+        float2 acc[3][2];
+#pragma unroll
+        for (int g = 0; g < 3; ++g) acc[g][0] = acc[g][1] = make_float2(0.0f, 0.0f);
+        const float4* hv = reinterpret_cast<const float4*>(&h_s[cur][0][0]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 h4 = hv[ks + 8 * i];                 // (k, row0), (k, row1), (k+1, row0), (k+1, row1)
+#pragma unroll
+            for (int g = 0; g < 3; ++g)
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    acc[g][u] = __ffma2_rn(make_float2(w[g][u][2 * i], w[g][u][2 * i]), make_float2(h4.x, h4.y), acc[g][u]);
+                    acc[g][u] = __ffma2_rn(make_float2(w[g][u][2 * i + 1], w[g][u][2 * i + 1]), make_float2(h4.z, h4.w), acc[g][u]);
+                }
+        }
+        // fold the 8 k slices: lanes with bit 2 clear keep unit 0, the others unit 1; then two butterflies
+        float2 v[3];
+        {
+            const bool upper = (lane & 4) != 0;
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                const float2 send = upper ? acc[g][0] : acc[g][1], keep = upper ? acc[g][1] : acc[g][0];
+                v[g].x = keep.x + __shfl_xor_sync(0xffffffffu, send.x, 4);
+                v[g].y = keep.y + __shfl_xor_sync(0xffffffffu, send.y, 4);
+            }
+#pragma unroll
+            for (int off = 2; off >= 1; off >>= 1)
+#pragma unroll
+                for (int g = 0; g < 3; ++g) {
+                    v[g].x += __shfl_xor_sync(0xffffffffu, v[g].x, off);
+                    v[g].y += __shfl_xor_sync(0xffffffffu, v[g].y, off);
+                }
+        }
+        cp_async_wait<kOpDepth - 1>();                        // this step's gi has landed
+        if (gate) {
+            const float* o = my_ops + (size_t)(step % kOpDepth) * (kSlotStride / 4);
+            const float g0 = (r == 0 ? v[0].x : v[0].y) + bias[0];
+            const float g1 = (r == 0 ? v[1].x : v[1].y) + bias[1];
+            const float g2 = (r == 0 ? v[2].x : v[2].y) + bias[2];
+            const float rr = fast_sigmoid(o[0] + g0);
+            const float z = fast_sigmoid(o[kOpStride / 4] + g1);
+            const float n = fast_tanh(fmaf(rr, g2, o[2 * (kOpStride / 4)]));
+            hprev = fmaf(z, hprev - n, n);
+            h_s[cur ^ 1][j][r] = hprev;
+            out[io] = hprev;
+            gates[is] = rr; gates[is + H] = z; gates[is + 2 * H] = n; gates[is + 3 * H] = g2;
+            io += (int)dOut; is += (int)dGs;
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+}
+
+__global__ void __launch_bounds__(512, 1)
+gru_scan_fwd_tile128_kernel(const float* __restrict__ gi, const float* __restrict__ whh, const float* __restrict__ bhh,
+                            float* __restrict__ out, float* __restrict__ gates, int B, int T) {
+    __shared__ __align__(16) float h_s[2][128][2];            // [buffer][hidden unit][row]
+    __shared__ float ops[kOpDepth][3][128][2];                // cp.async ring of gi
+    if (blockIdx.y == 0) gru_fwd_tile128_body<false>(gi, whh, bhh, out, gates, B, T, h_s, ops);
+    else gru_fwd_tile128_body<true>(gi, whh, bhh, out, gates, B, T, h_s, ops);
+}
+
 template <int H>
 int launch_warp_fwd(const float* gi, const float* whh, const float* bhh, float* out, float* gates, int B, int T,
                     cudaStream_t st) {
@@ -944,8 +1067,9 @@ int gru_scan_forward(const float* gi, const float* whh, const float* bhh, float*
     if (H == 16) return launch_warp_fwd<16>(gi, whh, bhh, out, gates, B, T, st);
     if (H == 8) return launch_warp_fwd<8>(gi, whh, bhh, out, gates, B, T, st);
     if (H == 128 || H == 64) {
+        SED_REQUIRE((long)B * T * 2 * 4 * H < (1L << 31), SEDB200_ESHAPE, "gru_scan: B*T too large for H=%d (B=%d T=%d)", H, B, T);
         dim3 grid((B + kSplitBT - 1) / kSplitBT, 2);
-        if (H == 128) gru_scan_fwd_split_kernel<128><<<grid, 512, 0, st>>>(gi, whh, bhh, out, gates, B, T);
+        if (H == 128) gru_scan_fwd_tile128_kernel<<<grid, 512, 0, st>>>(gi, whh, bhh, out, gates, B, T);
         else gru_scan_fwd_split_kernel<64><<<grid, 256, 0, st>>>(gi, whh, bhh, out, gates, B, T);
         SED_POST_LAUNCH();
         return SEDB200_OK;
@@ -978,6 +1102,7 @@ int gru_scan_backward(const float* dout, const float* out, const float* gates, c
     if (H == 16) return launch_warp_bwd<16>(dout, out, gates, whh, dgi, dgh, part_w, part_b, B, T, st);
     if (H == 8) return launch_warp_bwd<8>(dout, out, gates, whh, dgi, dgh, part_w, part_b, B, T, st);
     if (H == 128 || H == 64) {
+        SED_REQUIRE((long)B * T * 2 * 4 * H < (1L << 31), SEDB200_ESHAPE, "gru_scan: B*T too large for H=%d (B=%d T=%d)", H, B, T);
         dim3 grid((B + kSplitBT - 1) / kSplitBT, 2);
         if (H == 128) gru_scan_bwd_tile128_kernel<<<grid, 512, 0, st>>>(dout, out, gates, whh, dgi, dgh, part_b, B, T);
         else gru_scan_bwd_split_kernel<64><<<grid, 256, 0, st>>>(dout, out, gates, whh, dgi, dgh, part_b, B, T);
