@@ -272,7 +272,7 @@ def other_configs_leg(torch, config, engine, main_config):
     """The BASELINE configs that are not the bench line (parity-test cases), timed for reference on one GPU:
     device-resident batches, CUDA events, 3 warm-up + 5 timed steps each.  Informational only."""
     out = {}
-    for name, B in (("c1", 128), ("c5", 128)):
+    for name, B in (("c1", 128), ("c5", 128), ("fork", 128)):
         if name == main_config:
             continue
         try:

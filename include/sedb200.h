@@ -276,6 +276,21 @@ size_t sedb200_conv3x3_wgrad_tc_scratch_bytes(int B, int H, int W, int Cin, int 
 int    sedb200_conv3x3_wgrad_tc(const float* dy_dev, const float* in_dev, float* dw_dev, int B, int H, int W,
                                 int Cin, int Cout, void* scratch_dev, size_t scratch_bytes, void* stream);
 
+/* Small-channel direct 3x3 convolutions (<= 64 channels: the reference's shipped CONV_DEPTH = 16,
+ * train_constants.py), exposed for unit tests.  `in` is read through strides (element b*sB + h*sH + w*sW + k*sC), so
+ * NCHW user input and channels-last activations both work; outputs are channels-last.
+ *   forward (dgrad = 0): out [B][H][W][N] = conv(in [K channels], weight [N][K][3][3]) + bias
+ *   data gradient (dgrad = 1): in = dY with K = Cout channels, weight = the forward weight [K][N][3][3], out = dX
+ *   weight gradient: dw [N][K][3][3] from dy [B][H][W][N] and the conv input (K channels). */
+int    sedb200_conv3x3_small_supported(int K, int N, int W, int wgrad);
+int    sedb200_conv3x3_small(const float* in_dev, long sB, long sH, long sW, long sC, int K, int B, int H, int W,
+                             const float* weight_dev, const float* bias_dev, int N, int dgrad, float* out_dev,
+                             void* stream);
+size_t sedb200_conv3x3_small_wgrad_scratch_bytes(int K, int N, int B, int H);
+int    sedb200_conv3x3_small_wgrad(const float* dy_dev, const float* in_dev, long sB, long sH, long sW, long sC, int K,
+                                   int N, int B, int H, int W, float* dw_dev, void* scratch_dev, size_t scratch_bytes,
+                                   void* stream);
+
 /* Plain GEMM on tcgen05 with the same 3-term bf16 split (unit-test entry for the kernel behind the GRU input
  * projections, crnn_lightning.py:61-62 / sed.py:101, and their gradients):
  *   out[M][N] (+bias[N]) = sum_k A(m,k) * B(n,k),   a_mn / b_mn: 0 = operand stored [rows][K], 1 = stored [K][rows].

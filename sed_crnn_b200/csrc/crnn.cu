@@ -9,6 +9,7 @@
 #include <cuda_bf16.h>
 #include "crnn_plan.cuh"
 #include "gemm_simt.cuh"
+#include "conv_small.cuh"
 #include "gru_scan.cuh"
 #include "tc_conv.cuh"
 #include "tc_gemm.cuh"
@@ -1157,6 +1158,10 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
             rc = conv_tc_forward(in, params + P.conv_w[i], params + P.conv_b[i], y, batch, P.H, P.win[i], P.cin[i], P.C,
                                  0, wsf(ws, P.tc), P.tc_bytes, st);
             if (rc) return rc;
+        } else if (conv_small_supported(P.cin[i], P.C, P.win[i])) {
+            rc = conv_small_forward(in, s.sB, s.sH, s.sW, s.sC, P.cin[i], batch, P.H, P.win[i], params + P.conv_w[i],
+                                    params + P.conv_b[i], P.C, 0, y, st);
+            if (rc) return rc;
         } else {
             rc = gemm_simt(M, P.C, K, 1, ConvFwdA{in, P.H, P.win[i], P.cin[i], s.sB, s.sH, s.sW, s.sC},
                            ConvFwdB{params + P.conv_w[i], P.cin[i]}, EpiStore{y, P.C, params + P.conv_b[i], 0}, st);
@@ -1518,6 +1523,11 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         } else if (i > 0 && d->tensor_cores && wgrad_tc_supported(P.H, P.win[i], P.cin[i], P.C)) {
             rc = wgrad_tc(dy, in, grads + P.conv_w[i], batch, P.H, P.win[i], P.cin[i], P.C, wsf(ws, P.tc), P.tc_bytes, st);
             if (rc) return rc;
+        } else if (conv_small_wgrad_supported(P.cin[i], P.C, P.win[i]) &&
+                   conv_small_wgrad_part_floats(P.cin[i], P.C, batch, P.H) <= P.part_floats) {
+            rc = conv_small_wgrad(dy, in, s.sB, s.sH, s.sW, s.sC, P.cin[i], P.C, batch, P.H, P.win[i], part,
+                                  grads + P.conv_w[i], st);
+            if (rc) return rc;
         } else {
         rc = gemm_simt(P.C, J, M, want, ColMajor{dy, P.C}, ConvWgradB{in, P.H, P.win[i], s.sB, s.sH, s.sW, s.sC},
                        EpiPartial{part, (long)P.C * J, J}, st);
@@ -1536,6 +1546,9 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
             else if (d->tensor_cores && conv_tc_supported(P.H, P.win[i], P.C, P.cin[i]))
                 rc = conv_tc_forward(dy, params + P.conv_w[i], nullptr, dprev, batch, P.H, P.win[i], P.cin[i], P.C, 1,
                                      wsf(ws, P.tc), P.tc_bytes, st);
+            else if (conv_small_supported(P.C, P.cin[i], P.win[i]))
+                rc = conv_small_forward(dy, (long)P.H * P.win[i] * P.C, (long)P.win[i] * P.C, P.C, 1, P.C, batch, P.H,
+                                        P.win[i], params + P.conv_w[i], nullptr, P.cin[i], 1, dprev, st);
             else
                 rc = gemm_simt(M, P.cin[i], 9 * P.C, 1, ConvDgradA{dy, P.H, P.win[i], P.C},
                                ConvDgradB{params + P.conv_w[i], P.cin[i], P.C}, EpiStore{dprev, P.cin[i], nullptr, 0}, st);

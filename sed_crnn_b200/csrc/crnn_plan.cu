@@ -1,6 +1,7 @@
 // crnn_plan.cu -- host-side geometry / layout helpers of the CRNN C ABI (no GPU needed).
 #include "crnn_plan.cuh"
 #include "gru_scan.cuh"
+#include "conv_small.cuh"
 #include "gemm_simt.cuh"
 #include "tc_conv.cuh"
 #include "tc_gemm.cuh"
@@ -141,6 +142,9 @@ int make_plan(const sedb200_crnn_desc* d, int batch, Plan* p) {
     part = std::max(part, 148L * 16 * 2 * P.C);
     for (int i = 1; i < P.n_conv; ++i) part = std::max(part, 2L * P.C * B * ((P.H * P.win[i] + 127) / 128 + 1));   // conv-epilogue BN partials                                                 // BN backward sums
     if (head_fused_supported(P)) part = std::max(part, (long)head_fused_part_floats(P, (int)B));   // fused head partials
+    for (int i = 0; i < P.n_conv; ++i)                                                            // small-channel wgrad partials
+        if (conv_small_wgrad_supported(P.cin[i], P.C, P.win[i]))
+            part = std::max(part, (long)conv_small_wgrad_part_floats(P.cin[i], P.C, (int)B, P.H));
     P.part_floats = (size_t)part;
     P.part = take(part);
     // plane-native tensor-core blocks
