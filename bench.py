@@ -80,6 +80,10 @@ def phase_model(cfg, B, per):
         if i == 0:
             m["conv0.fwd"] = ("hbm", y + xin, "conv0_fwd_stats_kernel (direct fp32 conv + BN statistics)")
             m["conv0.bwd_fused"] = ("hbm", y + a + xin, "conv0_bwd_fused_t_kernel (BN/ReLU/pool backward + wgrad, dy never written)")
+            # lean block 0 (conv output never stored): input + pooled output + one winner byte per output element
+            m["conv0.stats"] = ("hbm", xin, "conv0_gram_kernel (patch moments of the input -> BatchNorm statistics)")
+            m["conv0.fwd_fused"] = ("hbm", xin + a + a / 4, "conv0_lean_fwd_kernel (conv + BN + ReLU + max-pool + dropout in registers)")
+            m["conv0.bwd_lean"] = ("hbm", xin + a + a / 4, "conv0_lean_bwd_kernel (winner contributions to dW / d gamma / d beta)")
         elif tc_ok:
             for ph, kn in (("fwd", "conv_tc_kernel"), ("dgrad", "conv_tc_kernel"), ("wgrad", "wgrad_tc_kernel")):
                 m[f"conv{i}.{ph}"] = ("tensor", per[f"conv{i}"], f"{kn} (tcgen05 implicit GEMM, 3-term bf16 split) + bf16 plane split")

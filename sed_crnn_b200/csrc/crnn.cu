@@ -992,6 +992,372 @@ __global__ void conv0_bwd_reduce_kernel(const float* __restrict__ part, int nblk
 inline bool conv0_direct_ok(int cin, int C) { return (cin == 1 || cin == 2) && C % 128 == 0; }
 inline long conv0_blocks(int B, int H) { return (long)B * ((H + kC0Rows - 1) / kC0Rows); }
 
+// ----------------------------------------------------------------------------- first conv block, lean
+// The output of conv 0 (4 B x B*H*W*C: 671 MB at C2, 10.7 GB at C5) is the largest tensor of the step, and
+// with K = 9*Cin <= 18 it is also the cheapest one to describe.  This path never writes or reads it:
+//
+//   * BatchNorm statistics of y = w.patch + b are a function of the first two moments of the PATCHES:
+//         mean_c = b_c + w_c.m,   var_c = w_c^T (G - m m^T) w_c,   m = E[patch], G = E[patch patch^T]  (K x K)
+//     so one pass over the INPUT (conv0_gram_kernel) replaces the statistics pass over y.
+//   * The forward kernel knows scale / shift before it starts: conv + BN + ReLU + max-pool + dropout happen in
+//     registers; it writes the pooled block output and one byte per (window, channel): the winner's position in
+//     the window, bit 7 set when the ReLU or the dropout killed the window.
+//   * Backward: dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)) is dense in the pixels, but the only dense
+//     terms are (constant) and (xhat): sum_pix patch_k and sum_pix xhat*patch_k follow from (m, G) again.  What
+//     needs the data is S_k = sum over WINDOWS of dz * patch_k(winner) (one pixel in p), and
+//     sum dz*xhat(winner) = invstd * (b*sum dz + w.S - mean*sum dz) needs nothing else.  So one kernel reads
+//     dA + the winner bytes + the input rows, and a per-channel finalizer closes d(gamma), d(beta) and dW.
+//     The conv bias gradient through train-mode BatchNorm is identically zero and is written as 0.
+//
+// HBM traffic of block 0 at C2: forward |x| + |a| + |a|/4 = 178 MB (was 671 MB written + 805 MB read back),
+// backward |dA| + |a|/4 + |x| = 178 MB (was 268 + 816 MB).
+template <int CIN>
+struct GramDims {
+    static constexpr int K = CIN * 9, KR = CIN * 3, NA = KR * (K + 1);   // a team (kernel row r) owns KR patch entries
+};
+constexpr int kGramTeam = 96, kGramThreads = 3 * kGramTeam;
+
+// part[blk][team r][a = ci*3 + t][k'] = sum over the block's pixels of patch[ci*9 + r*3 + t] * patch[k']
+// (k' = K: the plain sum).  Per-thread fp32 sums of ~50 products, fixed-order tree per block, doubles afterwards.
+template <int CIN>
+__global__ void __launch_bounds__(kGramThreads)
+conv0_gram_kernel(const float* __restrict__ x, int H, int W, int groups_per_img, int n_groups, float* __restrict__ part) {
+    using D = GramDims<CIN>;
+    extern __shared__ float xs_all[];                     // 2 x [CIN][10][W+2]
+    __shared__ float red[kGramThreads / 32][D::NA];
+    const int team = threadIdx.x / kGramTeam, tt = threadIdx.x % kGramTeam;
+    const int Wp = W + 2, xsz = CIN * (kC0Rows + 2) * Wp;
+    float acc[D::KR][D::K + 1];
+#pragma unroll
+    for (int a = 0; a < D::KR; ++a)
+#pragma unroll
+        for (int k = 0; k <= D::K; ++k) acc[a][k] = 0.0f;
+    int grp = blockIdx.x, buf = 0;
+    if (grp < n_groups) load_x_rows<CIN>(x, xs_all, grp / groups_per_img, (grp % groups_per_img) * kC0Rows, H, W);
+    __syncthreads();
+    for (; grp < n_groups; grp += gridDim.x, buf ^= 1) {
+        const float* xs = xs_all + buf * xsz;
+        const int h0 = (grp % groups_per_img) * kC0Rows;
+        const int nxt = grp + gridDim.x;
+        if (nxt < n_groups)
+            load_x_rows<CIN>(x, xs_all + (buf ^ 1) * xsz, nxt / groups_per_img, (nxt % groups_per_img) * kC0Rows, H, W);
+        const int npix = min(kC0Rows, H - h0) * W;
+        for (int p = tt; p < npix; p += kGramTeam) {
+            const int row = p / W, col = p - row * W;
+            const float* base = xs + row * Wp + col;
+            float pv[D::K], own[D::KR];
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) pv[ci * 9 + r * 3 + t] = base[(ci * (kC0Rows + 2) + r) * Wp + t];
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+                for (int t = 0; t < 3; ++t) own[ci * 3 + t] = base[(ci * (kC0Rows + 2) + team) * Wp + t];
+#pragma unroll
+            for (int a = 0; a < D::KR; ++a) {
+#pragma unroll
+                for (int k = 0; k < D::K; ++k) acc[a][k] = fmaf(own[a], pv[k], acc[a][k]);
+                acc[a][D::K] += own[a];
+            }
+        }
+        __syncthreads();
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int a = 0; a < D::KR; ++a)
+#pragma unroll
+        for (int k = 0; k <= D::K; ++k) {
+            float v = acc[a][k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) red[warp][a * (D::K + 1) + k] = v;
+        }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 3 * D::NA; e += kGramThreads) {
+        const int tm = e / D::NA, i = e - tm * D::NA;
+        part[(long)blockIdx.x * 3 * D::NA + e] = red[3 * tm][i] + red[3 * tm + 1][i] + red[3 * tm + 2][i];
+    }
+}
+
+// gram[k][k'] (k' <= K, doubles, divided by the pixel count): one warp per entry, fixed order
+__global__ void conv0_gram_reduce_kernel(const float* __restrict__ part, int nblk, int cin, double inv_n,
+                                         double* __restrict__ gram) {
+    const int K = cin * 9, KR = cin * 3, NA = KR * (K + 1);
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (e >= 3 * NA) return;
+    double a = 0.0;
+    for (int b = lane; b < nblk; b += 32) a += (double)__ldg(part + (long)b * 3 * NA + e);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+    if (lane == 0) {
+        const int team = e / NA, i = e - team * NA, aidx = i / (K + 1), kp = i - aidx * (K + 1);
+        const int ci = aidx / 3, t = aidx - ci * 3;
+        gram[(ci * 9 + team * 3 + t) * (K + 1) + kp] = a * inv_n;
+    }
+}
+
+// BatchNorm statistics of conv 0 from the patch moments; same outputs as bn_finalize_train_kernel
+__global__ void __launch_bounds__(128)
+conv0_bn_finalize_kernel(const double* __restrict__ gram, int cin, int C, long n, const float* __restrict__ w,
+                         const float* __restrict__ bias, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running,
+                         float* __restrict__ stat) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, K = cin * 9;
+    if (c >= C) return;
+    const float* wc = w + (long)c * K;
+    double mean = (double)bias[c], var = 0.0;
+    for (int k = 0; k < K; ++k) {
+        const double mk = gram[k * (K + 1) + K], wk = (double)wc[k];
+        mean += wk * mk;
+        double row = 0.0;
+        for (int k2 = 0; k2 < K; ++k2) row += (double)wc[k2] * (gram[k * (K + 1) + k2] - mk * gram[k2 * (K + 1) + K]);
+        var += wk * row;
+    }
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * invstd;
+    stat[c] = (float)mean;
+    stat[C + c] = invstd;
+    stat[2 * C + c] = sc;
+    stat[3 * C + c] = beta[c] - (float)mean * sc;
+    const double unbiased = n > 1 ? var * (double)n / (double)(n - 1) : var;
+    running[c] = (1.0f - momentum) * running[c] + momentum * (float)mean;
+    running[C + c] = (1.0f - momentum) * running[C + c] + momentum * (float)unbiased;
+}
+
+// conv + bias -> BN -> ReLU -> max-pool(1,P) -> dropout in registers.  Same thread mapping, input staging and
+// accumulation order as conv0_fwd_stats_kernel (y is bit-identical to what that kernel would have stored).
+template <int CIN, int P>
+__global__ void __launch_bounds__(256)
+conv0_lean_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                      const float* __restrict__ stat, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
+                      __nv_bfloat16* __restrict__ out_lo, unsigned* __restrict__ argw, PoolGeom g, int groups_per_img,
+                      int n_groups) {
+    extern __shared__ float xs_all[];                     // 2 x [CIN][10][W+2]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c4 = blockIdx.y * 32 + lane, c = c4 * 4, C4 = g.C >> 2, Wp = g.W + 2, xsz = CIN * (kC0Rows + 2) * Wp;
+    float2 wr[2][CIN * 9], bs[2], sc[2], sh[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        bs[q] = make_float2(__ldg(bias + c + 2 * q), __ldg(bias + c + 2 * q + 1));
+        sc[q] = make_float2(__ldg(stat + 2 * g.C + c + 2 * q), __ldg(stat + 2 * g.C + c + 2 * q + 1));
+        sh[q] = make_float2(__ldg(stat + 3 * g.C + c + 2 * q), __ldg(stat + 3 * g.C + c + 2 * q + 1));
+#pragma unroll
+        for (int k = 0; k < CIN * 9; ++k)
+            wr[q][k] = make_float2(__ldg(w + (long)(c + 2 * q) * CIN * 9 + k), __ldg(w + (long)(c + 2 * q + 1) * CIN * 9 + k));
+    }
+    const float keep_scale = g.drop_p > 0.0f ? 1.0f / (1.0f - g.drop_p) : 1.0f;
+    int grp = blockIdx.x, buf = 0;
+    if (grp < n_groups) load_x_rows<CIN>(x, xs_all, grp / groups_per_img, (grp % groups_per_img) * kC0Rows, g.H, g.W);
+    __syncthreads();
+    for (; grp < n_groups; grp += gridDim.x, buf ^= 1) {
+        const float* xs = xs_all + buf * xsz;
+        const int b = grp / groups_per_img, h0 = (grp % groups_per_img) * kC0Rows;
+        const int nxt = grp + gridDim.x;
+        if (nxt < n_groups)
+            load_x_rows<CIN>(x, xs_all + (buf ^ 1) * xsz, nxt / groups_per_img, (nxt % groups_per_img) * kC0Rows, g.H, g.W);
+        const int h = h0 + warp;
+        if (h < g.H) {
+            for (int wo = 0; wo < g.Wo; ++wo) {
+                float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                unsigned arg[4] = {0u, 0u, 0u, 0u};
+                auto consider = [&](int j, const float2 a01, const float2 a23) {
+                    const float2 z01 = __ffma2_rn(a01, sc[0], sh[0]), z23 = __ffma2_rn(a23, sc[1], sh[1]);
+                    const float z[4] = {z01.x, z01.y, z23.x, z23.y};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (z[q] > best[q]) { best[q] = z[q]; arg[q] = (unsigned)j; }      // first maximum wins
+                };
+#pragma unroll
+                for (int j = 0; j + 1 < P; j += 2) {
+                    const int ww = wo * P + j;
+                    float2 acc[2][2] = {{bs[0], bs[1]}, {bs[0], bs[1]}};
+#pragma unroll
+                    for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) {
+                            const float* xr = xs + (ci * (kC0Rows + 2) + warp + r) * Wp + ww;
+                            float xc[4];
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) xc[t] = xr[t];
+#pragma unroll
+                            for (int t = 0; t < 3; ++t) {
+                                const float2 x0 = make_float2(xc[t], xc[t]), x1 = make_float2(xc[t + 1], xc[t + 1]);
+                                acc[0][0] = __ffma2_rn(wr[0][ci * 9 + r * 3 + t], x0, acc[0][0]);
+                                acc[0][1] = __ffma2_rn(wr[1][ci * 9 + r * 3 + t], x0, acc[0][1]);
+                                acc[1][0] = __ffma2_rn(wr[0][ci * 9 + r * 3 + t], x1, acc[1][0]);
+                                acc[1][1] = __ffma2_rn(wr[1][ci * 9 + r * 3 + t], x1, acc[1][1]);
+                            }
+                        }
+                    consider(j, acc[0][0], acc[0][1]);
+                    consider(j + 1, acc[1][0], acc[1][1]);
+                }
+                if (P & 1) {
+                    const int ww = wo * P + P - 1;
+                    float2 acc[2] = {bs[0], bs[1]};
+#pragma unroll
+                    for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+                        for (int r = 0; r < 3; ++r)
+#pragma unroll
+                            for (int t = 0; t < 3; ++t) {
+                                const float xv = xs[(ci * (kC0Rows + 2) + warp + r) * Wp + ww + t];
+                                const float2 x2 = make_float2(xv, xv);
+                                acc[0] = __ffma2_rn(wr[0][ci * 9 + r * 3 + t], x2, acc[0]);
+                                acc[1] = __ffma2_rn(wr[1][ci * 9 + r * 3 + t], x2, acc[1]);
+                            }
+                    consider(P - 1, acc[0], acc[1]);
+                }
+                const long pix = ((long)b * g.H + h) * g.Wo + wo;
+                const long i = pix * C4 + c4;                      // element numbering of the pool kernels (dropout)
+                Keep4 kp;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) kp.k[q] = true;
+                if (g.drop_p > 0.0f) kp = dropout_keep4(g.seed, (unsigned long long)i, g.drop_p);
+                float m[4];
+                unsigned word = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool alive = best[q] > 0.0f && kp.k[q];
+                    m[q] = alive ? best[q] * keep_scale : 0.0f;
+                    word |= (arg[q] | (alive ? 0u : 0x80u)) << (8 * q);
+                }
+                const float4 m4 = make_float4(m[0], m[1], m[2], m[3]);
+                if (argw) argw[i] = word;
+                if (out_hi) store_planes4(out_hi, out_lo, i, m4);
+                if (out) {
+                    float* dst = out + (long)b * g.oB + (long)h * g.oH + (long)wo * g.oW + (long)c * g.oC;
+                    if (g.oC == 1) {
+                        *reinterpret_cast<float4*>(dst) = m4;
+                    } else {
+                        dst[0] = m[0]; dst[g.oC] = m[1]; dst[2 * g.oC] = m[2]; dst[3 * g.oC] = m[3];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// S[k][c] = sum over windows of dz * patch_k(winner), S[K][c] = sum dz; part layout [nblk][K+1][C]
+template <int CIN, int P>
+__global__ void __launch_bounds__(256)
+conv0_lean_bwd_kernel(const float* __restrict__ x, const unsigned* __restrict__ argw, const float* __restrict__ dA,
+                      PoolGeom g, int groups_per_img, int n_groups, float* __restrict__ part) {
+    constexpr int K = CIN * 9;
+    extern __shared__ float xs_all[];                     // 2 x [CIN][10][W+2]
+    __shared__ float red[kC0Rows][128];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c4 = blockIdx.y * 32 + lane, c = c4 * 4, C4 = g.C >> 2, Wp = g.W + 2, xsz = CIN * (kC0Rows + 2) * Wp;
+    const float keep_scale = g.drop_p > 0.0f ? 1.0f / (1.0f - g.drop_p) : 1.0f;
+    float acc[4][K + 1];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int k = 0; k <= K; ++k) acc[q][k] = 0.0f;
+    int grp = blockIdx.x, buf = 0;
+    if (grp < n_groups) load_x_rows<CIN>(x, xs_all, grp / groups_per_img, (grp % groups_per_img) * kC0Rows, g.H, g.W);
+    __syncthreads();
+    for (; grp < n_groups; grp += gridDim.x, buf ^= 1) {
+        const float* xs = xs_all + buf * xsz;
+        const int b = grp / groups_per_img, h0 = (grp % groups_per_img) * kC0Rows;
+        const int nxt = grp + gridDim.x;
+        if (nxt < n_groups)
+            load_x_rows<CIN>(x, xs_all + (buf ^ 1) * xsz, nxt / groups_per_img, (nxt % groups_per_img) * kC0Rows, g.H, g.W);
+        const int h = h0 + warp;
+        if (h < g.H) {
+            const unsigned* arow = argw + (((long)b * g.H + h) * g.Wo) * C4 + c4;
+            const float* darow = dA + (long)b * g.oB + (long)h * g.oH + (long)c * g.oC;
+            const float* xrow = xs + warp * Wp;
+            unsigned word = __ldg(arow), wordn = 0;
+            float gq[4], gn[4] = {0, 0, 0, 0};
+            load_dA(darow, g.oC, gq);
+            for (int wo = 0; wo < g.Wo; ++wo) {
+                if (wo + 1 < g.Wo) {
+                    wordn = __ldg(arow + (long)(wo + 1) * C4);
+                    load_dA(darow + (long)(wo + 1) * g.oW, g.oC, gn);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const unsigned by = (word >> (8 * q)) & 0xFFu;
+                    const float dz = (by & 0x80u) ? 0.0f : gq[q] * keep_scale;
+                    const float* base = xrow + wo * P + (int)(by & 0x7Fu);
+#pragma unroll
+                    for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+                        for (int r = 0; r < 3; ++r)
+#pragma unroll
+                            for (int t = 0; t < 3; ++t)
+                                acc[q][ci * 9 + r * 3 + t] =
+                                    fmaf(dz, base[(ci * (kC0Rows + 2) + r) * Wp + t], acc[q][ci * 9 + r * 3 + t]);
+                    acc[q][K] += dz;
+                }
+                word = wordn;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) gq[q] = gn[q];
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k <= K; ++k) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) red[warp][lane * 4 + q] = acc[q][k];
+        __syncthreads();
+        if (threadIdx.x < 128) {
+            float t = 0.0f;
+#pragma unroll
+            for (int r = 0; r < kC0Rows; ++r) t += red[r][threadIdx.x];
+            part[((long)blockIdx.x * (K + 1) + k) * g.C + blockIdx.y * 128 + threadIdx.x] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// one block per channel: d(beta), d(gamma), dW of conv 0 (and its zero bias gradient) from S, the patch
+// moments and the forward statistics
+__global__ void __launch_bounds__(128)
+conv0_lean_bwd_finalize_kernel(const float* __restrict__ part, int nblk, int cin, int C, const double* __restrict__ gram,
+                               const float* __restrict__ w, const float* __restrict__ bias,
+                               const float* __restrict__ gamma, const float* __restrict__ stat,
+                               float* __restrict__ dw, float* __restrict__ db, float* __restrict__ dgamma,
+                               float* __restrict__ dbeta) {
+    __shared__ double S[32];
+    const int c = blockIdx.x, K = cin * 9, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = warp; k <= K; k += 4) {
+        double a = 0.0;
+        for (int b = lane; b < nblk; b += 32) a += (double)__ldg(part + ((long)b * (K + 1) + k) * C + c);
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+        if (lane == 0) S[k] = a;
+    }
+    __syncthreads();
+    const int k = threadIdx.x;
+    if (k >= K) return;
+    const float* wc = w + (long)c * K;
+    const double mean = (double)stat[c], invstd = (double)stat[C + c], bc = (double)bias[c];
+    const double sum_dz = S[K];
+    double sum_dz_y = bc * sum_dz, wg = 0.0;
+    for (int k2 = 0; k2 < K; ++k2) {
+        sum_dz_y += (double)wc[k2] * S[k2];
+        wg += (double)wc[k2] * gram[k2 * (K + 1) + k];                 // G is symmetric
+    }
+    const double dg = invstd * (sum_dz_y - mean * sum_dz);             // sum dz * xhat
+    const double mk = gram[k * (K + 1) + K];
+    const double tk = invstd * (wg + (bc - mean) * mk);                // mean over pixels of xhat * patch_k
+    dw[(long)c * K + k] = (float)((double)gamma[c] * invstd * (S[k] - sum_dz * mk - dg * tk));
+    if (k == 0) {
+        dgamma[c] = (float)dg;
+        dbeta[c] = (float)sum_dz;
+        db[c] = 0.0f;
+    }
+}
+
+inline bool conv0_lean_ok(int cin, int C, int pool) { return conv0_direct_ok(cin, C) && (pool == 5 || pool == 2); }
+
 
 // ----------------------------------------------------------------------------- small dense layers, backward
 // The per-frame dense head is tiny (e.g. 64 -> 16 -> 6): one kernel per layer produces d(input) for its 128
@@ -1134,6 +1500,48 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
         float* running = bn_state + 2L * i * P.C;
         const bool direct0 = (i == 0) && conv0_direct_ok(P.cin[0], P.C);
         int nblk = 0;
+        if (i == 0 && conv0_lean_ok(P.cin[0], P.C, P.pool[0])) {
+            // lean block 0: statistics from the patch moments of the input, then one fused kernel; y0 is never stored
+            const int gpi = (P.H + kC0Rows - 1) / kC0Rows, n_groups = gpi * batch;
+            const size_t sm = 2 * (size_t)P.cin[0] * (kC0Rows + 2) * (P.win[0] + 2) * 4;
+            const int cin0 = P.cin[0], K0 = 9 * cin0;
+            double* gram = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + P.gram);
+            {
+                SED_PROF("conv0.stats", st);
+                if (training) {
+                    const int gblk = std::min(n_groups, 2 * sm_count());
+                    if (cin0 == 1) conv0_gram_kernel<1><<<gblk, kGramThreads, sm, st>>>(x, P.H, P.win[0], gpi, n_groups, wsf(ws, P.part));
+                    else conv0_gram_kernel<2><<<gblk, kGramThreads, sm, st>>>(x, P.H, P.win[0], gpi, n_groups, wsf(ws, P.part));
+                    SED_POST_LAUNCH();
+                    const int entries = 3 * (3 * cin0) * (K0 + 1);
+                    conv0_gram_reduce_kernel<<<(entries * 32 + 255) / 256, 256, 0, st>>>(
+                        wsf(ws, P.part), gblk, cin0, 1.0 / (double)M, gram);
+                    SED_POST_LAUNCH();
+                    conv0_bn_finalize_kernel<<<(P.C + 127) / 128, 128, 0, st>>>(
+                        gram, cin0, P.C, (long)M, params + P.conv_w[0], params + P.conv_b[0], params + P.bn_w[0],
+                        params + P.bn_b[0], d->bn_eps, d->bn_momentum, running, stat);
+                } else {
+                    bn_finalize_eval_kernel<<<(P.C + 127) / 128, 128, 0, st>>>(P.C, params + P.bn_w[0], params + P.bn_b[0],
+                                                                               d->bn_eps, running, stat);
+                }
+                SED_POST_LAUNCH();
+            }
+            SED_PROF("conv0.fwd_fused", st);
+            const PoolGeom g = pool_geom(P, d, 0, training, seed);
+            const bool to_planes = (P.n_conv > 1) && P.conv_tc_all[1];
+            __nv_bfloat16* ph = to_planes ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(ws) + P.actp[0]) : nullptr;
+            __nv_bfloat16* pl = to_planes ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(ws) + P.actp[0] + P.act_plane_bytes[0]) : nullptr;
+            float* of = to_planes ? nullptr : wsf(ws, P.act[0]);
+            unsigned* argw = training ? reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + P.arg0) : nullptr;
+            const dim3 grid(std::min(n_groups, 2 * sm_count()), P.C / 128);
+            const float *w0 = params + P.conv_w[0], *b0 = params + P.conv_b[0];
+            if (cin0 == 1 && g.p == 5) conv0_lean_fwd_kernel<1, 5><<<grid, 256, sm, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, gpi, n_groups);
+            else if (cin0 == 1) conv0_lean_fwd_kernel<1, 2><<<grid, 256, sm, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, gpi, n_groups);
+            else if (g.p == 5) conv0_lean_fwd_kernel<2, 5><<<grid, 256, sm, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, gpi, n_groups);
+            else conv0_lean_fwd_kernel<2, 2><<<grid, 256, sm, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, gpi, n_groups);
+            SED_POST_LAUNCH();
+            continue;
+        }
         { char _nm[40]; snprintf(_nm, sizeof _nm, "conv%d.fwd", i); SED_PROF(_nm, st);
         if (direct0) {
             const int gpi = (P.H + kC0Rows - 1) / kC0Rows, n_groups = gpi * batch;
@@ -1439,6 +1847,39 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         const PoolGeom g = pool_geom(P, d, i, 1, seed);
         const float* y = wsf(ws, P.y[i]);
         const float* stat = wsf(ws, P.stat[i]);
+        if (i == 0 && conv0_lean_ok(P.cin[0], P.C, P.pool[0])) {
+            const int gpi = (P.H + kC0Rows - 1) / kC0Rows, n_groups = gpi * batch;
+            const size_t sm = 2 * (size_t)P.cin[0] * (kC0Rows + 2) * (P.win[0] + 2) * 4;
+            const int cin0 = P.cin[0], K0 = 9 * cin0;
+            if (!dx) {
+                // lean block 0: winners' contributions from dA + winner bytes + input rows, the dense terms from
+                // the patch moments the forward pass left in the workspace
+                SED_PROF("conv0.bwd_lean", st);
+                const unsigned* argw = reinterpret_cast<const unsigned*>(reinterpret_cast<const char*>(ws) + P.arg0);
+                const double* gram = reinterpret_cast<const double*>(reinterpret_cast<const char*>(ws) + P.gram);
+                const dim3 grid(std::min(n_groups, sm_count()), P.C / 128);
+                if (cin0 == 1 && g.p == 5) conv0_lean_bwd_kernel<1, 5><<<grid, 256, sm, st>>>(x, argw, dA, g, gpi, n_groups, part);
+                else if (cin0 == 1) conv0_lean_bwd_kernel<1, 2><<<grid, 256, sm, st>>>(x, argw, dA, g, gpi, n_groups, part);
+                else if (g.p == 5) conv0_lean_bwd_kernel<2, 5><<<grid, 256, sm, st>>>(x, argw, dA, g, gpi, n_groups, part);
+                else conv0_lean_bwd_kernel<2, 2><<<grid, 256, sm, st>>>(x, argw, dA, g, gpi, n_groups, part);
+                SED_POST_LAUNCH();
+                conv0_lean_bwd_finalize_kernel<<<P.C, 128, 0, st>>>(
+                    part, (int)grid.x, cin0, P.C, gram, params + P.conv_w[0], params + P.conv_b[0], params + P.bn_w[0], stat,
+                    grads + P.conv_w[0], grads + P.conv_b[0], grads + P.bn_w[0], grads + P.bn_b[0]);
+                SED_POST_LAUNCH();
+                (void)K0;
+                break;
+            }
+            // the caller wants d(input): rebuild y0 (bit-identical to what the fused forward consumed) and take the
+            // general route below
+            SED_PROF("conv0.recompute_y", st);
+            const dim3 grid(std::min(n_groups, 2 * sm_count()), P.C / 128);
+            if (cin0 == 1)
+                conv0_fwd_stats_kernel<1><<<grid, 256, sm, st>>>(x, params + P.conv_w[0], params + P.conv_b[0], wsf(ws, P.y[0]), P.H, P.win[0], P.C, gpi, n_groups, part);
+            else
+                conv0_fwd_stats_kernel<2><<<grid, 256, sm, st>>>(x, params + P.conv_w[0], params + P.conv_b[0], wsf(ws, P.y[0]), P.H, P.win[0], P.C, gpi, n_groups, part);
+            SED_POST_LAUNCH();
+        }
         const long n_pix_out = B * P.H * P.wout[i];
         const long n_elem = B * P.H * P.win[i];                 // BN population per channel
         const int rows = 256 / (P.C / 4);

@@ -31,6 +31,9 @@ struct Plan {
     size_t hp_plane_bytes[SEDB200_MAX_GRU], dg_plane_bytes;
     size_t hid[SEDB200_MAX_DENSE];
     size_t dy, dact[2], dseq[2], dgi, dgh, dhid[2], part, bnsum, tc;
+    // lean block 0 (crnn.cu, "first conv block without its output tensor"): per-window winner bytes written by the
+    // fused forward kernel, and the K x (K+1) patch Gram matrix (doubles) both BatchNorm passes are derived from
+    size_t arg0 = 0, gram = 0;
     // plane-native tensor-core flow: block i (>= 1) runs fwd, dgrad and wgrad on tcgen05 and exchanges
     // bf16 hi/lo planes with its neighbours instead of fp32 tensors
     bool conv_tc_all[SEDB200_MAX_CONV];

@@ -320,3 +320,29 @@ def test_fused_head_matches_unfused_path(pkg, preset, loss):
         if it == 0:
             solid = a.grads.abs() > 1e-3 * scale
             assert torch.allclose(a.params[solid], b.params[solid], rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("preset,ov,batch", [("c1", {"seq_len": 32}, 5), ("c2", {"seq_len": 24}, 3)])
+def test_input_gradient_with_lean_block0(pkg, preset, ov, batch):
+    """Block 0 runs without storing its conv output (patch-moment BatchNorm statistics, winner bytes).  When the
+    caller asks for d(input) the backward pass rebuilds that tensor and takes the general route: d(input) must
+    match autograd, and both routes must produce the same parameter gradients."""
+    rcfg, ref, cfg, eng = make_pair(pkg, preset, ov, "bce", 1e-4, 1.0, tensor_cores=False)
+    x, y = R.synth_batch(rcfg, batch, seed=5)
+    xr = x.clone().requires_grad_(True)
+    ref.train()
+    R.loss_fn("bce")(ref(xr), y).backward()
+    xd, yd = x.cuda(), y.cuda()
+    logits = eng.forward(xd, training=True)
+    _, _, dlog = eng.loss_and_grad(logits, yd)
+    dx = torch.empty_like(xd)
+    g_general = eng.backward(xd, dlog, dx=dx).clone()
+    g_lean = eng.backward(xd, dlog).clone()
+    want = xr.grad
+    assert (dx.cpu() - want).abs().max().item() <= 2e-3 * want.abs().max().item()
+    va, vb = eng.views(g_general), eng.views(g_lean)
+    for name in va:
+        if name.startswith("conv") and name.endswith("bias"):
+            continue
+        err = (va[name] - vb[name]).norm().item() / max(va[name].norm().item(), 1e-12)
+        assert err <= 1e-3, (name, err)
