@@ -1011,58 +1011,113 @@ inline long conv0_blocks(int B, int H) { return (long)B * ((H + kC0Rows - 1) / k
 //
 // HBM traffic of block 0 at C2: forward |x| + |a| + |a|/4 = 178 MB (was 671 MB written + 805 MB read back),
 // backward |dA| + |a|/4 + |x| = 178 MB (was 268 + 816 MB).
+// ---- asynchronous, division-free staging of the input rows of one row group (8 rows + halo, zero-filled borders):
+// warp <-> (input channel, row), lane <-> column; 4-byte cp.async with src-size 0 for the zero fill
+__device__ __forceinline__ void cpa4_zfill(float* smem_dst, const float* gsrc, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int n = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cpa16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cpa_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int CIN>
+__device__ __forceinline__ void stage_x_rows_async(const float* __restrict__ x, float* xs, int b, int h0, int H, int W) {
+    const int Wp = W + 2, nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int rowid = warp; rowid < CIN * (kC0Rows + 2); rowid += nwarps) {
+        const int ci = rowid / (kC0Rows + 2), rr = rowid - ci * (kC0Rows + 2);      // constant divisor: no XU work
+        const int hh = h0 - 1 + rr;
+        const bool rowok = hh >= 0 && hh < H;
+        const float* src = x + (((long)b * CIN + ci) * H + (rowok ? hh : 0)) * W;
+        float* dst = xs + rowid * Wp;
+        for (int cc = lane; cc < Wp; cc += 32) {
+            const bool ok = rowok && cc >= 1 && cc <= W;
+            cpa4_zfill(dst + cc, src + (ok ? cc - 1 : 0), ok);
+        }
+    }
+}
+
+// (image, first row) of the row groups a persistent block walks, advanced without divisions
+struct GroupWalk {
+    int b, gi, step_b, step_g, gpi;
+    __device__ GroupWalk(int grp0, int stride, int groups_per_img) : gpi(groups_per_img) {
+        b = grp0 / gpi; gi = grp0 - b * gpi;
+        step_b = stride / gpi; step_g = stride - step_b * gpi;
+    }
+    __device__ void next() {
+        b += step_b; gi += step_g;
+        if (gi >= gpi) { gi -= gpi; ++b; }
+    }
+    __device__ int h0() const { return gi * kC0Rows; }
+};
+
 template <int CIN>
 struct GramDims {
-    static constexpr int K = CIN * 9, KR = CIN * 3, NA = KR * (K + 1);   // a team (kernel row r) owns KR patch entries
+    static constexpr int K = CIN * 9, KR = CIN * 3;     // a team (kernel row r) owns KR patch entries
+    static constexpr int KP = (K + 2) / 2;              // column pairs: k' = 0..K-1, then the constant 1 (plain sums)
+    static constexpr int NA = KR * (K + 1);
 };
 constexpr int kGramTeam = 96, kGramThreads = 3 * kGramTeam;
 
 // part[blk][team r][a = ci*3 + t][k'] = sum over the block's pixels of patch[ci*9 + r*3 + t] * patch[k']
-// (k' = K: the plain sum).  Per-thread fp32 sums of ~50 products, fixed-order tree per block, doubles afterwards.
+// (k' = K: the plain sum).  Per-thread fp32 sums of ~50 products (packed fma.f32x2 over column pairs), fixed-order
+// tree per block, doubles afterwards.  `wmagic` = ceil(2^32 / W): row = umulhi(p, wmagic) for p < 2^16.
 template <int CIN>
 __global__ void __launch_bounds__(kGramThreads)
-conv0_gram_kernel(const float* __restrict__ x, int H, int W, int groups_per_img, int n_groups, float* __restrict__ part) {
+conv0_gram_kernel(const float* __restrict__ x, int H, int W, unsigned wmagic, int groups_per_img, int n_groups,
+                  float* __restrict__ part) {
     using D = GramDims<CIN>;
     extern __shared__ float xs_all[];                     // 2 x [CIN][10][W+2]
     __shared__ float red[kGramThreads / 32][D::NA];
-    const int team = threadIdx.x / kGramTeam, tt = threadIdx.x % kGramTeam;
+    const int team = threadIdx.x / kGramTeam, tt = threadIdx.x - team * kGramTeam;
     const int Wp = W + 2, xsz = CIN * (kC0Rows + 2) * Wp;
-    float acc[D::KR][D::K + 1];
+    float2 acc[D::KR][D::KP];
 #pragma unroll
     for (int a = 0; a < D::KR; ++a)
 #pragma unroll
-        for (int k = 0; k <= D::K; ++k) acc[a][k] = 0.0f;
+        for (int k = 0; k < D::KP; ++k) acc[a][k] = make_float2(0.0f, 0.0f);
     int grp = blockIdx.x, buf = 0;
-    if (grp < n_groups) load_x_rows<CIN>(x, xs_all, grp / groups_per_img, (grp % groups_per_img) * kC0Rows, H, W);
+    GroupWalk gw(grp, gridDim.x, groups_per_img), gn = gw;
+    if (grp < n_groups) stage_x_rows_async<CIN>(x, xs_all, gw.b, gw.h0(), H, W);
+    cpa_commit();
+    cpa_wait_all();
     __syncthreads();
     for (; grp < n_groups; grp += gridDim.x, buf ^= 1) {
         const float* xs = xs_all + buf * xsz;
-        const int h0 = (grp % groups_per_img) * kC0Rows;
-        const int nxt = grp + gridDim.x;
-        if (nxt < n_groups)
-            load_x_rows<CIN>(x, xs_all + (buf ^ 1) * xsz, nxt / groups_per_img, (nxt % groups_per_img) * kC0Rows, H, W);
+        const int h0 = gw.h0();
+        gn.next();
+        if (grp + (int)gridDim.x < n_groups) stage_x_rows_async<CIN>(x, xs_all + (buf ^ 1) * xsz, gn.b, gn.h0(), H, W);
+        cpa_commit();
         const int npix = min(kC0Rows, H - h0) * W;
         for (int p = tt; p < npix; p += kGramTeam) {
-            const int row = p / W, col = p - row * W;
+            const int row = (int)__umulhi((unsigned)p, wmagic), col = p - row * W;
             const float* base = xs + row * Wp + col;
-            float pv[D::K], own[D::KR];
+            float pv[2 * D::KP], own[D::KR];
 #pragma unroll
             for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
                 for (int r = 0; r < 3; ++r)
 #pragma unroll
                     for (int t = 0; t < 3; ++t) pv[ci * 9 + r * 3 + t] = base[(ci * (kC0Rows + 2) + r) * Wp + t];
+            pv[D::K] = 1.0f;
+            if (D::K + 1 < 2 * D::KP) pv[2 * D::KP - 1] = 0.0f;
 #pragma unroll
             for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
                 for (int t = 0; t < 3; ++t) own[ci * 3 + t] = base[(ci * (kC0Rows + 2) + team) * Wp + t];
 #pragma unroll
             for (int a = 0; a < D::KR; ++a) {
+                const float2 o2 = make_float2(own[a], own[a]);
 #pragma unroll
-                for (int k = 0; k < D::K; ++k) acc[a][k] = fmaf(own[a], pv[k], acc[a][k]);
-                acc[a][D::K] += own[a];
+                for (int k = 0; k < D::KP; ++k) acc[a][k] = __ffma2_rn(o2, make_float2(pv[2 * k], pv[2 * k + 1]), acc[a][k]);
             }
         }
+        gw = gn;
+        cpa_wait_all();
         __syncthreads();
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1070,7 +1125,7 @@ conv0_gram_kernel(const float* __restrict__ x, int H, int W, int groups_per_img,
     for (int a = 0; a < D::KR; ++a)
 #pragma unroll
         for (int k = 0; k <= D::K; ++k) {
-            float v = acc[a][k];
+            float v = (k & 1) ? acc[a][k >> 1].y : acc[a][k >> 1].x;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
             if (lane == 0) red[warp][a * (D::K + 1) + k] = v;
@@ -1151,14 +1206,17 @@ conv0_lean_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
     }
     const float keep_scale = g.drop_p > 0.0f ? 1.0f / (1.0f - g.drop_p) : 1.0f;
     int grp = blockIdx.x, buf = 0;
-    if (grp < n_groups) load_x_rows<CIN>(x, xs_all, grp / groups_per_img, (grp % groups_per_img) * kC0Rows, g.H, g.W);
+    GroupWalk gw(grp, gridDim.x, groups_per_img), gn = gw;
+    if (grp < n_groups) stage_x_rows_async<CIN>(x, xs_all, gw.b, gw.h0(), g.H, g.W);
+    cpa_commit();
+    cpa_wait_all();
     __syncthreads();
     for (; grp < n_groups; grp += gridDim.x, buf ^= 1) {
         const float* xs = xs_all + buf * xsz;
-        const int b = grp / groups_per_img, h0 = (grp % groups_per_img) * kC0Rows;
-        const int nxt = grp + gridDim.x;
-        if (nxt < n_groups)
-            load_x_rows<CIN>(x, xs_all + (buf ^ 1) * xsz, nxt / groups_per_img, (nxt % groups_per_img) * kC0Rows, g.H, g.W);
+        const int b = gw.b, h0 = gw.h0();
+        gn.next();
+        if (grp + (int)gridDim.x < n_groups) stage_x_rows_async<CIN>(x, xs_all + (buf ^ 1) * xsz, gn.b, gn.h0(), g.H, g.W);
+        cpa_commit();
         const int h = h0 + warp;
         if (h < g.H) {
             for (int wo = 0; wo < g.Wo; ++wo) {
@@ -1238,74 +1296,119 @@ conv0_lean_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
                 }
             }
         }
+        gw = gn;
+        cpa_wait_all();
         __syncthreads();
     }
 }
 
-// S[k][c] = sum over windows of dz * patch_k(winner), S[K][c] = sum dz; part layout [nblk][K+1][C]
+// S[k][c] = sum over windows of dz * patch_k(winner), S[K][c] = sum dz; part layout [nblk][K+1][C].
+// dA and the winner bytes of the NEXT tile (8 rows x kLeanWC windows x 128 channels) travel global -> shared with
+// 16-byte cp.async while the current tile is consumed, so no warp ever waits on HBM; channel pairs accumulate with
+// packed fma.f32x2 (each half has its own winner, i.e. its own patch value).  Needs the channels-last block output
+// (g.oC == 1: block 0 is not the last conv block).
+constexpr int kLeanWC = 8;
+inline size_t conv0_lean_bwd_smem(int cin, int W) {
+    const size_t xpad = (2 * (size_t)cin * (kC0Rows + 2) * (W + 2) + 3) & ~(size_t)3;
+    return xpad * 4 + 2 * (size_t)kC0Rows * kLeanWC * (128 + 32) * 4;
+}
 template <int CIN, int P>
 __global__ void __launch_bounds__(256)
 conv0_lean_bwd_kernel(const float* __restrict__ x, const unsigned* __restrict__ argw, const float* __restrict__ dA,
                       PoolGeom g, int groups_per_img, int n_groups, float* __restrict__ part) {
     constexpr int K = CIN * 9;
-    extern __shared__ float xs_all[];                     // 2 x [CIN][10][W+2]
+    extern __shared__ __align__(16) float lean_smem[];
     __shared__ float red[kC0Rows][128];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c4 = blockIdx.y * 32 + lane, c = c4 * 4, C4 = g.C >> 2, Wp = g.W + 2, xsz = CIN * (kC0Rows + 2) * Wp;
+    const int C4 = g.C >> 2, Wp = g.W + 2, xsz = CIN * (kC0Rows + 2) * Wp;
+    const int xpad = (2 * xsz + 3) & ~3;                                         // keep the tiles 16 B aligned
+    float* xs_all = lean_smem;                                                   // 2 x [CIN][10][W+2]
+    float* da_all = lean_smem + xpad;                                            // 2 x [8][WC][128]
+    unsigned* ar_all = reinterpret_cast<unsigned*>(da_all + 2 * kC0Rows * kLeanWC * 128);   // 2 x [8][WC][32]
     const float keep_scale = g.drop_p > 0.0f ? 1.0f / (1.0f - g.drop_p) : 1.0f;
-    float acc[4][K + 1];
+    const int n_chunks = (g.Wo + kLeanWC - 1) / kLeanWC;
+    float2 acc[2][K + 1];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+    for (int q = 0; q < 2; ++q)
 #pragma unroll
-        for (int k = 0; k <= K; ++k) acc[q][k] = 0.0f;
-    int grp = blockIdx.x, buf = 0;
-    if (grp < n_groups) load_x_rows<CIN>(x, xs_all, grp / groups_per_img, (grp % groups_per_img) * kC0Rows, g.H, g.W);
-    __syncthreads();
-    for (; grp < n_groups; grp += gridDim.x, buf ^= 1) {
-        const float* xs = xs_all + buf * xsz;
-        const int b = grp / groups_per_img, h0 = (grp % groups_per_img) * kC0Rows;
-        const int nxt = grp + gridDim.x;
-        if (nxt < n_groups)
-            load_x_rows<CIN>(x, xs_all + (buf ^ 1) * xsz, nxt / groups_per_img, (nxt % groups_per_img) * kC0Rows, g.H, g.W);
+        for (int k = 0; k <= K; ++k) acc[q][k] = make_float2(0.0f, 0.0f);
+
+    // one warp per image row of the tile: 512 B of dA (all lanes) + 128 B of winner words (lanes 0..7) per window
+    auto stage_tile = [&](int tb, int b, int h0, int chunk) {
         const int h = h0 + warp;
-        if (h < g.H) {
-            const unsigned* arow = argw + (((long)b * g.H + h) * g.Wo) * C4 + c4;
-            const float* darow = dA + (long)b * g.oB + (long)h * g.oH + (long)c * g.oC;
-            const float* xrow = xs + warp * Wp;
-            unsigned word = __ldg(arow), wordn = 0;
-            float gq[4], gn[4] = {0, 0, 0, 0};
-            load_dA(darow, g.oC, gq);
-            for (int wo = 0; wo < g.Wo; ++wo) {
-                if (wo + 1 < g.Wo) {
-                    wordn = __ldg(arow + (long)(wo + 1) * C4);
-                    load_dA(darow + (long)(wo + 1) * g.oW, g.oC, gn);
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const unsigned by = (word >> (8 * q)) & 0xFFu;
-                    const float dz = (by & 0x80u) ? 0.0f : gq[q] * keep_scale;
-                    const float* base = xrow + wo * P + (int)(by & 0x7Fu);
-#pragma unroll
-                    for (int ci = 0; ci < CIN; ++ci)
-#pragma unroll
-                        for (int r = 0; r < 3; ++r)
-#pragma unroll
-                            for (int t = 0; t < 3; ++t)
-                                acc[q][ci * 9 + r * 3 + t] =
-                                    fmaf(dz, base[(ci * (kC0Rows + 2) + r) * Wp + t], acc[q][ci * 9 + r * 3 + t]);
-                    acc[q][K] += dz;
-                }
-                word = wordn;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) gq[q] = gn[q];
-            }
+        if (h >= g.H) return;
+        const int w0 = chunk * kLeanWC, nw = min(kLeanWC, g.Wo - w0);
+        const float* src = dA + (long)b * g.oB + (long)h * g.oH + (long)w0 * g.oW + blockIdx.y * 128 + lane * 4;
+        const unsigned* asrc = argw + (((long)b * g.H + h) * g.Wo + w0) * C4 + blockIdx.y * 32 + lane * 4;
+        float* dd = da_all + ((tb * kC0Rows + warp) * kLeanWC) * 128 + lane * 4;
+        unsigned* ad = ar_all + ((tb * kC0Rows + warp) * kLeanWC) * 32 + lane * 4;
+        for (int wl = 0; wl < nw; ++wl) {
+            cpa16(dd + wl * 128, src + (long)wl * g.oW);
+            if (lane < 8) cpa16(ad + wl * 32, asrc + (long)wl * C4);
         }
-        __syncthreads();
+    };
+
+    int grp = blockIdx.x, xb = 0, tb = 0;
+    GroupWalk gw(grp, gridDim.x, groups_per_img), gn = gw;
+    if (grp < n_groups) {
+        stage_x_rows_async<CIN>(x, xs_all, gw.b, gw.h0(), g.H, g.W);
+        stage_tile(0, gw.b, gw.h0(), 0);
+    }
+    cpa_commit();
+    cpa_wait_all();
+    __syncthreads();
+    for (; grp < n_groups; grp += gridDim.x, xb ^= 1) {
+        const float* xs = xs_all + xb * xsz;
+        const int h0 = gw.h0();
+        gn.next();
+        const bool more = grp + (int)gridDim.x < n_groups;
+        for (int chunk = 0; chunk < n_chunks; ++chunk, tb ^= 1) {
+            if (chunk + 1 < n_chunks) {
+                stage_tile(tb ^ 1, gw.b, h0, chunk + 1);
+            } else if (more) {
+                stage_x_rows_async<CIN>(x, xs_all + (xb ^ 1) * xsz, gn.b, gn.h0(), g.H, g.W);
+                stage_tile(tb ^ 1, gn.b, gn.h0(), 0);
+            }
+            cpa_commit();
+            if (h0 + warp < g.H) {
+                const int w0 = chunk * kLeanWC, nw = min(kLeanWC, g.Wo - w0);
+                const float* xrow = xs + warp * Wp + w0 * P;
+                const float* dd = da_all + ((tb * kC0Rows + warp) * kLeanWC) * 128 + lane * 4;
+                const unsigned* ad = ar_all + ((tb * kC0Rows + warp) * kLeanWC) * 32 + lane;
+                for (int wl = 0; wl < nw; ++wl) {
+                    const float4 g4 = *reinterpret_cast<const float4*>(dd + wl * 128);
+                    const unsigned word = ad[wl * 32];
+                    const float gq[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+                    for (int pr = 0; pr < 2; ++pr) {
+                        const unsigned b0 = (word >> (16 * pr)) & 0xFFu, b1 = (word >> (16 * pr + 8)) & 0xFFu;
+                        const float2 dz = make_float2((b0 & 0x80u) ? 0.0f : gq[2 * pr] * keep_scale,
+                                                      (b1 & 0x80u) ? 0.0f : gq[2 * pr + 1] * keep_scale);
+                        const float* base0 = xrow + wl * P + (int)(b0 & 0x7Fu);
+                        const float* base1 = xrow + wl * P + (int)(b1 & 0x7Fu);
+#pragma unroll
+                        for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+                            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                                for (int t = 0; t < 3; ++t) {
+                                    const int off = (ci * (kC0Rows + 2) + r) * Wp + t;
+                                    acc[pr][ci * 9 + r * 3 + t] = __ffma2_rn(dz, make_float2(base0[off], base1[off]),
+                                                                             acc[pr][ci * 9 + r * 3 + t]);
+                                }
+                        acc[pr][K] = __fadd2_rn(acc[pr][K], dz);
+                    }
+                }
+            }
+            cpa_wait_all();
+            __syncthreads();
+        }
+        gw = gn;
     }
 #pragma unroll
     for (int k = 0; k <= K; ++k) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) red[warp][lane * 4 + q] = acc[q][k];
+        red[warp][lane * 4 + 0] = acc[0][k].x; red[warp][lane * 4 + 1] = acc[0][k].y;
+        red[warp][lane * 4 + 2] = acc[1][k].x; red[warp][lane * 4 + 3] = acc[1][k].y;
         __syncthreads();
         if (threadIdx.x < 128) {
             float t = 0.0f;
@@ -1356,7 +1459,9 @@ conv0_lean_bwd_finalize_kernel(const float* __restrict__ part, int nblk, int cin
     }
 }
 
-inline bool conv0_lean_ok(int cin, int C, int pool) { return conv0_direct_ok(cin, C) && (pool == 5 || pool == 2); }
+inline bool conv0_lean_ok(int cin, int C, int pool, int n_conv) {
+    return conv0_direct_ok(cin, C) && (pool == 5 || pool == 2) && n_conv > 1;
+}
 
 
 // ----------------------------------------------------------------------------- small dense layers, backward
@@ -1500,7 +1605,7 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
         float* running = bn_state + 2L * i * P.C;
         const bool direct0 = (i == 0) && conv0_direct_ok(P.cin[0], P.C);
         int nblk = 0;
-        if (i == 0 && conv0_lean_ok(P.cin[0], P.C, P.pool[0])) {
+        if (i == 0 && conv0_lean_ok(P.cin[0], P.C, P.pool[0], P.n_conv)) {
             // lean block 0: statistics from the patch moments of the input, then one fused kernel; y0 is never stored
             const int gpi = (P.H + kC0Rows - 1) / kC0Rows, n_groups = gpi * batch;
             const size_t sm = 2 * (size_t)P.cin[0] * (kC0Rows + 2) * (P.win[0] + 2) * 4;
@@ -1510,8 +1615,9 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
                 SED_PROF("conv0.stats", st);
                 if (training) {
                     const int gblk = std::min(n_groups, 2 * sm_count());
-                    if (cin0 == 1) conv0_gram_kernel<1><<<gblk, kGramThreads, sm, st>>>(x, P.H, P.win[0], gpi, n_groups, wsf(ws, P.part));
-                    else conv0_gram_kernel<2><<<gblk, kGramThreads, sm, st>>>(x, P.H, P.win[0], gpi, n_groups, wsf(ws, P.part));
+                    const unsigned wmagic = (unsigned)(((1ull << 32) + (unsigned)P.win[0] - 1) / (unsigned)P.win[0]);
+                    if (cin0 == 1) conv0_gram_kernel<1><<<gblk, kGramThreads, sm, st>>>(x, P.H, P.win[0], wmagic, gpi, n_groups, wsf(ws, P.part));
+                    else conv0_gram_kernel<2><<<gblk, kGramThreads, sm, st>>>(x, P.H, P.win[0], wmagic, gpi, n_groups, wsf(ws, P.part));
                     SED_POST_LAUNCH();
                     const int entries = 3 * (3 * cin0) * (K0 + 1);
                     conv0_gram_reduce_kernel<<<(entries * 32 + 255) / 256, 256, 0, st>>>(
@@ -1847,7 +1953,7 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         const PoolGeom g = pool_geom(P, d, i, 1, seed);
         const float* y = wsf(ws, P.y[i]);
         const float* stat = wsf(ws, P.stat[i]);
-        if (i == 0 && conv0_lean_ok(P.cin[0], P.C, P.pool[0])) {
+        if (i == 0 && conv0_lean_ok(P.cin[0], P.C, P.pool[0], P.n_conv)) {
             const int gpi = (P.H + kC0Rows - 1) / kC0Rows, n_groups = gpi * batch;
             const size_t sm = 2 * (size_t)P.cin[0] * (kC0Rows + 2) * (P.win[0] + 2) * 4;
             const int cin0 = P.cin[0], K0 = 9 * cin0;
@@ -1857,11 +1963,16 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
                 SED_PROF("conv0.bwd_lean", st);
                 const unsigned* argw = reinterpret_cast<const unsigned*>(reinterpret_cast<const char*>(ws) + P.arg0);
                 const double* gram = reinterpret_cast<const double*>(reinterpret_cast<const char*>(ws) + P.gram);
-                const dim3 grid(std::min(n_groups, sm_count()), P.C / 128);
-                if (cin0 == 1 && g.p == 5) conv0_lean_bwd_kernel<1, 5><<<grid, 256, sm, st>>>(x, argw, dA, g, gpi, n_groups, part);
-                else if (cin0 == 1) conv0_lean_bwd_kernel<1, 2><<<grid, 256, sm, st>>>(x, argw, dA, g, gpi, n_groups, part);
-                else if (g.p == 5) conv0_lean_bwd_kernel<2, 5><<<grid, 256, sm, st>>>(x, argw, dA, g, gpi, n_groups, part);
-                else conv0_lean_bwd_kernel<2, 2><<<grid, 256, sm, st>>>(x, argw, dA, g, gpi, n_groups, part);
+                const dim3 grid(std::min(n_groups, 2 * sm_count()), P.C / 128);
+                const size_t bsm = conv0_lean_bwd_smem(cin0, P.win[0]);
+                const void* kfn = cin0 == 1 ? (g.p == 5 ? (const void*)conv0_lean_bwd_kernel<1, 5> : (const void*)conv0_lean_bwd_kernel<1, 2>)
+                                            : (g.p == 5 ? (const void*)conv0_lean_bwd_kernel<2, 5> : (const void*)conv0_lean_bwd_kernel<2, 2>);
+                rc = ensure_dyn_smem(kfn, (int)bsm);
+                if (rc) return rc;
+                if (cin0 == 1 && g.p == 5) conv0_lean_bwd_kernel<1, 5><<<grid, 256, bsm, st>>>(x, argw, dA, g, gpi, n_groups, part);
+                else if (cin0 == 1) conv0_lean_bwd_kernel<1, 2><<<grid, 256, bsm, st>>>(x, argw, dA, g, gpi, n_groups, part);
+                else if (g.p == 5) conv0_lean_bwd_kernel<2, 5><<<grid, 256, bsm, st>>>(x, argw, dA, g, gpi, n_groups, part);
+                else conv0_lean_bwd_kernel<2, 2><<<grid, 256, bsm, st>>>(x, argw, dA, g, gpi, n_groups, part);
                 SED_POST_LAUNCH();
                 conv0_lean_bwd_finalize_kernel<<<P.C, 128, 0, st>>>(
                     part, (int)grid.x, cin0, P.C, gram, params + P.conv_w[0], params + P.conv_b[0], params + P.bn_w[0], stat,
