@@ -1057,27 +1057,29 @@ struct GroupWalk {
 
 template <int CIN>
 struct GramDims {
-    static constexpr int K = CIN * 9, KR = CIN * 3;     // a team (kernel row r) owns KR patch entries
+    static constexpr int K = CIN * 9;
+    static constexpr int TEAMS = CIN * 3;               // a team = one warp = (input channel, kernel row) of the OWN entry
     static constexpr int KP = (K + 2) / 2;              // column pairs: k' = 0..K-1, then the constant 1 (plain sums)
-    static constexpr int NA = KR * (K + 1);
+    static constexpr int THREADS = TEAMS * 32;
 };
-constexpr int kGramTeam = 96, kGramThreads = 3 * kGramTeam;
 
-// part[blk][team r][a = ci*3 + t][k'] = sum over the block's pixels of patch[ci*9 + r*3 + t] * patch[k']
-// (k' = K: the plain sum).  Per-thread fp32 sums of ~50 products (packed fma.f32x2 over column pairs), fixed-order
-// tree per block, doubles afterwards.  `wmagic` = ceil(2^32 / W): row = umulhi(p, wmagic) for p < 2^16.
+// part[blk][k][k'] = sum over the block's pixels of patch[k] * patch[k'] (k' = K: the plain sum).  Warp (ci, r) owns
+// the three rows k = ci*9 + r*3 + t; lanes walk the pixels of the row group.  Per-thread fp32 sums of ~140 products
+// (packed fma.f32x2 over column pairs), fixed shuffle tree, doubles afterwards.  `wmagic` = ceil(2^32 / W):
+// row = umulhi(p, wmagic) for p < 2^16.
 template <int CIN>
-__global__ void __launch_bounds__(kGramThreads)
+__global__ void __launch_bounds__(GramDims<CIN>::THREADS)
 conv0_gram_kernel(const float* __restrict__ x, int H, int W, unsigned wmagic, int groups_per_img, int n_groups,
                   float* __restrict__ part) {
     using D = GramDims<CIN>;
     extern __shared__ float xs_all[];                     // 2 x [CIN][10][W+2]
-    __shared__ float red[kGramThreads / 32][D::NA];
-    const int team = threadIdx.x / kGramTeam, tt = threadIdx.x - team * kGramTeam;
+    const int team = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tci = team / 3, tr = team - tci * 3;
     const int Wp = W + 2, xsz = CIN * (kC0Rows + 2) * Wp;
-    float2 acc[D::KR][D::KP];
+    const int own_off = (tci * (kC0Rows + 2) + tr) * Wp;
+    float2 acc[3][D::KP];
 #pragma unroll
-    for (int a = 0; a < D::KR; ++a)
+    for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int k = 0; k < D::KP; ++k) acc[a][k] = make_float2(0.0f, 0.0f);
     int grp = blockIdx.x, buf = 0;
@@ -1093,10 +1095,10 @@ conv0_gram_kernel(const float* __restrict__ x, int H, int W, unsigned wmagic, in
         if (grp + (int)gridDim.x < n_groups) stage_x_rows_async<CIN>(x, xs_all + (buf ^ 1) * xsz, gn.b, gn.h0(), H, W);
         cpa_commit();
         const int npix = min(kC0Rows, H - h0) * W;
-        for (int p = tt; p < npix; p += kGramTeam) {
+        for (int p = lane; p < npix; p += 32) {
             const int row = (int)__umulhi((unsigned)p, wmagic), col = p - row * W;
             const float* base = xs + row * Wp + col;
-            float pv[2 * D::KP], own[D::KR];
+            float pv[2 * D::KP], own[3];
 #pragma unroll
             for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
@@ -1106,11 +1108,9 @@ conv0_gram_kernel(const float* __restrict__ x, int H, int W, unsigned wmagic, in
             pv[D::K] = 1.0f;
             if (D::K + 1 < 2 * D::KP) pv[2 * D::KP - 1] = 0.0f;
 #pragma unroll
-            for (int ci = 0; ci < CIN; ++ci)
+            for (int t = 0; t < 3; ++t) own[t] = base[own_off + t];
 #pragma unroll
-                for (int t = 0; t < 3; ++t) own[ci * 3 + t] = base[(ci * (kC0Rows + 2) + team) * Wp + t];
-#pragma unroll
-            for (int a = 0; a < D::KR; ++a) {
+            for (int a = 0; a < 3; ++a) {
                 const float2 o2 = make_float2(own[a], own[a]);
 #pragma unroll
                 for (int k = 0; k < D::KP; ++k) acc[a][k] = __ffma2_rn(o2, make_float2(pv[2 * k], pv[2 * k + 1]), acc[a][k]);
@@ -1120,57 +1120,61 @@ conv0_gram_kernel(const float* __restrict__ x, int H, int W, unsigned wmagic, in
         cpa_wait_all();
         __syncthreads();
     }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-    for (int a = 0; a < D::KR; ++a)
+    for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int k = 0; k <= D::K; ++k) {
             float v = (k & 1) ? acc[a][k >> 1].y : acc[a][k >> 1].x;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) red[warp][a * (D::K + 1) + k] = v;
+            if (lane == 0) part[((long)blockIdx.x * D::K + team * 3 + a) * (D::K + 1) + k] = v;
         }
-    __syncthreads();
-    for (int e = threadIdx.x; e < 3 * D::NA; e += kGramThreads) {
-        const int tm = e / D::NA, i = e - tm * D::NA;
-        part[(long)blockIdx.x * 3 * D::NA + e] = red[3 * tm][i] + red[3 * tm + 1][i] + red[3 * tm + 2][i];
-    }
 }
 
 // gram[k][k'] (k' <= K, doubles, divided by the pixel count): one warp per entry, fixed order
 __global__ void conv0_gram_reduce_kernel(const float* __restrict__ part, int nblk, int cin, double inv_n,
                                          double* __restrict__ gram) {
-    const int K = cin * 9, KR = cin * 3, NA = KR * (K + 1);
+    const int K = cin * 9, NE = K * (K + 1);
     const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (e >= 3 * NA) return;
+    if (e >= NE) return;
     double a = 0.0;
-    for (int b = lane; b < nblk; b += 32) a += (double)__ldg(part + (long)b * 3 * NA + e);
+#pragma unroll 4
+    for (int b = lane; b < nblk; b += 32) a += (double)__ldg(part + (long)b * NE + e);
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
-    if (lane == 0) {
-        const int team = e / NA, i = e - team * NA, aidx = i / (K + 1), kp = i - aidx * (K + 1);
-        const int ci = aidx / 3, t = aidx - ci * 3;
-        gram[(ci * 9 + team * 3 + t) * (K + 1) + kp] = a * inv_n;
-    }
+    if (lane == 0) gram[e] = a * inv_n;
 }
 
-// BatchNorm statistics of conv 0 from the patch moments; same outputs as bn_finalize_train_kernel
-__global__ void __launch_bounds__(128)
+// BatchNorm statistics of conv 0 from the patch moments; same outputs as bn_finalize_train_kernel.  One warp per
+// channel: lane k owns row k of w^T (G - m m^T) w, fixed shuffle tree.
+__global__ void __launch_bounds__(256)
 conv0_bn_finalize_kernel(const double* __restrict__ gram, int cin, int C, long n, const float* __restrict__ w,
                          const float* __restrict__ bias, const float* __restrict__ gamma,
                          const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running,
                          float* __restrict__ stat) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x, K = cin * 9;
+    __shared__ double gsh[18 * 19];
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, k = threadIdx.x & 31, K = cin * 9;
+    for (int i = threadIdx.x; i < K * (K + 1); i += blockDim.x) gsh[i] = gram[i];
+    __syncthreads();
+    gram = gsh;
     if (c >= C) return;
     const float* wc = w + (long)c * K;
-    double mean = (double)bias[c], var = 0.0;
-    for (int k = 0; k < K; ++k) {
+    double mpart = 0.0, vpart = 0.0;
+    if (k < K) {
         const double mk = gram[k * (K + 1) + K], wk = (double)wc[k];
-        mean += wk * mk;
         double row = 0.0;
         for (int k2 = 0; k2 < K; ++k2) row += (double)wc[k2] * (gram[k * (K + 1) + k2] - mk * gram[k2 * (K + 1) + K]);
-        var += wk * row;
+        mpart = wk * mk;
+        vpart = wk * row;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mpart += __shfl_xor_sync(0xffffffffu, mpart, o);
+        vpart += __shfl_xor_sync(0xffffffffu, vpart, o);
+    }
+    if (k != 0) return;
+    const double mean = (double)bias[c] + mpart;
+    double var = vpart;
     if (var < 0.0) var = 0.0;
     const float invstd = (float)(1.0 / sqrt(var + (double)eps));
     const float sc = gamma[c] * invstd;
@@ -1183,17 +1187,20 @@ conv0_bn_finalize_kernel(const double* __restrict__ gram, int cin, int C, long n
     running[C + c] = (1.0f - momentum) * running[C + c] + momentum * (float)unbiased;
 }
 
-// conv + bias -> BN -> ReLU -> max-pool(1,P) -> dropout in registers.  Same thread mapping, input staging and
-// accumulation order as conv0_fwd_stats_kernel (y is bit-identical to what that kernel would have stored).
+// conv + bias -> BN -> ReLU -> max-pool(1,P) -> dropout in registers.  Same accumulation order as
+// conv0_fwd_stats_kernel (y is bit-identical to what that kernel would have stored).  lane <-> 4 output channels
+// (weights in registers as channel pairs for fma.f32x2), warp <-> one image row at a time.  Every warp stages ITS
+// OWN three input rows (per input channel) with cp.async, one row ahead, and never meets a block-wide barrier: the
+// warps of an SM drift apart, so the FMA-heavy window bodies of some overlap the max / dropout / store tails of others.
 template <int CIN, int P>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 conv0_lean_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                       const float* __restrict__ stat, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
-                      __nv_bfloat16* __restrict__ out_lo, unsigned* __restrict__ argw, PoolGeom g, int groups_per_img,
-                      int n_groups) {
-    extern __shared__ float xs_all[];                     // 2 x [CIN][10][W+2]
+                      __nv_bfloat16* __restrict__ out_lo, unsigned* __restrict__ argw, PoolGeom g, int n_rows) {
+    extern __shared__ float xs_all[];                     // [8 warps][2][CIN][3][W+2]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c4 = blockIdx.y * 32 + lane, c = c4 * 4, C4 = g.C >> 2, Wp = g.W + 2, xsz = CIN * (kC0Rows + 2) * Wp;
+    const int c4 = blockIdx.y * 32 + lane, c = c4 * 4, C4 = g.C >> 2, Wp = g.W + 2, xsz = CIN * 3 * Wp;
+    float* xw = xs_all + warp * 2 * xsz;
     float2 wr[2][CIN * 9], bs[2], sc[2], sh[2];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -1205,100 +1212,111 @@ conv0_lean_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
             wr[q][k] = make_float2(__ldg(w + (long)(c + 2 * q) * CIN * 9 + k), __ldg(w + (long)(c + 2 * q + 1) * CIN * 9 + k));
     }
     const float keep_scale = g.drop_p > 0.0f ? 1.0f / (1.0f - g.drop_p) : 1.0f;
-    int grp = blockIdx.x, buf = 0;
-    GroupWalk gw(grp, gridDim.x, groups_per_img), gn = gw;
-    if (grp < n_groups) stage_x_rows_async<CIN>(x, xs_all, gw.b, gw.h0(), g.H, g.W);
+    // rows h-1, h, h+1 of every input channel of image b, zero-filled outside the image
+    auto stage_row = [&](float* dst, int b, int h) {
+#pragma unroll
+        for (int rowid = 0; rowid < CIN * 3; ++rowid) {
+            const int ci = rowid / 3, hh = h - 1 + (rowid - ci * 3);
+            const bool rowok = hh >= 0 && hh < g.H;
+            const float* src = x + (((long)b * CIN + ci) * g.H + (rowok ? hh : 0)) * g.W;
+            for (int cc = lane; cc < Wp; cc += 32) {
+                const bool ok = rowok && cc >= 1 && cc <= g.W;
+                cpa4_zfill(dst + rowid * Wp + cc, src + (ok ? cc - 1 : 0), ok);
+            }
+        }
+    };
+    const int stride = gridDim.x * kC0Rows;
+    int row = blockIdx.x * kC0Rows + warp, buf = 0;
+    int b = row / g.H, h = row - b * g.H;
+    const int step_b = stride / g.H, step_h = stride - step_b * g.H;
+    if (row < n_rows) stage_row(xw, b, h);
     cpa_commit();
-    cpa_wait_all();
-    __syncthreads();
-    for (; grp < n_groups; grp += gridDim.x, buf ^= 1) {
-        const float* xs = xs_all + buf * xsz;
-        const int b = gw.b, h0 = gw.h0();
-        gn.next();
-        if (grp + (int)gridDim.x < n_groups) stage_x_rows_async<CIN>(x, xs_all + (buf ^ 1) * xsz, gn.b, gn.h0(), g.H, g.W);
+    for (; row < n_rows; row += stride, buf ^= 1) {
+        int bn = b + step_b, hn = h + step_h;
+        if (hn >= g.H) { hn -= g.H; ++bn; }
+        if (row + stride < n_rows) stage_row(xw + (buf ^ 1) * xsz, bn, hn);
         cpa_commit();
-        const int h = h0 + warp;
-        if (h < g.H) {
-            for (int wo = 0; wo < g.Wo; ++wo) {
-                float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-                unsigned arg[4] = {0u, 0u, 0u, 0u};
-                auto consider = [&](int j, const float2 a01, const float2 a23) {
-                    const float2 z01 = __ffma2_rn(a01, sc[0], sh[0]), z23 = __ffma2_rn(a23, sc[1], sh[1]);
-                    const float z[4] = {z01.x, z01.y, z23.x, z23.y};
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        const float* xs = xw + buf * xsz;
+        for (int wo = 0; wo < g.Wo; ++wo) {
+            float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            unsigned arg[4] = {0u, 0u, 0u, 0u};
+            auto consider = [&](int j, const float2 a01, const float2 a23) {
+                const float2 z01 = __ffma2_rn(a01, sc[0], sh[0]), z23 = __ffma2_rn(a23, sc[1], sh[1]);
+                const float z[4] = {z01.x, z01.y, z23.x, z23.y};
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (z[q] > best[q]) { best[q] = z[q]; arg[q] = (unsigned)j; }      // first maximum wins
-                };
+                for (int q = 0; q < 4; ++q)
+                    if (z[q] > best[q]) { best[q] = z[q]; arg[q] = (unsigned)j; }      // first maximum wins
+            };
 #pragma unroll
-                for (int j = 0; j + 1 < P; j += 2) {
-                    const int ww = wo * P + j;
-                    float2 acc[2][2] = {{bs[0], bs[1]}, {bs[0], bs[1]}};
+            for (int j = 0; j + 1 < P; j += 2) {
+                const int ww = wo * P + j;
+                float2 acc[2][2] = {{bs[0], bs[1]}, {bs[0], bs[1]}};
 #pragma unroll
-                    for (int ci = 0; ci < CIN; ++ci)
+                for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
-                        for (int r = 0; r < 3; ++r) {
-                            const float* xr = xs + (ci * (kC0Rows + 2) + warp + r) * Wp + ww;
-                            float xc[4];
+                    for (int r = 0; r < 3; ++r) {
+                        const float* xr = xs + (ci * 3 + r) * Wp + ww;
+                        float xc[4];
 #pragma unroll
-                            for (int t = 0; t < 4; ++t) xc[t] = xr[t];
+                        for (int t = 0; t < 4; ++t) xc[t] = xr[t];
 #pragma unroll
-                            for (int t = 0; t < 3; ++t) {
-                                const float2 x0 = make_float2(xc[t], xc[t]), x1 = make_float2(xc[t + 1], xc[t + 1]);
-                                acc[0][0] = __ffma2_rn(wr[0][ci * 9 + r * 3 + t], x0, acc[0][0]);
-                                acc[0][1] = __ffma2_rn(wr[1][ci * 9 + r * 3 + t], x0, acc[0][1]);
-                                acc[1][0] = __ffma2_rn(wr[0][ci * 9 + r * 3 + t], x1, acc[1][0]);
-                                acc[1][1] = __ffma2_rn(wr[1][ci * 9 + r * 3 + t], x1, acc[1][1]);
-                            }
+                        for (int t = 0; t < 3; ++t) {
+                            const float2 x0 = make_float2(xc[t], xc[t]), x1 = make_float2(xc[t + 1], xc[t + 1]);
+                            acc[0][0] = __ffma2_rn(wr[0][ci * 9 + r * 3 + t], x0, acc[0][0]);
+                            acc[0][1] = __ffma2_rn(wr[1][ci * 9 + r * 3 + t], x0, acc[0][1]);
+                            acc[1][0] = __ffma2_rn(wr[0][ci * 9 + r * 3 + t], x1, acc[1][0]);
+                            acc[1][1] = __ffma2_rn(wr[1][ci * 9 + r * 3 + t], x1, acc[1][1]);
                         }
-                    consider(j, acc[0][0], acc[0][1]);
-                    consider(j + 1, acc[1][0], acc[1][1]);
-                }
-                if (P & 1) {
-                    const int ww = wo * P + P - 1;
-                    float2 acc[2] = {bs[0], bs[1]};
-#pragma unroll
-                    for (int ci = 0; ci < CIN; ++ci)
-#pragma unroll
-                        for (int r = 0; r < 3; ++r)
-#pragma unroll
-                            for (int t = 0; t < 3; ++t) {
-                                const float xv = xs[(ci * (kC0Rows + 2) + warp + r) * Wp + ww + t];
-                                const float2 x2 = make_float2(xv, xv);
-                                acc[0] = __ffma2_rn(wr[0][ci * 9 + r * 3 + t], x2, acc[0]);
-                                acc[1] = __ffma2_rn(wr[1][ci * 9 + r * 3 + t], x2, acc[1]);
-                            }
-                    consider(P - 1, acc[0], acc[1]);
-                }
-                const long pix = ((long)b * g.H + h) * g.Wo + wo;
-                const long i = pix * C4 + c4;                      // element numbering of the pool kernels (dropout)
-                Keep4 kp;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) kp.k[q] = true;
-                if (g.drop_p > 0.0f) kp = dropout_keep4(g.seed, (unsigned long long)i, g.drop_p);
-                float m[4];
-                unsigned word = 0;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const bool alive = best[q] > 0.0f && kp.k[q];
-                    m[q] = alive ? best[q] * keep_scale : 0.0f;
-                    word |= (arg[q] | (alive ? 0u : 0x80u)) << (8 * q);
-                }
-                const float4 m4 = make_float4(m[0], m[1], m[2], m[3]);
-                if (argw) argw[i] = word;
-                if (out_hi) store_planes4(out_hi, out_lo, i, m4);
-                if (out) {
-                    float* dst = out + (long)b * g.oB + (long)h * g.oH + (long)wo * g.oW + (long)c * g.oC;
-                    if (g.oC == 1) {
-                        *reinterpret_cast<float4*>(dst) = m4;
-                    } else {
-                        dst[0] = m[0]; dst[g.oC] = m[1]; dst[2 * g.oC] = m[2]; dst[3 * g.oC] = m[3];
                     }
+                consider(j, acc[0][0], acc[0][1]);
+                consider(j + 1, acc[1][0], acc[1][1]);
+            }
+            if (P & 1) {
+                const int ww = wo * P + P - 1;
+                float2 acc[2] = {bs[0], bs[1]};
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int t = 0; t < 3; ++t) {
+                            const float xv = xs[(ci * 3 + r) * Wp + ww + t];
+                            const float2 x2 = make_float2(xv, xv);
+                            acc[0] = __ffma2_rn(wr[0][ci * 9 + r * 3 + t], x2, acc[0]);
+                            acc[1] = __ffma2_rn(wr[1][ci * 9 + r * 3 + t], x2, acc[1]);
+                        }
+                consider(P - 1, acc[0], acc[1]);
+            }
+            const long pix = ((long)b * g.H + h) * g.Wo + wo;
+            const long i = pix * C4 + c4;                      // element numbering of the pool kernels (dropout)
+            Keep4 kp;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) kp.k[q] = true;
+            if (g.drop_p > 0.0f) kp = dropout_keep4(g.seed, (unsigned long long)i, g.drop_p);
+            float m[4];
+            unsigned word = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const bool alive = best[q] > 0.0f && kp.k[q];
+                m[q] = alive ? best[q] * keep_scale : 0.0f;
+                word |= (arg[q] | (alive ? 0u : 0x80u)) << (8 * q);
+            }
+            const float4 m4 = make_float4(m[0], m[1], m[2], m[3]);
+            if (argw) argw[i] = word;
+            if (out_hi) store_planes4(out_hi, out_lo, i, m4);
+            if (out) {
+                float* dst = out + (long)b * g.oB + (long)h * g.oH + (long)wo * g.oW + (long)c * g.oC;
+                if (g.oC == 1) {
+                    *reinterpret_cast<float4*>(dst) = m4;
+                } else {
+                    dst[0] = m[0]; dst[g.oC] = m[1]; dst[2 * g.oC] = m[2]; dst[3 * g.oC] = m[3];
                 }
             }
         }
-        gw = gn;
-        cpa_wait_all();
-        __syncthreads();
+        __syncwarp();                                          // every lane is done with xs[buf] before it is refilled
+        b = bn; h = hn;
     }
 }
 
@@ -1422,16 +1440,19 @@ conv0_lean_bwd_kernel(const float* __restrict__ x, const unsigned* __restrict__ 
 
 // one block per channel: d(beta), d(gamma), dW of conv 0 (and its zero bias gradient) from S, the patch
 // moments and the forward statistics
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 conv0_lean_bwd_finalize_kernel(const float* __restrict__ part, int nblk, int cin, int C, const double* __restrict__ gram,
                                const float* __restrict__ w, const float* __restrict__ bias,
                                const float* __restrict__ gamma, const float* __restrict__ stat,
                                float* __restrict__ dw, float* __restrict__ db, float* __restrict__ dgamma,
                                float* __restrict__ dbeta) {
     __shared__ double S[32];
+    __shared__ double gsh[18 * 19];
     const int c = blockIdx.x, K = cin * 9, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int k = warp; k <= K; k += 4) {
+    for (int i = threadIdx.x; i < K * (K + 1); i += blockDim.x) gsh[i] = gram[i];
+    for (int k = warp; k <= K; k += 8) {
         double a = 0.0;
+#pragma unroll 5
         for (int b = lane; b < nblk; b += 32) a += (double)__ldg(part + ((long)b * (K + 1) + k) * C + c);
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
@@ -1446,10 +1467,10 @@ conv0_lean_bwd_finalize_kernel(const float* __restrict__ part, int nblk, int cin
     double sum_dz_y = bc * sum_dz, wg = 0.0;
     for (int k2 = 0; k2 < K; ++k2) {
         sum_dz_y += (double)wc[k2] * S[k2];
-        wg += (double)wc[k2] * gram[k2 * (K + 1) + k];                 // G is symmetric
+        wg += (double)wc[k2] * gsh[k2 * (K + 1) + k];                  // G is symmetric
     }
     const double dg = invstd * (sum_dz_y - mean * sum_dz);             // sum dz * xhat
-    const double mk = gram[k * (K + 1) + K];
+    const double mk = gsh[k * (K + 1) + K];
     const double tk = invstd * (wg + (bc - mean) * mk);                // mean over pixels of xhat * patch_k
     dw[(long)c * K + k] = (float)((double)gamma[c] * invstd * (S[k] - sum_dz * mk - dg * tk));
     if (k == 0) {
@@ -1614,16 +1635,16 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
             {
                 SED_PROF("conv0.stats", st);
                 if (training) {
-                    const int gblk = std::min(n_groups, 2 * sm_count());
+                    const int gblk = std::min(n_groups, (cin0 == 1 ? 5 : 3) * sm_count());
                     const unsigned wmagic = (unsigned)(((1ull << 32) + (unsigned)P.win[0] - 1) / (unsigned)P.win[0]);
-                    if (cin0 == 1) conv0_gram_kernel<1><<<gblk, kGramThreads, sm, st>>>(x, P.H, P.win[0], wmagic, gpi, n_groups, wsf(ws, P.part));
-                    else conv0_gram_kernel<2><<<gblk, kGramThreads, sm, st>>>(x, P.H, P.win[0], wmagic, gpi, n_groups, wsf(ws, P.part));
+                    if (cin0 == 1) conv0_gram_kernel<1><<<gblk, GramDims<1>::THREADS, sm, st>>>(x, P.H, P.win[0], wmagic, gpi, n_groups, wsf(ws, P.part));
+                    else conv0_gram_kernel<2><<<gblk, GramDims<2>::THREADS, sm, st>>>(x, P.H, P.win[0], wmagic, gpi, n_groups, wsf(ws, P.part));
                     SED_POST_LAUNCH();
-                    const int entries = 3 * (3 * cin0) * (K0 + 1);
+                    const int entries = K0 * (K0 + 1);
                     conv0_gram_reduce_kernel<<<(entries * 32 + 255) / 256, 256, 0, st>>>(
                         wsf(ws, P.part), gblk, cin0, 1.0 / (double)M, gram);
                     SED_POST_LAUNCH();
-                    conv0_bn_finalize_kernel<<<(P.C + 127) / 128, 128, 0, st>>>(
+                    conv0_bn_finalize_kernel<<<(P.C * 32 + 255) / 256, 256, 0, st>>>(
                         gram, cin0, P.C, (long)M, params + P.conv_w[0], params + P.conv_b[0], params + P.bn_w[0],
                         params + P.bn_b[0], d->bn_eps, d->bn_momentum, running, stat);
                 } else {
@@ -1641,10 +1662,12 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
             unsigned* argw = training ? reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + P.arg0) : nullptr;
             const dim3 grid(std::min(n_groups, 2 * sm_count()), P.C / 128);
             const float *w0 = params + P.conv_w[0], *b0 = params + P.conv_b[0];
-            if (cin0 == 1 && g.p == 5) conv0_lean_fwd_kernel<1, 5><<<grid, 256, sm, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, gpi, n_groups);
-            else if (cin0 == 1) conv0_lean_fwd_kernel<1, 2><<<grid, 256, sm, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, gpi, n_groups);
-            else if (g.p == 5) conv0_lean_fwd_kernel<2, 5><<<grid, 256, sm, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, gpi, n_groups);
-            else conv0_lean_fwd_kernel<2, 2><<<grid, 256, sm, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, gpi, n_groups);
+            const size_t smw = (size_t)kC0Rows * 2 * cin0 * 3 * (P.win[0] + 2) * 4;      // per-warp row buffers
+            const int n_rows = batch * P.H;
+            if (cin0 == 1 && g.p == 5) conv0_lean_fwd_kernel<1, 5><<<grid, 256, smw, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, n_rows);
+            else if (cin0 == 1) conv0_lean_fwd_kernel<1, 2><<<grid, 256, smw, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, n_rows);
+            else if (g.p == 5) conv0_lean_fwd_kernel<2, 5><<<grid, 256, smw, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, n_rows);
+            else conv0_lean_fwd_kernel<2, 2><<<grid, 256, smw, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, n_rows);
             SED_POST_LAUNCH();
             continue;
         }
@@ -1974,7 +1997,7 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
                 else if (g.p == 5) conv0_lean_bwd_kernel<2, 5><<<grid, 256, bsm, st>>>(x, argw, dA, g, gpi, n_groups, part);
                 else conv0_lean_bwd_kernel<2, 2><<<grid, 256, bsm, st>>>(x, argw, dA, g, gpi, n_groups, part);
                 SED_POST_LAUNCH();
-                conv0_lean_bwd_finalize_kernel<<<P.C, 128, 0, st>>>(
+                conv0_lean_bwd_finalize_kernel<<<P.C, 256, 0, st>>>(
                     part, (int)grid.x, cin0, P.C, gram, params + P.conv_w[0], params + P.conv_b[0], params + P.bn_w[0], stat,
                     grads + P.conv_w[0], grads + P.conv_b[0], grads + P.bn_w[0], grads + P.bn_b[0]);
                 SED_POST_LAUNCH();
