@@ -453,34 +453,61 @@ def run_ours(args, rank, world, local_rank):
     total_flops, per = crnn_flops(cfg, B)
     phases = {k: v[0] / prof_steps for k, v in prof.items()}
     model = phase_model(cfg, B, per)
-    # dominant kernel = the modelled phase with the largest share of the step
-    dom = max((k for k in phases if k in model), key=lambda k: phases[k])
-    kind, amount, kname = model[dom]
-    dom_ms = phases[dom] / (prof[dom][1] / prof_steps)
+    # dominant kernel = the KERNEL (not the launch) with the largest share of the step: phases that are launches of
+    # the same kernel are pooled; achieved = algorithmic work of its launches / their device time
+    groups = {}
+    for k in phases:
+        if k in model:
+            gname = model[k][2].split(" ")[0]
+            groups.setdefault(gname, []).append(k)
+    dom_kernel = max(groups, key=lambda gname: sum(phases[k] for k in groups[gname]))
+    dks = groups[dom_kernel]
+    kind, kname = model[dks[0]][0], model[dks[0]][2]
+    amount_step = sum(model[k][1] for k in dks)                       # algorithmic bytes / FLOPs of all its launches
+    ms_kernel_step = sum(phases[k] for k in dks)
+    n_launch = sum(prof[k][1] for k in dks) / prof_steps
+    dom_ms = ms_kernel_step / n_launch
+    amount = amount_step / n_launch
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get(args.config, {}).get(dom)
+            tr = json.load(f).get(args.config, {})
+        have = [k for k in dks if k in tr]
+        if have:                                   # per launch, averaged over the launches ncu captured
+            traffic = sum(tr[k] for k in have) / len(have)
     except Exception:
         pass
     if kind == "tensor":
-        ach = amount / (dom_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": kname, "phase": dom, "achieved": ach, "peak": pk["tf_sustained"],
+        ach = amount_step / (ms_kernel_step * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": kname, "phases": dks, "achieved": ach, "peak": pk["tf_sustained"],
                 "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "traffic": traffic,
+                "traffic_note": "dram bytes per launch, mean of the launches captured by ncu --set full (forward "
+                "launches; profiles/ncu_traffic.json)",
                 "peak_source": pk["src"] + " (sustained bf16)", "algorithmic_flops_per_launch": amount,
-                "mma_tflops_issued": 3 * ach, "note": "fp32-grade 3-term bf16 split: the tensor pipe executes 3x the "
-                "algorithmic FLOPs; frac is algorithmic FLOPs / bf16 peak"}
+                "mma_tflops_issued": 3 * ach, "frac_issued": 3 * ach / pk["tf_sustained"],
+                "note": "fp32-grade 3-term bf16 split: the tensor pipe executes 3x the algorithmic FLOPs; frac is "
+                "algorithmic FLOPs / bf16 peak, frac_issued the tensor-pipe work actually issued / bf16 peak"}
     else:
-        ach = amount / (dom_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": kname, "phase": dom, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+        ach = amount_step / (ms_kernel_step * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": kname, "phases": dks, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
                 "frac": ach / pk["hbm"], "traffic": traffic, "peak_source": pk["src"],
                 "algorithmic_bytes_per_launch": amount}
-    roof.update({"ms_per_launch": dom_ms, "share_of_step": phases[dom] / sum(phases.values()),
+    roof.update({"launches_per_step": n_launch, "ms_per_launch": dom_ms,
+                 "share_of_step": ms_kernel_step / sum(phases.values()),
                  "whole_step": {"algorithmic_tflops": total_flops / (ms_step * 1e-3) / 1e12,
                                 "frac_of_bf16_peak": total_flops / (ms_step * 1e-3) / 1e12 / pk["tf_sustained"]}})
-    # the tensor-core conv kernel is reported next to it whichever phase dominates
+    # the largest CUDA-core (non-tensor) kernel is reported next to it: its bytes against the HBM roofline
+    nt = [gname for gname in groups if model[groups[gname][0]][0] == "hbm"]
+    if nt and kind == "tensor":
+        gname = max(nt, key=lambda gname: sum(phases[k] for k in groups[gname]))
+        ks = groups[gname]
+        t_ms = sum(phases[k] for k in ks)
+        by = sum(model[k][1] for k in ks)
+        roof["cuda_core_kernel"] = {"kernel": model[ks[0]][2], "phases": ks, "ms_per_step": t_ms,
+                                    "algorithmic_bytes_per_step": by, "achieved": by / (t_ms * 1e-3) / 1e9,
+                                    "unit": "GB/s", "frac_of_hbm": by / (t_ms * 1e-3) / 1e9 / pk["hbm"]}
     tc = [k for k in phases if k in model and model[k][0] == "tensor"]
-    if tc:
+    if tc and kind != "tensor":
         k = max(tc, key=lambda k: phases[k])
         t_ms = phases[k] / (prof[k][1] / prof_steps)
         a = model[k][1] / (t_ms * 1e-3) / 1e12

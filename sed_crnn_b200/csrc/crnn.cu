@@ -8,6 +8,8 @@
 // This file holds the fp32-exact path: contractions run through the functor GEMM of gemm_simt.cuh.
 #include <cuda_bf16.h>
 #include "crnn_plan.cuh"
+#include <map>
+#include <mutex>
 #include "gemm_simt.cuh"
 #include "conv_small.cuh"
 #include "gru_scan.cuh"
@@ -1595,6 +1597,32 @@ InStrides in_strides(const Plan& P, const sedb200_crnn_desc* d, int i) {
 
 inline float* wsf(void* ws, size_t off) { return reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + off); }
 
+// One helper stream + fork / done events per device (created once, never destroyed): the GRU backward pass runs the
+// weight-gradient GEMMs of a layer there while the caller's stream continues with the critical path.
+struct SideStream {
+    cudaStream_t st = nullptr;
+    cudaEvent_t fork[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+};
+std::mutex g_side_mu;
+std::map<int, SideStream> g_side;
+int side_stream(SideStream** out) {
+    int dev = 0;
+    SED_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_side_mu);
+    auto it = g_side.find(dev);
+    if (it == g_side.end()) {
+        SideStream s;
+        SED_CUDA_OK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            SED_CUDA_OK(cudaEventCreateWithFlags(&s.fork[i], cudaEventDisableTiming));
+            SED_CUDA_OK(cudaEventCreateWithFlags(&s.done[i], cudaEventDisableTiming));
+        }
+        it = g_side.emplace(dev, s).first;
+    }
+    *out = &it->second;
+    return SEDB200_OK;
+}
+
 }  // namespace
 }  // namespace sedb200
 
@@ -1874,21 +1902,67 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
 
     // ---- BiGRU stack (dout = grad wrt the layer's output, in dseq[cur])
     int cur = 0;
+    SideStream* side = nullptr;
+    bool side_busy[2] = {false, false};
     for (int l = P.n_gru - 1; l >= 0; --l) {
         const int h = P.gh[l], in = P.gin[l];
         const float* xin = l == 0 ? wsf(ws, P.act[P.n_conv - 1]) : wsf(ws, P.gout[l - 1]);
         float* dgi = wsf(ws, P.dgi);
         float* dgh = wsf(ws, P.dgh);
         const bool fusedg = gru_scan_fused_param_grads(h);
+        // two-stream layer: the scan emits the tensor-core operand planes itself, so everything that is NOT on the path to
+        // d(input) (bias reduction, dW_hh, dW_ih) can run beside the main stream
+        const bool two_stream = P.gru_planes[l] && P.gru_tc[l] && fusedg && gemm_tc_supported(6 * h, 2 * h, BT) && P.dgp2 != 0;
+        const int par = l & 1;
         float* part_w = part;                                      // [B][2][3h][h]
-        float* part_b = part + (size_t)B * 6 * h * h;              // [B][2][2][3h]
-        char* dgpl = reinterpret_cast<char*>(ws) + P.dgp;       // {dgi_hi, dgi_lo, dgh_hi, dgh_lo} when the scan emits planes
+        float* part_b = two_stream ? wsf(ws, P.gbias[par]) : part + (size_t)B * 6 * h * h;   // [B][2][2][3h]
+        char* dgpl = reinterpret_cast<char*>(ws) + ((two_stream && par) ? P.dgp2 : P.dgp);   // {dgi_hi, dgi_lo, dgh_hi, dgh_lo} when the scan emits planes
         void* planes[4] = {dgpl, dgpl + P.dg_plane_bytes, dgpl + 2 * P.dg_plane_bytes, dgpl + 3 * P.dg_plane_bytes};
+        if (two_stream) {
+            if (!side) { rc = side_stream(&side); if (rc) return rc; }
+            // an earlier layer of the same parity may still be reading these planes on the side stream
+            if (side_busy[par]) SED_CUDA_OK(cudaStreamWaitEvent(st, side->done[par], 0));
+        }
 { char _nm[40]; snprintf(_nm, sizeof _nm, "gru%d.scan_bwd", l); SED_PROF(_nm, st);
         rc = gru_scan_backward(wsf(ws, P.dseq[cur]), wsf(ws, P.gout[l]), wsf(ws, P.gates[l]), params + P.whh[l],
                                dgi, dgh, part_w, part_b, batch, P.T, h, st, P.gru_planes[l] ? planes : nullptr);
         if (rc) return rc;
 }
+        if (two_stream) {
+            char _nm3[40]; snprintf(_nm3, sizeof _nm3, "gru%d.bwd_dx", l); SED_PROF(_nm3, st);
+            cudaStream_t ss = side->st;
+            SED_CUDA_OK(cudaEventRecord(side->fork[par], st));
+            SED_CUDA_OK(cudaStreamWaitEvent(ss, side->fork[par], 0));
+            // ---- side stream: bias gradients, dW_hh, dW_ih
+            rc = reduce_bias_partials(part_b, grads + P.bih[l], grads + P.bhh[l], 6 * h, batch, ss);
+            if (rc) return rc;
+            const char *gi_hi = dgpl, *gi_lo = dgpl + P.dg_plane_bytes;
+            const char *gh_hi = dgpl + 2 * P.dg_plane_bytes, *gh_lo = dgpl + 3 * P.dg_plane_bytes;
+            const char* hp_hi = reinterpret_cast<const char*>(ws) + P.hpp[l];
+            const char* hp_lo = hp_hi + P.hp_plane_bytes[l];
+            float* stmp = wsf(ws, P.tc_side);
+            float* stpart = stmp + 12 * h * h + 64;
+            rc = gemm_tc(gh_hi, gh_lo, 1, hp_hi, hp_lo, 1, 6 * h, 2 * h, BT, nullptr, stmp, 2 * h, 1, stpart, ss);
+            if (rc) return rc;
+            extract_whh_kernel<<<(6 * h * h + 255) / 256, 256, 0, ss>>>(stmp, h, grads + P.whh[l]);
+            SED_POST_LAUNCH();
+            const size_t xpb = ((size_t)BT * in * 2 + 1023) & ~(size_t)1023, wpb = ((size_t)6 * h * in * 2 + 1023) & ~(size_t)1023;
+            const char* xp = reinterpret_cast<const char*>(ws) + P.gxp[l];
+            // dW_ih[n6][k] = sum_m dgi[m][n6] * xin[m][k]        (both operands stored [B*T][.]: MN-major)
+            rc = gemm_tc(gi_hi, gi_lo, 1, xp, xp + xpb, 1, 6 * h, in, BT, nullptr, grads + P.wih[l], in, 1, wsf(ws, P.tc_side), ss);
+            if (rc) return rc;
+            SED_CUDA_OK(cudaEventRecord(side->done[par], ss));
+            side_busy[par] = true;
+            // ---- main stream: d(xin)[m][k] = sum_n6 dgi[m][n6] * W_ih[n6][k]    (W_ih stored [n6][k] = [K][N]: MN-major)
+            char* wp = reinterpret_cast<char*>(ws) + P.tc;
+            rc = split_planes(params + P.wih[l], wp, wp + wpb, 6L * h * in, st);
+            if (rc) return rc;
+            float* dxin2 = wsf(ws, P.dseq[cur ^ 1]);
+            rc = gemm_tc(gi_hi, gi_lo, 0, wp, wp + wpb, 1, BT, in, 6 * h, nullptr, dxin2, in, 0, nullptr, st);
+            if (rc) return rc;
+            cur ^= 1;
+            continue;
+        }
         char _nm2[40]; snprintf(_nm2, sizeof _nm2, "gru%d.bwd_gemms", l); SED_PROF(_nm2, st);
         if (fusedg) {
             // the scan left per-batch-row partials of both bias gradients: fixed-order sum over B
@@ -1972,6 +2046,10 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
 
     // ---- conv blocks (dA = grad wrt block output; for the last block it is dseq[cur] in [B][T][flat])
     const float* dA = wsf(ws, P.dseq[cur]);
+    struct SideJoin {           // the weight-gradient GEMMs rejoin the caller's stream on every way out of this function
+        SideStream* s; const bool* busy; cudaStream_t st;
+        ~SideJoin() { for (int i = 0; s && i < 2; ++i) if (busy[i]) cudaStreamWaitEvent(st, s->done[i], 0); }
+    } side_join{side, side_busy, st};
     for (int i = P.n_conv - 1; i >= 0; --i) {
         const PoolGeom g = pool_geom(P, d, i, 1, seed);
         const float* y = wsf(ws, P.y[i]);

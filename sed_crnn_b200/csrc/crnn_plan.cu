@@ -197,6 +197,21 @@ int make_plan(const sedb200_crnn_desc* d, int batch, Plan* p) {
         P.dg_plane_bytes = std::max(P.dg_plane_bytes, plane(BT * 6L * P.gh[l]));
     }
     P.dgp = P.dg_plane_bytes ? take((long)(4 * P.dg_plane_bytes / 4)) : 0;
+    if (P.dg_plane_bytes) {
+        P.dgp2 = take((long)(4 * P.dg_plane_bytes / 4));
+        size_t side = 0;
+        long gb = 0;
+        for (int l = 0; l < P.n_gru; ++l) {
+            if (!P.gru_planes[l]) continue;
+            const size_t h6 = 6 * (size_t)P.gh[l];
+            side = std::max(side, ((size_t)sm_count() + 1) * h6 * 2 * P.gh[l] * 4 + 8192);      // dW_hh: tmp + split-K partials
+            side = std::max(side, (size_t)sm_count() * h6 * P.gin[l] * 4 + 4096);                // dW_ih split-K partials
+            gb = std::max(gb, B * 24L * P.gh[l]);
+        }
+        P.gbias[0] = take(gb);
+        P.gbias[1] = take(gb);
+        P.tc_side = take((long)(side / 4) + 64);
+    }
     P.tc_bytes = tc;
     P.tc = take((long)(tc / 4) + 64);
     P.ws_bytes = o;

@@ -34,6 +34,10 @@ struct Plan {
     // lean block 0 (crnn.cu, "first conv block without its output tensor"): per-window winner bytes written by the
     // fused forward kernel, and the K x (K+1) patch Gram matrix (doubles) both BatchNorm passes are derived from
     size_t arg0 = 0, gram = 0;
+    // GRU backward on two streams: weight / bias gradient GEMMs of layer l run on a side stream while the main stream
+    // goes on with d(input) and the next scan -- gradient planes and bias partials alternate by layer parity, and the
+    // side stream has its own GEMM scratch
+    size_t dgp2 = 0, gbias[2] = {0, 0}, tc_side = 0;
     // plane-native tensor-core flow: block i (>= 1) runs fwd, dgrad and wgrad on tcgen05 and exchanges
     // bf16 hi/lo planes with its neighbours instead of fp32 tensors
     bool conv_tc_all[SEDB200_MAX_CONV];
