@@ -15,6 +15,7 @@
 #include "gru_scan.cuh"
 #include "tc_conv.cuh"
 #include "tc_gemm.cuh"
+#include "tc_umma.cuh"
 
 #include <algorithm>
 
@@ -1486,6 +1487,205 @@ inline bool conv0_lean_ok(int cin, int C, int pool, int n_conv) {
     return conv0_direct_ok(cin, C) && (pool == 5 || pool == 2) && n_conv > 1;
 }
 
+// ----------------------------------------------------------------------------- lean block 0 forward on tcgen05
+// Same contract as conv0_lean_fwd_kernel (pooled output + winner bytes, statistics known up front), with the
+// contraction on the tensor cores: a tile is NW = 128/P pooling windows = TP = NW*P pixels (rows of the MMA),
+//   1. every thread pair builds one im2col row (K = 9*Cin <= 18 values, zero-padded to 16-wide k-steps) as bf16 hi / lo
+//      planes straight into the 128-byte-swizzled K-major layout tcgen05 reads (what TMA would have produced),
+//   2. one thread issues 3 MMAs (hi*hi + hi*lo + lo*hi, the fp32-grade split of tc_conv.cu) per k-step into a
+//      128 x 128 fp32 TMEM accumulator,
+//   3. the 8 warps move the accumulator TMEM -> registers -> an XOR-swizzled [pixel][channel] shared tile (it aliases
+//      the A planes, which the MMAs are done with),
+//   4. warp <-> window, lane <-> 4 channels: bias + BN + max / argmax over the window's P rows, ReLU, dropout, stores.
+// Two CTAs per SM (96 KB of shared memory, 128 TMEM columns each) overlap one CTA's epilogue with the other's build.
+namespace c0tc {
+constexpr int kPlane = 128 * 128;                               // bytes: 128 rows x 128 B (64 bf16 K slots, <= 32 used)
+constexpr int kSmem = 1024 + 2 * kPlane + 128 * 128 * 4 + 64;   // align + B planes + tile (aliases the A planes) + barrier
+__device__ __forceinline__ uint32_t sw128(int r, int c) {       // byte offset of 16-byte chunk c of row r
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+}
+template <int K>
+__device__ __forceinline__ void put_row(unsigned char* plane, int r, const float (&v)[K], bool lo) {
+    constexpr int CH = ((K + 15) / 16) * 2;                     // chunks of 8 bf16 covering the k-steps in use
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k0 = c * 8 + 2 * e;
+            const float a = k0 < K ? v[k0 < K ? k0 : 0] : 0.0f, b = k0 + 1 < K ? v[k0 + 1 < K ? k0 + 1 : 0] : 0.0f;
+            __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+            if (lo) {
+                ha = __float2bfloat16_rn(a - __bfloat162float(ha));
+                hb = __float2bfloat16_rn(b - __bfloat162float(hb));
+            }
+            w[e] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+        }
+        *reinterpret_cast<uint4*>(plane + sw128(r, c)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+}  // namespace c0tc
+
+template <int CIN, int P>
+__global__ void __launch_bounds__(256, 2)
+conv0_tc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                    const float* __restrict__ stat, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
+                    __nv_bfloat16* __restrict__ out_lo, unsigned* __restrict__ argw, PoolGeom g, long n_windows,
+                    int n_tiles) {
+    using namespace umma;
+    constexpr int K = CIN * 9, KSTEPS = (K + 15) / 16, NW = 128 / P, TP = NW * P;
+    extern __shared__ unsigned char c0tc_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(c0tc_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *b_hi = smem, *b_lo = smem + c0tc::kPlane;
+    unsigned char *a_hi = smem + 2 * c0tc::kPlane, *a_lo = a_hi + c0tc::kPlane;
+    float* ys = reinterpret_cast<float*>(smem + 2 * c0tc::kPlane);                   // [128][128], aliases a_hi / a_lo
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * c0tc::kPlane + 128 * 128 * 4);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (warp == 1) tmem_alloc(tmem_slot, 128);
+    {   // B operand: row n = output channel, the same K ordering as the im2col rows (w[c][ci][r][t])
+        const int n = tid >> 1;
+        float v[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = __ldg(w + (long)(blockIdx.y * 128 + n) * K + k);
+        c0tc::put_row<K>((tid & 1) ? b_lo : b_hi, n, v, (tid & 1) != 0);
+    }
+    tc_fence_before();
+    fence_proxy_async();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int c4 = blockIdx.y * 32 + lane, c = c4 * 4, C4 = g.C >> 2;
+    const float4 bs = __ldg(reinterpret_cast<const float4*>(bias + c));
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(stat + 2 * g.C + c));
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(stat + 3 * g.C + c));
+    const float bsv[4] = {bs.x, bs.y, bs.z, bs.w}, scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+    const float keep_scale = g.drop_p > 0.0f ? 1.0f / (1.0f - g.drop_p) : 1.0f;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // ---- 1. im2col rows of this tile (thread pair <-> row; even thread: hi plane, odd thread: lo plane)
+        {
+            const int r = tid >> 1;
+            const long q = (long)tile * NW + r / P;
+            const int j = r % P;
+            float v[K];
+            if (r < TP && q < n_windows) {
+                const long bh = q / g.Wo;
+                const int wo = (int)(q - bh * g.Wo);
+                const long b = bh / g.H;
+                const int h = (int)(bh - b * g.H), wc = wo * P + j;
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+                    for (int rr = 0; rr < 3; ++rr) {
+                        const int hh = h + rr - 1;
+                        const float* src = x + ((b * CIN + ci) * g.H + hh) * g.W + wc - 1;
+#pragma unroll
+                        for (int t = 0; t < 3; ++t) {
+                            const int ww = wc + t - 1;
+                            v[ci * 9 + rr * 3 + t] = (hh >= 0 && hh < g.H && ww >= 0 && ww < g.W) ? __ldg(src + t) : 0.0f;
+                        }
+                    }
+            } else {
+#pragma unroll
+                for (int k = 0; k < K; ++k) v[k] = 0.0f;
+            }
+            c0tc::put_row<K>((tid & 1) ? a_lo : a_hi, r, v, (tid & 1) != 0);
+        }
+        fence_proxy_async();
+        __syncthreads();
+        // ---- 2. MMAs
+        if (tid == 0) {
+            tc_fence_after();
+            constexpr uint32_t idesc = idesc_bf16(128, 128, 0, 0);
+            const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh2 = smem_u32(b_hi), bl = smem_u32(b_lo);
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k) {
+                const uint64_t dah = smem_desc_sw128(ah + k * 32, 16, 1024), dal = smem_desc_sw128(al + k * 32, 16, 1024);
+                const uint64_t dbh = smem_desc_sw128(bh2 + k * 32, 16, 1024), dbl = smem_desc_sw128(bl + k * 32, 16, 1024);
+                mma_bf16(tmem, dah, dbh, idesc, k != 0);
+                mma_bf16(tmem, dah, dbl, idesc, 1);
+                mma_bf16(tmem, dal, dbh, idesc, 1);
+            }
+            mma_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        // ---- 3. accumulator -> shared [pixel][channel] tile (chunk index XOR row: conflict-free both ways)
+        {
+            const int qd = warp & 3, half = warp >> 2, r = qd * 32 + lane;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                float v[32];
+                tmem_ld32(tmem + ((uint32_t)(qd * 32) << 16) + half * 64 + cc * 32, v);
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const int chunk = half * 16 + cc * 8 + jj;
+                    *reinterpret_cast<float4*>(ys + r * 128 + ((chunk ^ lane) << 2)) =
+                        make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        // ---- 4. windows: warp <-> window, lane <-> 4 channels
+        for (int wl = warp; wl < NW; wl += 8) {
+            const long q = (long)tile * NW + wl;
+            if (q >= n_windows) break;
+            float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            unsigned arg[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const int row = wl * P + j;
+                const float4 y4 = *reinterpret_cast<const float4*>(ys + row * 128 + ((lane ^ (row & 31)) << 2));
+                const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    const float z = fmaf(yv[qq] + bsv[qq], scv[qq], shv[qq]);
+                    if (z > best[qq]) { best[qq] = z; arg[qq] = (unsigned)j; }      // first maximum wins
+                }
+            }
+            const long i = q * C4 + c4;                        // element numbering of the pool kernels (dropout)
+            Keep4 kp;
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) kp.k[qq] = true;
+            if (g.drop_p > 0.0f) kp = dropout_keep4(g.seed, (unsigned long long)i, g.drop_p);
+            float m[4];
+            unsigned word = 0;
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+                const bool alive = best[qq] > 0.0f && kp.k[qq];
+                m[qq] = alive ? best[qq] * keep_scale : 0.0f;
+                word |= (arg[qq] | (alive ? 0u : 0x80u)) << (8 * qq);
+            }
+            const float4 m4 = make_float4(m[0], m[1], m[2], m[3]);
+            if (argw) argw[i] = word;
+            if (out_hi) store_planes4(out_hi, out_lo, i, m4);
+            if (out) {
+                const long bh = q / g.Wo;
+                const int wo = (int)(q - bh * g.Wo);
+                const long b = bh / g.H;
+                const int h = (int)(bh - b * g.H);
+                float* dst = out + b * g.oB + (long)h * g.oH + (long)wo * g.oW + (long)c * g.oC;
+                if (g.oC == 1) {
+                    *reinterpret_cast<float4*>(dst) = m4;
+                } else {
+                    dst[0] = m[0]; dst[g.oC] = m[1]; dst[2 * g.oC] = m[2]; dst[3 * g.oC] = m[3];
+                }
+            }
+        }
+        __syncthreads();                                       // the tile is free again before the next rows are built
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 128);
+    }
+}
+
 
 // ----------------------------------------------------------------------------- small dense layers, backward
 // The per-frame dense head is tiny (e.g. 64 -> 16 -> 6): one kernel per layer produces d(input) for its 128
@@ -1692,6 +1892,22 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
             const float *w0 = params + P.conv_w[0], *b0 = params + P.conv_b[0];
             const size_t smw = (size_t)kC0Rows * 2 * cin0 * 3 * (P.win[0] + 2) * 4;      // per-warp row buffers
             const int n_rows = batch * P.H;
+            if (d->tensor_cores) {
+                // contraction on tcgen05 (same 3-term split as conv 2 / 3; the fp32 CUDA-core kernel below serves
+                // tensor_cores = 0)
+                const long n_windows = (long)batch * P.H * P.wout[0];
+                const int NWt = 128 / g.p;
+                const int n_tiles = (int)((n_windows + NWt - 1) / NWt);
+                const dim3 tgrid(std::min(n_tiles, 2 * sm_count()), P.C / 128);
+                const void* kfn = cin0 == 1 ? (g.p == 5 ? (const void*)conv0_tc_fwd_kernel<1, 5> : (const void*)conv0_tc_fwd_kernel<1, 2>)
+                                            : (g.p == 5 ? (const void*)conv0_tc_fwd_kernel<2, 5> : (const void*)conv0_tc_fwd_kernel<2, 2>);
+                rc = ensure_dyn_smem(kfn, c0tc::kSmem);
+                if (rc) return rc;
+                if (cin0 == 1 && g.p == 5) conv0_tc_fwd_kernel<1, 5><<<tgrid, 256, c0tc::kSmem, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, n_windows, n_tiles);
+                else if (cin0 == 1) conv0_tc_fwd_kernel<1, 2><<<tgrid, 256, c0tc::kSmem, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, n_windows, n_tiles);
+                else if (g.p == 5) conv0_tc_fwd_kernel<2, 5><<<tgrid, 256, c0tc::kSmem, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, n_windows, n_tiles);
+                else conv0_tc_fwd_kernel<2, 2><<<tgrid, 256, c0tc::kSmem, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, n_windows, n_tiles);
+            } else
             if (cin0 == 1 && g.p == 5) conv0_lean_fwd_kernel<1, 5><<<grid, 256, smw, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, n_rows);
             else if (cin0 == 1) conv0_lean_fwd_kernel<1, 2><<<grid, 256, smw, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, n_rows);
             else if (g.p == 5) conv0_lean_fwd_kernel<2, 5><<<grid, 256, smw, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, n_rows);
