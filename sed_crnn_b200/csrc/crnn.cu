@@ -1490,7 +1490,7 @@ inline bool conv0_lean_ok(int cin, int C, int pool, int n_conv) {
 // ----------------------------------------------------------------------------- lean block 0 forward on tcgen05
 // Same contract as conv0_lean_fwd_kernel (pooled output + winner bytes, statistics known up front), with the
 // contraction on the tensor cores: a tile is NW = 128/P pooling windows = TP = NW*P pixels (rows of the MMA),
-//   1. every thread pair builds one im2col row (K = 9*Cin <= 18 values, zero-padded to 16-wide k-steps) as bf16 hi / lo
+//   1. two threads (warps 0-3: hi plane, warps 4-7: lo plane) build one im2col row (K = 9*Cin <= 18 values, zero-padded to 16-wide k-steps) as bf16 hi / lo
 //      planes straight into the 128-byte-swizzled K-major layout tcgen05 reads (what TMA would have produced),
 //   2. one thread issues 3 MMAs (hi*hi + hi*lo + lo*hi, the fp32-grade split of tc_conv.cu) per k-step into a
 //      128 x 128 fp32 TMEM accumulator,
@@ -1500,7 +1500,7 @@ inline bool conv0_lean_ok(int cin, int C, int pool, int n_conv) {
 // Two CTAs per SM (96 KB of shared memory, 128 TMEM columns each) overlap one CTA's epilogue with the other's build.
 namespace c0tc {
 constexpr int kPlane = 128 * 128;                               // bytes: 128 rows x 128 B (64 bf16 K slots, <= 32 used)
-constexpr int kSmem = 1024 + 2 * kPlane + 128 * 128 * 4 + 64;   // align + B planes + tile (aliases the A planes) + barrier
+constexpr int kSmem = 1024 + 2 * kPlane + 128 * 128 * 4 + 18 * 128 * 4 + 64;   // align + B planes + tile (aliases the A planes) + patch staging + barrier
 __device__ __forceinline__ uint32_t sw128(int r, int c) {       // byte offset of 16-byte chunk c of row r
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
@@ -1530,27 +1530,53 @@ template <int CIN, int P>
 __global__ void __launch_bounds__(256, 2)
 conv0_tc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                     const float* __restrict__ stat, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
-                    __nv_bfloat16* __restrict__ out_lo, unsigned* __restrict__ argw, PoolGeom g, long n_windows,
+                    __nv_bfloat16* __restrict__ out_lo, unsigned* __restrict__ argw, PoolGeom g, unsigned n_windows,
                     int n_tiles) {
     using namespace umma;
     constexpr int K = CIN * 9, KSTEPS = (K + 15) / 16, NW = 128 / P, TP = NW * P;
+    constexpr int KH = (K + 1) / 2;                               // patch entries fetched by each thread of a row pair
     extern __shared__ unsigned char c0tc_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(c0tc_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *b_hi = smem, *b_lo = smem + c0tc::kPlane;
     unsigned char *a_hi = smem + 2 * c0tc::kPlane, *a_lo = a_hi + c0tc::kPlane;
     float* ys = reinterpret_cast<float*>(smem + 2 * c0tc::kPlane);                   // [128][128], aliases a_hi / a_lo
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * c0tc::kPlane + 128 * 128 * 4);
+    float* xst = reinterpret_cast<float*>(smem + 2 * c0tc::kPlane + 128 * 128 * 4);  // [K][128] patch staging (cp.async)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(xst + 18 * 128);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
     if (warp == 1) tmem_alloc(tmem_slot, 128);
     {   // B operand: row n = output channel, the same K ordering as the im2col rows (w[c][ci][r][t])
-        const int n = tid >> 1;
+        const int n = tid & 127;
         float v[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) v[k] = __ldg(w + (long)(blockIdx.y * 128 + n) * K + k);
-        c0tc::put_row<K>((tid & 1) ? b_lo : b_hi, n, v, (tid & 1) != 0);
+        c0tc::put_row<K>((tid >> 7) ? b_lo : b_hi, n, v, (tid >> 7) != 0);
     }
+    // patch values of a tile's rows: global -> shared with zero-filling 4-byte cp.async, one tile ahead of their use;
+    // the two threads of a row (tid, tid + 128) fetch half of its entries each
+    const unsigned uWo = (unsigned)g.Wo, uH = (unsigned)g.H;
+    auto fetch_tile = [&](int tile) {
+        const int r = tid & 127;
+        const unsigned q = (unsigned)tile * NW + (unsigned)(r / P);
+        const int j = r % P;
+        const bool rowok = r < TP && q < n_windows;
+        const unsigned bh = q / uWo, wo = q - bh * uWo, b = bh / uH, h = bh - b * uH;
+        const int wc = (int)wo * P + j;
+#pragma unroll
+        for (int kk = 0; kk < KH; ++kk) {
+            const int k = (tid >> 7) * KH + kk;
+            if (k < K) {
+                const int ci = k / 9, rr = (k - ci * 9) / 3, t = k - ci * 9 - rr * 3;
+                const int hh = (int)h + rr - 1, ww = wc + t - 1;
+                const bool ok = rowok && hh >= 0 && hh < g.H && ww >= 0 && ww < g.W;
+                const float* src = x + (((long)b * CIN + ci) * g.H + (ok ? hh : 0)) * g.W + (ok ? ww : 0);
+                cpa4_zfill(xst + k * 128 + r, ok ? src : x, ok);
+            }
+        }
+    };
+    if ((int)blockIdx.x < n_tiles) fetch_tile(blockIdx.x);
+    cpa_commit();
     tc_fence_before();
     fence_proxy_async();
     __syncthreads();
@@ -1560,38 +1586,21 @@ conv0_tc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, co
     const float4 bs = __ldg(reinterpret_cast<const float4*>(bias + c));
     const float4 sc = __ldg(reinterpret_cast<const float4*>(stat + 2 * g.C + c));
     const float4 sh = __ldg(reinterpret_cast<const float4*>(stat + 3 * g.C + c));
-    const float bsv[4] = {bs.x, bs.y, bs.z, bs.w}, scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+    // z = sc * (acc + bias) + sh: the conv bias is folded into the shift
+    const float scv[4] = {sc.x, sc.y, sc.z, sc.w};
+    const float shv[4] = {fmaf(bs.x, sc.x, sh.x), fmaf(bs.y, sc.y, sh.y), fmaf(bs.z, sc.z, sh.z), fmaf(bs.w, sc.w, sh.w)};
     const float keep_scale = g.drop_p > 0.0f ? 1.0f / (1.0f - g.drop_p) : 1.0f;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // ---- 1. im2col rows of this tile (thread pair <-> row; even thread: hi plane, odd thread: lo plane)
+        // ---- 1. im2col rows of this tile (thread <-> row; warps 0-3: hi plane, warps 4-7: lo plane)
+        cpa_wait_all();
+        __syncthreads();                                       // staged patches visible; previous tile's windows are done
         {
-            const int r = tid >> 1;
-            const long q = (long)tile * NW + r / P;
-            const int j = r % P;
+            const int r = tid & 127;
             float v[K];
-            if (r < TP && q < n_windows) {
-                const long bh = q / g.Wo;
-                const int wo = (int)(q - bh * g.Wo);
-                const long b = bh / g.H;
-                const int h = (int)(bh - b * g.H), wc = wo * P + j;
 #pragma unroll
-                for (int ci = 0; ci < CIN; ++ci)
-#pragma unroll
-                    for (int rr = 0; rr < 3; ++rr) {
-                        const int hh = h + rr - 1;
-                        const float* src = x + ((b * CIN + ci) * g.H + hh) * g.W + wc - 1;
-#pragma unroll
-                        for (int t = 0; t < 3; ++t) {
-                            const int ww = wc + t - 1;
-                            v[ci * 9 + rr * 3 + t] = (hh >= 0 && hh < g.H && ww >= 0 && ww < g.W) ? __ldg(src + t) : 0.0f;
-                        }
-                    }
-            } else {
-#pragma unroll
-                for (int k = 0; k < K; ++k) v[k] = 0.0f;
-            }
-            c0tc::put_row<K>((tid & 1) ? a_lo : a_hi, r, v, (tid & 1) != 0);
+            for (int k = 0; k < K; ++k) v[k] = xst[k * 128 + r];
+            c0tc::put_row<K>((tid >> 7) ? a_lo : a_hi, r, v, (tid >> 7) != 0);
         }
         fence_proxy_async();
         __syncthreads();
@@ -1610,6 +1619,8 @@ conv0_tc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, co
             }
             mma_commit(bar);
         }
+        if (tile + (int)gridDim.x < n_tiles) fetch_tile(tile + gridDim.x);     // lands while the MMAs and the epilogue run
+        cpa_commit();
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
@@ -1632,7 +1643,7 @@ conv0_tc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, co
         __syncthreads();
         // ---- 4. windows: warp <-> window, lane <-> 4 channels
         for (int wl = warp; wl < NW; wl += 8) {
-            const long q = (long)tile * NW + wl;
+            const unsigned q = (unsigned)tile * NW + (unsigned)wl;
             if (q >= n_windows) break;
             float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
             unsigned arg[4] = {0u, 0u, 0u, 0u};
@@ -1643,11 +1654,11 @@ conv0_tc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, co
                 const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
 #pragma unroll
                 for (int qq = 0; qq < 4; ++qq) {
-                    const float z = fmaf(yv[qq] + bsv[qq], scv[qq], shv[qq]);
+                    const float z = fmaf(yv[qq], scv[qq], shv[qq]);
                     if (z > best[qq]) { best[qq] = z; arg[qq] = (unsigned)j; }      // first maximum wins
                 }
             }
-            const long i = q * C4 + c4;                        // element numbering of the pool kernels (dropout)
+            const long i = (long)q * C4 + c4;                  // element numbering of the pool kernels (dropout)
             Keep4 kp;
 #pragma unroll
             for (int qq = 0; qq < 4; ++qq) kp.k[qq] = true;
@@ -1664,11 +1675,8 @@ conv0_tc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, co
             if (argw) argw[i] = word;
             if (out_hi) store_planes4(out_hi, out_lo, i, m4);
             if (out) {
-                const long bh = q / g.Wo;
-                const int wo = (int)(q - bh * g.Wo);
-                const long b = bh / g.H;
-                const int h = (int)(bh - b * g.H);
-                float* dst = out + b * g.oB + (long)h * g.oH + (long)wo * g.oW + (long)c * g.oC;
+                const unsigned bh = q / uWo, wo = q - bh * uWo, b = bh / uH, h = bh - b * uH;
+                float* dst = out + (long)b * g.oB + (long)h * g.oH + (long)wo * g.oW + (long)c * g.oC;
                 if (g.oC == 1) {
                     *reinterpret_cast<float4*>(dst) = m4;
                 } else {
@@ -1676,7 +1684,6 @@ conv0_tc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, co
                 }
             }
         }
-        __syncthreads();                                       // the tile is free again before the next rows are built
     }
     tc_fence_before();
     __syncthreads();
@@ -1895,9 +1902,9 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
             if (d->tensor_cores) {
                 // contraction on tcgen05 (same 3-term split as conv 2 / 3; the fp32 CUDA-core kernel below serves
                 // tensor_cores = 0)
-                const long n_windows = (long)batch * P.H * P.wout[0];
+                const unsigned n_windows = (unsigned)((long)batch * P.H * P.wout[0]);
                 const int NWt = 128 / g.p;
-                const int n_tiles = (int)((n_windows + NWt - 1) / NWt);
+                const int n_tiles = (int)((n_windows + (unsigned)NWt - 1) / (unsigned)NWt);
                 const dim3 tgrid(std::min(n_tiles, 2 * sm_count()), P.C / 128);
                 const void* kfn = cin0 == 1 ? (g.p == 5 ? (const void*)conv0_tc_fwd_kernel<1, 5> : (const void*)conv0_tc_fwd_kernel<1, 2>)
                                             : (g.p == 5 ? (const void*)conv0_tc_fwd_kernel<2, 5> : (const void*)conv0_tc_fwd_kernel<2, 2>);
