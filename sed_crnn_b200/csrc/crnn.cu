@@ -134,6 +134,9 @@ __device__ __forceinline__ void reduce_pair(const float* __restrict__ part, int 
                                             double& ss) {
     __shared__ double sh[2][4];
     double a = 0.0, b = 0.0;
+    // the strided loads of several iterations are issued together (latency-bound otherwise); the order of the
+    // additions is unchanged
+#pragma unroll 8
     for (int k = threadIdx.x; k < nblk; k += 128) {
         a += (double)__ldg(part + ((long)k * 2 + 0) * C + c);
         b += (double)__ldg(part + ((long)k * 2 + 1) * C + c);
@@ -1029,15 +1032,16 @@ __device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_gro
 __device__ __forceinline__ void cpa_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <int CIN>
-__device__ __forceinline__ void stage_x_rows_async(const float* __restrict__ x, float* xs, int b, int h0, int H, int W) {
-    const int Wp = W + 2, nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__device__ __forceinline__ void stage_x_rows_async(const float* __restrict__ x, float* xs, int b, int h0, int H, int W,
+                                                   int row_stride = 0) {
+    const int Wp = row_stride ? row_stride : W + 2, nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int rowid = warp; rowid < CIN * (kC0Rows + 2); rowid += nwarps) {
         const int ci = rowid / (kC0Rows + 2), rr = rowid - ci * (kC0Rows + 2);      // constant divisor: no XU work
         const int hh = h0 - 1 + rr;
         const bool rowok = hh >= 0 && hh < H;
         const float* src = x + (((long)b * CIN + ci) * H + (rowok ? hh : 0)) * W;
         float* dst = xs + rowid * Wp;
-        for (int cc = lane; cc < Wp; cc += 32) {
+        for (int cc = lane; cc < W + 2; cc += 32) {
             const bool ok = rowok && cc >= 1 && cc <= W;
             cpa4_zfill(dst + cc, src + (ok ? cc - 1 : 0), ok);
         }
@@ -1075,10 +1079,11 @@ __global__ void __launch_bounds__(GramDims<CIN>::THREADS)
 conv0_gram_kernel(const float* __restrict__ x, int H, int W, unsigned wmagic, int groups_per_img, int n_groups,
                   float* __restrict__ part) {
     using D = GramDims<CIN>;
-    extern __shared__ float xs_all[];                     // 2 x [CIN][10][W+2]
+    extern __shared__ float xs_all[];                     // 2 x [CIN][10][W+32]: row stride = W (mod 32), so the
+                                                          // lanes that wrap to the next image row keep walking the banks
     const int team = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tci = team / 3, tr = team - tci * 3;
-    const int Wp = W + 2, xsz = CIN * (kC0Rows + 2) * Wp;
+    const int Wp = W + 32, xsz = CIN * (kC0Rows + 2) * Wp;
     const int own_off = (tci * (kC0Rows + 2) + tr) * Wp;
     float2 acc[3][D::KP];
 #pragma unroll
@@ -1087,7 +1092,7 @@ conv0_gram_kernel(const float* __restrict__ x, int H, int W, unsigned wmagic, in
         for (int k = 0; k < D::KP; ++k) acc[a][k] = make_float2(0.0f, 0.0f);
     int grp = blockIdx.x, buf = 0;
     GroupWalk gw(grp, gridDim.x, groups_per_img), gn = gw;
-    if (grp < n_groups) stage_x_rows_async<CIN>(x, xs_all, gw.b, gw.h0(), H, W);
+    if (grp < n_groups) stage_x_rows_async<CIN>(x, xs_all, gw.b, gw.h0(), H, W, Wp);
     cpa_commit();
     cpa_wait_all();
     __syncthreads();
@@ -1095,7 +1100,7 @@ conv0_gram_kernel(const float* __restrict__ x, int H, int W, unsigned wmagic, in
         const float* xs = xs_all + buf * xsz;
         const int h0 = gw.h0();
         gn.next();
-        if (grp + (int)gridDim.x < n_groups) stage_x_rows_async<CIN>(x, xs_all + (buf ^ 1) * xsz, gn.b, gn.h0(), H, W);
+        if (grp + (int)gridDim.x < n_groups) stage_x_rows_async<CIN>(x, xs_all + (buf ^ 1) * xsz, gn.b, gn.h0(), H, W, Wp);
         cpa_commit();
         const int npix = min(kC0Rows, H - h0) * W;
         for (int p = lane; p < npix; p += 32) {
@@ -1441,41 +1446,51 @@ conv0_lean_bwd_kernel(const float* __restrict__ x, const unsigned* __restrict__ 
     }
 }
 
-// one block per channel: d(beta), d(gamma), dW of conv 0 (and its zero bias gradient) from S, the patch
-// moments and the forward statistics
+// S[k][c] = sum_blk part[blk][k][c] in double: block <-> (k, 128-channel slice), thread <-> (channel, 1 of 8 interleaved
+// block ranges); every load is a coalesced 512 B row, the eight range sums are added in a fixed order
+__global__ void __launch_bounds__(1024)
+conv0_lean_bwd_colsum_kernel(const float* __restrict__ part, int nblk, int K1, int C, double* __restrict__ S) {
+    __shared__ double red[8][128];
+    const int k = blockIdx.x, c = blockIdx.y * 128 + (threadIdx.x & 127), grp = threadIdx.x >> 7;
+    double a = 0.0;
+#pragma unroll 8
+    for (int b = grp; b < nblk; b += 8) a += (double)__ldg(part + ((long)b * K1 + k) * C + c);
+    red[grp][threadIdx.x & 127] = a;
+    __syncthreads();
+    if (grp == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t += red[r][threadIdx.x];
+        S[(long)k * C + c] = t;
+    }
+}
+
+// d(beta), d(gamma), dW of conv 0 (and its zero bias gradient) from S, the patch moments and the forward statistics;
+// one warp per channel, lane k <-> dW[c][k]
 __global__ void __launch_bounds__(256)
-conv0_lean_bwd_finalize_kernel(const float* __restrict__ part, int nblk, int cin, int C, const double* __restrict__ gram,
+conv0_lean_bwd_finalize_kernel(const double* __restrict__ S, int cin, int C, const double* __restrict__ gram,
                                const float* __restrict__ w, const float* __restrict__ bias,
                                const float* __restrict__ gamma, const float* __restrict__ stat,
                                float* __restrict__ dw, float* __restrict__ db, float* __restrict__ dgamma,
                                float* __restrict__ dbeta) {
-    __shared__ double S[32];
     __shared__ double gsh[18 * 19];
-    const int c = blockIdx.x, K = cin * 9, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int K = cin * 9;
     for (int i = threadIdx.x; i < K * (K + 1); i += blockDim.x) gsh[i] = gram[i];
-    for (int k = warp; k <= K; k += 8) {
-        double a = 0.0;
-#pragma unroll 5
-        for (int b = lane; b < nblk; b += 32) a += (double)__ldg(part + ((long)b * (K + 1) + k) * C + c);
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
-        if (lane == 0) S[k] = a;
-    }
     __syncthreads();
-    const int k = threadIdx.x;
-    if (k >= K) return;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, k = threadIdx.x & 31;
+    if (c >= C || k >= K) return;
     const float* wc = w + (long)c * K;
     const double mean = (double)stat[c], invstd = (double)stat[C + c], bc = (double)bias[c];
-    const double sum_dz = S[K];
+    const double sum_dz = S[(long)K * C + c];
     double sum_dz_y = bc * sum_dz, wg = 0.0;
     for (int k2 = 0; k2 < K; ++k2) {
-        sum_dz_y += (double)wc[k2] * S[k2];
+        sum_dz_y += (double)wc[k2] * S[(long)k2 * C + c];
         wg += (double)wc[k2] * gsh[k2 * (K + 1) + k];                  // G is symmetric
     }
     const double dg = invstd * (sum_dz_y - mean * sum_dz);             // sum dz * xhat
     const double mk = gsh[k * (K + 1) + K];
     const double tk = invstd * (wg + (bc - mean) * mk);                // mean over pixels of xhat * patch_k
-    dw[(long)c * K + k] = (float)((double)gamma[c] * invstd * (S[k] - sum_dz * mk - dg * tk));
+    dw[(long)c * K + k] = (float)((double)gamma[c] * invstd * (S[(long)k * C + c] - sum_dz * mk - dg * tk));
     if (k == 0) {
         dgamma[c] = (float)dg;
         dbeta[c] = (float)sum_dz;
@@ -1872,8 +1887,9 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
                 if (training) {
                     const int gblk = std::min(n_groups, (cin0 == 1 ? 5 : 3) * sm_count());
                     const unsigned wmagic = (unsigned)(((1ull << 32) + (unsigned)P.win[0] - 1) / (unsigned)P.win[0]);
-                    if (cin0 == 1) conv0_gram_kernel<1><<<gblk, GramDims<1>::THREADS, sm, st>>>(x, P.H, P.win[0], wmagic, gpi, n_groups, wsf(ws, P.part));
-                    else conv0_gram_kernel<2><<<gblk, GramDims<2>::THREADS, sm, st>>>(x, P.H, P.win[0], wmagic, gpi, n_groups, wsf(ws, P.part));
+                    const size_t gsm = 2 * (size_t)cin0 * (kC0Rows + 2) * (P.win[0] + 32) * 4;
+                    if (cin0 == 1) conv0_gram_kernel<1><<<gblk, GramDims<1>::THREADS, gsm, st>>>(x, P.H, P.win[0], wmagic, gpi, n_groups, wsf(ws, P.part));
+                    else conv0_gram_kernel<2><<<gblk, GramDims<2>::THREADS, gsm, st>>>(x, P.H, P.win[0], wmagic, gpi, n_groups, wsf(ws, P.part));
                     SED_POST_LAUNCH();
                     const int entries = K0 * (K0 + 1);
                     conv0_gram_reduce_kernel<<<(entries * 32 + 255) / 256, 256, 0, st>>>(
@@ -2298,8 +2314,11 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
                 else if (g.p == 5) conv0_lean_bwd_kernel<2, 5><<<grid, 256, bsm, st>>>(x, argw, dA, g, gpi, n_groups, part);
                 else conv0_lean_bwd_kernel<2, 2><<<grid, 256, bsm, st>>>(x, argw, dA, g, gpi, n_groups, part);
                 SED_POST_LAUNCH();
-                conv0_lean_bwd_finalize_kernel<<<P.C, 256, 0, st>>>(
-                    part, (int)grid.x, cin0, P.C, gram, params + P.conv_w[0], params + P.conv_b[0], params + P.bn_w[0], stat,
+                double* Ssum = reinterpret_cast<double*>(part + (size_t)grid.x * (K0 + 1) * P.C + 64);   // behind the partials
+                conv0_lean_bwd_colsum_kernel<<<dim3(K0 + 1, P.C / 128), 1024, 0, st>>>(part, (int)grid.x, K0 + 1, P.C, Ssum);
+                SED_POST_LAUNCH();
+                conv0_lean_bwd_finalize_kernel<<<(P.C * 32 + 255) / 256, 256, 0, st>>>(
+                    Ssum, cin0, P.C, gram, params + P.conv_w[0], params + P.conv_b[0], params + P.bn_w[0], stat,
                     grads + P.conv_w[0], grads + P.conv_b[0], grads + P.bn_w[0], grads + P.bn_b[0]);
                 SED_POST_LAUNCH();
                 (void)K0;

@@ -140,7 +140,8 @@ int make_plan(const sedb200_crnn_desc* d, int batch, Plan* p) {
         part = std::max(part, 64L * P.dout[j] * P.din[j]);
         part = std::max(part, ((BT + 127) / 128) * ((long)P.dout[j] * P.din[j] + P.dout[j]));     // per-block dW/db partials
     }
-    part = std::max(part, B * ((P.H + 7) / 8) * (long)std::max(2, P.cin[0] * 9 + 1) * P.C);   // direct block-0 partials
+    part = std::max(part, B * ((P.H + 7) / 8) * (long)std::max(2, P.cin[0] * 9 + 1) * P.C     // direct block-0 partials
+                              + 2L * (P.cin[0] * 9 + 1) * P.C + 64);                               // + their column sums (doubles)
     part = std::max(part, 148L * 16 * 2 * P.C);
     for (int i = 1; i < P.n_conv; ++i) part = std::max(part, 2L * P.C * B * ((P.H * P.win[i] + 127) / 128 + 1));   // conv-epilogue BN partials                                                 // BN backward sums
     if (head_fused_supported(P)) part = std::max(part, (long)head_fused_part_floats(P, (int)B));   // fused head partials
