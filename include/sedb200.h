@@ -79,6 +79,17 @@ int    sedb200_logmel_host_f32(const float* pcm_host, int n_clips, int n_ch, lon
                                int sr, int pad_mode, float* out_host,
                                void* scratch_dev, size_t scratch_bytes, void* stream);
 
+/* int16 PCM ingest ("int16/f32 PCM ingest so a real decoder can feed the kernel"): the same
+ * kernel reading 16-bit samples as a WAV file or `ffmpeg -f s16le` delivers them (feature.py:40-50 asks ffmpeg for
+ * f32le).  A sample s stands for the float32 value s / 32768 -- exact in fp32 -- so the result is bit-identical to
+ * sedb200_logmel_f32 on the converted signal; host -> device traffic is halved. */
+int    sedb200_logmel_i16(const short* pcm_dev, int n_clips, int n_ch, long n_samples,
+                          int sr, int pad_mode, float* out_dev, void* stream);
+size_t sedb200_logmel_host_scratch_i16(int n_clips, int n_ch, long n_samples);
+int    sedb200_logmel_host_i16(const short* pcm_host, int n_clips, int n_ch, long n_samples,
+                               int sr, int pad_mode, float* out_host,
+                               void* scratch_dev, size_t scratch_bytes, void* stream);
+
 /* Per-bin standardisation -- the step between the two halves of the hot path (feature.py:127-129:
  * sklearn.preprocessing.StandardScaler().fit_transform(X_train) / .transform(X_test)).
  * fit:   mean[c], var[c] (population variance), scale[c] = sqrt(var) (1.0 for constant columns) of x [rows][cols],
@@ -141,7 +152,8 @@ typedef struct sedb200_crnn_desc {
     int   dropout_each_block;          /* sed.py:107 applies it after every block */
     float bn_eps, bn_momentum;         /* nn.BatchNorm2d defaults 1e-5 / 0.1 */
     int   tensor_cores;                /* 1: conv contractions on tcgen05 (3-term bf16 split, fp32-grade) wherever the
-                                          shape allows (channels % 128 == 0, W | 128); 0: fp32 CUDA cores everywhere */
+                                          shape allows (channels % 128 == 0, W | 128; the first block with in_ch <= 2
+                                          and pool 2 or 5); 0: fp32 CUDA cores everywhere */
 } sedb200_crnn_desc;
 
 /* geometry helpers (host only, no GPU needed) */
@@ -185,7 +197,12 @@ int sedb200_crnn_head_fwd_bwd(const sedb200_crnn_desc* d, const float* params_de
 
 /* Backward of the last training forward held in ws_dev: grads_dev (same layout as params) is
  * OVERWRITTEN with d(loss)/d(params); dx_dev (optional, [B][in_ch][H][W]) receives d(loss)/d(x).
- * dlogits_dev == NULL: continue after sedb200_crnn_head_fwd_bwd (see above). */
+ * dlogits_dev == NULL: continue after sedb200_crnn_head_fwd_bwd (see above).
+ * Stream semantics: everything is ordered after the work already enqueued on `stream`, and everything enqueued on
+ * `stream` after the call returns is ordered after the whole backward pass.  Internally the GRU weight-gradient GEMMs
+ * run on a helper stream the library creates once per device (forked from and rejoined to `stream` with events; no
+ * host synchronisation).  The first conv block keeps no conv output ("lean block 0"): with dx_dev != NULL
+ * it is rebuilt from x_dev, which must therefore still hold the batch given to sedb200_crnn_forward. */
 int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params_dev, const float* x_dev,
                           int batch, unsigned long long seed, void* ws_dev, size_t ws_bytes,
                           const float* dlogits_dev, float* grads_dev, float* dx_dev, void* stream);

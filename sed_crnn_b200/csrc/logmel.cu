@@ -119,20 +119,33 @@ __device__ __forceinline__ void fft32(float2 (&v)[32]) {
     }
 }
 
+// PCM sample types: float32 as the reference decodes it (feature.py:45-50, ffmpeg -f f32le), or int16 as a WAV /
+// `-f s16le` decoder delivers it; an int16 sample s stands for the float32 value s / 32768 (exact), so both
+// ingest paths feed the same arithmetic
+__device__ __forceinline__ float ld_sample(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_sample(const short* p) { return (float)__ldg(p) * (1.0f / 32768.0f); }
+__device__ __forceinline__ float2 ld_pair(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+__device__ __forceinline__ float2 ld_pair(const short* p) {
+    const short2 v = __ldg(reinterpret_cast<const short2*>(p));
+    return make_float2((float)v.x * (1.0f / 32768.0f), (float)v.y * (1.0f / 32768.0f));
+}
+
 // sample `i` of a clip of S samples under librosa's centre padding
-__device__ __forceinline__ float padded_sample(const float* __restrict__ x, long S, long i, int pad_mode) {
-    if (i >= 0 && i < S) return __ldg(x + i);
+template <typename T>
+__device__ __forceinline__ float padded_sample(const T* __restrict__ x, long S, long i, int pad_mode) {
+    if (i >= 0 && i < S) return ld_sample(x + i);
     if (pad_mode == SEDB200_PAD_CONSTANT) return 0.0f;
-    if (S == 1) return __ldg(x);
+    if (S == 1) return ld_sample(x);
     const long period = 2 * (S - 1);
     long m = i % period;
     if (m < 0) m += period;
-    return __ldg(x + (m < S ? m : period - m));
+    return ld_sample(x + (m < S ? m : period - m));
 }
 
 // ------------------------------------------------------------------------------ the kernel
+template <typename T>
 __global__ void __launch_bounds__(kWarps * 32, 1)
-logmel_kernel(const float* __restrict__ pcm, float* __restrict__ out, int n_ch, long S, int n_frames,
+logmel_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, long S, int n_frames,
               long total_frames, int pad_mode, const LogmelTables* __restrict__ gtab) {
     extern __shared__ __align__(16) unsigned char smem[];
     LogmelTables& tab = *reinterpret_cast<LogmelTables*>(smem);
@@ -160,22 +173,21 @@ logmel_kernel(const float* __restrict__ pcm, float* __restrict__ out, int n_ch, 
             frame -= n_frames;
             ++cc;
         }
-        const float* __restrict__ xb = pcm + cc * S;
+        const T* __restrict__ xb = pcm + cc * S;
         const long start = (long)(frame - 1) * kHop;       // first sample of the frame (may be < 0)
 
         // ---- load + window: v[j] = z[lane + 32 j]
         float2 v[32];
         if (start >= 0 && start + kNfft <= S) {
-            const float* xs = xb + start;
-            if ((reinterpret_cast<uintptr_t>(xs) & 7) == 0) {
-                const float2* x2 = reinterpret_cast<const float2*>(xs);
+            const T* xs = xb + start;
+            if ((reinterpret_cast<uintptr_t>(xs) & (2 * sizeof(T) - 1)) == 0) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __ldg(x2 + lane + 32 * j);
+                for (int j = 0; j < 32; ++j) v[j] = ld_pair(xs + 2 * (lane + 32 * j));
             } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    v[j].x = __ldg(xs + 2 * (lane + 32 * j));
-                    v[j].y = __ldg(xs + 2 * (lane + 32 * j) + 1);
+                    v[j].x = ld_sample(xs + 2 * (lane + 32 * j));
+                    v[j].y = ld_sample(xs + 2 * (lane + 32 * j) + 1);
                 }
             }
         } else {
@@ -457,17 +469,10 @@ int get_tables(int sr, cudaStream_t stream, const LogmelTables** out) {
     return SEDB200_OK;
 }
 
-}  // namespace
-}  // namespace sedb200
 
-using namespace sedb200;
-
-extern "C" {
-
-long sedb200_logmel_frames(long n_samples) { return n_samples <= 0 ? 0 : 1 + n_samples / kHop; }
-
-int sedb200_logmel_f32(const float* pcm_dev, int n_clips, int n_ch, long n_samples, int sr, int pad_mode,
-                       float* out_dev, void* stream) {
+template <typename T>
+int logmel_launch(const T* pcm_dev, int n_clips, int n_ch, long n_samples, int sr, int pad_mode, float* out_dev,
+                  void* stream) {
     SED_REQUIRE(n_clips >= 0 && n_ch >= 1, SEDB200_EINVAL, "logmel: n_clips=%d n_ch=%d", n_clips, n_ch);
     SED_REQUIRE(n_samples >= 1, SEDB200_EINVAL, "logmel: empty signal (n_samples=%ld)", n_samples);
     SED_REQUIRE(sr > 0, SEDB200_EINVAL, "logmel: sr=%d", sr);
@@ -481,47 +486,84 @@ int sedb200_logmel_f32(const float* pcm_dev, int n_clips, int n_ch, long n_sampl
     const LogmelTables* tab = nullptr;
     rc = get_tables(sr, st, &tab);
     if (rc) return rc;
-    const long nfr = sedb200_logmel_frames(n_samples);
+    const long nfr = n_samples <= 0 ? 0 : 1 + n_samples / kHop;
     SED_REQUIRE(nfr < (1L << 31), SEDB200_ESHAPE, "logmel: %ld frames per clip", nfr);
     SED_REQUIRE((long)n_clips * n_ch < (1L << 31), SEDB200_ESHAPE, "logmel: %ld channel-clips", (long)n_clips * n_ch);
     const long total = (long)n_clips * n_ch * nfr;
     const long want = (total + kWarps - 1) / kWarps;
     const int grid = (int)std::min<long>(want, sm_count());
-    rc = ensure_dyn_smem((const void*)logmel_kernel, kSmemBytes);
+    rc = ensure_dyn_smem((const void*)logmel_kernel<T>, kSmemBytes);
     if (rc) return rc;
-    logmel_kernel<<<grid, kWarps * 32, kSmemBytes, st>>>(pcm_dev, out_dev, n_ch, n_samples, (int)nfr, total,
-                                                         pad_mode, tab);
+    logmel_kernel<T><<<grid, kWarps * 32, kSmemBytes, st>>>(pcm_dev, out_dev, n_ch, n_samples, (int)nfr, total,
+                                                            pad_mode, tab);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }
 
-size_t sedb200_logmel_host_scratch(int n_clips, int n_ch, long n_samples) {
+inline size_t logmel_scratch_bytes(int n_clips, int n_ch, long n_samples, int elem) {
     if (n_clips <= 0 || n_ch <= 0 || n_samples <= 0) return 0;
-    const size_t in = (size_t)n_clips * n_ch * n_samples * 4;
-    const size_t outb = (size_t)n_clips * sedb200_logmel_frames(n_samples) * n_ch * kMel * 4;
+    const size_t in = (size_t)n_clips * n_ch * n_samples * elem;
+    const size_t outb = (size_t)n_clips * (1 + n_samples / kHop) * n_ch * kMel * 4;
     return ((in + 255) & ~(size_t)255) + outb;
 }
 
-int sedb200_logmel_host_f32(const float* pcm_host, int n_clips, int n_ch, long n_samples, int sr, int pad_mode,
-                            float* out_host, void* scratch_dev, size_t scratch_bytes, void* stream) {
+template <typename T>
+int logmel_host(const T* pcm_host, int n_clips, int n_ch, long n_samples, int sr, int pad_mode, float* out_host,
+                void* scratch_dev, size_t scratch_bytes, void* stream) {
     SED_REQUIRE(n_clips >= 0 && n_ch >= 1 && n_samples >= 1, SEDB200_EINVAL, "logmel_host: bad shape");
     if (n_clips == 0) return SEDB200_OK;
     SED_REQUIRE(pcm_host && out_host && scratch_dev, SEDB200_EINVAL, "logmel_host: null buffer");
-    const size_t need = sedb200_logmel_host_scratch(n_clips, n_ch, n_samples);
+    const size_t need = logmel_scratch_bytes(n_clips, n_ch, n_samples, (int)sizeof(T));
     SED_REQUIRE(scratch_bytes >= need, SEDB200_EWORKSPACE, "logmel_host: scratch %zu < %zu bytes", scratch_bytes, need);
     int rc = require_sm100();
     if (rc) return rc;
     cudaStream_t st = as_stream(stream);
-    const size_t in = (size_t)n_clips * n_ch * n_samples * 4;
-    const size_t outb = (size_t)n_clips * sedb200_logmel_frames(n_samples) * n_ch * kMel * 4;
-    float* d_in = reinterpret_cast<float*>(scratch_dev);
+    const size_t in = (size_t)n_clips * n_ch * n_samples * sizeof(T);
+    const size_t outb = (size_t)n_clips * (1 + n_samples / kHop) * n_ch * kMel * 4;
+    T* d_in = reinterpret_cast<T*>(scratch_dev);
     float* d_out = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch_dev) + ((in + 255) & ~(size_t)255));
     SED_CUDA_OK(cudaMemcpyAsync(d_in, pcm_host, in, cudaMemcpyHostToDevice, st));
-    rc = sedb200_logmel_f32(d_in, n_clips, n_ch, n_samples, sr, pad_mode, d_out, stream);
+    rc = logmel_launch<T>(d_in, n_clips, n_ch, n_samples, sr, pad_mode, d_out, stream);
     if (rc) return rc;
     SED_CUDA_OK(cudaMemcpyAsync(out_host, d_out, outb, cudaMemcpyDeviceToHost, st));
     SED_CUDA_OK(cudaStreamSynchronize(st));
     return SEDB200_OK;
+}
+
+}  // namespace
+}  // namespace sedb200
+
+using namespace sedb200;
+
+extern "C" {
+
+long sedb200_logmel_frames(long n_samples) { return n_samples <= 0 ? 0 : 1 + n_samples / kHop; }
+
+int sedb200_logmel_f32(const float* pcm_dev, int n_clips, int n_ch, long n_samples, int sr, int pad_mode,
+                       float* out_dev, void* stream) {
+    return logmel_launch<float>(pcm_dev, n_clips, n_ch, n_samples, sr, pad_mode, out_dev, stream);
+}
+
+int sedb200_logmel_i16(const short* pcm_dev, int n_clips, int n_ch, long n_samples, int sr, int pad_mode,
+                       float* out_dev, void* stream) {
+    return logmel_launch<short>(pcm_dev, n_clips, n_ch, n_samples, sr, pad_mode, out_dev, stream);
+}
+
+size_t sedb200_logmel_host_scratch(int n_clips, int n_ch, long n_samples) {
+    return logmel_scratch_bytes(n_clips, n_ch, n_samples, 4);
+}
+size_t sedb200_logmel_host_scratch_i16(int n_clips, int n_ch, long n_samples) {
+    return logmel_scratch_bytes(n_clips, n_ch, n_samples, 2);
+}
+
+int sedb200_logmel_host_f32(const float* pcm_host, int n_clips, int n_ch, long n_samples, int sr, int pad_mode,
+                            float* out_host, void* scratch_dev, size_t scratch_bytes, void* stream) {
+    return logmel_host<float>(pcm_host, n_clips, n_ch, n_samples, sr, pad_mode, out_host, scratch_dev, scratch_bytes, stream);
+}
+
+int sedb200_logmel_host_i16(const short* pcm_host, int n_clips, int n_ch, long n_samples, int sr, int pad_mode,
+                            float* out_host, void* scratch_dev, size_t scratch_bytes, void* stream) {
+    return logmel_host<short>(pcm_host, n_clips, n_ch, n_samples, sr, pad_mode, out_host, scratch_dev, scratch_bytes, stream);
 }
 
 int sedb200_mel_filterbank(int sr, float* out_host) {

@@ -31,13 +31,14 @@ def n_frames(n_samples: int) -> int:
 
 def mbe_device(pcm: torch.Tensor, sr: int = SR, pad_mode: str = DEFAULT_PAD_MODE,
                out: torch.Tensor | None = None) -> torch.Tensor:
-    """Device-resident form.  pcm: CUDA float32 [S], [n_ch, S] or [n_clips, n_ch, S] ->
+    """Device-resident form.  pcm: CUDA float32 (or int16, value = s / 32768) [S], [n_ch, S] or [n_clips, n_ch, S] ->
     [frames, 40], [frames, n_ch*40] or [n_clips, frames, n_ch*40] on the same device, enqueued on
     the current stream (no synchronisation)."""
     if not (isinstance(pcm, torch.Tensor) and pcm.is_cuda):
         raise TypeError("mbe_device needs a CUDA tensor (no CPU fallback)")
-    if pcm.dtype != torch.float32:
-        raise TypeError("pcm must be float32 (feature.py:50 decodes to f32le)")
+    if pcm.dtype not in (torch.float32, torch.int16):
+        raise TypeError("pcm must be float32 (feature.py:50 decodes to f32le) or int16 (s16le / WAV samples, "
+                        "value = s / 32768)")
     shape = pcm.shape
     if pcm.dim() == 1:
         n_clips, n_ch, S = 1, 1, shape[0]
@@ -58,16 +59,17 @@ def mbe_device(pcm: torch.Tensor, sr: int = SR, pad_mode: str = DEFAULT_PAD_MODE
             or out.device != pcm.device:
         raise ValueError(f"out must be contiguous float32 {oshape} on {pcm.device}")
     with torch.cuda.device(pcm.device):
-        _lib.check(_lib.lib().sedb200_logmel_f32(
-            pcm.data_ptr(), n_clips, n_ch, S, int(sr), _lib.PAD_MODES[pad_mode], out.data_ptr(),
-            _lib.current_stream_ptr()))
+        fn = _lib.lib().sedb200_logmel_i16 if pcm.dtype == torch.int16 else _lib.lib().sedb200_logmel_f32
+        _lib.check(fn(pcm.data_ptr(), n_clips, n_ch, S, int(sr), _lib.PAD_MODES[pad_mode], out.data_ptr(),
+                      _lib.current_stream_ptr()))
     return out
 
 
 def mbe_batch(pcm: np.ndarray, sr: int = SR, pad_mode: str = DEFAULT_PAD_MODE,
               device: str | torch.device = "cuda") -> np.ndarray:
-    """Host form for a batch: float32 [n_clips, n_ch, S] -> float32 [n_clips, frames, n_ch*40]."""
-    x = np.ascontiguousarray(pcm, dtype=np.float32)
+    """Host form for a batch: float32 (or int16) [n_clips, n_ch, S] -> float32 [n_clips, frames, n_ch*40]."""
+    pcm = np.asarray(pcm)
+    x = np.ascontiguousarray(pcm, dtype=np.int16 if pcm.dtype == np.int16 else np.float32)
     if x.ndim != 3:
         raise ValueError("mbe_batch takes [n_clips, n_ch, S]")
     d = torch.from_numpy(x).to(device, non_blocking=False)
@@ -76,7 +78,8 @@ def mbe_batch(pcm: np.ndarray, sr: int = SR, pad_mode: str = DEFAULT_PAD_MODE,
 
 def _mbe(y: np.ndarray, sr: int = SR) -> np.ndarray:
     """feature._mbe (feature.py:55-59): mono float32 PCM -> log-mel (frames, 40), host in / host out."""
-    y = np.ascontiguousarray(y, dtype=np.float32)
+    y = np.asarray(y)
+    y = np.ascontiguousarray(y, dtype=np.int16 if y.dtype == np.int16 else np.float32)   # int16: s16le samples
     if y.ndim != 1:
         raise ValueError("_mbe takes a mono 1-D signal (feature.py:45 decodes with -ac 1)")
     if y.shape[0] == 0:

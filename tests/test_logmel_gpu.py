@@ -126,3 +126,28 @@ def test_standard_scaler_matches_sklearn(feat):
     np.testing.assert_allclose(got_te, want_te, rtol=0, atol=2e-5)
     d = mine.transform(torch.from_numpy(Xte).cuda())
     assert d.is_cuda and torch.equal(d.cpu(), torch.from_numpy(got_te))
+
+
+@pytest.mark.parametrize("n_ch,n", [(1, 1), (1, 2047), (2, 30001), (1, 44100), (2, 1024 * 9)])
+@pytest.mark.parametrize("pad_mode", ["constant", "reflect"])
+def test_int16_ingest_is_bit_identical_to_float(feat, n_ch, n, pad_mode):
+    """sedb200_logmel_i16: a 16-bit sample s stands for the float32 value s / 32768, which is exact,
+    so the int16 path must give the very bits of the float32 path on the converted signal -- including odd clip
+    lengths (unaligned frame starts of the second channel) and both padding rules."""
+    rng = np.random.default_rng(7 + n)
+    pcm16 = rng.integers(-32768, 32768, size=(n_ch, n), dtype=np.int16)
+    pcm16[pcm16 == 0] = 1                                   # digital silence is log(0) = -inf (feature.py:59)
+    as_float = (pcm16.astype(np.float32) / np.float32(32768.0))
+    a = feat.mbe_device(torch.from_numpy(pcm16).cuda(), pad_mode=pad_mode)
+    b = feat.mbe_device(torch.from_numpy(as_float).cuda(), pad_mode=pad_mode)
+    assert torch.equal(a, b)
+    want = L.mbe_multichannel(as_float, pad_mode=pad_mode)
+    assert close(a.cpu().numpy(), want) <= RTOL
+
+
+def test_int16_host_drop_in(feat):
+    y = L.synth_clip(5, 2 * 44100, 1, "mix")[0]
+    y16 = np.round(np.clip(y, -1, 1) * 32767).astype(np.int16)
+    got = feat._mbe(y16, feat.SR)
+    want = L.mbe(y16.astype(np.float32) / np.float32(32768.0))
+    assert got.shape == want.shape and close(got, want) <= RTOL
