@@ -179,6 +179,7 @@ class DevicePrefetcher:
         self.freed = [torch.cuda.Event(), torch.cuda.Event()]
         self.slot = 0
         self.pending = None
+        self._deferred = False
         self._enqueue()
 
     def _enqueue(self):
@@ -204,14 +205,23 @@ class DevicePrefetcher:
         return self
 
     def __next__(self):
+        if self._deferred:                    # the consumer never called release(): start the copy now
+            self._deferred = False
+            self._enqueue()
         if self.pending is None:
             raise StopIteration
         k = self.pending
         torch.cuda.current_stream(self.device).wait_event(self.ready[k])
         out = self.bufs[k]
-        self._enqueue()                       # start copying the following batch right away
+        # the copy of the following batch (into the OTHER buffer pair) is enqueued by release(), i.e. after the consumer
+        # has enqueued its own work: a consumer that synchronises every step (sed.py:138 reads the loss) then finds the
+        # GPU busy ~25 us earlier
+        self._deferred = True
         return out[0], out[1], k
 
     def release(self, k: int) -> None:
         """call after the work that reads buffer pair k has been enqueued on the current stream"""
         self.freed[k].record(torch.cuda.current_stream(self.device))
+        if self._deferred:
+            self._deferred = False
+            self._enqueue()
