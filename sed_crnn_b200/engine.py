@@ -228,6 +228,10 @@ class CRNNEngine:
     def train_step(self, x: torch.Tensor, y: torch.Tensor):
         """One optimisation step on device-resident (x, y).  Returns (loss, probs) as device tensors
         (views of engine-owned buffers, valid until the next call)."""
+        if self.xch is None and self.fused_head and x.is_contiguous() and y.is_contiguous():
+            from . import parallel
+            if parallel.world_info(self.pg)[1] == 1:
+                return self._train_step_single(x, y)
         if self.xch is not None:
             self.grads = self.xch.next_grad_buffer()                  # this step's half of the exchange region
         if self.fused_head:
@@ -250,6 +254,38 @@ class CRNNEngine:
         world = round(1.0 / scale)
         self.optimizer_step(world)
         return loss, probs
+
+    def _train_step_single(self, x, y):
+        """train_step for the common single-process case (fused head, no gradient exchange): the same four library
+        calls as the general route, with the argument marshalling done once -- a caller that reads the loss every
+        step (sed.py:138) waits for this host code while the GPU is idle."""
+        x = self._check_x(x)
+        B = x.shape[0]
+        shape = self.cfg.target_shape(B)
+        if tuple(y.shape) != tuple(shape) or y.dtype != torch.float32 or not y.is_cuda:
+            raise ValueError("targets must be CUDA float32 with the logits' shape")
+        ws = self._workspace(B)
+        logits, probs = self._buf(("logits", B), shape), self._buf(("probs", tuple(shape)), shape)
+        L, desc = self.L, C.byref(self.desc)
+        seed = self._last_seed = self.seed + self.step_count
+        p_params, p_grads, p_ws, n_ws, p_x = (self.params.data_ptr(), self.grads.data_ptr(), ws.data_ptr(), ws.numel(),
+                                              x.data_ptr())
+        p_scal = self._scalars.data_ptr()
+        with torch.cuda.device(self.device):
+            st = _lib.current_stream_ptr()
+            _lib.check(L.sedb200_crnn_forward(desc, p_params, self.bn_state.data_ptr(), p_x, B, 1, seed, p_ws, n_ws,
+                                              None, st))
+            self.num_batches_tracked += 1
+            _lib.check(L.sedb200_crnn_head_fwd_bwd(desc, p_params, B, p_ws, n_ws, y.data_ptr(), self.loss_kind,
+                                                   self.alpha, self.gamma, 1.0, logits.data_ptr(), probs.data_ptr(),
+                                                   p_scal, p_grads, st))
+            _lib.check(L.sedb200_crnn_backward(desc, p_params, p_x, B, seed, p_ws, n_ws, None, p_grads, None, st))
+            self.step_count += 1
+            _lib.check(L.sedb200_clip_adam(p_params, p_grads, self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                           self.params.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
+                                           self.weight_decay, self.step_count, self.clip, 1.0, p_scal + 4,
+                                           self._scratch.data_ptr(), self._scratch.numel() * 4, st))
+        return self._scalars[0], probs
 
     @torch.no_grad()
     def predict_proba(self, x: torch.Tensor, training_bn: bool = False) -> torch.Tensor:
