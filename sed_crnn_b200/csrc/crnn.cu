@@ -1866,8 +1866,42 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
     cudaStream_t st = as_stream(stream);
     const long B = batch;
 
+    // ---- operand planes of the weights (conv blocks on tcgen05: forward and flipped data-gradient layout; W_ih of the
+    //      tensor-core GRU layers), built on the side stream while block 0 runs; the backward pass reuses them
+    SideStream* wside = nullptr;
+    bool wp_pending = false;
+    if (P.weight_planes_ahead) {
+        rc = side_stream(&wside);
+        if (rc) return rc;
+        cudaStream_t ss = wside->st;
+        SED_CUDA_OK(cudaEventRecord(wside->fork[0], st));
+        SED_CUDA_OK(cudaStreamWaitEvent(ss, wside->fork[0], 0));
+        for (int i = 1; i < P.n_conv; ++i) {
+            if (!P.conv_tc_all[i]) continue;
+            for (int dg = 0; dg < 2; ++dg) {
+                rc = conv_tc_weight_planes(params + P.conv_w[i], P.cin[i], P.C, dg, reinterpret_cast<char*>(ws) + P.wpl[i][dg], ss);
+                if (rc) return rc;
+            }
+        }
+        for (int l = 0; l < P.n_gru; ++l) {
+            if (!P.gru_tc[l]) continue;
+            const size_t wpb = ((size_t)6 * P.gh[l] * P.gin[l] * 2 + 1023) & ~(size_t)1023;
+            char* wp = reinterpret_cast<char*>(ws) + P.wihp[l];
+            rc = split_planes(params + P.wih[l], wp, wp + wpb, 6L * P.gh[l] * P.gin[l], ss);
+            if (rc) return rc;
+        }
+        SED_CUDA_OK(cudaEventRecord(wside->done[0], ss));
+        wp_pending = true;
+    }
+    struct WpJoin {             // rejoin on every way out, and before the first consumer
+        SideStream*& s; bool& pending; cudaStream_t st;
+        void now() { if (pending) { cudaStreamWaitEvent(st, s->done[0], 0); pending = false; } }
+        ~WpJoin() { now(); }
+    } wp_join{wside, wp_pending, st};
+
     // ---- conv blocks
     for (int i = 0; i < P.n_conv; ++i) {
+        if (i > 0) wp_join.now();
         const float* in = i == 0 ? x : wsf(ws, P.act[i - 1]);
         const InStrides s = in_strides(P, d, i);
         const int M = (int)(B * P.H * P.win[i]), K = 9 * P.cin[i];
@@ -1953,9 +1987,9 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
             // plane-native: input planes were written by the previous block's pool kernel; BatchNorm partial sums
             // come out of the conv epilogue
             const char* ap = reinterpret_cast<const char*>(ws) + P.actp[i - 1];
-            rc = conv_tc_planes(ap, ap + P.act_plane_bytes[i - 1], params + P.conv_w[i], params + P.conv_b[i], y,
-                                training ? wsf(ws, P.part) : nullptr, batch, P.H, P.win[i], P.cin[i], P.C, 0,
-                                wsf(ws, P.tc), st);
+            rc = conv_tc_planes_w(ap, ap + P.act_plane_bytes[i - 1], reinterpret_cast<const char*>(ws) + P.wpl[i][0],
+                                  params + P.conv_b[i], y, training ? wsf(ws, P.part) : nullptr, batch, P.H, P.win[i],
+                                  P.cin[i], P.C, 0, st);
             if (rc) return rc;
             nblk = conv_tc_stat_tiles(batch, P.H, P.win[i]);
         } else if (i > 0 && d->tensor_cores && conv_tc_supported(P.H, P.win[i], P.cin[i], P.C)) {
@@ -2013,18 +2047,17 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
     // ---- BiGRU stack
     const int BT = (int)(B * P.T);
     const float* seq = wsf(ws, P.act[P.n_conv - 1]);
+    wp_join.now();
     for (int l = 0; l < P.n_gru; ++l) {
         const int h = P.gh[l], in = P.gin[l];
         float* gi = wsf(ws, P.gi[l]);
 { char _nm[40]; snprintf(_nm, sizeof _nm, "gru%d.proj", l); SED_PROF(_nm, st);
         if (P.gru_tc[l]) {
-            // tcgen05: X planes are kept for the backward dW_ih, W_ih planes are rebuilt every step (tiny)
+            // tcgen05: X planes are kept for the backward dW_ih; the W_ih planes were built on the side stream
             const size_t xpb = ((size_t)BT * in * 2 + 1023) & ~(size_t)1023, wpb = ((size_t)6 * h * in * 2 + 1023) & ~(size_t)1023;
             char* xp = reinterpret_cast<char*>(ws) + P.gxp[l];
-            char* wp = reinterpret_cast<char*>(ws) + P.tc;
+            const char* wp = reinterpret_cast<const char*>(ws) + P.wihp[l];
             rc = split_planes(seq, xp, xp + xpb, (long)BT * in, st);
-            if (rc) return rc;
-            rc = split_planes(params + P.wih[l], wp, wp + wpb, 6L * h * in, st);
             if (rc) return rc;
             rc = gemm_tc(xp, xp + xpb, 0, wp, wp + wpb, 0, BT, 6 * h, in, params + P.bih[l], gi, 6L * h, 0, nullptr, st);
         } else {
@@ -2193,9 +2226,7 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
             SED_CUDA_OK(cudaEventRecord(side->done[par], ss));
             side_busy[par] = true;
             // ---- main stream: d(xin)[m][k] = sum_n6 dgi[m][n6] * W_ih[n6][k]    (W_ih stored [n6][k] = [K][N]: MN-major)
-            char* wp = reinterpret_cast<char*>(ws) + P.tc;
-            rc = split_planes(params + P.wih[l], wp, wp + wpb, 6L * h * in, st);
-            if (rc) return rc;
+            const char* wp = reinterpret_cast<const char*>(ws) + P.wihp[l];          // built by the forward pass
             float* dxin2 = wsf(ws, P.dseq[cur ^ 1]);
             rc = gemm_tc(gi_hi, gi_lo, 0, wp, wp + wpb, 1, BT, in, 6 * h, nullptr, dxin2, in, 0, nullptr, st);
             if (rc) return rc;
@@ -2260,13 +2291,12 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
                 rc = split_planes(dgi, gp, gp + gpb, (long)BT * 6 * h, st);
                 if (rc) return rc;
             }
-            rc = split_planes(params + P.wih[l], wp, wp + wpb, 6L * h * in, st);
-            if (rc) return rc;
+            const char* wihp = reinterpret_cast<const char*>(ws) + P.wihp[l];          // built by the forward pass
             // dW_ih[n6][k] = sum_m dgi[m][n6] * xin[m][k]        (both operands stored [B*T][.]: MN-major)
             rc = gemm_tc(gi_hi, gi_lo, 1, xp, xp + xpb, 1, 6 * h, in, BT, nullptr, grads + P.wih[l], in, 1, tpart, st);
             if (rc) return rc;
             // d(xin)[m][k] = sum_n6 dgi[m][n6] * W_ih[n6][k]    (W_ih stored [n6][k] = [K][N]: MN-major)
-            rc = gemm_tc(gi_hi, gi_lo, 0, wp, wp + wpb, 1, BT, in, 6 * h, nullptr, dxin, in, 0, nullptr, st);
+            rc = gemm_tc(gi_hi, gi_lo, 0, wihp, wihp + wpb, 1, BT, in, 6 * h, nullptr, dxin, in, 0, nullptr, st);
             if (rc) return rc;
         } else {
         // dW_ih[n6][k] = sum_m dgi[m][n6] * xin[m][k]
@@ -2436,8 +2466,8 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
             float* dprev = wsf(ws, P.dact[i & 1]);
 { char _nm[40]; snprintf(_nm, sizeof _nm, "conv%d.dgrad", i); SED_PROF(_nm, st);
             if (P.conv_tc_all[i])
-                rc = conv_tc_planes(dyh, dyl, params + P.conv_w[i], nullptr, dprev, nullptr, batch, P.H, P.win[i],
-                                    P.cin[i], P.C, 1, wsf(ws, P.tc), st);
+                rc = conv_tc_planes_w(dyh, dyl, reinterpret_cast<const char*>(ws) + P.wpl[i][1], nullptr, dprev, nullptr,
+                                      batch, P.H, P.win[i], P.cin[i], P.C, 1, st);     // planes built by the forward pass
             else if (d->tensor_cores && conv_tc_supported(P.H, P.win[i], P.C, P.cin[i]))
                 rc = conv_tc_forward(dy, params + P.conv_w[i], nullptr, dprev, batch, P.H, P.win[i], P.cin[i], P.C, 1,
                                      wsf(ws, P.tc), P.tc_bytes, st);

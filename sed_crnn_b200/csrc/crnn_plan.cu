@@ -213,6 +213,19 @@ int make_plan(const sedb200_crnn_desc* d, int batch, Plan* p) {
         P.gbias[1] = take(gb);
         P.tc_side = take((long)(side / 4) + 64);
     }
+    for (int i = 0; i < P.n_conv; ++i) {
+        P.wpl[i][0] = P.wpl[i][1] = 0;
+        if (!P.conv_tc_all[i]) continue;
+        P.wpl[i][0] = take((long)(conv_tc_weight_scratch_bytes(P.cin[i], P.C) / 4));
+        P.wpl[i][1] = take((long)(conv_tc_weight_scratch_bytes(P.cin[i], P.C) / 4));
+        P.weight_planes_ahead = true;
+    }
+    for (int l = 0; l < P.n_gru; ++l) {
+        P.wihp[l] = 0;
+        if (!P.gru_tc[l]) continue;
+        P.wihp[l] = take((long)(2 * plane(6L * P.gh[l] * P.gin[l]) / 4));
+        P.weight_planes_ahead = true;
+    }
     P.tc_bytes = tc;
     P.tc = take((long)(tc / 4) + 64);
     P.ws_bytes = o;

@@ -38,6 +38,10 @@ struct Plan {
     // goes on with d(input) and the next scan -- gradient planes and bias partials alternate by layer parity, and the
     // side stream has its own GEMM scratch
     size_t dgp2 = 0, gbias[2] = {0, 0}, tc_side = 0;
+    // operand planes of the WEIGHTS, built once per step on the side stream while block 0 runs: conv weights of the
+    // plane-native blocks (forward layout and the flipped data-gradient layout) and W_ih of the tensor-core GRU layers
+    size_t wpl[SEDB200_MAX_CONV][2], wihp[SEDB200_MAX_GRU];
+    bool weight_planes_ahead = false;
     // plane-native tensor-core flow: block i (>= 1) runs fwd, dgrad and wgrad on tcgen05 and exchanges
     // bf16 hi/lo planes with its neighbours instead of fp32 tensors
     bool conv_tc_all[SEDB200_MAX_CONV];

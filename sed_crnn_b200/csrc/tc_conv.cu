@@ -422,16 +422,33 @@ bool conv_tc_supported(int H, int W, int Cin, int Cout) {
 
 size_t conv_tc_weight_scratch_bytes(int Cin, int Cout) { return 2 * (((size_t)9 * Cout * Cin * 2 + 1023) & ~(size_t)1023); }
 
+// B-operand planes of a conv weight (forward or flipped / transposed for the data gradient) into `wplanes`
+// (conv_tc_weight_scratch_bytes); they stay valid until the weight changes
+int conv_tc_weight_planes(const float* w, int Cin, int Cout, int dgrad, void* wplanes, cudaStream_t st) {
+    const size_t wp = ((size_t)9 * Cout * Cin * 2 + 1023) & ~(size_t)1023;
+    __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(wplanes);
+    __nv_bfloat16* w_lo = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(wplanes) + wp);
+    weight_planes_kernel<<<(int)std::min<long>((9L * Cout * Cin + 255) / 256, 1184), 256, 0, st>>>(w, Cout, Cin, dgrad, w_hi, w_lo);
+    SED_POST_LAUNCH();
+    return SEDB200_OK;
+}
+
 // activation planes given ([B][H][W][Kc] bf16 hi / lo); weight planes are rebuilt into wscratch (tiny)
 int conv_tc_planes(const void* a_hi, const void* a_lo, const float* w, const float* bias, float* out, float* stats,
                    int B, int H, int W, int Cin, int Cout, int dgrad, void* wscratch, cudaStream_t st) {
+    const int rc = conv_tc_weight_planes(w, Cin, Cout, dgrad, wscratch, st);
+    if (rc) return rc;
+    return conv_tc_planes_w(a_hi, a_lo, wscratch, bias, out, stats, B, H, W, Cin, Cout, dgrad, st);
+}
+
+// same with the weight planes already built (conv_tc_weight_planes)
+int conv_tc_planes_w(const void* a_hi, const void* a_lo, const void* wplanes, const float* bias, float* out, float* stats,
+                     int B, int H, int W, int Cin, int Cout, int dgrad, cudaStream_t st) {
     const int Kc = dgrad ? Cout : Cin, Nc = dgrad ? Cin : Cout;
     SED_REQUIRE(conv_tc_supported(H, W, Kc, Nc), SEDB200_ESHAPE, "conv_tc: shape H=%d W=%d K=%d N=%d unsupported", H, W, Kc, Nc);
     const size_t wp = ((size_t)9 * Nc * Kc * 2 + 1023) & ~(size_t)1023;
-    __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(wscratch);
-    __nv_bfloat16* w_lo = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(wscratch) + wp);
-    weight_planes_kernel<<<(int)std::min<long>((9L * Cout * Cin + 255) / 256, 1184), 256, 0, st>>>(w, Cout, Cin, dgrad, w_hi, w_lo);
-    SED_POST_LAUNCH();
+    const __nv_bfloat16* w_hi = reinterpret_cast<const __nv_bfloat16*>(wplanes);
+    const __nv_bfloat16* w_lo = reinterpret_cast<const __nv_bfloat16*>(reinterpret_cast<const char*>(wplanes) + wp);
 
     const int Ht = kTileM / W;
     CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;

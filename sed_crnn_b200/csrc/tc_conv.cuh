@@ -26,6 +26,9 @@ size_t conv_tc_weight_scratch_bytes(int Cin, int Cout);
 int conv_tc_stat_tiles(int B, int H, int W);
 int conv_tc_planes(const void* a_hi, const void* a_lo, const float* w, const float* bias, float* out, float* stats,
                    int B, int H, int W, int Cin, int Cout, int dgrad, void* wscratch, cudaStream_t st);
+int conv_tc_weight_planes(const float* w, int Cin, int Cout, int dgrad, void* wplanes, cudaStream_t st);
+int conv_tc_planes_w(const void* a_hi, const void* a_lo, const void* wplanes, const float* bias, float* out, float* stats,
+                     int B, int H, int W, int Cin, int Cout, int dgrad, cudaStream_t st);
 size_t wgrad_tc_part_bytes(int Cin, int Cout);
 int wgrad_tc_planes(const void* y_hi, const void* y_lo, const void* x_hi, const void* x_lo, float* dw, int B, int H,
                     int W, int Cin, int Cout, float* part, cudaStream_t st);
