@@ -54,6 +54,23 @@ int  ensure_dyn_smem(const void* func, int bytes);
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // ------------------------------------------------------------------ device helpers
+// p[0] + p[stride] + ... (n terms) added in ascending order, U loads in flight at a time: the partial-sum
+// finalizers are chains of dependent global loads otherwise (one L2 round trip per term)
+template <int U, typename Acc>
+__device__ __forceinline__ Acc ordered_sum(const float* __restrict__ p, long stride, int n) {
+    Acc a = (Acc)0;
+    int k = 0;
+    for (; k + U <= n; k += U) {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = __ldg(p + (long)(k + u) * stride);
+#pragma unroll
+        for (int u = 0; u < U; ++u) a += (Acc)v[u];
+    }
+    for (; k < n; ++k) a += (Acc)__ldg(p + (long)k * stride);
+    return a;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -133,14 +133,10 @@ struct EpiStrided {                     // dx in NCHW from m = (b,h,w), n = ci
 __device__ __forceinline__ void reduce_pair(const float* __restrict__ part, int nblk, int C, int c, double& s,
                                             double& ss) {
     __shared__ double sh[2][4];
-    double a = 0.0, b = 0.0;
-    // the strided loads of several iterations are issued together (latency-bound otherwise); the order of the
-    // additions is unchanged
-#pragma unroll 8
-    for (int k = threadIdx.x; k < nblk; k += 128) {
-        a += (double)__ldg(part + ((long)k * 2 + 0) * C + c);
-        b += (double)__ldg(part + ((long)k * 2 + 1) * C + c);
-    }
+    // thread t owns partials t, t + 128, ...
+    const int mine = nblk > (int)threadIdx.x ? (nblk - (int)threadIdx.x + 127) / 128 : 0;
+    double a = ordered_sum<8, double>(part + ((long)threadIdx.x * 2 + 0) * C + c, 256L * C, mine);
+    double b = ordered_sum<8, double>(part + ((long)threadIdx.x * 2 + 1) * C + c, 256L * C, mine);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         a += __shfl_xor_sync(0xffffffffu, a, o);
@@ -1145,9 +1141,8 @@ __global__ void conv0_gram_reduce_kernel(const float* __restrict__ part, int nbl
     const int K = cin * 9, NE = K * (K + 1);
     const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (e >= NE) return;
-    double a = 0.0;
-#pragma unroll 4
-    for (int b = lane; b < nblk; b += 32) a += (double)__ldg(part + (long)b * NE + e);
+    const int mine = nblk > lane ? (nblk - lane + 31) / 32 : 0;
+    double a = ordered_sum<8, double>(part + (long)lane * NE + e, 32L * NE, mine);
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
     if (lane == 0) gram[e] = a * inv_n;
@@ -1452,9 +1447,8 @@ __global__ void __launch_bounds__(1024)
 conv0_lean_bwd_colsum_kernel(const float* __restrict__ part, int nblk, int K1, int C, double* __restrict__ S) {
     __shared__ double red[8][128];
     const int k = blockIdx.x, c = blockIdx.y * 128 + (threadIdx.x & 127), grp = threadIdx.x >> 7;
-    double a = 0.0;
-#pragma unroll 8
-    for (int b = grp; b < nblk; b += 8) a += (double)__ldg(part + ((long)b * K1 + k) * C + c);
+    const int mine = nblk > grp ? (nblk - grp + 7) / 8 : 0;
+    const double a = ordered_sum<8, double>(part + ((long)grp * K1 + k) * C + c, 8L * K1 * C, mine);
     red[grp][threadIdx.x & 127] = a;
     __syncthreads();
     if (grp == 0) {
@@ -1774,8 +1768,7 @@ __global__ void reduce_bias_partials_kernel(const float* __restrict__ part_b, fl
                                             float* __restrict__ dbhh, int n6, int B) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 2 * n6) return;
-    float acc = 0.0f;
-    for (int b = 0; b < B; ++b) acc += __ldg(part_b + (long)b * 2 * n6 + i);
+    const float acc = ordered_sum<16, float>(part_b + i, 2L * n6, B);
     if (i < n6) dbih[i] = acc;
     else dbhh[i - n6] = acc;
 }

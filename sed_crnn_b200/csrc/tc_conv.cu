@@ -402,9 +402,7 @@ wgrad_reduce_kernel(const float* __restrict__ part, int slices, int Cout, int Ci
         const int ci = (int)(i % Cin);
         const int co = (int)((i / Cin) % Cout);
         const int tap = (int)(i / ((long)Cin * Cout));
-        float acc = 0.0f;
-        for (int z = 0; z < slices; ++z) acc += __ldg(part + (long)z * n + i);
-        dw[((long)co * Cin + ci) * 9 + tap] = acc;
+        dw[((long)co * Cin + ci) * 9 + tap] = ordered_sum<8, float>(part + i, n, slices);
     }
 }
 

@@ -8,9 +8,7 @@ namespace sedb200 {
 __global__ void reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, long n,
                                        int splits) {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-        float s = 0.0f;
-        for (int z = 0; z < splits; ++z) s += part[(long)z * n + i];
-        out[i] = s;
+        out[i] = ordered_sum<8, float>(part + i, n, splits);
     }
 }
 
