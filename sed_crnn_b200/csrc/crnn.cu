@@ -2361,12 +2361,16 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         const long n_elem = B * P.H * P.win[i];                 // BN population per channel
         const int rows = 256 / (P.C / 4);
         const int nblk = (int)std::min<long>((n_pix_out + rows - 1) / rows, 148L * 16);
+        int sblk = nblk;                                          // blocks (= partials) of the sums pass
 { char _nm[40]; snprintf(_nm, sizeof _nm, "pool%d.bwd_sums", i); SED_PROF(_nm, st);
         const bool idx32 = n_pix_out < (1L << 31);
         const bool planes_out = (i + 1 < P.n_conv) && P.conv_tc_all[i + 1];      // what the forward pass stored
         if (idx32 && 256 % (P.C / 4) == 0) {
             const char* ap = reinterpret_cast<const char*>(ws) + P.actp[i];
-            bn_bwd_sums_act_kernel<<<nblk, 256, 0, st>>>(
+            // few long-lived blocks (4 per SM): the per-block prologue / shared-memory reduction / partial store and
+            // the finalizer's work shrink with the block count, the loads in flight do not
+            sblk = (int)std::min<long>(nblk, 148L * 4);
+            bn_bwd_sums_act_kernel<<<sblk, 256, 0, st>>>(
                 planes_out ? nullptr : wsf(ws, P.act[i]),
                 planes_out ? reinterpret_cast<const __nv_bfloat16*>(ap) : nullptr,
                 planes_out ? reinterpret_cast<const __nv_bfloat16*>(ap + P.act_plane_bytes[i]) : nullptr, stat, dA,
@@ -2377,7 +2381,7 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         SED_POST_LAUNCH();
 }
         float* bnsum = wsf(ws, P.bnsum);
-        bn_bwd_finalize_kernel<<<P.C, 128, 0, st>>>(part, nblk, P.C, n_elem, grads + P.bn_w[i],
+        bn_bwd_finalize_kernel<<<P.C, 128, 0, st>>>(part, sblk, P.C, n_elem, grads + P.bn_w[i],
                                                                  grads + P.bn_b[i], bnsum);
         SED_POST_LAUNCH();
         if (i == 0 && !dx && conv0_direct_ok(P.cin[0], P.C)) {

@@ -346,3 +346,34 @@ def test_input_gradient_with_lean_block0(pkg, preset, ov, batch):
             continue
         err = (va[name] - vb[name]).norm().item() / max(va[name].norm().item(), 1e-12)
         assert err <= 1e-3, (name, err)
+
+
+@pytest.mark.parametrize("tc,tol", [(False, 1e-3), (True, 3e-2)])
+def test_lean_block0_with_dropout_matches_general_route(pkg, tc, tol):
+    """Dropout on (every block, p = 0.5): the fused block-0 forward stores 'killed by ReLU or dropout' in bit 7 of the
+    winner byte, the general route (taken when d(input) is requested) recomputes the mask from the counter-based
+    generator.  Both must describe the same network: same parameter gradients (tensor-core conv 0 differs from the
+    rebuilt fp32 conv output by ~1e-5 relative, which can move a near-tie winner, hence the looser L2 gate there)."""
+    config, engine = pkg
+    cfg = replace(config.PRESETS["c2"], seq_len=32, dropout=0.5, tensor_cores=tc)
+    eng = engine.CRNNEngine(cfg, loss="bce", seed=11)
+    eng.init_default(1)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(cfg.input_shape(4), generator=g).cuda()
+    y = (torch.rand(cfg.target_shape(4), generator=g) < 0.3).float().cuda()
+    logits = eng.forward(x, training=True)
+    _, _, dlog = eng.loss_and_grad(logits, y)
+    logits = logits.clone()                                 # engine-owned buffer: the next forward overwrites it
+    dx = torch.empty_like(x)
+    g_general = eng.backward(x, dlog, dx=dx).clone()
+    g_lean = eng.backward(x, dlog).clone()
+    assert torch.isfinite(dx).all() and dx.abs().max().item() > 0
+    va, vb = eng.views(g_general), eng.views(g_lean)
+    for name in va:
+        if name.startswith("conv") and name.endswith("bias"):
+            continue
+        err = (va[name] - vb[name]).norm().item() / max(va[name].norm().item(), 1e-12)
+        assert err <= tol, (name, err)
+    # and the mask is really applied: a second forward with another seed gives different logits
+    other = eng.forward(x, training=True, seed=12345).clone()
+    assert not torch.equal(other, logits)
