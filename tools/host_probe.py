@@ -11,18 +11,21 @@ x = torch.randn(cfg.input_shape(B), device="cuda"); y = (torch.rand(cfg.target_s
 for _ in range(3): eng.train_step(x, y)
 torch.cuda.synchronize()
 L = eng.L
+sync_each = len(sys.argv) > 3 and sys.argv[3] == 'sync'
 acc = {}
 orig = {}
-for name in ("sedb200_crnn_forward", "sedb200_loss_fwd_bwd", "sedb200_crnn_backward", "sedb200_clip_adam"):
+for name in ("sedb200_crnn_forward", "sedb200_loss_fwd_bwd", "sedb200_crnn_head_fwd_bwd", "sedb200_crnn_backward", "sedb200_clip_adam"):
     f = getattr(L, name)
     def wrap(*a, _f=f, _n=name):
         t0 = time.perf_counter(); r = _f(*a); acc[_n] = acc.get(_n, 0.0) + time.perf_counter() - t0; return r
     orig[name] = f
     setattr(L, name, wrap)
-N = 20
+N = 200
 l0 = L.sedb200_launch_count()
 t0 = time.perf_counter()
-for _ in range(N): eng.train_step(x, y)
+for _ in range(N):
+    eng.train_step(x, y)
+    if sync_each: torch.cuda.synchronize()
 t_host = (time.perf_counter() - t0) / N * 1e3
 launches = (L.sedb200_launch_count() - l0) / N
 torch.cuda.synchronize()
