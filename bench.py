@@ -562,7 +562,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=["c1", "c2", "c5", "fork", "sedpy"])
     ap.add_argument("--ref-batch", type=int, default=16, help="CPU-baseline sample batch")
     ap.add_argument("--grad-exchange", default="auto", choices=["auto", "nccl", "p2p"])
-    ap.add_argument("--clock-period-ms", type=int, default=50, help="nvidia-smi sampling period during the run")
+    ap.add_argument("--clock-period-ms", type=int, default=20, help="nvidia-smi sampling period during the run")
     ap.add_argument("--no-logmel", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the C1 / C5 reference timings (N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU-baseline leg (profiling runs)")
