@@ -47,6 +47,13 @@ CASES = [
     ("c2", {"seq_len": 24, "conv_ch": 64}, 3, "focal", 1e-4, 1.0, False),
     ("c5", {"seq_len": 16, "conv_ch": 32, "gru_units": (64, 16, 8)}, 2, "bce", 1e-4, 1.0, False),
     ("c5", {"seq_len": 16, "gru_units": (64, 16, 8)}, 2, "bce", 1e-4, 1.0, True),   # 256 ch on tcgen05
+    # ragged geometry for the lean first block: H not a multiple of the 8-row groups, W not a multiple of the pool
+    # width (the left-over columns count in the BatchNorm statistics but never reach the output), pooling windows that
+    # do not fill the last 24-window tensor-core tile, both input-channel counts
+    ("c2", {"seq_len": 13, "n_freq": 43}, 2, "bce", 1e-4, 1.0, False),
+    ("c2", {"seq_len": 13, "n_freq": 43}, 2, "bce", 1e-4, 1.0, True),
+    ("c1", {"seq_len": 9, "n_freq": 22}, 3, "focal", 1e-4, 1.0, False),
+    ("c1", {"seq_len": 9, "n_freq": 22}, 3, "focal", 1e-4, 1.0, True),
 ]
 
 
