@@ -15,7 +15,8 @@
 #include "gru_scan.cuh"
 #include "tc_conv.cuh"
 #include "tc_gemm.cuh"
-#include "tc_umma.cuh"
+#include "crnn_block.cuh"
+#include "conv0_lean.cuh"
 
 #include <algorithm>
 
@@ -185,51 +186,6 @@ __global__ void bn_finalize_eval_kernel(int C, const float* __restrict__ gamma, 
     stat[3 * C + c] = beta[c] - mean * sc;
 }
 
-// ----------------------------------------------------------------------------- dropout generator
-// One 64-bit hash (splitmix64 finaliser) per group of FOUR consecutive elements; element q of the group keeps its
-// value iff the q-th 16-bit field of the hash is >= p * 65536.  Forward and backward kernels all go through
-// dropout_keep4(seed, group index), so they agree on the mask without storing it.
-__device__ __forceinline__ unsigned long long hash64(unsigned long long seed, unsigned long long idx) {
-    unsigned long long x = seed + idx * 0x9E3779B97F4A7C15ull;
-    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
-    x ^= x >> 27; x *= 0x94D049BB133111EBull;
-    x ^= x >> 31;
-    return x;
-}
-struct Keep4 { bool k[4]; };
-__device__ __forceinline__ Keep4 dropout_keep4(unsigned long long seed, unsigned long long group, float p) {
-    const unsigned long long x = hash64(seed, group);
-    const unsigned thr = (unsigned)(p * 65536.0f);
-    Keep4 r;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) r.k[q] = (unsigned)((x >> (16 * q)) & 0xFFFFu) >= thr;
-    return r;
-}
-__host__ __device__ inline unsigned long long block_seed(unsigned long long seed, int block) {
-    return seed * 0x2545F4914F6CDD1Dull + (unsigned long long)(block + 1) * 0xD6E8FEB86659FD93ull;
-}
-
-// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): the tensor-core operand format (tc_conv.cu)
-__device__ __forceinline__ void store_planes4(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long i4,
-                                              const float4 v) {
-    __nv_bfloat16 h[4], l[4];
-    const float f[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        h[q] = __float2bfloat16_rn(f[q]);
-        l[q] = __float2bfloat16_rn(f[q] - __bfloat162float(h[q]));
-    }
-    reinterpret_cast<uint2*>(hi)[i4] = *reinterpret_cast<uint2*>(h);
-    reinterpret_cast<uint2*>(lo)[i4] = *reinterpret_cast<uint2*>(l);
-}
-
-struct PoolGeom {
-    int H, W, Wo, C, p;
-    long oB, oH, oW, oC;         // strides of the block OUTPUT (channels-last, or the [B][T][flat] layout)
-    float drop_p;                // 0 disables
-    unsigned long long seed;
-};
-
 // ----------------------------------------------------------------------------- BN + ReLU + max-pool(1,p) (+dropout)
 __global__ void __launch_bounds__(256)
 bn_relu_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ stat, float* __restrict__ out,
@@ -360,15 +316,6 @@ template <int P>
 __device__ __forceinline__ void load_window(const float* __restrict__ src, int C, float4 (&v)[P]) {
 #pragma unroll
     for (int j = 0; j < P; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(src + (long)j * C));
-}
-__device__ __forceinline__ void load_dA(const float* __restrict__ da, long oC, float (&g)[4]) {
-    if (oC == 1) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(da));
-        g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
-    } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) g[q] = __ldg(da + q * oC);
-    }
 }
 template <int P>
 __device__ __forceinline__ void eval_window(const float4 (&v)[P], const float (&scv)[4], const float (&shv)[4],
@@ -678,7 +625,6 @@ bn_pool_bwd_dy_t_kernel(const float* __restrict__ y, const float* __restrict__ s
 // Thread mapping: lane <-> 4 consecutive output channels (weights / dW live in registers for the whole
 // kernel), warp <-> one image row, block <-> 8 rows; the input rows (with zero halo) sit in shared memory
 // and are read as warp-wide broadcasts; every y0 access is a 512 B coalesced row of 128 channels.
-constexpr int kC0Rows = 8;
 
 template <int CIN>
 __device__ __forceinline__ void load_x_rows(const float* __restrict__ x, float* xs, int b, int h0, int H, int W) {
@@ -991,717 +937,6 @@ __global__ void conv0_bwd_reduce_kernel(const float* __restrict__ part, int nblk
     }
 }
 
-inline bool conv0_direct_ok(int cin, int C) { return (cin == 1 || cin == 2) && C % 128 == 0; }
-inline long conv0_blocks(int B, int H) { return (long)B * ((H + kC0Rows - 1) / kC0Rows); }
-
-// ----------------------------------------------------------------------------- first conv block, lean
-// The output of conv 0 (4 B x B*H*W*C: 671 MB at C2, 10.7 GB at C5) is the largest tensor of the step, and
-// with K = 9*Cin <= 18 it is also the cheapest one to describe.  This path never writes or reads it:
-//
-//   * BatchNorm statistics of y = w.patch + b are a function of the first two moments of the PATCHES:
-//         mean_c = b_c + w_c.m,   var_c = w_c^T (G - m m^T) w_c,   m = E[patch], G = E[patch patch^T]  (K x K)
-//     so one pass over the INPUT (conv0_gram_kernel) replaces the statistics pass over y.
-//   * The forward kernel knows scale / shift before it starts: conv + BN + ReLU + max-pool + dropout happen in
-//     registers; it writes the pooled block output and one byte per (window, channel): the winner's position in
-//     the window, bit 7 set when the ReLU or the dropout killed the window.
-//   * Backward: dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)) is dense in the pixels, but the only dense
-//     terms are (constant) and (xhat): sum_pix patch_k and sum_pix xhat*patch_k follow from (m, G) again.  What
-//     needs the data is S_k = sum over WINDOWS of dz * patch_k(winner) (one pixel in p), and
-//     sum dz*xhat(winner) = invstd * (b*sum dz + w.S - mean*sum dz) needs nothing else.  So one kernel reads
-//     dA + the winner bytes + the input rows, and a per-channel finalizer closes d(gamma), d(beta) and dW.
-//     The conv bias gradient through train-mode BatchNorm is identically zero and is written as 0.
-//
-// HBM traffic of block 0 at C2: forward |x| + |a| + |a|/4 = 178 MB (was 671 MB written + 805 MB read back),
-// backward |dA| + |a|/4 + |x| = 178 MB (was 268 + 816 MB).
-// ---- asynchronous, division-free staging of the input rows of one row group (8 rows + halo, zero-filled borders):
-// warp <-> (input channel, row), lane <-> column; 4-byte cp.async with src-size 0 for the zero fill
-__device__ __forceinline__ void cpa4_zfill(float* smem_dst, const float* gsrc, bool valid) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    const int n = valid ? 4 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
-}
-__device__ __forceinline__ void cpa16(void* smem_dst, const void* gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cpa_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-template <int CIN>
-__device__ __forceinline__ void stage_x_rows_async(const float* __restrict__ x, float* xs, int b, int h0, int H, int W,
-                                                   int row_stride = 0) {
-    const int Wp = row_stride ? row_stride : W + 2, nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int rowid = warp; rowid < CIN * (kC0Rows + 2); rowid += nwarps) {
-        const int ci = rowid / (kC0Rows + 2), rr = rowid - ci * (kC0Rows + 2);      // constant divisor: no XU work
-        const int hh = h0 - 1 + rr;
-        const bool rowok = hh >= 0 && hh < H;
-        const float* src = x + (((long)b * CIN + ci) * H + (rowok ? hh : 0)) * W;
-        float* dst = xs + rowid * Wp;
-        for (int cc = lane; cc < W + 2; cc += 32) {
-            const bool ok = rowok && cc >= 1 && cc <= W;
-            cpa4_zfill(dst + cc, src + (ok ? cc - 1 : 0), ok);
-        }
-    }
-}
-
-// (image, first row) of the row groups a persistent block walks, advanced without divisions
-struct GroupWalk {
-    int b, gi, step_b, step_g, gpi;
-    __device__ GroupWalk(int grp0, int stride, int groups_per_img) : gpi(groups_per_img) {
-        b = grp0 / gpi; gi = grp0 - b * gpi;
-        step_b = stride / gpi; step_g = stride - step_b * gpi;
-    }
-    __device__ void next() {
-        b += step_b; gi += step_g;
-        if (gi >= gpi) { gi -= gpi; ++b; }
-    }
-    __device__ int h0() const { return gi * kC0Rows; }
-};
-
-template <int CIN>
-struct GramDims {
-    static constexpr int K = CIN * 9;
-    static constexpr int TEAMS = CIN * 3;               // a team = one warp = (input channel, kernel row) of the OWN entry
-    static constexpr int KP = (K + 2) / 2;              // column pairs: k' = 0..K-1, then the constant 1 (plain sums)
-    static constexpr int THREADS = TEAMS * 32;
-};
-
-// part[blk][k][k'] = sum over the block's pixels of patch[k] * patch[k'] (k' = K: the plain sum).  Warp (ci, r) owns
-// the three rows k = ci*9 + r*3 + t; lanes walk the pixels of the row group.  Per-thread fp32 sums of ~140 products
-// (packed fma.f32x2 over column pairs), fixed shuffle tree, doubles afterwards.  `wmagic` = ceil(2^32 / W):
-// row = umulhi(p, wmagic) for p < 2^16.
-template <int CIN>
-__global__ void __launch_bounds__(GramDims<CIN>::THREADS)
-conv0_gram_kernel(const float* __restrict__ x, int H, int W, unsigned wmagic, int groups_per_img, int n_groups,
-                  float* __restrict__ part) {
-    using D = GramDims<CIN>;
-    extern __shared__ float xs_all[];                     // 2 x [CIN][10][W+32]: row stride = W (mod 32), so the
-                                                          // lanes that wrap to the next image row keep walking the banks
-    const int team = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tci = team / 3, tr = team - tci * 3;
-    const int Wp = W + 32, xsz = CIN * (kC0Rows + 2) * Wp;
-    const int own_off = (tci * (kC0Rows + 2) + tr) * Wp;
-    float2 acc[3][D::KP];
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int k = 0; k < D::KP; ++k) acc[a][k] = make_float2(0.0f, 0.0f);
-    int grp = blockIdx.x, buf = 0;
-    GroupWalk gw(grp, gridDim.x, groups_per_img), gn = gw;
-    if (grp < n_groups) stage_x_rows_async<CIN>(x, xs_all, gw.b, gw.h0(), H, W, Wp);
-    cpa_commit();
-    cpa_wait_all();
-    __syncthreads();
-    for (; grp < n_groups; grp += gridDim.x, buf ^= 1) {
-        const float* xs = xs_all + buf * xsz;
-        const int h0 = gw.h0();
-        gn.next();
-        if (grp + (int)gridDim.x < n_groups) stage_x_rows_async<CIN>(x, xs_all + (buf ^ 1) * xsz, gn.b, gn.h0(), H, W, Wp);
-        cpa_commit();
-        const int npix = min(kC0Rows, H - h0) * W;
-        for (int p = lane; p < npix; p += 32) {
-            const int row = (int)__umulhi((unsigned)p, wmagic), col = p - row * W;
-            const float* base = xs + row * Wp + col;
-            float pv[2 * D::KP], own[3];
-#pragma unroll
-            for (int ci = 0; ci < CIN; ++ci)
-#pragma unroll
-                for (int r = 0; r < 3; ++r)
-#pragma unroll
-                    for (int t = 0; t < 3; ++t) pv[ci * 9 + r * 3 + t] = base[(ci * (kC0Rows + 2) + r) * Wp + t];
-            pv[D::K] = 1.0f;
-            if (D::K + 1 < 2 * D::KP) pv[2 * D::KP - 1] = 0.0f;
-#pragma unroll
-            for (int t = 0; t < 3; ++t) own[t] = base[own_off + t];
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const float2 o2 = make_float2(own[a], own[a]);
-#pragma unroll
-                for (int k = 0; k < D::KP; ++k) acc[a][k] = __ffma2_rn(o2, make_float2(pv[2 * k], pv[2 * k + 1]), acc[a][k]);
-            }
-        }
-        gw = gn;
-        cpa_wait_all();
-        __syncthreads();
-    }
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int k = 0; k <= D::K; ++k) {
-            float v = (k & 1) ? acc[a][k >> 1].y : acc[a][k >> 1].x;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) part[((long)blockIdx.x * D::K + team * 3 + a) * (D::K + 1) + k] = v;
-        }
-}
-
-// gram[k][k'] (k' <= K, doubles, divided by the pixel count): one warp per entry, fixed order
-__global__ void conv0_gram_reduce_kernel(const float* __restrict__ part, int nblk, int cin, double inv_n,
-                                         double* __restrict__ gram) {
-    const int K = cin * 9, NE = K * (K + 1);
-    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (e >= NE) return;
-    const int mine = nblk > lane ? (nblk - lane + 31) / 32 : 0;
-    double a = ordered_sum<8, double>(part + (long)lane * NE + e, 32L * NE, mine);
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
-    if (lane == 0) gram[e] = a * inv_n;
-}
-
-// BatchNorm statistics of conv 0 from the patch moments; same outputs as bn_finalize_train_kernel.  One warp per
-// channel: lane k owns row k of w^T (G - m m^T) w, fixed shuffle tree.
-__global__ void __launch_bounds__(256)
-conv0_bn_finalize_kernel(const double* __restrict__ gram, int cin, int C, long n, const float* __restrict__ w,
-                         const float* __restrict__ bias, const float* __restrict__ gamma,
-                         const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running,
-                         float* __restrict__ stat) {
-    __shared__ double gsh[18 * 19];
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, k = threadIdx.x & 31, K = cin * 9;
-    for (int i = threadIdx.x; i < K * (K + 1); i += blockDim.x) gsh[i] = gram[i];
-    __syncthreads();
-    gram = gsh;
-    if (c >= C) return;
-    const float* wc = w + (long)c * K;
-    double mpart = 0.0, vpart = 0.0;
-    if (k < K) {
-        const double mk = gram[k * (K + 1) + K], wk = (double)wc[k];
-        double row = 0.0;
-        for (int k2 = 0; k2 < K; ++k2) row += (double)wc[k2] * (gram[k * (K + 1) + k2] - mk * gram[k2 * (K + 1) + K]);
-        mpart = wk * mk;
-        vpart = wk * row;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        mpart += __shfl_xor_sync(0xffffffffu, mpart, o);
-        vpart += __shfl_xor_sync(0xffffffffu, vpart, o);
-    }
-    if (k != 0) return;
-    const double mean = (double)bias[c] + mpart;
-    double var = vpart;
-    if (var < 0.0) var = 0.0;
-    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float sc = gamma[c] * invstd;
-    stat[c] = (float)mean;
-    stat[C + c] = invstd;
-    stat[2 * C + c] = sc;
-    stat[3 * C + c] = beta[c] - (float)mean * sc;
-    const double unbiased = n > 1 ? var * (double)n / (double)(n - 1) : var;
-    running[c] = (1.0f - momentum) * running[c] + momentum * (float)mean;
-    running[C + c] = (1.0f - momentum) * running[C + c] + momentum * (float)unbiased;
-}
-
-// conv + bias -> BN -> ReLU -> max-pool(1,P) -> dropout in registers.  Same accumulation order as
-// conv0_fwd_stats_kernel (y is bit-identical to what that kernel would have stored).  lane <-> 4 output channels
-// (weights in registers as channel pairs for fma.f32x2), warp <-> one image row at a time.  Every warp stages ITS
-// OWN three input rows (per input channel) with cp.async, one row ahead, and never meets a block-wide barrier: the
-// warps of an SM drift apart, so the FMA-heavy window bodies of some overlap the max / dropout / store tails of others.
-template <int CIN, int P>
-__global__ void __launch_bounds__(256, 2)
-conv0_lean_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                      const float* __restrict__ stat, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
-                      __nv_bfloat16* __restrict__ out_lo, unsigned* __restrict__ argw, PoolGeom g, int n_rows) {
-    extern __shared__ float xs_all[];                     // [8 warps][2][CIN][3][W+2]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c4 = blockIdx.y * 32 + lane, c = c4 * 4, C4 = g.C >> 2, Wp = g.W + 2, xsz = CIN * 3 * Wp;
-    float* xw = xs_all + warp * 2 * xsz;
-    float2 wr[2][CIN * 9], bs[2], sc[2], sh[2];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        bs[q] = make_float2(__ldg(bias + c + 2 * q), __ldg(bias + c + 2 * q + 1));
-        sc[q] = make_float2(__ldg(stat + 2 * g.C + c + 2 * q), __ldg(stat + 2 * g.C + c + 2 * q + 1));
-        sh[q] = make_float2(__ldg(stat + 3 * g.C + c + 2 * q), __ldg(stat + 3 * g.C + c + 2 * q + 1));
-#pragma unroll
-        for (int k = 0; k < CIN * 9; ++k)
-            wr[q][k] = make_float2(__ldg(w + (long)(c + 2 * q) * CIN * 9 + k), __ldg(w + (long)(c + 2 * q + 1) * CIN * 9 + k));
-    }
-    const float keep_scale = g.drop_p > 0.0f ? 1.0f / (1.0f - g.drop_p) : 1.0f;
-    // rows h-1, h, h+1 of every input channel of image b, zero-filled outside the image
-    auto stage_row = [&](float* dst, int b, int h) {
-#pragma unroll
-        for (int rowid = 0; rowid < CIN * 3; ++rowid) {
-            const int ci = rowid / 3, hh = h - 1 + (rowid - ci * 3);
-            const bool rowok = hh >= 0 && hh < g.H;
-            const float* src = x + (((long)b * CIN + ci) * g.H + (rowok ? hh : 0)) * g.W;
-            for (int cc = lane; cc < Wp; cc += 32) {
-                const bool ok = rowok && cc >= 1 && cc <= g.W;
-                cpa4_zfill(dst + rowid * Wp + cc, src + (ok ? cc - 1 : 0), ok);
-            }
-        }
-    };
-    const int stride = gridDim.x * kC0Rows;
-    int row = blockIdx.x * kC0Rows + warp, buf = 0;
-    int b = row / g.H, h = row - b * g.H;
-    const int step_b = stride / g.H, step_h = stride - step_b * g.H;
-    if (row < n_rows) stage_row(xw, b, h);
-    cpa_commit();
-    for (; row < n_rows; row += stride, buf ^= 1) {
-        int bn = b + step_b, hn = h + step_h;
-        if (hn >= g.H) { hn -= g.H; ++bn; }
-        if (row + stride < n_rows) stage_row(xw + (buf ^ 1) * xsz, bn, hn);
-        cpa_commit();
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        __syncwarp();
-        const float* xs = xw + buf * xsz;
-        for (int wo = 0; wo < g.Wo; ++wo) {
-            float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-            unsigned arg[4] = {0u, 0u, 0u, 0u};
-            auto consider = [&](int j, const float2 a01, const float2 a23) {
-                const float2 z01 = __ffma2_rn(a01, sc[0], sh[0]), z23 = __ffma2_rn(a23, sc[1], sh[1]);
-                const float z[4] = {z01.x, z01.y, z23.x, z23.y};
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (z[q] > best[q]) { best[q] = z[q]; arg[q] = (unsigned)j; }      // first maximum wins
-            };
-#pragma unroll
-            for (int j = 0; j + 1 < P; j += 2) {
-                const int ww = wo * P + j;
-                float2 acc[2][2] = {{bs[0], bs[1]}, {bs[0], bs[1]}};
-#pragma unroll
-                for (int ci = 0; ci < CIN; ++ci)
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        const float* xr = xs + (ci * 3 + r) * Wp + ww;
-                        float xc[4];
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) xc[t] = xr[t];
-#pragma unroll
-                        for (int t = 0; t < 3; ++t) {
-                            const float2 x0 = make_float2(xc[t], xc[t]), x1 = make_float2(xc[t + 1], xc[t + 1]);
-                            acc[0][0] = __ffma2_rn(wr[0][ci * 9 + r * 3 + t], x0, acc[0][0]);
-                            acc[0][1] = __ffma2_rn(wr[1][ci * 9 + r * 3 + t], x0, acc[0][1]);
-                            acc[1][0] = __ffma2_rn(wr[0][ci * 9 + r * 3 + t], x1, acc[1][0]);
-                            acc[1][1] = __ffma2_rn(wr[1][ci * 9 + r * 3 + t], x1, acc[1][1]);
-                        }
-                    }
-                consider(j, acc[0][0], acc[0][1]);
-                consider(j + 1, acc[1][0], acc[1][1]);
-            }
-            if (P & 1) {
-                const int ww = wo * P + P - 1;
-                float2 acc[2] = {bs[0], bs[1]};
-#pragma unroll
-                for (int ci = 0; ci < CIN; ++ci)
-#pragma unroll
-                    for (int r = 0; r < 3; ++r)
-#pragma unroll
-                        for (int t = 0; t < 3; ++t) {
-                            const float xv = xs[(ci * 3 + r) * Wp + ww + t];
-                            const float2 x2 = make_float2(xv, xv);
-                            acc[0] = __ffma2_rn(wr[0][ci * 9 + r * 3 + t], x2, acc[0]);
-                            acc[1] = __ffma2_rn(wr[1][ci * 9 + r * 3 + t], x2, acc[1]);
-                        }
-                consider(P - 1, acc[0], acc[1]);
-            }
-            const long pix = ((long)b * g.H + h) * g.Wo + wo;
-            const long i = pix * C4 + c4;                      // element numbering of the pool kernels (dropout)
-            Keep4 kp;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) kp.k[q] = true;
-            if (g.drop_p > 0.0f) kp = dropout_keep4(g.seed, (unsigned long long)i, g.drop_p);
-            float m[4];
-            unsigned word = 0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const bool alive = best[q] > 0.0f && kp.k[q];
-                m[q] = alive ? best[q] * keep_scale : 0.0f;
-                word |= (arg[q] | (alive ? 0u : 0x80u)) << (8 * q);
-            }
-            const float4 m4 = make_float4(m[0], m[1], m[2], m[3]);
-            if (argw) argw[i] = word;
-            if (out_hi) store_planes4(out_hi, out_lo, i, m4);
-            if (out) {
-                float* dst = out + (long)b * g.oB + (long)h * g.oH + (long)wo * g.oW + (long)c * g.oC;
-                if (g.oC == 1) {
-                    *reinterpret_cast<float4*>(dst) = m4;
-                } else {
-                    dst[0] = m[0]; dst[g.oC] = m[1]; dst[2 * g.oC] = m[2]; dst[3 * g.oC] = m[3];
-                }
-            }
-        }
-        __syncwarp();                                          // every lane is done with xs[buf] before it is refilled
-        b = bn; h = hn;
-    }
-}
-
-// S[k][c] = sum over windows of dz * patch_k(winner), S[K][c] = sum dz; part layout [nblk][K+1][C].
-// dA and the winner bytes of the NEXT tile (8 rows x kLeanWC windows x 128 channels) travel global -> shared with
-// 16-byte cp.async while the current tile is consumed, so no warp ever waits on HBM; channel pairs accumulate with
-// packed fma.f32x2 (each half has its own winner, i.e. its own patch value).  Needs the channels-last block output
-// (g.oC == 1: block 0 is not the last conv block).
-constexpr int kLeanWC = 8;
-inline size_t conv0_lean_bwd_smem(int cin, int W) {
-    const size_t xpad = (2 * (size_t)cin * (kC0Rows + 2) * (W + 2) + 3) & ~(size_t)3;
-    return xpad * 4 + 2 * (size_t)kC0Rows * kLeanWC * (128 + 32) * 4;
-}
-template <int CIN, int P>
-__global__ void __launch_bounds__(256)
-conv0_lean_bwd_kernel(const float* __restrict__ x, const unsigned* __restrict__ argw, const float* __restrict__ dA,
-                      PoolGeom g, int groups_per_img, int n_groups, float* __restrict__ part) {
-    constexpr int K = CIN * 9;
-    extern __shared__ __align__(16) float lean_smem[];
-    __shared__ float red[kC0Rows][128];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int C4 = g.C >> 2, Wp = g.W + 2, xsz = CIN * (kC0Rows + 2) * Wp;
-    const int xpad = (2 * xsz + 3) & ~3;                                         // keep the tiles 16 B aligned
-    float* xs_all = lean_smem;                                                   // 2 x [CIN][10][W+2]
-    float* da_all = lean_smem + xpad;                                            // 2 x [8][WC][128]
-    unsigned* ar_all = reinterpret_cast<unsigned*>(da_all + 2 * kC0Rows * kLeanWC * 128);   // 2 x [8][WC][32]
-    const float keep_scale = g.drop_p > 0.0f ? 1.0f / (1.0f - g.drop_p) : 1.0f;
-    const int n_chunks = (g.Wo + kLeanWC - 1) / kLeanWC;
-    float2 acc[2][K + 1];
-#pragma unroll
-    for (int q = 0; q < 2; ++q)
-#pragma unroll
-        for (int k = 0; k <= K; ++k) acc[q][k] = make_float2(0.0f, 0.0f);
-
-    // one warp per image row of the tile: 512 B of dA (all lanes) + 128 B of winner words (lanes 0..7) per window
-    auto stage_tile = [&](int tb, int b, int h0, int chunk) {
-        const int h = h0 + warp;
-        if (h >= g.H) return;
-        const int w0 = chunk * kLeanWC, nw = min(kLeanWC, g.Wo - w0);
-        const float* src = dA + (long)b * g.oB + (long)h * g.oH + (long)w0 * g.oW + blockIdx.y * 128 + lane * 4;
-        const unsigned* asrc = argw + (((long)b * g.H + h) * g.Wo + w0) * C4 + blockIdx.y * 32 + lane * 4;
-        float* dd = da_all + ((tb * kC0Rows + warp) * kLeanWC) * 128 + lane * 4;
-        unsigned* ad = ar_all + ((tb * kC0Rows + warp) * kLeanWC) * 32 + lane * 4;
-        for (int wl = 0; wl < nw; ++wl) {
-            cpa16(dd + wl * 128, src + (long)wl * g.oW);
-            if (lane < 8) cpa16(ad + wl * 32, asrc + (long)wl * C4);
-        }
-    };
-
-    int grp = blockIdx.x, xb = 0, tb = 0;
-    GroupWalk gw(grp, gridDim.x, groups_per_img), gn = gw;
-    if (grp < n_groups) {
-        stage_x_rows_async<CIN>(x, xs_all, gw.b, gw.h0(), g.H, g.W);
-        stage_tile(0, gw.b, gw.h0(), 0);
-    }
-    cpa_commit();
-    cpa_wait_all();
-    __syncthreads();
-    for (; grp < n_groups; grp += gridDim.x, xb ^= 1) {
-        const float* xs = xs_all + xb * xsz;
-        const int h0 = gw.h0();
-        gn.next();
-        const bool more = grp + (int)gridDim.x < n_groups;
-        for (int chunk = 0; chunk < n_chunks; ++chunk, tb ^= 1) {
-            if (chunk + 1 < n_chunks) {
-                stage_tile(tb ^ 1, gw.b, h0, chunk + 1);
-            } else if (more) {
-                stage_x_rows_async<CIN>(x, xs_all + (xb ^ 1) * xsz, gn.b, gn.h0(), g.H, g.W);
-                stage_tile(tb ^ 1, gn.b, gn.h0(), 0);
-            }
-            cpa_commit();
-            if (h0 + warp < g.H) {
-                const int w0 = chunk * kLeanWC, nw = min(kLeanWC, g.Wo - w0);
-                const float* xrow = xs + warp * Wp + w0 * P;
-                const float* dd = da_all + ((tb * kC0Rows + warp) * kLeanWC) * 128 + lane * 4;
-                const unsigned* ad = ar_all + ((tb * kC0Rows + warp) * kLeanWC) * 32 + lane;
-                for (int wl = 0; wl < nw; ++wl) {
-                    const float4 g4 = *reinterpret_cast<const float4*>(dd + wl * 128);
-                    const unsigned word = ad[wl * 32];
-                    const float gq[4] = {g4.x, g4.y, g4.z, g4.w};
-#pragma unroll
-                    for (int pr = 0; pr < 2; ++pr) {
-                        const unsigned b0 = (word >> (16 * pr)) & 0xFFu, b1 = (word >> (16 * pr + 8)) & 0xFFu;
-                        const float2 dz = make_float2((b0 & 0x80u) ? 0.0f : gq[2 * pr] * keep_scale,
-                                                      (b1 & 0x80u) ? 0.0f : gq[2 * pr + 1] * keep_scale);
-                        const float* base0 = xrow + wl * P + (int)(b0 & 0x7Fu);
-                        const float* base1 = xrow + wl * P + (int)(b1 & 0x7Fu);
-#pragma unroll
-                        for (int ci = 0; ci < CIN; ++ci)
-#pragma unroll
-                            for (int r = 0; r < 3; ++r)
-#pragma unroll
-                                for (int t = 0; t < 3; ++t) {
-                                    const int off = (ci * (kC0Rows + 2) + r) * Wp + t;
-                                    acc[pr][ci * 9 + r * 3 + t] = __ffma2_rn(dz, make_float2(base0[off], base1[off]),
-                                                                             acc[pr][ci * 9 + r * 3 + t]);
-                                }
-                        acc[pr][K] = __fadd2_rn(acc[pr][K], dz);
-                    }
-                }
-            }
-            cpa_wait_all();
-            __syncthreads();
-        }
-        gw = gn;
-    }
-#pragma unroll
-    for (int k = 0; k <= K; ++k) {
-        red[warp][lane * 4 + 0] = acc[0][k].x; red[warp][lane * 4 + 1] = acc[0][k].y;
-        red[warp][lane * 4 + 2] = acc[1][k].x; red[warp][lane * 4 + 3] = acc[1][k].y;
-        __syncthreads();
-        if (threadIdx.x < 128) {
-            float t = 0.0f;
-#pragma unroll
-            for (int r = 0; r < kC0Rows; ++r) t += red[r][threadIdx.x];
-            part[((long)blockIdx.x * (K + 1) + k) * g.C + blockIdx.y * 128 + threadIdx.x] = t;
-        }
-        __syncthreads();
-    }
-}
-
-// S[k][c] = sum_blk part[blk][k][c] in double: block <-> (k, 128-channel slice), thread <-> (channel, 1 of 8 interleaved
-// block ranges); every load is a coalesced 512 B row, the eight range sums are added in a fixed order
-__global__ void __launch_bounds__(1024)
-conv0_lean_bwd_colsum_kernel(const float* __restrict__ part, int nblk, int K1, int C, double* __restrict__ S) {
-    __shared__ double red[8][128];
-    const int k = blockIdx.x, c = blockIdx.y * 128 + (threadIdx.x & 127), grp = threadIdx.x >> 7;
-    const int mine = nblk > grp ? (nblk - grp + 7) / 8 : 0;
-    const double a = ordered_sum<8, double>(part + ((long)grp * K1 + k) * C + c, 8L * K1 * C, mine);
-    red[grp][threadIdx.x & 127] = a;
-    __syncthreads();
-    if (grp == 0) {
-        double t = 0.0;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) t += red[r][threadIdx.x];
-        S[(long)k * C + c] = t;
-    }
-}
-
-// d(beta), d(gamma), dW of conv 0 (and its zero bias gradient) from S, the patch moments and the forward statistics;
-// one warp per channel, lane k <-> dW[c][k]
-__global__ void __launch_bounds__(256)
-conv0_lean_bwd_finalize_kernel(const double* __restrict__ S, int cin, int C, const double* __restrict__ gram,
-                               const float* __restrict__ w, const float* __restrict__ bias,
-                               const float* __restrict__ gamma, const float* __restrict__ stat,
-                               float* __restrict__ dw, float* __restrict__ db, float* __restrict__ dgamma,
-                               float* __restrict__ dbeta) {
-    __shared__ double gsh[18 * 19];
-    const int K = cin * 9;
-    for (int i = threadIdx.x; i < K * (K + 1); i += blockDim.x) gsh[i] = gram[i];
-    __syncthreads();
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, k = threadIdx.x & 31;
-    if (c >= C || k >= K) return;
-    const float* wc = w + (long)c * K;
-    const double mean = (double)stat[c], invstd = (double)stat[C + c], bc = (double)bias[c];
-    const double sum_dz = S[(long)K * C + c];
-    double sum_dz_y = bc * sum_dz, wg = 0.0;
-    for (int k2 = 0; k2 < K; ++k2) {
-        sum_dz_y += (double)wc[k2] * S[(long)k2 * C + c];
-        wg += (double)wc[k2] * gsh[k2 * (K + 1) + k];                  // G is symmetric
-    }
-    const double dg = invstd * (sum_dz_y - mean * sum_dz);             // sum dz * xhat
-    const double mk = gsh[k * (K + 1) + K];
-    const double tk = invstd * (wg + (bc - mean) * mk);                // mean over pixels of xhat * patch_k
-    dw[(long)c * K + k] = (float)((double)gamma[c] * invstd * (S[(long)k * C + c] - sum_dz * mk - dg * tk));
-    if (k == 0) {
-        dgamma[c] = (float)dg;
-        dbeta[c] = (float)sum_dz;
-        db[c] = 0.0f;
-    }
-}
-
-inline bool conv0_lean_ok(int cin, int C, int pool, int n_conv) {
-    return conv0_direct_ok(cin, C) && (pool == 5 || pool == 2) && n_conv > 1;
-}
-
-// ----------------------------------------------------------------------------- lean block 0 forward on tcgen05
-// Same contract as conv0_lean_fwd_kernel (pooled output + winner bytes, statistics known up front), with the
-// contraction on the tensor cores: a tile is NW = 128/P pooling windows = TP = NW*P pixels (rows of the MMA),
-//   1. two threads (warps 0-3: hi plane, warps 4-7: lo plane) build one im2col row (K = 9*Cin <= 18 values, zero-padded to 16-wide k-steps) as bf16 hi / lo
-//      planes straight into the 128-byte-swizzled K-major layout tcgen05 reads (what TMA would have produced),
-//   2. one thread issues 3 MMAs (hi*hi + hi*lo + lo*hi, the fp32-grade split of tc_conv.cu) per k-step into a
-//      128 x 128 fp32 TMEM accumulator,
-//   3. the 8 warps move the accumulator TMEM -> registers -> an XOR-swizzled [pixel][channel] shared tile (it aliases
-//      the A planes, which the MMAs are done with),
-//   4. warp <-> window, lane <-> 4 channels: bias + BN + max / argmax over the window's P rows, ReLU, dropout, stores.
-// Two CTAs per SM (96 KB of shared memory, 128 TMEM columns each) overlap one CTA's epilogue with the other's build.
-namespace c0tc {
-constexpr int kPlane = 128 * 128;                               // bytes: 128 rows x 128 B (64 bf16 K slots, <= 32 used)
-constexpr int kSmem = 1024 + 2 * kPlane + 128 * 128 * 4 + 18 * 128 * 4 + 64;   // align + B planes + tile (aliases the A planes) + patch staging + barrier
-__device__ __forceinline__ uint32_t sw128(int r, int c) {       // byte offset of 16-byte chunk c of row r
-    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
-}
-template <int K>
-__device__ __forceinline__ void put_row(unsigned char* plane, int r, const float (&v)[K], bool lo) {
-    constexpr int CH = ((K + 15) / 16) * 2;                     // chunks of 8 bf16 covering the k-steps in use
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-        uint32_t w[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int k0 = c * 8 + 2 * e;
-            const float a = k0 < K ? v[k0 < K ? k0 : 0] : 0.0f, b = k0 + 1 < K ? v[k0 + 1 < K ? k0 + 1 : 0] : 0.0f;
-            __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
-            if (lo) {
-                ha = __float2bfloat16_rn(a - __bfloat162float(ha));
-                hb = __float2bfloat16_rn(b - __bfloat162float(hb));
-            }
-            w[e] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
-        }
-        *reinterpret_cast<uint4*>(plane + sw128(r, c)) = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-}
-}  // namespace c0tc
-
-template <int CIN, int P>
-__global__ void __launch_bounds__(256, 2)
-conv0_tc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                    const float* __restrict__ stat, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
-                    __nv_bfloat16* __restrict__ out_lo, unsigned* __restrict__ argw, PoolGeom g, unsigned n_windows,
-                    int n_tiles) {
-    using namespace umma;
-    constexpr int K = CIN * 9, KSTEPS = (K + 15) / 16, NW = 128 / P, TP = NW * P;
-    constexpr int KH = (K + 1) / 2;                               // patch entries fetched by each thread of a row pair
-    extern __shared__ unsigned char c0tc_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(c0tc_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char *b_hi = smem, *b_lo = smem + c0tc::kPlane;
-    unsigned char *a_hi = smem + 2 * c0tc::kPlane, *a_lo = a_hi + c0tc::kPlane;
-    float* ys = reinterpret_cast<float*>(smem + 2 * c0tc::kPlane);                   // [128][128], aliases a_hi / a_lo
-    float* xst = reinterpret_cast<float*>(smem + 2 * c0tc::kPlane + 128 * 128 * 4);  // [K][128] patch staging (cp.async)
-    uint64_t* bar = reinterpret_cast<uint64_t*>(xst + 18 * 128);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
-    if (warp == 1) tmem_alloc(tmem_slot, 128);
-    {   // B operand: row n = output channel, the same K ordering as the im2col rows (w[c][ci][r][t])
-        const int n = tid & 127;
-        float v[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) v[k] = __ldg(w + (long)(blockIdx.y * 128 + n) * K + k);
-        c0tc::put_row<K>((tid >> 7) ? b_lo : b_hi, n, v, (tid >> 7) != 0);
-    }
-    // patch values of a tile's rows: global -> shared with zero-filling 4-byte cp.async, one tile ahead of their use;
-    // the two threads of a row (tid, tid + 128) fetch half of its entries each
-    const unsigned uWo = (unsigned)g.Wo, uH = (unsigned)g.H;
-    auto fetch_tile = [&](int tile) {
-        const int r = tid & 127;
-        const unsigned q = (unsigned)tile * NW + (unsigned)(r / P);
-        const int j = r % P;
-        const bool rowok = r < TP && q < n_windows;
-        const unsigned bh = q / uWo, wo = q - bh * uWo, b = bh / uH, h = bh - b * uH;
-        const int wc = (int)wo * P + j;
-#pragma unroll
-        for (int kk = 0; kk < KH; ++kk) {
-            const int k = (tid >> 7) * KH + kk;
-            if (k < K) {
-                const int ci = k / 9, rr = (k - ci * 9) / 3, t = k - ci * 9 - rr * 3;
-                const int hh = (int)h + rr - 1, ww = wc + t - 1;
-                const bool ok = rowok && hh >= 0 && hh < g.H && ww >= 0 && ww < g.W;
-                const float* src = x + (((long)b * CIN + ci) * g.H + (ok ? hh : 0)) * g.W + (ok ? ww : 0);
-                cpa4_zfill(xst + k * 128 + r, ok ? src : x, ok);
-            }
-        }
-    };
-    if ((int)blockIdx.x < n_tiles) fetch_tile(blockIdx.x);
-    cpa_commit();
-    tc_fence_before();
-    fence_proxy_async();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-    const int c4 = blockIdx.y * 32 + lane, c = c4 * 4, C4 = g.C >> 2;
-    const float4 bs = __ldg(reinterpret_cast<const float4*>(bias + c));
-    const float4 sc = __ldg(reinterpret_cast<const float4*>(stat + 2 * g.C + c));
-    const float4 sh = __ldg(reinterpret_cast<const float4*>(stat + 3 * g.C + c));
-    // z = sc * (acc + bias) + sh: the conv bias is folded into the shift
-    const float scv[4] = {sc.x, sc.y, sc.z, sc.w};
-    const float shv[4] = {fmaf(bs.x, sc.x, sh.x), fmaf(bs.y, sc.y, sh.y), fmaf(bs.z, sc.z, sh.z), fmaf(bs.w, sc.w, sh.w)};
-    const float keep_scale = g.drop_p > 0.0f ? 1.0f / (1.0f - g.drop_p) : 1.0f;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // ---- 1. im2col rows of this tile (thread <-> row; warps 0-3: hi plane, warps 4-7: lo plane)
-        cpa_wait_all();
-        __syncthreads();                                       // staged patches visible; previous tile's windows are done
-        {
-            const int r = tid & 127;
-            float v[K];
-#pragma unroll
-            for (int k = 0; k < K; ++k) v[k] = xst[k * 128 + r];
-            c0tc::put_row<K>((tid >> 7) ? a_lo : a_hi, r, v, (tid >> 7) != 0);
-        }
-        fence_proxy_async();
-        __syncthreads();
-        // ---- 2. MMAs
-        if (tid == 0) {
-            tc_fence_after();
-            constexpr uint32_t idesc = idesc_bf16(128, 128, 0, 0);
-            const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh2 = smem_u32(b_hi), bl = smem_u32(b_lo);
-#pragma unroll
-            for (int k = 0; k < KSTEPS; ++k) {
-                const uint64_t dah = smem_desc_sw128(ah + k * 32, 16, 1024), dal = smem_desc_sw128(al + k * 32, 16, 1024);
-                const uint64_t dbh = smem_desc_sw128(bh2 + k * 32, 16, 1024), dbl = smem_desc_sw128(bl + k * 32, 16, 1024);
-                mma_bf16(tmem, dah, dbh, idesc, k != 0);
-                mma_bf16(tmem, dah, dbl, idesc, 1);
-                mma_bf16(tmem, dal, dbh, idesc, 1);
-            }
-            mma_commit(bar);
-        }
-        if (tile + (int)gridDim.x < n_tiles) fetch_tile(tile + gridDim.x);     // lands while the MMAs and the epilogue run
-        cpa_commit();
-        mbar_wait(bar, phase);
-        phase ^= 1;
-        tc_fence_after();
-        // ---- 3. accumulator -> shared [pixel][channel] tile (chunk index XOR row: conflict-free both ways)
-        {
-            const int qd = warp & 3, half = warp >> 2, r = qd * 32 + lane;
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                float v[32];
-                tmem_ld32(tmem + ((uint32_t)(qd * 32) << 16) + half * 64 + cc * 32, v);
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                    const int chunk = half * 16 + cc * 8 + jj;
-                    *reinterpret_cast<float4*>(ys + r * 128 + ((chunk ^ lane) << 2)) =
-                        make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
-                }
-            }
-        }
-        tc_fence_before();
-        __syncthreads();
-        // ---- 4. windows: warp <-> window, lane <-> 4 channels
-        for (int wl = warp; wl < NW; wl += 8) {
-            const unsigned q = (unsigned)tile * NW + (unsigned)wl;
-            if (q >= n_windows) break;
-            float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-            unsigned arg[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-            for (int j = 0; j < P; ++j) {
-                const int row = wl * P + j;
-                const float4 y4 = *reinterpret_cast<const float4*>(ys + row * 128 + ((lane ^ (row & 31)) << 2));
-                const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
-#pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
-                    const float z = fmaf(yv[qq], scv[qq], shv[qq]);
-                    if (z > best[qq]) { best[qq] = z; arg[qq] = (unsigned)j; }      // first maximum wins
-                }
-            }
-            const long i = (long)q * C4 + c4;                  // element numbering of the pool kernels (dropout)
-            Keep4 kp;
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq) kp.k[qq] = true;
-            if (g.drop_p > 0.0f) kp = dropout_keep4(g.seed, (unsigned long long)i, g.drop_p);
-            float m[4];
-            unsigned word = 0;
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
-                const bool alive = best[qq] > 0.0f && kp.k[qq];
-                m[qq] = alive ? best[qq] * keep_scale : 0.0f;
-                word |= (arg[qq] | (alive ? 0u : 0x80u)) << (8 * qq);
-            }
-            const float4 m4 = make_float4(m[0], m[1], m[2], m[3]);
-            if (argw) argw[i] = word;
-            if (out_hi) store_planes4(out_hi, out_lo, i, m4);
-            if (out) {
-                const unsigned bh = q / uWo, wo = q - bh * uWo, b = bh / uH, h = bh - b * uH;
-                float* dst = out + (long)b * g.oB + (long)h * g.oH + (long)wo * g.oW + (long)c * g.oC;
-                if (g.oC == 1) {
-                    *reinterpret_cast<float4*>(dst) = m4;
-                } else {
-                    dst[0] = m[0]; dst[g.oC] = m[1]; dst[2 * g.oC] = m[2]; dst[3 * g.oC] = m[3];
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc(tmem, 128);
-    }
-}
-
 
 // ----------------------------------------------------------------------------- small dense layers, backward
 // The per-frame dense head is tiny (e.g. 64 -> 16 -> 6): one kernel per layer produces d(input) for its 128
@@ -1904,32 +1139,20 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
         const bool direct0 = (i == 0) && conv0_direct_ok(P.cin[0], P.C);
         int nblk = 0;
         if (i == 0 && conv0_lean_ok(P.cin[0], P.C, P.pool[0], P.n_conv)) {
-            // lean block 0: statistics from the patch moments of the input, then one fused kernel; y0 is never stored
-            const int gpi = (P.H + kC0Rows - 1) / kC0Rows, n_groups = gpi * batch;
-            const size_t sm = 2 * (size_t)P.cin[0] * (kC0Rows + 2) * (P.win[0] + 2) * 4;
-            const int cin0 = P.cin[0], K0 = 9 * cin0;
-            double* gram = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + P.gram);
+            // lean block 0 (conv0_lean.cu): statistics from the patch moments of the input, then one fused kernel; y0 is
+            // never stored
             {
                 SED_PROF("conv0.stats", st);
                 if (training) {
-                    const int gblk = std::min(n_groups, (cin0 == 1 ? 5 : 3) * sm_count());
-                    const unsigned wmagic = (unsigned)(((1ull << 32) + (unsigned)P.win[0] - 1) / (unsigned)P.win[0]);
-                    const size_t gsm = 2 * (size_t)cin0 * (kC0Rows + 2) * (P.win[0] + 32) * 4;
-                    if (cin0 == 1) conv0_gram_kernel<1><<<gblk, GramDims<1>::THREADS, gsm, st>>>(x, P.H, P.win[0], wmagic, gpi, n_groups, wsf(ws, P.part));
-                    else conv0_gram_kernel<2><<<gblk, GramDims<2>::THREADS, gsm, st>>>(x, P.H, P.win[0], wmagic, gpi, n_groups, wsf(ws, P.part));
-                    SED_POST_LAUNCH();
-                    const int entries = K0 * (K0 + 1);
-                    conv0_gram_reduce_kernel<<<(entries * 32 + 255) / 256, 256, 0, st>>>(
-                        wsf(ws, P.part), gblk, cin0, 1.0 / (double)M, gram);
-                    SED_POST_LAUNCH();
-                    conv0_bn_finalize_kernel<<<(P.C * 32 + 255) / 256, 256, 0, st>>>(
-                        gram, cin0, P.C, (long)M, params + P.conv_w[0], params + P.conv_b[0], params + P.bn_w[0],
-                        params + P.bn_b[0], d->bn_eps, d->bn_momentum, running, stat);
+                    rc = conv0_lean_stats(x, P.cin[0], P.C, P.H, P.win[0], batch, params + P.conv_w[0], params + P.conv_b[0],
+                                          params + P.bn_w[0], params + P.bn_b[0], d->bn_eps, d->bn_momentum, running, stat,
+                                          reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + P.gram), wsf(ws, P.part), st);
+                    if (rc) return rc;
                 } else {
                     bn_finalize_eval_kernel<<<(P.C + 127) / 128, 128, 0, st>>>(P.C, params + P.bn_w[0], params + P.bn_b[0],
                                                                                d->bn_eps, running, stat);
+                    SED_POST_LAUNCH();
                 }
-                SED_POST_LAUNCH();
             }
             SED_PROF("conv0.fwd_fused", st);
             const PoolGeom g = pool_geom(P, d, 0, training, seed);
@@ -1938,31 +1161,9 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
             __nv_bfloat16* pl = to_planes ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(ws) + P.actp[0] + P.act_plane_bytes[0]) : nullptr;
             float* of = to_planes ? nullptr : wsf(ws, P.act[0]);
             unsigned* argw = training ? reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws) + P.arg0) : nullptr;
-            const dim3 grid(std::min(n_groups, 2 * sm_count()), P.C / 128);
-            const float *w0 = params + P.conv_w[0], *b0 = params + P.conv_b[0];
-            const size_t smw = (size_t)kC0Rows * 2 * cin0 * 3 * (P.win[0] + 2) * 4;      // per-warp row buffers
-            const int n_rows = batch * P.H;
-            if (d->tensor_cores) {
-                // contraction on tcgen05 (same 3-term split as conv 2 / 3; the fp32 CUDA-core kernel below serves
-                // tensor_cores = 0)
-                const unsigned n_windows = (unsigned)((long)batch * P.H * P.wout[0]);
-                const int NWt = 128 / g.p;
-                const int n_tiles = (int)((n_windows + (unsigned)NWt - 1) / (unsigned)NWt);
-                const dim3 tgrid(std::min(n_tiles, 2 * sm_count()), P.C / 128);
-                const void* kfn = cin0 == 1 ? (g.p == 5 ? (const void*)conv0_tc_fwd_kernel<1, 5> : (const void*)conv0_tc_fwd_kernel<1, 2>)
-                                            : (g.p == 5 ? (const void*)conv0_tc_fwd_kernel<2, 5> : (const void*)conv0_tc_fwd_kernel<2, 2>);
-                rc = ensure_dyn_smem(kfn, c0tc::kSmem);
-                if (rc) return rc;
-                if (cin0 == 1 && g.p == 5) conv0_tc_fwd_kernel<1, 5><<<tgrid, 256, c0tc::kSmem, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, n_windows, n_tiles);
-                else if (cin0 == 1) conv0_tc_fwd_kernel<1, 2><<<tgrid, 256, c0tc::kSmem, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, n_windows, n_tiles);
-                else if (g.p == 5) conv0_tc_fwd_kernel<2, 5><<<tgrid, 256, c0tc::kSmem, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, n_windows, n_tiles);
-                else conv0_tc_fwd_kernel<2, 2><<<tgrid, 256, c0tc::kSmem, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, n_windows, n_tiles);
-            } else
-            if (cin0 == 1 && g.p == 5) conv0_lean_fwd_kernel<1, 5><<<grid, 256, smw, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, n_rows);
-            else if (cin0 == 1) conv0_lean_fwd_kernel<1, 2><<<grid, 256, smw, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, n_rows);
-            else if (g.p == 5) conv0_lean_fwd_kernel<2, 5><<<grid, 256, smw, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, n_rows);
-            else conv0_lean_fwd_kernel<2, 2><<<grid, 256, smw, st>>>(x, w0, b0, stat, of, ph, pl, argw, g, n_rows);
-            SED_POST_LAUNCH();
+            rc = conv0_lean_forward(x, P.cin[0], batch, params + P.conv_w[0], params + P.conv_b[0], stat, g, d->tensor_cores,
+                                    of, ph, pl, argw, st);
+            if (rc) return rc;
             continue;
         }
         { char _nm[40]; snprintf(_nm, sizeof _nm, "conv%d.fwd", i); SED_PROF(_nm, st);
@@ -2319,32 +1520,17 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         if (i == 0 && conv0_lean_ok(P.cin[0], P.C, P.pool[0], P.n_conv)) {
             const int gpi = (P.H + kC0Rows - 1) / kC0Rows, n_groups = gpi * batch;
             const size_t sm = 2 * (size_t)P.cin[0] * (kC0Rows + 2) * (P.win[0] + 2) * 4;
-            const int cin0 = P.cin[0], K0 = 9 * cin0;
+            const int cin0 = P.cin[0];
             if (!dx) {
                 // lean block 0: winners' contributions from dA + winner bytes + input rows, the dense terms from
                 // the patch moments the forward pass left in the workspace
                 SED_PROF("conv0.bwd_lean", st);
-                const unsigned* argw = reinterpret_cast<const unsigned*>(reinterpret_cast<const char*>(ws) + P.arg0);
-                const double* gram = reinterpret_cast<const double*>(reinterpret_cast<const char*>(ws) + P.gram);
-                const dim3 grid(std::min(n_groups, 2 * sm_count()), P.C / 128);
-                const size_t bsm = conv0_lean_bwd_smem(cin0, P.win[0]);
-                const void* kfn = cin0 == 1 ? (g.p == 5 ? (const void*)conv0_lean_bwd_kernel<1, 5> : (const void*)conv0_lean_bwd_kernel<1, 2>)
-                                            : (g.p == 5 ? (const void*)conv0_lean_bwd_kernel<2, 5> : (const void*)conv0_lean_bwd_kernel<2, 2>);
-                rc = ensure_dyn_smem(kfn, (int)bsm);
+                rc = conv0_lean_backward(x, cin0, batch,
+                                         reinterpret_cast<const unsigned*>(reinterpret_cast<const char*>(ws) + P.arg0), dA, g,
+                                         reinterpret_cast<const double*>(reinterpret_cast<const char*>(ws) + P.gram),
+                                         params + P.conv_w[0], params + P.conv_b[0], params + P.bn_w[0], stat, part,
+                                         grads + P.conv_w[0], grads + P.conv_b[0], grads + P.bn_w[0], grads + P.bn_b[0], st);
                 if (rc) return rc;
-                if (cin0 == 1 && g.p == 5) conv0_lean_bwd_kernel<1, 5><<<grid, 256, bsm, st>>>(x, argw, dA, g, gpi, n_groups, part);
-                else if (cin0 == 1) conv0_lean_bwd_kernel<1, 2><<<grid, 256, bsm, st>>>(x, argw, dA, g, gpi, n_groups, part);
-                else if (g.p == 5) conv0_lean_bwd_kernel<2, 5><<<grid, 256, bsm, st>>>(x, argw, dA, g, gpi, n_groups, part);
-                else conv0_lean_bwd_kernel<2, 2><<<grid, 256, bsm, st>>>(x, argw, dA, g, gpi, n_groups, part);
-                SED_POST_LAUNCH();
-                double* Ssum = reinterpret_cast<double*>(part + (size_t)grid.x * (K0 + 1) * P.C + 64);   // behind the partials
-                conv0_lean_bwd_colsum_kernel<<<dim3(K0 + 1, P.C / 128), 1024, 0, st>>>(part, (int)grid.x, K0 + 1, P.C, Ssum);
-                SED_POST_LAUNCH();
-                conv0_lean_bwd_finalize_kernel<<<(P.C * 32 + 255) / 256, 256, 0, st>>>(
-                    Ssum, cin0, P.C, gram, params + P.conv_w[0], params + P.conv_b[0], params + P.bn_w[0], stat,
-                    grads + P.conv_w[0], grads + P.conv_b[0], grads + P.bn_w[0], grads + P.bn_b[0]);
-                SED_POST_LAUNCH();
-                (void)K0;
                 break;
             }
             // the caller wants d(input): rebuild y0 (bit-identical to what the fused forward consumed) and take the
