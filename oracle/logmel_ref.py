@@ -20,7 +20,9 @@ here is librosa's published algorithm:
     triangular filters, area normalisation 2/(f[i+2]-f[i]).
 
 PARITY UNPINNED by the reference (it holds no tests / golden vectors).  Cross-checks live in
-tests/test_oracle_logmel.py (torchaudio.functional.melscale_fbanks, torch.stft).
+tests/test_oracle_logmel.py (torchaudio.functional.melscale_fbanks, torch.stft), together with committed vectors of an
+independent third-party implementation (transformers.audio_utils; oracle/make_golden_logmel_thirdparty.py ->
+tests/golden/logmel_thirdparty.npz), which this restatement matches to 5e-7.
 """
 from __future__ import annotations
 

@@ -151,3 +151,13 @@ def test_int16_host_drop_in(feat):
     got = feat._mbe(y16, feat.SR)
     want = L.mbe(y16.astype(np.float32) / np.float32(32768.0))
     assert got.shape == want.shape and close(got, want) <= RTOL
+
+
+def test_against_third_party_golden(feat, golden_dir):
+    """The CUDA kernel against vectors of `transformers.audio_utils` (oracle/make_golden_logmel_thirdparty.py): an
+    implementation that shares no code with this repository or its oracle."""
+    g = np.load(os.path.join(golden_dir, "logmel_thirdparty.npz"))
+    for name in ("mix_1s", "noise_odd", "chirp_7k", "short"):
+        for pm in ("constant", "reflect"):
+            got = feat.mbe_device(torch.from_numpy(g[name + "_pcm"]).cuda(), pad_mode=pm).cpu().numpy()
+            assert close(got, g[f"{name}_{pm}"].astype(np.float64)) <= RTOL, (name, pm)

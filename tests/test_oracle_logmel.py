@@ -70,3 +70,17 @@ def test_frozen_anchor(golden_dir):
             got = L.mbe_multichannel(g[name + "_pcm"], pad_mode=pm)
             np.testing.assert_allclose(got, g[f"{name}_{pm}"], rtol=1e-6, atol=1e-6)
     np.testing.assert_array_equal(g["mel_fb"], L.mel_filterbank())
+
+
+def test_third_party_golden(golden_dir):
+    """Vectors produced by `transformers.audio_utils` (an independent librosa-compatible implementation; generating
+    script: oracle/make_golden_logmel_thirdparty.py).  Not the reference's own numbers -- librosa is absent -- but a
+    pin that does not come from this repository's code."""
+    g = np.load(os.path.join(golden_dir, "logmel_thirdparty.npz"))
+    for name in ("mix_1s", "noise_odd", "chirp_7k", "short"):
+        for pm in ("constant", "reflect"):
+            want = g[f"{name}_{pm}"]
+            got = L.mbe(g[name + "_pcm"], pad_mode=pm)
+            assert got.shape == want.shape
+            err = np.abs(got.astype(np.float64) - want) / np.maximum(np.abs(want), 1.0)
+            assert err.max() <= 5e-6, (name, pm, err.max())
