@@ -90,10 +90,10 @@ def phase_model(cfg, B, per):
         elif tc_ok:
             for ph, kn in (("fwd", "conv_tc_kernel"), ("dgrad", "conv_tc_kernel"), ("wgrad", "wgrad_tc_kernel")):
                 m[f"conv{i}.{ph}"] = ("tensor", per[f"conv{i}"], f"{kn} (tcgen05 implicit GEMM, 3-term bf16 split) + bf16 plane split")
-        m[f"pool{i}.fwd"] = ("hbm", y + a, "bn_relu_pool_fwd_kernel")
-        m[f"pool{i}.bwd_sums"] = ("hbm", y + a, "bn_pool_bwd_sums_t_kernel")
+        m[f"pool{i}.fwd"] = ("hbm", y + a, "bn_relu_pool_fwd_t_kernel (BN + ReLU + max-pool + dropout: conv output in, pooled planes out)")
+        m[f"pool{i}.bwd_sums"] = ("hbm", 2 * a, "bn_bwd_sums_act_kernel (BatchNorm backward sums from the saved block output and dA)")
         if i > 0:
-            m[f"pool{i}.bwd_dy"] = ("hbm", 2 * y + a, "bn_pool_bwd_dy_kernel")
+            m[f"pool{i}.bwd_dy"] = ("hbm", 2 * y + a, "bn_pool_bwd_dy_t_kernel (dy of every conv output element as bf16 planes)")
         w //= p
         cin = C
     return m
