@@ -1095,32 +1095,40 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
     const long B = batch;
 
     // ---- operand planes of the weights (conv blocks on tcgen05: forward and flipped data-gradient layout; W_ih of the
-    //      tensor-core GRU layers), built on the side stream while block 0 runs; the backward pass reuses them
+    //      tensor-core GRU layers), built on the side stream while block 0 runs; the backward pass reuses them.  The fork
+    //      point is the start of the call (the parameters are final there); the side-stream launches themselves are
+    //      enqueued AFTER block 0's own kernels, so that a caller who synchronises every step sees the GPU busy sooner.
     SideStream* wside = nullptr;
-    bool wp_pending = false;
+    bool wp_pending = false, wp_forked = false;
     if (P.weight_planes_ahead) {
         rc = side_stream(&wside);
         if (rc) return rc;
-        cudaStream_t ss = wside->st;
         SED_CUDA_OK(cudaEventRecord(wside->fork[0], st));
+    }
+    auto enqueue_weight_planes = [&]() -> int {
+        if (!P.weight_planes_ahead || wp_forked) return SEDB200_OK;
+        wp_forked = true;
+        cudaStream_t ss = wside->st;
         SED_CUDA_OK(cudaStreamWaitEvent(ss, wside->fork[0], 0));
         for (int i = 1; i < P.n_conv; ++i) {
             if (!P.conv_tc_all[i]) continue;
             for (int dg = 0; dg < 2; ++dg) {
-                rc = conv_tc_weight_planes(params + P.conv_w[i], P.cin[i], P.C, dg, reinterpret_cast<char*>(ws) + P.wpl[i][dg], ss);
-                if (rc) return rc;
+                const int rc2 = conv_tc_weight_planes(params + P.conv_w[i], P.cin[i], P.C, dg,
+                                                      reinterpret_cast<char*>(ws) + P.wpl[i][dg], ss);
+                if (rc2) return rc2;
             }
         }
         for (int l = 0; l < P.n_gru; ++l) {
             if (!P.gru_tc[l]) continue;
             const size_t wpb = ((size_t)6 * P.gh[l] * P.gin[l] * 2 + 1023) & ~(size_t)1023;
             char* wp = reinterpret_cast<char*>(ws) + P.wihp[l];
-            rc = split_planes(params + P.wih[l], wp, wp + wpb, 6L * P.gh[l] * P.gin[l], ss);
-            if (rc) return rc;
+            const int rc2 = split_planes(params + P.wih[l], wp, wp + wpb, 6L * P.gh[l] * P.gin[l], ss);
+            if (rc2) return rc2;
         }
         SED_CUDA_OK(cudaEventRecord(wside->done[0], ss));
         wp_pending = true;
-    }
+        return SEDB200_OK;
+    };
     struct WpJoin {             // rejoin on every way out, and before the first consumer
         SideStream*& s; bool& pending; cudaStream_t st;
         void now() { if (pending) { cudaStreamWaitEvent(st, s->done[0], 0); pending = false; } }
@@ -1129,7 +1137,11 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
 
     // ---- conv blocks
     for (int i = 0; i < P.n_conv; ++i) {
-        if (i > 0) wp_join.now();
+        if (i > 0) {
+            rc = enqueue_weight_planes();
+            if (rc) return rc;
+            wp_join.now();
+        }
         const float* in = i == 0 ? x : wsf(ws, P.act[i - 1]);
         const InStrides s = in_strides(P, d, i);
         const int M = (int)(B * P.H * P.win[i]), K = 9 * P.cin[i];
@@ -1241,6 +1253,8 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
     // ---- BiGRU stack
     const int BT = (int)(B * P.T);
     const float* seq = wsf(ws, P.act[P.n_conv - 1]);
+    rc = enqueue_weight_planes();
+    if (rc) return rc;
     wp_join.now();
     for (int l = 0; l < P.n_gru; ++l) {
         const int h = P.gh[l], in = P.gin[l];
