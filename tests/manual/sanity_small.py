@@ -1,6 +1,6 @@
 """Tiny end-to-end exercise of every kernel family (for compute-sanitizer runs)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from dataclasses import replace
 import numpy as np, torch
 from oracle import logmel_ref, crnn_ref as R
