@@ -490,8 +490,8 @@ def run_ours(args, rank, world, local_rank):
         ach = amount_step / (ms_kernel_step * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": kname, "phases": dks, "achieved": ach, "peak": pk["tf_sustained"],
                 "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "traffic": traffic,
-                "traffic_note": "dram bytes per launch, mean of the launches captured by ncu --set full (forward "
-                "launches; profiles/ncu_traffic.json)",
+                "traffic_note": "dram bytes per launch, mean of this kernel's launches in one step as captured by ncu "
+                "--set full (profiles/ncu_traffic.json, profiles/r01_conv_tc_final_metrics.csv)",
                 "peak_source": pk["src"] + " (sustained bf16)", "algorithmic_flops_per_launch": amount,
                 "mma_tflops_issued": 3 * ach, "frac_issued": 3 * ach / pk["tf_sustained"],
                 "note": "fp32-grade 3-term bf16 split: the tensor pipe executes 3x the algorithmic FLOPs; frac is "
