@@ -207,6 +207,28 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params_dev, c
                           int batch, unsigned long long seed, void* ws_dev, size_t ws_bytes,
                           const float* dlogits_dev, float* grads_dev, float* dx_dev, void* stream);
 
+/* The keep-mask of conv block `block`'s dropout for (seed, batch) exactly as the fused kernels evaluate it (counter-
+ * based generator, nothing is stored by the forward pass), laid out as the reference's nn.Dropout would see the
+ * tensor: bytes [batch][conv_ch][H][W_out], 1 = kept (crnn_lightning.py:52, sed.py:92,107).  Blocks that carry no
+ * dropout in this configuration give all ones.  Test hook: lets an oracle apply the SAME mask. */
+int sedb200_crnn_dropout_mask(const sedb200_crnn_desc* d, int batch, unsigned long long seed, int block,
+                              unsigned char* mask_dev, void* stream);
+
+/* The recurrent half of nn.GRU(bidirectional=True, batch_first=True) on its own (crnn_lightning.py:61-62,71;
+ * sed.py:101,111), exposed for unit tests.  Gate order r, z, n; h0 = 0.
+ *   gi    [B][T][2][3H]  x W_ih^T + b_ih per direction (0 = forward in time, 1 = reverse)
+ *   whh   [2][3H][H], bhh [2][3H]
+ *   out   [B][T][2H]     forward half | reverse half
+ *   gates [B][T][2][4H]  r, z, n, q = W_hn h_{t-1} + b_hn (saved for the backward scan)
+ *   dout  [B][T][2H] -> dgi [B][T][2][3H] (gradient w.r.t. gi), dgh [B][T][2][3H] (w.r.t. W_hh h_{t-1} + b_hh);
+ *   part_b [B][2][2][3H]: per-batch-row sums over t of dgi ([.][0]) and dgh ([.][1]) when
+ *   sedb200_gru_scan_fused_bias_grads(H) != 0 (then it must be given), untouched otherwise. */
+int sedb200_gru_scan_fused_bias_grads(int H);
+int sedb200_gru_scan_fwd(const float* gi_dev, const float* whh_dev, const float* bhh_dev, float* out_dev,
+                         float* gates_dev, int B, int T, int H, void* stream);
+int sedb200_gru_scan_bwd(const float* dout_dev, const float* out_dev, const float* gates_dev, const float* whh_dev,
+                         float* dgi_dev, float* dgh_dev, float* part_b_dev, int B, int T, int H, void* stream);
+
 /* Global-norm clip (clip_grad_norm_ semantics: coef = min(1, max_norm/(norm+1e-6)); max_norm <= 0
  * disables) followed by torch.optim.Adam with coupled L2 weight decay, over flat buffers.
  * grad_prescale multiplies every gradient first (1/world_size after a sum all-reduce).

@@ -55,6 +55,10 @@ SIGNATURES = {
     "sedb200_crnn_head_supported": (_i, [_p]),
     "sedb200_crnn_head_fwd_bwd": (_i, [_p, _p, _i, _p, _sz, _p, _i, _f, _f, _f, _p, _p, _p, _p, _p]),
     "sedb200_crnn_backward": (_i, [_p, _p, _p, _i, C.c_ulonglong, _p, _sz, _p, _p, _p, _p]),
+    "sedb200_crnn_dropout_mask": (_i, [_p, _i, C.c_ulonglong, _i, _p, _p]),
+    "sedb200_gru_scan_fused_bias_grads": (_i, [_i]),
+    "sedb200_gru_scan_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "sedb200_gru_scan_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "sedb200_clip_adam_scratch_bytes": (_sz, [_l]),
     "sedb200_clip_adam": (_i, [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _l, _f, _f, _p, _p, _sz, _p]),
     "sedb200_p2p_region_bytes": (_sz, [_l]),

@@ -1073,6 +1073,27 @@ int side_stream(SideStream** out) {
     return SEDB200_OK;
 }
 
+
+// keep-mask of one block's dropout as the reference would hold it: NCHW bytes [B][C][H][Wo] (1 = kept), from the same
+// counter-based generator the fused kernels evaluate (element group i = ((b*H + h)*Wo + wo)*C/4 + c/4)
+__global__ void __launch_bounds__(256)
+dropout_mask_kernel(unsigned char* __restrict__ mask, long n_vec, PoolGeom g) {
+    const int C4 = g.C >> 2;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        long t = i / C4;
+        const int wo = (int)(t % g.Wo); t /= g.Wo;
+        const int h = (int)(t % g.H);
+        const long b = t / g.H;
+        Keep4 kp;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) kp.k[q] = true;
+        if (g.drop_p > 0.0f) kp = dropout_keep4(g.seed, (unsigned long long)i, g.drop_p);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            mask[((b * g.C + (c4 * 4 + q)) * g.H + h) * g.Wo + wo] = kp.k[q] ? 1 : 0;
+    }
+}
 }  // namespace
 }  // namespace sedb200
 
@@ -1684,6 +1705,22 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
             if (rc) return rc;
         }
     }
+    return SEDB200_OK;
+}
+
+int sedb200_crnn_dropout_mask(const sedb200_crnn_desc* d, int batch, unsigned long long seed, int block,
+                              unsigned char* mask_dev, void* stream) {
+    Plan P;
+    int rc = make_plan(d, 0, &P);
+    if (rc) return rc;
+    SED_REQUIRE(batch >= 1 && mask_dev, SEDB200_EINVAL, "crnn_dropout_mask: batch %d / null buffer", batch);
+    SED_REQUIRE(block >= 0 && block < P.n_conv, SEDB200_EINVAL, "crnn_dropout_mask: block %d of %d", block, P.n_conv);
+    rc = require_sm100();
+    if (rc) return rc;
+    const PoolGeom g = pool_geom(P, d, block, 1, seed);
+    const long n_vec = (long)batch * P.H * P.wout[block] * (P.C / 4);
+    dropout_mask_kernel<<<ew_blocks(n_vec), 256, 0, as_stream(stream)>>>(mask_dev, n_vec, g);
+    SED_POST_LAUNCH();
     return SEDB200_OK;
 }
 

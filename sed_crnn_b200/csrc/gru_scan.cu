@@ -1121,3 +1121,32 @@ int gru_scan_backward(const float* dout, const float* out, const float* gates, c
 }
 
 }  // namespace sedb200
+
+using namespace sedb200;
+
+extern "C" {
+
+int sedb200_gru_scan_fused_bias_grads(int H) { return gru_scan_fused_param_grads(H) ? 1 : 0; }
+
+int sedb200_gru_scan_fwd(const float* gi_dev, const float* whh_dev, const float* bhh_dev, float* out_dev,
+                         float* gates_dev, int B, int T, int H, void* stream) {
+    SED_REQUIRE(gi_dev && whh_dev && bhh_dev && out_dev && gates_dev, SEDB200_EINVAL, "gru_scan_fwd: null buffer");
+    SED_REQUIRE(B >= 1 && T >= 1 && H >= 1, SEDB200_EINVAL, "gru_scan_fwd: B=%d T=%d H=%d", B, T, H);
+    int rc = require_sm100();
+    if (rc) return rc;
+    return gru_scan_forward(gi_dev, whh_dev, bhh_dev, out_dev, gates_dev, B, T, H, as_stream(stream));
+}
+
+int sedb200_gru_scan_bwd(const float* dout_dev, const float* out_dev, const float* gates_dev, const float* whh_dev,
+                         float* dgi_dev, float* dgh_dev, float* part_b_dev, int B, int T, int H, void* stream) {
+    SED_REQUIRE(dout_dev && out_dev && gates_dev && whh_dev && dgi_dev && dgh_dev, SEDB200_EINVAL, "gru_scan_bwd: null buffer");
+    SED_REQUIRE(B >= 1 && T >= 1 && H >= 1, SEDB200_EINVAL, "gru_scan_bwd: B=%d T=%d H=%d", B, T, H);
+    SED_REQUIRE(part_b_dev || !gru_scan_fused_param_grads(H), SEDB200_EINVAL,
+                "gru_scan_bwd: H=%d writes bias-gradient partials, part_b_dev must be given", H);
+    int rc = require_sm100();
+    if (rc) return rc;
+    return gru_scan_backward(dout_dev, out_dev, gates_dev, whh_dev, dgi_dev, dgh_dev, nullptr, part_b_dev, B, T, H,
+                             as_stream(stream));
+}
+
+}  // extern "C"

@@ -10,17 +10,25 @@ decorte_datamodule.py:41-48,67-74,89) -- so under the same seeds the windows are
 
 `DeviceWindowLoader` replaces `DataLoader(HitWindowDataset, batch_size, shuffle, drop_last)`
 (decorte_datamodule.py:127-137): it yields CUDA tensors `[B,1,N_MELS,SEQ_LEN_IN]`, `[B,SEQ_LEN_OUT,1]`.
+`DecorteDataModule(fold_id, cache_dir, batch_size, num_workers)` (decorte_datamodule.py:117-137), `_load_all_npz`
+(:24-34) and `_spec_augment` (:39-49) keep the reference names, so `from decorte_datamodule import DecorteDataModule`
+(train_lightning.py:12) works against this module.  `HitWindowDataset.__getitem__` returns CUDA tensors, so it must
+NOT be wrapped in a `DataLoader(num_workers > 0, pin_memory=True)` -- use the loaders the DataModule returns.
 There is no CPU path: every window is produced by the kernel.
 """
 from __future__ import annotations
 
+import os
 import random
 
 import numpy as np
 import torch
 
 from . import _lib
-from .train_constants import (BATCH_SIZE, FREQ_MASK_W, MASKS_PER_EX, SEQ_LEN_IN, SEQ_LEN_OUT, TIME_MASK_W)
+from .train_constants import (BATCH_SIZE, FREQ_MASK_W, MASKS_PER_EX, NUM_WORKERS, SEQ_LEN_IN, SEQ_LEN_OUT,
+                              TIME_MASK_W)
+
+CACHE_DIR = os.path.expanduser("~/src/plai_cv/cache/decorte_metadata/features")     # train_constants.py:9
 
 LAYOUT_FORK, LAYOUT_SEDNET = 0, 1
 
@@ -46,6 +54,40 @@ def _find_clean_negatives(label_vec, seq_len_in: int = SEQ_LEN_IN) -> np.ndarray
         _lib.check(_lib.lib().sedb200_clean_negatives(lab.data_ptr(), lab.shape[0], lab.shape[1], seq_len_in,
                                                       flag.data_ptr(), _lib.current_stream_ptr()))
     return np.flatnonzero(flag.cpu().numpy()).astype(np.int64)
+
+
+def _load_all_npz(folder: str, folds=range(1, 5), verbose: bool = True) -> dict:
+    """decorte_datamodule.py:24-34 / sed.py:115-125: read the fold packs `mbe_mon_fold{i}.npz` (keys `arr_0..arr_3` =
+    train_x, train_y, val_x, val_y, written by feature.py:131 / `feature.pack_folds`) into host RAM."""
+    out = {}
+    for i in folds:
+        fp = os.path.join(folder, f"mbe_mon_fold{i}.npz")
+        arr = np.load(fp)
+        out[i] = {"train_x": arr["arr_0"], "train_y": arr["arr_1"], "val_x": arr["arr_2"], "val_y": arr["arr_3"]}
+        if verbose:
+            print(f"loaded into RAM -> fold {i}  ({arr['arr_0'].nbytes / 1e6:0.1f} MB train)")
+    return out
+
+
+def _spec_augment(mel):
+    """decorte_datamodule.py:39-49 for ONE window `mel` [N_MELS, SEQ_LEN_IN] (CUDA tensor or numpy array): draws the
+    mask offsets from `np.random` exactly like the reference (time offset, then frequency offset, MASKS_PER_EX times)
+    and zeroes the bands with the window kernel's masking path.  Returns the same kind of object it was given."""
+    was_numpy = not isinstance(mel, torch.Tensor)
+    m = _as_dev(mel)
+    F, T = m.shape
+    t0, f0 = [-1] * MASKS_PER_EX, [-1] * MASKS_PER_EX
+    for i in range(MASKS_PER_EX):
+        if T > TIME_MASK_W:
+            t0[i] = int(np.random.randint(0, T - TIME_MASK_W))
+        if F > FREQ_MASK_W:
+            f0[i] = int(np.random.randint(0, F - FREQ_MASK_W))
+    x, _ = window_batch(m.t().contiguous(), None, [0], seq_in=T, tmask=[t0], fmask=[f0])
+    out = x[0, 0]
+    if was_numpy:
+        mel[...] = out.cpu().numpy()             # the reference masks in place and returns its argument
+        return mel
+    return out
 
 
 def window_batch(mel: torch.Tensor, lab: torch.Tensor | None, starts, *, seq_in: int = SEQ_LEN_IN,
@@ -171,23 +213,75 @@ class DeviceWindowLoader:
 
     def __init__(self, ds: HitWindowDataset, batch_size: int = BATCH_SIZE, shuffle: bool = False,
                  drop_last: bool = False, generator: torch.Generator | None = None, rank: int = 0,
-                 world_size: int = 1):
+                 world_size: int = 1, seed: int | None = None):
         self.ds, self.batch_size, self.shuffle, self.drop_last = ds, batch_size, shuffle, drop_last
         self.generator, self.rank, self.world_size = generator, rank, world_size
+        self.seed, self.epoch = seed, 0
         if batch_size % world_size:
             raise ValueError(f"global batch {batch_size} does not split over {world_size} ranks")
+        if world_size > 1 and shuffle and generator is None and seed is None:
+            # every rank must walk the SAME permutation, or "rank r's slice of global batch b" means nothing
+            raise ValueError("DeviceWindowLoader(world_size > 1, shuffle=True) needs `seed` (shared by all ranks) or "
+                             "an identically seeded `generator`")
 
     def __len__(self):
         n = len(self.ds)
         return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
 
+    def set_epoch(self, epoch: int) -> None:
+        self.epoch = int(epoch)
+
     def __iter__(self):
         n = len(self.ds)
-        order = torch.randperm(n, generator=self.generator).tolist() if self.shuffle else list(range(n))
-        per = self.batch_size // self.world_size
+        gen = self.generator
+        if self.shuffle and gen is None and self.seed is not None:
+            gen = torch.Generator().manual_seed(self.seed + self.epoch)
+        order = torch.randperm(n, generator=gen).tolist() if self.shuffle else list(range(n))
+        self.epoch += 1
         for b in range(len(self)):
             idx = order[b * self.batch_size:(b + 1) * self.batch_size]
             if self.world_size > 1:
-                idx = idx[self.rank * per:(self.rank + 1) * per]
-            if idx:
-                yield self.ds.batch(idx)
+                # every rank must yield the SAME number of batches (one gradient exchange per batch): the last, partial
+                # global batch is split as evenly as its size allows, and when it holds fewer items than ranks the
+                # ranks left over re-use its first items (their gradients enter the average like anyone's)
+                from .parallel import shard_range
+                r = shard_range(len(idx), self.rank, self.world_size)
+                idx = idx[r.start:r.stop] if len(r) else idx[:1]
+            yield self.ds.batch(idx)
+
+
+try:                                                       # real Lightning when it is installed
+    import pytorch_lightning as pl
+    _DataModuleBase = pl.LightningDataModule
+except Exception:                                          # pragma: no cover - not installed in this image
+    class _DataModuleBase:
+        def __init__(self):
+            pass
+
+
+class DecorteDataModule(_DataModuleBase):
+    """Drop-in for decorte_datamodule.DecorteDataModule (decorte_datamodule.py:117-137): same constructor, `setup`,
+    `train_dataloader`, `val_dataloader`, attributes `train_ds` / `val_ds`.  The fold pack is read from
+    `cache_dir/mbe_mon_fold{fold_id}.npz` and uploaded once; the loaders are `DeviceWindowLoader`s (one kernel launch
+    per batch) instead of `DataLoader(num_workers=4, pin_memory=True)` -- `num_workers` is accepted and ignored.
+    `rank` / `world_size` / `seed` shard every global batch over data-parallel ranks (reference: devices=1)."""
+
+    def __init__(self, fold_id: int, cache_dir: str = CACHE_DIR, batch_size: int = BATCH_SIZE,
+                 num_workers: int = NUM_WORKERS, rank: int = 0, world_size: int = 1, seed: int | None = None):
+        super().__init__()
+        self.fold_id, self.cache_dir = fold_id, cache_dir
+        self.batch_size, self.num_workers = batch_size, num_workers
+        self.rank, self.world_size, self.seed = rank, world_size, seed
+
+    def setup(self, stage=None):
+        fdata = _load_all_npz(self.cache_dir, folds=[self.fold_id])[self.fold_id]    # the reference loads all four
+        self.train_ds = HitWindowDataset(fdata["train_x"], fdata["train_y"], augment=True)
+        self.val_ds = HitWindowDataset(fdata["val_x"], fdata["val_y"], augment=False)
+
+    def train_dataloader(self):
+        return DeviceWindowLoader(self.train_ds, self.batch_size, shuffle=True, drop_last=True, rank=self.rank,
+                                  world_size=self.world_size, seed=self.seed)
+
+    def val_dataloader(self):
+        return DeviceWindowLoader(self.val_ds, self.batch_size, shuffle=False, rank=self.rank,
+                                  world_size=self.world_size)

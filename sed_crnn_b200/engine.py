@@ -305,6 +305,21 @@ class CRNNEngine:
             self.num_batches_tracked = nbt
         return out
 
+    def dropout_masks(self, batch: int, seed: int | None = None) -> list[torch.Tensor]:
+        """Keep-masks (uint8 [B, conv_ch, H, W_out], one per conv block) of the training forward run with `seed`
+        (default: the seed of the last forward).  The forward pass never stores them -- they come from the same
+        counter-based generator -- so this is a test hook: an oracle can apply the SAME masks."""
+        seed = self._last_seed if seed is None else int(seed)
+        out, w = [], self.cfg.W
+        for i, p in enumerate(self.cfg.pool):
+            w //= p
+            m = torch.empty(batch, self.cfg.conv_ch, self.cfg.H, w, dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.check(self.L.sedb200_crnn_dropout_mask(C.byref(self.desc), batch, seed, i, m.data_ptr(),
+                                                            _lib.current_stream_ptr()))
+            out.append(m)
+        return out
+
     # ------------------------------------------------------------------ metrics on device
     def threshold_counts(self, probs: torch.Tensor, targets: torch.Tensor, block: int, threshold: float = 0.5):
         """13 integer counts behind metrics.py (see sedb200.h); probs/targets [..., n_cls] CUDA float32."""

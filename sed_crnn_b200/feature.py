@@ -169,3 +169,46 @@ class StandardScaler:
 
     def fit_transform(self, X):
         return self.fit(X).transform(X)
+
+
+# ----------------------------------------------------------------------------------------------- fold packs
+FOLD_PACK_FMT = "mbe_mon_fold{}.npz"         # feature.py:131; read back by decorte_datamodule._load_all_npz / sed.load_all_npz
+
+
+def _dev2d(a) -> torch.Tensor:
+    t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    if t.dim() == 1:
+        t = t[:, None]
+    return t.to("cuda", torch.float32, non_blocking=True)
+
+
+def pack_folds(per_video: dict, cache_dir: str, n_folds: int | None = None) -> list[str]:
+    """feature.py:109-133 -- the step between the two halves of the hot path, with the arithmetic on the device.
+
+    per_video: {video_name: (mbe [frames, n_feat], lbl [frames, 1], fold_id)} in the reference's iteration order
+    (numpy arrays or CUDA tensors, e.g. straight from `mbe_device` / `rasterize_labels`).  For every fold f:
+    test = the videos of fold f concatenated in dict order, train = all the others; a `StandardScaler` is fitted on
+    the training frames and applied to both (feature.py:127-129); the pack is written with `np.savez` positional
+    arrays, i.e. keys `arr_0..arr_3` = X_train, Y_train, X_test, Y_test, float32, into
+    `cache_dir/mbe_mon_fold{f+1}.npz` -- the file format `_load_all_npz` (decorte_datamodule.py:24-34) and
+    `load_all_npz` (sed.py:115-125) read.  Returns the paths written."""
+    import os
+    if not per_video:
+        raise ValueError("pack_folds: no videos")
+    fold_k = (max(v[2] for v in per_video.values()) + 1) if n_folds is None else int(n_folds)     # feature.py:112
+    dev = {k: (_dev2d(m), _dev2d(l), int(f)) for k, (m, l, f) in per_video.items()}
+    paths = []
+    for f in range(fold_k):
+        tr = [(m, l) for (m, l, fold) in dev.values() if fold != f]
+        te = [(m, l) for (m, l, fold) in dev.values() if fold == f]
+        if not tr or not te:
+            raise ValueError(f"pack_folds: fold {f} has no {'training' if not tr else 'test'} video")
+        X_train, Y_train = torch.cat([m for m, _ in tr]), torch.cat([l for _, l in tr])
+        X_test, Y_test = torch.cat([m for m, _ in te]), torch.cat([l for _, l in te])
+        scaler = StandardScaler()
+        X_train = scaler.fit_transform(X_train)
+        X_test = scaler.transform(X_test)
+        out_fold = os.path.join(cache_dir, FOLD_PACK_FMT.format(f + 1))
+        np.savez(out_fold, X_train.cpu().numpy(), Y_train.cpu().numpy(), X_test.cpu().numpy(), Y_test.cpu().numpy())
+        paths.append(out_fold)
+    return paths

@@ -8,6 +8,8 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from .decorte_datamodule import HitWindowDataset, _find_clean_negatives as find_clean_negatives   # noqa: F401  (sed.py:48-79)
+from .decorte_datamodule import _load_all_npz as load_all_npz                  # noqa: F401  (sed.py:115-125)
 from .modules import BCEWithLogitsLoss, SedTimePooledCRNN as TimePooledCRNN   # noqa: F401
 from .train_constants import FPS_OUT, SEQ_LEN_IN, SEQ_LEN_OUT, TIME_POOL       # noqa: F401
 
