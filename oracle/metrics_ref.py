@@ -82,3 +82,16 @@ def er_overall_1sec(O, T, block_size):
 def compute_scores(pred, y, frames_in_1_sec=50):
     return {"f1_overall_1sec": f1_overall_1sec(pred, y, frames_in_1_sec),
             "er_overall_1sec": er_overall_1sec(pred, y, frames_in_1_sec)}
+
+
+def counts13(O, T, block):
+    """The 13 integers `sedb200_threshold_counts` produces (include/sedb200.h), from the restatement above:
+    frame-level TP, Nsys, Nref, S, D, I; block-max (ceil blocks, metrics.py:50) TP, Nsys, Nref; block-max (floor
+    blocks, metrics.py:62) S, D, I, Nref."""
+    O, T = _as2d(O), _as2d(T)
+    fr = frame_counts(O, T)
+    nc, nf = int(np.ceil(O.shape[0] / block)), int(O.shape[0] / block)
+    f1 = frame_counts(_block_max(O, block, nc), _block_max(T, block, nc)) if nc else dict(TP=0, Nsys=0, Nref=0)
+    er = frame_counts(_block_max(O, block, nf), _block_max(T, block, nf)) if nf else dict(S=0, D=0, I=0, Nref=0)
+    return np.array([fr["TP"], fr["Nsys"], fr["Nref"], fr["S"], fr["D"], fr["I"], f1["TP"], f1["Nsys"], f1["Nref"],
+                     er["S"], er["D"], er["I"], er["Nref"]], dtype=np.int64)

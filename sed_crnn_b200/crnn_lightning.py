@@ -70,11 +70,23 @@ class CRNNLightning(_Base):
         p_t = torch.cat(self._buf[mode]["preds"])
         t_t = torch.cat(self._buf[mode]["trues"])
         loss = torch.stack(self._buf[mode]["losses"]).mean().item()
+        step_rows = [p.shape[0] * p.shape[1] for p in self._buf[mode]["preds"]]
         for k in self._buf[mode]:
             self._buf[mode][k].clear()
-        c = metrics._counts(p_t, t_t, FPS_OUT)                       # 13 integers, one small D2H
+        from . import parallel
+        if parallel.world_info()[1] > 1:
+            # data-parallel epoch: decisions are re-assembled in single-process order, counted on block-aligned shards
+            # and summed with one integer all-reduce (parallel.sharded_metric_counts) -- same scores as one process
+            n_cls = p_t.shape[-1]
+            c = parallel.sharded_metric_counts((p_t > 0.5).reshape(-1, n_cls), t_t.reshape(-1, n_cls), step_rows,
+                                               FPS_OUT)
+            total_t = torch.tensor([p_t.numel()], dtype=torch.int64, device=p_t.device)
+            total = int(parallel.allreduce_counts_(total_t)[0])
+        else:
+            c = metrics._counts(p_t, t_t, FPS_OUT)                   # 13 integers, one small D2H
+            total = p_t.numel()
         f1_fr, er_fr, f1_1s, er_1s = metrics.scores_from_counts(c)
-        tp, nsys, nref, total = int(c[0]), int(c[1]), int(c[2]), p_t.numel()
+        tp, nsys, nref = int(c[0]), int(c[1]), int(c[2])
         fp, fn = nsys - tp, nref - tp
         cm = np.array([[total - tp - fp - fn, fp], [fn, tp]])
         return dict(loss=loss, f1_frame=f1_fr, er_frame=er_fr, f1_1s=f1_1s, er_1s=er_1s, cm=cm)

@@ -58,6 +58,85 @@ def broadcast_(flat: torch.Tensor, src: int = 0, group=None) -> None:
         dist.broadcast(flat, src=src, group=group)
 
 
+# ----------------------------------------------------------------------------------------------- metrics across ranks
+def metric_row_shard(n_rows: int, block: int, rank: int, world: int) -> range:
+    """Rows of the flattened (N*T) decision matrix that `rank` counts: a contiguous run of WHOLE blocks of `block`
+    rows (metrics.py:46-68 takes block maxima over consecutive rows of the flattened axis, utils.py:11-12), so that
+    no block straddles two ranks and the 13 integer counts are additive.  Only the last non-empty shard can end in
+    the global trailing partial block -- which f1_overall_1sec counts (ceil, metrics.py:50) and er_overall_1sec drops
+    (int(), metrics.py:62), exactly as in one process."""
+    if block < 1:
+        raise ValueError("block must be >= 1")
+    n_blocks = -(-n_rows // block)
+    b = shard_range(n_blocks, rank, world)
+    return range(min(b.start * block, n_rows), min(b.stop * block, n_rows))
+
+
+def allreduce_counts_(counts: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place integer SUM all-reduce of the 13 metric counts (exact: int64)."""
+    if counts.dtype != torch.int64:
+        raise TypeError("metric counts are int64")
+    _, world = world_info(group)
+    if world > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    return counts
+
+
+def gather_rows_in_global_order(local: torch.Tensor, step_rows, group=None) -> torch.Tensor:
+    """local: [rows_local, C] = this rank's rows of every step, concatenated in step order; step_rows: rows per step on
+    this rank.  Returns the rows of ALL ranks in the order a single process would have seen them: for each step, rank
+    0's slice of the global batch, then rank 1's, ... (the contiguous per-rank slices of `DeviceWindowLoader` /
+    `batch_slice`).  Ranks may hold different row counts per step (a last partial batch)."""
+    rank, world = world_info(group)
+    if world == 1:
+        return local
+    step_rows = [int(r) for r in step_rows]
+    if sum(step_rows) != local.shape[0]:
+        raise ValueError("step_rows does not add up to the local row count")
+    all_steps = [None] * world
+    dist.all_gather_object(all_steps, step_rows, group=group)
+    if len({len(s) for s in all_steps}) != 1:
+        raise RuntimeError(f"ranks ran different numbers of steps: {[len(s) for s in all_steps]}")
+    totals = [sum(s) for s in all_steps]
+    pad = max(totals)
+    buf = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    buf[:local.shape[0]] = local
+    gathered = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(gathered, buf, group=group)
+    offs = [0] * world
+    pieces = []
+    for s in range(len(step_rows)):
+        for r in range(world):
+            n = all_steps[r][s]
+            pieces.append(gathered[r][offs[r]:offs[r] + n])
+            offs[r] += n
+    return torch.cat(pieces)
+
+
+def sharded_metric_counts(decisions_local: torch.Tensor, targets_local: torch.Tensor, step_rows, block: int,
+                          group=None, count_fn=None):
+    """The 13 integer counts behind metrics.py for an epoch whose predictions are spread over data-parallel ranks
+    (SURVEY 8e row 4): decisions / targets ([rows_local, C], uint8 or float) are exchanged once as bytes, every rank
+    counts its block-aligned shard of the GLOBAL flattened axis on its own GPU (`sedb200_threshold_counts`), and the
+    counts are summed with one integer all-reduce.  Equal, bit for bit, to counting everything in one process.
+    `count_fn(O, T, block) -> 13 ints` defaults to the device counter (`metrics._counts`)."""
+    if count_fn is None:
+        from . import metrics
+        count_fn = metrics._counts
+    rank, world = world_info(group)
+    O = gather_rows_in_global_order(decisions_local.to(torch.uint8), step_rows, group)
+    T = gather_rows_in_global_order(targets_local.to(torch.uint8), step_rows, group)
+    rows = metric_row_shard(O.shape[0], block, rank, world)
+    import numpy as np
+    if len(rows):
+        c = np.asarray(count_fn(O[rows.start:rows.stop], T[rows.start:rows.stop], block), dtype=np.int64)
+    else:
+        c = np.zeros(13, dtype=np.int64)
+    counts = torch.from_numpy(c.copy()).to(O.device)
+    allreduce_counts_(counts, group)
+    return counts.cpu().numpy()
+
+
 class _RawCudaArray:
     """`__cuda_array_interface__` view of library-owned device memory, so torch can wrap it without a copy."""
 
