@@ -251,7 +251,12 @@ int sedb200_clip_adam(float* params_dev, const float* grads_dev, float* exp_avg_
  * pass for exchange number `seq` must write its gradients at region + sedb200_p2p_grad_offset_bytes(n, seq & 1).
  * `seq` starts at 1 and increases by exactly 1 per call on every rank; `step` is Adam's bias-correction step.
  * reduced_dev [n] receives the summed gradients; results are bit-identical on all ranks (fixed rank order).
- * sedb200_p2p_status reads back the region's status word: non-zero = a peer did not publish within ~2 s. */
+ * Failure handling: if a peer does not publish within the wait bound (60 s; environment variable
+ * SEDB200_P2P_TIMEOUT_MS overrides) the kernel raises the region's status word, which is STICKY, and this and every
+ * later exchange aborts grid-uniformly: params / exp_avg / exp_avg_sq are left untouched and gnorm_dev[0] = NaN (a
+ * stale peer buffer is never applied).  sedb200_p2p_status reads the word back (synchronising copy); the word sits at
+ * byte offset sedb200_p2p_status_offset_bytes() of the region for callers that prefer an asynchronous copy. */
+long   sedb200_p2p_status_offset_bytes(void);
 size_t sedb200_p2p_region_bytes(long n);
 long   sedb200_p2p_grad_offset_bytes(long n, int parity);
 int    sedb200_p2p_region_alloc(size_t bytes, void** region_dev, unsigned char* ipc_handle /* [64] */);

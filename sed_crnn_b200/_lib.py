@@ -69,6 +69,7 @@ SIGNATURES = {
     "sedb200_p2p_region_free": (_i, [_p]),
     "sedb200_p2p_status": (_i, [_p, _p]),
     "sedb200_p2p_scratch_bytes": (_sz, []),
+    "sedb200_p2p_status_offset_bytes": (_l, []),
     "sedb200_p2p_allreduce_clip_adam": (_i, [_p, _i, _i, _l, _l, _l, _p, _p, _p, _p, _f, _f, _f, _f, _f, _f, _f, _p,
                                             _p, _sz, _p]),
     "sedb200_threshold_counts": (_i, [_p, _p, _l, _i, _i, _f, _p, _p]),

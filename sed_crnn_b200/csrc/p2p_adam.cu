@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace cg = cooperative_groups;
@@ -34,12 +35,14 @@ namespace {
 constexpr int kMaxWorld = 16;
 constexpr int kThreads = 256;
 constexpr size_t kHeaderBytes = 1024;          // flags[kMaxWorld] (u64) + status word, then the two gradient buffers
-constexpr long long kSpinTimeoutCycles = 4LL * 1000 * 1000 * 1000;   // ~2 s at 2 GHz
+constexpr long long kDefaultTimeoutMs = 60 * 1000;   // SEDB200_P2P_TIMEOUT_MS overrides; a peer may legitimately be late
+                                                     // (checkpoint on rank 0, validation, a data-loader stall)
 
 struct P2PArgs {
     unsigned char* region[kMaxWorld];   // exchange regions in rank order (own one included), peer-mapped
     int world, rank, parity;
     unsigned long long seq;             // step number published in the flags (monotonic)
+    long long timeout_cycles;           // bound of the flag wait
     long n, buf_stride;                 // floats per gradient buffer (padded)
     float* params; float* m; float* v; float* reduced; float* part; float* gnorm;
     float lr, b1, b2, eps, wd, bc1, bc2_sqrt, max_norm, prescale;
@@ -78,8 +81,9 @@ p2p_reduce_clip_adam_kernel(const P2PArgs a) {
         }
         const long long t0 = clock64();
         while (ld_acquire_sys(my_flags + p) < a.seq) {
-            if (clock64() - t0 > kSpinTimeoutCycles) {      // a peer died: flag it and fall through (no hang)
+            if (clock64() - t0 > a.timeout_cycles) {        // a peer died: raise the (sticky) status word -- no hang
                 atomicExch(status, 1u);
+                __threadfence();
                 break;
             }
         }
@@ -109,6 +113,14 @@ p2p_reduce_clip_adam_kernel(const P2PArgs a) {
         a.part[blockIdx.x] = t;
     }
     grid.sync();
+
+    // ---- abort, grid-uniformly, if ANY block of this or an earlier step gave up waiting: the sums above may contain a
+    //      peer's stale buffer, so parameters and Adam state stay untouched and the norm reads NaN; the status word is
+    //      never cleared, every later step aborts too, and the host raises when it looks (P2PGradExchange.check)
+    if (*reinterpret_cast<volatile unsigned int*>(status) != 0u) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.gnorm[0] = __int_as_float(0x7fc00000);
+        return;
+    }
 
     // ---- 3. global norm: every block folds the same partials in the same order
     if (threadIdx.x < 32) {
@@ -209,6 +221,8 @@ int sedb200_p2p_status(const void* region_dev, unsigned int* status_host) {
     return SEDB200_OK;
 }
 
+long sedb200_p2p_status_offset_bytes(void) { return (long)kMaxWorld * 8; }
+
 size_t sedb200_p2p_scratch_bytes(void) { return 1024 * sizeof(float); }
 
 int sedb200_p2p_allreduce_clip_adam(void* const* regions_host, int world, int rank, long n, long seq, long step,
@@ -238,6 +252,14 @@ int sedb200_p2p_allreduce_clip_adam(void* const* regions_host, int world, int ra
     a.bc1 = (float)(1.0 - std::pow((double)beta1, (double)step));
     a.bc2_sqrt = (float)std::sqrt(1.0 - std::pow((double)beta2, (double)step));
     a.max_norm = max_norm; a.prescale = grad_prescale;
+    {
+        long long ms = kDefaultTimeoutMs;
+        if (const char* e = std::getenv("SEDB200_P2P_TIMEOUT_MS")) { const long long v = std::atoll(e); if (v > 0) ms = v; }
+        int dev = 0, khz = 0;
+        SED_CUDA_OK(cudaGetDevice(&dev));
+        SED_CUDA_OK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
+        a.timeout_cycles = ms * (long long)std::max(khz, 100000);          // clock64 ticks at the SM clock (kHz = cycles/ms)
+    }
     const long n4 = a.n >> 2;
     int grid = (int)std::max<long>(1, std::min<long>((n4 + kThreads - 1) / kThreads, sm_count()));
     grid = std::min(grid, 1024);

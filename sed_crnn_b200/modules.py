@@ -317,6 +317,32 @@ class FusedClipAdam(torch.optim.Optimizer):
         self.module = module
         super().__init__(list(module.parameters()), dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.max_norm = max_norm
+        if module._engine is not None:             # a NEW optimizer starts from zero moments, like torch.optim.Adam
+            module._engine.reset_optimizer()
+
+    # The moments live in the engine's flat buffers, not in Optimizer.state; checkpoints must still carry them
+    # (torch.optim.Adam's state round-trips through state_dict, and Lightning saves optimizer.state_dict()).
+    def state_dict(self):
+        eng = self.module.engine
+        sd = super().state_dict()
+        sd["sedb200_flat"] = {"exp_avg": eng.exp_avg.detach().cpu().clone(),
+                              "exp_avg_sq": eng.exp_avg_sq.detach().cpu().clone(), "step": int(eng.step_count),
+                              "layout": [(n, tuple(sh), int(off)) for n, sh, off in eng.specs]}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        flat = state_dict.pop("sedb200_flat", None)
+        super().load_state_dict(state_dict)
+        if flat is None:
+            raise KeyError("this optimizer state has no 'sedb200_flat' entry: it was not saved by FusedClipAdam")
+        eng = self.module.engine
+        if [(n, tuple(sh), int(off)) for n, sh, off in eng.specs] != [(n, tuple(sh), int(off)) for n, sh, off in flat["layout"]]:
+            raise ValueError("optimizer state was saved for a different parameter layout")
+        with torch.no_grad():
+            eng.exp_avg.copy_(flat["exp_avg"].to(eng.device))
+            eng.exp_avg_sq.copy_(flat["exp_avg_sq"].to(eng.device))
+        eng.step_count = int(flat["step"])
 
     @torch.no_grad()
     def step(self, closure=None):

@@ -140,8 +140,8 @@ def sharded_metric_counts(decisions_local: torch.Tensor, targets_local: torch.Te
 class _RawCudaArray:
     """`__cuda_array_interface__` view of library-owned device memory, so torch can wrap it without a copy."""
 
-    def __init__(self, ptr: int, n_floats: int):
-        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+    def __init__(self, ptr: int, n: int, typestr: str = "<f4"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
 class P2PGradExchange:
@@ -208,12 +208,31 @@ class P2PGradExchange:
         self.scratch = torch.zeros(int(self.L.sedb200_p2p_scratch_bytes()) // 4, dtype=torch.float32,
                                    device=self.device)
         self.seq = 0
+        # health: the region's sticky status word is copied to pinned host memory after every exchange (4 bytes, same
+        # stream, no synchronisation) and looked at before the next one -- a peer that never published makes the
+        # kernel abort (parameters untouched, gnorm = NaN) and the NEXT call raise, instead of training on garbage
+        self._status_dev = torch.as_tensor(
+            _RawCudaArray(self.own + int(self.L.sedb200_p2p_status_offset_bytes()), 1, "<i4"), device=self.device)
+        self._status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._status_evt = torch.cuda.Event()
+        self._status_pending = False
+
+    def check(self, wait: bool = False) -> None:
+        """Raise if an earlier exchange aborted.  wait=False looks only at copies that have already completed."""
+        if self._status_pending and (wait or self._status_evt.query()):
+            if wait:
+                self._status_evt.synchronize()
+            self._status_pending = False
+        if not self._status_pending and int(self._status_host[0]) != 0:
+            raise RuntimeError(f"P2PGradExchange (rank {self.rank}): a peer did not publish its gradients within the wait "
+                               "bound; the optimizer step was skipped (parameters untouched) -- the job must stop")
 
     def next_grad_buffer(self) -> torch.Tensor:
         """The buffer the NEXT exchange will read on every rank: backward must write its gradients here."""
         return self.grad_bufs[(self.seq + 1) & 1]
 
     def allreduce_clip_adam(self, params, exp_avg, exp_avg_sq, *, step, lr, betas, eps, weight_decay, clip, gnorm_out):
+        self.check()
         self.seq += 1
         with torch.cuda.device(self.device):
             self.check(self.L.sedb200_p2p_allreduce_clip_adam(
@@ -221,6 +240,9 @@ class P2PGradExchange:
                 exp_avg_sq.data_ptr(), self.reduced.data_ptr(), float(lr), float(betas[0]), float(betas[1]),
                 float(eps), float(weight_decay), float(clip), 1.0 / self.world, gnorm_out.data_ptr(),
                 self.scratch.data_ptr(), self.scratch.numel() * 4, torch.cuda.current_stream().cuda_stream))
+            self._status_host.copy_(self._status_dev, non_blocking=True)
+            self._status_evt.record()
+            self._status_pending = True
         return self.reduced
 
     def status(self) -> int:
@@ -239,6 +261,7 @@ class P2PGradExchange:
                 if r != self.rank and q is not None:
                     self.L.sedb200_p2p_region_close(q)
             self.grad_bufs = []
+            self._status_dev = None
             self.L.sedb200_p2p_region_free(self.own)
         self.own = None
 
@@ -259,6 +282,7 @@ class DevicePrefetcher:
         self.slot = 0
         self.pending = None
         self._deferred = False
+        self._released = [False, False]
         self._enqueue()
 
     def _enqueue(self):
@@ -268,11 +292,23 @@ class DevicePrefetcher:
             self.pending = None
             return
         k = self.slot
+        cur = torch.cuda.current_stream(self.device)
         if self.bufs[k] is None or self.bufs[k][0].shape != x.shape or self.bufs[k][1].shape != y.shape:
+            # a new buffer pair (first use, or the batch shape changed: a last partial batch).  The caching allocator
+            # may hand back a block with work still pending on the current stream, and whatever still reads the pair
+            # being replaced runs there too: order the copy after everything enqueued so far, and tell the allocator
+            # that the copy stream uses the new blocks
             self.bufs[k] = (torch.empty(x.shape, dtype=x.dtype, device=self.device),
                             torch.empty(y.shape, dtype=y.dtype, device=self.device))
-        else:
+            for b in self.bufs[k]:
+                b.record_stream(self.copy_stream)
+            self.copy_stream.wait_stream(cur)
+        elif self._released[k]:
             self.copy_stream.wait_event(self.freed[k])
+        else:
+            # the consumer never called release(k): the only safe order is "after everything it has enqueued so far"
+            self.copy_stream.wait_stream(cur)
+        self._released[k] = False
         with torch.cuda.stream(self.copy_stream):
             self.bufs[k][0].copy_(x, non_blocking=True)
             self.bufs[k][1].copy_(y, non_blocking=True)
@@ -301,6 +337,7 @@ class DevicePrefetcher:
     def release(self, k: int) -> None:
         """call after the work that reads buffer pair k has been enqueued on the current stream"""
         self.freed[k].record(torch.cuda.current_stream(self.device))
+        self._released[k] = True
         if self._deferred:
             self._deferred = False
             self._enqueue()

@@ -150,3 +150,69 @@ def test_device_prefetcher_orders_and_overlaps(mods):
     assert len(seen) == 5
     for (xh, yh), (xd, yd) in zip(host, seen):
         assert torch.equal(xd.cpu(), xh) and torch.equal(yd.cpu(), yh)
+
+
+def test_device_prefetcher_without_release_and_with_a_partial_last_batch(mods):
+    """(a) a consumer that never calls release() must not have its buffer overwritten while work that reads
+    it is still queued; (b) a shape change (last partial batch) allocates a new buffer that must be ordered after the
+    current stream."""
+    from sed_crnn_b200.parallel import DevicePrefetcher
+    g = torch.Generator().manual_seed(1)
+    host = [(torch.randn(b, 1, 40, 64, generator=g).pin_memory(), torch.rand(b, 8, 1, generator=g).pin_memory())
+            for b in (64, 64, 64, 64, 64, 17)]
+    sums = []
+    for x, y, k in DevicePrefetcher(iter(host)):              # no release(): the fallback ordering must hold
+        big = x.repeat(8, 1, 1, 1)
+        for _ in range(20):                                    # keep the current stream busy reading x
+            big = big * 1.0000001
+        sums.append((x.double().sum() + 0 * big.sum().double(), y.double().sum()))
+    assert len(sums) == 6
+    for (xh, yh), (sx, sy) in zip(host, sums):
+        assert abs(sx.item() - xh.double().sum().item()) < 1e-6 and abs(sy.item() - yh.double().sum().item()) < 1e-9
+
+
+def test_fused_clip_adam_state_round_trips_through_a_checkpoint(mods):
+    """optimizer.state_dict() must carry the Adam moments and the step (they live in the engine's flat
+    buffers); a resumed run must continue exactly like an uninterrupted one, and a new optimizer starts from zero."""
+    import io
+    _, sed, modules = mods
+    g = torch.Generator().manual_seed(3)
+    data = [(torch.randn(8, 1, 40, 64, generator=g).cuda(), (torch.rand(8, 8, 1, generator=g) < 0.2).float().cuda())
+            for _ in range(4)]
+    loss_fn = sed.BCEWithLogitsLoss()
+
+    def step(m, opt, xb, yb):
+        opt.zero_grad()
+        loss = loss_fn(m(xb), yb)
+        loss.backward()
+        opt.step()
+
+    torch.manual_seed(0)
+    a = sed.TimePooledCRNN(conv_channels=32, dropout=0.0).cuda()
+    oa = modules.FusedClipAdam(a, lr=1e-3, max_norm=1.0)
+    a.train()
+    for xb, yb in data[:2]:
+        step(a, oa, xb, yb)
+    buf = io.BytesIO()
+    torch.save({"model": a.state_dict(), "opt": oa.state_dict()}, buf)
+    sd = oa.state_dict()
+    assert sd["sedb200_flat"]["step"] == 2 and sd["sedb200_flat"]["exp_avg"].abs().max() > 0
+    for xb, yb in data[2:]:
+        step(a, oa, xb, yb)
+    # resume in a fresh module + optimizer
+    buf.seek(0)
+    ck = torch.load(buf, weights_only=False)
+    torch.manual_seed(123)
+    b = sed.TimePooledCRNN(conv_channels=32, dropout=0.0).cuda()
+    b.load_state_dict(ck["model"])
+    ob = modules.FusedClipAdam(b, lr=1e-3, max_norm=1.0)
+    b.train()
+    b(data[0][0])                                            # engine exists before the optimizer state arrives
+    assert not b.engine.exp_avg.any() and b.engine.step_count == 0
+    ob.load_state_dict(ck["opt"])
+    assert b.engine.step_count == 2
+    b.load_state_dict(ck["model"])                            # the probe forward above moved the BN running stats
+    for xb, yb in data[2:]:
+        step(b, ob, xb, yb)
+    for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb), ka

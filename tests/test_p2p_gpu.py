@@ -56,3 +56,38 @@ def test_p2p_rejects_bad_arguments(built_lib):
     rc = L.sedb200_p2p_allreduce_clip_adam(tab, 17, 0, 1024, 1, 1, None, None, None, None, 1e-3, .9, .999, 1e-8, 0.,
                                            1., 1., None, None, 0, None)
     assert rc == _lib.EINVAL
+
+
+def test_p2p_silent_peer_aborts_the_step_and_raises(built_lib, monkeypatch):
+    """on a flag-wait timeout the kernel used to continue and apply a stale peer buffer.  Now it raises the
+    sticky status word, leaves parameters and Adam state untouched, writes gnorm = NaN, and the next host call raises.
+    A silent peer is simulated on one GPU: a second exchange region nobody publishes into is listed as rank 1."""
+    import ctypes as C
+    from sed_crnn_b200 import _lib, parallel
+    monkeypatch.setenv("SEDB200_P2P_TIMEOUT_MS", "50")
+    L = _lib.lib()
+    n = 4096
+    xch = parallel.P2PGradExchange(n, torch.device("cuda"))
+    nbytes = int(L.sedb200_p2p_region_bytes(n))
+    fake, handle = C.c_void_p(), (C.c_ubyte * 64)()
+    _lib.check(L.sedb200_p2p_region_alloc(nbytes, C.byref(fake), handle))
+    xch.world, xch.table = 2, (C.c_void_p * 2)(xch.own, fake.value)
+    params = torch.randn(n, device="cuda")
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    p0 = params.clone()
+    xch.next_grad_buffer().fill_(0.5)
+    gn = torch.zeros(1, device="cuda")
+    xch.allreduce_clip_adam(params, m, v, step=1, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, clip=1.0,
+                            gnorm_out=gn)
+    torch.cuda.synchronize()
+    assert torch.equal(params, p0) and not m.any() and not v.any()
+    assert torch.isnan(gn).all()
+    assert xch.status() == 1
+    with pytest.raises(RuntimeError, match="did not publish"):
+        xch.check(wait=True)
+    with pytest.raises(RuntimeError, match="did not publish"):
+        xch.allreduce_clip_adam(params, m, v, step=2, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+                                clip=1.0, gnorm_out=gn)
+    xch.world = 1
+    xch.close()
+    L.sedb200_p2p_region_free(fake)
