@@ -215,11 +215,11 @@ def test_c5_shape_with_128_unit_gru(pkg):
 
 
 def test_full_size_c2_properties(pkg):
-    """BASELINE configs[1] at its full size (batch 128, T 256) -- too slow for the CPU oracle, so checked through
-    size-independent properties: (1) bit-exact run-to-run determinism of a training step, (2) eval-mode forward
-    of the full batch == the two half batches run separately (per-sample independence outside train-mode BN),
-    (3) the gradient of one step equals the mean of the two half-batch gradients when BatchNorm statistics are
-    frozen is not testable (train-mode BN), so instead: the loss goes down over a few steps on a fixed batch."""
+    """BASELINE configs[1] at its full size (batch 128, T 256), size-independent properties (the oracle comparison at
+    this size is tests/test_fullsize_gpu.py): (1) bit-exact run-to-run determinism of a training step with dropout
+    on, (2) eval-mode forward of the full batch == the two half batches run separately (per-sample independence
+    outside train-mode BN), (3) the loss goes down over a few steps on a fixed batch, (4) device metric counts ==
+    metrics.py on the same decisions."""
     config, engine = pkg
     cfg = config.C2
     g = torch.Generator().manual_seed(0)

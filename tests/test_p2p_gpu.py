@@ -1,7 +1,7 @@
 """Fused peer-memory all-reduce + clip + Adam kernel (sedb200_p2p_allreduce_clip_adam).
 
 Single GPU (world = 1: the exchange region is local, same kernel, same flag protocol) against the plain
-sedb200_clip_adam path; the two-rank NVLink run lives in tools/mgpu_check.py (needs `gpurun --gpus 2`)."""
+sedb200_clip_adam path; the two-rank NVLink run lives in tests/mgpu_check.py (needs `gpurun --gpus 2`)."""
 from dataclasses import replace
 
 import pytest
