@@ -706,7 +706,7 @@ def run_ours(args, rank, world, local_rank):
     value = frames_per_step / (ms_step * 1e-3)
     final_loss = loss.item()
     if eng.xch is not None:
-        eng.xch.check(wait=True)                             # a skipped exchange step must not produce a number
+        eng.xch.raise_if_failed(wait=True)                             # a skipped exchange step must not produce a number
 
     # ---- end-to-end through the public API with HOST batches: every step copies its pinned host batch to the
     #      device (parallel.DevicePrefetcher: batch i+1 is copied on a side stream while batch i trains, the way
@@ -747,7 +747,7 @@ def run_ours(args, rank, world, local_rank):
     e2e_nosync = e2e_run(False)
     clocks = sampler.stop(t_clk0, sampler.mark()) if rank == 0 else None
     if eng.xch is not None:
-        eng.xch.check(wait=True)
+        eng.xch.raise_if_failed(wait=True)
 
     # ---- BASELINE configs[3] as written, for this N: C1 shapes, FIXED global batch 1024 (strong scaling)
     fixed = None
@@ -774,7 +774,7 @@ def run_ours(args, rank, world, local_rank):
             if world > 1:
                 dist.all_reduce(t4, op=dist.ReduceOp.MAX)
             if eng4.xch is not None:
-                eng4.xch.check(wait=True)
+                eng4.xch.raise_if_failed(wait=True)
                 eng4.xch.close()
             ms4 = t4.item() / n4
             fixed = {"workload": workload_name("c4", world), "global_batch": 1024, "per_gpu_batch": Bf,

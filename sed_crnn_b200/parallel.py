@@ -217,7 +217,7 @@ class P2PGradExchange:
         self._status_evt = torch.cuda.Event()
         self._status_pending = False
 
-    def check(self, wait: bool = False) -> None:
+    def raise_if_failed(self, wait: bool = False) -> None:
         """Raise if an earlier exchange aborted.  wait=False looks only at copies that have already completed."""
         if self._status_pending and (wait or self._status_evt.query()):
             if wait:
@@ -232,7 +232,7 @@ class P2PGradExchange:
         return self.grad_bufs[(self.seq + 1) & 1]
 
     def allreduce_clip_adam(self, params, exp_avg, exp_avg_sq, *, step, lr, betas, eps, weight_decay, clip, gnorm_out):
-        self.check()
+        self.raise_if_failed()
         self.seq += 1
         with torch.cuda.device(self.device):
             self.check(self.L.sedb200_p2p_allreduce_clip_adam(

@@ -1,0 +1,176 @@
+"""Precision-budget study for the tensor-core conv contractions, on the CPU oracle.
+
+Every conv contraction of the oracle network (forward, data gradient, weight gradient of blocks >= 1) is replaced by
+an emulation of a candidate operand scheme -- operands rounded / split exactly as the kernel would hold them, products
+accumulated in fp32 -- and ONE training step (clip 1.0 + Adam) is compared with the unmodified fp32 oracle:
+probabilities after the step (gate 1e-3, target <= 5e-4 for a 2x margin), over several seeds.
+
+    python tests/manual/precision_study.py [--full] [--seeds 5] [--schemes s3,m2,...]
+
+Cost is in bf16-MMA units per k-step (fp8 kinds run at twice the bf16 rate, TF32 at half).
+"""
+import argparse
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from oracle import crnn_ref as R  # noqa: E402
+
+
+# ------------------------------------------------------------------ operand formats
+def pow2_scale(t, target):
+    amax = t.abs().max().clamp_min(1e-30)
+    return torch.exp2(torch.floor(torch.log2(target / amax)))
+
+
+def r_bf16(t):
+    return t.to(torch.bfloat16).float()
+
+
+def r_fp16(t, s):
+    return (t * s).to(torch.float16).float() / s
+
+
+def r_e4m3(t, s):
+    return (t * s).clamp(-448, 448).to(torch.float8_e4m3fn).float() / s
+
+
+def r_tf32(t):
+    # round-to-nearest-even on the low 13 mantissa bits
+    i = t.contiguous().view(torch.int32)
+    r = ((i >> 13) & 1) + 0x0FFF
+    return ((i + r) & ~0x1FFF).view(torch.float32)
+
+
+class Split:
+    """a tensor held as the planes a scheme needs"""
+
+    def __init__(self, t, scheme):
+        self.t = t
+        if scheme in ("s3", "b1", "b2a", "b2b"):
+            self.hi = r_bf16(t)
+            self.lo = r_bf16(t - self.hi)
+        elif scheme in ("f1", "f2a", "f2b", "f3", "m2", "m15a", "m15b"):
+            s = pow2_scale(t, 2.0 ** 14)
+            self.hi = r_fp16(t, s)
+            self.lo = r_fp16(t - self.hi, s * 2.0 ** 11)      # residual gets its own exponent window
+            s8 = pow2_scale(t, 256.0)
+            self.hi8 = r_e4m3(t, s8)
+            self.lo8 = r_e4m3(t - self.hi, pow2_scale(t - self.hi, 256.0))
+        elif scheme == "t1":
+            self.hi = r_tf32(t)
+        elif scheme == "bm2":                                   # bf16 hi*hi + e4m3 corrections
+            self.hi = r_bf16(t)
+            self.hi8 = r_e4m3(t, pow2_scale(t, 256.0))
+            self.lo8 = r_e4m3(t - self.hi, pow2_scale(t - self.hi, 256.0))
+
+
+COST = {"fp32": 0, "s3": 3, "b1": 1, "b2a": 2, "b2b": 2, "f1": 1, "f2a": 2, "f2b": 2, "f3": 3, "m2": 2, "m15a": 1.5,
+        "m15b": 1.5, "t1": 2, "bm2": 2}
+
+
+def contract(op, a, b, scheme):
+    """op(a_plane, b_plane) is bilinear; returns the sum of the scheme's terms.  a = activations / dY, b = weights
+    (forward, dgrad) or the second activation (wgrad)."""
+    if scheme == "fp32":
+        return op(a, b)
+    A, B = Split(a, scheme), Split(b, scheme)
+    if scheme in ("s3", "f3"):
+        return op(A.hi, B.hi) + op(A.hi, B.lo) + op(A.lo, B.hi)
+    if scheme in ("b1", "f1", "t1"):
+        return op(A.hi, B.hi)
+    if scheme in ("b2a", "f2a"):                                # full A, truncated B
+        return op(A.hi, B.hi) + op(A.lo, B.hi)
+    if scheme in ("b2b", "f2b"):                                # truncated A, full B
+        return op(A.hi, B.hi) + op(A.hi, B.lo)
+    if scheme in ("m2", "bm2"):                                 # 16-bit hi*hi + two fp8 correction terms
+        return op(A.hi, B.hi) + op(A.lo8, B.hi8) + op(A.hi8, B.lo8)
+    if scheme == "m15a":
+        return op(A.hi, B.hi) + op(A.lo8, B.hi8)
+    if scheme == "m15b":
+        return op(A.hi, B.hi) + op(A.hi8, B.lo8)
+    raise ValueError(scheme)
+
+
+class ConvEmu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, schemes):
+        ctx.save_for_backward(x, w)
+        ctx.schemes = schemes
+        y = contract(lambda a, b: F.conv2d(a, b, None, padding=1), x, w, schemes[0])
+        return y + bias.view(1, -1, 1, 1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        s = ctx.schemes
+        dx = contract(lambda a, b: torch.nn.grad.conv2d_input(x.shape, b, a, padding=1), dy, w, s[1])
+        dw = contract(lambda a, b: torch.nn.grad.conv2d_weight(b, w.shape, a, padding=1), dy, x, s[2])
+        return dx, dw, dy.sum((0, 2, 3)), None
+
+
+class EmuCRNN(R.RefCRNN):
+    schemes = ("fp32", "fp32", "fp32")
+
+    def forward(self, x, masks=None):
+        for i, (c, b, p) in enumerate(zip(self.convs, self.bns, self.pools)):
+            y = c(x) if i == 0 else ConvEmu.apply(x, c.weight, c.bias, self.schemes)
+            x = p(torch.relu(b(y)))
+        x = x.permute(0, 3, 1, 2) if self.mode == "fork" else x.permute(0, 2, 1, 3)
+        b_, t_, c_, f_ = x.shape
+        x = x.reshape(b_, t_, c_ * f_)
+        for g in self.grus:
+            x, _ = g(x)
+        for i, d in enumerate(self.denses):
+            x = d(x)
+            if i < len(self.denses) - 1:
+                x = torch.relu(x)
+        return x
+
+
+def one_step(model, x, y):
+    opt = R.make_adam(model, 1e-3, 1e-4)
+    R.train_step(model, opt, x, y, "bce", 1.0)
+    model.train()
+    with torch.no_grad():
+        return torch.sigmoid(model(x))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true", help="C2 at batch 128, T 256 (slow); default batch 16, T 64")
+    ap.add_argument("--preset", default="c2")
+    ap.add_argument("--seeds", type=int, default=3)
+    ap.add_argument("--schemes", default="s3,t1,f1,f2a,f2b,m2,bm2,m15a,m15b,b2a,b2b")
+    ap.add_argument("--mixed", default="", help="extra fwd/dgrad/wgrad triples, e.g. m2/m2/s3,f2a/f2a/s3")
+    args = ap.parse_args()
+    torch.set_num_threads(os.cpu_count() or 1)
+    rcfg = dict(R.PRESETS[args.preset])
+    B = 128
+    if not args.full:
+        rcfg["seq_len"] = 64
+        B = 16
+    triples = [(s, s, s) for s in args.schemes.split(",") if s]
+    triples += [tuple(t.split("/")) for t in args.mixed.split(",") if t]
+    print(f"{args.preset} batch {B} seq_len {rcfg['seq_len']}; max |dp| after one step vs the fp32 oracle, per seed")
+    for tr in triples:
+        errs = []
+        for seed in range(args.seeds):
+            torch.manual_seed(seed)
+            ref = R.RefCRNN(**rcfg)
+            emu = EmuCRNN(**rcfg)
+            emu.load_state_dict(ref.state_dict())
+            emu.schemes = tr
+            x, y = R.synth_batch(rcfg, B, seed=100 + seed)
+            p_ref = one_step(ref, x, y)
+            p_emu = one_step(emu, x, y)
+            errs.append((p_emu - p_ref).abs().max().item())
+        cost = sum(COST[s] for s in tr) / 3
+        print(f"{'/'.join(tr):18s} cost {cost:4.2f}  max {max(errs):.2e}  " + " ".join(f"{e:.1e}" for e in errs), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -84,7 +84,7 @@ def test_p2p_silent_peer_aborts_the_step_and_raises(built_lib, monkeypatch):
     assert torch.isnan(gn).all()
     assert xch.status() == 1
     with pytest.raises(RuntimeError, match="did not publish"):
-        xch.check(wait=True)
+        xch.raise_if_failed(wait=True)
     with pytest.raises(RuntimeError, match="did not publish"):
         xch.allreduce_clip_adam(params, m, v, step=2, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
                                 clip=1.0, gnorm_out=gn)
