@@ -19,6 +19,7 @@
 #include "conv0_lean.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace sedb200 {
 namespace {
@@ -398,7 +399,8 @@ bn_pool_bwd_sums_t_kernel(const float* __restrict__ y, const float* __restrict__
 __global__ void __launch_bounds__(256)
 bn_bwd_sums_act_kernel(const float* __restrict__ act, const __nv_bfloat16* __restrict__ act_hi,
                        const __nv_bfloat16* __restrict__ act_lo, const float* __restrict__ stat,
-                       const float* __restrict__ dA, unsigned n_pix, PoolGeom g, float* __restrict__ part) {
+                       const float* __restrict__ dA, unsigned n_pix, PoolGeom g, float* __restrict__ part,
+                       float* __restrict__ amax_part) {
     __shared__ float4 s1[256], s2[256];
     const int C4 = g.C >> 2, rows = 256 / C4;
     const int c4 = threadIdx.x % C4, prow = threadIdx.x / C4, c = c4 * 4;
@@ -415,6 +417,7 @@ bn_bwd_sums_act_kernel(const float* __restrict__ act, const __nv_bfloat16* __res
     const float inv_keep = g.drop_p > 0.0f ? 1.0f - g.drop_p : 1.0f;
     const unsigned Wo = (unsigned)g.Wo, H = (unsigned)g.H;
     float a[4] = {0, 0, 0, 0}, bsum[4] = {0, 0, 0, 0};
+    float amax = 0.0f;                                                 // max |dz| this thread saw (-> dy_scale_kernel)
     // two pixels per trip: all six loads are issued before the first use
     auto fetch = [&](unsigned pix, float (&av)[4], float (&gq)[4]) {
         const unsigned t = pix / Wo, wo = pix - t * Wo;
@@ -423,13 +426,8 @@ bn_bwd_sums_act_kernel(const float* __restrict__ act, const __nv_bfloat16* __res
         if (act) {
             load_dA(act + off, g.oC, av);
         } else {
-            const long i4 = (long)pix * C4 + c4;
-            const uint2 hb = __ldg(reinterpret_cast<const uint2*>(act_hi) + i4);
-            const uint2 lb = __ldg(reinterpret_cast<const uint2*>(act_lo) + i4);
-            const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(&hb);
-            const __nv_bfloat16* lp = reinterpret_cast<const __nv_bfloat16*>(&lb);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) av[q] = __bfloat162float(hp[q]) + __bfloat162float(lp[q]);
+            const float4 t4 = load_planes4(act_hi, act_lo, (long)pix * C4 + c4);
+            av[0] = t4.x; av[1] = t4.y; av[2] = t4.z; av[3] = t4.w;
         }
         load_dA(dA + off, g.oC, gq);
     };
@@ -441,6 +439,7 @@ bn_bwd_sums_act_kernel(const float* __restrict__ act, const __nv_bfloat16* __res
                 const float xh = fmaf(av[q] * inv_keep - shv[q], rs[q], -mis[q]);
                 a[q] += dz;
                 bsum[q] = fmaf(dz, xh, bsum[q]);
+                amax = fmaxf(amax, fabsf(dz));
             }
         }
     };
@@ -470,6 +469,49 @@ bn_bwd_sums_act_kernel(const float* __restrict__ act, const __nv_bfloat16* __res
         }
         *reinterpret_cast<float4*>(part + ((long)blockIdx.x * 2 + 0) * g.C + c) = ta;
         *reinterpret_cast<float4*>(part + ((long)blockIdx.x * 2 + 1) * g.C + c) = tb;
+    }
+    if (amax_part) {                                                   // max is order-independent: still deterministic
+        __shared__ float smax[8];
+        amax = warp_max(amax);
+        if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = amax;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float m = smax[0];
+            for (int w = 1; w < 8; ++w) m = fmaxf(m, smax[w]);
+            amax_part[blockIdx.x] = m;
+        }
+    }
+}
+
+// Power-of-two scale of the fp16 gradient plane of one conv block (crnn_block.cuh: store_dy4):
+//   |dy| = |sc| * |dz - mean(dz) - xhat * mean(dz*xhat)|  <=  max_c |sc_c| * (max|dz| + |m1_c| + 16 |m2_c|)
+// (|xhat| < 16 for any realistic batch; the conversion saturates if that is ever exceeded), placed at 2^13.
+// out[0] = scale, out[1] = 1 / scale.
+__global__ void __launch_bounds__(128)
+dy_scale_kernel(const float* __restrict__ amax_part, int nblk, const float* __restrict__ stat,
+                const float* __restrict__ bnsum, int C, float* __restrict__ out) {
+    __shared__ float sm[4], sb[4];
+    float m = 0.0f, b = 0.0f;
+    for (int i = threadIdx.x; i < nblk; i += 128) m = fmaxf(m, amax_part[i]);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = fmaxf(fmaxf(sm[0], sm[1]), fmaxf(sm[2], sm[3]));
+    for (int c = threadIdx.x; c < C; c += 128)
+        b = fmaxf(b, fabsf(stat[2 * C + c]) * (m + fabsf(bnsum[c]) + 16.0f * fabsf(bnsum[C + c])));
+    b = warp_max(b);
+    if ((threadIdx.x & 31) == 0) sb[threadIdx.x >> 5] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        b = fmaxf(fmaxf(sb[0], sb[1]), fmaxf(sb[2], sb[3]));
+        int e = 0;
+        float sc = 1.0f;
+        if (b > 0.0f && isfinite(b)) {
+            frexpf(b, &e);                                             // b = f * 2^e, f in [0.5, 1)
+            sc = exp2f((float)max(-100, min(100, 13 - e)));
+        }
+        out[0] = sc;
+        out[1] = 1.0f / sc;
     }
 }
 
@@ -536,8 +578,9 @@ bn_bwd_finalize_kernel(const float* __restrict__ part, int nblk, int C, long n,
 __global__ void __launch_bounds__(256)
 bn_pool_bwd_dy_kernel(const float* __restrict__ y, const float* __restrict__ stat, const float* __restrict__ dA,
                       const float* __restrict__ bnsum, long n_vec, PoolGeom g, float* __restrict__ dy,
-                      __nv_bfloat16* __restrict__ dy_hi, __nv_bfloat16* __restrict__ dy_lo) {
+                      __nv_bfloat16* __restrict__ dy_hi, const float* __restrict__ dy_scale) {
     const int C4 = g.C >> 2;
+    const float dscale = dy_scale ? __ldg(dy_scale) : 1.0f;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long)gridDim.x * blockDim.x) {
         const int c4 = (int)(i % C4);
         long t = i / C4;
@@ -565,7 +608,7 @@ bn_pool_bwd_dy_kernel(const float* __restrict__ y, const float* __restrict__ sta
             o.z = sc.z * ((wg.arg[2] == j && j < g.p ? wg.dz[2] : 0.0f) - k1.z - (v.z - mu.z) * is.z * k2.z);
             o.w = sc.w * ((wg.arg[3] == j && j < g.p ? wg.dz[3] : 0.0f) - k1.w - (v.w - mu.w) * is.w * k2.w);
             if (dy) *reinterpret_cast<float4*>(dy + (row + j) * g.C + c) = o;
-            if (dy_hi) store_planes4(dy_hi, dy_lo, ((row + j) * g.C + c) >> 2, o);
+            if (dy_hi) store_dy4(dy_hi, ((row + j) * g.C + c) >> 2, o, dscale);
         }
     }
 }
@@ -578,8 +621,9 @@ template <int P>
 __global__ void __launch_bounds__(256)
 bn_pool_bwd_dy_t_kernel(const float* __restrict__ y, const float* __restrict__ stat, const float* __restrict__ dA,
                         const float* __restrict__ bnsum, unsigned n_pix, PoolGeom g, float* __restrict__ dy,
-                        __nv_bfloat16* __restrict__ dy_hi, __nv_bfloat16* __restrict__ dy_lo) {
+                        __nv_bfloat16* __restrict__ dy_hi, const float* __restrict__ dy_scale) {
     const int C4 = g.C >> 2, rows = 256 / C4;
+    const float dscale = dy_scale ? __ldg(dy_scale) : 1.0f;
     const int c4 = threadIdx.x % C4, prow = threadIdx.x / C4, c = c4 * 4;
     const float4 sc = *reinterpret_cast<const float4*>(stat + 2 * g.C + c);
     const float4 sh = *reinterpret_cast<const float4*>(stat + 3 * g.C + c);
@@ -610,7 +654,7 @@ bn_pool_bwd_dy_t_kernel(const float* __restrict__ y, const float* __restrict__ s
             for (int q = 0; q < 4; ++q) o[q] = fmaf(-Bc[q], vv[q], (arg[q] == j ? scv[q] * dz[q] : 0.0f) - Ac[q]);
             const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
             if (dy) *reinterpret_cast<float4*>(dy + (row + j) * g.C + c) = o4;
-            if (dy_hi) store_planes4(dy_hi, dy_lo, ((row + j) * g.C + c) >> 2, o4);
+            if (dy_hi) store_dy4(dy_hi, ((row + j) * g.C + c) >> 2, o4, dscale);
         }
     }
 }
@@ -1135,7 +1179,7 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
             if (!P.conv_tc_all[i]) continue;
             for (int dg = 0; dg < 2; ++dg) {
                 const int rc2 = conv_tc_weight_planes(params + P.conv_w[i], P.cin[i], P.C, dg,
-                                                      reinterpret_cast<char*>(ws) + P.wpl[i][dg], ss);
+                                                      reinterpret_cast<char*>(ws) + P.wpl[i][dg], ss, kPlaneF16);
                 if (rc2) return rc2;
             }
         }
@@ -1216,7 +1260,7 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
             const char* ap = reinterpret_cast<const char*>(ws) + P.actp[i - 1];
             rc = conv_tc_planes_w(ap, ap + P.act_plane_bytes[i - 1], reinterpret_cast<const char*>(ws) + P.wpl[i][0],
                                   params + P.conv_b[i], y, training ? wsf(ws, P.part) : nullptr, batch, P.H, P.win[i],
-                                  P.cin[i], P.C, 0, st);
+                                  P.cin[i], P.C, 0, st, 3, kPlaneF16, nullptr);
             if (rc) return rc;
             nblk = conv_tc_stat_tiles(batch, P.H, P.win[i]);
         } else if (i > 0 && d->tensor_cores && conv_tc_supported(P.H, P.win[i], P.cin[i], P.C)) {
@@ -1583,6 +1627,7 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         const int rows = 256 / (P.C / 4);
         const int nblk = (int)std::min<long>((n_pix_out + rows - 1) / rows, 148L * 16);
         int sblk = nblk;                                          // blocks (= partials) of the sums pass
+        bool have_amax = false;                                   // the sums pass left max |dz| per block (fp16 dy plane)
 { char _nm[40]; snprintf(_nm, sizeof _nm, "pool%d.bwd_sums", i); SED_PROF(_nm, st);
         const bool idx32 = n_pix_out < (1L << 31);
         const bool planes_out = (i + 1 < P.n_conv) && P.conv_tc_all[i + 1];      // what the forward pass stored
@@ -1595,7 +1640,8 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
                 planes_out ? nullptr : wsf(ws, P.act[i]),
                 planes_out ? reinterpret_cast<const __nv_bfloat16*>(ap) : nullptr,
                 planes_out ? reinterpret_cast<const __nv_bfloat16*>(ap + P.act_plane_bytes[i]) : nullptr, stat, dA,
-                (unsigned)n_pix_out, g, part);
+                (unsigned)n_pix_out, g, part, P.conv_tc_all[i] ? wsf(ws, P.dys) + 8 : nullptr);
+            have_amax = P.conv_tc_all[i];
         } else if (g.p == 5 && idx32) bn_pool_bwd_sums_t_kernel<5><<<nblk, 256, 0, st>>>(y, stat, dA, n_pix_out, g, part);
         else if (g.p == 2 && idx32) bn_pool_bwd_sums_t_kernel<2><<<nblk, 256, 0, st>>>(y, stat, dA, n_pix_out, g, part);
         else bn_pool_bwd_sums_kernel<<<nblk, 256, 0, st>>>(y, stat, dA, n_pix_out, g, part);
@@ -1633,17 +1679,27 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         }
         float* dy = wsf(ws, P.dy);
         const long n_vec = n_pix_out * (P.C / 4);
+        // plane-native block: dy exists only as ONE fp16 plane of dy * scale (crnn_block.cuh: store_dy4); the scale
+        // {s, 1/s} lives in the workspace and is read by the kernels that produce / consume the plane
         __nv_bfloat16* dyh = P.conv_tc_all[i] ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(ws) + P.dyp) : nullptr;
-        __nv_bfloat16* dyl = P.conv_tc_all[i] ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(ws) + P.dyp + P.dy_plane_bytes) : nullptr;
+        float* dys = wsf(ws, P.dys);
+        if (P.conv_tc_all[i]) {
+            if (have_amax) {
+                dy_scale_kernel<<<1, 128, 0, st>>>(dys + 8, sblk, stat, bnsum, P.C, dys);
+                SED_POST_LAUNCH();
+            } else {
+                return fail(SEDB200_ESHAPE, "crnn_backward: plane-native block %d without the activation-sums pass", i);
+            }
+        }
 { char _nm[40]; snprintf(_nm, sizeof _nm, "pool%d.bwd_dy", i); SED_PROF(_nm, st);
         float* dyf = P.conv_tc_all[i] ? nullptr : dy;
         const bool exact_t = g.W == g.Wo * g.p && (g.p == 5 || g.p == 2) && 256 % (P.C / 4) == 0 && n_pix_out < (1L << 31);
         if (exact_t && g.p == 5)
-            bn_pool_bwd_dy_t_kernel<5><<<nblk, 256, 0, st>>>(y, stat, dA, bnsum, (unsigned)n_pix_out, g, dyf, dyh, dyl);
+            bn_pool_bwd_dy_t_kernel<5><<<nblk, 256, 0, st>>>(y, stat, dA, bnsum, (unsigned)n_pix_out, g, dyf, dyh, dyh ? dys : nullptr);
         else if (exact_t)
-            bn_pool_bwd_dy_t_kernel<2><<<nblk, 256, 0, st>>>(y, stat, dA, bnsum, (unsigned)n_pix_out, g, dyf, dyh, dyl);
+            bn_pool_bwd_dy_t_kernel<2><<<nblk, 256, 0, st>>>(y, stat, dA, bnsum, (unsigned)n_pix_out, g, dyf, dyh, dyh ? dys : nullptr);
         else
-            bn_pool_bwd_dy_kernel<<<ew_blocks(n_vec), 256, 0, st>>>(y, stat, dA, bnsum, n_vec, g, dyf, dyh, dyl);
+            bn_pool_bwd_dy_kernel<<<ew_blocks(n_vec), 256, 0, st>>>(y, stat, dA, bnsum, n_vec, g, dyf, dyh, dyh ? dys : nullptr);
         SED_POST_LAUNCH();
 }
 
@@ -1660,8 +1716,8 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         if (P.conv_tc_all[i]) {
             const char* xp = reinterpret_cast<const char*>(ws) + P.actp[i - 1];
             float* wpart = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + P.tc + conv_tc_weight_scratch_bytes(P.cin[i], P.C));
-            rc = wgrad_tc_planes(dyh, dyl, xp, xp + P.act_plane_bytes[i - 1], grads + P.conv_w[i], batch, P.H, P.win[i],
-                                 P.cin[i], P.C, wpart, st);
+            rc = wgrad_tc_planes(dyh, nullptr, xp, nullptr, grads + P.conv_w[i], batch, P.H, P.win[i], P.cin[i], P.C, wpart,
+                                 st, 1, kPlaneF16, dys + 1);
             if (rc) return rc;
         } else if (i > 0 && d->tensor_cores && wgrad_tc_supported(P.H, P.win[i], P.cin[i], P.C)) {
             rc = wgrad_tc(dy, in, grads + P.conv_w[i], batch, P.H, P.win[i], P.cin[i], P.C, wsf(ws, P.tc), P.tc_bytes, st);
@@ -1684,8 +1740,8 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
             float* dprev = wsf(ws, P.dact[i & 1]);
 { char _nm[40]; snprintf(_nm, sizeof _nm, "conv%d.dgrad", i); SED_PROF(_nm, st);
             if (P.conv_tc_all[i])
-                rc = conv_tc_planes_w(dyh, dyl, reinterpret_cast<const char*>(ws) + P.wpl[i][1], nullptr, dprev, nullptr,
-                                      batch, P.H, P.win[i], P.cin[i], P.C, 1, st);     // planes built by the forward pass
+                rc = conv_tc_planes_w(dyh, nullptr, reinterpret_cast<const char*>(ws) + P.wpl[i][1], nullptr, dprev, nullptr,
+                                      batch, P.H, P.win[i], P.cin[i], P.C, 1, st, 1, kPlaneF16, dys + 1);   // weight planes built by the forward pass
             else if (d->tensor_cores && conv_tc_supported(P.H, P.win[i], P.C, P.cin[i]))
                 rc = conv_tc_forward(dy, params + P.conv_w[i], nullptr, dprev, batch, P.H, P.win[i], P.cin[i], P.C, 1,
                                      wsf(ws, P.tc), P.tc_bytes, st);

@@ -2,6 +2,7 @@
 // dropout generator, the bf16 hi / lo plane store, the geometry of a BN + ReLU + max-pool block.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace sedb200 {
@@ -33,18 +34,39 @@ __host__ __device__ inline unsigned long long block_seed(unsigned long long seed
     return seed * 0x2545F4914F6CDD1Dull + (unsigned long long)(block + 1) * 0xD6E8FEB86659FD93ull;
 }
 
-// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): the tensor-core operand format (tc_conv.cu)
+// Activation planes of the plane-native conv blocks: x = hi + lo with hi = fp16(x), lo = fp16(x - hi) -- 22 significand
+// bits for the O(1) values BatchNorm produces (residuals below 2^-14 go subnormal: absolute precision 2^-24).  The
+// conversions saturate at the fp16 range instead of producing inf.  Storage type of all 16-bit planes is
+// `__nv_bfloat16` (just 2 bytes); what the bytes mean is the producer's / consumer's contract.
+__device__ __forceinline__ __half sat_half(float x) { return __float2half_rn(fminf(fmaxf(x, -65504.0f), 65504.0f)); }
 __device__ __forceinline__ void store_planes4(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long i4,
                                               const float4 v) {
-    __nv_bfloat16 h[4], l[4];
+    __half h[4], l[4];
     const float f[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        h[q] = __float2bfloat16_rn(f[q]);
-        l[q] = __float2bfloat16_rn(f[q] - __bfloat162float(h[q]));
+        h[q] = sat_half(f[q]);
+        l[q] = sat_half(f[q] - __half2float(h[q]));
     }
     reinterpret_cast<uint2*>(hi)[i4] = *reinterpret_cast<uint2*>(h);
     reinterpret_cast<uint2*>(lo)[i4] = *reinterpret_cast<uint2*>(l);
+}
+__device__ __forceinline__ float4 load_planes4(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                               long i4) {
+    const uint2 hb = __ldg(reinterpret_cast<const uint2*>(hi) + i4);
+    const uint2 lb = __ldg(reinterpret_cast<const uint2*>(lo) + i4);
+    const __half* hp = reinterpret_cast<const __half*>(&hb);
+    const __half* lp = reinterpret_cast<const __half*>(&lb);
+    return make_float4(__half2float(hp[0]) + __half2float(lp[0]), __half2float(hp[1]) + __half2float(lp[1]),
+                       __half2float(hp[2]) + __half2float(lp[2]), __half2float(hp[3]) + __half2float(lp[3]));
+}
+// Gradient plane of a conv output: ONE fp16 plane of dy * scale, scale a power of two chosen per tensor from a bound
+// on |dy| (dy_scale_kernel) so that the largest elements sit near 2^13; the contractions that consume it multiply
+// their result by 1 / scale.  (The data / weight gradient contractions run single-pass: measured on the oracle,
+// fp16-rounded gradient operands change the probabilities after a step by < 1e-4, the forward needs the split.)
+__device__ __forceinline__ void store_dy4(__nv_bfloat16* __restrict__ hi, long i4, const float4 v, float scale) {
+    __half h[4] = {sat_half(v.x * scale), sat_half(v.y * scale), sat_half(v.z * scale), sat_half(v.w * scale)};
+    reinterpret_cast<uint2*>(hi)[i4] = *reinterpret_cast<uint2*>(h);
 }
 
 struct PoolGeom {

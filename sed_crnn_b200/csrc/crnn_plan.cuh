@@ -31,6 +31,7 @@ struct Plan {
     size_t hp_plane_bytes[SEDB200_MAX_GRU], dg_plane_bytes;
     size_t hid[SEDB200_MAX_DENSE];
     size_t dy, dact[2], dseq[2], dgi, dgh, dhid[2], part, bnsum, tc;
+    size_t dys = 0;                           // fp16 gradient-plane scale {s, 1/s} (+ the max |dz| partials behind it)
     // lean block 0 (crnn.cu, "first conv block without its output tensor"): per-window winner bytes written by the
     // fused forward kernel, and the K x (K+1) patch Gram matrix (doubles) both BatchNorm passes are derived from
     size_t arg0 = 0, gram = 0;

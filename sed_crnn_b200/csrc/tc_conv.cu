@@ -21,6 +21,7 @@
 //   warps 4-7 = epilogue (tcgen05.ld -> +bias -> fp32 NHWC store).  Two TMEM accumulator buffers so the
 //   epilogue of tile i overlaps the MMAs of tile i+1; 3-stage smem ring (64 KB per stage).
 //   dgrad is the same kernel on dY with the weights flipped and transposed beforehand.
+#include <cuda_fp16.h>
 #include "tc_umma.cuh"
 #include "tc_conv.cuh"
 
@@ -58,7 +59,8 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 namespace {
 using namespace umma;
 
-constexpr int kStages = 3;
+constexpr int kStages = 3;                                       // 3-term stages (64 KB each)
+constexpr int kMaxStages = 6;                                    // 1-term stages are half the size: twice as many fit
 constexpr int kTileM = 128, kTileN = 128, kBlockK = 64;
 constexpr int kTileBytes = kTileM * kBlockK * 2;                 // 16 KB: one bf16 operand tile
 constexpr int kStageBytes = 4 * kTileBytes;                      // A_hi, A_lo, B_hi, B_lo
@@ -70,6 +72,9 @@ constexpr uint32_t kTmemCols = 256;                              // two 128-colu
 
 struct ConvTcParams {
     int B, H, W, Ht, tiles_per_img, n_tiles_n, total_tiles, kchunks, n_total;
+    int terms;               // 3: A_hi*B_hi + A_hi*B_lo + A_lo*B_hi (fp32-grade);  1: hi planes only (gradient contractions)
+    uint32_t idesc;          // instruction descriptor (operand formats: bf16 or fp16 planes)
+    const float* out_scale;  // null, or a device scalar every accumulator is multiplied by (fp16 gradient planes)
     float* out;              // [B*H*W][out_ld] fp32
     const float* bias;       // [n_total] or null
     long out_ld;
@@ -83,11 +88,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-    uint64_t* full = bars;                    // [kStages]  TMA -> MMA
-    uint64_t* empty = bars + kStages;         // [kStages]  MMA -> TMA
-    uint64_t* tfull = bars + 2 * kStages;     // [2]        MMA -> epilogue
-    uint64_t* tempty = bars + 2 * kStages + 2;// [2]        epilogue -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    uint64_t* full = bars;                       // [kMaxStages]  TMA -> MMA
+    uint64_t* empty = bars + kMaxStages;         // [kMaxStages]  MMA -> TMA
+    uint64_t* tfull = bars + 2 * kMaxStages;     // [2]           MMA -> epilogue
+    uint64_t* tempty = bars + 2 * kMaxStages + 2;// [2]           epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+    const int n_stages = p.terms == 1 ? kMaxStages : kStages;
+    const int stage_bytes = p.terms == 1 ? kStageBytes / 2 : kStageBytes;
     float* stat_s = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);     // [4 warps][2][128]
     float* epi_stage = stat_s + 1024;                                                 // [4 warps][32][kEpiPitch]
 
@@ -96,7 +103,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        for (int i = 0; i < kMaxStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
         fence_barrier_init();
     }
@@ -117,18 +124,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 const int tap = kb / p.kchunks, c0 = (kb % p.kchunks) * kBlockK;
                 const int r = tap / 3, s = tap - 3 * r;
                 mbar_wait(empty + stage, phase ^ 1);
-                unsigned char* st = smem + stage * kStageBytes;
-                mbar_expect_tx(full + stage, kStageBytes);
-                tma_load_4d(st, &tmA_hi, full + stage, c0, s - 1, h0 + r - 1, b);
-                tma_load_4d(st + kTileBytes, &tmA_lo, full + stage, c0, s - 1, h0 + r - 1, b);
-                tma_load_2d(st + 2 * kTileBytes, &tmB_hi, full + stage, c0, tap * p.n_total + nt * kTileN);
-                tma_load_2d(st + 3 * kTileBytes, &tmB_lo, full + stage, c0, tap * p.n_total + nt * kTileN);
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                unsigned char* st = smem + stage * stage_bytes;
+                mbar_expect_tx(full + stage, stage_bytes);
+                if (p.terms == 1) {                            // stage = {A_hi, B_hi}
+                    tma_load_4d(st, &tmA_hi, full + stage, c0, s - 1, h0 + r - 1, b);
+                    tma_load_2d(st + kTileBytes, &tmB_hi, full + stage, c0, tap * p.n_total + nt * kTileN);
+                } else {                                       // stage = {A_hi, A_lo, B_hi, B_lo}
+                    tma_load_4d(st, &tmA_hi, full + stage, c0, s - 1, h0 + r - 1, b);
+                    tma_load_4d(st + kTileBytes, &tmA_lo, full + stage, c0, s - 1, h0 + r - 1, b);
+                    tma_load_2d(st + 2 * kTileBytes, &tmB_hi, full + stage, c0, tap * p.n_total + nt * kTileN);
+                    tma_load_2d(st + 3 * kTileBytes, &tmB_lo, full + stage, c0, tap * p.n_total + nt * kTileN);
+                }
+                if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1 && lane == 0) {
         // ================= MMA issuer =================
-        constexpr uint32_t idesc = idesc_bf16(kTileM, kTileN, 0, 0);
+        const uint32_t idesc = p.idesc;
         int stage = 0; uint32_t phase = 0;
         int buf = 0; uint32_t bphase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -138,18 +150,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             for (int kb = 0; kb < n_kb; ++kb) {
                 mbar_wait(full + stage, phase);
                 tc_fence_after();
-                const uint32_t a_hi = smem_u32(smem + stage * kStageBytes);
-                const uint32_t a_lo = a_hi + kTileBytes, b_hi = a_hi + 2 * kTileBytes, b_lo = a_hi + 3 * kTileBytes;
+                const uint32_t a_hi = smem_u32(smem + stage * stage_bytes);
+                if (p.terms == 1) {
+                    const uint32_t b_hi = a_hi + kTileBytes;
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
-                    const uint64_t dah = smem_desc_sw128(a_hi + k * 32, 16, 1024), dal = smem_desc_sw128(a_lo + k * 32, 16, 1024);
-                    const uint64_t dbh = smem_desc_sw128(b_hi + k * 32, 16, 1024), dbl = smem_desc_sw128(b_lo + k * 32, 16, 1024);
-                    mma_bf16(d, dah, dbh, idesc, (kb | k) != 0);
-                    mma_bf16(d, dah, dbl, idesc, 1);
-                    mma_bf16(d, dal, dbh, idesc, 1);
+                    for (int k = 0; k < kBlockK / 16; ++k)
+                        mma_bf16(d, smem_desc_sw128(a_hi + k * 32, 16, 1024), smem_desc_sw128(b_hi + k * 32, 16, 1024), idesc,
+                                 (kb | k) != 0);
+                } else {
+                    const uint32_t a_lo = a_hi + kTileBytes, b_hi = a_hi + 2 * kTileBytes, b_lo = a_hi + 3 * kTileBytes;
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        const uint64_t dah = smem_desc_sw128(a_hi + k * 32, 16, 1024), dal = smem_desc_sw128(a_lo + k * 32, 16, 1024);
+                        const uint64_t dbh = smem_desc_sw128(b_hi + k * 32, 16, 1024), dbl = smem_desc_sw128(b_lo + k * 32, 16, 1024);
+                        mma_bf16(d, dah, dbh, idesc, (kb | k) != 0);
+                        mma_bf16(d, dah, dbl, idesc, 1);
+                        mma_bf16(d, dal, dbh, idesc, 1);
+                    }
                 }
                 mma_commit(empty + stage);                 // smem slot reusable once these MMAs retire
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
             mma_commit(tfull + buf);                       // accumulator complete
             if (++buf == 2) { buf = 0; bphase ^= 1; }
@@ -158,6 +178,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         // ================= epilogue (4 warps, one TMEM sub-partition each) =================
         const int q = warp - 4;                            // == warp % 4
         int buf = 0; uint32_t bphase = 0;
+        const float osc = p.out_scale ? __ldg(p.out_scale) : 1.0f;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
             const int b = mt / p.tiles_per_img, h0 = (mt % p.tiles_per_img) * p.Ht;
@@ -182,7 +203,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
                 for (int r = 0; r < 32; r += 4) {
                     float4 o = *reinterpret_cast<const float4*>(stg + (r + sub_r) * kEpiPitch + sub_c);
-                    o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                    o.x = fmaf(o.x, osc, bb.x); o.y = fmaf(o.y, osc, bb.y); o.z = fmaf(o.z, osc, bb.z); o.w = fmaf(o.w, osc, bb.w);
                     if ((h0 + (q * 32 + r + sub_r) / p.W) < p.H)
                         *reinterpret_cast<float4*>(dst0 + (long)(r + sub_r) * p.out_ld + cc * 32 + sub_c) = o;
                 }
@@ -192,7 +213,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
                     for (int r = 0; r < 32; ++r) {
-                        const float x = stg[r * kEpiPitch + lane] + bl;
+                        const float x = fmaf(stg[r * kEpiPitch + lane], osc, bl);
                         if ((h0 + (q * 32 + r) / p.W) < p.H) { s1 += x; s2 = fmaf(x, x, s2); }
                     }
                     stat_s[(q * 2 + 0) * 128 + cc * 32 + lane] = s1;
@@ -246,7 +267,7 @@ split_planes_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
 //   fwd  : N = Cout, K = Cin, plane[tap][co][ci] = w[co][ci][tap]
 //   dgrad: N = Cin,  K = Cout, plane[tap][ci][co] = w[co][ci][8 - tap]      (flipped taps)
 __global__ void __launch_bounds__(256)
-weight_planes_kernel(const float* __restrict__ w, int Cout, int Cin, int dgrad, __nv_bfloat16* __restrict__ hi,
+weight_planes_kernel(const float* __restrict__ w, int Cout, int Cin, int dgrad, int fmt, __nv_bfloat16* __restrict__ hi,
                      __nv_bfloat16* __restrict__ lo) {
     const long n = 9L * Cout * Cin;
     const int N = dgrad ? Cin : Cout, K = dgrad ? Cout : Cin;
@@ -255,7 +276,15 @@ weight_planes_kernel(const float* __restrict__ w, int Cout, int Cin, int dgrad, 
         const int nn = (int)((i / K) % N);
         const int tap = (int)(i / ((long)K * N));
         const int co = dgrad ? k : nn, ci = dgrad ? nn : k, t = dgrad ? 8 - tap : tap;
-        split_bf16(__ldg(w + ((long)co * Cin + ci) * 9 + t), hi[i], lo[i]);
+        const float x = __ldg(w + ((long)co * Cin + ci) * 9 + t);
+        if (fmt == kPlaneF16) {                               // fp16 hi / lo (saturating), same storage
+            const __half h = __float2half_rn(fminf(fmaxf(x, -65504.0f), 65504.0f));
+            const __half l = __float2half_rn(fminf(fmaxf(x - __half2float(h), -65504.0f), 65504.0f));
+            reinterpret_cast<__half*>(hi)[i] = h;
+            reinterpret_cast<__half*>(lo)[i] = l;
+        } else {
+            split_bf16(x, hi[i], lo[i]);
+        }
     }
 }
 
@@ -278,7 +307,8 @@ constexpr int kWgSmemBytes = kStages * kWgStageBytes + 1024 + 256;
 constexpr uint32_t kWgTmemCols = 512;
 
 struct WgradTcParams {
-    int B, H, W, Hk, hblocks_per_img, total_kblocks, n_mt, n_nt, slices;
+    int B, H, W, Hk, hblocks_per_img, total_kblocks, n_mt, n_nt, slices, terms;
+    uint32_t idesc;
     float* part;             // [slices][9][Cout][Cin]
     int Cout, Cin;
 };
@@ -291,16 +321,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kWgStageBytes);
     uint64_t* full = bars;
-    uint64_t* empty = bars + kStages;
-    uint64_t* tfull = bars + 2 * kStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+    uint64_t* empty = bars + kMaxStages;
+    uint64_t* tfull = bars + 2 * kMaxStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
+    const int n_stages = p.terms == 1 ? kMaxStages : kStages;
+    const int stage_bytes = p.terms == 1 ? kWgStageBytes / 2 : kWgStageBytes;
+    // 1-term stage: {dY hi: 2 halves} + 3 x {In hi: 2 halves}; 3-term stage: each of those followed by its lo boxes
+    const int a_bytes = p.terms == 1 ? kWgABytes / 2 : kWgABytes, b_bytes = p.terms == 1 ? kWgBBytes / 2 : kWgBBytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmY_hi); prefetch_tmap(&tmY_lo); prefetch_tmap(&tmX_hi); prefetch_tmap(&tmX_lo);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        for (int i = 0; i < kMaxStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
         mbar_init(tfull, 1);
         fence_barrier_init();
     }
@@ -323,43 +357,45 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
         for (int kb = kb0; kb < kb1; ++kb) {
             const int b = kb / p.hblocks_per_img, h0 = (kb % p.hblocks_per_img) * p.Hk;
             mbar_wait(empty + stage, phase ^ 1);
-            unsigned char* st = smem + stage * kWgStageBytes;
-            mbar_expect_tx(full + stage, kWgStageBytes);
+            unsigned char* st = smem + stage * stage_bytes;
+            mbar_expect_tx(full + stage, stage_bytes);
             for (int half = 0; half < 2; ++half) {
                 tma_load_4d(st + half * kWgBox, &tmY_hi, full + stage, mt * 128 + half * 64, 0, h0, b);
-                tma_load_4d(st + (2 + half) * kWgBox, &tmY_lo, full + stage, mt * 128 + half * 64, 0, h0, b);
+                if (p.terms != 1) tma_load_4d(st + (2 + half) * kWgBox, &tmY_lo, full + stage, mt * 128 + half * 64, 0, h0, b);
             }
             for (int s = 0; s < 3; ++s) {
-                unsigned char* bt = st + kWgABytes + s * kWgBBytes;
+                unsigned char* bt = st + a_bytes + s * b_bytes;
                 for (int half = 0; half < 2; ++half) {
                     tma_load_4d(bt + half * kWgBox, &tmX_hi, full + stage, nt * 128 + half * 64, s - 1, h0 + r - 1, b);
-                    tma_load_4d(bt + (2 + half) * kWgBox, &tmX_lo, full + stage, nt * 128 + half * 64, s - 1, h0 + r - 1, b);
+                    if (p.terms != 1) tma_load_4d(bt + (2 + half) * kWgBox, &tmX_lo, full + stage, nt * 128 + half * 64, s - 1, h0 + r - 1, b);
                 }
             }
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1 && lane == 0) {
-        constexpr uint32_t idesc = idesc_bf16(128, 128, 1, 1);      // both operands MN-major
+        const uint32_t idesc = p.idesc;                             // both operands MN-major
         int stage = 0; uint32_t phase = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(full + stage, phase);
             tc_fence_after();
-            const uint32_t a_hi = smem_u32(smem + stage * kWgStageBytes), a_lo = a_hi + 2 * kWgBox;
+            const uint32_t a_hi = smem_u32(smem + stage * stage_bytes), a_lo = a_hi + 2 * kWgBox;
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
-                const uint32_t b_hi = a_hi + kWgABytes + s * kWgBBytes, b_lo = b_hi + 2 * kWgBox;
+                const uint32_t b_hi = a_hi + a_bytes + s * b_bytes, b_lo = b_hi + 2 * kWgBox;
                 const uint32_t d = tmem_base + s * 128;
 #pragma unroll
                 for (int k = 0; k < kWgKp / 16; ++k) {
-                    const uint64_t dah = smem_desc_sw128(a_hi + k * 2048, kWgBox, 1024), dal = smem_desc_sw128(a_lo + k * 2048, kWgBox, 1024);
-                    const uint64_t dbh = smem_desc_sw128(b_hi + k * 2048, kWgBox, 1024), dbl = smem_desc_sw128(b_lo + k * 2048, kWgBox, 1024);
+                    const uint64_t dah = smem_desc_sw128(a_hi + k * 2048, kWgBox, 1024), dbh = smem_desc_sw128(b_hi + k * 2048, kWgBox, 1024);
                     mma_bf16(d, dah, dbh, idesc, (kb != kb0 || k != 0));
-                    mma_bf16(d, dah, dbl, idesc, 1);
-                    mma_bf16(d, dal, dbh, idesc, 1);
+                    if (p.terms != 1) {
+                        const uint64_t dal = smem_desc_sw128(a_lo + k * 2048, kWgBox, 1024), dbl = smem_desc_sw128(b_lo + k * 2048, kWgBox, 1024);
+                        mma_bf16(d, dah, dbl, idesc, 1);
+                        mma_bf16(d, dal, dbh, idesc, 1);
+                    }
                 }
             }
             mma_commit(empty + stage);
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
         mma_commit(tfull);
     } else if (warp >= 4) {
@@ -396,13 +432,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
 
 // dW[co][ci][tap] = sum_slice part[slice][tap][co][ci]
 __global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const float* __restrict__ part, int slices, int Cout, int Cin, float* __restrict__ dw) {
+wgrad_reduce_kernel(const float* __restrict__ part, int slices, int Cout, int Cin, float* __restrict__ dw,
+                    const float* __restrict__ out_scale) {
     const long n = 9L * Cout * Cin;
+    const float osc = out_scale ? __ldg(out_scale) : 1.0f;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
         const int ci = (int)(i % Cin);
         const int co = (int)((i / Cin) % Cout);
         const int tap = (int)(i / ((long)Cin * Cout));
-        dw[((long)co * Cin + ci) * 9 + tap] = ordered_sum<8, float>(part + i, n, slices);
+        dw[((long)co * Cin + ci) * 9 + tap] = ordered_sum<8, float>(part + i, n, slices) * osc;
     }
 }
 
@@ -422,11 +460,11 @@ size_t conv_tc_weight_scratch_bytes(int Cin, int Cout) { return 2 * (((size_t)9 
 
 // B-operand planes of a conv weight (forward or flipped / transposed for the data gradient) into `wplanes`
 // (conv_tc_weight_scratch_bytes); they stay valid until the weight changes
-int conv_tc_weight_planes(const float* w, int Cin, int Cout, int dgrad, void* wplanes, cudaStream_t st) {
+int conv_tc_weight_planes(const float* w, int Cin, int Cout, int dgrad, void* wplanes, cudaStream_t st, int fmt) {
     const size_t wp = ((size_t)9 * Cout * Cin * 2 + 1023) & ~(size_t)1023;
     __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(wplanes);
     __nv_bfloat16* w_lo = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(wplanes) + wp);
-    weight_planes_kernel<<<(int)std::min<long>((9L * Cout * Cin + 255) / 256, 1184), 256, 0, st>>>(w, Cout, Cin, dgrad, w_hi, w_lo);
+    weight_planes_kernel<<<(int)std::min<long>((9L * Cout * Cin + 255) / 256, 1184), 256, 0, st>>>(w, Cout, Cin, dgrad, fmt, w_hi, w_lo);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }
@@ -441,8 +479,11 @@ int conv_tc_planes(const void* a_hi, const void* a_lo, const float* w, const flo
 
 // same with the weight planes already built (conv_tc_weight_planes)
 int conv_tc_planes_w(const void* a_hi, const void* a_lo, const void* wplanes, const float* bias, float* out, float* stats,
-                     int B, int H, int W, int Cin, int Cout, int dgrad, cudaStream_t st) {
+                     int B, int H, int W, int Cin, int Cout, int dgrad, cudaStream_t st, int terms, int fmt,
+                     const float* out_scale) {
     const int Kc = dgrad ? Cout : Cin, Nc = dgrad ? Cin : Cout;
+    SED_REQUIRE(terms == 1 || terms == 3, SEDB200_EINVAL, "conv_tc: terms = %d", terms);
+    if (terms == 1 || !a_lo) a_lo = a_hi;                       // 1-term: the lo maps are encoded but never used
     SED_REQUIRE(conv_tc_supported(H, W, Kc, Nc), SEDB200_ESHAPE, "conv_tc: shape H=%d W=%d K=%d N=%d unsupported", H, W, Kc, Nc);
     const size_t wp = ((size_t)9 * Nc * Kc * 2 + 1023) & ~(size_t)1023;
     const __nv_bfloat16* w_hi = reinterpret_cast<const __nv_bfloat16*>(wplanes);
@@ -475,6 +516,9 @@ int conv_tc_planes_w(const void* a_hi, const void* a_lo, const void* wplanes, co
     p.total_tiles = B * p.tiles_per_img * p.n_tiles_n;
     p.kchunks = Kc / kBlockK;
     p.n_total = Nc;
+    p.terms = terms;
+    p.idesc = fmt == kPlaneF16 ? idesc_f16(kTileM, kTileN, 0, 0) : idesc_bf16(kTileM, kTileN, 0, 0);
+    p.out_scale = out_scale;
     p.out = out; p.bias = bias; p.out_ld = Nc; p.stats = stats;
     { const int rc = ensure_dyn_smem((const void*)conv_tc_kernel, kSmemBytes); if (rc) return rc; }
     const int grid = std::min(p.total_tiles, sm_count());
@@ -522,8 +566,11 @@ size_t wgrad_tc_part_bytes(int Cin, int Cout) { return (size_t)wgrad_slices(Cin,
 
 // planes given: dY [B][H][W][Cout] and In [B][H][W][Cin] as bf16 hi / lo
 int wgrad_tc_planes(const void* y_hi, const void* y_lo, const void* x_hi, const void* x_lo, float* dw, int B, int H,
-                    int W, int Cin, int Cout, float* part, cudaStream_t st) {
+                    int W, int Cin, int Cout, float* part, cudaStream_t st, int terms, int fmt, const float* out_scale) {
     SED_REQUIRE(wgrad_tc_supported(H, W, Cin, Cout), SEDB200_ESHAPE, "wgrad_tc: shape H=%d W=%d Cin=%d Cout=%d unsupported", H, W, Cin, Cout);
+    SED_REQUIRE(terms == 1 || terms == 3, SEDB200_EINVAL, "wgrad_tc: terms = %d", terms);
+    if (terms == 1 || !y_lo) y_lo = y_hi;
+    if (terms == 1 || !x_lo) x_lo = x_hi;
     const int Hk = kWgKp / W;
     CUtensorMap tmY_hi, tmY_lo, tmX_hi, tmX_lo;
     const uint32_t box[4] = {64, (uint32_t)W, (uint32_t)Hk, 1};
@@ -549,12 +596,13 @@ int wgrad_tc_planes(const void* y_hi, const void* y_lo, const void* x_hi, const 
     p.total_kblocks = B * p.hblocks_per_img;
     p.n_mt = Cout / 128; p.n_nt = Cin / 128;
     p.slices = std::min(wgrad_slices(Cin, Cout), p.total_kblocks);
-    p.part = part; p.Cout = Cout; p.Cin = Cin;
+    p.part = part; p.Cout = Cout; p.Cin = Cin; p.terms = terms;
+    p.idesc = fmt == kPlaneF16 ? idesc_f16(128, 128, 1, 1) : idesc_bf16(128, 128, 1, 1);
     { const int rc = ensure_dyn_smem((const void*)wgrad_tc_kernel, kWgSmemBytes); if (rc) return rc; }
     const int grid = p.n_mt * p.n_nt * 3 * p.slices;
     wgrad_tc_kernel<<<grid, kThreads, kWgSmemBytes, st>>>(tmY_hi, tmY_lo, tmX_hi, tmX_lo, p);
     SED_POST_LAUNCH();
-    wgrad_reduce_kernel<<<(int)std::min<long>((9L * Cout * Cin + 255) / 256, 1184), 256, 0, st>>>(part, p.slices, Cout, Cin, dw);
+    wgrad_reduce_kernel<<<(int)std::min<long>((9L * Cout * Cin + 255) / 256, 1184), 256, 0, st>>>(part, p.slices, Cout, Cin, dw, out_scale);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }

@@ -115,6 +115,11 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn_major, 
            | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16)
            | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// same with both operands fp16 (format code 0)
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
 // Shared-memory matrix descriptor, 128-byte swizzle.  Offsets are in bytes (16 B granularity).
 //   K-major : rows of 128 B (64 bf16 along K); 8-row groups `sbo` bytes apart; lbo unused (0).
 //   MN-major: rows of 128 B (64 bf16 along M/N) per k; 8-k groups `sbo` apart; 64-element M/N groups `lbo` apart.

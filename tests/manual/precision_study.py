@@ -60,6 +60,9 @@ class Split:
             s8 = pow2_scale(t, 256.0)
             self.hi8 = r_e4m3(t, s8)
             self.lo8 = r_e4m3(t - self.hi, pow2_scale(t - self.hi, 256.0))
+        elif scheme == "x1":                                    # A (dY) bf16, B (weights / activations) fp16, one term
+            self.hi = r_bf16(t)
+            self.hi_b = r_fp16(t, pow2_scale(t, 2.0 ** 14))
         elif scheme == "t1":
             self.hi = r_tf32(t)
         elif scheme == "bm2":                                   # bf16 hi*hi + e4m3 corrections
@@ -69,7 +72,7 @@ class Split:
 
 
 COST = {"fp32": 0, "s3": 3, "b1": 1, "b2a": 2, "b2b": 2, "f1": 1, "f2a": 2, "f2b": 2, "f3": 3, "m2": 2, "m15a": 1.5,
-        "m15b": 1.5, "t1": 2, "bm2": 2}
+        "m15b": 1.5, "t1": 2, "bm2": 2, "x1": 1}
 
 
 def contract(op, a, b, scheme):
@@ -82,6 +85,8 @@ def contract(op, a, b, scheme):
         return op(A.hi, B.hi) + op(A.hi, B.lo) + op(A.lo, B.hi)
     if scheme in ("b1", "f1", "t1"):
         return op(A.hi, B.hi)
+    if scheme == "x1":
+        return op(A.hi, B.hi_b)
     if scheme in ("b2a", "f2a"):                                # full A, truncated B
         return op(A.hi, B.hi) + op(A.lo, B.hi)
     if scheme in ("b2b", "f2b"):                                # truncated A, full B

@@ -106,9 +106,7 @@ def one_step_parity(case, rcfg, ref, cfg, eng, x, y, loss, wd, clip, *, masks_fr
         else:
             err = (got - g).norm().item() / max(g.norm().item(), 1e-12)
             worst["conv_l2"] = max(worst["conv_l2"], err)
-            # the first conv's weight gradient sits behind all three pool decisions and BatchNorm cancellations and has
-            # only 9 * in_ch * C elements: measured up to 1.3e-2 on reduced cases, 3e-3 at full size
-            assert err <= (2 * conv_grad_l2 if name == "conv0.weight" else conv_grad_l2), (name, err)
+            assert err <= conv_grad_l2, (name, err)
     gn = eng.optimizer_step()
     gnerr = abs(gn.item() - gn_ref.item()) / gn_ref.item()
     assert gnerr <= 1e-4, gnerr
