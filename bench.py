@@ -91,13 +91,17 @@ def phase_model(cfg, B, per):
             # lean block 0 (conv output never stored): input + pooled output + one winner byte per output element
             m["conv0.stats"] = ("hbm", xin, "conv0_gram_kernel (patch moments of the input -> BatchNorm statistics)")
             m["conv0.fwd_fused"] = ("hbm", xin + a + a / 4,
-                                    "conv0_tc_fwd_kernel (tcgen05 conv + BN + ReLU + max-pool + dropout epilogue, conv output never stored)"
+                                    "conv0_win_fwd_kernel (tcgen05 conv with a pooling window per MMA row: BN folded into the "
+                                    "weights, max-pool / ReLU / dropout in registers, conv output never stored)"
                                     if cfg.tensor_cores else
                                     "conv0_lean_fwd_kernel (conv + BN + ReLU + max-pool + dropout in registers)")
             m["conv0.bwd_lean"] = ("hbm", xin + a + a / 4, "conv0_lean_bwd_kernel (winner contributions to dW / d gamma / d beta)")
         elif tc_ok:
-            for ph, kn in (("fwd", "conv_tc_kernel"), ("dgrad", "conv_tc_kernel"), ("wgrad", "wgrad_tc_kernel")):
-                m[f"conv{i}.{ph}"] = ("tensor", per[f"conv{i}"], f"{kn} (tcgen05 implicit GEMM, 3-term bf16 split) + bf16 plane split")
+            # MMA passes per k-step: the forward runs the 3-term fp16 hi/lo split (fp32-grade), the data / weight
+            # gradients ONE pass on fp16 planes (dy scaled by a per-tensor power of two) -- DESIGN.md section 3
+            for ph, kn, terms in (("fwd", "conv_tc_kernel", 3), ("dgrad", "conv_tc_kernel", 1), ("wgrad", "wgrad_tc_kernel", 1)):
+                m[f"conv{i}.{ph}"] = ("tensor", per[f"conv{i}"], f"{kn} (tcgen05 implicit GEMM on fp16 planes: 3-term split "
+                                      f"forward, single-pass gradients)", terms)
         m[f"pool{i}.fwd"] = ("hbm", y + a, "bn_relu_pool_fwd_t_kernel (BN + ReLU + max-pool + dropout: conv output in, pooled planes out)")
         m[f"pool{i}.bwd_sums"] = ("hbm", 2 * a, "bn_bwd_sums_act_kernel (BatchNorm backward sums from the saved block output and dA)")
         if i > 0:
@@ -830,14 +834,18 @@ def run_ours(args, rank, world, local_rank):
         pass
     if kind == "tensor":
         ach = amount_step / (ms_kernel_step * 1e-3) / 1e12
+        issued = sum(model[k][1] * (model[k][3] if len(model[k]) > 3 else 1) for k in dks) / (ms_kernel_step * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": kname, "phases": dks, "achieved": ach, "peak": pk["tf_sustained"],
                 "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "traffic": traffic,
                 "traffic_note": "dram bytes per launch, mean of this kernel's launches in one step as captured by ncu "
-                "--set full (profiles/ncu_traffic.json, profiles/r01_conv_tc_final_metrics.csv)",
+                "--set full (profiles/ncu_traffic.json)",
                 "peak_source": pk["src"] + " (sustained bf16)", "algorithmic_flops_per_launch": amount,
-                "mma_tflops_issued": 3 * ach, "frac_issued": 3 * ach / pk["tf_sustained"],
-                "note": "fp32-grade 3-term bf16 split: the tensor pipe executes 3x the algorithmic FLOPs; frac is "
-                "algorithmic FLOPs / bf16 peak, frac_issued the tensor-pipe work actually issued / bf16 peak"}
+                "mma_tflops_issued": issued, "frac_issued": issued / pk["tf_sustained"],
+                "per_phase": {k: {"ms": phases[k], "algorithmic_tflops": model[k][1] / (phases[k] * 1e-3) / 1e12,
+                                  "mma_passes": model[k][3] if len(model[k]) > 3 else 1} for k in dks},
+                "note": "frac = algorithmic FLOPs (2*M*K*N, SURVEY 8d) / measured sustained fp16/bf16 peak, pooled over this "
+                "kernel's launches in a step; the forward launches run the fp32-grade 3-term fp16 split (3 MMA passes per "
+                "k-step), the data-gradient launches one pass; frac_issued counts the MMA work actually issued"}
     else:
         ach = amount_step / (ms_kernel_step * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": kname, "phases": dks, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
@@ -864,7 +872,7 @@ def run_ours(args, rank, world, local_rank):
         a = model[k][1] / (t_ms * 1e-3) / 1e12
         roof["tensor_kernel"] = {"phase": k, "kernel": model[k][2], "achieved": a, "unit": "TFLOP/s",
                                  "peak": pk["tf_sustained"], "frac": a / pk["tf_sustained"], "ms_per_launch": t_ms,
-                                 "mma_tflops_issued": 3 * a}
+                                 "mma_tflops_issued": (model[k][3] if len(model[k]) > 3 else 1) * a}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,

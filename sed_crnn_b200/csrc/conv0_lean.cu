@@ -7,6 +7,7 @@
 #include "tc_umma.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace sedb200 {
 namespace {
@@ -752,7 +753,11 @@ int conv0_lean_forward(const float* x, int cin, int batch, const float* w, const
                        unsigned* argw, cudaStream_t st) {
     const int gpi = (g.H + kC0Rows - 1) / kC0Rows, n_groups = gpi * batch;
     if (tensor_cores) {
-        // contraction on tcgen05 (same 3-term split as conv 2 / 3); the fp32 kernel below serves tensor_cores = 0
+        // contraction on tcgen05 (same 3-term split as conv 2 / 3); the fp32 kernel below serves tensor_cores = 0.
+        // Window-row formulation (conv0_win.cu) unless SEDB200_CONV0_PIXEL_ROWS=1 asks for the pixel-row kernel below
+        static const bool pixel_rows = [] { const char* e = std::getenv("SEDB200_CONV0_PIXEL_ROWS"); return e && e[0] == '1'; }();
+        if (!pixel_rows && conv0_win_ok(cin, g.C, g.p, (long)batch * g.H * g.Wo))
+            return conv0_win_forward(x, cin, batch, w, bias, stat, g, out, out_hi, out_lo, argw, st);
         const unsigned n_windows = (unsigned)((long)batch * g.H * g.Wo);
         const int NWt = 128 / g.p;
         const int n_tiles = (int)((n_windows + (unsigned)NWt - 1) / (unsigned)NWt);
@@ -787,9 +792,19 @@ long conv0_lean_bwd_part_floats(int cin, int C, int batch, int H) {
 }
 int conv0_lean_backward(const float* x, int cin, int batch, const unsigned* argw, const float* dA, const PoolGeom& g,
                         const double* gram, const float* w, const float* bias, const float* gamma, const float* stat,
-                        float* part, float* dw, float* db, float* dgamma, float* dbeta, cudaStream_t st) {
+                        float* part, float* dw, float* db, float* dgamma, float* dbeta, cudaStream_t st,
+                        int tensor_cores) {
     const int gpi = (g.H + kC0Rows - 1) / kC0Rows, n_groups = gpi * batch, K0 = 9 * cin;
-    const dim3 grid(std::min(n_groups, 2 * sm_count()), g.C / 128);
+    dim3 grid(std::min(n_groups, 2 * sm_count()), g.C / 128);
+    // tcgen05 formulation in window coordinates (conv0_win.cu) when the forward ran on the tensor cores; the fp32
+    // kernel below serves tensor_cores = 0 and SEDB200_CONV0_PIXEL_ROWS=1
+    static const bool pixel_rows = [] { const char* e = std::getenv("SEDB200_CONV0_PIXEL_ROWS"); return e && e[0] == '1'; }();
+    if (tensor_cores && !pixel_rows && conv0_win_bwd_ok(cin, g, (long)batch * g.H * g.Wo)) {
+        int nb = 0;
+        const int rc = conv0_win_backward_partials(x, cin, batch, argw, dA, g, part, &nb, st);
+        if (rc) return rc;
+        grid.x = (unsigned)nb;
+    } else {
     const size_t bsm = conv0_lean_bwd_smem(cin, g.W);
     const void* kfn = cin == 1 ? (g.p == 5 ? (const void*)conv0_lean_bwd_kernel<1, 5> : (const void*)conv0_lean_bwd_kernel<1, 2>)
                                : (g.p == 5 ? (const void*)conv0_lean_bwd_kernel<2, 5> : (const void*)conv0_lean_bwd_kernel<2, 2>);
@@ -800,6 +815,7 @@ int conv0_lean_backward(const float* x, int cin, int batch, const unsigned* argw
     else if (g.p == 5) conv0_lean_bwd_kernel<2, 5><<<grid, 256, bsm, st>>>(x, argw, dA, g, gpi, n_groups, part);
     else conv0_lean_bwd_kernel<2, 2><<<grid, 256, bsm, st>>>(x, argw, dA, g, gpi, n_groups, part);
     SED_POST_LAUNCH();
+    }
     double* Ssum = reinterpret_cast<double*>(part + (size_t)grid.x * (K0 + 1) * g.C + 64);   // behind the partials
     conv0_lean_bwd_colsum_kernel<<<dim3(K0 + 1, g.C / 128), 1024, 0, st>>>(part, (int)grid.x, K0 + 1, g.C, Ssum);
     SED_POST_LAUNCH();

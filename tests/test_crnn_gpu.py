@@ -276,9 +276,14 @@ def test_fused_head_matches_unfused_path(pkg, preset, loss):
         assert (a.grads - b.grads).abs().max().item() <= (5e-6 if it == 0 else 2e-3) * scale
         # Adam turns a gradient that is pure rounding noise (conv biases under BatchNorm) into +-lr: compare the
         # weights only where the gradient is above the noise
+        # (with weight decay the quantity Adam normalises is g + wd * p: where those two nearly cancel, a 1e-6-relative
+        # difference in g -- the fp16 gradient planes round differently once d(gru output) differs in its last bit --
+        # still flips the update, so a handful of entries may differ by up to 2 * lr)
         if it == 0:
             solid = a.grads.abs() > 1e-3 * scale
-            assert torch.allclose(a.params[solid], b.params[solid], rtol=0, atol=2e-5)
+            diff = (a.params[solid] - b.params[solid]).abs()
+            assert diff.max().item() <= 2.1e-3
+            assert (diff > 2e-5).float().mean().item() <= 1e-4
 
 
 @pytest.mark.parametrize("preset,ov,batch", [("c1", {"seq_len": 32}, 5), ("c2", {"seq_len": 24}, 3)])
