@@ -792,19 +792,9 @@ long conv0_lean_bwd_part_floats(int cin, int C, int batch, int H) {
 }
 int conv0_lean_backward(const float* x, int cin, int batch, const unsigned* argw, const float* dA, const PoolGeom& g,
                         const double* gram, const float* w, const float* bias, const float* gamma, const float* stat,
-                        float* part, float* dw, float* db, float* dgamma, float* dbeta, cudaStream_t st,
-                        int tensor_cores) {
+                        float* part, float* dw, float* db, float* dgamma, float* dbeta, cudaStream_t st) {
     const int gpi = (g.H + kC0Rows - 1) / kC0Rows, n_groups = gpi * batch, K0 = 9 * cin;
-    dim3 grid(std::min(n_groups, 2 * sm_count()), g.C / 128);
-    // tcgen05 formulation in window coordinates (conv0_win.cu) when the forward ran on the tensor cores; the fp32
-    // kernel below serves tensor_cores = 0 and SEDB200_CONV0_PIXEL_ROWS=1
-    static const bool pixel_rows = [] { const char* e = std::getenv("SEDB200_CONV0_PIXEL_ROWS"); return e && e[0] == '1'; }();
-    if (tensor_cores && !pixel_rows && conv0_win_bwd_ok(cin, g, (long)batch * g.H * g.Wo)) {
-        int nb = 0;
-        const int rc = conv0_win_backward_partials(x, cin, batch, argw, dA, g, part, &nb, st);
-        if (rc) return rc;
-        grid.x = (unsigned)nb;
-    } else {
+    const dim3 grid(std::min(n_groups, 2 * sm_count()), g.C / 128);
     const size_t bsm = conv0_lean_bwd_smem(cin, g.W);
     const void* kfn = cin == 1 ? (g.p == 5 ? (const void*)conv0_lean_bwd_kernel<1, 5> : (const void*)conv0_lean_bwd_kernel<1, 2>)
                                : (g.p == 5 ? (const void*)conv0_lean_bwd_kernel<2, 5> : (const void*)conv0_lean_bwd_kernel<2, 2>);
@@ -815,7 +805,6 @@ int conv0_lean_backward(const float* x, int cin, int batch, const unsigned* argw
     else if (g.p == 5) conv0_lean_bwd_kernel<2, 5><<<grid, 256, bsm, st>>>(x, argw, dA, g, gpi, n_groups, part);
     else conv0_lean_bwd_kernel<2, 2><<<grid, 256, bsm, st>>>(x, argw, dA, g, gpi, n_groups, part);
     SED_POST_LAUNCH();
-    }
     double* Ssum = reinterpret_cast<double*>(part + (size_t)grid.x * (K0 + 1) * g.C + 64);   // behind the partials
     conv0_lean_bwd_colsum_kernel<<<dim3(K0 + 1, g.C / 128), 1024, 0, st>>>(part, (int)grid.x, K0 + 1, g.C, Ssum);
     SED_POST_LAUNCH();

@@ -21,14 +21,9 @@ int conv0_win_forward(const float* x, int cin, int batch, const float* w, const 
                       const PoolGeom& g, float* out, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, unsigned* argw,
                       cudaStream_t st);
 
-bool conv0_win_bwd_ok(int cin, const PoolGeom& g, long n_windows);
-int conv0_win_backward_partials(const float* x, int cin, int batch, const unsigned* argw, const float* dA,
-                                const PoolGeom& g, float* part, int* nblk, cudaStream_t st);
-
 long conv0_lean_bwd_part_floats(int cin, int C, int batch, int H);
 int conv0_lean_backward(const float* x, int cin, int batch, const unsigned* argw, const float* dA, const PoolGeom& g,
                         const double* gram, const float* w, const float* bias, const float* gamma, const float* stat,
-                        float* part, float* dw, float* db, float* dgamma, float* dbeta, cudaStream_t st,
-                        int tensor_cores = 0);
+                        float* part, float* dw, float* db, float* dgamma, float* dbeta, cudaStream_t st);
 
 }  // namespace sedb200

@@ -1608,8 +1608,7 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
                                          reinterpret_cast<const unsigned*>(reinterpret_cast<const char*>(ws) + P.arg0), dA, g,
                                          reinterpret_cast<const double*>(reinterpret_cast<const char*>(ws) + P.gram),
                                          params + P.conv_w[0], params + P.conv_b[0], params + P.bn_w[0], stat, part,
-                                         grads + P.conv_w[0], grads + P.conv_b[0], grads + P.bn_w[0], grads + P.bn_b[0], st,
-                                         d->tensor_cores);
+                                         grads + P.conv_w[0], grads + P.conv_b[0], grads + P.bn_w[0], grads + P.bn_b[0], st);
                 if (rc) return rc;
                 break;
             }

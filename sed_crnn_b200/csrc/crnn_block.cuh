@@ -11,23 +11,26 @@ constexpr int kC0Rows = 8;             // image rows per row group of the direct
 inline bool conv0_direct_ok(int cin, int C) { return (cin == 1 || cin == 2) && C % 128 == 0; }
 
 // ----------------------------------------------------------------------------- dropout generator
-// One 64-bit hash (splitmix64 finaliser) per group of FOUR consecutive elements; element q of the group keeps its
-// value iff the q-th 16-bit field of the hash is >= p * 65536.  Forward and backward kernels all go through
-// dropout_keep4(seed, group index), so they agree on the mask without storing it.
-__device__ __forceinline__ unsigned long long hash64(unsigned long long seed, unsigned long long idx) {
-    unsigned long long x = seed + idx * 0x9E3779B97F4A7C15ull;
-    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
-    x ^= x >> 27; x *= 0x94D049BB133111EBull;
-    x ^= x >> 31;
+// Two 32-bit hashes (murmur3 finaliser over the element-group index and the seed) per group of FOUR consecutive
+// elements; element q of the group keeps its value iff the q-th 16-bit field is >= p * 65536.  Forward and backward
+// kernels (and sedb200_crnn_dropout_mask) all go through dropout_keep4(seed, group index), so they agree on the mask
+// without storing it.  32-bit arithmetic on purpose: the 64-bit splitmix of round 1 cost ~30 instructions per group,
+// a tenth of the fused block-0 epilogue.
+__device__ __forceinline__ unsigned mix32(unsigned x) {
+    x ^= x >> 16; x *= 0x85EBCA6Bu;
+    x ^= x >> 13; x *= 0xC2B2AE35u;
+    x ^= x >> 16;
     return x;
 }
 struct Keep4 { bool k[4]; };
 __device__ __forceinline__ Keep4 dropout_keep4(unsigned long long seed, unsigned long long group, float p) {
-    const unsigned long long x = hash64(seed, group);
+    const unsigned lo = (unsigned)group, hi = (unsigned)(group >> 32);
+    const unsigned a = mix32(lo * 0x9E3779B1u + hi * 0x7FEB352Du + (unsigned)seed);
+    const unsigned b = mix32((lo ^ 0x68E31DA4u) * 0xB5297A4Du + hi + (unsigned)(seed >> 32));
     const unsigned thr = (unsigned)(p * 65536.0f);
     Keep4 r;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) r.k[q] = (unsigned)((x >> (16 * q)) & 0xFFFFu) >= thr;
+    r.k[0] = (a & 0xFFFFu) >= thr; r.k[1] = (a >> 16) >= thr;
+    r.k[2] = (b & 0xFFFFu) >= thr; r.k[3] = (b >> 16) >= thr;
     return r;
 }
 __host__ __device__ inline unsigned long long block_seed(unsigned long long seed, int block) {
@@ -38,18 +41,19 @@ __host__ __device__ inline unsigned long long block_seed(unsigned long long seed
 // bits for the O(1) values BatchNorm produces (residuals below 2^-14 go subnormal: absolute precision 2^-24).  The
 // conversions saturate at the fp16 range instead of producing inf.  Storage type of all 16-bit planes is
 // `__nv_bfloat16` (just 2 bytes); what the bytes mean is the producer's / consumer's contract.
-__device__ __forceinline__ __half sat_half(float x) { return __float2half_rn(fminf(fmaxf(x, -65504.0f), 65504.0f)); }
+// {fp16(a), fp16(b)} packed (a in the low half), round-to-nearest, saturating at +-65504: one F2FP instruction
+__device__ __forceinline__ unsigned pack_half2_sat(float a, float b) {
+    unsigned d;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
+}
+__device__ __forceinline__ float2 unpack_half2(unsigned v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
 __device__ __forceinline__ void store_planes4(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long i4,
                                               const float4 v) {
-    __half h[4], l[4];
-    const float f[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        h[q] = sat_half(f[q]);
-        l[q] = sat_half(f[q] - __half2float(h[q]));
-    }
-    reinterpret_cast<uint2*>(hi)[i4] = *reinterpret_cast<uint2*>(h);
-    reinterpret_cast<uint2*>(lo)[i4] = *reinterpret_cast<uint2*>(l);
+    const unsigned h01 = pack_half2_sat(v.x, v.y), h23 = pack_half2_sat(v.z, v.w);
+    const float2 f01 = unpack_half2(h01), f23 = unpack_half2(h23);
+    reinterpret_cast<uint2*>(hi)[i4] = make_uint2(h01, h23);
+    reinterpret_cast<uint2*>(lo)[i4] = make_uint2(pack_half2_sat(v.x - f01.x, v.y - f01.y), pack_half2_sat(v.z - f23.x, v.w - f23.y));
 }
 __device__ __forceinline__ float4 load_planes4(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
                                                long i4) {
@@ -65,8 +69,7 @@ __device__ __forceinline__ float4 load_planes4(const __nv_bfloat16* __restrict__
 // their result by 1 / scale.  (The data / weight gradient contractions run single-pass: measured on the oracle,
 // fp16-rounded gradient operands change the probabilities after a step by < 1e-4, the forward needs the split.)
 __device__ __forceinline__ void store_dy4(__nv_bfloat16* __restrict__ hi, long i4, const float4 v, float scale) {
-    __half h[4] = {sat_half(v.x * scale), sat_half(v.y * scale), sat_half(v.z * scale), sat_half(v.w * scale)};
-    reinterpret_cast<uint2*>(hi)[i4] = *reinterpret_cast<uint2*>(h);
+    reinterpret_cast<uint2*>(hi)[i4] = make_uint2(pack_half2_sat(v.x * scale, v.y * scale), pack_half2_sat(v.z * scale, v.w * scale));
 }
 
 struct PoolGeom {
