@@ -255,10 +255,9 @@ int sedb200_p2p_allreduce_clip_adam(void* const* regions_host, int world, int ra
     {
         long long ms = kDefaultTimeoutMs;
         if (const char* e = std::getenv("SEDB200_P2P_TIMEOUT_MS")) { const long long v = std::atoll(e); if (v > 0) ms = v; }
-        int dev = 0, khz = 0;
-        SED_CUDA_OK(cudaGetDevice(&dev));
-        SED_CUDA_OK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
-        a.timeout_cycles = ms * (long long)std::max(khz, 100000);          // clock64 ticks at the SM clock (kHz = cycles/ms)
+        // clock64 ticks at the SM clock; the nominal maximum (2.1 GHz covers every B200 bin) keeps the bound a wall-clock
+        // LOWER bound on the wait.  (cudaDevAttrClockRate is a ~1 ms driver query: not something to call per step.)
+        a.timeout_cycles = ms * 2100000LL;
     }
     const long n4 = a.n >> 2;
     int grid = (int)std::max<long>(1, std::min<long>((n4 + kThreads - 1) / kThreads, sm_count()));
