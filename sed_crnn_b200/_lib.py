@@ -7,7 +7,7 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsedb200.so")
+LIB_PATH = os.environ.get("SEDB200_LIB_PATH") or os.path.join(HERE, "libsedb200.so")   # override: A/B builds
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "sedb200.h")
 
 OK, EINVAL, ESHAPE, EWORKSPACE, ECUDA, EARCH = 0, -1, -2, -3, -4, -5

@@ -26,6 +26,7 @@
 #include "tc_conv.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 namespace sedb200 {
@@ -59,20 +60,41 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 namespace {
 using namespace umma;
 
-constexpr int kStages = 3;                                       // 3-term stages (64 KB each)
-constexpr int kMaxStages = 6;                                    // 1-term stages are half the size: twice as many fit
+constexpr int kStages = 3;                                       // wgrad_tc_kernel, 3-term
+constexpr int kMaxStages = 6;                                    // barrier slots
 constexpr int kTileM = 128, kTileN = 128, kBlockK = 64;
-constexpr int kTileBytes = kTileM * kBlockK * 2;                 // 16 KB: one bf16 operand tile
-constexpr int kStageBytes = 4 * kTileBytes;                      // A_hi, A_lo, B_hi, B_lo
+constexpr int kTileBytes = kTileM * kBlockK * 2;                 // 16 KB: one 16-bit operand tile
+constexpr int kStageBytes = 4 * kTileBytes;                      // wgrad_tc_kernel: A_hi, A_lo, B_hi, B_lo
 constexpr int kEpiPitch = 36;                                    // floats per staged row: LDS/STS.128 conflict-free
-constexpr int kEpiBytes = 4 * 32 * kEpiPitch * 4;                // one 32 x 32 staging tile per epilogue warp
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 4096 /*BN-stat staging*/ + kEpiBytes;
-constexpr int kThreads = 256;
-constexpr uint32_t kTmemCols = 256;                              // two 128-column accumulators
+constexpr int kEpiTile = 32 * kEpiPitch * 4;                     // one 32 x 32 staging tile per epilogue warp
+constexpr int kThreads = 256;                                    // wgrad_tc_kernel
+constexpr int kConvThreads = 384;                                // conv_tc_kernel: warps 8-11 = second epilogue set
+constexpr uint32_t kTmemCols = 512;                              // conv_tc_kernel: 2 buffers x 2 tiles x 128 columns
+
+// conv_tc_kernel modes.  Every tensor-core kernel here turned out to be bound by the bytes an SM can ingest from L2
+// (~50 B/clk/SM measured: profiles/README.md), so the knobs are about bytes per MMA:
+//   terms  3: A_hi*B_hi + A_hi*B_lo + A_lo*B_hi (fp32-grade, forward) / 1: hi planes only (gradient contractions)
+//   tpi    tiles per work item: 2 = two M tiles (256 output pixels) share every weight k-block -- 24 instead of 32 KB
+//          per 128x128x64 MMA block -- when there are enough tiles to keep the 148 CTAs balanced; 1 otherwise
+// stage = tpi * planes A tiles + planes B tiles of 16 KB, planes = 2 (hi, lo) or 1.
+struct ConvMode { int planes, tpi, stage_bytes, n_stages, n_epi_warps, smem_bytes; };
+inline ConvMode conv_mode(int terms, int tpi) {
+    ConvMode m;
+    m.planes = terms == 3 ? 2 : 1;
+    m.tpi = tpi;
+    m.stage_bytes = (tpi + 1) * m.planes * kTileBytes;           // 32 / 48 / 64 / 96 KB
+    // 1-term: a third of the MMA work per tile -> EIGHT epilogue warps (two per TMEM sub-partition, half of the
+    // columns each); the 4-warp epilogue was the bound there (ncu: tensor pipe 40 %, issue 16 %)
+    m.n_epi_warps = terms == 1 ? 8 : 4;
+    const int fixed = 1024 /*align*/ + 256 /*barriers*/ + 4096 /*BN-stat staging*/ + m.n_epi_warps * kEpiTile;
+    m.n_stages = std::min(kMaxStages, (227 * 1024 - fixed) / m.stage_bytes);
+    m.smem_bytes = m.n_stages * m.stage_bytes + fixed;
+    return m;
+}
 
 struct ConvTcParams {
-    int B, H, W, Ht, tiles_per_img, n_tiles_n, total_tiles, kchunks, n_total;
-    int terms;               // 3: A_hi*B_hi + A_hi*B_lo + A_lo*B_hi (fp32-grade);  1: hi planes only (gradient contractions)
+    int B, H, W, Ht, tiles_per_img, n_tiles_n, m_tiles, total_items, kchunks, n_total;
+    int terms, tpi, planes, stage_bytes, n_stages, n_epi_warps;
     uint32_t idesc;          // instruction descriptor (operand formats: bf16 or fp16 planes)
     const float* out_scale;  // null, or a device scalar every accumulator is multiplied by (fp16 gradient planes)
     float* out;              // [B*H*W][out_ld] fp32
@@ -81,22 +103,21 @@ struct ConvTcParams {
     float* stats;            // null, or per-M-tile partial BatchNorm sums [m_tiles][2][n_total] (sum, sum of squares)
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const ConvTcParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    const int n_stages = p.n_stages, stage_bytes = p.stage_bytes, n_epi_warps = p.n_epi_warps, tpi = p.tpi, planes = p.planes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + n_stages * stage_bytes);
     uint64_t* full = bars;                       // [kMaxStages]  TMA -> MMA
     uint64_t* empty = bars + kMaxStages;         // [kMaxStages]  MMA -> TMA
     uint64_t* tfull = bars + 2 * kMaxStages;     // [2]           MMA -> epilogue
     uint64_t* tempty = bars + 2 * kMaxStages + 2;// [2]           epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
-    const int n_stages = p.terms == 1 ? kMaxStages : kStages;
-    const int stage_bytes = p.terms == 1 ? kStageBytes / 2 : kStageBytes;
-    float* stat_s = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);     // [4 warps][2][128]
-    float* epi_stage = stat_s + 1024;                                                 // [4 warps][32][kEpiPitch]
+    float* stat_s = reinterpret_cast<float*>(smem + n_stages * stage_bytes + 256);    // [4 warps][2][128]
+    float* epi_stage = stat_s + 1024;                                                 // [epilogue warps][32][kEpiPitch]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
@@ -104,7 +125,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kMaxStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, n_epi_warps); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
@@ -113,87 +134,114 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int n_kb = 9 * p.kchunks;
+    // work item -> (N tile, first M tile); an item covers M tiles mt0 .. mt0 + tpi - 1 (a tile past the end reads zeros
+    // -- TMA fills boxes outside the tensor -- and is never stored)
+    const int b_off = tpi * planes * kTileBytes;                 // B planes behind the A tiles of a stage
 
     if (warp == 0 && lane == 0) {
         // ================= TMA producer =================
         int stage = 0; uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
-            const int b = mt / p.tiles_per_img, h0 = (mt % p.tiles_per_img) * p.Ht;
-            for (int kb = 0; kb < n_kb; ++kb) {
-                const int tap = kb / p.kchunks, c0 = (kb % p.kchunks) * kBlockK;
-                const int r = tap / 3, s = tap - 3 * r;
-                mbar_wait(empty + stage, phase ^ 1);
-                unsigned char* st = smem + stage * stage_bytes;
-                mbar_expect_tx(full + stage, stage_bytes);
-                if (p.terms == 1) {                            // stage = {A_hi, B_hi}
-                    tma_load_4d(st, &tmA_hi, full + stage, c0, s - 1, h0 + r - 1, b);
-                    tma_load_2d(st + kTileBytes, &tmB_hi, full + stage, c0, tap * p.n_total + nt * kTileN);
-                } else {                                       // stage = {A_hi, A_lo, B_hi, B_lo}
-                    tma_load_4d(st, &tmA_hi, full + stage, c0, s - 1, h0 + r - 1, b);
-                    tma_load_4d(st + kTileBytes, &tmA_lo, full + stage, c0, s - 1, h0 + r - 1, b);
-                    tma_load_2d(st + 2 * kTileBytes, &tmB_hi, full + stage, c0, tap * p.n_total + nt * kTileN);
-                    tma_load_2d(st + 3 * kTileBytes, &tmB_lo, full + stage, c0, tap * p.n_total + nt * kTileN);
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            const int nt = item % p.n_tiles_n, mt0 = (item / p.n_tiles_n) * tpi;
+            int tb[2], th[2];                              // (image, first row) of the item's tiles: no divisions per k-block
+            for (int t = 0; t < 2; ++t) {
+                const int mt = mt0 + t;
+                tb[t] = mt / p.tiles_per_img; th[t] = (mt - tb[t] * p.tiles_per_img) * p.Ht;
+            }
+            const int ncol = nt * kTileN;
+            for (int tap = 0; tap < 9; ++tap) {
+                const int r = tap / 3, s = tap - 3 * r;    // constant divisor
+                for (int c0 = 0; c0 < p.kchunks * kBlockK; c0 += kBlockK) {
+                    mbar_wait(empty + stage, phase ^ 1);
+                    unsigned char* st = smem + stage * stage_bytes;
+                    mbar_expect_tx(full + stage, stage_bytes);
+                    tma_load_4d(st, &tmA_hi, full + stage, c0, s - 1, th[0] + r - 1, tb[0]);
+                    if (planes == 2) tma_load_4d(st + kTileBytes, &tmA_lo, full + stage, c0, s - 1, th[0] + r - 1, tb[0]);
+                    if (tpi == 2) {
+                        tma_load_4d(st + planes * kTileBytes, &tmA_hi, full + stage, c0, s - 1, th[1] + r - 1, tb[1]);
+                        if (planes == 2)
+                            tma_load_4d(st + (planes + 1) * kTileBytes, &tmA_lo, full + stage, c0, s - 1, th[1] + r - 1, tb[1]);
+                    }
+                    tma_load_2d(st + b_off, &tmB_hi, full + stage, c0, tap * p.n_total + ncol);
+                    if (planes == 2) tma_load_2d(st + b_off + kTileBytes, &tmB_lo, full + stage, c0, tap * p.n_total + ncol);
+                    if (++stage == n_stages) { stage = 0; phase ^= 1; }
                 }
-                if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1 && lane == 0) {
         // ================= MMA issuer =================
+        // The issuing thread is a serial instruction stream: with one MMA pass per k-step a stage holds only ~256 cycles
+        // of tensor work, so descriptor construction must not cost more than that -- every descriptor is the
+        // descriptor of the shared-memory base plus a (16-byte-unit) offset added to its low word.
         const uint32_t idesc = p.idesc;
+        const uint64_t dbase = smem_desc_sw128(smem_u32(smem), 16, 1024);
+        const uint32_t stage_u = (uint32_t)stage_bytes >> 4, tile_u = kTileBytes >> 4, b_u = (uint32_t)b_off >> 4;
         int stage = 0; uint32_t phase = 0;
         int buf = 0; uint32_t bphase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
             mbar_wait(tempty + buf, bphase ^ 1);
             tc_fence_after();
-            const uint32_t d = tmem_base + buf * kTileN;
             for (int kb = 0; kb < n_kb; ++kb) {
                 mbar_wait(full + stage, phase);
                 tc_fence_after();
-                const uint32_t a_hi = smem_u32(smem + stage * stage_bytes);
-                if (p.terms == 1) {
-                    const uint32_t b_hi = a_hi + kTileBytes;
+                const uint64_t ds = dbase + (uint64_t)(stage * stage_u);
+                const uint64_t dbh0 = ds + b_u, dbl0 = dbh0 + tile_u;
+                const uint32_t acc0 = kb != 0;
+                if (planes == 1) {
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k)
-                        mma_bf16(d, smem_desc_sw128(a_hi + k * 32, 16, 1024), smem_desc_sw128(b_hi + k * 32, 16, 1024), idesc,
-                                 (kb | k) != 0);
+                    for (int t = 0; t < 2; ++t) {
+                        if (t < tpi) {
+                            const uint32_t d = tmem_base + (buf * 2 + t) * kTileN;
+                            const uint64_t dah0 = ds + (uint64_t)(t * tile_u);
+#pragma unroll
+                            for (int k = 0; k < kBlockK / 16; ++k) mma_bf16(d, dah0 + 2 * k, dbh0 + 2 * k, idesc, k ? 1u : acc0);
+                        }
+                    }
                 } else {
-                    const uint32_t a_lo = a_hi + kTileBytes, b_hi = a_hi + 2 * kTileBytes, b_lo = a_hi + 3 * kTileBytes;
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        const uint64_t dah = smem_desc_sw128(a_hi + k * 32, 16, 1024), dal = smem_desc_sw128(a_lo + k * 32, 16, 1024);
-                        const uint64_t dbh = smem_desc_sw128(b_hi + k * 32, 16, 1024), dbl = smem_desc_sw128(b_lo + k * 32, 16, 1024);
-                        mma_bf16(d, dah, dbh, idesc, (kb | k) != 0);
-                        mma_bf16(d, dah, dbl, idesc, 1);
-                        mma_bf16(d, dal, dbh, idesc, 1);
+                    for (int t = 0; t < 2; ++t) {
+                        if (t < tpi) {
+                            const uint32_t d = tmem_base + (buf * 2 + t) * kTileN;
+                            const uint64_t dah0 = ds + (uint64_t)(t * 2 * tile_u), dal0 = dah0 + tile_u;
+#pragma unroll
+                            for (int k = 0; k < kBlockK / 16; ++k) {
+                                mma_bf16(d, dah0 + 2 * k, dbh0 + 2 * k, idesc, k ? 1u : acc0);
+                                mma_bf16(d, dah0 + 2 * k, dbl0 + 2 * k, idesc, 1);
+                                mma_bf16(d, dal0 + 2 * k, dbh0 + 2 * k, idesc, 1);
+                            }
+                        }
                     }
                 }
                 mma_commit(empty + stage);                 // smem slot reusable once these MMAs retire
                 if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
-            mma_commit(tfull + buf);                       // accumulator complete
+            mma_commit(tfull + buf);                       // accumulators complete
             if (++buf == 2) { buf = 0; bphase ^= 1; }
         }
-    } else if (warp >= 4) {
-        // ================= epilogue (4 warps, one TMEM sub-partition each) =================
-        const int q = warp - 4;                            // == warp % 4
+    } else if (warp >= 4 && warp < 4 + n_epi_warps) {
+        // ================= epilogue (one TMEM sub-partition per warp; with 8 warps, half of the columns each) =====
+        const int q = warp & 3;                            // TMEM sub-partition == warp % 4
+        const int cc0 = (n_epi_warps == 8) ? ((warp - 4) >> 2) * 2 : 0, cc1 = (n_epi_warps == 8) ? cc0 + 2 : kTileN / 32;
         int buf = 0; uint32_t bphase = 0;
         const float osc = p.out_scale ? __ldg(p.out_scale) : 1.0f;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
-            const int b = mt / p.tiles_per_img, h0 = (mt % p.tiles_per_img) * p.Ht;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            const int nt = item % p.n_tiles_n, mt0 = (item / p.n_tiles_n) * tpi;
             mbar_wait(tfull + buf, bphase);
             tc_fence_after();
+            for (int t = 0; t < tpi; ++t) {
+            const int mt = mt0 + t;
+            if (mt >= p.m_tiles) break;                    // uniform over the epilogue warps
+            const int b = mt / p.tiles_per_img, h0 = (mt % p.tiles_per_img) * p.Ht;
             // TMEM hands every lane one output ROW (pixel); each 32 x 32 chunk goes through a per-warp staging tile so
             // that one store instruction writes four full 128 B channel segments (instead of 16 B pieces of 32 pixels),
             // and the BatchNorm column sums are plain conflict-free column reads of the same tile.
             float* dst0 = p.out + (((long)b * p.H + h0) * p.W + q * 32) * p.out_ld + nt * kTileN;
-            float* stg = epi_stage + q * (32 * kEpiPitch);
+            float* stg = epi_stage + (warp - 4) * (32 * kEpiPitch);
             const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
 #pragma unroll 1
-            for (int cc = 0; cc < kTileN / 32; ++cc) {
+            for (int cc = cc0; cc < cc1; ++cc) {
                 float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * kTileN + cc * 32, v);
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (buf * 2 + t) * kTileN + cc * 32, v);
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<float4*>(stg + lane * kEpiPitch + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -230,6 +278,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 p.stats[((long)mt * 2 + 0) * p.n_total + nt * kTileN + e] = a;
                 p.stats[((long)mt * 2 + 1) * p.n_total + nt * kTileN + e] = b2;
                 asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
             }
             tc_fence_before();
             __syncwarp();
@@ -513,16 +562,26 @@ int conv_tc_planes_w(const void* a_hi, const void* a_lo, const void* wplanes, co
     p.B = B; p.H = H; p.W = W; p.Ht = Ht;
     p.tiles_per_img = (H + Ht - 1) / Ht;
     p.n_tiles_n = Nc / kTileN;
-    p.total_tiles = B * p.tiles_per_img * p.n_tiles_n;
+    p.m_tiles = B * p.tiles_per_img;
     p.kchunks = Kc / kBlockK;
     p.n_total = Nc;
     p.terms = terms;
+    // two M tiles per work item when the CTAs stay balanced with half as many items (>= 5 per CTA)
+    static const int force_tpi = [] { const char* e = std::getenv("SEDB200_CONV_TPI"); return e ? std::atoi(e) : 0; }();
+    const long pairs = (long)((p.m_tiles + 1) / 2) * p.n_tiles_n;
+    int tpi = pairs >= 5L * sm_count() ? 2 : 1;
+    if (force_tpi == 1 || force_tpi == 2) tpi = force_tpi;
+    const ConvMode md = conv_mode(terms, tpi);
+    p.tpi = tpi; p.planes = md.planes; p.stage_bytes = md.stage_bytes; p.n_stages = md.n_stages; p.n_epi_warps = md.n_epi_warps;
+    p.total_items = ((p.m_tiles + tpi - 1) / tpi) * p.n_tiles_n;
     p.idesc = fmt == kPlaneF16 ? idesc_f16(kTileM, kTileN, 0, 0) : idesc_bf16(kTileM, kTileN, 0, 0);
     p.out_scale = out_scale;
     p.out = out; p.bias = bias; p.out_ld = Nc; p.stats = stats;
-    { const int rc = ensure_dyn_smem((const void*)conv_tc_kernel, kSmemBytes); if (rc) return rc; }
-    const int grid = std::min(p.total_tiles, sm_count());
-    conv_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+    SED_REQUIRE(md.n_stages >= 2, SEDB200_ESHAPE, "conv_tc: no room for two pipeline stages");
+    { const int rc = ensure_dyn_smem((const void*)conv_tc_kernel, 227 * 1024); if (rc) return rc; }
+    const int grid = std::min(p.total_items, sm_count());
+    SED_REQUIRE(terms == 3 || !stats, SEDB200_EINVAL, "conv_tc: BatchNorm statistics need the 3-term (forward) mode");
+    conv_tc_kernel<<<grid, kConvThreads, md.smem_bytes, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }
