@@ -138,32 +138,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // -- TMA fills boxes outside the tensor -- and is never stored)
     const int b_off = tpi * planes * kTileBytes;                 // B planes behind the A tiles of a stage
 
-    if (warp == 0 && lane == 0) {
-        // ================= TMA producer =================
+    if (warp == 0) {
+        // ================= TMA producer: lane i requests box i of a stage (A tiles first, then B; hi planes on even
+        //                   lanes, lo planes on odd lanes in the 3-pass mode); lane 0 waits for the slot ===============
         int stage = 0; uint32_t phase = 0;
+        const int n_boxes = (tpi + 1) * planes;
+        const bool mine = lane < n_boxes;
+        const int opnd = lane / planes, plane = lane - opnd * planes;        // opnd < tpi: A tile, == tpi: B
+        const bool is_b = opnd == tpi;
+        const CUtensorMap* tm = is_b ? (plane ? &tmB_lo : &tmB_hi) : (plane ? &tmA_lo : &tmA_hi);
+        const int dst_off = lane * kTileBytes;
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
             const int nt = item % p.n_tiles_n, mt0 = (item / p.n_tiles_n) * tpi;
-            int tb[2], th[2];                              // (image, first row) of the item's tiles: no divisions per k-block
-            for (int t = 0; t < 2; ++t) {
-                const int mt = mt0 + t;
-                tb[t] = mt / p.tiles_per_img; th[t] = (mt - tb[t] * p.tiles_per_img) * p.Ht;
-            }
+            const int mt = mt0 + (is_b ? 0 : opnd);
+            const int tb = mt / p.tiles_per_img, th = (mt - tb * p.tiles_per_img) * p.Ht;   // once per item
             const int ncol = nt * kTileN;
             for (int tap = 0; tap < 9; ++tap) {
                 const int r = tap / 3, s = tap - 3 * r;    // constant divisor
                 for (int c0 = 0; c0 < p.kchunks * kBlockK; c0 += kBlockK) {
-                    mbar_wait(empty + stage, phase ^ 1);
-                    unsigned char* st = smem + stage * stage_bytes;
-                    mbar_expect_tx(full + stage, stage_bytes);
-                    tma_load_4d(st, &tmA_hi, full + stage, c0, s - 1, th[0] + r - 1, tb[0]);
-                    if (planes == 2) tma_load_4d(st + kTileBytes, &tmA_lo, full + stage, c0, s - 1, th[0] + r - 1, tb[0]);
-                    if (tpi == 2) {
-                        tma_load_4d(st + planes * kTileBytes, &tmA_hi, full + stage, c0, s - 1, th[1] + r - 1, tb[1]);
-                        if (planes == 2)
-                            tma_load_4d(st + (planes + 1) * kTileBytes, &tmA_lo, full + stage, c0, s - 1, th[1] + r - 1, tb[1]);
+                    if (lane == 0) {
+                        mbar_wait(empty + stage, phase ^ 1);
+                        mbar_expect_tx(full + stage, stage_bytes);
                     }
-                    tma_load_2d(st + b_off, &tmB_hi, full + stage, c0, tap * p.n_total + ncol);
-                    if (planes == 2) tma_load_2d(st + b_off + kTileBytes, &tmB_lo, full + stage, c0, tap * p.n_total + ncol);
+                    __syncwarp();
+                    if (mine) {
+                        unsigned char* st = smem + stage * stage_bytes + dst_off;
+                        if (is_b) tma_load_2d(st, tm, full + stage, c0, tap * p.n_total + ncol);
+                        else tma_load_4d(st, tm, full + stage, c0, s - 1, th + r - 1, tb);
+                    }
                     if (++stage == n_stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -401,24 +403,34 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
     const int kb_per = (p.total_kblocks + p.slices - 1) / p.slices;
     const int kb0 = slice * kb_per, kb1 = min(p.total_kblocks, kb0 + kb_per);
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
+        // The producer is a serial instruction stream too: per K-block it has 8 (single-pass) or 16 boxes to request,
+        // ~40 cycles of issue each, against 384 cycles of MMA work -- so lane i requests box i (all lanes of the warp in
+        // one instruction), lane 0 alone waits for the slot and posts the byte count, and (image, row) advance without
+        // divisions.
         int stage = 0; uint32_t phase = 0;
+        int b = kb0 / p.hblocks_per_img, hb = kb0 - b * p.hblocks_per_img;
+        // lane -> (operand, tap, half, plane): boxes 0-1 dY hi, 2-7 In hi (tap s, half); +8: the lo planes (3-term)
+        const int box = lane & 7, plane = lane >> 3;
+        const bool mine = lane < (p.terms == 1 ? 8 : 16);
+        const bool is_y = box < 2;
+        const int half = is_y ? box : (box - 2) & 1, s = is_y ? 0 : (box - 2) >> 1;
+        const int c_first = (is_y ? mt : nt) * 128 + half * 64;
+        const int dst_off = is_y ? (plane * 2 + half) * kWgBox : a_bytes + s * b_bytes + (plane * 2 + half) * kWgBox;
+        const CUtensorMap* tm = is_y ? (plane ? &tmY_lo : &tmY_hi) : (plane ? &tmX_lo : &tmX_hi);
         for (int kb = kb0; kb < kb1; ++kb) {
-            const int b = kb / p.hblocks_per_img, h0 = (kb % p.hblocks_per_img) * p.Hk;
-            mbar_wait(empty + stage, phase ^ 1);
-            unsigned char* st = smem + stage * stage_bytes;
-            mbar_expect_tx(full + stage, stage_bytes);
-            for (int half = 0; half < 2; ++half) {
-                tma_load_4d(st + half * kWgBox, &tmY_hi, full + stage, mt * 128 + half * 64, 0, h0, b);
-                if (p.terms != 1) tma_load_4d(st + (2 + half) * kWgBox, &tmY_lo, full + stage, mt * 128 + half * 64, 0, h0, b);
+            const int h0 = hb * p.Hk;
+            if (lane == 0) {
+                mbar_wait(empty + stage, phase ^ 1);
+                mbar_expect_tx(full + stage, stage_bytes);
             }
-            for (int s = 0; s < 3; ++s) {
-                unsigned char* bt = st + a_bytes + s * b_bytes;
-                for (int half = 0; half < 2; ++half) {
-                    tma_load_4d(bt + half * kWgBox, &tmX_hi, full + stage, nt * 128 + half * 64, s - 1, h0 + r - 1, b);
-                    if (p.terms != 1) tma_load_4d(bt + (2 + half) * kWgBox, &tmX_lo, full + stage, nt * 128 + half * 64, s - 1, h0 + r - 1, b);
-                }
+            __syncwarp();
+            if (mine) {
+                unsigned char* st = smem + stage * stage_bytes;
+                if (is_y) tma_load_4d(st + dst_off, tm, full + stage, c_first, 0, h0, b);
+                else tma_load_4d(st + dst_off, tm, full + stage, c_first, s - 1, h0 + r - 1, b);
             }
+            if (++hb == p.hblocks_per_img) { hb = 0; ++b; }
             if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1 && lane == 0) {
