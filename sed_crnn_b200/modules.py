@@ -52,7 +52,8 @@ class _CRNNFunction(torch.autograd.Function):
         eng._last_seed = ctx.seed
         dx = torch.empty_like(ctx.x) if ctx.needs_input_grad[1] else None
         eng.backward(ctx.x, dlogits.contiguous(), dx=dx)
-        flat = eng.grads.clone()
+        flat = eng.grads.clone()                      # autograd owns what it is handed; the engine buffer is reused
+        module._last_flat_grad = flat                 # FusedClipAdam recognises gradients that still alias this buffer
         grads = []
         for (name, shape, off, sub) in module._slots:
             n = int(np.prod(shape))
@@ -350,6 +351,33 @@ class FusedClipAdam(torch.optim.Optimizer):
         g = self.param_groups[0]
         eng.lr, eng.betas, eng.eps, eng.weight_decay = g["lr"], g["betas"], g["eps"], g["weight_decay"]
         eng.clip = float(self.max_norm) if self.max_norm else 0.0
+        # Fast path: after zero_grad(set_to_none=True) + one backward, autograd adopted the views of the flat gradient
+        # buffer the backward pass returned -- every p.grad still sits at its offset of that buffer, so the buffer IS
+        # the flat gradient and no per-tensor copies are needed.  Anything else (accumulated gradients, hooks that
+        # replaced a gradient, a missing one) takes the general route.
+        flat = getattr(self.module, "_last_flat_grad", None)
+        aliased = flat is not None and flat.device == eng.grads.device
+        if aliased:
+            base = flat.data_ptr()
+            for (p, cname, sub), (_, shape, off, _) in zip(self.module._param_slots, self.module._slots):
+                g = p.grad
+                if g is None or not g.is_contiguous():
+                    aliased = False
+                    break
+                n = 1
+                for d in shape:
+                    n *= d
+                want = base + 4 * (off + (sub * (n // shape[0]) if sub is not None else 0))
+                if g.data_ptr() != want:
+                    aliased = False
+                    break
+        if aliased:
+            keep, eng.grads = eng.grads, flat
+            try:
+                eng.optimizer_step(1)
+            finally:
+                eng.grads = keep
+            return None
         views = eng.views(eng.grads)
         eng.grads.zero_()
         for (p, cname, sub) in self.module._param_slots:

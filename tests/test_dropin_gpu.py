@@ -216,3 +216,33 @@ def test_fused_clip_adam_state_round_trips_through_a_checkpoint(mods):
         step(b, ob, xb, yb)
     for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
         assert ka == kb and torch.equal(va, vb), ka
+
+
+def test_fused_clip_adam_fast_path_equals_general_route(mods):
+    """FusedClipAdam skips the per-tensor gradient copies when every p.grad still aliases the flat buffer the backward
+    pass returned; cloning the gradients first forces the general route -- both must produce the same parameters."""
+    _, sed, modules = mods
+    g = torch.Generator().manual_seed(5)
+    data = [(torch.randn(8, 1, 40, 64, generator=g).cuda(), (torch.rand(8, 8, 1, generator=g) < 0.2).float().cuda())
+            for _ in range(3)]
+    loss_fn = sed.BCEWithLogitsLoss()
+    outs = []
+    for force_general in (False, True):
+        torch.manual_seed(0)
+        m = sed.TimePooledCRNN(conv_channels=32, dropout=0.0).cuda().train()
+        opt = modules.FusedClipAdam(m, lr=1e-3, weight_decay=1e-4, max_norm=1.0)
+        took_fast = []
+        for xb, yb in data:
+            opt.zero_grad()
+            loss_fn(m(xb), yb).backward()
+            flat = m._last_flat_grad
+            took_fast.append(all(p.grad is not None and flat.data_ptr() <= p.grad.data_ptr() < flat.data_ptr() + 4 * flat.numel()
+                                 for p in m.parameters()))
+            if force_general:
+                for p in m.parameters():
+                    p.grad = p.grad.clone()
+            opt.step()
+        outs.append((took_fast, {k: v.clone() for k, v in m.state_dict().items()}))
+    assert all(outs[0][0]), "autograd did not adopt the returned gradient views: the fast path is never taken"
+    for k in outs[0][1]:
+        assert torch.equal(outs[0][1][k], outs[1][1][k]), k

@@ -91,3 +91,21 @@ def test_p2p_silent_peer_aborts_the_step_and_raises(built_lib, monkeypatch):
     xch.world = 1
     xch.close()
     L.sedb200_p2p_region_free(fake)
+
+
+def test_two_gpu_exchange_against_virtual_replica_oracle(built_lib):
+    """tests/mgpu_check.py under torchrun when the box has at least two GPUs (skipped on a single-GPU box): ranks
+    bit-identical, fused NVLink kernel == NCCL path, both == the 2-virtual-replica CPU oracle after one step."""
+    import json
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(29700 + os.getpid() % 200),
+                        os.path.join(root, "tests", "mgpu_check.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{") and '"verdict"' in l][-1]
+    assert json.loads(line)["verdict"] == "PASS"
