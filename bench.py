@@ -394,7 +394,7 @@ def other_configs_leg(torch, config, engine, main_config):
             continue
         try:
             cfg = config.PRESETS[name]
-            eng = engine.CRNNEngine(cfg, loss="bce", lr=1e-3, weight_decay=1e-4, clip=1.0, seed=99)
+            eng = engine.CRNNEngine(cfg, loss="bce", lr=1e-3, weight_decay=1e-4, clip=1.0, seed=99, cuda_graph=True)
             eng.init_default(seed=0)
             g = torch.Generator(device="cuda").manual_seed(5)
             x = torch.randn(cfg.input_shape(B), device="cuda", generator=g)
@@ -650,9 +650,10 @@ def run_ours(args, rank, world, local_rank):
     # gradient exchange: the fused NVLink peer-memory kernel when there is more than one rank ("auto"); if its
     # set-up fails (agreed on by all ranks) the run uses NCCL and SAYS so in config.grad_exchange
     gx_mode, gx_note = ("nccl" if world == 1 else "p2p") if args.grad_exchange == "auto" else args.grad_exchange, None
+    use_graph = not args.no_cuda_graph and (world == 1 or gx_mode == "p2p")
     try:
         eng = engine.CRNNEngine(cfg, loss="bce", lr=1e-3, weight_decay=1e-4, clip=1.0, seed=1234 + rank,
-                                grad_exchange=gx_mode)
+                                grad_exchange=gx_mode, cuda_graph=use_graph)
     except RuntimeError as e:
         if gx_mode != "p2p" or args.grad_exchange == "p2p":
             raise
@@ -679,8 +680,12 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
         sampler.wait_first()
-    for i in range(max(args.warmup, 3)):
+    n_warm = max(args.warmup, 3)
+    for i in range(n_warm):
         eng.train_step(xs[i % n_in], ys[i % n_in])
+    if use_graph:                                    # untimed: one more pass so that every rotated batch has its graph
+        for i in range(n_warm, n_warm + n_in + 1):
+            eng.train_step(xs[i % n_in], ys[i % n_in])
     barrier()
 
     # ---- timed region: device-resident inputs.  A block = EXACTLY args.steps steps between barriers, CUDA events,
@@ -689,7 +694,7 @@ def run_ours(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def timed_block():
-        l0 = L.sedb200_launch_count()
+        l0 = L.sedb200_launch_count() + eng.graph_replays * eng.launches_per_graph_step
         barrier()
         e0.record()
         for i in range(args.steps):
@@ -699,12 +704,15 @@ def run_ours(args, rank, world, local_rank):
         t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.item(), L.sedb200_launch_count() - l0, loss_
+        return t.item(), L.sedb200_launch_count() + eng.graph_replays * eng.launches_per_graph_step - l0, loss_
 
     t_clk0 = sampler.mark()
     first_ms, launches, loss = timed_block()
     n_blocks = max(1, min(200, int(-(-args.min_timed_s * 1e3 // max(first_ms, 1e-3)))))
-    block_ms = [first_ms] + [timed_block()[0] for _ in range(n_blocks - 1)]
+    block_ms = [first_ms]
+    for _ in range(n_blocks - 1):
+        bm, launches, loss = timed_block()
+        block_ms.append(bm)
     ms_step = sorted(block_ms)[len(block_ms) // 2] / args.steps
     frames_per_step = B * cfg.seq_len * world
     value = frames_per_step / (ms_step * 1e-3)
@@ -760,12 +768,12 @@ def run_ours(args, rank, world, local_rank):
             Bf = 1024 // world
             cfg4 = config.PRESETS["c1"]
             eng4 = engine.CRNNEngine(cfg4, loss="bce", lr=1e-3, weight_decay=1e-4, clip=1.0, seed=4321 + rank,
-                                     grad_exchange=gx_mode)
+                                     grad_exchange=gx_mode, cuda_graph=use_graph)
             eng4.init_default(seed=0)
             g4 = torch.Generator(device="cuda").manual_seed(200 + rank)
             x4 = [torch.randn(cfg4.input_shape(Bf), device="cuda", generator=g4) for _ in range(2)]
             y4 = [(torch.rand(cfg4.target_shape(Bf), device="cuda", generator=g4) < 0.2).float() for _ in range(2)]
-            for i in range(3):
+            for i in range(7):                          # eager first call + one graph per (batch, parity)
                 eng4.train_step(x4[i % 2], y4[i % 2])
             n4 = 10
             barrier()
@@ -790,6 +798,7 @@ def run_ours(args, rank, world, local_rank):
             fixed = {"error": str(e)[:200]}
 
     # ---- phase breakdown (extra instrumented steps, CUDA events on the launching stream)
+    eng.cuda_graph = False                              # the phase profiler brackets individual launches: eager steps
     L.sedb200_prof_enable(1)
     prof_steps = 3
     for i in range(prof_steps):
@@ -880,6 +889,9 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": workload_name(args.config, world), "per_gpu_batch": B, "global_batch": B * world,
                    "seq_len": cfg.seq_len, "parallelism": f"dp{world}", "l2": "per-step working set (>1 GB of "
                    "activations) exceeds the 126 MB L2; 4 input batches rotated",
+                   "cuda_graph": (f"the step is ONE CUDA-graph launch ({eng.launches_per_graph_step} kernels per replay, "
+                                  f"{eng.graph_replays} replays so far); seed / Adam step live in a device-side step state"
+                                  if eng.graph_replays else "off (eager launches)"),
                    "timing": f"{len(block_ms)} blocks of {args.steps} steps (>= {args.min_timed_s} s timed), median block; "
                              f"block ms min/median/max = {min(block_ms):.3f}/{sorted(block_ms)[len(block_ms) // 2]:.3f}/"
                              f"{max(block_ms):.3f}", "loss": "bce", "optimizer":
@@ -933,6 +945,7 @@ def main():
     ap.add_argument("--min-timed-s", type=float, default=0.5, help="repeat the --steps block until this much is timed")
     ap.add_argument("--no-library-baseline", action="store_true", help="skip the PyTorch-eager-on-GPU bar")
     ap.add_argument("--no-dropin", action="store_true", help="skip the drop-in-interface end-to-end leg")
+    ap.add_argument("--no-cuda-graph", action="store_true", help="launch every kernel of the step eagerly (N = 1)")
     ap.add_argument("--no-fixed-global", action="store_true", help="skip the fixed-global-batch-1024 (configs[3]) point")
     ap.add_argument("--grad-exchange", default="auto", choices=["auto", "nccl", "p2p"])
     ap.add_argument("--clock-period-ms", type=int, default=20, help="nvidia-smi sampling period during the run")

@@ -240,6 +240,37 @@ int sedb200_clip_adam(float* params_dev, const float* grads_dev, float* exp_avg_
                       void* scratch_dev, size_t scratch_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Whole training steps in a CUDA graph.  Two things change from step to step besides the data: the dropout seed and
+ * Adam's bias corrections (crnn_lightning.py:195-197: torch.optim.Adam's `step`).  Passed by value they would be frozen
+ * into a captured graph, so the *_s variants read them from a 32-byte device-side step state instead:
+ *   { u64 seed; i64 step; f32 bias_correction1; f32 sqrt(bias_correction2); 8 pad bytes }
+ * sedb200_step_state_init sets the number of completed steps; sedb200_step_advance (the first node of a captured step)
+ * does  step += 1; seed = base_seed + step - 1; corrections for `step`  -- exactly the values the by-value entry points
+ * are given by the host loop, so a replayed graph and an eager step are bit-identical.
+ * Everything the step enqueues (the library's helper stream included: it is forked from and joined to `stream` with
+ * events) is capturable; no entry point synchronises or allocates. */
+size_t sedb200_step_state_bytes(void);
+int sedb200_step_state_init(void* step_state_dev, long completed_steps, void* stream);
+int sedb200_step_advance(void* step_state_dev, unsigned long long base_seed, float beta1, float beta2, void* stream);
+int sedb200_crnn_forward_s(const sedb200_crnn_desc* d, const float* params_dev, float* bn_state_dev,
+                           const float* x_dev, int batch, int training, const void* step_state_dev,
+                           void* ws_dev, size_t ws_bytes, float* logits_dev, void* stream);
+int sedb200_crnn_backward_s(const sedb200_crnn_desc* d, const float* params_dev, const float* x_dev,
+                            int batch, const void* step_state_dev, void* ws_dev, size_t ws_bytes,
+                            const float* dlogits_dev, float* grads_dev, float* dx_dev, void* stream);
+int sedb200_clip_adam_s(float* params_dev, const float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev,
+                        long n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                        const void* step_state_dev, float max_norm, float grad_prescale, float* gnorm_dev,
+                        void* scratch_dev, size_t scratch_bytes, void* stream);
+/* the fused NVLink exchange step (below) for captured steps: exchange number == step of the state, `parity` = that
+ * step & 1 is fixed per captured graph (capture one graph per parity and alternate them) */
+int sedb200_p2p_allreduce_clip_adam_s(void* const* regions_host, int world, int rank, long n, int parity,
+                                      const void* step_state_dev, float* params_dev, float* exp_avg_dev,
+                                      float* exp_avg_sq_dev, float* reduced_dev, float lr, float beta1, float beta2,
+                                      float eps, float weight_decay, float max_norm, float grad_prescale,
+                                      float* gnorm_dev, void* scratch_dev, size_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Data-parallel exchange step as ONE kernel over NVLink peer memory (single node, one process per GPU):
  * sum all-reduce of the flat gradient buffers of all ranks + global-norm clip + Adam, replacing
  * `dist.all_reduce(grads)` followed by sedb200_clip_adam (train_lightning.py:50, crnn_lightning.py:195-197).

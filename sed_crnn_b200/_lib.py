@@ -61,6 +61,12 @@ SIGNATURES = {
     "sedb200_gru_scan_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "sedb200_clip_adam_scratch_bytes": (_sz, [_l]),
     "sedb200_clip_adam": (_i, [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _l, _f, _f, _p, _p, _sz, _p]),
+    "sedb200_step_state_bytes": (_sz, []),
+    "sedb200_step_state_init": (_i, [_p, _l, _p]),
+    "sedb200_step_advance": (_i, [_p, C.c_ulonglong, _f, _f, _p]),
+    "sedb200_crnn_forward_s": (_i, [_p, _p, _p, _p, _i, _i, _p, _p, _sz, _p, _p]),
+    "sedb200_crnn_backward_s": (_i, [_p, _p, _p, _i, _p, _p, _sz, _p, _p, _p, _p]),
+    "sedb200_clip_adam_s": (_i, [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _p, _f, _f, _p, _p, _sz, _p]),
     "sedb200_p2p_region_bytes": (_sz, [_l]),
     "sedb200_p2p_grad_offset_bytes": (_l, [_l, _i]),
     "sedb200_p2p_region_alloc": (_i, [_sz, _p, _p]),
@@ -72,6 +78,8 @@ SIGNATURES = {
     "sedb200_p2p_status_offset_bytes": (_l, []),
     "sedb200_p2p_allreduce_clip_adam": (_i, [_p, _i, _i, _l, _l, _l, _p, _p, _p, _p, _f, _f, _f, _f, _f, _f, _f, _p,
                                             _p, _sz, _p]),
+    "sedb200_p2p_allreduce_clip_adam_s": (_i, [_p, _i, _i, _l, _i, _p, _p, _p, _p, _p, _f, _f, _f, _f, _f, _f, _f, _p,
+                                              _p, _sz, _p]),
     "sedb200_threshold_counts": (_i, [_p, _p, _l, _i, _i, _f, _p, _p]),
     "sedb200_window_batch_f32": (_i, [_p, _p, _l, _i, _i, _i, _p, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "sedb200_clean_negatives": (_i, [_p, _l, _i, _i, _p, _p]),

@@ -315,7 +315,7 @@ conv0_lean_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
             Keep4 kp;
 #pragma unroll
             for (int q = 0; q < 4; ++q) kp.k[q] = true;
-            if (g.drop_p > 0.0f) kp = dropout_keep4(g.seed, (unsigned long long)i, g.drop_p);
+            if (g.drop_p > 0.0f) kp = dropout_keep4(pool_seed(g), (unsigned long long)i, g.drop_p);
             float m[4];
             unsigned word = 0;
 #pragma unroll
@@ -686,7 +686,7 @@ conv0_tc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, co
             Keep4 kp;
 #pragma unroll
             for (int qq = 0; qq < 4; ++qq) kp.k[qq] = true;
-            if (g.drop_p > 0.0f) kp = dropout_keep4(g.seed, (unsigned long long)i, g.drop_p);
+            if (g.drop_p > 0.0f) kp = dropout_keep4(pool_seed(g), (unsigned long long)i, g.drop_p);
             float m[4];
             unsigned word = 0;
 #pragma unroll

@@ -249,7 +249,7 @@ conv0_win_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
                         Keep4 kp;
 #pragma unroll
                         for (int qq = 0; qq < 4; ++qq) kp.k[qq] = true;
-                        if (g.drop_p > 0.0f) kp = dropout_keep4(g.seed, (unsigned long long)i, g.drop_p);
+                        if (g.drop_p > 0.0f) kp = dropout_keep4(pool_seed(g), (unsigned long long)i, g.drop_p);
                         float mv[4];
                         unsigned word = 0;
 #pragma unroll

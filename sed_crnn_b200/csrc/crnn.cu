@@ -212,7 +212,7 @@ bn_relu_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ s
             m.w = fmaxf(m.w, fmaf(v.w, sc.w, sh.w));
         }
         if (g.drop_p > 0.0f) {
-            const Keep4 kp = dropout_keep4(g.seed, (unsigned long long)i, g.drop_p);
+            const Keep4 kp = dropout_keep4(pool_seed(g), (unsigned long long)i, g.drop_p);
             m.x = kp.k[0] ? m.x * keep_scale : 0.0f;
             m.y = kp.k[1] ? m.y * keep_scale : 0.0f;
             m.z = kp.k[2] ? m.z * keep_scale : 0.0f;
@@ -260,7 +260,7 @@ bn_relu_pool_fwd_t_kernel(const float* __restrict__ y, const float* __restrict__
         }
         const long i = (long)pix * C4 + c4;                        // same element numbering as the generic kernel
         if (g.drop_p > 0.0f) {
-            const Keep4 kp = dropout_keep4(g.seed, (unsigned long long)i, g.drop_p);
+            const Keep4 kp = dropout_keep4(pool_seed(g), (unsigned long long)i, g.drop_p);
             m.x = kp.k[0] ? m.x * keep_scale : 0.0f;
             m.y = kp.k[1] ? m.y * keep_scale : 0.0f;
             m.z = kp.k[2] ? m.z * keep_scale : 0.0f;
@@ -300,7 +300,7 @@ __device__ __forceinline__ WindowGrad window_grad(const float* __restrict__ src,
     }
     const float keep_scale = g.drop_p > 0.0f ? 1.0f / (1.0f - g.drop_p) : 1.0f;
     Keep4 kp;
-    if (g.drop_p > 0.0f) kp = dropout_keep4(g.seed, (unsigned long long)i, g.drop_p);
+    if (g.drop_p > 0.0f) kp = dropout_keep4(pool_seed(g), (unsigned long long)i, g.drop_p);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         float gq = __ldg(dA + q * g.oC);
@@ -336,7 +336,7 @@ __device__ __forceinline__ void eval_window(const float4 (&v)[P], const float (&
     }
     const float keep_scale = g.drop_p > 0.0f ? 1.0f / (1.0f - g.drop_p) : 1.0f;
     Keep4 kp;
-    if (g.drop_p > 0.0f) kp = dropout_keep4(g.seed, (unsigned long long)i, g.drop_p);
+    if (g.drop_p > 0.0f) kp = dropout_keep4(pool_seed(g), (unsigned long long)i, g.drop_p);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         float t = gq[q];
@@ -1066,8 +1066,10 @@ inline int reduce_bias_partials(const float* part_b, float* dbih, float* dbhh, i
 
 inline int ew_blocks(long n) { return (int)std::min<long>((n + 255) / 256, 148L * 16); }
 
-PoolGeom pool_geom(const Plan& P, const sedb200_crnn_desc* d, int i, int training, unsigned long long seed) {
+PoolGeom pool_geom(const Plan& P, const sedb200_crnn_desc* d, int i, int training, unsigned long long seed,
+                   const unsigned long long* seed_ptr = nullptr) {
     PoolGeom g;
+    g.seed_ptr = seed_ptr; g.block = i;
     g.H = P.H; g.W = P.win[i]; g.Wo = P.wout[i]; g.C = P.C; g.p = P.pool[i];
     const bool last = (i == P.n_conv - 1);
     if (!last) {
@@ -1132,7 +1134,7 @@ dropout_mask_kernel(unsigned char* __restrict__ mask, long n_vec, PoolGeom g) {
         Keep4 kp;
 #pragma unroll
         for (int q = 0; q < 4; ++q) kp.k[q] = true;
-        if (g.drop_p > 0.0f) kp = dropout_keep4(g.seed, (unsigned long long)i, g.drop_p);
+        if (g.drop_p > 0.0f) kp = dropout_keep4(pool_seed(g), (unsigned long long)i, g.drop_p);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
             mask[((b * g.C + (c4 * 4 + q)) * g.H + h) * g.Wo + wo] = kp.k[q] ? 1 : 0;
@@ -1145,9 +1147,9 @@ using namespace sedb200;
 
 extern "C" {
 
-int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float* bn_state, const float* x,
-                         int batch, int training, unsigned long long seed, void* ws, size_t ws_bytes,
-                         float* logits, void* stream) {
+static int crnn_forward_impl(const sedb200_crnn_desc* d, const float* params, float* bn_state, const float* x,
+                             int batch, int training, unsigned long long seed, const unsigned long long* seed_ptr,
+                             void* ws, size_t ws_bytes, float* logits, void* stream) {
     Plan P;
     int rc = make_plan(d, batch, &P);
     if (rc) return rc;
@@ -1232,7 +1234,7 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
                 }
             }
             SED_PROF("conv0.fwd_fused", st);
-            const PoolGeom g = pool_geom(P, d, 0, training, seed);
+            const PoolGeom g = pool_geom(P, d, 0, training, seed, seed_ptr);
             const bool to_planes = (P.n_conv > 1) && P.conv_tc_all[1];
             __nv_bfloat16* ph = to_planes ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(ws) + P.actp[0]) : nullptr;
             __nv_bfloat16* pl = to_planes ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(ws) + P.actp[0] + P.act_plane_bytes[0]) : nullptr;
@@ -1292,7 +1294,7 @@ int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float*
         }
         SED_POST_LAUNCH();
         }
-        const PoolGeom g = pool_geom(P, d, i, training, seed);
+        const PoolGeom g = pool_geom(P, d, i, training, seed, seed_ptr);
         const long n_vec = B * P.H * P.wout[i] * (P.C / 4);
 { char _nm[40]; snprintf(_nm, sizeof _nm, "pool%d.fwd", i); SED_PROF(_nm, st);
         {
@@ -1387,9 +1389,9 @@ int sedb200_crnn_head_fwd_bwd(const sedb200_crnn_desc* d, const float* params, i
                           logits, probs, loss, wsf(ws, P.dseq[0]), grads, wsf(ws, P.part), st);
 }
 
-int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const float* x, int batch,
-                          unsigned long long seed, void* ws, size_t ws_bytes, const float* dlogits,
-                          float* grads, float* dx, void* stream) {
+static int crnn_backward_impl(const sedb200_crnn_desc* d, const float* params, const float* x, int batch,
+                              unsigned long long seed, const unsigned long long* seed_ptr, void* ws, size_t ws_bytes,
+                              const float* dlogits, float* grads, float* dx, void* stream) {
     Plan P;
     int rc = make_plan(d, batch, &P);
     if (rc) return rc;
@@ -1593,7 +1595,7 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         ~SideJoin() { for (int i = 0; s && i < 2; ++i) if (busy[i]) cudaStreamWaitEvent(st, s->done[i], 0); }
     } side_join{side, side_busy, st};
     for (int i = P.n_conv - 1; i >= 0; --i) {
-        const PoolGeom g = pool_geom(P, d, i, 1, seed);
+        const PoolGeom g = pool_geom(P, d, i, 1, seed, seed_ptr);
         const float* y = wsf(ws, P.y[i]);
         const float* stat = wsf(ws, P.stat[i]);
         if (i == 0 && conv0_lean_ok(P.cin[0], P.C, P.pool[0], P.n_conv)) {
@@ -1762,6 +1764,31 @@ int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const
         }
     }
     return SEDB200_OK;
+}
+
+int sedb200_crnn_forward(const sedb200_crnn_desc* d, const float* params, float* bn_state, const float* x,
+                         int batch, int training, unsigned long long seed, void* ws, size_t ws_bytes,
+                         float* logits, void* stream) {
+    return crnn_forward_impl(d, params, bn_state, x, batch, training, seed, nullptr, ws, ws_bytes, logits, stream);
+}
+int sedb200_crnn_forward_s(const sedb200_crnn_desc* d, const float* params, float* bn_state, const float* x,
+                           int batch, int training, const void* step_state, void* ws, size_t ws_bytes,
+                           float* logits, void* stream) {
+    SED_REQUIRE(step_state, SEDB200_EINVAL, "crnn_forward_s: null step state");
+    return crnn_forward_impl(d, params, bn_state, x, batch, training, 0, reinterpret_cast<const unsigned long long*>(step_state),
+                             ws, ws_bytes, logits, stream);
+}
+int sedb200_crnn_backward(const sedb200_crnn_desc* d, const float* params, const float* x, int batch,
+                          unsigned long long seed, void* ws, size_t ws_bytes, const float* dlogits,
+                          float* grads, float* dx, void* stream) {
+    return crnn_backward_impl(d, params, x, batch, seed, nullptr, ws, ws_bytes, dlogits, grads, dx, stream);
+}
+int sedb200_crnn_backward_s(const sedb200_crnn_desc* d, const float* params, const float* x, int batch,
+                            const void* step_state, void* ws, size_t ws_bytes, const float* dlogits,
+                            float* grads, float* dx, void* stream) {
+    SED_REQUIRE(step_state, SEDB200_EINVAL, "crnn_backward_s: null step state");
+    return crnn_backward_impl(d, params, x, batch, 0, reinterpret_cast<const unsigned long long*>(step_state), ws, ws_bytes,
+                              dlogits, grads, dx, stream);
 }
 
 int sedb200_crnn_dropout_mask(const sedb200_crnn_desc* d, int batch, unsigned long long seed, int block,

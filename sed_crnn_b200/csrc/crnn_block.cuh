@@ -76,8 +76,15 @@ struct PoolGeom {
     int H, W, Wo, C, p;
     long oB, oH, oW, oC;         // strides of the block OUTPUT (channels-last, or the [B][T][flat] layout)
     float drop_p;                // 0 disables
-    unsigned long long seed;
+    unsigned long long seed;     // dropout seed of this block (block_seed(step seed, block))
+    // CUDA-graph steps: the step seed lives in device memory (sedb200_step_state) and is read at run time, so that a
+    // captured step draws fresh masks at every replay; null = use `seed`
+    const unsigned long long* seed_ptr;
+    int block;
 };
+__device__ __forceinline__ unsigned long long pool_seed(const PoolGeom& g) {
+    return g.seed_ptr ? block_seed(__ldg(g.seed_ptr), g.block) : g.seed;
+}
 
 __device__ __forceinline__ void load_dA(const float* __restrict__ da, long oC, float (&g)[4]) {
     if (oC == 1) {

@@ -79,7 +79,8 @@ __global__ void gnorm_final_kernel(const float* __restrict__ part, int nblk, flo
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
             float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float max_norm,
-            float prescale, const float* __restrict__ gnorm) {
+            float prescale, const float* __restrict__ gnorm, const float* __restrict__ bc_dev) {
+    if (bc_dev) { bc1 = __ldg(bc_dev); bc2_sqrt = __ldg(bc_dev + 1); }     // CUDA-graph steps: bias corrections of the device-side step
     float coef = prescale;
     if (max_norm > 0.0f) {
         const float c = max_norm / (gnorm[0] + 1e-6f);
@@ -97,6 +98,21 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
         const float denom = sqrtf(vi) / bc2_sqrt + eps;
         p[i] = w - step_size * (mi / denom);
     }
+}
+
+// ---- step state on the device (include/sedb200.h: sedb200_step_state): lets a whole training step be captured in a
+//      CUDA graph -- the dropout seed and Adam's bias corrections change every step, so they are read from memory.
+struct StepState { unsigned long long seed; long long step; float bc1, bc2_sqrt; float pad[2]; };
+static_assert(sizeof(StepState) == 32, "sedb200_step_state is 32 bytes");
+__global__ void step_state_init_kernel(StepState* s, long long step) {
+    s->seed = 0; s->step = step; s->bc1 = 1.0f; s->bc2_sqrt = 1.0f; s->pad[0] = s->pad[1] = 0.0f;
+}
+__global__ void step_advance_kernel(StepState* s, unsigned long long base_seed, float b1, float b2) {
+    const long long step = s->step + 1;
+    s->step = step;
+    s->seed = base_seed + (unsigned long long)(step - 1);
+    s->bc1 = (float)(1.0 - pow((double)b1, (double)step));
+    s->bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, (double)step));
 }
 
 // ---- threshold + counts.  counts: [0..5] frame TP,Nsys,Nref,S,D,I ; [6..11] block ; [12] block Nref (floor blocks)
@@ -174,11 +190,11 @@ int sedb200_loss_fwd_bwd(int kind, float alpha, float gamma, const float* logits
 
 size_t sedb200_clip_adam_scratch_bytes(long n) { (void)n; return (size_t)kRedBlocks * 4; }
 
-int sedb200_clip_adam(float* params, const float* grads, float* m, float* v, long n, float lr, float b1, float b2,
-                      float eps, float wd, long step, float max_norm, float prescale, float* gnorm, void* scratch,
-                      size_t scratch_bytes, void* stream) {
+static int clip_adam_impl(float* params, const float* grads, float* m, float* v, long n, float lr, float b1, float b2,
+                          float eps, float wd, long step, const void* step_state, float max_norm, float prescale,
+                          float* gnorm, void* scratch, size_t scratch_bytes, void* stream) {
     SED_REQUIRE(n >= 1 && params && grads && m && v && gnorm && scratch, SEDB200_EINVAL, "clip_adam: bad argument");
-    SED_REQUIRE(step >= 1, SEDB200_EINVAL, "clip_adam: step %ld (1-based)", step);
+    SED_REQUIRE(step >= 1 || step_state, SEDB200_EINVAL, "clip_adam: step %ld (1-based)", step);
     SED_REQUIRE(scratch_bytes >= sedb200_clip_adam_scratch_bytes(n), SEDB200_EWORKSPACE, "clip_adam: scratch too small");
     int rc = require_sm100();
     if (rc) return rc;
@@ -190,10 +206,43 @@ int sedb200_clip_adam(float* params, const float* grads, float* m, float* v, lon
     SED_POST_LAUNCH();
     gnorm_final_kernel<<<1, 32, 0, st>>>(part, nb, gnorm);
     SED_POST_LAUNCH();
-    const double bc1 = 1.0 - std::pow((double)b1, (double)step);
-    const double bc2 = 1.0 - std::pow((double)b2, (double)step);
+    const double bc1 = step_state ? 1.0 : 1.0 - std::pow((double)b1, (double)step);
+    const double bc2 = step_state ? 1.0 : 1.0 - std::pow((double)b2, (double)step);
+    const float* bc_dev = step_state ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(step_state) + 16) : nullptr;
     adam_kernel<<<nb, 256, 0, st>>>(params, grads, m, v, n, lr, b1, b2, eps, wd, (float)bc1, (float)std::sqrt(bc2),
-                                    max_norm, prescale, gnorm);
+                                    max_norm, prescale, gnorm, bc_dev);
+    SED_POST_LAUNCH();
+    return SEDB200_OK;
+}
+
+int sedb200_clip_adam(float* params, const float* grads, float* m, float* v, long n, float lr, float b1, float b2,
+                      float eps, float wd, long step, float max_norm, float prescale, float* gnorm, void* scratch,
+                      size_t scratch_bytes, void* stream) {
+    return clip_adam_impl(params, grads, m, v, n, lr, b1, b2, eps, wd, step, nullptr, max_norm, prescale, gnorm, scratch,
+                          scratch_bytes, stream);
+}
+int sedb200_clip_adam_s(float* params, const float* grads, float* m, float* v, long n, float lr, float b1, float b2,
+                        float eps, float wd, const void* step_state, float max_norm, float prescale, float* gnorm,
+                        void* scratch, size_t scratch_bytes, void* stream) {
+    SED_REQUIRE(step_state, SEDB200_EINVAL, "clip_adam_s: null step state");
+    return clip_adam_impl(params, grads, m, v, n, lr, b1, b2, eps, wd, 0, step_state, max_norm, prescale, gnorm, scratch,
+                          scratch_bytes, stream);
+}
+
+size_t sedb200_step_state_bytes(void) { return sizeof(StepState); }
+int sedb200_step_state_init(void* step_state, long step, void* stream) {
+    SED_REQUIRE(step_state && step >= 0, SEDB200_EINVAL, "step_state_init: bad argument");
+    int rc = require_sm100();
+    if (rc) return rc;
+    step_state_init_kernel<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<StepState*>(step_state), step);
+    SED_POST_LAUNCH();
+    return SEDB200_OK;
+}
+int sedb200_step_advance(void* step_state, unsigned long long base_seed, float b1, float b2, void* stream) {
+    SED_REQUIRE(step_state, SEDB200_EINVAL, "step_advance: null step state");
+    int rc = require_sm100();
+    if (rc) return rc;
+    step_advance_kernel<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<StepState*>(step_state), base_seed, b1, b2);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }

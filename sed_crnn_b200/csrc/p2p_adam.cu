@@ -46,6 +46,9 @@ struct P2PArgs {
     long n, buf_stride;                 // floats per gradient buffer (padded)
     float* params; float* m; float* v; float* reduced; float* part; float* gnorm;
     float lr, b1, b2, eps, wd, bc1, bc2_sqrt, max_norm, prescale;
+    // CUDA-graph steps: exchange number (= optimizer step) and Adam's bias corrections come from the device-side step
+    // state (sedb200_step_state: {u64 seed; i64 step; f32 bc1; f32 bc2_sqrt}); null = the by-value fields above
+    const unsigned long long* state;
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
@@ -71,16 +74,19 @@ p2p_reduce_clip_adam_kernel(const P2PArgs a) {
     __shared__ float s_coef;
     unsigned long long* my_flags = reinterpret_cast<unsigned long long*>(a.region[a.rank]);
     unsigned int* status = reinterpret_cast<unsigned int*>(a.region[a.rank] + kMaxWorld * 8);
+    const unsigned long long seq = a.state ? a.state[1] : a.seq;
+    const float bc1 = a.state ? reinterpret_cast<const float*>(a.state)[4] : a.bc1;
+    const float bc2_sqrt = a.state ? reinterpret_cast<const float*>(a.state)[5] : a.bc2_sqrt;
 
     // ---- 1. publish + wait (one thread per peer)
     if (threadIdx.x < a.world) {
         const int p = threadIdx.x;
         if (blockIdx.x == 0) {
             __threadfence_system();     // the backward kernels' gradient stores precede the flag, system-wide
-            st_release_sys(reinterpret_cast<unsigned long long*>(a.region[p]) + a.rank, a.seq);
+            st_release_sys(reinterpret_cast<unsigned long long*>(a.region[p]) + a.rank, seq);
         }
         const long long t0 = clock64();
-        while (ld_acquire_sys(my_flags + p) < a.seq) {
+        while (ld_acquire_sys(my_flags + p) < seq) {
             if (clock64() - t0 > a.timeout_cycles) {        // a peer died: raise the (sticky) status word -- no hang
                 atomicExch(status, 1u);
                 __threadfence();
@@ -137,7 +143,7 @@ p2p_reduce_clip_adam_kernel(const P2PArgs a) {
         }
     }
     __syncthreads();
-    const float coef = s_coef, step_size = a.lr / a.bc1;
+    const float coef = s_coef, step_size = a.lr / bc1;
 
     // ---- 4. Adam (same arithmetic, term for term, as adam_kernel in head_optim.cu)
     for (long i = (long)blockIdx.x * kThreads + threadIdx.x; i < n4; i += (long)gridDim.x * kThreads) {
@@ -156,7 +162,7 @@ p2p_reduce_clip_adam_kernel(const P2PArgs a) {
             const float vi = fmaf(a.b2, vs[k], (1.0f - a.b2) * grad * grad);
             ms[k] = mi;
             vs[k] = vi;
-            const float denom = sqrtf(vi) / a.bc2_sqrt + a.eps;
+            const float denom = sqrtf(vi) / bc2_sqrt + a.eps;
             ps[k] = w - step_size * (mi / denom);
         }
         reinterpret_cast<float4*>(a.params)[i] = p4;
@@ -225,11 +231,11 @@ long sedb200_p2p_status_offset_bytes(void) { return (long)kMaxWorld * 8; }
 
 size_t sedb200_p2p_scratch_bytes(void) { return 1024 * sizeof(float); }
 
-int sedb200_p2p_allreduce_clip_adam(void* const* regions_host, int world, int rank, long n, long seq, long step,
-                                    float* params_dev, float* exp_avg_dev, float* exp_avg_sq_dev,
-                                    float* reduced_dev, float lr, float beta1, float beta2, float eps,
-                                    float weight_decay, float max_norm, float grad_prescale, float* gnorm_dev,
-                                    void* scratch_dev, size_t scratch_bytes, void* stream) {
+static int p2p_impl(void* const* regions_host, int world, int rank, long n, long seq, long step, const void* step_state,
+                    float* params_dev, float* exp_avg_dev, float* exp_avg_sq_dev,
+                    float* reduced_dev, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, float max_norm, float grad_prescale, float* gnorm_dev,
+                    void* scratch_dev, size_t scratch_bytes, void* stream) {
     SED_REQUIRE(regions_host && world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, SEDB200_EINVAL,
                 "p2p_allreduce_clip_adam: world=%d rank=%d", world, rank);
     SED_REQUIRE(n % 4 == 0, SEDB200_ESHAPE, "p2p_allreduce_clip_adam: n=%ld is not a multiple of 4 floats", n);
@@ -245,6 +251,7 @@ int sedb200_p2p_allreduce_clip_adam(void* const* regions_host, int world, int ra
         a.region[r] = reinterpret_cast<unsigned char*>(regions_host[r]);
     }
     a.world = world; a.rank = rank; a.parity = (int)(seq & 1); a.seq = (unsigned long long)seq;
+    a.state = reinterpret_cast<const unsigned long long*>(step_state);
     a.n = pad4(n); a.buf_stride = buf_stride_floats(n);
     a.params = params_dev; a.m = exp_avg_dev; a.v = exp_avg_sq_dev; a.reduced = reduced_dev;
     a.part = reinterpret_cast<float*>(scratch_dev); a.gnorm = gnorm_dev;
@@ -268,6 +275,29 @@ int sedb200_p2p_allreduce_clip_adam(void* const* regions_host, int world, int ra
     SED_CUDA_OK(cudaLaunchCooperativeKernel((void*)p2p_reduce_clip_adam_kernel, dim3(grid), dim3(kThreads), kargs, 0, st));
     SED_POST_LAUNCH();
     return SEDB200_OK;
+}
+
+int sedb200_p2p_allreduce_clip_adam(void* const* regions_host, int world, int rank, long n, long seq, long step,
+                                    float* params_dev, float* exp_avg_dev, float* exp_avg_sq_dev,
+                                    float* reduced_dev, float lr, float beta1, float beta2, float eps,
+                                    float weight_decay, float max_norm, float grad_prescale, float* gnorm_dev,
+                                    void* scratch_dev, size_t scratch_bytes, void* stream) {
+    return p2p_impl(regions_host, world, rank, n, seq, step, nullptr, params_dev, exp_avg_dev, exp_avg_sq_dev, reduced_dev,
+                    lr, beta1, beta2, eps, weight_decay, max_norm, grad_prescale, gnorm_dev, scratch_dev, scratch_bytes, stream);
+}
+
+/* CUDA-graph variant: the exchange number (== optimizer step: one exchange per step since the state was initialised)
+ * and the bias corrections are read from the device-side step state; `parity` = (that step) & 1 selects the gradient
+ * buffers and is a property of the captured graph (capture one graph per parity and alternate). */
+int sedb200_p2p_allreduce_clip_adam_s(void* const* regions_host, int world, int rank, long n, int parity,
+                                      const void* step_state_dev, float* params_dev, float* exp_avg_dev,
+                                      float* exp_avg_sq_dev, float* reduced_dev, float lr, float beta1, float beta2,
+                                      float eps, float weight_decay, float max_norm, float grad_prescale,
+                                      float* gnorm_dev, void* scratch_dev, size_t scratch_bytes, void* stream) {
+    SED_REQUIRE(step_state_dev && (parity == 0 || parity == 1), SEDB200_EINVAL, "p2p_allreduce_clip_adam_s: bad argument");
+    return p2p_impl(regions_host, world, rank, n, 2 + parity, 1, step_state_dev, params_dev, exp_avg_dev, exp_avg_sq_dev,
+                    reduced_dev, lr, beta1, beta2, eps, weight_decay, max_norm, grad_prescale, gnorm_dev, scratch_dev,
+                    scratch_bytes, stream);
 }
 
 }  // extern "C"

@@ -23,7 +23,7 @@ LOSS_KINDS = {"bce": 0, "focal": 1}
 class CRNNEngine:
     def __init__(self, cfg: CRNNConfig, device="cuda", *, loss="focal", alpha=0.25, gamma=2.0,
                  lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, clip=1.0, seed=0,
-                 process_group=None, grad_exchange: str = "nccl"):
+                 process_group=None, grad_exchange: str = "nccl", cuda_graph: bool = False):
         self.cfg = cfg
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -56,6 +56,15 @@ class CRNNEngine:
         self._ws_batch = 0
         self._bufs = {}
         self._last_seed = self.seed
+        # cuda_graph: single-process train_step calls are captured once per (input buffers, hyper-parameters) and
+        # replayed; the per-step dropout seed and Adam bias corrections live in a device-side step state
+        self.cuda_graph = bool(cuda_graph)
+        self._graphs = {}
+        self._graph_misses = 0
+        self._step_state = torch.zeros(int(self.L.sedb200_step_state_bytes()) // 8, dtype=torch.int64, device=self.device)
+        self._state_step = 0                        # the step counter the device-side state holds
+        self.graph_replays = 0
+        self.launches_per_graph_step = 0
         # "nccl": dist.all_reduce + clip_adam kernels;  "p2p": one fused kernel over NVLink peer memory
         if grad_exchange not in ("nccl", "p2p"):
             raise ValueError("grad_exchange must be 'nccl' or 'p2p'")
@@ -228,9 +237,14 @@ class CRNNEngine:
     def train_step(self, x: torch.Tensor, y: torch.Tensor):
         """One optimisation step on device-resident (x, y).  Returns (loss, probs) as device tensors
         (views of engine-owned buffers, valid until the next call)."""
-        if self.xch is None and self.fused_head and x.is_contiguous() and y.is_contiguous():
+        if self.fused_head and x.is_contiguous() and y.is_contiguous():
             from . import parallel
-            if parallel.world_info(self.pg)[1] == 1:
+            single = self.xch is None and parallel.world_info(self.pg)[1] == 1
+            if (single or self.xch is not None) and self.cuda_graph and self._ws is not None and self._ws_batch == x.shape[0]:
+                out = self._train_step_graph(x, y)     # (the first call per batch size runs eagerly)
+                if out is not None:
+                    return out
+            if single:
                 return self._train_step_single(x, y)
         if self.xch is not None:
             self.grads = self.xch.next_grad_buffer()                  # this step's half of the exchange region
@@ -254,6 +268,77 @@ class CRNNEngine:
         world = round(1.0 / scale)
         self.optimizer_step(world)
         return loss, probs
+
+    def _train_step_graph(self, x, y):
+        """The single-process step as a CUDA graph: captured once per (x, y buffers, batch, hyper-parameters), then ONE
+        launch per step.  Bit-identical to the eager step: the graph's first node advances the device-side step state
+        to exactly the seed / bias corrections the eager path passes by value."""
+        B = x.shape[0]
+        xch = self.xch
+        if xch is not None and xch.seq != self.step_count:
+            return None                                # exchange number and optimizer step must move together
+        parity = (self.step_count + 1) & 1 if xch is not None else 0
+        gbuf = xch.grad_bufs[parity] if xch is not None else self.grads
+        key = (x.data_ptr(), y.data_ptr(), B, self.lr, self.betas, self.eps, self.weight_decay, self.clip,
+               float(self.desc.dropout), self.loss_kind, self.alpha, self.gamma, self.params.data_ptr(), gbuf.data_ptr())
+        L, desc = self.L, C.byref(self.desc)
+        if self._state_step != self.step_count:       # eager steps / reset_optimizer moved the host counter
+            with torch.cuda.device(self.device):
+                _lib.check(L.sedb200_step_state_init(self._step_state.data_ptr(), self.step_count, _lib.current_stream_ptr()))
+            self._state_step = self.step_count
+        entry = self._graphs.get(key)
+        if entry is None:
+            if len(self._graphs) >= 16 or self._graph_misses >= 64:
+                return None                            # inputs arrive in ever-new buffers: stay eager
+            self._graph_misses += 1
+            x = self._check_x(x)
+            shape = self.cfg.target_shape(B)
+            if tuple(y.shape) != tuple(shape) or y.dtype != torch.float32 or not y.is_cuda:
+                raise ValueError("targets must be CUDA float32 with the logits' shape")
+            ws = self._workspace(B)
+            logits, probs = self._buf(("logits", B), shape), self._buf(("probs", tuple(shape)), shape)
+            p_state = self._step_state.data_ptr()
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(self.device)
+            l0 = L.sedb200_launch_count()
+            with torch.cuda.device(self.device), torch.cuda.graph(graph):
+                st = _lib.current_stream_ptr()
+                _lib.check(L.sedb200_step_advance(p_state, self.seed, self.betas[0], self.betas[1], st))
+                _lib.check(L.sedb200_crnn_forward_s(desc, self.params.data_ptr(), self.bn_state.data_ptr(), x.data_ptr(), B, 1,
+                                                    p_state, ws.data_ptr(), ws.numel(), None, st))
+                _lib.check(L.sedb200_crnn_head_fwd_bwd(desc, self.params.data_ptr(), B, ws.data_ptr(), ws.numel(),
+                                                       y.data_ptr(), self.loss_kind, self.alpha, self.gamma, 1.0,
+                                                       logits.data_ptr(), probs.data_ptr(), self._scalars.data_ptr(),
+                                                       gbuf.data_ptr(), st))
+                _lib.check(L.sedb200_crnn_backward_s(desc, self.params.data_ptr(), x.data_ptr(), B, p_state, ws.data_ptr(),
+                                                     ws.numel(), None, gbuf.data_ptr(), None, st))
+                if xch is None:
+                    _lib.check(L.sedb200_clip_adam_s(self.params.data_ptr(), gbuf.data_ptr(), self.exp_avg.data_ptr(),
+                                                     self.exp_avg_sq.data_ptr(), self.params.numel(), self.lr, self.betas[0],
+                                                     self.betas[1], self.eps, self.weight_decay, p_state, self.clip, 1.0,
+                                                     self._scalars.data_ptr() + 4, self._scratch.data_ptr(),
+                                                     self._scratch.numel() * 4, st))
+                else:                                   # fused NVLink exchange + clip + Adam, this parity's buffers
+                    _lib.check(L.sedb200_p2p_allreduce_clip_adam_s(
+                        xch.table, xch.world, xch.rank, xch.n, parity, p_state, self.params.data_ptr(),
+                        self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), xch.reduced.data_ptr(), self.lr, self.betas[0],
+                        self.betas[1], self.eps, self.weight_decay, self.clip, 1.0 / xch.world,
+                        self._scalars.data_ptr() + 4, xch.scratch.data_ptr(), xch.scratch.numel() * 4, st))
+            self.launches_per_graph_step = int(L.sedb200_launch_count() - l0)
+            entry = (graph, probs, ws, (x, y))            # the captured step reads these buffers: keep them alive
+            self._graphs[key] = entry
+        self._last_seed = self.seed + self.step_count
+        if xch is not None:
+            xch.raise_if_failed()
+        entry[0].replay()
+        if xch is not None:
+            xch.after_graph_exchange()
+            self.grads = xch.reduced
+        self.step_count += 1
+        self._state_step += 1
+        self.num_batches_tracked += 1
+        self.graph_replays += 1
+        return self._scalars[0], entry[1]
 
     def _train_step_single(self, x, y):
         """train_step for the common single-process case (fused head, no gradient exchange): the same four library

@@ -245,6 +245,15 @@ class P2PGradExchange:
             self._status_pending = True
         return self.reduced
 
+    def after_graph_exchange(self) -> None:
+        """Bookkeeping after a CUDA-graph replay that contained the exchange kernel (engine.CRNNEngine, cuda_graph=True):
+        the exchange number advances and the health word is copied out, exactly as allreduce_clip_adam does."""
+        self.seq += 1
+        with torch.cuda.device(self.device):
+            self._status_host.copy_(self._status_dev, non_blocking=True)
+            self._status_evt.record()
+            self._status_pending = True
+
     def status(self) -> int:
         """0 = healthy; non-zero = some peer failed to publish its gradients within the kernel's spin bound."""
         v = self.C.c_uint(0)

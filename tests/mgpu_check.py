@@ -108,6 +108,8 @@ def main():
     cfg = replace(config.PRESETS["c2"], dropout=0.0)
     B = 32
     engs = {k: engine.CRNNEngine(cfg, loss="bce", weight_decay=1e-4, clip=1.0, grad_exchange=k) for k in ("nccl", "p2p")}
+    # the same fused exchange with the whole step replayed from a CUDA graph (one graph per exchange parity)
+    engs["p2p_graph"] = engine.CRNNEngine(cfg, loss="bce", weight_decay=1e-4, clip=1.0, grad_exchange="p2p", cuda_graph=True)
     for e in engs.values():
         e.init_default(7)
     g = torch.Generator(device="cuda").manual_seed(100 + rank)
@@ -129,6 +131,10 @@ def main():
         # two ranks: a + b is the same sum in either order, so the two paths must agree bit for bit; more ranks: NCCL
         # adds in ring / tree order, the fused kernel in rank order -- gradients agree to rounding, and Adam may turn a
         # last-bit difference of a near-zero gradient into +-lr, so the weights are only required to stay close
+        graph_same = torch.equal(engs["p2p_graph"].params, p)
+        if rank == 0 and not graph_same:
+            print(f"step {i}: CUDA-graph replay differs from the eager fused exchange")
+        ok &= graph_same
         if world == 2:
             ok &= same and diff == 0.0 and gd == 0.0
         else:
@@ -149,10 +155,13 @@ def main():
         t = torch.tensor([e0.elapsed_time(e1) / 30], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         times[k] = t.item()
+    replays = engs["p2p_graph"].graph_replays
+    ok &= replays > 0
+    engs["p2p_graph"].xch.close()
     st = engs["p2p"].xch.status()
     if rank == 0:
         good = bool(ok) and st == 0 and orc["oracle_ok"]
-        print(json.dumps({"world": world, "ok": good, "verdict": "PASS" if good else "FAIL", "ranks_identical_and_paths_agree": bool(ok),
+        print(json.dumps({"world": world, "ok": good, "verdict": "PASS" if good else "FAIL", "ranks_identical_and_paths_agree": bool(ok), "cuda_graph_replays": replays,
                           "vs_virtual_replica_oracle": orc, "p2p_status": st, "ms_per_step": times,
                           "batch_per_gpu": B, "n_params": int(engs["p2p"].params.numel())}))
     dist.barrier()

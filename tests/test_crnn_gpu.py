@@ -341,3 +341,35 @@ def test_lean_block0_with_dropout_matches_general_route(pkg, tc, tol):
     # and the mask is really applied: a second forward with another seed gives different logits
     other = eng.forward(x, training=True, seed=12345).clone()
     assert not torch.equal(other, logits)
+
+
+def test_cuda_graph_steps_are_bit_identical_to_eager_steps(pkg):
+    """CRNNEngine(cuda_graph=True) captures the single-process step once per input buffer pair and replays it; the
+    dropout seed and Adam's bias corrections come from the device-side step state (sedb200_step_advance), so replays
+    must reproduce the eager steps bit for bit -- with dropout on, over rotating input buffers, and across an
+    interleaved eager call."""
+    config, engine = pkg
+    cfg = replace(config.C2, seq_len=32)
+    g = torch.Generator().manual_seed(4)
+    batches = [(torch.randn(cfg.input_shape(8), generator=g).cuda(), (torch.rand(cfg.target_shape(8), generator=g) < 0.2).float().cuda())
+               for _ in range(3)]
+    runs = {}
+    for mode in (False, True):
+        eng = engine.CRNNEngine(cfg, loss="bce", weight_decay=1e-4, clip=1.0, seed=21, cuda_graph=mode)
+        eng.init_default(5)
+        losses = []
+        for it in range(9):
+            x, y = batches[it % 3]
+            if it == 6:                                         # an eager-only API call in between moves nothing
+                eng.predict_proba(x)
+            loss, probs = eng.train_step(x, y)
+            losses.append(loss.item())
+        runs[mode] = (losses, eng.params.clone(), eng.exp_avg_sq.clone(), eng.bn_state.clone(), probs.clone(), eng)
+    assert runs[True][5].graph_replays >= 5 and runs[True][5].launches_per_graph_step > 20
+    assert runs[False][0] == runs[True][0]
+    for i in (1, 2, 3, 4):
+        assert torch.equal(runs[False][i], runs[True][i]), i
+    # masks of the last replayed step are the eager ones as well
+    m0 = runs[False][5].dropout_masks(8)
+    m1 = runs[True][5].dropout_masks(8)
+    assert all(torch.equal(a, b) for a, b in zip(m0, m1))
