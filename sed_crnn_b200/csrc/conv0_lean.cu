@@ -326,7 +326,7 @@ conv0_lean_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
             }
             const float4 m4 = make_float4(m[0], m[1], m[2], m[3]);
             if (argw) argw[i] = word;
-            if (out_hi) store_planes4(out_hi, out_lo, i, m4);
+            if (out_hi) store_planes4(out_hi, out_lo, pix, c4, C4, m4);
             if (out) {
                 float* dst = out + (long)b * g.oB + (long)h * g.oH + (long)wo * g.oW + (long)c * g.oC;
                 if (g.oC == 1) {
@@ -697,7 +697,7 @@ conv0_tc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, co
             }
             const float4 m4 = make_float4(m[0], m[1], m[2], m[3]);
             if (argw) argw[i] = word;
-            if (out_hi) store_planes4(out_hi, out_lo, i, m4);
+            if (out_hi) store_planes4(out_hi, out_lo, (long)q, c4, C4, m4);
             if (out) {
                 const unsigned bh = q / uWo, wo = q - bh * uWo, b = bh / uH, h = bh - b * uH;
                 float* dst = out + (long)b * g.oB + (long)h * g.oH + (long)wo * g.oW + (long)c * g.oC;

@@ -242,6 +242,7 @@ conv0_win_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
                     if (lane == 0) mbar_arrive(t_empty + gq);     // registers hold the tile: the accumulator is free
                 }
                 if (live) {
+                    float4 pend = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int mm = 0; mm < 2; ++mm) {
                         const int m = 2 * hf + mm;
@@ -266,7 +267,8 @@ conv0_win_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
                         }
                         words[m] = word;
                         const float4 m4 = make_float4(mv[0], mv[1], mv[2], mv[3]);
-                        if (out_hi) store_planes4(out_hi, out_lo, i, m4);
+                        if (mm == 0) pend = m4;
+                        else if (out_hi) store_planes8(out_hi, out_lo, (long)q, (c_first >> 2) + m - 1, C4, pend, m4);
                         if (out) {
                             const unsigned bh = q / uWo, wo = q - bh * uWo, b = bh / uH, h = bh - b * uH;
                             float* dst = out + (long)b * g.oB + (long)h * g.oH + (long)wo * g.oW + (long)(c_first + 4 * m) * g.oC;

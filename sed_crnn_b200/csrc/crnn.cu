@@ -218,7 +218,7 @@ bn_relu_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ s
             m.z = kp.k[2] ? m.z * keep_scale : 0.0f;
             m.w = kp.k[3] ? m.w * keep_scale : 0.0f;
         }
-        if (out_hi) store_planes4(out_hi, out_lo, i, m);        // channels-last planes: element index == 4*i
+        if (out_hi) store_planes4(out_hi, out_lo, i / C4, c4, C4, m);   // channels-last planes
         if (out) {
             float* dst = out + b * g.oB + h * g.oH + wo * g.oW + c * g.oC;
             if (g.oC == 1) {
@@ -266,7 +266,7 @@ bn_relu_pool_fwd_t_kernel(const float* __restrict__ y, const float* __restrict__
             m.z = kp.k[2] ? m.z * keep_scale : 0.0f;
             m.w = kp.k[3] ? m.w * keep_scale : 0.0f;
         }
-        if (out_hi) store_planes4(out_hi, out_lo, i, m);
+        if (out_hi) store_planes4(out_hi, out_lo, (long)pix, c4, C4, m);
         if (out) {
             float* dst = out + (long)b * g.oB + (long)h * g.oH + (long)wo * g.oW + (long)c * g.oC;
             if (g.oC == 1) {
@@ -426,7 +426,7 @@ bn_bwd_sums_act_kernel(const float* __restrict__ act, const __nv_bfloat16* __res
         if (act) {
             load_dA(act + off, g.oC, av);
         } else {
-            const float4 t4 = load_planes4(act_hi, act_lo, (long)pix * C4 + c4);
+            const float4 t4 = load_planes4(act_hi, act_lo, (long)pix, c4, C4);
             av[0] = t4.x; av[1] = t4.y; av[2] = t4.z; av[3] = t4.w;
         }
         load_dA(dA + off, g.oC, gq);
@@ -1180,8 +1180,10 @@ static int crnn_forward_impl(const sedb200_crnn_desc* d, const float* params, fl
         for (int i = 1; i < P.n_conv; ++i) {
             if (!P.conv_tc_all[i]) continue;
             for (int dg = 0; dg < 2; ++dg) {
+                // forward layout: fp16 hi + the combined e4m3 correction plane and its scale; data-gradient layout: fp16 hi
                 const int rc2 = conv_tc_weight_planes(params + P.conv_w[i], P.cin[i], P.C, dg,
-                                                      reinterpret_cast<char*>(ws) + P.wpl[i][dg], ss, kPlaneF16);
+                                                      reinterpret_cast<char*>(ws) + P.wpl[i][dg], ss, kPlaneF16,
+                                                      dg == 0 ? wsf(ws, P.dys) + 1040 + 2 * i : nullptr);
                 if (rc2) return rc2;
             }
         }
@@ -1262,7 +1264,7 @@ static int crnn_forward_impl(const sedb200_crnn_desc* d, const float* params, fl
             const char* ap = reinterpret_cast<const char*>(ws) + P.actp[i - 1];
             rc = conv_tc_planes_w(ap, ap + P.act_plane_bytes[i - 1], reinterpret_cast<const char*>(ws) + P.wpl[i][0],
                                   params + P.conv_b[i], y, training ? wsf(ws, P.part) : nullptr, batch, P.H, P.win[i],
-                                  P.cin[i], P.C, 0, st, 3, kPlaneF16, nullptr);
+                                  P.cin[i], P.C, 0, st, 2, kPlaneF16, nullptr, wsf(ws, P.dys) + 1040 + 2 * i + 1);
             if (rc) return rc;
             nblk = conv_tc_stat_tiles(batch, P.H, P.win[i]);
         } else if (i > 0 && d->tensor_cores && conv_tc_supported(P.H, P.win[i], P.cin[i], P.C)) {

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include "common.cuh"
 
 namespace sedb200 {
@@ -37,10 +38,17 @@ __host__ __device__ inline unsigned long long block_seed(unsigned long long seed
     return seed * 0x2545F4914F6CDD1Dull + (unsigned long long)(block + 1) * 0xD6E8FEB86659FD93ull;
 }
 
-// Activation planes of the plane-native conv blocks: x = hi + lo with hi = fp16(x), lo = fp16(x - hi) -- 22 significand
-// bits for the O(1) values BatchNorm produces (residuals below 2^-14 go subnormal: absolute precision 2^-24).  The
-// conversions saturate at the fp16 range instead of producing inf.  Storage type of all 16-bit planes is
-// `__nv_bfloat16` (just 2 bytes); what the bytes mean is the producer's / consumer's contract.
+// Activation planes of the plane-native conv blocks (what the tensor-core forward reads):
+//   hi  [pixel][C] fp16           hi = fp16(x), saturating
+//   c8  [pixel][C/64][2][64] e4m3 the two CORRECTION operands, 128 bytes per 64 channels: first e4m3(x), then
+//                                 e4m3(2^12 (x - hi)) -- the same bytes per pixel as an fp16 plane, so that a 64-channel
+//                                 K-block of it is one 128-byte-swizzled tile whose K = 128 fp8 contraction against the
+//                                 weight tile laid out in the OPPOSITE order yields  x8 . w_lo8 + x_lo8 . w8  in one go.
+// x ~ hi + 2^-12 * decode(lo8): 15 significand bits for the reader that needs the value back (bn_bwd_sums_act_kernel).
+// The scales are static: the planes hold BatchNorm -> ReLU -> max-pool -> dropout outputs, O(1) by construction; e4m3
+// covers 2^-9 .. 448 after scaling, values below flush (their correction term is below fp32 noise), values above
+// saturate.  Storage type of all planes is `__nv_bfloat16` / bytes; what they mean is this contract.
+constexpr float kActLo8Scale = 4096.0f;                    // (the e4m3 copy of x itself is unscaled: one multiply less per element)
 // {fp16(a), fp16(b)} packed (a in the low half), round-to-nearest, saturating at +-65504: one F2FP instruction
 __device__ __forceinline__ unsigned pack_half2_sat(float a, float b) {
     unsigned d;
@@ -48,21 +56,50 @@ __device__ __forceinline__ unsigned pack_half2_sat(float a, float b) {
     return d;
 }
 __device__ __forceinline__ float2 unpack_half2(unsigned v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
-__device__ __forceinline__ void store_planes4(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long i4,
-                                              const float4 v) {
+// {e4m3(a), e4m3(b)} packed (a in the low byte), saturating
+__device__ __forceinline__ unsigned pack_e4m3x2(float a, float b) {
+    unsigned short d;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(d) : "f"(b), "f"(a));
+    return d;
+}
+__device__ __forceinline__ long c8_offset(long pix, int c4, int C4) {          // byte offset of channels 4*c4 .. +3
+    return pix * 8 * C4 + (c4 >> 4) * 128 + (c4 & 15) * 4;
+}
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ c8, long pix,
+                                              int c4, int C4, const float4 v) {
     const unsigned h01 = pack_half2_sat(v.x, v.y), h23 = pack_half2_sat(v.z, v.w);
     const float2 f01 = unpack_half2(h01), f23 = unpack_half2(h23);
-    reinterpret_cast<uint2*>(hi)[i4] = make_uint2(h01, h23);
-    reinterpret_cast<uint2*>(lo)[i4] = make_uint2(pack_half2_sat(v.x - f01.x, v.y - f01.y), pack_half2_sat(v.z - f23.x, v.w - f23.y));
+    reinterpret_cast<uint2*>(hi)[pix * C4 + c4] = make_uint2(h01, h23);
+    unsigned char* p8 = reinterpret_cast<unsigned char*>(c8) + c8_offset(pix, c4, C4);
+    *reinterpret_cast<unsigned*>(p8) = pack_e4m3x2(v.x, v.y) | (pack_e4m3x2(v.z, v.w) << 16);
+    *reinterpret_cast<unsigned*>(p8 + 64) =
+        pack_e4m3x2((v.x - f01.x) * kActLo8Scale, (v.y - f01.y) * kActLo8Scale) |
+        (pack_e4m3x2((v.z - f23.x) * kActLo8Scale, (v.w - f23.y) * kActLo8Scale) << 16);
 }
-__device__ __forceinline__ float4 load_planes4(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
-                                               long i4) {
-    const uint2 hb = __ldg(reinterpret_cast<const uint2*>(hi) + i4);
-    const uint2 lb = __ldg(reinterpret_cast<const uint2*>(lo) + i4);
-    const __half* hp = reinterpret_cast<const __half*>(&hb);
-    const __half* lp = reinterpret_cast<const __half*>(&lb);
-    return make_float4(__half2float(hp[0]) + __half2float(lp[0]), __half2float(hp[1]) + __half2float(lp[1]),
-                       __half2float(hp[2]) + __half2float(lp[2]), __half2float(hp[3]) + __half2float(lp[3]));
+// eight consecutive channels (c4 even): one 16-byte store to the fp16 plane, two 8-byte stores to the e4m3 plane
+__device__ __forceinline__ void store_planes8(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ c8, long pix,
+                                              int c4, int C4, const float4 a, const float4 b) {
+    const unsigned h0 = pack_half2_sat(a.x, a.y), h1 = pack_half2_sat(a.z, a.w), h2 = pack_half2_sat(b.x, b.y), h3 = pack_half2_sat(b.z, b.w);
+    const float2 f0 = unpack_half2(h0), f1 = unpack_half2(h1), f2 = unpack_half2(h2), f3 = unpack_half2(h3);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint2*>(hi) + pix * C4 + c4) = make_uint4(h0, h1, h2, h3);
+    unsigned char* p8 = reinterpret_cast<unsigned char*>(c8) + c8_offset(pix, c4, C4);
+    *reinterpret_cast<uint2*>(p8) = make_uint2(pack_e4m3x2(a.x, a.y) | (pack_e4m3x2(a.z, a.w) << 16),
+                                               pack_e4m3x2(b.x, b.y) | (pack_e4m3x2(b.z, b.w) << 16));
+    constexpr float s = kActLo8Scale;
+    *reinterpret_cast<uint2*>(p8 + 64) =
+        make_uint2(pack_e4m3x2((a.x - f0.x) * s, (a.y - f0.y) * s) | (pack_e4m3x2((a.z - f1.x) * s, (a.w - f1.y) * s) << 16),
+                   pack_e4m3x2((b.x - f2.x) * s, (b.y - f2.y) * s) | (pack_e4m3x2((b.z - f3.x) * s, (b.w - f3.y) * s) << 16));
+}
+__device__ __forceinline__ float4 load_planes4(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ c8,
+                                               long pix, int c4, int C4) {
+    const uint2 hb = __ldg(reinterpret_cast<const uint2*>(hi) + pix * C4 + c4);
+    const unsigned lb = __ldg(reinterpret_cast<const unsigned*>(reinterpret_cast<const unsigned char*>(c8) + c8_offset(pix, c4, C4) + 64));
+    const float2 f01 = unpack_half2(hb.x), f23 = unpack_half2(hb.y);
+    __half2_raw l01 = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(lb & 0xFFFFu), __NV_E4M3);
+    __half2_raw l23 = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(lb >> 16), __NV_E4M3);
+    const float2 g01 = __half22float2(*reinterpret_cast<__half2*>(&l01)), g23 = __half22float2(*reinterpret_cast<__half2*>(&l23));
+    constexpr float inv = 1.0f / kActLo8Scale;
+    return make_float4(fmaf(g01.x, inv, f01.x), fmaf(g01.y, inv, f01.y), fmaf(g23.x, inv, f23.x), fmaf(g23.y, inv, f23.y));
 }
 // Gradient plane of a conv output: ONE fp16 plane of dy * scale, scale a power of two chosen per tensor from a bound
 // on |dy| (dy_scale_kernel) so that the largest elements sit near 2^13; the contractions that consume it multiply

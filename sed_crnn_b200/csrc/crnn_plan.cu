@@ -126,7 +126,8 @@ int make_plan(const sedb200_crnn_desc* d, int batch, Plan* p) {
     P.dhid[0] = take(max_hid);
     P.dhid[1] = take(max_hid);
     P.bnsum = take(4L * P.C);
-    P.dys = take(8 + 1024);                                                // {scale, 1/scale} + per-block max |dz| partials
+    P.dys = take(8 + 1024 + 8 + 2 * SEDB200_MAX_CONV + 8);                  // {scale, 1/scale} + per-block max |dz| partials;
+                                                                           // from float 1040: per block {2^b, 2^-(12+b)} (weight fp8 scale)
     P.arg0 = take((B * P.H * P.wout[0] * P.C + 3) / 4);                 // one byte per (window, channel)
     P.gram = take(2L * (9 * P.cin[0]) * (9 * P.cin[0] + 1));           // doubles
     // partial-sum scratch: column-sum partials and split-K partials

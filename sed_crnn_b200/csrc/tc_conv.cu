@@ -22,6 +22,7 @@
 //   epilogue of tile i overlaps the MMAs of tile i+1; 3-stage smem ring (64 KB per stage).
 //   dgrad is the same kernel on dY with the weights flipped and transposed beforehand.
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include "tc_umma.cuh"
 #include "tc_conv.cuh"
 
@@ -80,7 +81,7 @@ constexpr uint32_t kTmemCols = 512;                              // conv_tc_kern
 struct ConvMode { int planes, tpi, stage_bytes, n_stages, n_epi_warps, smem_bytes; };
 inline ConvMode conv_mode(int terms, int tpi) {
     ConvMode m;
-    m.planes = terms == 3 ? 2 : 1;
+    m.planes = terms >= 2 ? 2 : 1;
     m.tpi = tpi;
     m.stage_bytes = (tpi + 1) * m.planes * kTileBytes;           // 32 / 48 / 64 / 96 KB
     // 1-term: a third of the MMA work per tile -> EIGHT epilogue warps (two per TMEM sub-partition, half of the
@@ -97,6 +98,7 @@ struct ConvTcParams {
     int terms, tpi, planes, stage_bytes, n_stages, n_epi_warps;
     uint32_t idesc;          // instruction descriptor (operand formats: bf16 or fp16 planes)
     const float* out_scale;  // null, or a device scalar every accumulator is multiplied by (fp16 gradient planes)
+    const float* out2_scale; // terms == 2: device scalar of the fp8 correction accumulator
     float* out;              // [B*H*W][out_ld] fp32
     const float* bias;       // [n_total] or null
     long out_ld;
@@ -189,7 +191,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 const uint64_t ds = dbase + (uint64_t)(stage * stage_u);
                 const uint64_t dbh0 = ds + b_u, dbl0 = dbh0 + tile_u;
                 const uint32_t acc0 = kb != 0;
-                if (planes == 1) {
+                if (p.terms == 2) {
+                    // fp16 hi*hi into accumulator 0, the combined e4m3 correction tiles (128 fp8 along K) into accumulator 1
+                    const uint32_t d1 = tmem_base + (buf * 2) * kTileN, d2 = d1 + kTileN;
+                    const uint64_t dah0 = ds, dac0 = ds + tile_u;
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) mma_bf16(d1, dah0 + 2 * k, dbh0 + 2 * k, idesc, k ? 1u : acc0);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) mma_f8(d2, dac0 + 2 * k, dbl0 + 2 * k, idesc, k ? 1u : acc0);
+                } else if (planes == 1) {
 #pragma unroll
                     for (int t = 0; t < 2; ++t) {
                         if (t < tpi) {
@@ -226,6 +236,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int cc0 = (n_epi_warps == 8) ? ((warp - 4) >> 2) * 2 : 0, cc1 = (n_epi_warps == 8) ? cc0 + 2 : kTileN / 32;
         int buf = 0; uint32_t bphase = 0;
         const float osc = p.out_scale ? __ldg(p.out_scale) : 1.0f;
+        const float osc2 = (p.terms == 2 && p.out2_scale) ? __ldg(p.out2_scale) : 0.0f;
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
             const int nt = item % p.n_tiles_n, mt0 = (item / p.n_tiles_n) * tpi;
             mbar_wait(tfull + buf, bphase);
@@ -244,6 +255,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             for (int cc = cc0; cc < cc1; ++cc) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (buf * 2 + t) * kTileN + cc * 32, v);
+                if (p.terms == 2) {                        // + the fp8 correction accumulator (the tile's second slot)
+                    float v2[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (buf * 2 + 1) * kTileN + cc * 32, v2);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaf(v2[j], osc2, v[j]);
+                }
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<float4*>(stg + lane * kEpiPitch + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -319,7 +336,7 @@ split_planes_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
 //   dgrad: N = Cin,  K = Cout, plane[tap][ci][co] = w[co][ci][8 - tap]      (flipped taps)
 __global__ void __launch_bounds__(256)
 weight_planes_kernel(const float* __restrict__ w, int Cout, int Cin, int dgrad, int fmt, __nv_bfloat16* __restrict__ hi,
-                     __nv_bfloat16* __restrict__ lo) {
+                     __nv_bfloat16* __restrict__ lo, const float* __restrict__ scale2) {
     const long n = 9L * Cout * Cin;
     const int N = dgrad ? Cin : Cout, K = dgrad ? Cout : Cin;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -330,9 +347,20 @@ weight_planes_kernel(const float* __restrict__ w, int Cout, int Cin, int dgrad, 
         const float x = __ldg(w + ((long)co * Cin + ci) * 9 + t);
         if (fmt == kPlaneF16) {                               // fp16 hi / lo (saturating), same storage
             const __half h = __float2half_rn(fminf(fmaxf(x, -65504.0f), 65504.0f));
-            const __half l = __float2half_rn(fminf(fmaxf(x - __half2float(h), -65504.0f), 65504.0f));
             reinterpret_cast<__half*>(hi)[i] = h;
-            reinterpret_cast<__half*>(lo)[i] = l;
+            if (scale2) {
+                // combined e4m3 correction plane, the OPPOSITE order of the activations' (crnn_block.cuh):
+                // row [tap][n], per 64 k: 64 x e4m3(2^(b+12) (w - hi)) then 64 x e4m3(2^b w)  (activations: x unscaled,
+                // residual 2^12: both products carry 2^(b+12))
+                const float sb = __ldg(scale2);
+                unsigned char* row = reinterpret_cast<unsigned char*>(lo) + (i / K) * 2L * K + (k >> 6) * 128 + (k & 63);
+                const __nv_fp8_storage_t l8 = __nv_cvt_float_to_fp8((x - __half2float(h)) * sb * 4096.0f, __NV_SATFINITE, __NV_E4M3);
+                const __nv_fp8_storage_t h8 = __nv_cvt_float_to_fp8(x * sb, __NV_SATFINITE, __NV_E4M3);
+                row[0] = l8;
+                row[64] = h8;
+            } else {
+                reinterpret_cast<__half*>(lo)[i] = __float2half_rn(fminf(fmaxf(x - __half2float(h), -65504.0f), 65504.0f));
+            }
         } else {
             split_bf16(x, hi[i], lo[i]);
         }
@@ -507,6 +535,33 @@ wgrad_reduce_kernel(const float* __restrict__ part, int slices, int Cout, int Ci
 
 }  // namespace
 
+// {2^b, 2^-(12 + b)}: 2^b places the largest |w| just below e4m3's 448 / 2 (the fp8 scale of a weight tensor)
+__global__ void __launch_bounds__(1024)
+weight_scale_kernel(const float* __restrict__ w, long n, float* __restrict__ out) {
+    __shared__ float sm[32];
+    float m = 0.0f;
+    const long n4 = n >> 2;                                        // conv weights: 9 * Cout * Cin floats, 16-byte aligned
+    for (long i = threadIdx.x; i < n4; i += 1024) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(w) + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    for (long i = (n4 << 2) + threadIdx.x; i < n; i += 1024) m = fmaxf(m, fabsf(__ldg(w + i)));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 32; ++i) m = fmaxf(m, sm[i]);
+        int e = 0;
+        float sb = 1.0f;
+        if (m > 0.0f && isfinite(m)) {
+            frexpf(m, &e);                                         // m = f * 2^e, f in [0.5, 1)
+            sb = exp2f((float)max(-100, min(100, 7 - e)));         // m * sb in [64, 128)
+        }
+        out[0] = sb;
+        out[1] = 1.0f / (sb * 4096.0f);
+    }
+}
+
 size_t conv_tc_scratch_bytes(int B, int H, int W, int Cin, int Cout) {
     const size_t act = (size_t)B * H * W * Cin * 2;      // one bf16 plane of the input
     const size_t wp = (size_t)9 * Cout * Cin * 2;
@@ -521,11 +576,18 @@ size_t conv_tc_weight_scratch_bytes(int Cin, int Cout) { return 2 * (((size_t)9 
 
 // B-operand planes of a conv weight (forward or flipped / transposed for the data gradient) into `wplanes`
 // (conv_tc_weight_scratch_bytes); they stay valid until the weight changes
-int conv_tc_weight_planes(const float* w, int Cin, int Cout, int dgrad, void* wplanes, cudaStream_t st, int fmt) {
+int conv_tc_weight_planes(const float* w, int Cin, int Cout, int dgrad, void* wplanes, cudaStream_t st, int fmt,
+                          float* scale2) {
+    SED_REQUIRE(!scale2 || (fmt == kPlaneF16 && !dgrad && Cin % 64 == 0), SEDB200_EINVAL,
+                "conv_tc_weight_planes: the fp8 correction plane exists for the fp16 forward layout only");
+    if (scale2) {
+        weight_scale_kernel<<<1, 1024, 0, st>>>(w, 9L * Cout * Cin, scale2);
+        SED_POST_LAUNCH();
+    }
     const size_t wp = ((size_t)9 * Cout * Cin * 2 + 1023) & ~(size_t)1023;
     __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(wplanes);
     __nv_bfloat16* w_lo = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(wplanes) + wp);
-    weight_planes_kernel<<<(int)std::min<long>((9L * Cout * Cin + 255) / 256, 1184), 256, 0, st>>>(w, Cout, Cin, dgrad, fmt, w_hi, w_lo);
+    weight_planes_kernel<<<(int)std::min<long>((9L * Cout * Cin + 255) / 256, 1184), 256, 0, st>>>(w, Cout, Cin, dgrad, fmt, w_hi, w_lo, scale2);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }
@@ -541,9 +603,10 @@ int conv_tc_planes(const void* a_hi, const void* a_lo, const float* w, const flo
 // same with the weight planes already built (conv_tc_weight_planes)
 int conv_tc_planes_w(const void* a_hi, const void* a_lo, const void* wplanes, const float* bias, float* out, float* stats,
                      int B, int H, int W, int Cin, int Cout, int dgrad, cudaStream_t st, int terms, int fmt,
-                     const float* out_scale) {
+                     const float* out_scale, const float* out2_scale) {
     const int Kc = dgrad ? Cout : Cin, Nc = dgrad ? Cin : Cout;
-    SED_REQUIRE(terms == 1 || terms == 3, SEDB200_EINVAL, "conv_tc: terms = %d", terms);
+    SED_REQUIRE(terms == 1 || terms == 2 || terms == 3, SEDB200_EINVAL, "conv_tc: terms = %d", terms);
+    SED_REQUIRE(terms != 2 || (fmt == kPlaneF16 && out2_scale && a_lo), SEDB200_EINVAL, "conv_tc: the fp16 + fp8 mode needs fp16 planes, the correction planes and their scale");
     if (terms == 1 || !a_lo) a_lo = a_hi;                       // 1-term: the lo maps are encoded but never used
     SED_REQUIRE(conv_tc_supported(H, W, Kc, Nc), SEDB200_ESHAPE, "conv_tc: shape H=%d W=%d K=%d N=%d unsupported", H, W, Kc, Nc);
     const size_t wp = ((size_t)9 * Nc * Kc * 2 + 1023) & ~(size_t)1023;
@@ -583,16 +646,18 @@ int conv_tc_planes_w(const void* a_hi, const void* a_lo, const void* wplanes, co
     const long pairs = (long)((p.m_tiles + 1) / 2) * p.n_tiles_n;
     int tpi = pairs >= 5L * sm_count() ? 2 : 1;
     if (force_tpi == 1 || force_tpi == 2) tpi = force_tpi;
+    if (terms == 2) tpi = 1;                                     // the tile's second accumulator slot holds the fp8 pass
     const ConvMode md = conv_mode(terms, tpi);
     p.tpi = tpi; p.planes = md.planes; p.stage_bytes = md.stage_bytes; p.n_stages = md.n_stages; p.n_epi_warps = md.n_epi_warps;
     p.total_items = ((p.m_tiles + tpi - 1) / tpi) * p.n_tiles_n;
     p.idesc = fmt == kPlaneF16 ? idesc_f16(kTileM, kTileN, 0, 0) : idesc_bf16(kTileM, kTileN, 0, 0);
     p.out_scale = out_scale;
+    p.out2_scale = out2_scale;
     p.out = out; p.bias = bias; p.out_ld = Nc; p.stats = stats;
     SED_REQUIRE(md.n_stages >= 2, SEDB200_ESHAPE, "conv_tc: no room for two pipeline stages");
     { const int rc = ensure_dyn_smem((const void*)conv_tc_kernel, 227 * 1024); if (rc) return rc; }
     const int grid = std::min(p.total_items, sm_count());
-    SED_REQUIRE(terms == 3 || !stats, SEDB200_EINVAL, "conv_tc: BatchNorm statistics need the 3-term (forward) mode");
+    SED_REQUIRE(terms != 1 || !stats, SEDB200_EINVAL, "conv_tc: BatchNorm statistics need a forward mode");
     conv_tc_kernel<<<grid, kConvThreads, md.smem_bytes, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
     SED_POST_LAUNCH();
     return SEDB200_OK;

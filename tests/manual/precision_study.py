@@ -60,6 +60,13 @@ class Split:
             s8 = pow2_scale(t, 256.0)
             self.hi8 = r_e4m3(t, s8)
             self.lo8 = r_e4m3(t - self.hi, pow2_scale(t - self.hi, 256.0))
+        elif scheme == "m2s":                                   # what the kernels hold: fp16 hi; e4m3 of x and of the fp16
+            self.hi = r_fp16(t, 1.0)                            # residual with the STATIC activation scales 2 / 2^12, or
+            self.hi8_act = r_e4m3(t, 2.0)                       # (weights) the per-tensor power of two placing amax at 224
+            self.lo8_act = r_e4m3(t - self.hi, 4096.0)
+            sw = pow2_scale(t, 224.0)
+            self.hi8_w = r_e4m3(t, sw)
+            self.lo8_w = r_e4m3(t - self.hi, sw * 2048.0)
         elif scheme == "x1":                                    # A (dY) bf16, B (weights / activations) fp16, one term
             self.hi = r_bf16(t)
             self.hi_b = r_fp16(t, pow2_scale(t, 2.0 ** 14))
@@ -72,7 +79,7 @@ class Split:
 
 
 COST = {"fp32": 0, "s3": 3, "b1": 1, "b2a": 2, "b2b": 2, "f1": 1, "f2a": 2, "f2b": 2, "f3": 3, "m2": 2, "m15a": 1.5,
-        "m15b": 1.5, "t1": 2, "bm2": 2, "x1": 1}
+        "m15b": 1.5, "t1": 2, "bm2": 2, "x1": 1, "m2s": 2}
 
 
 def contract(op, a, b, scheme):
@@ -93,6 +100,8 @@ def contract(op, a, b, scheme):
         return op(A.hi, B.hi) + op(A.hi, B.lo)
     if scheme in ("m2", "bm2"):                                 # 16-bit hi*hi + two fp8 correction terms
         return op(A.hi, B.hi) + op(A.lo8, B.hi8) + op(A.hi8, B.lo8)
+    if scheme == "m2s":                                         # a = activations (static scales), b = weights
+        return op(A.hi, B.hi) + op(A.lo8_act, B.hi8_w) + op(A.hi8_act, B.lo8_w)
     if scheme == "m15a":
         return op(A.hi, B.hi) + op(A.lo8, B.hi8)
     if scheme == "m15b":
