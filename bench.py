@@ -97,11 +97,12 @@ def phase_model(cfg, B, per):
                                     "conv0_lean_fwd_kernel (conv + BN + ReLU + max-pool + dropout in registers)")
             m["conv0.bwd_lean"] = ("hbm", xin + a + a / 4, "conv0_lean_bwd_kernel (winner contributions to dW / d gamma / d beta)")
         elif tc_ok:
-            # MMA passes per k-step: the forward runs the 3-term fp16 hi/lo split (fp32-grade), the data / weight
-            # gradients ONE pass on fp16 planes (dy scaled by a per-tensor power of two) -- DESIGN.md section 3
-            for ph, kn, terms in (("fwd", "conv_tc_kernel", 3), ("dgrad", "conv_tc_kernel", 1), ("wgrad", "wgrad_tc_kernel", 1)):
-                m[f"conv{i}.{ph}"] = ("tensor", per[f"conv{i}"], f"{kn} (tcgen05 implicit GEMM on fp16 planes: 3-term split "
-                                      f"forward, single-pass gradients)", terms)
+            # tensor-pipe cost per k-step in fp16-pass units: the forward runs ONE fp16 pass + ONE e4m3 correction pass over
+            # twice the K at twice the rate (= 2 units, fp32-grade to ~2^-15), the data / weight gradients ONE fp16 pass
+            # (dy scaled by a per-tensor power of two) -- DESIGN.md section 3
+            for ph, kn, terms in (("fwd", "conv_tc_kernel", 2), ("dgrad", "conv_tc_kernel", 1), ("wgrad", "wgrad_tc_kernel", 1)):
+                m[f"conv{i}.{ph}"] = ("tensor", per[f"conv{i}"], f"{kn} (tcgen05 implicit GEMM: fp16 pass + e4m3 correction "
+                                      f"pass forward, single-pass fp16 gradients)", terms)
         m[f"pool{i}.fwd"] = ("hbm", y + a, "bn_relu_pool_fwd_t_kernel (BN + ReLU + max-pool + dropout: conv output in, pooled planes out)")
         m[f"pool{i}.bwd_sums"] = ("hbm", 2 * a, "bn_bwd_sums_act_kernel (BatchNorm backward sums from the saved block output and dA)")
         if i > 0:
@@ -170,7 +171,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ reference arm
-DTYPE = "f32 (bf16x3 tensor-core operands, fp32 accumulate)"
+DTYPE = "f32 (fp16 + e4m3-correction tensor-core operands in the conv forward, fp16 single-pass gradients, bf16x3 GRU GEMMs; fp32 accumulate)"
 
 
 def _ref_model(R, config):
@@ -853,8 +854,9 @@ def run_ours(args, rank, world, local_rank):
                 "per_phase": {k: {"ms": phases[k], "algorithmic_tflops": model[k][1] / (phases[k] * 1e-3) / 1e12,
                                   "mma_passes": model[k][3] if len(model[k]) > 3 else 1} for k in dks},
                 "note": "frac = algorithmic FLOPs (2*M*K*N, SURVEY 8d) / measured sustained fp16/bf16 peak, pooled over this "
-                "kernel's launches in a step; the forward launches run the fp32-grade 3-term fp16 split (3 MMA passes per "
-                "k-step), the data-gradient launches one pass; frac_issued counts the MMA work actually issued"}
+                "kernel's launches in a step; the forward launches run one fp16 pass plus one e4m3 correction pass (twice the K "
+                "at twice the rate: 2 fp16-pass units per k-step), the data-gradient launches one pass; frac_issued counts "
+                "the tensor-pipe work actually issued in fp16-pass units"}
     else:
         ach = amount_step / (ms_kernel_step * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": kname, "phases": dks, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
