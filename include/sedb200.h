@@ -90,6 +90,23 @@ int    sedb200_logmel_host_i16(const short* pcm_host, int n_clips, int n_ch, lon
                                int sr, int pad_mode, float* out_host,
                                void* scratch_dev, size_t scratch_bytes, void* stream);
 
+/* The same two calls with the kernel named.  Two kernels implement the front end:
+ *   SEDB200_LOGMEL_FP32 : one warp per frame, 32 x 32 register FFT in fp32 on the CUDA cores (csrc/logmel.cu);
+ *   SEDB200_LOGMEL_TC   : the 2048-point real DFT as two batched tcgen05 GEMMs (64-point real stage over rows
+ *                         (frame, n2), 32-point complex stage over rows (frame, k1)) on fp16 hi / lo operand planes
+ *                         with fp32 accumulation in TMEM (csrc/logmel_tc.cu); same result to ~1e-6 relative.
+ * SEDB200_LOGMEL_AUTO picks the build's default (sedb200_logmel_default_kernel(); the environment variable
+ * SEDB200_LOGMEL_KERNEL = "fp32" | "tc" overrides it), which is what sedb200_logmel_f32 / _i16 / _host_* run. */
+#define SEDB200_LOGMEL_AUTO 0
+#define SEDB200_LOGMEL_FP32 1
+#define SEDB200_LOGMEL_TC   2
+#define SEDB200_LOGMEL_DEFAULT_KERNEL SEDB200_LOGMEL_FP32
+int    sedb200_logmel_f32_k(const float* pcm_dev, int n_clips, int n_ch, long n_samples,
+                            int sr, int pad_mode, float* out_dev, void* stream, int kernel);
+int    sedb200_logmel_i16_k(const short* pcm_dev, int n_clips, int n_ch, long n_samples,
+                            int sr, int pad_mode, float* out_dev, void* stream, int kernel);
+int    sedb200_logmel_default_kernel(void);
+
 /* Per-bin standardisation -- the step between the two halves of the hot path (feature.py:127-129:
  * sklearn.preprocessing.StandardScaler().fit_transform(X_train) / .transform(X_test)).
  * fit:   mean[c], var[c] (population variance), scale[c] = sqrt(var) (1.0 for constant columns) of x [rows][cols],

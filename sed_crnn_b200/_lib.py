@@ -38,6 +38,9 @@ SIGNATURES = {
     "sedb200_logmel_i16": (_i, [_p, _i, _i, _l, _i, _i, _p, _p]),
     "sedb200_logmel_host_scratch_i16": (_sz, [_i, _i, _l]),
     "sedb200_logmel_host_i16": (_i, [_p, _i, _i, _l, _i, _i, _p, _p, _sz, _p]),
+    "sedb200_logmel_f32_k": (_i, [_p, _i, _i, _l, _i, _i, _p, _p, _i]),
+    "sedb200_logmel_i16_k": (_i, [_p, _i, _i, _l, _i, _i, _p, _p, _i]),
+    "sedb200_logmel_default_kernel": (_i, []),
     "sedb200_mel_filterbank": (_i, [_i, _p]),
     "sedb200_standardize_scratch_bytes": (_sz, [_l, _i]),
     "sedb200_standardize_fit": (_i, [_p, _l, _i, _p, _p, _p, _p, _sz, _p]),

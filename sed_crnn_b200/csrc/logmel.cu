@@ -22,9 +22,10 @@
 // precision, a DFT-as-GEMM at that precision needs 3 bf16 MMAs per product (>= 1.6 MFLOP/frame,
 // i.e. more than the whole tensor peak at the HBM roofline), while the factored fp32 FFT is
 // ~45 kFLOP/frame ("log-mel kernel").
-#include "common.cuh"
+#include "logmel.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -33,30 +34,7 @@
 namespace sedb200 {
 namespace {
 
-constexpr int kNfft = SEDB200_NFFT;      // 2048
-constexpr int kHop = SEDB200_HOP;        // 1024
-constexpr int kBins = kNfft / 2 + 1;     // 1025
-constexpr int kMel = SEDB200_NMEL;       // 40
-constexpr int kM = kNfft / 2;            // complex FFT length 1024
 constexpr int kWarps = 16;               // warps (= frames in flight) per CTA
-constexpr int kBinStride = 33;           // bins walked per lane in the mel stage
-constexpr int kMaxSlots = 96;            // (lane, segment) partial sums
-constexpr int kMaxTerms = 12;            // max partial sums feeding one mel band
-constexpr int kBandsRound1 = 32;         // bands kMel-32 .. kMel-1 are closed by lanes 0..31, the rest in a second round
-
-// Constant tables, built on the host in double precision, one copy per (device, sr).
-struct LogmelTables {
-    float2 tw1[32 * 32];        // [a][t] = exp(-2 pi i t a / 1024)
-    float  win[kNfft / 2];      // first half of the periodic Hann window; w[n + 1024] = 1 - w[n]
-    float2 tw2[kM / 2 + 8];     // exp(-2 pi i k / 2048), k = 0..512
-    float2 coef[kMel * kMaxTerms];          // per band: (A, B) of each partial sum: band += A * S0 + B * S1
-    unsigned long long lanemask[32];        // bit i: the band-edge segment steps up at the lane's i-th bin
-    unsigned char gslot[kMel * kMaxTerms];  // per band: the partial-sum slot of each term (padding: slot 0, A = B = 0)
-    unsigned char lanebase[32];             // first slot of each lane (its segments take consecutive slots)
-    int terms_round1, terms_round2;         // loop trip counts of the two closing rounds
-    int pad_[2];
-};
-static_assert(sizeof(LogmelTables) % 16 == 0, "tables are copied as uint4");
 
 constexpr int kBufBytes = 32 * 33 * 8;                 // per-warp exchange buffer (8448 B)
 constexpr int kExchBytes = 512 * 8;                    // untangle exchange: Z[512..1023]; P starts behind it
@@ -117,29 +95,6 @@ __device__ __forceinline__ void fft32(float2 (&v)[32]) {
             }
         }
     }
-}
-
-// PCM sample types: float32 as the reference decodes it (feature.py:45-50, ffmpeg -f f32le), or int16 as a WAV /
-// `-f s16le` decoder delivers it; an int16 sample s stands for the float32 value s / 32768 (exact), so both
-// ingest paths feed the same arithmetic
-__device__ __forceinline__ float ld_sample(const float* p) { return __ldg(p); }
-__device__ __forceinline__ float ld_sample(const short* p) { return (float)__ldg(p) * (1.0f / 32768.0f); }
-__device__ __forceinline__ float2 ld_pair(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
-__device__ __forceinline__ float2 ld_pair(const short* p) {
-    const short2 v = __ldg(reinterpret_cast<const short2*>(p));
-    return make_float2((float)v.x * (1.0f / 32768.0f), (float)v.y * (1.0f / 32768.0f));
-}
-
-// sample `i` of a clip of S samples under librosa's centre padding
-template <typename T>
-__device__ __forceinline__ float padded_sample(const T* __restrict__ x, long S, long i, int pad_mode) {
-    if (i >= 0 && i < S) return ld_sample(x + i);
-    if (pad_mode == SEDB200_PAD_CONSTANT) return 0.0f;
-    if (S == 1) return ld_sample(x);
-    const long period = 2 * (S - 1);
-    long m = i % period;
-    if (m < 0) m += period;
-    return ld_sample(x + (m < S ? m : period - m));
 }
 
 // ------------------------------------------------------------------------------ the kernel
@@ -450,7 +405,9 @@ int build_tables(int sr, LogmelTables& t) {
 std::mutex g_tab_mu;
 std::map<std::pair<int, int>, LogmelTables*> g_tabs;   // (device, sr) -> device copy
 
-int get_tables(int sr, cudaStream_t stream, const LogmelTables** out) {
+}  // namespace
+
+int logmel_get_tables(int sr, cudaStream_t stream, const LogmelTables** out) {
     int dev = 0;
     SED_CUDA_OK(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(g_tab_mu);
@@ -469,10 +426,22 @@ int get_tables(int sr, cudaStream_t stream, const LogmelTables** out) {
     return SEDB200_OK;
 }
 
+namespace {
+
+// which kernel sedb200_logmel_* runs when the caller does not say: SEDB200_LOGMEL_KERNEL = "fp32" | "tc" overrides
+int default_kernel() {
+    static const int k = [] {
+        const char* e = std::getenv("SEDB200_LOGMEL_KERNEL");
+        if (e && std::strcmp(e, "fp32") == 0) return SEDB200_LOGMEL_FP32;
+        if (e && std::strcmp(e, "tc") == 0) return SEDB200_LOGMEL_TC;
+        return SEDB200_LOGMEL_DEFAULT_KERNEL;
+    }();
+    return k;
+}
 
 template <typename T>
 int logmel_launch(const T* pcm_dev, int n_clips, int n_ch, long n_samples, int sr, int pad_mode, float* out_dev,
-                  void* stream) {
+                  void* stream, int kernel = SEDB200_LOGMEL_AUTO) {
     SED_REQUIRE(n_clips >= 0 && n_ch >= 1, SEDB200_EINVAL, "logmel: n_clips=%d n_ch=%d", n_clips, n_ch);
     SED_REQUIRE(n_samples >= 1, SEDB200_EINVAL, "logmel: empty signal (n_samples=%ld)", n_samples);
     SED_REQUIRE(sr > 0, SEDB200_EINVAL, "logmel: sr=%d", sr);
@@ -483,8 +452,12 @@ int logmel_launch(const T* pcm_dev, int n_clips, int n_ch, long n_samples, int s
     int rc = require_sm100();
     if (rc) return rc;
     cudaStream_t st = as_stream(stream);
+    SED_REQUIRE(kernel == SEDB200_LOGMEL_AUTO || kernel == SEDB200_LOGMEL_FP32 || kernel == SEDB200_LOGMEL_TC,
+                SEDB200_EINVAL, "logmel: kernel=%d", kernel);
+    if (kernel == SEDB200_LOGMEL_AUTO) kernel = default_kernel();
+    if (kernel == SEDB200_LOGMEL_TC) return logmel_tc_launch<T>(pcm_dev, n_clips, n_ch, n_samples, sr, pad_mode, out_dev, st);
     const LogmelTables* tab = nullptr;
-    rc = get_tables(sr, st, &tab);
+    rc = logmel_get_tables(sr, st, &tab);
     if (rc) return rc;
     const long nfr = n_samples <= 0 ? 0 : 1 + n_samples / kHop;
     SED_REQUIRE(nfr < (1L << 31), SEDB200_ESHAPE, "logmel: %ld frames per clip", nfr);
@@ -548,6 +521,18 @@ int sedb200_logmel_i16(const short* pcm_dev, int n_clips, int n_ch, long n_sampl
                        float* out_dev, void* stream) {
     return logmel_launch<short>(pcm_dev, n_clips, n_ch, n_samples, sr, pad_mode, out_dev, stream);
 }
+
+int sedb200_logmel_f32_k(const float* pcm_dev, int n_clips, int n_ch, long n_samples, int sr, int pad_mode,
+                         float* out_dev, void* stream, int kernel) {
+    return logmel_launch<float>(pcm_dev, n_clips, n_ch, n_samples, sr, pad_mode, out_dev, stream, kernel);
+}
+
+int sedb200_logmel_i16_k(const short* pcm_dev, int n_clips, int n_ch, long n_samples, int sr, int pad_mode,
+                         float* out_dev, void* stream, int kernel) {
+    return logmel_launch<short>(pcm_dev, n_clips, n_ch, n_samples, sr, pad_mode, out_dev, stream, kernel);
+}
+
+int sedb200_logmel_default_kernel(void) { return default_kernel(); }
 
 size_t sedb200_logmel_host_scratch(int n_clips, int n_ch, long n_samples) {
     return logmel_scratch_bytes(n_clips, n_ch, n_samples, 4);

@@ -29,11 +29,15 @@ def n_frames(n_samples: int) -> int:
     return 1 + n_samples // HOP
 
 
+LOGMEL_KERNELS = {"auto": 0, "fp32": 1, "tc": 2}      # include/sedb200.h: SEDB200_LOGMEL_*
+
+
 def mbe_device(pcm: torch.Tensor, sr: int = SR, pad_mode: str = DEFAULT_PAD_MODE,
-               out: torch.Tensor | None = None) -> torch.Tensor:
+               out: torch.Tensor | None = None, kernel: str = "auto") -> torch.Tensor:
     """Device-resident form.  pcm: CUDA float32 (or int16, value = s / 32768) [S], [n_ch, S] or [n_clips, n_ch, S] ->
     [frames, 40], [frames, n_ch*40] or [n_clips, frames, n_ch*40] on the same device, enqueued on
-    the current stream (no synchronisation)."""
+    the current stream (no synchronisation).  `kernel`: "fp32" (CUDA-core FFT), "tc" (tcgen05 DFT-as-GEMM) or "auto"
+    (the library default / SEDB200_LOGMEL_KERNEL)."""
     if not (isinstance(pcm, torch.Tensor) and pcm.is_cuda):
         raise TypeError("mbe_device needs a CUDA tensor (no CPU fallback)")
     if pcm.dtype not in (torch.float32, torch.int16):
@@ -59,9 +63,9 @@ def mbe_device(pcm: torch.Tensor, sr: int = SR, pad_mode: str = DEFAULT_PAD_MODE
             or out.device != pcm.device:
         raise ValueError(f"out must be contiguous float32 {oshape} on {pcm.device}")
     with torch.cuda.device(pcm.device):
-        fn = _lib.lib().sedb200_logmel_i16 if pcm.dtype == torch.int16 else _lib.lib().sedb200_logmel_f32
+        fn = _lib.lib().sedb200_logmel_i16_k if pcm.dtype == torch.int16 else _lib.lib().sedb200_logmel_f32_k
         _lib.check(fn(pcm.data_ptr(), n_clips, n_ch, S, int(sr), _lib.PAD_MODES[pad_mode], out.data_ptr(),
-                      _lib.current_stream_ptr()))
+                      _lib.current_stream_ptr(), LOGMEL_KERNELS[kernel]))
     return out
 
 
