@@ -111,8 +111,9 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
-// per-warpgroup register budget (the kernel is compiled for 96 registers x 640 threads; the producers and the mel walk
-// need more, the stage-1 epilogue and the MMA thread less)
+// per-warpgroup register budget.  The kernel is compiled for 96 registers x 640 threads and setmaxnreg only moves registers
+// INSIDE that allocation: 56 (stage-1 epilogue) and 40 (MMA warpgroup) free 12288, the producers (160) and the two mel
+// warpgroups (112) take exactly that.
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -260,7 +261,7 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
         }
     } else if (warp < 8) {
         // ================================================= stage-1 epilogue: TMEM lane = row position of (frame, n2)
-        reg_dec<64>();
+        reg_dec<56>();
         const int fw = warp - 4;
         const int n2 = 4 * (lane & 7) + (lane >> 3);
         uint32_t xo[8];
@@ -315,7 +316,7 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
         }
     } else if (warp < 16) {
         // ================================================= stage-2 epilogue + mel: two sets alternate tiles
-        reg_inc<120>();
+        reg_inc<112>();
         const int set = (warp - 8) >> 2, fw = (warp - 8) & 3;
         float* P = Pall + (set * 4 + fw) * kPStride;
         float2* part = reinterpret_cast<float2*>(smem + kOffPart) + (warp - 8) * kMaxSlots;
