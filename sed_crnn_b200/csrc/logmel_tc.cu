@@ -116,6 +116,37 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float (&v)[8]) {
 // warpgroups (112) take exactly that.
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+// mbarrier wait that SLEEPS in hardware (suspend-time hint) instead of polling: a polling role eats the issue slots of the
+// roles it is waiting for (first build: 700 of 1840 warp instructions per frame were wait loops).  Bounded: a pipeline
+// bug traps instead of hanging the GPU.
+__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
+    for (int spin = 0; spin < 200000; ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity), "r"(20000u)
+            : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+// shared-memory accesses by 32-bit shared address (generic pointers cost 64-bit address arithmetic and LD / ST)
+__device__ __forceinline__ float lds32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ float2 lds64(uint32_t a) { float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ float4 lds128c(uint32_t a) {      // constants: may be hoisted / reordered
+    float4 v; asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ float2 lds64c(uint32_t a) { float2 v; asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds8c(uint32_t a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void stsf32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -181,7 +212,7 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
         // ================================================= producers: one warp per frame of the tile
         reg_inc<160>();
         const int fw = warp, m = lane & 7, g = lane >> 3;
-        const float4* wrow = reinterpret_cast<const float4*>(cst.win + lane * 36);
+        const uint32_t wrow = smem_u32(cst.win + lane * 36);
         for (int i = 0; i < n_local; ++i) {
             const int b = i % kNBuf;
             const unsigned q = 4u * (unsigned)(t0 + i) + (unsigned)fw;
@@ -227,7 +258,7 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
             // Hann: w for the first half, 1 - w for the second (periodic window: w[n + 1024] = 1 - w[n])
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float4 w = wrow[j];
+                const float4 w = lds128c(wrow + 16 * j);
                 const float2 wa = __fmul2_rn(make_float2(w.x, w.y), make_float2(s, s)), wb = __fmul2_rn(make_float2(w.z, w.w), make_float2(s, s));
                 const float2 ua = __ffma2_rn(make_float2(-w.x, -w.y), make_float2(s, s), make_float2(s, s));
                 const float2 ub = __ffma2_rn(make_float2(-w.z, -w.w), make_float2(s, s), make_float2(s, s));
@@ -236,7 +267,7 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
                 v[j] = make_float4(p0.x, p0.y, p1.x, p1.y);
                 v[j + 8] = make_float4(r0.x, r0.y, r1.x, r1.y);
             }
-            mbar_wait(buf_free + b, ((uint32_t)(i / kNBuf) & 1u) ^ 1u);     // stage 2 of the tile that used this buffer retired
+            wait_bar(buf_free + b, ((uint32_t)(i / kNBuf) & 1u) ^ 1u);     // stage 2 of the tile that used this buffer retired
             const uint32_t tile = tiles_u32 + b * kTileBytes + (4 * fw) * 1024 + m * 128;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -268,9 +299,10 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
 #pragma unroll
         for (int mm = 0; mm < 8; ++mm) xo[mm] = (uint32_t)((((lane & 7) ^ mm) << 4) + (lane >> 3) * 4);
         const uint32_t spec_off = (uint32_t)(fw * 128 + (((n2 >> 3) ^ fw) << 4) + (n2 & 7) * 2);
+        const uint32_t tw_u32 = smem_u32(cst.tw + lane);
         for (int i = 0; i < n_local; ++i) {
             const int b = i % kNBuf, tb = i & 1;
-            mbar_wait(d1_full + tb, (uint32_t)(i >> 1) & 1u);
+            wait_bar(d1_full + tb, (uint32_t)(i >> 1) & 1u);
             tc_fence_after();
             const uint32_t ta = tmem + ((uint32_t)(32 * fw) << 16) + tb * 64;
             const uint32_t rows = tiles_u32 + b * kTileBytes + (4 * fw) * 1024;
@@ -289,7 +321,7 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
                 if (jq == 0) { y32 = im[0]; im[0] = 0.0f; }         // the slot of Im Y[0] (= 0) carries Y[32]
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
-                    const float4 t = cst.tw[(4 * jq + p) * 32 + lane];
+                    const float4 t = lds128(tw_u32 + (4 * jq + p) * 512);       // volatile: 16 hoisted float4s would not fit
                     const float2 r2 = make_float2(re[2 * p], re[2 * p + 1]), i2 = make_float2(im[2 * p], im[2 * p + 1]);
                     const float2 c2 = make_float2(t.x, t.y), s2 = make_float2(t.z, t.w);
                     const float2 zr = __ffma2_rn(i2, s2, __fmul2_rn(r2, c2));                       // (re + i im)(c - i s)
@@ -318,10 +350,15 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
         // ================================================= stage-2 epilogue + mel: two sets alternate tiles
         reg_inc<112>();
         const int set = (warp - 8) >> 2, fw = (warp - 8) & 3;
-        float* P = Pall + (set * 4 + fw) * kPStride;
-        float2* part = reinterpret_cast<float2*>(smem + kOffPart) + (warp - 8) * kMaxSlots;
+        const uint32_t P = smem_u32(Pall + (set * 4 + fw) * kPStride);
+        const uint32_t Pfwd = P + 4 * lane, Pmir = P + 4 * 2048 - 4 * lane;      // bin k1 + 64 k2 / mirror bin 2048 - k
+        const uint32_t part = smem_u32(smem + kOffPart) + (warp - 8) * kMaxSlots * 8;
+        const uint32_t coef_u32 = smem_u32(mel.coef), gslot_u32 = smem_u32(mel.gslot);
+        const unsigned long long msk = mel.lanemask[lane];
+        const uint32_t slot0 = part + 8u * mel.lanebase[lane];
+        const int terms1 = mel.terms_round1, terms2 = mel.terms_round2;
         for (int i = set; i < n_local; i += 2) {
-            mbar_wait(d2_full + set, (uint32_t)(i >> 1) & 1u);
+            wait_bar(d2_full + set, (uint32_t)(i >> 1) & 1u);
             tc_fence_after();
             const uint32_t ta = tmem + ((uint32_t)(32 * fw) << 16) + 128 + set * 64;
             named_bar(1 + set, 128);                               // the set's previous walk is over (special bins cross warps)
@@ -335,17 +372,17 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
                 for (int e = 0; e < 8; ++e) {
                     const int k2 = 8 * jq + e;
                     const float pw = fmaf(re[e], re[e], im[e] * im[e]);          // 4 |X|^2 (B2 is doubled)
-                    if (k2 < 16) P[lane + 64 * k2] = pw;                          // bin k1 + 64 k2
-                    else if (lane != 0 || k2 == 16) P[2048 - 64 * k2 - lane] = pw;   // mirror bin 2048 - k
+                    if (k2 < 16) stsf32(Pfwd + 256 * k2, pw);                     // bin k1 + 64 k2
+                    else if (lane != 0 || k2 == 16) stsf32(Pmir - 256 * k2, pw);  // mirror bin 2048 - k
                 }
             }
             if (fw == 0) {                                         // special rows: TMEM lanes 0..3 = the tile's frames
                 float sp[32];
                 tmem_ld32(tmem + 256 + set * 32, sp);
                 if (lane < 4) {
-                    float* Ps = Pall + (set * 4 + lane) * kPStride;
+                    const uint32_t Ps = smem_u32(Pall + (set * 4 + lane) * kPStride) + 4 * 32;
 #pragma unroll
-                    for (int k2 = 0; k2 < 16; ++k2) Ps[32 + 64 * k2] = fmaf(sp[k2], sp[k2], sp[16 + k2] * sp[16 + k2]);
+                    for (int k2 = 0; k2 < 16; ++k2) stsf32(Ps + 256 * k2, fmaf(sp[k2], sp[k2], sp[16 + k2] * sp[16 + k2]));
                 }
             }
             tc_fence_before();
@@ -357,14 +394,13 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
             const float unscale = -1.3862943611198906f * scale_exp[(i & 7) * 4 + fw];     // -2 ln2 * exponent
             // ---- mel projection: the walk of logmel.cu (per-lane (sum P, sum i P) per band-edge segment, fixed order)
             {
-                const float* Pl = P + lane * kBinStride;
-                const unsigned long long msk = mel.lanemask[lane];
+                const uint32_t Pl = P + 4 * lane * kBinStride;
                 const unsigned mlo = (unsigned)msk, mhi = (unsigned)(msk >> 32);
-                unsigned slot = (unsigned)__cvta_generic_to_shared(part + mel.lanebase[lane]);
+                unsigned slot = slot0;
                 float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
                 for (int ii = 0; ii < kBinStride; ++ii) {
-                    const float p = Pl[ii];
+                    const float p = lds32(Pl + 4 * ii);
                     if (ii > 0) {
                         asm volatile(
                             "{\n\t.reg .pred q;\n\t"
@@ -390,9 +426,9 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
                 {
                     const int bnd = kMel - kBandsRound1 + lane;
                     float acc = 0.0f;
-                    for (int ii = 0; ii < mel.terms_round1; ++ii) {
-                        const float2 c = mel.coef[bnd * kMaxTerms + ii];
-                        const float2 sv = part[mel.gslot[bnd * kMaxTerms + ii]];
+                    for (int ii = 0; ii < terms1; ++ii) {
+                        const float2 c = lds64c(coef_u32 + 8 * (bnd * kMaxTerms + ii));
+                        const float2 sv = lds64(part + 8 * lds8c(gslot_u32 + bnd * kMaxTerms + ii));
                         acc = fmaf(c.x, sv.x, acc);
                         acc = fmaf(c.y, sv.y, acc);
                     }
@@ -401,9 +437,9 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
                 if (lane < kMel - kBandsRound1) {
                     const int bnd = lane;
                     float acc = 0.0f;
-                    for (int ii = 0; ii < mel.terms_round2; ++ii) {
-                        const float2 c = mel.coef[bnd * kMaxTerms + ii];
-                        const float2 sv = part[mel.gslot[bnd * kMaxTerms + ii]];
+                    for (int ii = 0; ii < terms2; ++ii) {
+                        const float2 c = lds64c(coef_u32 + 8 * (bnd * kMaxTerms + ii));
+                        const float2 sv = lds64(part + 8 * lds8c(gslot_u32 + bnd * kMaxTerms + ii));
                         acc = fmaf(c.x, sv.x, acc);
                         acc = fmaf(c.y, sv.y, acc);
                     }
@@ -423,8 +459,8 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
         for (int i = 0; i <= n_local; ++i) {
             if (i < n_local) {
                 const int b = i % kNBuf, tb = i & 1;
-                mbar_wait(a1_full + b, (uint32_t)(i / kNBuf) & 1u);
-                mbar_wait(d1_empty + tb, ((uint32_t)(i >> 1) & 1u) ^ 1u);
+                wait_bar(a1_full + b, (uint32_t)(i / kNBuf) & 1u);
+                wait_bar(d1_empty + tb, ((uint32_t)(i >> 1) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t ah = tiles_u32 + b * kTileBytes, al = ah + kPlane, d = tmem + tb * 64;
 #pragma unroll
@@ -439,8 +475,8 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
             }
             if (i >= 1) {
                 const int ii = i - 1, b = ii % kNBuf, tb = ii & 1;
-                mbar_wait(a2_full + b, (uint32_t)(ii / kNBuf) & 1u);
-                mbar_wait(d2_empty + tb, ((uint32_t)(ii >> 1) & 1u) ^ 1u);
+                wait_bar(a2_full + b, (uint32_t)(ii / kNBuf) & 1u);
+                wait_bar(d2_empty + tb, ((uint32_t)(ii >> 1) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t ah = tiles_u32 + b * kTileBytes, al = ah + kPlane, d = tmem + 128 + tb * 64;
 #pragma unroll
