@@ -42,12 +42,13 @@ namespace sedb200 {
 namespace {
 using namespace umma;
 
-constexpr int kNBuf = 3;                         // tile buffers in flight
-constexpr int kTcThreads = 20 * 32;              // five warpgroups: producers, stage-1 epilogue, 2 x stage-2 epilogue, MMA (+3 idle warps)
+constexpr int kTeams = 4;                        // tiles in flight per CTA: a team = 4 warps = one tile (4 frames)
+constexpr int kTcThreads = kTeams * 128;
 constexpr int kPlane = 128 * 128;                // one operand plane of a tile: 128 rows x 128 B
-constexpr int kTileBytes = 2 * kPlane;           // hi | lo
+constexpr int kTileBytes = 2 * kPlane;           // hi | lo; later the power spectra of the four frames (4 x 4224 B)
 constexpr int kSpecBytes = 2 * 1024;             // special rows of a tile: one 8-row atom per plane (rows 0..3 used)
 constexpr int kPStride = 33 * 32;                // floats per frame in the power-spectrum buffer (bins 0..1024 + pad)
+constexpr int kTmemCols = 128;                   // per team: D1 / D2 at +0 (64 columns, never live together), D2-special at +64
 
 // constant operands, built on the host in double precision, laid out exactly as they sit in shared memory
 struct TcConst {
@@ -68,19 +69,18 @@ struct MelTab {                                  // the mel-walk part of LogmelT
     int pad_[2];
 };
 
-// shared-memory map (bytes from the 1024-aligned base)
+// shared-memory map (bytes from the 1024-aligned base).  The special-row atoms come first: their MMA reads 128 rows,
+// i.e. 16 KB from the atom's base, of which only rows 0..3 are meaningful -- the rest must merely be mapped.
 constexpr int kOffSpec = 0;
-constexpr int kOffTiles = kOffSpec + kNBuf * kSpecBytes;            // 6144
-constexpr int kOffConst = kOffTiles + kNBuf * kTileBytes;           // 104448 (1024-aligned)
-constexpr int kOffP = kOffConst + (int)sizeof(TcConst);
-constexpr int kOffPart = kOffP + 8 * kPStride * 4;
-constexpr int kOffMel = kOffPart + 8 * kMaxSlots * 8;
-constexpr int kOffScale = kOffMel + (int)sizeof(MelTab);
-constexpr int kOffBars = kOffScale + 8 * 4 * 4;
-constexpr int kNumBars = 3 * kNBuf + 8;
-constexpr int kTcSmem = kOffBars + kNumBars * 8 + 16 + 1024;
+constexpr int kOffTiles = kOffSpec + kTeams * kSpecBytes;           // 8192
+constexpr int kOffConst = kOffTiles + kTeams * kTileBytes;          // 139264 (1024-aligned)
+constexpr int kOffPart = kOffConst + (int)sizeof(TcConst);
+constexpr int kOffMel = kOffPart + kTeams * 4 * kMaxSlots * 8;
+constexpr int kOffBars = kOffMel + (int)sizeof(MelTab);
+constexpr int kTcSmem = kOffBars + kTeams * 8 + 16 + 1024;
 static_assert(kOffTiles % 1024 == 0 && kOffConst % 1024 == 0, "swizzle atoms are 1024-byte aligned");
-static_assert(kOffBars % 8 == 0 && kOffMel % 8 == 0 && kOffP % 16 == 0, "alignment");
+static_assert(kOffBars % 8 == 0 && kOffMel % 8 == 0 && kOffPart % 16 == 0, "alignment");
+static_assert(4 * kPStride * 4 <= kTileBytes, "the four power spectra of a tile live in its operand buffer");
 static_assert(kTcSmem <= 232448, "shared memory budget");
 
 __device__ __forceinline__ uint32_t sw128(int r, int c) {          // byte offset of 16-byte chunk c of row r
@@ -111,11 +111,6 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
-// per-warpgroup register budget.  The kernel is compiled for 96 registers x 640 threads and setmaxnreg only moves registers
-// INSIDE that allocation: 56 (stage-1 epilogue) and 40 (MMA warpgroup) free 12288, the producers (160) and the two mel
-// warpgroups (112) take exactly that.
-template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 // mbarrier wait that SLEEPS in hardware (suspend-time hint) instead of polling: a polling role eats the issue slots of the
 // roles it is waiting for (first build: 700 of 1840 warp instructions per frame were wait loops).  Bounded: a pipeline
 // bug traps instead of hanging the GPU.
@@ -175,21 +170,17 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
     extern __shared__ unsigned char lmtc_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(lmtc_raw) + 1023) & ~(uintptr_t)1023);
     TcConst& cst = *reinterpret_cast<TcConst*>(smem + kOffConst);
-    float* Pall = reinterpret_cast<float*>(smem + kOffP);
     MelTab& mel = *reinterpret_cast<MelTab*>(smem + kOffMel);
-    float* scale_exp = reinterpret_cast<float*>(smem + kOffScale);            // [tile & 7][frame in tile]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
-    uint64_t *buf_free = bars, *a1_full = bars + kNBuf, *a2_full = bars + 2 * kNBuf;
-    uint64_t *d1_full = bars + 3 * kNBuf, *d1_empty = d1_full + 2, *d2_full = d1_full + 4, *d2_empty = d1_full + 6;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);              // one per team: "my MMAs have retired"
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kTeams);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int team = warp >> 2, fw = warp & 3;                                  // fw: frame of the tile = TMEM sub-partition
 
     if (tid == 0) {
-        for (int i = 0; i < kNBuf; ++i) { mbar_init(buf_free + i, 1); mbar_init(a1_full + i, 128); mbar_init(a2_full + i, 128); }
-        for (int i = 0; i < 2; ++i) { mbar_init(d1_full + i, 1); mbar_init(d1_empty + i, 4); mbar_init(d2_full + i, 1); mbar_init(d2_empty + i, 4); }
+        for (int i = 0; i < kTeams; ++i) mbar_init(bars + i, 1);
         fence_barrier_init();
     }
-    if (warp == 16) tmem_alloc(tmem_slot, 512);
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
     {
         const uint4* src = reinterpret_cast<const uint4*>(gconst);
         uint4* dst = reinterpret_cast<uint4*>(&cst);
@@ -197,115 +188,140 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
         for (int i = tid; i < kMel * kMaxTerms; i += kTcThreads) { mel.coef[i] = gtab->coef[i]; mel.gslot[i] = gtab->gslot[i]; }
         if (tid < 32) { mel.lanemask[tid] = gtab->lanemask[tid]; mel.lanebase[tid] = gtab->lanebase[tid]; }
         if (tid == 0) { mel.terms_round1 = gtab->terms_round1; mel.terms_round2 = gtab->terms_round2; }
-        for (int i = tid; i < 8 * kPStride; i += kTcThreads) Pall[i] = 0.0f;   // bins 1025.. stay zero for good
     }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = *tmem_slot + team * kTmemCols;
     const int t0 = (int)((long)blockIdx.x * n_tiles / gridDim.x), t1 = (int)((long)(blockIdx.x + 1) * n_tiles / gridDim.x);
     const int n_local = t1 - t0;
-    const uint32_t tiles_u32 = smem_u32(smem + kOffTiles), spec_u32 = smem_u32(smem + kOffSpec);
+    uint64_t* bar = bars + team;
+    uint32_t phase = 0;
+    const bool issuer = fw == 0 && lane == 0;
 
-    if (warp < 4) {
-        // ================================================= producers: one warp per frame of the tile
-        reg_inc<160>();
-        const int fw = warp, m = lane & 7, g = lane >> 3;
-        const uint32_t wrow = smem_u32(cst.win + lane * 36);
-        for (int i = 0; i < n_local; ++i) {
-            const int b = i % kNBuf;
-            const unsigned q = 4u * (unsigned)(t0 + i) + (unsigned)fw;
-            float4 v[16];
-            if (q < total_frames) {
-                const unsigned cc = q / n_frames, frame = q - cc * n_frames;
-                const T* __restrict__ xb = pcm + (long)cc * S;
-                const long start = ((long)frame - 1) * kHop;
-                if (start >= 0 && start + kNfft <= S) {
-                    const T* xs = xb + start + 4 * lane;
-                    if ((reinterpret_cast<uintptr_t>(xs) & (4 * sizeof(T) - 1)) == 0) {
+    // ---- per-thread constants of the three phases
+    const uint32_t tile = smem_u32(smem + kOffTiles + team * kTileBytes);       // A1, then A2, then P of the team's tile
+    const uint32_t spec = smem_u32(smem + kOffSpec + team * kSpecBytes);
+    // producer: rows 8 e + (lane & 7) of the frame, 16-byte chunks 2 (lane >> 3) + h
+    const int m = lane & 7, g = lane >> 3;
+    const uint32_t wrow = smem_u32(cst.win + lane * 36);
+    const uint32_t a1row = tile + (4 * fw) * 1024 + m * 128;
+    // stage-1 epilogue: TMEM lane = row position of (frame, n2)
+    const int n2 = 4 * m + g;
+    const uint32_t spec_off = spec + (uint32_t)(fw * 128 + (((n2 >> 3) ^ fw) << 4) + (n2 & 7) * 2);
+    const uint32_t tw_u32 = smem_u32(cst.tw + lane);
+    const uint32_t a2rows = tile + (4 * fw) * 1024 + g * 4;                     // + jq * 1024 + q * 128 + ((m ^ q) << 4)
+    const uint32_t ta = tmem + ((uint32_t)(32 * fw) << 16);
+    // stage-2 epilogue + mel
+    const uint32_t P = tile + fw * (kPStride * 4);
+    const uint32_t Pfwd = P + 4 * lane, Pmir = P + 4 * 2048 - 4 * lane;         // bin k1 + 64 k2 / mirror bin 2048 - k
+    const uint32_t part = smem_u32(smem + kOffPart) + warp * kMaxSlots * 8;
+    const uint32_t coef_u32 = smem_u32(mel.coef), gslot_u32 = smem_u32(mel.gslot);
+    const unsigned long long msk = mel.lanemask[lane];
+    const uint32_t slot0 = part + 8u * mel.lanebase[lane];
+    const int terms1 = mel.terms_round1, terms2 = mel.terms_round2;
+    // MMA operands (the issuing thread)
+    constexpr uint32_t idesc64 = idesc_f16(128, 64, 0, 0), idesc32 = idesc_f16(128, 32, 0, 0);
+    const uint64_t dzero = smem_desc_sw128(0, 16, 1024);
+    const uint64_t dAh = dzero | (uint64_t)((tile & 0x3FFFFu) >> 4), dAl = dzero | (uint64_t)(((tile + kPlane) & 0x3FFFFu) >> 4);
+    const uint64_t dSh = dzero | (uint64_t)((spec & 0x3FFFFu) >> 4), dSl = dzero | (uint64_t)(((spec + 1024) & 0x3FFFFu) >> 4);
+    const uint64_t dB1h = dzero | (uint64_t)((smem_u32(cst.b1[0]) & 0x3FFFFu) >> 4), dB1l = dzero | (uint64_t)((smem_u32(cst.b1[1]) & 0x3FFFFu) >> 4);
+    const uint64_t dB2h = dzero | (uint64_t)((smem_u32(cst.b2[0]) & 0x3FFFFu) >> 4), dB2l = dzero | (uint64_t)((smem_u32(cst.b2[1]) & 0x3FFFFu) >> 4);
+    const uint64_t dBsh = dzero | (uint64_t)((smem_u32(cst.b2s[0]) & 0x3FFFFu) >> 4), dBsl = dzero | (uint64_t)((smem_u32(cst.b2s[1]) & 0x3FFFFu) >> 4);
+
+    for (int i = team; i < n_local; i += kTeams) {
+        const unsigned q = 4u * (unsigned)(t0 + i) + (unsigned)fw;
+        const bool live = q < total_frames;
+        unsigned cc = 0, frame = 0;
+        if (live) { cc = q / n_frames; frame = q - cc * n_frames; }
+        // =========================================== phase 1: PCM -> Hann -> per-frame scale -> fp16 hi / lo A1 rows
+        float4 v[16];
+        if (live) {
+            const T* __restrict__ xb = pcm + (long)cc * S;
+            const long start = ((long)frame - 1) * kHop;
+            if (start >= 0 && start + kNfft <= S) {
+                const T* xs = xb + start + 4 * lane;
+                if ((reinterpret_cast<uintptr_t>(xs) & (4 * sizeof(T) - 1)) == 0) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = ld_quad(xs + 128 * j);
-                    } else {
+                    for (int j = 0; j < 16; ++j) v[j] = ld_quad(xs + 128 * j);
+                } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            v[j] = make_float4(ld_sample(xs + 128 * j), ld_sample(xs + 128 * j + 1), ld_sample(xs + 128 * j + 2),
-                                               ld_sample(xs + 128 * j + 3));
-                    }
-                } else {                                           // first / last frames of a clip: the padding rule
+                    for (int j = 0; j < 16; ++j)
+                        v[j] = make_float4(ld_sample(xs + 128 * j), ld_sample(xs + 128 * j + 1), ld_sample(xs + 128 * j + 2),
+                                           ld_sample(xs + 128 * j + 3));
+                }
+            } else {                                               // first / last frames of a clip: the padding rule
 #pragma unroll 1
-                    for (int j = 0; j < 16; ++j) {
-                        const long i0 = start + 128 * j + 4 * lane;
-                        const float4 val = make_float4(padded_sample(xb, S, i0, pad_mode), padded_sample(xb, S, i0 + 1, pad_mode),
-                                                       padded_sample(xb, S, i0 + 2, pad_mode), padded_sample(xb, S, i0 + 3, pad_mode));
+                for (int j = 0; j < 16; ++j) {
+                    const long i0 = start + 128 * j + 4 * lane;
+                    const float4 val = make_float4(padded_sample(xb, S, i0, pad_mode), padded_sample(xb, S, i0 + 1, pad_mode),
+                                                   padded_sample(xb, S, i0 + 2, pad_mode), padded_sample(xb, S, i0 + 3, pad_mode));
 #pragma unroll
-                        for (int jj = 0; jj < 16; ++jj)             // v[] stays in registers: no dynamic index
-                            if (jj == j) v[jj] = val;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            // per-frame power-of-two scale: max |x| of the frame lands in [256, 512), so |Y| < 2^15 and the lo planes
-            // stay clear of fp16's subnormal range
-            float amax = 0.0f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) amax = fmaxf(fmaxf(amax, fabsf(v[j].x)), fmaxf(fmaxf(fabsf(v[j].y), fabsf(v[j].z)), fabsf(v[j].w)));
-            unsigned E = __reduce_max_sync(0xffffffffu, __float_as_uint(amax)) >> 23;
-            E = E < 8u ? 8u : E;
-            const float s = __uint_as_float((262u - E) << 23);
-            // Hann: w for the first half, 1 - w for the second (periodic window: w[n + 1024] = 1 - w[n])
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 w = lds128c(wrow + 16 * j);
-                const float2 wa = __fmul2_rn(make_float2(w.x, w.y), make_float2(s, s)), wb = __fmul2_rn(make_float2(w.z, w.w), make_float2(s, s));
-                const float2 ua = __ffma2_rn(make_float2(-w.x, -w.y), make_float2(s, s), make_float2(s, s));
-                const float2 ub = __ffma2_rn(make_float2(-w.z, -w.w), make_float2(s, s), make_float2(s, s));
-                const float2 p0 = __fmul2_rn(make_float2(v[j].x, v[j].y), wa), p1 = __fmul2_rn(make_float2(v[j].z, v[j].w), wb);
-                const float2 r0 = __fmul2_rn(make_float2(v[j + 8].x, v[j + 8].y), ua), r1 = __fmul2_rn(make_float2(v[j + 8].z, v[j + 8].w), ub);
-                v[j] = make_float4(p0.x, p0.y, p1.x, p1.y);
-                v[j + 8] = make_float4(r0.x, r0.y, r1.x, r1.y);
-            }
-            wait_bar(buf_free + b, ((uint32_t)(i / kNBuf) & 1u) ^ 1u);     // stage 2 of the tile that used this buffer retired
-            const uint32_t tile = tiles_u32 + b * kTileBytes + (4 * fw) * 1024 + m * 128;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t hi[4], lo[4];
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const float4 a4 = v[8 * h + 2 * jj], b4 = v[8 * h + 2 * jj + 1];
-                        const float a = e == 0 ? a4.x : e == 1 ? a4.y : e == 2 ? a4.z : a4.w;
-                        const float bb = e == 0 ? b4.x : e == 1 ? b4.y : e == 2 ? b4.z : b4.w;
-                        split2(a, bb, hi[jj], lo[jj]);
-                    }
-                    const uint32_t addr = tile + e * 1024 + (uint32_t)(((2 * g + h) ^ m) << 4);
-                    sts128(addr, hi[0], hi[1], hi[2], hi[3]);
-                    sts128(addr + kPlane, lo[0], lo[1], lo[2], lo[3]);
+                    for (int jj = 0; jj < 16; ++jj)                 // v[] stays in registers: no dynamic index
+                        if (jj == j) v[jj] = val;
                 }
             }
-            if (lane == 0) scale_exp[(i & 7) * 4 + fw] = (float)(135 - (int)E);
-            fence_proxy_async();
-            mbar_arrive(a1_full + b);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-    } else if (warp < 8) {
-        // ================================================= stage-1 epilogue: TMEM lane = row position of (frame, n2)
-        reg_dec<56>();
-        const int fw = warp - 4;
-        const int n2 = 4 * (lane & 7) + (lane >> 3);
-        uint32_t xo[8];
+        // per-frame power-of-two scale: max |x| of the frame lands in [256, 512), so |Y| < 2^15 and the lo planes stay
+        // clear of fp16's subnormal range
+        float amax = 0.0f;
 #pragma unroll
-        for (int mm = 0; mm < 8; ++mm) xo[mm] = (uint32_t)((((lane & 7) ^ mm) << 4) + (lane >> 3) * 4);
-        const uint32_t spec_off = (uint32_t)(fw * 128 + (((n2 >> 3) ^ fw) << 4) + (n2 & 7) * 2);
-        const uint32_t tw_u32 = smem_u32(cst.tw + lane);
-        for (int i = 0; i < n_local; ++i) {
-            const int b = i % kNBuf, tb = i & 1;
-            wait_bar(d1_full + tb, (uint32_t)(i >> 1) & 1u);
+        for (int j = 0; j < 16; ++j) amax = fmaxf(fmaxf(amax, fabsf(v[j].x)), fmaxf(fmaxf(fabsf(v[j].y), fabsf(v[j].z)), fabsf(v[j].w)));
+        unsigned E = __reduce_max_sync(0xffffffffu, __float_as_uint(amax)) >> 23;
+        E = E < 8u ? 8u : E;
+        const float s = __uint_as_float((262u - E) << 23);
+        const float unscale = -1.3862943611198906f * (float)(135 - (int)E);       // -2 ln2 * exponent, added after the log
+        // Hann: w for the first half, 1 - w for the second (periodic window: w[n + 1024] = 1 - w[n])
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 w = lds128c(wrow + 16 * j);
+            const float2 wa = __fmul2_rn(make_float2(w.x, w.y), make_float2(s, s)), wb = __fmul2_rn(make_float2(w.z, w.w), make_float2(s, s));
+            const float2 ua = __ffma2_rn(make_float2(-w.x, -w.y), make_float2(s, s), make_float2(s, s));
+            const float2 ub = __ffma2_rn(make_float2(-w.z, -w.w), make_float2(s, s), make_float2(s, s));
+            const float2 p0 = __fmul2_rn(make_float2(v[j].x, v[j].y), wa), p1 = __fmul2_rn(make_float2(v[j].z, v[j].w), wb);
+            const float2 r0 = __fmul2_rn(make_float2(v[j + 8].x, v[j + 8].y), ua), r1 = __fmul2_rn(make_float2(v[j + 8].z, v[j + 8].w), ub);
+            v[j] = make_float4(p0.x, p0.y, p1.x, p1.y);
+            v[j + 8] = make_float4(r0.x, r0.y, r1.x, r1.y);
+        }
+        named_bar(1 + team, 128);                                  // the team's previous mel walk (it reads this buffer) is over
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const float4 a4 = v[8 * h + 2 * jj], b4 = v[8 * h + 2 * jj + 1];
+                    const float a = e == 0 ? a4.x : e == 1 ? a4.y : e == 2 ? a4.z : a4.w;
+                    const float bb = e == 0 ? b4.x : e == 1 ? b4.y : e == 2 ? b4.z : b4.w;
+                    split2(a, bb, hi[jj], lo[jj]);
+                }
+                const uint32_t addr = a1row + e * 1024 + (uint32_t)(((2 * g + h) ^ m) << 4);
+                sts128(addr, hi[0], hi[1], hi[2], hi[3]);
+                sts128(addr + kPlane, lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+        fence_proxy_async();
+        named_bar(1 + team, 128);
+        if (issuer) {
             tc_fence_after();
-            const uint32_t ta = tmem + ((uint32_t)(32 * fw) << 16) + tb * 64;
-            const uint32_t rows = tiles_u32 + b * kTileBytes + (4 * fw) * 1024;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                mma_bf16(tmem, dAh + 2 * k, dB1h + 2 * k, idesc64, k != 0);
+                mma_bf16(tmem, dAh + 2 * k, dB1l + 2 * k, idesc64, 1);
+                mma_bf16(tmem, dAl + 2 * k, dB1h + 2 * k, idesc64, 1);
+            }
+            mma_commit(bar);
+        }
+        wait_bar(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        // =========================================== phase 2: TMEM -> twiddle -> fp16 hi / lo A2 rows, in place over A1
+        {
             float y32 = 0.0f;
 #pragma unroll
             for (int jq = 0; jq < 4; ++jq) {
@@ -313,200 +329,140 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
                 tmem_ld8_nowait(ta + 8 * jq, re);
                 tmem_ld8_nowait(ta + 32 + 8 * jq, im);
                 tmem_ld_wait();
-                if (jq == 3) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(d1_empty + tb);     // the accumulator sits in registers
-                }
                 if (jq == 0) { y32 = im[0]; im[0] = 0.0f; }         // the slot of Im Y[0] (= 0) carries Y[32]
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
-                    const float4 t = lds128(tw_u32 + (4 * jq + p) * 512);       // volatile: 16 hoisted float4s would not fit
+                    const float4 t = lds128(tw_u32 + (4 * jq + p) * 512);
                     const float2 r2 = make_float2(re[2 * p], re[2 * p + 1]), i2 = make_float2(im[2 * p], im[2 * p + 1]);
                     const float2 c2 = make_float2(t.x, t.y), s2 = make_float2(t.z, t.w);
                     const float2 zr = __ffma2_rn(i2, s2, __fmul2_rn(r2, c2));                       // (re + i im)(c - i s)
                     const float2 zi = __ffma2_rn(make_float2(-r2.x, -r2.y), s2, __fmul2_rn(i2, c2));
                     uint32_t hi, lo;
                     split2(zr.x, zi.x, hi, lo);
-                    uint32_t addr = rows + jq * 1024 + (2 * p) * 128 + xo[2 * p];
+                    uint32_t addr = a2rows + jq * 1024 + (2 * p) * 128 + (uint32_t)((m ^ (2 * p)) << 4);
                     sts32(addr, hi);
                     sts32(addr + kPlane, lo);
                     split2(zr.y, zi.y, hi, lo);
-                    addr = rows + jq * 1024 + (2 * p + 1) * 128 + xo[2 * p + 1];
+                    addr = a2rows + jq * 1024 + (2 * p + 1) * 128 + (uint32_t)((m ^ (2 * p + 1)) << 4);
                     sts32(addr, hi);
                     sts32(addr + kPlane, lo);
                 }
             }
-            {
-                uint32_t hi, lo;
-                split2(y32, 0.0f, hi, lo);
-                sts16(spec_u32 + b * kSpecBytes + spec_off, hi);
-                sts16(spec_u32 + b * kSpecBytes + 1024 + spec_off, lo);
-            }
-            fence_proxy_async();
-            mbar_arrive(a2_full + b);
+            uint32_t hi, lo;
+            split2(y32, 0.0f, hi, lo);
+            sts16(spec_off, hi);
+            sts16(spec_off + 1024, lo);
         }
-    } else if (warp < 16) {
-        // ================================================= stage-2 epilogue + mel: two sets alternate tiles
-        reg_inc<112>();
-        const int set = (warp - 8) >> 2, fw = (warp - 8) & 3;
-        const uint32_t P = smem_u32(Pall + (set * 4 + fw) * kPStride);
-        const uint32_t Pfwd = P + 4 * lane, Pmir = P + 4 * 2048 - 4 * lane;      // bin k1 + 64 k2 / mirror bin 2048 - k
-        const uint32_t part = smem_u32(smem + kOffPart) + (warp - 8) * kMaxSlots * 8;
-        const uint32_t coef_u32 = smem_u32(mel.coef), gslot_u32 = smem_u32(mel.gslot);
-        const unsigned long long msk = mel.lanemask[lane];
-        const uint32_t slot0 = part + 8u * mel.lanebase[lane];
-        const int terms1 = mel.terms_round1, terms2 = mel.terms_round2;
-        for (int i = set; i < n_local; i += 2) {
-            wait_bar(d2_full + set, (uint32_t)(i >> 1) & 1u);
+        tc_fence_before();
+        fence_proxy_async();
+        named_bar(1 + team, 128);
+        if (issuer) {
             tc_fence_after();
-            const uint32_t ta = tmem + ((uint32_t)(32 * fw) << 16) + 128 + set * 64;
-            named_bar(1 + set, 128);                               // the set's previous walk is over (special bins cross warps)
 #pragma unroll
-            for (int jq = 0; jq < 4; ++jq) {
-                float re[8], im[8];
-                tmem_ld8_nowait(ta + 8 * jq, re);
-                tmem_ld8_nowait(ta + 32 + 8 * jq, im);
-                tmem_ld_wait();
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int k2 = 8 * jq + e;
-                    const float pw = fmaf(re[e], re[e], im[e] * im[e]);          // 4 |X|^2 (B2 is doubled)
-                    if (k2 < 16) stsf32(Pfwd + 256 * k2, pw);                     // bin k1 + 64 k2
-                    else if (lane != 0 || k2 == 16) stsf32(Pmir - 256 * k2, pw);  // mirror bin 2048 - k
-                }
+            for (int k = 0; k < 4; ++k) {
+                mma_bf16(tmem, dAh + 2 * k, dB2h + 2 * k, idesc64, k != 0);
+                mma_bf16(tmem, dAh + 2 * k, dB2l + 2 * k, idesc64, 1);
+                mma_bf16(tmem, dAl + 2 * k, dB2h + 2 * k, idesc64, 1);
             }
-            if (fw == 0) {                                         // special rows: TMEM lanes 0..3 = the tile's frames
-                float sp[32];
-                tmem_ld32(tmem + 256 + set * 32, sp);
-                if (lane < 4) {
-                    const uint32_t Ps = smem_u32(Pall + (set * 4 + lane) * kPStride) + 4 * 32;
 #pragma unroll
-                    for (int k2 = 0; k2 < 16; ++k2) stsf32(Ps + 256 * k2, fmaf(sp[k2], sp[k2], sp[16 + k2] * sp[16 + k2]));
-                }
+            for (int k = 0; k < 2; ++k) {
+                mma_bf16(tmem + 64, dSh + 2 * k, dBsh + 2 * k, idesc32, k != 0);
+                mma_bf16(tmem + 64, dSh + 2 * k, dBsl + 2 * k, idesc32, 1);
+                mma_bf16(tmem + 64, dSl + 2 * k, dBsh + 2 * k, idesc32, 1);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(d2_empty + set);
-            named_bar(1 + set, 128);                               // every bin of the four frames is in place
-            const unsigned q = 4u * (unsigned)(t0 + i) + (unsigned)fw;
-            if (q >= total_frames) continue;
-            const float unscale = -1.3862943611198906f * scale_exp[(i & 7) * 4 + fw];     // -2 ln2 * exponent
-            // ---- mel projection: the walk of logmel.cu (per-lane (sum P, sum i P) per band-edge segment, fixed order)
+            mma_commit(bar);
+        }
+        wait_bar(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        // =========================================== phase 3: TMEM -> |X|^2 -> P of the frame (over the dead operands)
+#pragma unroll
+        for (int jq = 0; jq < 4; ++jq) {
+            float re[8], im[8];
+            tmem_ld8_nowait(ta + 8 * jq, re);
+            tmem_ld8_nowait(ta + 32 + 8 * jq, im);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int k2 = 8 * jq + e;
+                const float pw = fmaf(re[e], re[e], im[e] * im[e]);              // 4 |X|^2 (B2 is doubled)
+                if (k2 < 16) stsf32(Pfwd + 256 * k2, pw);                         // bin k1 + 64 k2
+                else if (lane != 0 || k2 == 16) stsf32(Pmir - 256 * k2, pw);      // mirror bin 2048 - k
+            }
+        }
+        if (lane < 31) stsf32(P + 4 * (1025 + lane), 0.0f);                       // the walk reads 33 x 32 bins
+        if (fw == 0) {                                             // special rows: TMEM lanes 0..3 = the tile's frames
+            float sp[32];
+            tmem_ld32(tmem + 64, sp);
+            if (lane < 4) {
+                const uint32_t Ps = tile + lane * (kPStride * 4) + 4 * 32;
+#pragma unroll
+                for (int k2 = 0; k2 < 16; ++k2) stsf32(Ps + 256 * k2, fmaf(sp[k2], sp[k2], sp[16 + k2] * sp[16 + k2]));
+            }
+        }
+        tc_fence_before();
+        named_bar(1 + team, 128);                                  // every bin of the four frames is in place
+        if (!live) continue;
+        // ---- mel projection: the walk of logmel.cu (per-lane (sum P, sum i P) per band-edge segment, fixed order)
+        {
+            const uint32_t Pl = P + 4 * lane * kBinStride;
+            const unsigned mlo = (unsigned)msk, mhi = (unsigned)(msk >> 32);
+            unsigned slot = slot0;
+            float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+            for (int ii = 0; ii < kBinStride; ++ii) {
+                const float p = lds32(Pl + 4 * ii);
+                if (ii > 0) {
+                    asm volatile(
+                        "{\n\t.reg .pred q;\n\t"
+                        "setp.ne.u32 q, %3, 0;\n\t"
+                        "@q st.shared.v2.f32 [%0], {%1, %2};\n\t"
+                        "@q add.u32 %0, %0, 8;\n\t"
+                        "@q mov.f32 %1, 0f00000000;\n\t"
+                        "@q mov.f32 %2, 0f00000000;\n\t}"
+                        : "+r"(slot), "+f"(s0), "+f"(s1)
+                        : "r"((ii < 32 ? mlo : mhi) & (1u << (ii & 31)))
+                        : "memory");
+                }
+                s0 += p;
+                s1 = fmaf((float)ii, p, s1);
+            }
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(slot), "f"(s0), "f"(s1) : "memory");
+        }
+        __syncwarp();
+        {
+            const unsigned clip = cc / (unsigned)n_ch, ch = cc - clip * (unsigned)n_ch;
+            float* o = out + (((long)clip * n_frames + frame) * n_ch + ch) * kMel;
             {
-                const uint32_t Pl = P + 4 * lane * kBinStride;
-                const unsigned mlo = (unsigned)msk, mhi = (unsigned)(msk >> 32);
-                unsigned slot = slot0;
-                float s0 = 0.0f, s1 = 0.0f;
-#pragma unroll
-                for (int ii = 0; ii < kBinStride; ++ii) {
-                    const float p = lds32(Pl + 4 * ii);
-                    if (ii > 0) {
-                        asm volatile(
-                            "{\n\t.reg .pred q;\n\t"
-                            "setp.ne.u32 q, %3, 0;\n\t"
-                            "@q st.shared.v2.f32 [%0], {%1, %2};\n\t"
-                            "@q add.u32 %0, %0, 8;\n\t"
-                            "@q mov.f32 %1, 0f00000000;\n\t"
-                            "@q mov.f32 %2, 0f00000000;\n\t}"
-                            : "+r"(slot), "+f"(s0), "+f"(s1)
-                            : "r"((ii < 32 ? mlo : mhi) & (1u << (ii & 31)))
-                            : "memory");
-                    }
-                    s0 += p;
-                    s1 = fmaf((float)ii, p, s1);
+                const int bnd = kMel - kBandsRound1 + lane;
+                float acc = 0.0f;
+                for (int ii = 0; ii < terms1; ++ii) {
+                    const float2 c = lds64c(coef_u32 + 8 * (bnd * kMaxTerms + ii));
+                    const float2 sv = lds64(part + 8 * lds8c(gslot_u32 + bnd * kMaxTerms + ii));
+                    acc = fmaf(c.x, sv.x, acc);
+                    acc = fmaf(c.y, sv.y, acc);
                 }
-                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(slot), "f"(s0), "f"(s1) : "memory");
+                o[bnd] = logf(acc) + unscale;
             }
-            __syncwarp();
-            {
-                const unsigned cc = q / n_frames, frame = q - cc * n_frames;
-                const unsigned clip = cc / (unsigned)n_ch, ch = cc - clip * (unsigned)n_ch;
-                float* o = out + (((long)clip * n_frames + frame) * n_ch + ch) * kMel;
-                {
-                    const int bnd = kMel - kBandsRound1 + lane;
-                    float acc = 0.0f;
-                    for (int ii = 0; ii < terms1; ++ii) {
-                        const float2 c = lds64c(coef_u32 + 8 * (bnd * kMaxTerms + ii));
-                        const float2 sv = lds64(part + 8 * lds8c(gslot_u32 + bnd * kMaxTerms + ii));
-                        acc = fmaf(c.x, sv.x, acc);
-                        acc = fmaf(c.y, sv.y, acc);
-                    }
-                    o[bnd] = logf(acc) + unscale;
+            if (lane < kMel - kBandsRound1) {
+                const int bnd = lane;
+                float acc = 0.0f;
+                for (int ii = 0; ii < terms2; ++ii) {
+                    const float2 c = lds64c(coef_u32 + 8 * (bnd * kMaxTerms + ii));
+                    const float2 sv = lds64(part + 8 * lds8c(gslot_u32 + bnd * kMaxTerms + ii));
+                    acc = fmaf(c.x, sv.x, acc);
+                    acc = fmaf(c.y, sv.y, acc);
                 }
-                if (lane < kMel - kBandsRound1) {
-                    const int bnd = lane;
-                    float acc = 0.0f;
-                    for (int ii = 0; ii < terms2; ++ii) {
-                        const float2 c = lds64c(coef_u32 + 8 * (bnd * kMaxTerms + ii));
-                        const float2 sv = lds64(part + 8 * lds8c(gslot_u32 + bnd * kMaxTerms + ii));
-                        acc = fmaf(c.x, sv.x, acc);
-                        acc = fmaf(c.y, sv.y, acc);
-                    }
-                    o[bnd] = logf(acc) + unscale;
-                }
-            }
-            __syncwarp();
-        }
-    } else {
-        reg_dec<40>();
-        if (warp == 16 && lane == 0) {
-        // ================================================= the MMA thread: stage 1 of tile i, then stage 2 of tile i - 1
-        constexpr uint32_t idesc64 = idesc_f16(128, 64, 0, 0), idesc32 = idesc_f16(128, 32, 0, 0);
-        const uint32_t b1h = smem_u32(cst.b1[0]), b1l = smem_u32(cst.b1[1]);
-        const uint32_t b2h = smem_u32(cst.b2[0]), b2l = smem_u32(cst.b2[1]);
-        const uint32_t bsh = smem_u32(cst.b2s[0]), bsl = smem_u32(cst.b2s[1]);
-        for (int i = 0; i <= n_local; ++i) {
-            if (i < n_local) {
-                const int b = i % kNBuf, tb = i & 1;
-                wait_bar(a1_full + b, (uint32_t)(i / kNBuf) & 1u);
-                wait_bar(d1_empty + tb, ((uint32_t)(i >> 1) & 1u) ^ 1u);
-                tc_fence_after();
-                const uint32_t ah = tiles_u32 + b * kTileBytes, al = ah + kPlane, d = tmem + tb * 64;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint64_t dah = smem_desc_sw128(ah + k * 32, 16, 1024), dal = smem_desc_sw128(al + k * 32, 16, 1024);
-                    const uint64_t dbh = smem_desc_sw128(b1h + k * 32, 16, 1024), dbl = smem_desc_sw128(b1l + k * 32, 16, 1024);
-                    mma_bf16(d, dah, dbh, idesc64, k != 0);
-                    mma_bf16(d, dah, dbl, idesc64, 1);
-                    mma_bf16(d, dal, dbh, idesc64, 1);
-                }
-                mma_commit(d1_full + tb);
-            }
-            if (i >= 1) {
-                const int ii = i - 1, b = ii % kNBuf, tb = ii & 1;
-                wait_bar(a2_full + b, (uint32_t)(ii / kNBuf) & 1u);
-                wait_bar(d2_empty + tb, ((uint32_t)(ii >> 1) & 1u) ^ 1u);
-                tc_fence_after();
-                const uint32_t ah = tiles_u32 + b * kTileBytes, al = ah + kPlane, d = tmem + 128 + tb * 64;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint64_t dah = smem_desc_sw128(ah + k * 32, 16, 1024), dal = smem_desc_sw128(al + k * 32, 16, 1024);
-                    const uint64_t dbh = smem_desc_sw128(b2h + k * 32, 16, 1024), dbl = smem_desc_sw128(b2l + k * 32, 16, 1024);
-                    mma_bf16(d, dah, dbh, idesc64, k != 0);
-                    mma_bf16(d, dah, dbl, idesc64, 1);
-                    mma_bf16(d, dal, dbh, idesc64, 1);
-                }
-                const uint32_t sh = spec_u32 + b * kSpecBytes, sl = sh + 1024, ds = tmem + 256 + tb * 32;
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const uint64_t dah = smem_desc_sw128(sh + k * 32, 16, 1024), dal = smem_desc_sw128(sl + k * 32, 16, 1024);
-                    const uint64_t dbh = smem_desc_sw128(bsh + k * 32, 16, 1024), dbl = smem_desc_sw128(bsl + k * 32, 16, 1024);
-                    mma_bf16(ds, dah, dbh, idesc32, k != 0);
-                    mma_bf16(ds, dah, dbl, idesc32, 1);
-                    mma_bf16(ds, dal, dbh, idesc32, 1);
-                }
-                mma_commit(d2_full + tb);
-                mma_commit(buf_free + b);
+                o[bnd] = logf(acc) + unscale;
             }
         }
-        }
+        __syncwarp();
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 16) {
+    if (warp == 0) {
         tc_fence_after();
-        tmem_dealloc(tmem, 512);
+        tmem_dealloc(*tmem_slot, 512);
     }
 }
 
