@@ -168,7 +168,9 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
                  unsigned total_frames, int n_tiles, int pad_mode, const TcConst* __restrict__ gconst,
                  const LogmelTables* __restrict__ gtab) {
     extern __shared__ unsigned char lmtc_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(lmtc_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by pointer arithmetic ON the shared array (an integer round trip would turn every access below
+    // into a generic LD / ST with 64-bit address arithmetic instead of LDS / STS with immediate offsets)
+    unsigned char* smem = lmtc_raw + ((1024u - (smem_u32(lmtc_raw) & 1023u)) & 1023u);
     TcConst& cst = *reinterpret_cast<TcConst*>(smem + kOffConst);
     MelTab& mel = *reinterpret_cast<MelTab*>(smem + kOffMel);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);              // one per team: "my MMAs have retired"
@@ -201,25 +203,26 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
     const bool issuer = fw == 0 && lane == 0;
 
     // ---- per-thread constants of the three phases
-    const uint32_t tile = smem_u32(smem + kOffTiles + team * kTileBytes);       // A1, then A2, then P of the team's tile
-    const uint32_t spec = smem_u32(smem + kOffSpec + team * kSpecBytes);
+    unsigned char* const tilep = smem + kOffTiles + team * kTileBytes;          // A1, then A2, then P of the team's tile
+    unsigned char* const specp = smem + kOffSpec + team * kSpecBytes;
+    const uint32_t tile = smem_u32(tilep), spec = smem_u32(specp);
     // producer: rows 8 e + (lane & 7) of the frame, 16-byte chunks 2 (lane >> 3) + h
     const int m = lane & 7, g = lane >> 3;
-    const uint32_t wrow = smem_u32(cst.win + lane * 36);
-    const uint32_t a1row = tile + (4 * fw) * 1024 + m * 128;
+    const float4* const wrow = reinterpret_cast<const float4*>(cst.win + lane * 36);
+    unsigned char* const a1row = tilep + (4 * fw) * 1024 + m * 128;
     // stage-1 epilogue: TMEM lane = row position of (frame, n2)
     const int n2 = 4 * m + g;
-    const uint32_t spec_off = spec + (uint32_t)(fw * 128 + (((n2 >> 3) ^ fw) << 4) + (n2 & 7) * 2);
-    const uint32_t tw_u32 = smem_u32(cst.tw + lane);
-    const uint32_t a2rows = tile + (4 * fw) * 1024 + g * 4;                     // + jq * 1024 + q * 128 + ((m ^ q) << 4)
+    unsigned short* const spec_row = reinterpret_cast<unsigned short*>(specp + fw * 128 + (((n2 >> 3) ^ fw) << 4) + (n2 & 7) * 2);
+    const float4* const twp = cst.tw + lane;
+    unsigned char* const a2rows = tilep + (4 * fw) * 1024 + g * 4;              // + jq * 1024 + q * 128 + ((m ^ q) << 4)
     const uint32_t ta = tmem + ((uint32_t)(32 * fw) << 16);
     // stage-2 epilogue + mel
-    const uint32_t P = tile + fw * (kPStride * 4);
-    const uint32_t Pfwd = P + 4 * lane, Pmir = P + 4 * 2048 - 4 * lane;         // bin k1 + 64 k2 / mirror bin 2048 - k
-    const uint32_t part = smem_u32(smem + kOffPart) + warp * kMaxSlots * 8;
-    const uint32_t coef_u32 = smem_u32(mel.coef), gslot_u32 = smem_u32(mel.gslot);
+    float* const P = reinterpret_cast<float*>(tilep) + fw * kPStride;
+    float* const Pfwd = P + lane;                                               // bin k1 + 64 k2
+    float* const Pmir = P + 2048 - lane;                                        // mirror bin 2048 - k
+    float2* const part = reinterpret_cast<float2*>(smem + kOffPart) + warp * kMaxSlots;
     const unsigned long long msk = mel.lanemask[lane];
-    const uint32_t slot0 = part + 8u * mel.lanebase[lane];
+    const uint32_t slot0 = smem_u32(part + mel.lanebase[lane]);
     const int terms1 = mel.terms_round1, terms2 = mel.terms_round2;
     // MMA operands (the issuing thread)
     constexpr uint32_t idesc64 = idesc_f16(128, 64, 0, 0), idesc32 = idesc_f16(128, 32, 0, 0);
@@ -231,13 +234,13 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
     const uint64_t dBsh = dzero | (uint64_t)((smem_u32(cst.b2s[0]) & 0x3FFFFu) >> 4), dBsl = dzero | (uint64_t)((smem_u32(cst.b2s[1]) & 0x3FFFFu) >> 4);
 
     for (int i = team; i < n_local; i += kTeams) {
-        const unsigned q = 4u * (unsigned)(t0 + i) + (unsigned)fw;
-        const bool live = q < total_frames;
-        unsigned cc = 0, frame = 0;
-        if (live) { cc = q / n_frames; frame = q - cc * n_frames; }
+        const unsigned q0 = 4u * (unsigned)(t0 + i) + (unsigned)fw;
+        const bool live = q0 < total_frames;
+        const unsigned q = live ? q0 : total_frames - 1;          // a dead row of the last tile recomputes the last frame
+        const unsigned cc = q / n_frames, frame = q - cc * n_frames;
         // =========================================== phase 1: PCM -> Hann -> per-frame scale -> fp16 hi / lo A1 rows
         float4 v[16];
-        if (live) {
+        {
             const T* __restrict__ xb = pcm + (long)cc * S;
             const long start = ((long)frame - 1) * kHop;
             if (start >= 0 && start + kNfft <= S) {
@@ -262,9 +265,6 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
                         if (jj == j) v[jj] = val;
                 }
             }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         // per-frame power-of-two scale: max |x| of the frame lands in [256, 512), so |Y| < 2^15 and the lo planes stay
         // clear of fp16's subnormal range
@@ -278,7 +278,7 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
         // Hann: w for the first half, 1 - w for the second (periodic window: w[n + 1024] = 1 - w[n])
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float4 w = lds128c(wrow + 16 * j);
+            const float4 w = wrow[j];
             const float2 wa = __fmul2_rn(make_float2(w.x, w.y), make_float2(s, s)), wb = __fmul2_rn(make_float2(w.z, w.w), make_float2(s, s));
             const float2 ua = __ffma2_rn(make_float2(-w.x, -w.y), make_float2(s, s), make_float2(s, s));
             const float2 ub = __ffma2_rn(make_float2(-w.z, -w.w), make_float2(s, s), make_float2(s, s));
@@ -300,9 +300,9 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
                     const float bb = e == 0 ? b4.x : e == 1 ? b4.y : e == 2 ? b4.z : b4.w;
                     split2(a, bb, hi[jj], lo[jj]);
                 }
-                const uint32_t addr = a1row + e * 1024 + (uint32_t)(((2 * g + h) ^ m) << 4);
-                sts128(addr, hi[0], hi[1], hi[2], hi[3]);
-                sts128(addr + kPlane, lo[0], lo[1], lo[2], lo[3]);
+                unsigned char* addr = a1row + e * 1024 + (((2 * g + h) ^ m) << 4);
+                *reinterpret_cast<uint4*>(addr) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(addr + kPlane) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
         }
         fence_proxy_async();
@@ -317,8 +317,9 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
             }
             mma_commit(bar);
         }
-        wait_bar(bar, phase);
+        if (fw == 0) wait_bar(bar, phase);                         // one warp polls; the others sleep at the barrier
         phase ^= 1;
+        named_bar(1 + team, 128);
         tc_fence_after();
         // =========================================== phase 2: TMEM -> twiddle -> fp16 hi / lo A2 rows, in place over A1
         {
@@ -332,26 +333,26 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
                 if (jq == 0) { y32 = im[0]; im[0] = 0.0f; }         // the slot of Im Y[0] (= 0) carries Y[32]
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
-                    const float4 t = lds128(tw_u32 + (4 * jq + p) * 512);
+                    const float4 t = twp[(4 * jq + p) * 32];
                     const float2 r2 = make_float2(re[2 * p], re[2 * p + 1]), i2 = make_float2(im[2 * p], im[2 * p + 1]);
                     const float2 c2 = make_float2(t.x, t.y), s2 = make_float2(t.z, t.w);
                     const float2 zr = __ffma2_rn(i2, s2, __fmul2_rn(r2, c2));                       // (re + i im)(c - i s)
                     const float2 zi = __ffma2_rn(make_float2(-r2.x, -r2.y), s2, __fmul2_rn(i2, c2));
                     uint32_t hi, lo;
                     split2(zr.x, zi.x, hi, lo);
-                    uint32_t addr = a2rows + jq * 1024 + (2 * p) * 128 + (uint32_t)((m ^ (2 * p)) << 4);
-                    sts32(addr, hi);
-                    sts32(addr + kPlane, lo);
+                    unsigned char* addr = a2rows + jq * 1024 + (2 * p) * 128 + ((m ^ (2 * p)) << 4);
+                    *reinterpret_cast<uint32_t*>(addr) = hi;
+                    *reinterpret_cast<uint32_t*>(addr + kPlane) = lo;
                     split2(zr.y, zi.y, hi, lo);
-                    addr = a2rows + jq * 1024 + (2 * p + 1) * 128 + (uint32_t)((m ^ (2 * p + 1)) << 4);
-                    sts32(addr, hi);
-                    sts32(addr + kPlane, lo);
+                    addr = a2rows + jq * 1024 + (2 * p + 1) * 128 + ((m ^ (2 * p + 1)) << 4);
+                    *reinterpret_cast<uint32_t*>(addr) = hi;
+                    *reinterpret_cast<uint32_t*>(addr + kPlane) = lo;
                 }
             }
             uint32_t hi, lo;
             split2(y32, 0.0f, hi, lo);
-            sts16(spec_off, hi);
-            sts16(spec_off + 1024, lo);
+            spec_row[0] = (unsigned short)hi;
+            spec_row[512] = (unsigned short)lo;
         }
         tc_fence_before();
         fence_proxy_async();
@@ -372,8 +373,9 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
             }
             mma_commit(bar);
         }
-        wait_bar(bar, phase);
+        if (fw == 0) wait_bar(bar, phase);
         phase ^= 1;
+        named_bar(1 + team, 128);
         tc_fence_after();
         // =========================================== phase 3: TMEM -> |X|^2 -> P of the frame (over the dead operands)
 #pragma unroll
@@ -383,21 +385,26 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
             tmem_ld8_nowait(ta + 32 + 8 * jq, im);
             tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int k2 = 8 * jq + e;
-                const float pw = fmaf(re[e], re[e], im[e] * im[e]);              // 4 |X|^2 (B2 is doubled)
-                if (k2 < 16) stsf32(Pfwd + 256 * k2, pw);                         // bin k1 + 64 k2
-                else if (lane != 0 || k2 == 16) stsf32(Pmir - 256 * k2, pw);      // mirror bin 2048 - k
+            for (int e2 = 0; e2 < 4; ++e2) {
+                const float2 r2 = make_float2(re[2 * e2], re[2 * e2 + 1]), i2 = make_float2(im[2 * e2], im[2 * e2 + 1]);
+                const float2 pw2 = __ffma2_rn(r2, r2, __fmul2_rn(i2, i2));       // 4 |X|^2 (B2 is doubled)
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int k2 = 8 * jq + 2 * e2 + u;
+                    const float pw = u == 0 ? pw2.x : pw2.y;
+                    if (k2 < 16) Pfwd[64 * k2] = pw;                              // bin k1 + 64 k2
+                    else if (lane != 0 || k2 == 16) Pmir[-64 * k2] = pw;          // mirror bin 2048 - k
+                }
             }
         }
-        if (lane < 31) stsf32(P + 4 * (1025 + lane), 0.0f);                       // the walk reads 33 x 32 bins
+        if (lane < 31) P[1025 + lane] = 0.0f;                       // the walk reads 33 x 32 bins
         if (fw == 0) {                                             // special rows: TMEM lanes 0..3 = the tile's frames
             float sp[32];
             tmem_ld32(tmem + 64, sp);
             if (lane < 4) {
-                const uint32_t Ps = tile + lane * (kPStride * 4) + 4 * 32;
+                float* Ps = reinterpret_cast<float*>(tilep) + lane * kPStride + 32;
 #pragma unroll
-                for (int k2 = 0; k2 < 16; ++k2) stsf32(Ps + 256 * k2, fmaf(sp[k2], sp[k2], sp[16 + k2] * sp[16 + k2]));
+                for (int k2 = 0; k2 < 16; ++k2) Ps[64 * k2] = fmaf(sp[k2], sp[k2], sp[16 + k2] * sp[16 + k2]);
             }
         }
         tc_fence_before();
@@ -405,13 +412,13 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
         if (!live) continue;
         // ---- mel projection: the walk of logmel.cu (per-lane (sum P, sum i P) per band-edge segment, fixed order)
         {
-            const uint32_t Pl = P + 4 * lane * kBinStride;
+            const float* Pl = P + lane * kBinStride;
             const unsigned mlo = (unsigned)msk, mhi = (unsigned)(msk >> 32);
             unsigned slot = slot0;
             float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
             for (int ii = 0; ii < kBinStride; ++ii) {
-                const float p = lds32(Pl + 4 * ii);
+                const float p = Pl[ii];
                 if (ii > 0) {
                     asm volatile(
                         "{\n\t.reg .pred q;\n\t"
@@ -437,8 +444,8 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
                 const int bnd = kMel - kBandsRound1 + lane;
                 float acc = 0.0f;
                 for (int ii = 0; ii < terms1; ++ii) {
-                    const float2 c = lds64c(coef_u32 + 8 * (bnd * kMaxTerms + ii));
-                    const float2 sv = lds64(part + 8 * lds8c(gslot_u32 + bnd * kMaxTerms + ii));
+                    const float2 c = mel.coef[bnd * kMaxTerms + ii];
+                    const float2 sv = part[mel.gslot[bnd * kMaxTerms + ii]];
                     acc = fmaf(c.x, sv.x, acc);
                     acc = fmaf(c.y, sv.y, acc);
                 }
@@ -448,8 +455,8 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
                 const int bnd = lane;
                 float acc = 0.0f;
                 for (int ii = 0; ii < terms2; ++ii) {
-                    const float2 c = lds64c(coef_u32 + 8 * (bnd * kMaxTerms + ii));
-                    const float2 sv = lds64(part + 8 * lds8c(gslot_u32 + bnd * kMaxTerms + ii));
+                    const float2 c = mel.coef[bnd * kMaxTerms + ii];
+                    const float2 sv = part[mel.gslot[bnd * kMaxTerms + ii]];
                     acc = fmaf(c.x, sv.x, acc);
                     acc = fmaf(c.y, sv.y, acc);
                 }
