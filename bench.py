@@ -290,6 +290,28 @@ def logmel_leg(torch, feature, L, pk, rank, world=1, dist=None):
                      "peak_source": pk["src"],
                      "traffic_source": "profiles/r01_logmel_full.ncu-rep (8 clips: 508.5 MB read + 19.8 MB written), scaled"},
     }
+    # the two kernels side by side on the same resident clips (every rank times both; max over ranks): "fp32" = warp per
+    # frame, 32 x 32 register FFT on the CUDA cores; "tc" = the DFT as two batched tcgen05 GEMMs on fp16 hi / lo planes.
+    # The default (what the lines above ran) is the faster one; profiles/README.md holds the ncu comparison.
+    kern = {}
+    for name in ("fp32", "tc"):
+        for _ in range(2):
+            feature.mbe_device(x, out=out, kernel=name)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            feature.mbe_device(x, out=out, kernel=name)
+        e1.record()
+        torch.cuda.synchronize()
+        tk_ = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda")
+        if world > 1:
+            dist.all_reduce(tk_, op=dist.ReduceOp.MAX)
+        kern[name] = {"ms_per_launch": tk_.item(), "gb_per_s": alg_bytes / tk_.item() / 1e6,
+                      "frac_of_hbm": alg_bytes / tk_.item() / 1e6 / pk["hbm"]}
+    from sed_crnn_b200 import _lib as _l
+    res["kernels"] = kern
+    res["default_kernel"] = {1: "fp32", 2: "tc"}[_l.lib().sedb200_logmel_default_kernel()]
+    res["roofline"]["kernel"] = "logmel_kernel" if res["default_kernel"] == "fp32" else "logmel_tc_kernel"
     if rank == 0:
         # e2e: pinned host PCM -> device -> kernel -> host log-mel, 4 clips per call; float32 as feature.py decodes it
         # and 16-bit PCM as a WAV / s16le decoder delivers it (sedb200_logmel_i16: half the H2D bytes).  Median of 7

@@ -392,8 +392,10 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
                 for (int u = 0; u < 2; ++u) {
                     const int k2 = 8 * jq + 2 * e2 + u;
                     const float pw = u == 0 ? pw2.x : pw2.y;
-                    if (k2 < 16) Pfwd[64 * k2] = pw;                              // bin k1 + 64 k2
-                    else if (lane != 0 || k2 == 16) Pmir[-64 * k2] = pw;          // mirror bin 2048 - k
+                    // bin k1 + 64 k2, or its mirror 2048 - k for k2 >= 16 (row k1 = 0 is a real sequence: its mirror
+                    // outputs k2 > 16 rewrite bins 64 .. 960 with the conjugate's -- equal -- power; no predicate)
+                    if (k2 < 16) Pfwd[64 * k2] = pw;
+                    else Pmir[-64 * k2] = pw;
                 }
             }
         }
