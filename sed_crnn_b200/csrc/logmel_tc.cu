@@ -142,6 +142,16 @@ __device__ __forceinline__ float4 lds128c(uint32_t a) {      // constants: may b
 __device__ __forceinline__ float2 lds64c(uint32_t a) { float2 v; asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds8c(uint32_t a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void stsf32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ bool elect_one() {                 // one lane of a converged warp
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, %1;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred)
+        : "r"(0xffffffffu));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -175,7 +185,11 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
     MelTab& mel = *reinterpret_cast<MelTab*>(smem + kOffMel);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);              // one per team: "my MMAs have retired"
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kTeams);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // the shuffle tells the compiler that the warp index is warp-uniform: team / tile addresses / MMA descriptors then
+    // live in uniform registers and every tcgen05.mma is ONE instruction (as thread registers each one was wrapped in
+    // a 14-instruction ELECT / R2UR / branch loop on the team's critical path)
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int team = warp >> 2, fw = warp & 3;                                  // fw: frame of the tile = TMEM sub-partition
 
     if (tid == 0) {
@@ -200,7 +214,7 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
     const int n_local = t1 - t0;
     uint64_t* bar = bars + team;
     uint32_t phase = 0;
-    const bool issuer = fw == 0 && lane == 0;
+    const bool issuer_warp = fw == 0;
 
     // ---- per-thread constants of the three phases
     unsigned char* const tilep = smem + kOffTiles + team * kTileBytes;          // A1, then A2, then P of the team's tile
@@ -307,7 +321,7 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
         }
         fence_proxy_async();
         named_bar(1 + team, 128);
-        if (issuer) {
+        if (issuer_warp && elect_one()) {
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -357,7 +371,7 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
         tc_fence_before();
         fence_proxy_async();
         named_bar(1 + team, 128);
-        if (issuer) {
+        if (issuer_warp && elect_one()) {
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
