@@ -55,13 +55,14 @@ struct TcConst {
     unsigned char b1[2][64 * 128];               // stage 1: N = 64 outputs x K = 64 (permuted n1), fp16, 128B-swizzled
     unsigned char b2[2][64 * 128];               // stage 2: N = 64 outputs x K = (n2, re / im); values doubled (P = 4|X|^2)
     unsigned char b2s[2][32 * 128];              // special: N = 32 outputs x K = n2 (first 64 B of each row)
-    float4 tw[16 * 32];                          // [k1 pair][TMEM lane]: (cos a, cos b, sin a, sin b) of W_2048^(n2 k1)
+    float4 tw[5 * 32];                           // [jq][TMEM lane]: (cos a, cos b, sin a, sin b) of W_2048^(n2 k1), k1 = 8 jq, 8 jq + 1;
+                                                 // [4][lane]: (cos, cos, sin, sin) of W_2048^(2 n2), the rotation to the next k1 pair
     float win[32 * 36];                          // [lane][4 j + e] = Hann(128 j + 4 lane + e), j < 8; rows padded to 36
 };
 static_assert(sizeof(TcConst) % 16 == 0, "copied as uint4");
 
-struct MelTab {                                  // the mel-walk part of LogmelTables
-    float2 coef[kMel * kMaxTerms];
+struct MelTab {                                  // the mel-walk part of LogmelTables; coef / gslot TRANSPOSED to [term][band]
+    float2 coef[kMel * kMaxTerms];               // so that the lanes (= bands) of the closing loop read consecutive words
     unsigned long long lanemask[32];
     unsigned char gslot[kMel * kMaxTerms];
     unsigned char lanebase[32];
@@ -201,7 +202,11 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
         const uint4* src = reinterpret_cast<const uint4*>(gconst);
         uint4* dst = reinterpret_cast<uint4*>(&cst);
         for (int i = tid; i < (int)(sizeof(TcConst) / 16); i += kTcThreads) dst[i] = __ldg(src + i);
-        for (int i = tid; i < kMel * kMaxTerms; i += kTcThreads) { mel.coef[i] = gtab->coef[i]; mel.gslot[i] = gtab->gslot[i]; }
+        for (int i = tid; i < kMel * kMaxTerms; i += kTcThreads) {
+            const int bnd = i / kMaxTerms, term = i - bnd * kMaxTerms;
+            mel.coef[term * kMel + bnd] = gtab->coef[i];
+            mel.gslot[term * kMel + bnd] = gtab->gslot[i];
+        }
         if (tid < 32) { mel.lanemask[tid] = gtab->lanemask[tid]; mel.lanebase[tid] = gtab->lanebase[tid]; }
         if (tid == 0) { mel.terms_round1 = gtab->terms_round1; mel.terms_round2 = gtab->terms_round2; }
     }
@@ -228,6 +233,7 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
     const int n2 = 4 * m + g;
     unsigned short* const spec_row = reinterpret_cast<unsigned short*>(specp + fw * 128 + (((n2 >> 3) ^ fw) << 4) + (n2 & 7) * 2);
     const float4* const twp = cst.tw + lane;
+    const float2 rot_c = make_float2(twp[4 * 32].x, twp[4 * 32].y), rot_s = make_float2(twp[4 * 32].z, twp[4 * 32].w);
     unsigned char* const a2rows = tilep + (4 * fw) * 1024 + g * 4;              // + jq * 1024 + q * 128 + ((m ^ q) << 4)
     const uint32_t ta = tmem + ((uint32_t)(32 * fw) << 16);
     // stage-2 epilogue + mel
@@ -253,6 +259,19 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
         const unsigned q = live ? q0 : total_frames - 1;          // a dead row of the last tile recomputes the last frame
         const unsigned cc = q / n_frames, frame = q - cc * n_frames;
         // =========================================== phase 1: PCM -> Hann -> per-frame scale -> fp16 hi / lo A1 rows
+        {   // the team's next tile: pull its samples into L2 now (no registers), ~15k cycles before they are loaded
+            const unsigned qn = q0 + 4u * kTeams;
+            if (qn < total_frames) {
+                const unsigned ccn = qn / n_frames, fn = qn - ccn * n_frames;
+                const long sn = ((long)fn - 1) * kHop;
+                if (sn >= 0 && sn + kNfft <= S) {
+                    const T* xn = pcm + (long)ccn * S + sn + (128 / sizeof(T)) * lane;          // one 128-byte line per lane
+#pragma unroll
+                    for (int j = 0; j < (int)(kNfft * sizeof(T) / 4096); ++j)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(xn + j * (4096 / sizeof(T))));
+                }
+            }
+        }
         float4 v[16];
         {
             const T* __restrict__ xb = pcm + (long)cc * S;
@@ -345,11 +364,18 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
                 tmem_ld8_nowait(ta + 32 + 8 * jq, im);
                 tmem_ld_wait();
                 if (jq == 0) { y32 = im[0]; im[0] = 0.0f; }         // the slot of Im Y[0] (= 0) carries Y[32]
+                // twiddles of k1 = 8 jq, 8 jq + 1 from the table; the next three pairs by rotating with W^(2 n2) (four
+                // packed FMA-pipe instructions instead of a 4-wavefront LDS.128: the shared-memory pipe is the busy one)
+                const float4 t0 = twp[jq * 32];
+                float2 c2 = make_float2(t0.x, t0.y), s2 = make_float2(t0.z, t0.w);
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
-                    const float4 t = twp[(4 * jq + p) * 32];
+                    if (p > 0) {
+                        const float2 nc = __ffma2_rn(make_float2(-s2.x, -s2.y), rot_s, __fmul2_rn(c2, rot_c));
+                        const float2 ns = __ffma2_rn(c2, rot_s, __fmul2_rn(s2, rot_c));
+                        c2 = nc; s2 = ns;
+                    }
                     const float2 r2 = make_float2(re[2 * p], re[2 * p + 1]), i2 = make_float2(im[2 * p], im[2 * p + 1]);
-                    const float2 c2 = make_float2(t.x, t.y), s2 = make_float2(t.z, t.w);
                     const float2 zr = __ffma2_rn(i2, s2, __fmul2_rn(r2, c2));                       // (re + i im)(c - i s)
                     const float2 zi = __ffma2_rn(make_float2(-r2.x, -r2.y), s2, __fmul2_rn(i2, c2));
                     uint32_t hi, lo;
@@ -460,8 +486,8 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
                 const int bnd = kMel - kBandsRound1 + lane;
                 float acc = 0.0f;
                 for (int ii = 0; ii < terms1; ++ii) {
-                    const float2 c = mel.coef[bnd * kMaxTerms + ii];
-                    const float2 sv = part[mel.gslot[bnd * kMaxTerms + ii]];
+                    const float2 c = mel.coef[ii * kMel + bnd];
+                    const float2 sv = part[mel.gslot[ii * kMel + bnd]];
                     acc = fmaf(c.x, sv.x, acc);
                     acc = fmaf(c.y, sv.y, acc);
                 }
@@ -471,8 +497,8 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
                 const int bnd = lane;
                 float acc = 0.0f;
                 for (int ii = 0; ii < terms2; ++ii) {
-                    const float2 c = mel.coef[bnd * kMaxTerms + ii];
-                    const float2 sv = part[mel.gslot[bnd * kMaxTerms + ii]];
+                    const float2 c = mel.coef[ii * kMel + bnd];
+                    const float2 sv = part[mel.gslot[ii * kMel + bnd]];
                     acc = fmaf(c.x, sv.x, acc);
                     acc = fmaf(c.y, sv.y, acc);
                 }
@@ -523,12 +549,15 @@ void build_const(TcConst& c) {
             const double ph = two_pi * (double)((n2 * (2 * k2 + 1)) % 64) / 64.0;
             put_f16(c.b2s[0], c.b2s[1], n, n2, 2.0 * (n < 16 ? std::cos(ph) : -std::sin(ph)));
         }
-    for (int p = 0; p < 16; ++p)
-        for (int l = 0; l < 32; ++l) {
-            const int n2 = 4 * (l & 7) + (l >> 3);
-            const double a = two_pi * (double)(n2 * (2 * p)) / kNfft, b = two_pi * (double)(n2 * (2 * p + 1)) / kNfft;
-            c.tw[p * 32 + l] = make_float4((float)std::cos(a), (float)std::cos(b), (float)std::sin(a), (float)std::sin(b));
+    for (int l = 0; l < 32; ++l) {
+        const int n2 = 4 * (l & 7) + (l >> 3);
+        for (int jq = 0; jq < 4; ++jq) {
+            const double a = two_pi * (double)(n2 * (8 * jq)) / kNfft, b = two_pi * (double)(n2 * (8 * jq + 1)) / kNfft;
+            c.tw[jq * 32 + l] = make_float4((float)std::cos(a), (float)std::cos(b), (float)std::sin(a), (float)std::sin(b));
         }
+        const double r = two_pi * (double)(2 * n2) / kNfft;
+        c.tw[4 * 32 + l] = make_float4((float)std::cos(r), (float)std::cos(r), (float)std::sin(r), (float)std::sin(r));
+    }
     for (int l = 0; l < 32; ++l)
         for (int j = 0; j < 8; ++j)
             for (int e = 0; e < 4; ++e) {
