@@ -253,11 +253,19 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
     const uint64_t dB2h = dzero | (uint64_t)((smem_u32(cst.b2[0]) & 0x3FFFFu) >> 4), dB2l = dzero | (uint64_t)((smem_u32(cst.b2[1]) & 0x3FFFFu) >> 4);
     const uint64_t dBsh = dzero | (uint64_t)((smem_u32(cst.b2s[0]) & 0x3FFFFu) >> 4), dBsl = dzero | (uint64_t)((smem_u32(cst.b2s[1]) & 0x3FFFFu) >> 4);
 
-    for (int i = team; i < n_local; i += kTeams) {
-        const unsigned q0 = 4u * (unsigned)(t0 + i) + (unsigned)fw;
-        const bool live = q0 < total_frames;
-        const unsigned q = live ? q0 : total_frames - 1;          // a dead row of the last tile recomputes the last frame
+    // ---- phase 1 of tile `ti` of this team: PCM -> Hann -> per-frame scale, left in v[] (64 registers).  It runs one
+    //      tile AHEAD, between the issue of a tile's stage-2 MMAs and the wait for them, so the tensor-core time and the
+    //      DRAM latency of the loads hide behind each other.
+    float4 v[16];
+    bool n_live = false;
+    unsigned n_cc = 0, n_frame = 0;
+    float n_unscale = 0.0f;
+    auto load_frame = [&](int ti) {
+        const unsigned q0 = 4u * (unsigned)(t0 + ti) + (unsigned)fw;
+        n_live = q0 < total_frames;
+        const unsigned q = n_live ? q0 : total_frames - 1;        // a dead row of the last tile recomputes the last frame
         const unsigned cc = q / n_frames, frame = q - cc * n_frames;
+        n_cc = cc; n_frame = frame;
         // =========================================== phase 1: PCM -> Hann -> per-frame scale -> fp16 hi / lo A1 rows
         {   // the team's next tile: pull its samples into L2 now (no registers), ~15k cycles before they are loaded
             const unsigned qn = q0 + 4u * kTeams;
@@ -272,7 +280,6 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
                 }
             }
         }
-        float4 v[16];
         {
             const T* __restrict__ xb = pcm + (long)cc * S;
             const long start = ((long)frame - 1) * kHop;
@@ -307,7 +314,7 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
         unsigned E = __reduce_max_sync(0xffffffffu, __float_as_uint(amax)) >> 23;
         E = E < 8u ? 8u : E;
         const float s = __uint_as_float((262u - E) << 23);
-        const float unscale = -1.3862943611198906f * (float)(135 - (int)E);       // -2 ln2 * exponent, added after the log
+        n_unscale = -1.3862943611198906f * (float)(135 - (int)E);             // -2 ln2 * exponent, added after the log
         // Hann: w for the first half, 1 - w for the second (periodic window: w[n + 1024] = 1 - w[n])
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -320,6 +327,13 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
             v[j] = make_float4(p0.x, p0.y, p1.x, p1.y);
             v[j + 8] = make_float4(r0.x, r0.y, r1.x, r1.y);
         }
+    };
+    if (team < n_local) load_frame(team);
+
+    for (int i = team; i < n_local; i += kTeams) {
+        const bool live = n_live;
+        const unsigned cc = n_cc, frame = n_frame;
+        const float unscale = n_unscale;
         named_bar(1 + team, 128);                                  // the team's previous mel walk (it reads this buffer) is over
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -413,6 +427,7 @@ logmel_tc_kernel(const T* __restrict__ pcm, float* __restrict__ out, int n_ch, l
             }
             mma_commit(bar);
         }
+        if (i + kTeams < n_local) load_frame(i + kTeams);          // next tile's phase 1, behind this tile's stage-2 MMAs
         if (fw == 0) wait_bar(bar, phase);
         phase ^= 1;
         named_bar(1 + team, 128);
