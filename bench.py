@@ -820,6 +820,40 @@ def run_ours(args, rank, world, local_rank):
         except Exception as e:                                  # noqa: BLE001 -- informational leg
             fixed = {"error": str(e)[:200]}
 
+    # ---- BASELINE configs[4] at N > 1: the long-context model data-parallel, batch 128 per GPU (weak scaling; the
+    #      N = 1 point is `other_configs.c5` of the single-GPU line)
+    long_ctx = None
+    if world > 1 and not strong and args.config != "c5" and not args.no_other_configs:
+        try:
+            cfg5 = config.PRESETS["c5"]
+            eng5 = engine.CRNNEngine(cfg5, loss="bce", lr=1e-3, weight_decay=1e-4, clip=1.0, seed=777 + rank,
+                                     grad_exchange=gx_mode, cuda_graph=use_graph)
+            eng5.init_default(seed=0)
+            g5 = torch.Generator(device="cuda").manual_seed(300 + rank)
+            x5 = [torch.randn(cfg5.input_shape(PER_GPU_BATCH), device="cuda", generator=g5) for _ in range(2)]
+            y5 = [(torch.rand(cfg5.target_shape(PER_GPU_BATCH), device="cuda", generator=g5) < 0.2).float() for _ in range(2)]
+            for i in range(5):
+                eng5.train_step(x5[i % 2], y5[i % 2])
+            n5 = 5
+            barrier()
+            e0.record()
+            for i in range(n5):
+                eng5.train_step(x5[i % 2], y5[i % 2])
+            e1.record()
+            barrier()
+            t5 = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+            dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+            if eng5.xch is not None:
+                eng5.xch.raise_if_failed(wait=True)
+                eng5.xch.close()
+            ms5 = t5.item() / n5
+            long_ctx = {"workload": workload_name("c5", world), "per_gpu_batch": PER_GPU_BATCH, "scaling": "weak",
+                        "ms_per_step": ms5, "frames_per_s": world * PER_GPU_BATCH * cfg5.seq_len / (ms5 * 1e-3), "steps": n5}
+            del eng5, x5, y5
+            torch.cuda.empty_cache()
+        except Exception as e:                                  # noqa: BLE001 -- informational leg
+            long_ctx = {"error": str(e)[:200]}
+
     # ---- phase breakdown (extra instrumented steps, CUDA events on the launching stream)
     eng.cuda_graph = False                              # the phase profiler brackets individual launches: eager steps
     for i in range(5):                                  # eager warm-up (the timed region above ran graph replays)
@@ -941,6 +975,8 @@ def run_ours(args, rank, world, local_rank):
     }
     if fixed is not None:
         line["fixed_global_batch"] = fixed
+    if long_ctx is not None:
+        line["long_context"] = long_ctx
     if world == 1:
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baselines(args, torch)

@@ -1097,8 +1097,8 @@ inline float* wsf(void* ws, size_t off) { return reinterpret_cast<float*>(reinte
 // weight-gradient GEMMs of a layer there while the caller's stream continues with the critical path.
 struct SideStream {
     cudaStream_t st = nullptr;
-    cudaEvent_t fork[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
-};
+    cudaEvent_t fork[4] = {nullptr, nullptr, nullptr, nullptr}, done[4] = {nullptr, nullptr, nullptr, nullptr};
+};                                                           // [0..1]: GRU layers by parity, [2..3]: conv blocks by parity
 std::mutex g_side_mu;
 std::map<int, SideStream> g_side;
 int side_stream(SideStream** out) {
@@ -1109,7 +1109,7 @@ int side_stream(SideStream** out) {
     if (it == g_side.end()) {
         SideStream s;
         SED_CUDA_OK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 4; ++i) {
             SED_CUDA_OK(cudaEventCreateWithFlags(&s.fork[i], cudaEventDisableTiming));
             SED_CUDA_OK(cudaEventCreateWithFlags(&s.done[i], cudaEventDisableTiming));
         }
@@ -1452,7 +1452,7 @@ static int crnn_backward_impl(const sedb200_crnn_desc* d, const float* params, c
     // ---- BiGRU stack (dout = grad wrt the layer's output, in dseq[cur])
     int cur = 0;
     SideStream* side = nullptr;
-    bool side_busy[2] = {false, false};
+    bool side_busy[4] = {false, false, false, false};
     for (int l = P.n_gru - 1; l >= 0; --l) {
         const int h = P.gh[l], in = P.gin[l];
         const float* xin = l == 0 ? wsf(ws, P.act[P.n_conv - 1]) : wsf(ws, P.gout[l - 1]);
@@ -1594,8 +1594,17 @@ static int crnn_backward_impl(const sedb200_crnn_desc* d, const float* params, c
     const float* dA = wsf(ws, P.dseq[cur]);
     struct SideJoin {           // the weight-gradient GEMMs rejoin the caller's stream on every way out of this function
         SideStream* s; const bool* busy; cudaStream_t st;
-        ~SideJoin() { for (int i = 0; s && i < 2; ++i) if (busy[i]) cudaStreamWaitEvent(st, s->done[i], 0); }
+        ~SideJoin() { for (int i = 0; s && i < 4; ++i) if (busy[i]) cudaStreamWaitEvent(st, s->done[i], 0); }
     } side_join{side, side_busy, st};
+    // Weight gradients of the plane-native blocks beside the main stream: wgrad_tc_kernel (TMA / tensor work, 0.07-0.12 ms
+    // at C2) starts when the block's data gradient has finished and then shares the SMs with the HBM-bound BatchNorm /
+    // pool backward passes of the next block (or with block 0's backward): nothing downstream reads dW before the
+    // optimizer.  The dy planes and their scale pair alternate by block parity so that the next block's passes do not
+    // overwrite what the side stream still reads.  Phase profiling keeps everything on one stream (serial phases).
+    // SEDB200_WGRAD_SIDE: 0 = off (one stream), n >= 2 = on with n pipeline stages in the weight-gradient kernel
+    // (default 3: C2 step 1.454 ms on one stream, 1.447 / 1.400 / 1.406 ms with 4 / 3 / 2 stages)
+    static const int wgrad_side_stages = [] { const char* e = std::getenv("SEDB200_WGRAD_SIDE"); return e ? std::atoi(e) : 3; }();
+    const bool wgrad_side = wgrad_side_stages >= 2 && !prof_on();
     for (int i = P.n_conv - 1; i >= 0; --i) {
         const PoolGeom g = pool_geom(P, d, i, 1, seed, seed_ptr);
         const float* y = wsf(ws, P.y[i]);
@@ -1685,11 +1694,14 @@ static int crnn_backward_impl(const sedb200_crnn_desc* d, const float* params, c
         const long n_vec = n_pix_out * (P.C / 4);
         // plane-native block: dy exists only as ONE fp16 plane of dy * scale (crnn_block.cuh: store_dy4); the scale
         // {s, 1/s} lives in the workspace and is read by the kernels that produce / consume the plane
-        __nv_bfloat16* dyh = P.conv_tc_all[i] ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(ws) + P.dyp) : nullptr;
-        float* dys = wsf(ws, P.dys);
+        const int cpar = i & 1;
+        __nv_bfloat16* dyh = P.conv_tc_all[i] ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(ws) + P.dyp + cpar * P.dy_plane_bytes) : nullptr;
+        float* dys = wsf(ws, P.dys) + 2 * cpar;                    // {s, 1/s} of this block's dy plane
         if (P.conv_tc_all[i]) {
+            // an earlier block of the same parity may still be read by its weight-gradient kernel on the side stream
+            if (side_busy[2 + cpar]) { SED_CUDA_OK(cudaStreamWaitEvent(st, side->done[2 + cpar], 0)); side_busy[2 + cpar] = false; }
             if (have_amax) {
-                dy_scale_kernel<<<1, 128, 0, st>>>(dys + 8, sblk, stat, bnsum, P.C, dys);
+                dy_scale_kernel<<<1, 128, 0, st>>>(wsf(ws, P.dys) + 8, sblk, stat, bnsum, P.C, dys);
                 SED_POST_LAUNCH();
             } else {
                 return fail(SEDB200_ESHAPE, "crnn_backward: plane-native block %d without the activation-sums pass", i);
@@ -1716,8 +1728,11 @@ static int crnn_backward_impl(const sedb200_crnn_desc* d, const float* params, c
         // wgrad
         const int want = std::max(1, std::min(64, M / 2048));
         const int sp = gemm_simt_splits(M, want);
+        const bool wg_side = wgrad_side && P.conv_tc_all[i] && i > 0;
 { char _nm[40]; snprintf(_nm, sizeof _nm, "conv%d.wgrad", i); SED_PROF(_nm, st);
-        if (P.conv_tc_all[i]) {
+        if (wg_side) {
+            // after the data gradient, below
+        } else if (P.conv_tc_all[i]) {
             const char* xp = reinterpret_cast<const char*>(ws) + P.actp[i - 1];
             float* wpart = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + P.tc + conv_tc_weight_scratch_bytes(P.cin[i], P.C));
             rc = wgrad_tc_planes(dyh, nullptr, xp, nullptr, grads + P.conv_w[i], batch, P.H, P.win[i], P.cin[i], P.C, wpart,
@@ -1757,6 +1772,21 @@ static int crnn_backward_impl(const sedb200_crnn_desc* d, const float* params, c
                                ConvDgradB{params + P.conv_w[i], P.cin[i], P.C}, EpiStore{dprev, P.cin[i], nullptr, 0}, st);
             if (rc) return rc;
 }
+            if (wg_side) {
+                if (!side) { rc = side_stream(&side); if (rc) return rc; side_join.s = side; }
+                cudaStream_t ss = side->st;
+                SED_CUDA_OK(cudaEventRecord(side->fork[2 + cpar], st));
+                SED_CUDA_OK(cudaStreamWaitEvent(ss, side->fork[2 + cpar], 0));
+                const char* xp = reinterpret_cast<const char*>(ws) + P.actp[i - 1];
+                float* wpart = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + P.tc + conv_tc_weight_scratch_bytes(P.cin[i], P.C));
+                // three pipeline stages instead of six: 97 KB of shared memory, so that the kernels of the main stream
+                // (block 0's backward: 95 KB per CTA) fit on the SM beside it
+                rc = wgrad_tc_planes(dyh, nullptr, xp, nullptr, grads + P.conv_w[i], batch, P.H, P.win[i], P.cin[i], P.C, wpart,
+                                     ss, 1, kPlaneF16, dys + 1, wgrad_side_stages);
+                if (rc) return rc;
+                SED_CUDA_OK(cudaEventRecord(side->done[2 + cpar], ss));
+                side_busy[2 + cpar] = true;
+            }
             dA = dprev;
         } else if (dx) {
             rc = gemm_simt(M, P.cin[0], 9 * P.C, 1, ConvDgradA{dy, P.H, P.win[0], P.C},

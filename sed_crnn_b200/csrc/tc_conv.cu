@@ -93,9 +93,34 @@ inline ConvMode conv_mode(int terms, int tpi) {
     return m;
 }
 
+// Halo mode: two thirds of the A bytes a launch pulls from L2 are the same pixels again: the boxes of the taps (r, s),
+// r = 0..2, are ONE box of Ht + 2 image rows seen from
+// three row offsets.  A row offset is W x 128 bytes, a whole number of 1024-byte swizzle atoms when W % 8 == 0, so the
+// three taps are three descriptor start addresses into the same box (no base-offset field needed).  Two rings instead
+// of one: A slots hold {planes} boxes of (tpi*Ht + 2) x W rows for one (s, 64-channel chunk), B slots hold one tap's
+// weight tile(s); the K walk is (s, chunk, r).  With two time-adjacent M tiles per item (single-pass launches) a
+// 128x128x64 MMA block costs 6 + 8 = 14 KB of shared-memory fill instead of 24 (forward, tpi 1: 45 instead of 64).
+struct HaloMode { int n_a, n_b, a_plane_bytes, a_slot_bytes, b_slot_bytes, ring_bytes, n_epi_warps, smem_bytes; };
+inline HaloMode conv_halo_mode(int terms, int tpi, int W) {
+    HaloMode m;
+    const int planes = terms >= 2 ? 2 : 1;
+    m.a_plane_bytes = (tpi * kTileM + 2 * W) * 128;
+    m.a_slot_bytes = planes * m.a_plane_bytes;
+    m.b_slot_bytes = planes * kTileBytes;
+    m.n_epi_warps = terms == 1 ? 8 : 4;
+    const int fixed = 1024 /*align*/ + 256 /*barriers*/ + 4096 /*BN-stat staging*/ + m.n_epi_warps * kEpiTile;
+    m.n_a = 2;
+    m.n_b = std::min(kMaxStages, (227 * 1024 - fixed - m.n_a * m.a_slot_bytes) / m.b_slot_bytes);
+    m.ring_bytes = m.n_a * m.a_slot_bytes + std::max(m.n_b, 0) * m.b_slot_bytes;
+    m.smem_bytes = m.ring_bytes + fixed;
+    return m;
+}
+
 struct ConvTcParams {
     int B, H, W, Ht, tiles_per_img, n_tiles_n, m_tiles, total_items, kchunks, n_total;
     int terms, tpi, planes, stage_bytes, n_stages, n_epi_warps;
+    // halo mode (conv_halo_mode): one A box per (tap column, channel chunk) carries the rows of all three tap rows
+    int halo, groups_per_img, n_a, a_plane_bytes, a_slot_bytes, ring_bytes;
     uint32_t idesc;          // instruction descriptor (operand formats: bf16 or fp16 planes)
     const float* out_scale;  // null, or a device scalar every accumulator is multiplied by (fp16 gradient planes)
     const float* out2_scale; // terms == 2: device scalar of the fp8 correction accumulator
@@ -112,13 +137,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int n_stages = p.n_stages, stage_bytes = p.stage_bytes, n_epi_warps = p.n_epi_warps, tpi = p.tpi, planes = p.planes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + n_stages * stage_bytes);
-    uint64_t* full = bars;                       // [kMaxStages]  TMA -> MMA
+    const int ring_bytes = p.halo ? p.ring_bytes : n_stages * stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ring_bytes);
+    uint64_t* full = bars;                       // [kMaxStages]  TMA -> MMA   (halo mode: the B ring)
     uint64_t* empty = bars + kMaxStages;         // [kMaxStages]  MMA -> TMA
     uint64_t* tfull = bars + 2 * kMaxStages;     // [2]           MMA -> epilogue
     uint64_t* tempty = bars + 2 * kMaxStages + 2;// [2]           epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
-    float* stat_s = reinterpret_cast<float*>(smem + n_stages * stage_bytes + 256);    // [4 warps][2][128]
+    uint64_t* afull = bars + 2 * kMaxStages + 6; // [2]           halo mode: the A ring
+    uint64_t* aempty = bars + 2 * kMaxStages + 8;// [2]
+    float* stat_s = reinterpret_cast<float*>(smem + ring_bytes + 256);                // [4 warps][2][128]
     float* epi_stage = stat_s + 1024;                                                 // [epilogue warps][32][kEpiPitch]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -128,6 +156,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kMaxStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(tfull + i, 1); mbar_init(tempty + i, n_epi_warps); }
+        for (int i = 0; i < 2; ++i) { mbar_init(afull + i, 1); mbar_init(aempty + i, 1); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
@@ -140,7 +169,99 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // -- TMA fills boxes outside the tensor -- and is never stored)
     const int b_off = tpi * planes * kTileBytes;                 // B planes behind the A tiles of a stage
 
-    if (warp == 0) {
+    if (warp == 0 && p.halo) {
+        // ================= TMA producer, halo mode: lane = plane; per (s, chunk) one A box, then the three taps' B tiles
+        int bs = 0; uint32_t bph = 0; int as = 0; uint32_t aph = 0;
+        const bool mine = lane < planes;
+        const CUtensorMap* tmA = lane ? &tmA_lo : &tmA_hi;
+        const CUtensorMap* tmB = lane ? &tmB_lo : &tmB_hi;
+        unsigned char* const b_ring = smem + p.n_a * p.a_slot_bytes;
+        const int b_slot_bytes = planes * kTileBytes;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            const int nt = item % p.n_tiles_n, g = item / p.n_tiles_n;
+            const int tb = g / p.groups_per_img, th = (g - tb * p.groups_per_img) * tpi * p.Ht;
+            const int ncol = nt * kTileN;
+            for (int s = 0; s < 3; ++s) {
+                for (int c0 = 0; c0 < p.kchunks * kBlockK; c0 += kBlockK) {
+                    if (lane == 0) {
+                        mbar_wait(aempty + as, aph ^ 1);
+                        mbar_expect_tx(afull + as, p.a_slot_bytes);
+                    }
+                    __syncwarp();
+                    if (mine) tma_load_4d(smem + as * p.a_slot_bytes + lane * p.a_plane_bytes, tmA, afull + as, c0, s - 1, th - 1, tb);
+                    if (++as == p.n_a) { as = 0; aph ^= 1; }
+                    for (int r = 0; r < 3; ++r) {
+                        if (lane == 0) {
+                            mbar_wait(empty + bs, bph ^ 1);
+                            mbar_expect_tx(full + bs, b_slot_bytes);
+                        }
+                        __syncwarp();
+                        if (mine) tma_load_2d(b_ring + bs * b_slot_bytes + lane * kTileBytes, tmB, full + bs, c0, (r * 3 + s) * p.n_total + ncol);
+                        if (++bs == n_stages) { bs = 0; bph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && p.halo) {
+        // ================= MMA issuer, halo mode: tap row r = descriptor start r * W rows into the A box =============
+        const uint32_t idesc = p.idesc;
+        const uint64_t dbase = smem_desc_sw128(smem_u32(smem), 16, 1024);
+        const uint32_t a_slot_u = (uint32_t)p.a_slot_bytes >> 4, a_plane_u = (uint32_t)p.a_plane_bytes >> 4;
+        const uint32_t b_ring_u = (uint32_t)(p.n_a * p.a_slot_bytes) >> 4, b_slot_u = (uint32_t)(planes * kTileBytes) >> 4;
+        const uint32_t tile_u = kTileBytes >> 4, row_u = (uint32_t)(p.W * 128) >> 4;
+        int bs = 0; uint32_t bph = 0; int as = 0; uint32_t aph = 0;
+        int buf = 0; uint32_t bphase = 0;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            mbar_wait(tempty + buf, bphase ^ 1);
+            tc_fence_after();
+            uint32_t acc0 = 0;
+            for (int sc = 0; sc < 3 * p.kchunks; ++sc) {
+                mbar_wait(afull + as, aph);
+                tc_fence_after();
+                const uint64_t da = dbase + (uint64_t)(as * a_slot_u);
+                for (int r = 0; r < 3; ++r) {
+                    mbar_wait(full + bs, bph);
+                    tc_fence_after();
+                    const uint64_t dbh0 = dbase + (uint64_t)(b_ring_u + bs * b_slot_u), dbl0 = dbh0 + tile_u;
+                    const uint64_t dar = da + (uint64_t)(r * row_u);
+                    if (p.terms == 2) {
+                        const uint32_t d1 = tmem_base + (buf * 2) * kTileN, d2 = d1 + kTileN;
+                        const uint64_t dac = dar + a_plane_u;
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) mma_bf16(d1, dar + 2 * k, dbh0 + 2 * k, idesc, k ? 1u : acc0);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) mma_f8(d2, dac + 2 * k, dbl0 + 2 * k, idesc, k ? 1u : acc0);
+                    } else if (planes == 1) {
+#pragma unroll
+                        for (int t = 0; t < 2; ++t) {
+                            if (t < tpi) {
+                                const uint32_t d = tmem_base + (buf * 2 + t) * kTileN;
+                                const uint64_t dah0 = dar + (uint64_t)(t * tile_u);      // tile t: Ht rows = 16 KB further
+#pragma unroll
+                                for (int k = 0; k < kBlockK / 16; ++k) mma_bf16(d, dah0 + 2 * k, dbh0 + 2 * k, idesc, k ? 1u : acc0);
+                            }
+                        }
+                    } else {                                                             // 3-term, one tile per item
+                        const uint32_t d = tmem_base + (buf * 2) * kTileN;
+                        const uint64_t dal0 = dar + a_plane_u;
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            mma_bf16(d, dar + 2 * k, dbh0 + 2 * k, idesc, k ? 1u : acc0);
+                            mma_bf16(d, dar + 2 * k, dbl0 + 2 * k, idesc, 1);
+                            mma_bf16(d, dal0 + 2 * k, dbh0 + 2 * k, idesc, 1);
+                        }
+                    }
+                    acc0 = 1;
+                    mma_commit(empty + bs);
+                    if (++bs == n_stages) { bs = 0; bph ^= 1; }
+                }
+                mma_commit(aempty + as);
+                if (++as == p.n_a) { as = 0; aph ^= 1; }
+            }
+            mma_commit(tfull + buf);
+            if (++buf == 2) { buf = 0; bphase ^= 1; }
+        }
+    } else if (warp == 0) {
         // ================= TMA producer: lane i requests box i of a stage (A tiles first, then B; hi planes on even
         //                   lanes, lo planes on odd lanes in the 3-pass mode); lane 0 waits for the slot ===============
         int stage = 0; uint32_t phase = 0;
@@ -238,13 +359,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const float osc = p.out_scale ? __ldg(p.out_scale) : 1.0f;
         const float osc2 = (p.terms == 2 && p.out2_scale) ? __ldg(p.out2_scale) : 0.0f;
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-            const int nt = item % p.n_tiles_n, mt0 = (item / p.n_tiles_n) * tpi;
+            const int nt = item % p.n_tiles_n, grp = item / p.n_tiles_n;
             mbar_wait(tfull + buf, bphase);
             tc_fence_after();
             for (int t = 0; t < tpi; ++t) {
-            const int mt = mt0 + t;
-            if (mt >= p.m_tiles) break;                    // uniform over the epilogue warps
-            const int b = mt / p.tiles_per_img, h0 = (mt % p.tiles_per_img) * p.Ht;
+            int mt, b, h0;
+            if (p.halo) {                                  // items never straddle images: (image, group of tpi tiles)
+                b = grp / p.groups_per_img;
+                const int ti = (grp - b * p.groups_per_img) * tpi + t;
+                if (ti >= p.tiles_per_img) break;          // uniform over the epilogue warps
+                mt = b * p.tiles_per_img + ti; h0 = ti * p.Ht;
+            } else {
+                mt = grp * tpi + t;
+                if (mt >= p.m_tiles) break;                // uniform over the epilogue warps
+                b = mt / p.tiles_per_img; h0 = (mt % p.tiles_per_img) * p.Ht;
+            }
             // TMEM hands every lane one output ROW (pixel); each 32 x 32 chunk goes through a per-warp staging tile so
             // that one store instruction writes four full 128 B channel segments (instead of 16 B pieces of 32 pixels),
             // and the BatchNorm column sums are plain conflict-free column reads of the same tile.
@@ -386,7 +515,7 @@ constexpr int kWgSmemBytes = kStages * kWgStageBytes + 1024 + 256;
 constexpr uint32_t kWgTmemCols = 512;
 
 struct WgradTcParams {
-    int B, H, W, Hk, hblocks_per_img, total_kblocks, n_mt, n_nt, slices, terms;
+    int B, H, W, Hk, hblocks_per_img, total_kblocks, n_mt, n_nt, slices, terms, n_stages;
     uint32_t idesc;
     float* part;             // [slices][9][Cout][Cin]
     int Cout, Cin;
@@ -398,12 +527,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
                 const WgradTcParams p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kWgStageBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.n_stages * (p.terms == 1 ? kWgStageBytes / 2 : kWgStageBytes));
     uint64_t* full = bars;
     uint64_t* empty = bars + kMaxStages;
     uint64_t* tfull = bars + 2 * kMaxStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
-    const int n_stages = p.terms == 1 ? kMaxStages : kStages;
+    const int n_stages = p.n_stages;
     const int stage_bytes = p.terms == 1 ? kWgStageBytes / 2 : kWgStageBytes;
     // 1-term stage: {dY hi: 2 halves} + 3 x {In hi: 2 halves}; 3-term stage: each of those followed by its lo boxes
     const int a_bytes = p.terms == 1 ? kWgABytes / 2 : kWgABytes, b_bytes = p.terms == 1 ? kWgBBytes / 2 : kWgBBytes;
@@ -614,11 +743,58 @@ int conv_tc_planes_w(const void* a_hi, const void* a_lo, const void* wplanes, co
     const __nv_bfloat16* w_lo = reinterpret_cast<const __nv_bfloat16*>(reinterpret_cast<const char*>(wplanes) + wp);
 
     const int Ht = kTileM / W;
+    ConvTcParams p;
+    p.B = B; p.H = H; p.W = W; p.Ht = Ht;
+    p.tiles_per_img = (H + Ht - 1) / Ht;
+    p.n_tiles_n = Nc / kTileN;
+    p.m_tiles = B * p.tiles_per_img;
+    p.kchunks = Kc / kBlockK;
+    p.n_total = Nc;
+    p.terms = terms;
+    // halo mode (one A box per tap COLUMN, conv_halo_mode): possible whenever a tap-row offset is a whole number of
+    // swizzle atoms.  Measured (profiles/README.md, "r02 halo boxes"): 30-40 % fewer bytes into shared memory and NO
+    // gain -- the launches sit on the tensor pipe's 64 cycles per 128x128x16 MMA, not on L2 -- so it is opt-in
+    // (SEDB200_CONV_HALO=1; the parity tests run both settings).
+    const char* e_halo = std::getenv("SEDB200_CONV_HALO");
+    bool halo = (W % 8 == 0) && e_halo && std::atoi(e_halo) != 0;
+    // two M tiles per work item when the CTAs stay balanced with half as many items (>= 5 per CTA)
+    const char* e_tpi = std::getenv("SEDB200_CONV_TPI");
+    const int force_tpi = e_tpi ? std::atoi(e_tpi) : 0;
+    int tpi = 1;
+    for (int pass = 0; pass < 2; ++pass) {
+        const long pairs = halo ? (long)B * ((p.tiles_per_img + 1) / 2) * p.n_tiles_n : (long)((p.m_tiles + 1) / 2) * p.n_tiles_n;
+        tpi = pairs >= 5L * sm_count() ? 2 : 1;
+        if (force_tpi == 1 || force_tpi == 2) tpi = force_tpi;
+        if (terms == 2) tpi = 1;                                 // the tile's second accumulator slot holds the fp8 pass
+        if (halo && terms == 3) tpi = 1;                         // two A slots of two planes of two tiles leave no room for B
+        if (!halo || conv_halo_mode(terms, tpi, W).n_b >= 2) break;
+        halo = false;                                            // wide rows (W = 64, 128): the halo rows do not fit
+    }
+    int n_epi_warps, smem_bytes;
+    p.halo = halo ? 1 : 0;
+    p.tpi = tpi;
+    p.planes = terms >= 2 ? 2 : 1;
+    if (halo) {
+        const HaloMode hm = conv_halo_mode(terms, tpi, W);
+        p.groups_per_img = (p.tiles_per_img + tpi - 1) / tpi;
+        p.n_a = hm.n_a; p.a_plane_bytes = hm.a_plane_bytes; p.a_slot_bytes = hm.a_slot_bytes; p.ring_bytes = hm.ring_bytes;
+        p.stage_bytes = hm.b_slot_bytes; p.n_stages = hm.n_b;    // the B ring
+        p.total_items = B * p.groups_per_img * p.n_tiles_n;
+        n_epi_warps = hm.n_epi_warps; smem_bytes = hm.smem_bytes;
+    } else {
+        const ConvMode md = conv_mode(terms, tpi);
+        SED_REQUIRE(md.n_stages >= 2, SEDB200_ESHAPE, "conv_tc: no room for two pipeline stages");
+        p.groups_per_img = 0; p.n_a = 0; p.a_plane_bytes = 0; p.a_slot_bytes = 0; p.ring_bytes = 0;
+        p.stage_bytes = md.stage_bytes; p.n_stages = md.n_stages;
+        p.total_items = ((p.m_tiles + tpi - 1) / tpi) * p.n_tiles_n;
+        n_epi_warps = md.n_epi_warps; smem_bytes = md.smem_bytes;
+    }
+    p.n_epi_warps = n_epi_warps;
     CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
     {
         const uint64_t dims[4] = {(uint64_t)Kc, (uint64_t)W, (uint64_t)H, (uint64_t)B};
         const uint64_t strides[3] = {(uint64_t)Kc * 2, (uint64_t)W * Kc * 2, (uint64_t)H * W * Kc * 2};
-        const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)W, (uint32_t)Ht, 1};
+        const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)W, (uint32_t)(halo ? tpi * Ht + 2 : Ht), 1};
         int rc = encode_tmap_bf16(&tmA_hi, a_hi, 4, dims, strides, box);
         if (rc) return rc;
         rc = encode_tmap_bf16(&tmA_lo, a_lo, 4, dims, strides, box);
@@ -633,32 +809,14 @@ int conv_tc_planes_w(const void* a_hi, const void* a_lo, const void* wplanes, co
         rc = encode_tmap_bf16(&tmB_lo, w_lo, 2, dims, strides, box);
         if (rc) return rc;
     }
-    ConvTcParams p;
-    p.B = B; p.H = H; p.W = W; p.Ht = Ht;
-    p.tiles_per_img = (H + Ht - 1) / Ht;
-    p.n_tiles_n = Nc / kTileN;
-    p.m_tiles = B * p.tiles_per_img;
-    p.kchunks = Kc / kBlockK;
-    p.n_total = Nc;
-    p.terms = terms;
-    // two M tiles per work item when the CTAs stay balanced with half as many items (>= 5 per CTA)
-    static const int force_tpi = [] { const char* e = std::getenv("SEDB200_CONV_TPI"); return e ? std::atoi(e) : 0; }();
-    const long pairs = (long)((p.m_tiles + 1) / 2) * p.n_tiles_n;
-    int tpi = pairs >= 5L * sm_count() ? 2 : 1;
-    if (force_tpi == 1 || force_tpi == 2) tpi = force_tpi;
-    if (terms == 2) tpi = 1;                                     // the tile's second accumulator slot holds the fp8 pass
-    const ConvMode md = conv_mode(terms, tpi);
-    p.tpi = tpi; p.planes = md.planes; p.stage_bytes = md.stage_bytes; p.n_stages = md.n_stages; p.n_epi_warps = md.n_epi_warps;
-    p.total_items = ((p.m_tiles + tpi - 1) / tpi) * p.n_tiles_n;
     p.idesc = fmt == kPlaneF16 ? idesc_f16(kTileM, kTileN, 0, 0) : idesc_bf16(kTileM, kTileN, 0, 0);
     p.out_scale = out_scale;
     p.out2_scale = out2_scale;
     p.out = out; p.bias = bias; p.out_ld = Nc; p.stats = stats;
-    SED_REQUIRE(md.n_stages >= 2, SEDB200_ESHAPE, "conv_tc: no room for two pipeline stages");
     { const int rc = ensure_dyn_smem((const void*)conv_tc_kernel, 227 * 1024); if (rc) return rc; }
     const int grid = std::min(p.total_items, sm_count());
     SED_REQUIRE(terms != 1 || !stats, SEDB200_EINVAL, "conv_tc: BatchNorm statistics need a forward mode");
-    conv_tc_kernel<<<grid, kConvThreads, md.smem_bytes, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+    conv_tc_kernel<<<grid, kConvThreads, smem_bytes, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }
@@ -702,7 +860,8 @@ size_t wgrad_tc_part_bytes(int Cin, int Cout) { return (size_t)wgrad_slices(Cin,
 
 // planes given: dY [B][H][W][Cout] and In [B][H][W][Cin] as bf16 hi / lo
 int wgrad_tc_planes(const void* y_hi, const void* y_lo, const void* x_hi, const void* x_lo, float* dw, int B, int H,
-                    int W, int Cin, int Cout, float* part, cudaStream_t st, int terms, int fmt, const float* out_scale) {
+                    int W, int Cin, int Cout, float* part, cudaStream_t st, int terms, int fmt, const float* out_scale,
+                    int max_stages) {
     SED_REQUIRE(wgrad_tc_supported(H, W, Cin, Cout), SEDB200_ESHAPE, "wgrad_tc: shape H=%d W=%d Cin=%d Cout=%d unsupported", H, W, Cin, Cout);
     SED_REQUIRE(terms == 1 || terms == 3, SEDB200_EINVAL, "wgrad_tc: terms = %d", terms);
     if (terms == 1 || !y_lo) y_lo = y_hi;
@@ -734,9 +893,14 @@ int wgrad_tc_planes(const void* y_hi, const void* y_lo, const void* x_hi, const 
     p.slices = std::min(wgrad_slices(Cin, Cout), p.total_kblocks);
     p.part = part; p.Cout = Cout; p.Cin = Cin; p.terms = terms;
     p.idesc = fmt == kPlaneF16 ? idesc_f16(128, 128, 1, 1) : idesc_bf16(128, 128, 1, 1);
+    // pipeline depth: 6 half-size stages (single pass) / 3 (3-term) fill the SM; a caller that wants the kernel to
+    // share its SMs with another one (crnn_backward_impl: beside the BatchNorm / block-0 backward) asks for fewer
+    p.n_stages = terms == 1 ? kMaxStages : kStages;
+    if (max_stages >= 2 && max_stages < p.n_stages) p.n_stages = max_stages;
+    const int smem_bytes = p.n_stages * (terms == 1 ? kWgStageBytes / 2 : kWgStageBytes) + 1024 + 256;
     { const int rc = ensure_dyn_smem((const void*)wgrad_tc_kernel, kWgSmemBytes); if (rc) return rc; }
     const int grid = p.n_mt * p.n_nt * 3 * p.slices;
-    wgrad_tc_kernel<<<grid, kThreads, kWgSmemBytes, st>>>(tmY_hi, tmY_lo, tmX_hi, tmX_lo, p);
+    wgrad_tc_kernel<<<grid, kThreads, smem_bytes, st>>>(tmY_hi, tmY_lo, tmX_hi, tmX_lo, p);
     SED_POST_LAUNCH();
     wgrad_reduce_kernel<<<(int)std::min<long>((9L * Cout * Cin + 255) / 256, 1184), 256, 0, st>>>(part, p.slices, Cout, Cin, dw, out_scale);
     SED_POST_LAUNCH();

@@ -45,6 +45,8 @@ int conv_tc_planes_w(const void* a_hi, const void* a_lo, const void* wplanes, co
 size_t wgrad_tc_part_bytes(int Cin, int Cout);
 int wgrad_tc_planes(const void* y_hi, const void* y_lo, const void* x_hi, const void* x_lo, float* dw, int B, int H,
                     int W, int Cin, int Cout, float* part, cudaStream_t st, int terms = 3, int fmt = kPlaneBF16,
-                    const float* out_scale = nullptr);
+                    const float* out_scale = nullptr, int max_stages = 0);
+// max_stages (optional): cap of the pipeline depth = shared memory per CTA (32 KB per single-pass stage), for callers
+// that run the kernel beside another one on the same SMs
 
 }  // namespace sedb200

@@ -37,6 +37,18 @@ def test_c1_c2_full_size_training_step(pkg, preset, seed):
     assert res["perr"] <= PU.PROB_TOL
 
 
+def test_c2_full_size_with_halo_boxes(pkg, monkeypatch):
+    """The opt-in operand staging of conv_tc_kernel (SEDB200_CONV_HALO=1: one halo box per tap column serves the three
+    tap rows; forward as fp16 + e4m3 passes on one tile, data gradients single-pass on tile pairs) against the same
+    oracle step at the benchmarked size."""
+    config, engine = pkg
+    monkeypatch.setenv("SEDB200_CONV_HALO", "1")
+    rcfg, ref, cfg, eng = PU.make_pair(config, engine, "c2", {}, "bce", 1e-4, 1.0, seed=3)
+    x, y = R.synth_batch(rcfg, 128, seed=13)
+    res = PU.one_step_parity("c2_full_b128_t256_halo", rcfg, ref, cfg, eng, x, y, "bce", 1e-4, 1.0)
+    assert res["perr"] <= PU.PROB_TOL
+
+
 def test_c5_long_context_t2048(pkg):
     """BASELINE configs[4] geometry at its real sequence length: T = 2048, 256 filters, 3 x BiGRU(128), 16 classes
     (batch 2: the recurrence length, not the batch, is what is new here -- 2,048 dependent fp32 steps per direction

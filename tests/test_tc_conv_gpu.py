@@ -17,6 +17,14 @@ def L(built_lib):
     return built_lib
 
 
+@pytest.fixture(params=["0", "1"], ids=["boxes-per-tap", "halo-boxes"])
+def halo(request, monkeypatch):
+    """conv_tc_kernel's operand staging: one box per tap (default) or one halo box per tap column (SEDB200_CONV_HALO=1,
+    read by the library at every launch)."""
+    monkeypatch.setenv("SEDB200_CONV_HALO", request.param)
+    return request.param
+
+
 def run_tc(L, x_nhwc, w, bias, dgrad):
     from sed_crnn_b200 import _lib
     B, H, W, Ck = x_nhwc.shape
@@ -34,8 +42,10 @@ def run_tc(L, x_nhwc, w, bias, dgrad):
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 32, 8, 64, 128), (1, 40, 32, 128, 128), (3, 16, 4, 128, 128),
                                             (2, 7, 16, 64, 256), (5, 256, 8, 128, 128), (1, 3, 128, 64, 128),
-                                            (21, 256, 8, 64, 128)])          # 336 tiles: > 2 per CTA
-def test_forward_matches_float64_conv(L, B, H, W, Cin, Cout):
+                                            (21, 256, 8, 64, 128),           # 336 tiles: > 2 per CTA
+                                            (3, 24, 8, 64, 128), (2, 40, 16, 128, 128),   # halo boxes: ragged last tile
+                                            (2, 9, 64, 64, 128)])            # W = 64: the halo rows do not fit
+def test_forward_matches_float64_conv(L, halo, B, H, W, Cin, Cout):
     g = torch.Generator().manual_seed(B * 1000 + H)
     x = torch.randn(B, Cin, H, W, generator=g)
     w = torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)
@@ -46,8 +56,9 @@ def test_forward_matches_float64_conv(L, B, H, W, Cin, Cout):
     assert err < 2e-5, err
 
 
-@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 32, 8, 128, 64), (1, 40, 32, 128, 128), (2, 16, 4, 256, 128)])
-def test_dgrad_matches_autograd(L, B, H, W, Cin, Cout):
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 32, 8, 128, 64), (1, 40, 32, 128, 128), (2, 16, 4, 256, 128),
+                                            (2, 40, 16, 128, 128), (3, 24, 8, 128, 128)])
+def test_dgrad_matches_autograd(L, halo, B, H, W, Cin, Cout):
     g = torch.Generator().manual_seed(7 + H)
     x = torch.randn(B, Cin, H, W, generator=g, dtype=torch.float64, requires_grad=True)
     w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5))
