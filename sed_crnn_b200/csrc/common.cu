@@ -1,5 +1,7 @@
 // common.cu -- error plumbing, device checks, version.
 #include "common.cuh"
+#include <algorithm>
+#include <cstdlib>
 #include <atomic>
 #include <map>
 #include <mutex>
@@ -82,6 +84,28 @@ std::mutex g_prof_mu;
 }  // namespace
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+namespace {
+std::atomic<cudaStream_t> g_plain_streams[16];
+std::atomic<int> g_n_plain{0};
+}
+void pdl_exclude_stream(cudaStream_t st) {
+    if (pdl_excluded(st)) return;
+    const int i = g_n_plain.fetch_add(1);
+    if (i < 16) g_plain_streams[i].store(st);
+}
+bool pdl_excluded(cudaStream_t st) {
+    const int n = std::min(16, g_n_plain.load(std::memory_order_acquire));
+    for (int i = 0; i < n; ++i) if (g_plain_streams[i].load(std::memory_order_relaxed) == st) return true;
+    return false;
+}
+bool& pdl_in_capture() {
+    static thread_local bool on = false;
+    return on;
+}
+bool pdl_on() {
+    static const bool on = [] { const char* e = std::getenv("SEDB200_PDL"); return !e || std::atoi(e) != 0; }();
+    return on;
+}
 bool prof_on() { return g_prof.load(std::memory_order_relaxed); }
 void prof_begin(const char* name, cudaStream_t st) {
     std::lock_guard<std::mutex> lk(g_prof_mu);

@@ -33,6 +33,49 @@ void count_launch();
         SED_CUDA_OK(cudaGetLastError());         \
     } while (0)
 
+// Kernel launches of the training step: programmatic dependent launch.  Every kernel begins with pdl_wait()
+// (griddepcontrol.wait: returns once the preceding kernel of the stream has completed and its writes are visible; a
+// no-op for a kernel launched without the attribute) and is launched with programmatic stream serialization, so that
+// the launch work of kernel k+1 -- and, where the SM has room, its CTAs up to that wait -- overlaps the tail of
+// kernel k instead of starting after it.  Inside the step's CUDA graph these become programmatic dependency edges.
+// SEDB200_PDL=0 launches plainly (A/B and debugging).
+// Measured on the C2 step (profiles/README.md, "r02 programmatic dependent launch"): eagerly launched steps 1.53 ->
+// 1.43 ms, but INSIDE a CUDA graph the programmatic edges cost the concurrency of the forked branches (1.40 -> 1.51 ms,
+// also with the helper stream launching plainly), while the launch-bound small model gains in both modes (0.61 -> 0.58
+// ms as a graph).  So: always on for eager launches; during stream capture only inside a PdlCaptureScope(true), which
+// the CRNN entry points open for models without tensor-core conv blocks.
+bool pdl_on();
+bool& pdl_in_capture();                                      // thread-local
+struct PdlCaptureScope {
+    bool prev;
+    explicit PdlCaptureScope(bool on) : prev(pdl_in_capture()) { pdl_in_capture() = on; }
+    ~PdlCaptureScope() { pdl_in_capture() = prev; }
+};
+// Streams whose launches stay plain: the library's helper stream.  A kernel node with TWO programmatic dependents (the
+// next kernel of the caller's stream and the first kernel of a forked branch) loses the concurrency of the branches
+// inside a CUDA graph (measured: the side-stream weight gradients stopped overlapping, C2 step 1.40 -> 1.50 ms), so
+// forked branches depend on their fork point through ordinary edges.
+void pdl_exclude_stream(cudaStream_t st);
+bool pdl_excluded(cudaStream_t st);
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    bool pdl = pdl_on() && !pdl_excluded(st);
+    if (pdl && !pdl_in_capture()) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) pdl = false;
+    }
+    if (pdl) { cfg.attrs = at; cfg.numAttrs = 1; }
+    (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<Args&&>(args)...);      // the error is read by SED_POST_LAUNCH
+}
+#endif
+
 // optional phase profiler (sedb200_prof_enable): CUDA events on the launching stream around a phase
 bool prof_on();
 void prof_begin(const char* name, cudaStream_t st);

@@ -92,6 +92,7 @@ template <int CIN>
 __global__ void __launch_bounds__(GramDims<CIN>::THREADS)
 conv0_gram_kernel(const float* __restrict__ x, int H, int W, unsigned wmagic, int groups_per_img, int n_groups,
                   float* __restrict__ part) {
+    pdl_wait();
     using D = GramDims<CIN>;
     extern __shared__ float xs_all[];                     // 2 x [CIN][10][W+32]: row stride = W (mod 32), so the
                                                           // lanes that wrap to the next image row keep walking the banks
@@ -156,6 +157,7 @@ conv0_gram_kernel(const float* __restrict__ x, int H, int W, unsigned wmagic, in
 // gram[k][k'] (k' <= K, doubles, divided by the pixel count): one warp per entry, fixed order
 __global__ void conv0_gram_reduce_kernel(const float* __restrict__ part, int nblk, int cin, double inv_n,
                                          double* __restrict__ gram) {
+    pdl_wait();
     const int K = cin * 9, NE = K * (K + 1);
     const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (e >= NE) return;
@@ -173,6 +175,7 @@ conv0_bn_finalize_kernel(const double* __restrict__ gram, int cin, int C, long n
                          const float* __restrict__ bias, const float* __restrict__ gamma,
                          const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running,
                          float* __restrict__ stat) {
+    pdl_wait();
     __shared__ double gsh[18 * 19];
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, k = threadIdx.x & 31, K = cin * 9;
     for (int i = threadIdx.x; i < K * (K + 1); i += blockDim.x) gsh[i] = gram[i];
@@ -218,6 +221,7 @@ __global__ void __launch_bounds__(256, 2)
 conv0_lean_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                       const float* __restrict__ stat, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
                       __nv_bfloat16* __restrict__ out_lo, unsigned* __restrict__ argw, PoolGeom g, int n_rows) {
+    pdl_wait();
     extern __shared__ float xs_all[];                     // [8 warps][2][CIN][3][W+2]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c4 = blockIdx.y * 32 + lane, c = c4 * 4, C4 = g.C >> 2, Wp = g.W + 2, xsz = CIN * 3 * Wp;
@@ -355,6 +359,7 @@ template <int CIN, int P>
 __global__ void __launch_bounds__(256)
 conv0_lean_bwd_kernel(const float* __restrict__ x, const unsigned* __restrict__ argw, const float* __restrict__ dA,
                       PoolGeom g, int groups_per_img, int n_groups, float* __restrict__ part) {
+    pdl_wait();
     constexpr int K = CIN * 9;
     extern __shared__ __align__(16) float lean_smem[];
     __shared__ float red[kC0Rows][128];
@@ -463,6 +468,7 @@ conv0_lean_bwd_kernel(const float* __restrict__ x, const unsigned* __restrict__ 
 // block ranges); every load is a coalesced 512 B row, the eight range sums are added in a fixed order
 __global__ void __launch_bounds__(1024)
 conv0_lean_bwd_colsum_kernel(const float* __restrict__ part, int nblk, int K1, int C, double* __restrict__ S) {
+    pdl_wait();
     __shared__ double red[8][128];
     const int k = blockIdx.x, c = blockIdx.y * 128 + (threadIdx.x & 127), grp = threadIdx.x >> 7;
     const int mine = nblk > grp ? (nblk - grp + 7) / 8 : 0;
@@ -485,6 +491,7 @@ conv0_lean_bwd_finalize_kernel(const double* __restrict__ S, int cin, int C, con
                                const float* __restrict__ gamma, const float* __restrict__ stat,
                                float* __restrict__ dw, float* __restrict__ db, float* __restrict__ dgamma,
                                float* __restrict__ dbeta) {
+    pdl_wait();
     __shared__ double gsh[18 * 19];
     const int K = cin * 9;
     for (int i = threadIdx.x; i < K * (K + 1); i += blockDim.x) gsh[i] = gram[i];
@@ -556,6 +563,7 @@ conv0_tc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, co
                     const float* __restrict__ stat, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
                     __nv_bfloat16* __restrict__ out_lo, unsigned* __restrict__ argw, PoolGeom g, unsigned n_windows,
                     int n_tiles) {
+    pdl_wait();
     using namespace umma;
     constexpr int K = CIN * 9, KSTEPS = (K + 15) / 16, NW = 128 / P, TP = NW * P;
     constexpr int KH = (K + 1) / 2;                               // patch entries fetched by each thread of a row pair
@@ -734,13 +742,13 @@ int conv0_lean_stats(const float* x, int cin, int C, int H, int W, int batch, co
     const int gblk = std::min(n_groups, (cin == 1 ? 5 : 3) * sm_count());
     const unsigned wmagic = (unsigned)(((1ull << 32) + (unsigned)W - 1) / (unsigned)W);
     const size_t gsm = 2 * (size_t)cin * (kC0Rows + 2) * (W + 32) * 4;
-    if (cin == 1) conv0_gram_kernel<1><<<gblk, GramDims<1>::THREADS, gsm, st>>>(x, H, W, wmagic, gpi, n_groups, part);
-    else conv0_gram_kernel<2><<<gblk, GramDims<2>::THREADS, gsm, st>>>(x, H, W, wmagic, gpi, n_groups, part);
+    if (cin == 1) launch_k(conv0_gram_kernel<1>, gblk, GramDims<1>::THREADS, gsm, st, x, H, W, wmagic, gpi, n_groups, part);
+    else launch_k(conv0_gram_kernel<2>, gblk, GramDims<2>::THREADS, gsm, st, x, H, W, wmagic, gpi, n_groups, part);
     SED_POST_LAUNCH();
     const int entries = K0 * (K0 + 1);
-    conv0_gram_reduce_kernel<<<(entries * 32 + 255) / 256, 256, 0, st>>>(part, gblk, cin, 1.0 / (double)M, gram);
+    launch_k(conv0_gram_reduce_kernel, (entries * 32 + 255) / 256, 256, 0, st, part, gblk, cin, 1.0 / (double)M, gram);
     SED_POST_LAUNCH();
-    conv0_bn_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, st>>>(gram, cin, C, M, w, bias, gamma, beta, eps, momentum,
+    launch_k(conv0_bn_finalize_kernel, (C * 32 + 255) / 256, 256, 0, st, gram, cin, C, M, w, bias, gamma, beta, eps, momentum,
                                                                   running, stat);
     SED_POST_LAUNCH();
     return SEDB200_OK;
@@ -766,20 +774,20 @@ int conv0_lean_forward(const float* x, int cin, int batch, const float* w, const
                                    : (g.p == 5 ? (const void*)conv0_tc_fwd_kernel<2, 5> : (const void*)conv0_tc_fwd_kernel<2, 2>);
         const int rc = ensure_dyn_smem(kfn, c0tc::kSmem);
         if (rc) return rc;
-        if (cin == 1 && g.p == 5) conv0_tc_fwd_kernel<1, 5><<<tgrid, 256, c0tc::kSmem, st>>>(x, w, bias, stat, out, out_hi, out_lo, argw, g, n_windows, n_tiles);
-        else if (cin == 1) conv0_tc_fwd_kernel<1, 2><<<tgrid, 256, c0tc::kSmem, st>>>(x, w, bias, stat, out, out_hi, out_lo, argw, g, n_windows, n_tiles);
-        else if (g.p == 5) conv0_tc_fwd_kernel<2, 5><<<tgrid, 256, c0tc::kSmem, st>>>(x, w, bias, stat, out, out_hi, out_lo, argw, g, n_windows, n_tiles);
-        else conv0_tc_fwd_kernel<2, 2><<<tgrid, 256, c0tc::kSmem, st>>>(x, w, bias, stat, out, out_hi, out_lo, argw, g, n_windows, n_tiles);
+        if (cin == 1 && g.p == 5) launch_k(conv0_tc_fwd_kernel<1, 5>, tgrid, 256, c0tc::kSmem, st, x, w, bias, stat, out, out_hi, out_lo, argw, g, n_windows, n_tiles);
+        else if (cin == 1) launch_k(conv0_tc_fwd_kernel<1, 2>, tgrid, 256, c0tc::kSmem, st, x, w, bias, stat, out, out_hi, out_lo, argw, g, n_windows, n_tiles);
+        else if (g.p == 5) launch_k(conv0_tc_fwd_kernel<2, 5>, tgrid, 256, c0tc::kSmem, st, x, w, bias, stat, out, out_hi, out_lo, argw, g, n_windows, n_tiles);
+        else launch_k(conv0_tc_fwd_kernel<2, 2>, tgrid, 256, c0tc::kSmem, st, x, w, bias, stat, out, out_hi, out_lo, argw, g, n_windows, n_tiles);
         SED_POST_LAUNCH();
         return SEDB200_OK;
     }
     const dim3 grid(std::min(n_groups, 2 * sm_count()), g.C / 128);
     const size_t smw = (size_t)kC0Rows * 2 * cin * 3 * (g.W + 2) * 4;      // per-warp row buffers
     const int n_rows = batch * g.H;
-    if (cin == 1 && g.p == 5) conv0_lean_fwd_kernel<1, 5><<<grid, 256, smw, st>>>(x, w, bias, stat, out, out_hi, out_lo, argw, g, n_rows);
-    else if (cin == 1) conv0_lean_fwd_kernel<1, 2><<<grid, 256, smw, st>>>(x, w, bias, stat, out, out_hi, out_lo, argw, g, n_rows);
-    else if (g.p == 5) conv0_lean_fwd_kernel<2, 5><<<grid, 256, smw, st>>>(x, w, bias, stat, out, out_hi, out_lo, argw, g, n_rows);
-    else conv0_lean_fwd_kernel<2, 2><<<grid, 256, smw, st>>>(x, w, bias, stat, out, out_hi, out_lo, argw, g, n_rows);
+    if (cin == 1 && g.p == 5) launch_k(conv0_lean_fwd_kernel<1, 5>, grid, 256, smw, st, x, w, bias, stat, out, out_hi, out_lo, argw, g, n_rows);
+    else if (cin == 1) launch_k(conv0_lean_fwd_kernel<1, 2>, grid, 256, smw, st, x, w, bias, stat, out, out_hi, out_lo, argw, g, n_rows);
+    else if (g.p == 5) launch_k(conv0_lean_fwd_kernel<2, 5>, grid, 256, smw, st, x, w, bias, stat, out, out_hi, out_lo, argw, g, n_rows);
+    else launch_k(conv0_lean_fwd_kernel<2, 2>, grid, 256, smw, st, x, w, bias, stat, out, out_hi, out_lo, argw, g, n_rows);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }
@@ -800,15 +808,15 @@ int conv0_lean_backward(const float* x, int cin, int batch, const unsigned* argw
                                : (g.p == 5 ? (const void*)conv0_lean_bwd_kernel<2, 5> : (const void*)conv0_lean_bwd_kernel<2, 2>);
     const int rc = ensure_dyn_smem(kfn, (int)bsm);
     if (rc) return rc;
-    if (cin == 1 && g.p == 5) conv0_lean_bwd_kernel<1, 5><<<grid, 256, bsm, st>>>(x, argw, dA, g, gpi, n_groups, part);
-    else if (cin == 1) conv0_lean_bwd_kernel<1, 2><<<grid, 256, bsm, st>>>(x, argw, dA, g, gpi, n_groups, part);
-    else if (g.p == 5) conv0_lean_bwd_kernel<2, 5><<<grid, 256, bsm, st>>>(x, argw, dA, g, gpi, n_groups, part);
-    else conv0_lean_bwd_kernel<2, 2><<<grid, 256, bsm, st>>>(x, argw, dA, g, gpi, n_groups, part);
+    if (cin == 1 && g.p == 5) launch_k(conv0_lean_bwd_kernel<1, 5>, grid, 256, bsm, st, x, argw, dA, g, gpi, n_groups, part);
+    else if (cin == 1) launch_k(conv0_lean_bwd_kernel<1, 2>, grid, 256, bsm, st, x, argw, dA, g, gpi, n_groups, part);
+    else if (g.p == 5) launch_k(conv0_lean_bwd_kernel<2, 5>, grid, 256, bsm, st, x, argw, dA, g, gpi, n_groups, part);
+    else launch_k(conv0_lean_bwd_kernel<2, 2>, grid, 256, bsm, st, x, argw, dA, g, gpi, n_groups, part);
     SED_POST_LAUNCH();
     double* Ssum = reinterpret_cast<double*>(part + (size_t)grid.x * (K0 + 1) * g.C + 64);   // behind the partials
-    conv0_lean_bwd_colsum_kernel<<<dim3(K0 + 1, g.C / 128), 1024, 0, st>>>(part, (int)grid.x, K0 + 1, g.C, Ssum);
+    launch_k(conv0_lean_bwd_colsum_kernel, dim3(K0 + 1, g.C / 128), 1024, 0, st, part, (int)grid.x, K0 + 1, g.C, Ssum);
     SED_POST_LAUNCH();
-    conv0_lean_bwd_finalize_kernel<<<(g.C * 32 + 255) / 256, 256, 0, st>>>(Ssum, cin, g.C, gram, w, bias, gamma, stat, dw,
+    launch_k(conv0_lean_bwd_finalize_kernel, (g.C * 32 + 255) / 256, 256, 0, st, Ssum, cin, g.C, gram, w, bias, gamma, stat, dw,
                                                                           db, dgamma, dbeta);
     SED_POST_LAUNCH();
     return SEDB200_OK;

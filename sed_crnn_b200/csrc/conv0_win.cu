@@ -107,6 +107,7 @@ conv0_win_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
                      const float* __restrict__ stat, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
                      __nv_bfloat16* __restrict__ out_lo, unsigned* __restrict__ argw, PoolGeom g, unsigned n_windows,
                      int n_tiles) {
+    pdl_wait();
     using D = WinDims<CIN, P>;
     extern __shared__ unsigned char c0w_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(c0w_raw) + 1023) & ~(uintptr_t)1023);
@@ -307,7 +308,7 @@ int launch_win(const float* x, int batch, const float* w, const float* bias, con
     const void* kfn = (const void*)conv0_win_fwd_kernel<CIN, P>;
     const int rc = ensure_dyn_smem(kfn, D::kSmem);
     if (rc) return rc;
-    conv0_win_fwd_kernel<CIN, P><<<grid, kWinThreads, D::kSmem, st>>>(x, w, bias, stat, out, out_hi, out_lo, argw, g,
+    launch_k(conv0_win_fwd_kernel<CIN, P>, grid, kWinThreads, D::kSmem, st, x, w, bias, stat, out, out_hi, out_lo, argw, g,
                                                                        n_windows, n_tiles);
     SED_POST_LAUNCH();
     return SEDB200_OK;

@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(512)
 conv_small_kernel(const float* __restrict__ in, long sB, long sH, long sW, long sC, int K, int H, int W,
                   const float* __restrict__ wgt, const float* __restrict__ bias, int N, int dgrad,
                   float* __restrict__ out) {
+    pdl_wait();
     extern __shared__ __align__(16) float sm[];
     const int Wp = in_pitch(W);
     float* xs = sm;                                  // [K][kRows+2][Wp]   column w of the image sits at index w + 1
@@ -97,6 +98,7 @@ conv_small_kernel(const float* __restrict__ in, long sB, long sH, long sW, long 
 __global__ void __launch_bounds__(1024)
 conv_small_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ in, long sB, long sH, long sW, long sC,
                         int K, int N, int H, int W, int RS, float* __restrict__ part) {
+    pdl_wait();
     extern __shared__ __align__(16) float sm[];
     const int Wp = W + 2;
     float* xs = sm;                                  // [kRows+2][Wp][K]   (k fastest: lanes of a warp read consecutive words)
@@ -149,6 +151,7 @@ conv_small_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ 
 
 // dW[i] = sum_blk part[blk][i]: one warp per output, fixed order
 __global__ void conv_small_wgrad_reduce_kernel(const float* __restrict__ part, int nblk, int n_out, float* __restrict__ dw) {
+    pdl_wait();
     const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (o >= n_out) return;
     double a = 0.0;
@@ -184,7 +187,7 @@ int conv_small_forward(const float* in, long sB, long sH, long sW, long sC, int 
     int rc = ensure_dyn_smem((const void*)conv_small_kernel, 200 * 1024);
     if (rc) return rc;
     const dim3 grid((H + kRows - 1) / kRows, B);
-    conv_small_kernel<<<grid, kRows * (W / 4) * (N / 8), smem, st>>>(in, sB, sH, sW, sC, K, H, W, wgt, bias, N, dgrad, out);
+    launch_k(conv_small_kernel, grid, kRows * (W / 4) * (N / 8), smem, st, in, sB, sH, sW, sC, K, H, W, wgt, bias, N, dgrad, out);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }
@@ -206,10 +209,10 @@ int conv_small_wgrad(const float* dy, const float* in, long sB, long sH, long sW
     int rc = ensure_dyn_smem((const void*)conv_small_wgrad_kernel, 200 * 1024);
     if (rc) return rc;
     const dim3 grid((H + kRows - 1) / kRows, B);
-    conv_small_wgrad_kernel<<<grid, K * N * RS, wgrad_smem(K, N, W, RS), st>>>(dy, in, sB, sH, sW, sC, K, N, H, W, RS, part);
+    launch_k(conv_small_wgrad_kernel, grid, K * N * RS, wgrad_smem(K, N, W, RS), st, dy, in, sB, sH, sW, sC, K, N, H, W, RS, part);
     SED_POST_LAUNCH();
     const int n_out = N * K * 9, nblk = (int)(grid.x * grid.y);
-    conv_small_wgrad_reduce_kernel<<<(n_out * 32 + 255) / 256, 256, 0, st>>>(part, nblk, n_out, dw);
+    launch_k(conv_small_wgrad_reduce_kernel, (n_out * 32 + 255) / 256, 256, 0, st, part, nblk, n_out, dw);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }

@@ -156,6 +156,7 @@ bn_finalize_train_kernel(const float* __restrict__ part, int nblk, int C, long n
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                          float eps, float momentum, float* __restrict__ running,
                                          float* __restrict__ stat) {
+    pdl_wait();
     const int c = blockIdx.x;
     double s, ss;
     reduce_pair(part, nblk, C, c, s, ss);
@@ -176,6 +177,7 @@ bn_finalize_train_kernel(const float* __restrict__ part, int nblk, int C, long n
 
 __global__ void bn_finalize_eval_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                                         float eps, const float* __restrict__ running, float* __restrict__ stat) {
+    pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float mean = running[c];
@@ -191,6 +193,7 @@ __global__ void bn_finalize_eval_kernel(int C, const float* __restrict__ gamma, 
 __global__ void __launch_bounds__(256)
 bn_relu_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ stat, float* __restrict__ out,
                         __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long n_vec, PoolGeom g) {
+    pdl_wait();
     const int C4 = g.C >> 2;
     const float keep_scale = g.drop_p > 0.0f ? 1.0f / (1.0f - g.drop_p) : 1.0f;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long)gridDim.x * blockDim.x) {
@@ -237,6 +240,7 @@ __global__ void __launch_bounds__(256)
 bn_relu_pool_fwd_t_kernel(const float* __restrict__ y, const float* __restrict__ stat, float* __restrict__ out,
                           __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, unsigned n_pix,
                           PoolGeom g) {
+    pdl_wait();
     const int C4 = g.C >> 2, rows = 256 / C4;
     const int c4 = threadIdx.x % C4, prow = threadIdx.x / C4, c = c4 * 4;
     const float4 sc = *reinterpret_cast<const float4*>(stat + 2 * g.C + c);
@@ -349,6 +353,7 @@ template <int P>
 __global__ void __launch_bounds__(256)
 bn_pool_bwd_sums_t_kernel(const float* __restrict__ y, const float* __restrict__ stat, const float* __restrict__ dA,
                           long n_pix, PoolGeom g, float* __restrict__ part) {
+    pdl_wait();
     __shared__ float4 s1[256], s2[256];
     const int C4 = g.C >> 2, rows = 256 / C4;
     const int c4 = threadIdx.x % C4, prow = threadIdx.x / C4;
@@ -401,6 +406,7 @@ bn_bwd_sums_act_kernel(const float* __restrict__ act, const __nv_bfloat16* __res
                        const __nv_bfloat16* __restrict__ act_lo, const float* __restrict__ stat,
                        const float* __restrict__ dA, unsigned n_pix, PoolGeom g, float* __restrict__ part,
                        float* __restrict__ amax_part) {
+    pdl_wait();
     __shared__ float4 s1[256], s2[256];
     const int C4 = g.C >> 2, rows = 256 / C4;
     const int c4 = threadIdx.x % C4, prow = threadIdx.x / C4, c = c4 * 4;
@@ -490,6 +496,7 @@ bn_bwd_sums_act_kernel(const float* __restrict__ act, const __nv_bfloat16* __res
 __global__ void __launch_bounds__(128)
 dy_scale_kernel(const float* __restrict__ amax_part, int nblk, const float* __restrict__ stat,
                 const float* __restrict__ bnsum, int C, float* __restrict__ out) {
+    pdl_wait();
     __shared__ float sm[4], sb[4];
     float m = 0.0f, b = 0.0f;
     for (int i = threadIdx.x; i < nblk; i += 128) m = fmaxf(m, amax_part[i]);
@@ -519,6 +526,7 @@ dy_scale_kernel(const float* __restrict__ amax_part, int nblk, const float* __re
 __global__ void __launch_bounds__(256)
 bn_pool_bwd_sums_kernel(const float* __restrict__ y, const float* __restrict__ stat, const float* __restrict__ dA,
                         long n_pix, PoolGeom g, float* __restrict__ part) {
+    pdl_wait();
     __shared__ float4 s1[256], s2[256];
     const int C4 = g.C >> 2, rows = 256 / C4;
     const int c4 = threadIdx.x % C4, prow = threadIdx.x / C4;
@@ -564,6 +572,7 @@ __global__ void __launch_bounds__(128)
 bn_bwd_finalize_kernel(const float* __restrict__ part, int nblk, int C, long n,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        float* __restrict__ bnsum) {
+    pdl_wait();
     const int c = blockIdx.x;                                        // one block per channel
     double s, sx;
     reduce_pair(part, nblk, C, c, s, sx);
@@ -579,6 +588,7 @@ __global__ void __launch_bounds__(256)
 bn_pool_bwd_dy_kernel(const float* __restrict__ y, const float* __restrict__ stat, const float* __restrict__ dA,
                       const float* __restrict__ bnsum, long n_vec, PoolGeom g, float* __restrict__ dy,
                       __nv_bfloat16* __restrict__ dy_hi, const float* __restrict__ dy_scale) {
+    pdl_wait();
     const int C4 = g.C >> 2;
     const float dscale = dy_scale ? __ldg(dy_scale) : 1.0f;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long)gridDim.x * blockDim.x) {
@@ -622,6 +632,7 @@ __global__ void __launch_bounds__(256)
 bn_pool_bwd_dy_t_kernel(const float* __restrict__ y, const float* __restrict__ stat, const float* __restrict__ dA,
                         const float* __restrict__ bnsum, unsigned n_pix, PoolGeom g, float* __restrict__ dy,
                         __nv_bfloat16* __restrict__ dy_hi, const float* __restrict__ dy_scale) {
+    pdl_wait();
     const int C4 = g.C >> 2, rows = 256 / C4;
     const float dscale = dy_scale ? __ldg(dy_scale) : 1.0f;
     const int c4 = threadIdx.x % C4, prow = threadIdx.x / C4, c = c4 * 4;
@@ -687,6 +698,7 @@ __global__ void __launch_bounds__(256)
 conv0_fwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                        float* __restrict__ y, int H, int W, int C, int groups_per_img, int n_groups,
                        float* __restrict__ part) {
+    pdl_wait();
     extern __shared__ float xs_all[];                     // 2 x [CIN][10][W+2]
     __shared__ float red[kC0Rows][2][128];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -784,6 +796,7 @@ __global__ void __launch_bounds__(256)
 conv0_bwd_fused_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ stat,
                        const float* __restrict__ dA, const float* __restrict__ bnsum, PoolGeom g,
                        float* __restrict__ part) {
+    pdl_wait();
     extern __shared__ float xs[];
     __shared__ float red[kC0Rows][128];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -863,6 +876,7 @@ __global__ void __launch_bounds__(256)
 conv0_bwd_fused_t_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ stat,
                          const float* __restrict__ dA, const float* __restrict__ bnsum, PoolGeom g, int groups_per_img,
                          int n_groups, float* __restrict__ part) {
+    pdl_wait();
     extern __shared__ float xs_all[];                 // 2 x [CIN][10][W+2]
     __shared__ float red[kC0Rows][128];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -968,6 +982,7 @@ conv0_bwd_fused_t_kernel(const float* __restrict__ x, const float* __restrict__ 
 // dW[c][j] = sum_blk part[blk][j][c] (j < J), db[c] = sum_blk part[blk][J][c]; one warp per output
 __global__ void conv0_bwd_reduce_kernel(const float* __restrict__ part, int nblk, int J, int C,
                                         float* __restrict__ dw, float* __restrict__ db) {
+    pdl_wait();
     const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (o >= (J + 1) * C) return;
     const int j = o / C, c = o - j * C;
@@ -990,6 +1005,7 @@ __global__ void __launch_bounds__(256)
 dense_bwd_small_kernel(const float* __restrict__ dout, const float* __restrict__ in, const float* __restrict__ W,
                        const float* __restrict__ relu_act /* activation of the producing layer or null */,
                        int rows, int N, int D, float* __restrict__ din, float* __restrict__ part) {
+    pdl_wait();
     extern __shared__ float sm[];
     float* s_do = sm;                       // [128][N]
     float* s_in = s_do + kDbRows * N;       // [128][D+1]
@@ -1028,6 +1044,7 @@ dense_bwd_small_kernel(const float* __restrict__ dout, const float* __restrict__
 }
 __global__ void dense_bwd_reduce_kernel(const float* __restrict__ part, int nblk, int ND, int N,
                                         float* __restrict__ dw, float* __restrict__ db) {
+    pdl_wait();
     const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (o >= ND + N) return;
     double a = 0.0;
@@ -1045,6 +1062,7 @@ inline bool dense_small_ok(int N, int D) { return dense_small_smem(N, D) <= 160 
 // part_b [B][2][n6] -> dbih[n6], dbhh[n6]  (fixed-order sum over B)
 __global__ void reduce_bias_partials_kernel(const float* __restrict__ part_b, float* __restrict__ dbih,
                                             float* __restrict__ dbhh, int n6, int B) {
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 2 * n6) return;
     const float acc = ordered_sum<16, float>(part_b + i, 2L * n6, B);
@@ -1053,13 +1071,14 @@ __global__ void reduce_bias_partials_kernel(const float* __restrict__ part_b, fl
 }
 // whh[dir][r][j] = full[dir*3h + r][dir*h + j],  full is [6h][2h]
 __global__ void extract_whh_kernel(const float* __restrict__ full, int h, float* __restrict__ whh) {
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 6 * h * h) return;
     const int j = i % h, r = (i / h) % (3 * h), dir = i / (3 * h * h);
     whh[i] = full[(long)(dir * 3 * h + r) * 2 * h + dir * h + j];
 }
 inline int reduce_bias_partials(const float* part_b, float* dbih, float* dbhh, int n6, int B, cudaStream_t st) {
-    reduce_bias_partials_kernel<<<(2 * n6 + 127) / 128, 128, 0, st>>>(part_b, dbih, dbhh, n6, B);
+    launch_k(reduce_bias_partials_kernel, (2 * n6 + 127) / 128, 128, 0, st, part_b, dbih, dbhh, n6, B);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }
@@ -1109,6 +1128,7 @@ int side_stream(SideStream** out) {
     if (it == g_side.end()) {
         SideStream s;
         SED_CUDA_OK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+        pdl_exclude_stream(s.st);
         for (int i = 0; i < 4; ++i) {
             SED_CUDA_OK(cudaEventCreateWithFlags(&s.fork[i], cudaEventDisableTiming));
             SED_CUDA_OK(cudaEventCreateWithFlags(&s.done[i], cudaEventDisableTiming));
@@ -1124,6 +1144,7 @@ int side_stream(SideStream** out) {
 // counter-based generator the fused kernels evaluate (element group i = ((b*H + h)*Wo + wo)*C/4 + c/4)
 __global__ void __launch_bounds__(256)
 dropout_mask_kernel(unsigned char* __restrict__ mask, long n_vec, PoolGeom g) {
+    pdl_wait();
     const int C4 = g.C >> 2;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long)gridDim.x * blockDim.x) {
         const int c4 = (int)(i % C4);
@@ -1147,12 +1168,20 @@ using namespace sedb200;
 
 extern "C" {
 
+// programmatic dependent launch inside a captured step only for models without tensor-core conv blocks: those steps are
+// chains of ~10 us kernels (launch-bound); the large models keep the concurrency of their forked branches instead
+static bool plan_launch_bound(const Plan& P) {
+    for (int i = 0; i < P.n_conv; ++i) if (P.conv_tc_all[i]) return false;
+    return true;
+}
+
 static int crnn_forward_impl(const sedb200_crnn_desc* d, const float* params, float* bn_state, const float* x,
                              int batch, int training, unsigned long long seed, const unsigned long long* seed_ptr,
                              void* ws, size_t ws_bytes, float* logits, void* stream) {
     Plan P;
     int rc = make_plan(d, batch, &P);
     if (rc) return rc;
+    PdlCaptureScope pdl_scope(plan_launch_bound(P));
     SED_REQUIRE(batch >= 1, SEDB200_EINVAL, "crnn_forward: batch %d", batch);
     SED_REQUIRE(params && bn_state && x && ws, SEDB200_EINVAL, "crnn_forward: null buffer");
     SED_REQUIRE(ws_bytes >= P.ws_bytes, SEDB200_EWORKSPACE, "crnn_forward: workspace %zu < %zu bytes", ws_bytes, P.ws_bytes);
@@ -1230,7 +1259,7 @@ static int crnn_forward_impl(const sedb200_crnn_desc* d, const float* params, fl
                                           reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + P.gram), wsf(ws, P.part), st);
                     if (rc) return rc;
                 } else {
-                    bn_finalize_eval_kernel<<<(P.C + 127) / 128, 128, 0, st>>>(P.C, params + P.bn_w[0], params + P.bn_b[0],
+                    launch_k(bn_finalize_eval_kernel, (P.C + 127) / 128, 128, 0, st, P.C, params + P.bn_w[0], params + P.bn_b[0],
                                                                                d->bn_eps, running, stat);
                     SED_POST_LAUNCH();
                 }
@@ -1253,9 +1282,9 @@ static int crnn_forward_impl(const sedb200_crnn_desc* d, const float* params, fl
             const dim3 grid(std::min(n_groups, 2 * sm_count()), P.C / 128);
             const size_t sm = 2 * (size_t)P.cin[0] * (kC0Rows + 2) * (P.win[0] + 2) * 4;
             if (P.cin[0] == 1)
-                conv0_fwd_stats_kernel<1><<<grid, 256, sm, st>>>(x, params + P.conv_w[0], params + P.conv_b[0], y, P.H, P.win[0], P.C, gpi, n_groups, wsf(ws, P.part));
+                launch_k(conv0_fwd_stats_kernel<1>, grid, 256, sm, st, x, params + P.conv_w[0], params + P.conv_b[0], y, P.H, P.win[0], P.C, gpi, n_groups, wsf(ws, P.part));
             else
-                conv0_fwd_stats_kernel<2><<<grid, 256, sm, st>>>(x, params + P.conv_w[0], params + P.conv_b[0], y, P.H, P.win[0], P.C, gpi, n_groups, wsf(ws, P.part));
+                launch_k(conv0_fwd_stats_kernel<2>, grid, 256, sm, st, x, params + P.conv_w[0], params + P.conv_b[0], y, P.H, P.win[0], P.C, gpi, n_groups, wsf(ws, P.part));
             SED_POST_LAUNCH();
             nblk = (int)grid.x;
         } else if (P.conv_tc_all[i]) {
@@ -1287,11 +1316,11 @@ static int crnn_forward_impl(const sedb200_crnn_desc* d, const float* params, fl
                 rc = colsum_partials(y, M, P.C, wsf(ws, P.part), &nblk, st);
                 if (rc) return rc;
             }
-            bn_finalize_train_kernel<<<P.C, 128, 0, st>>>(
+            launch_k(bn_finalize_train_kernel, P.C, 128, 0, st,
                 wsf(ws, P.part), nblk, P.C, (long)M, params + P.bn_w[i], params + P.bn_b[i], d->bn_eps,
                 d->bn_momentum, running, stat);
         } else {
-            bn_finalize_eval_kernel<<<(P.C + 127) / 128, 128, 0, st>>>(P.C, params + P.bn_w[i], params + P.bn_b[i],
+            launch_k(bn_finalize_eval_kernel, (P.C + 127) / 128, 128, 0, st, P.C, params + P.bn_w[i], params + P.bn_b[i],
                                                                        d->bn_eps, running, stat);
         }
         SED_POST_LAUNCH();
@@ -1311,9 +1340,9 @@ static int crnn_forward_impl(const sedb200_crnn_desc* d, const float* params, fl
             const bool fast = (g.p == 5 || g.p == 2) && 256 % C4 == 0 && n_pix < (1L << 31);
             const int prow = 256 / C4;
             const int nb = (int)std::min<long>((n_pix + prow - 1) / prow, 148L * 16);
-            if (fast && g.p == 5) bn_relu_pool_fwd_t_kernel<5><<<nb, 256, 0, st>>>(y, stat, of, ph, pl, (unsigned)n_pix, g);
-            else if (fast) bn_relu_pool_fwd_t_kernel<2><<<nb, 256, 0, st>>>(y, stat, of, ph, pl, (unsigned)n_pix, g);
-            else bn_relu_pool_fwd_kernel<<<ew_blocks(n_vec), 256, 0, st>>>(y, stat, of, ph, pl, n_vec, g);
+            if (fast && g.p == 5) launch_k(bn_relu_pool_fwd_t_kernel<5>, nb, 256, 0, st, y, stat, of, ph, pl, (unsigned)n_pix, g);
+            else if (fast) launch_k(bn_relu_pool_fwd_t_kernel<2>, nb, 256, 0, st, y, stat, of, ph, pl, (unsigned)n_pix, g);
+            else launch_k(bn_relu_pool_fwd_kernel, ew_blocks(n_vec), 256, 0, st, y, stat, of, ph, pl, n_vec, g);
         }
         SED_POST_LAUNCH();
 }
@@ -1397,6 +1426,7 @@ static int crnn_backward_impl(const sedb200_crnn_desc* d, const float* params, c
     Plan P;
     int rc = make_plan(d, batch, &P);
     if (rc) return rc;
+    PdlCaptureScope pdl_scope(plan_launch_bound(P));
     SED_REQUIRE(batch >= 1, SEDB200_EINVAL, "crnn_backward: batch %d", batch);
     SED_REQUIRE(params && x && ws && grads, SEDB200_EINVAL, "crnn_backward: null buffer");
     SED_REQUIRE(ws_bytes >= P.ws_bytes, SEDB200_EWORKSPACE, "crnn_backward: workspace %zu < %zu bytes", ws_bytes, P.ws_bytes);
@@ -1424,9 +1454,9 @@ static int crnn_backward_impl(const sedb200_crnn_desc* d, const float* params, c
             rc = ensure_dyn_smem((const void*)dense_bwd_small_kernel, 160 * 1024);
             if (rc) return rc;
             const int nblk = (BT + kDbRows - 1) / kDbRows;
-            dense_bwd_small_kernel<<<nblk, 256, dense_small_smem(N, D), st>>>(dout, in, params + P.dn_w[j], mask, BT, N, D, din, part);
+            launch_k(dense_bwd_small_kernel, nblk, 256, dense_small_smem(N, D), st, dout, in, params + P.dn_w[j], mask, BT, N, D, din, part);
             SED_POST_LAUNCH();
-            dense_bwd_reduce_kernel<<<((N * D + N) * 32 + 255) / 256, 256, 0, st>>>(part, nblk, N * D, N, grads + P.dn_w[j], grads + P.dn_b[j]);
+            launch_k(dense_bwd_reduce_kernel, ((N * D + N) * 32 + 255) / 256, 256, 0, st, part, nblk, N * D, N, grads + P.dn_w[j], grads + P.dn_b[j]);
             SED_POST_LAUNCH();
         } else {
         // dW[n][k] = sum_m dout[m][n] * in[m][k]
@@ -1493,7 +1523,7 @@ static int crnn_backward_impl(const sedb200_crnn_desc* d, const float* params, c
             float* stpart = stmp + 12 * h * h + 64;
             rc = gemm_tc(gh_hi, gh_lo, 1, hp_hi, hp_lo, 1, 6 * h, 2 * h, BT, nullptr, stmp, 2 * h, 1, stpart, ss);
             if (rc) return rc;
-            extract_whh_kernel<<<(6 * h * h + 255) / 256, 256, 0, ss>>>(stmp, h, grads + P.whh[l]);
+            launch_k(extract_whh_kernel, (6 * h * h + 255) / 256, 256, 0, ss, stmp, h, grads + P.whh[l]);
             SED_POST_LAUNCH();
             const size_t xpb = ((size_t)BT * in * 2 + 1023) & ~(size_t)1023, wpb = ((size_t)6 * h * in * 2 + 1023) & ~(size_t)1023;
             const char* xp = reinterpret_cast<const char*>(ws) + P.gxp[l];
@@ -1541,7 +1571,7 @@ static int crnn_backward_impl(const sedb200_crnn_desc* d, const float* params, c
             }
             rc = gemm_tc(gh_hi, gh_lo, 1, hp_hi, hp_lo, 1, 6 * h, 2 * h, BT, nullptr, tmp, 2 * h, 1, tpart, st);
             if (rc) return rc;
-            extract_whh_kernel<<<(6 * h * h + 255) / 256, 256, 0, st>>>(tmp, h, grads + P.whh[l]);
+            launch_k(extract_whh_kernel, (6 * h * h + 255) / 256, 256, 0, st, tmp, h, grads + P.whh[l]);
             SED_POST_LAUNCH();
         } else {
             for (int dir = 0; dir < 2; ++dir) {
@@ -1630,9 +1660,9 @@ static int crnn_backward_impl(const sedb200_crnn_desc* d, const float* params, c
             SED_PROF("conv0.recompute_y", st);
             const dim3 grid(std::min(n_groups, 2 * sm_count()), P.C / 128);
             if (cin0 == 1)
-                conv0_fwd_stats_kernel<1><<<grid, 256, sm, st>>>(x, params + P.conv_w[0], params + P.conv_b[0], wsf(ws, P.y[0]), P.H, P.win[0], P.C, gpi, n_groups, part);
+                launch_k(conv0_fwd_stats_kernel<1>, grid, 256, sm, st, x, params + P.conv_w[0], params + P.conv_b[0], wsf(ws, P.y[0]), P.H, P.win[0], P.C, gpi, n_groups, part);
             else
-                conv0_fwd_stats_kernel<2><<<grid, 256, sm, st>>>(x, params + P.conv_w[0], params + P.conv_b[0], wsf(ws, P.y[0]), P.H, P.win[0], P.C, gpi, n_groups, part);
+                launch_k(conv0_fwd_stats_kernel<2>, grid, 256, sm, st, x, params + P.conv_w[0], params + P.conv_b[0], wsf(ws, P.y[0]), P.H, P.win[0], P.C, gpi, n_groups, part);
             SED_POST_LAUNCH();
         }
         const long n_pix_out = B * P.H * P.wout[i];
@@ -1649,19 +1679,19 @@ static int crnn_backward_impl(const sedb200_crnn_desc* d, const float* params, c
             // few long-lived blocks (4 per SM): the per-block prologue / shared-memory reduction / partial store and
             // the finalizer's work shrink with the block count, the loads in flight do not
             sblk = (int)std::min<long>(nblk, 148L * 4);
-            bn_bwd_sums_act_kernel<<<sblk, 256, 0, st>>>(
+            launch_k(bn_bwd_sums_act_kernel, sblk, 256, 0, st,
                 planes_out ? nullptr : wsf(ws, P.act[i]),
                 planes_out ? reinterpret_cast<const __nv_bfloat16*>(ap) : nullptr,
                 planes_out ? reinterpret_cast<const __nv_bfloat16*>(ap + P.act_plane_bytes[i]) : nullptr, stat, dA,
                 (unsigned)n_pix_out, g, part, P.conv_tc_all[i] ? wsf(ws, P.dys) + 8 : nullptr);
             have_amax = P.conv_tc_all[i];
-        } else if (g.p == 5 && idx32) bn_pool_bwd_sums_t_kernel<5><<<nblk, 256, 0, st>>>(y, stat, dA, n_pix_out, g, part);
-        else if (g.p == 2 && idx32) bn_pool_bwd_sums_t_kernel<2><<<nblk, 256, 0, st>>>(y, stat, dA, n_pix_out, g, part);
-        else bn_pool_bwd_sums_kernel<<<nblk, 256, 0, st>>>(y, stat, dA, n_pix_out, g, part);
+        } else if (g.p == 5 && idx32) launch_k(bn_pool_bwd_sums_t_kernel<5>, nblk, 256, 0, st, y, stat, dA, n_pix_out, g, part);
+        else if (g.p == 2 && idx32) launch_k(bn_pool_bwd_sums_t_kernel<2>, nblk, 256, 0, st, y, stat, dA, n_pix_out, g, part);
+        else launch_k(bn_pool_bwd_sums_kernel, nblk, 256, 0, st, y, stat, dA, n_pix_out, g, part);
         SED_POST_LAUNCH();
 }
         float* bnsum = wsf(ws, P.bnsum);
-        bn_bwd_finalize_kernel<<<P.C, 128, 0, st>>>(part, sblk, P.C, n_elem, grads + P.bn_w[i],
+        launch_k(bn_bwd_finalize_kernel, P.C, 128, 0, st, part, sblk, P.C, n_elem, grads + P.bn_w[i],
                                                                  grads + P.bn_b[i], bnsum);
         SED_POST_LAUNCH();
         if (i == 0 && !dx && conv0_direct_ok(P.cin[0], P.C)) {
@@ -1676,16 +1706,16 @@ static int crnn_backward_impl(const sedb200_crnn_desc* d, const float* params, c
                 const int gpi = (P.H + kC0Rows - 1) / kC0Rows, n_groups = gpi * batch;
                 const dim3 pgrid(std::min(n_groups, sm_count()), P.C / 128);
                 nparts = (int)pgrid.x;
-                if (g.p == 5 && P.cin[0] == 1) conv0_bwd_fused_t_kernel<1, 5><<<pgrid, 256, 2 * sm, st>>>(x, y, stat, dA, bnsum, g, gpi, n_groups, part);
-                else if (g.p == 5) conv0_bwd_fused_t_kernel<2, 5><<<pgrid, 256, 2 * sm, st>>>(x, y, stat, dA, bnsum, g, gpi, n_groups, part);
-                else if (P.cin[0] == 1) conv0_bwd_fused_t_kernel<1, 2><<<pgrid, 256, 2 * sm, st>>>(x, y, stat, dA, bnsum, g, gpi, n_groups, part);
-                else conv0_bwd_fused_t_kernel<2, 2><<<pgrid, 256, 2 * sm, st>>>(x, y, stat, dA, bnsum, g, gpi, n_groups, part);
+                if (g.p == 5 && P.cin[0] == 1) launch_k(conv0_bwd_fused_t_kernel<1, 5>, pgrid, 256, 2 * sm, st, x, y, stat, dA, bnsum, g, gpi, n_groups, part);
+                else if (g.p == 5) launch_k(conv0_bwd_fused_t_kernel<2, 5>, pgrid, 256, 2 * sm, st, x, y, stat, dA, bnsum, g, gpi, n_groups, part);
+                else if (P.cin[0] == 1) launch_k(conv0_bwd_fused_t_kernel<1, 2>, pgrid, 256, 2 * sm, st, x, y, stat, dA, bnsum, g, gpi, n_groups, part);
+                else launch_k(conv0_bwd_fused_t_kernel<2, 2>, pgrid, 256, 2 * sm, st, x, y, stat, dA, bnsum, g, gpi, n_groups, part);
             } else if (P.cin[0] == 1)
-                conv0_bwd_fused_kernel<1><<<grid, 256, sm, st>>>(x, y, stat, dA, bnsum, g, part);
+                launch_k(conv0_bwd_fused_kernel<1>, grid, 256, sm, st, x, y, stat, dA, bnsum, g, part);
             else
-                conv0_bwd_fused_kernel<2><<<grid, 256, sm, st>>>(x, y, stat, dA, bnsum, g, part);
+                launch_k(conv0_bwd_fused_kernel<2>, grid, 256, sm, st, x, y, stat, dA, bnsum, g, part);
             SED_POST_LAUNCH();
-            conv0_bwd_reduce_kernel<<<((J + 1) * P.C * 32 + 255) / 256, 256, 0, st>>>(
+            launch_k(conv0_bwd_reduce_kernel, ((J + 1) * P.C * 32 + 255) / 256, 256, 0, st,
                 part, nparts, J, P.C, grads + P.conv_w[0], grads + P.conv_b[0]);
             SED_POST_LAUNCH();
             break;
@@ -1701,7 +1731,7 @@ static int crnn_backward_impl(const sedb200_crnn_desc* d, const float* params, c
             // an earlier block of the same parity may still be read by its weight-gradient kernel on the side stream
             if (side_busy[2 + cpar]) { SED_CUDA_OK(cudaStreamWaitEvent(st, side->done[2 + cpar], 0)); side_busy[2 + cpar] = false; }
             if (have_amax) {
-                dy_scale_kernel<<<1, 128, 0, st>>>(wsf(ws, P.dys) + 8, sblk, stat, bnsum, P.C, dys);
+                launch_k(dy_scale_kernel, 1, 128, 0, st, wsf(ws, P.dys) + 8, sblk, stat, bnsum, P.C, dys);
                 SED_POST_LAUNCH();
             } else {
                 return fail(SEDB200_ESHAPE, "crnn_backward: plane-native block %d without the activation-sums pass", i);
@@ -1711,11 +1741,11 @@ static int crnn_backward_impl(const sedb200_crnn_desc* d, const float* params, c
         float* dyf = P.conv_tc_all[i] ? nullptr : dy;
         const bool exact_t = g.W == g.Wo * g.p && (g.p == 5 || g.p == 2) && 256 % (P.C / 4) == 0 && n_pix_out < (1L << 31);
         if (exact_t && g.p == 5)
-            bn_pool_bwd_dy_t_kernel<5><<<nblk, 256, 0, st>>>(y, stat, dA, bnsum, (unsigned)n_pix_out, g, dyf, dyh, dyh ? dys : nullptr);
+            launch_k(bn_pool_bwd_dy_t_kernel<5>, nblk, 256, 0, st, y, stat, dA, bnsum, (unsigned)n_pix_out, g, dyf, dyh, dyh ? dys : nullptr);
         else if (exact_t)
-            bn_pool_bwd_dy_t_kernel<2><<<nblk, 256, 0, st>>>(y, stat, dA, bnsum, (unsigned)n_pix_out, g, dyf, dyh, dyh ? dys : nullptr);
+            launch_k(bn_pool_bwd_dy_t_kernel<2>, nblk, 256, 0, st, y, stat, dA, bnsum, (unsigned)n_pix_out, g, dyf, dyh, dyh ? dys : nullptr);
         else
-            bn_pool_bwd_dy_kernel<<<ew_blocks(n_vec), 256, 0, st>>>(y, stat, dA, bnsum, n_vec, g, dyf, dyh, dyh ? dys : nullptr);
+            launch_k(bn_pool_bwd_dy_kernel, ew_blocks(n_vec), 256, 0, st, y, stat, dA, bnsum, n_vec, g, dyf, dyh, dyh ? dys : nullptr);
         SED_POST_LAUNCH();
 }
 
@@ -1834,7 +1864,7 @@ int sedb200_crnn_dropout_mask(const sedb200_crnn_desc* d, int batch, unsigned lo
     if (rc) return rc;
     const PoolGeom g = pool_geom(P, d, block, 1, seed);
     const long n_vec = (long)batch * P.H * P.wout[block] * (P.C / 4);
-    dropout_mask_kernel<<<ew_blocks(n_vec), 256, 0, as_stream(stream)>>>(mask_dev, n_vec, g);
+    launch_k(dropout_mask_kernel, ew_blocks(n_vec), 256, 0, as_stream(stream), mask_dev, n_vec, g);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }

@@ -26,6 +26,7 @@ constexpr int GBM = 128, GBN = 64, GBK = 16, GTHREADS = 256;
 template <class AOp, class BOp, class Epi>
 __global__ void __launch_bounds__(GTHREADS)
 gemm_simt_kernel(int M, int N, int K, int k_slice, AOp A, BOp B, Epi epi) {
+    pdl_wait();
     __shared__ __align__(16) float As[2][GBK][GBM + 4];
     __shared__ __align__(16) float Bs[2][GBK][GBN + 4];
 
@@ -129,7 +130,7 @@ inline int gemm_simt(int M, int N, int K, int splits, AOp A, BOp B, Epi epi, cud
     if (k_slice < GBK) k_slice = GBK;
     splits = K > 0 ? (K + k_slice - 1) / k_slice : 1;
     dim3 grid((M + GBM - 1) / GBM, (N + GBN - 1) / GBN, splits);
-    gemm_simt_kernel<AOp, BOp, Epi><<<grid, GTHREADS, 0, st>>>(M, N, K, k_slice, A, B, epi);
+    launch_k(gemm_simt_kernel<AOp, BOp, Epi>, grid, GTHREADS, 0, st, M, N, K, k_slice, A, B, epi);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }

@@ -23,6 +23,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 __global__ void gru_scan_fwd_kernel(const float* __restrict__ gi, const float* __restrict__ whh,
                                     const float* __restrict__ bhh, float* __restrict__ out,
                                     float* __restrict__ gates, int B, int T, int H) {
+    pdl_wait();
     extern __shared__ __align__(16) float sm[];
     const int H3 = 3 * H;
     float* Wt = sm;                       // [H][3H]   Wt[k*3H + r] = W[r][k]
@@ -94,6 +95,7 @@ __global__ void gru_scan_fwd_kernel(const float* __restrict__ gi, const float* _
 __global__ void gru_scan_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out,
                                     const float* __restrict__ gates, const float* __restrict__ whh,
                                     float* __restrict__ dgi, float* __restrict__ dgh, int B, int T, int H) {
+    pdl_wait();
     extern __shared__ __align__(16) float sm[];
     const int H3 = 3 * H;
     float* W_s = sm;                      // [3H][H]
@@ -168,6 +170,7 @@ template <int H>
 __global__ void __launch_bounds__(128)
 gru_scan_fwd_warp_kernel(const float* __restrict__ gi, const float* __restrict__ whh, const float* __restrict__ bhh,
                          float* __restrict__ out, float* __restrict__ gates, int B, int T) {
+    pdl_wait();
     constexpr int IPW = 32 / H, H3 = 3 * H;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y, j = lane % H;
@@ -239,6 +242,7 @@ gru_scan_bwd_warp_kernel(const float* __restrict__ dout, const float* __restrict
                          const float* __restrict__ gates, const float* __restrict__ whh, float* __restrict__ dgi,
                          float* __restrict__ dgh, float* __restrict__ part_w, float* __restrict__ part_b, int B,
                          int T) {
+    pdl_wait();
     constexpr int IPW = 32 / H, H3 = 3 * H;
     __shared__ float Ws[H3 * H];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -457,6 +461,7 @@ __global__ void __launch_bounds__(256)
 gru_scan_fwd_bcast32_kernel(const float* __restrict__ gi, const float* __restrict__ whh, const float* __restrict__ bhh,
                             float* __restrict__ out, float* __restrict__ gates, int B, int T,
                             __nv_bfloat16* __restrict__ hp_hi, __nv_bfloat16* __restrict__ hp_lo) {
+    pdl_wait();
     __shared__ __align__(16) float h_s[2 * 4][32];          // [buffer][pair] rows; a pair uses rows pair and 4 + pair
     __shared__ float ring[4][5][32];                        // per pair: r, z, n, q, h of the step being handed over
     const int warp = threadIdx.x >> 5, pair = warp & 3;
@@ -589,6 +594,7 @@ gru_scan_bwd_bcast32_kernel(const float* __restrict__ dout, const float* __restr
                             float* __restrict__ dgh, float* __restrict__ part_b, int B, int T,
                             __nv_bfloat16* __restrict__ gi_hi, __nv_bfloat16* __restrict__ gi_lo,
                             __nv_bfloat16* __restrict__ gh_hi, __nv_bfloat16* __restrict__ gh_lo) {
+    pdl_wait();
     __shared__ __align__(16) float dg_s[2 * 4][96];
     __shared__ float ring[4][4][32];                        // per pair: dar, daz, dan, dq of the step being handed over
     const int warp = threadIdx.x >> 5, pair = warp & 3;
@@ -616,6 +622,7 @@ template <int H>
 __global__ void __launch_bounds__(4 * H, 1)
 gru_scan_fwd_split_kernel(const float* __restrict__ gi, const float* __restrict__ whh, const float* __restrict__ bhh,
                           float* __restrict__ out, float* __restrict__ gates, int B, int T) {
+    pdl_wait();
     constexpr int KS = H / 4, H3 = 3 * H, HP = H + 16;          // HP: row pitch with 4 floats of padding per K-slice
     __shared__ __align__(16) float h_s[2][kSplitBT][HP];
     const int tid = threadIdx.x, ks = tid & 3, j = tid >> 2;
@@ -691,6 +698,7 @@ __global__ void __launch_bounds__(4 * H, 1)
 gru_scan_bwd_split_kernel(const float* __restrict__ dout, const float* __restrict__ out,
                           const float* __restrict__ gates, const float* __restrict__ whh, float* __restrict__ dgi,
                           float* __restrict__ dgh, float* __restrict__ part_b, int B, int T) {
+    pdl_wait();
     constexpr int H3 = 3 * H, RS = H3 / 4, DP = H3 + 16;        // RS rows of W_hh per K-slice; padded pitch
     __shared__ __align__(16) float dg_s[2][kSplitBT][DP];
     const int tid = threadIdx.x, ks = tid & 3, j = tid >> 2;
@@ -901,6 +909,7 @@ __global__ void __launch_bounds__(512, 1)
 gru_scan_bwd_tile128_kernel(const float* __restrict__ dout, const float* __restrict__ out,
                             const float* __restrict__ gates, const float* __restrict__ whh, float* __restrict__ dgi,
                             float* __restrict__ dgh, float* __restrict__ part_b, int B, int T) {
+    pdl_wait();
     __shared__ __align__(16) float dg_s[2][384][2];           // [buffer][gradient word][row]
     __shared__ float ops[kOpDepth][6][128][2];                // cp.async ring of the gate threads' operands
     if (blockIdx.y == 0) gru_bwd_tile128_body<false>(dout, out, gates, whh, dgi, dgh, part_b, B, T, dg_s, ops);
@@ -1024,6 +1033,7 @@ __device__ __forceinline__ void gru_fwd_tile128_body(const float* __restrict__ g
 __global__ void __launch_bounds__(512, 1)
 gru_scan_fwd_tile128_kernel(const float* __restrict__ gi, const float* __restrict__ whh, const float* __restrict__ bhh,
                             float* __restrict__ out, float* __restrict__ gates, int B, int T) {
+    pdl_wait();
     __shared__ __align__(16) float h_s[2][128][2];            // [buffer][hidden unit][row]
     __shared__ float ops[kOpDepth][3][128][2];                // cp.async ring of gi
     if (blockIdx.y == 0) gru_fwd_tile128_body<false>(gi, whh, bhh, out, gates, B, T, h_s, ops);
@@ -1035,7 +1045,7 @@ int launch_warp_fwd(const float* gi, const float* whh, const float* bhh, float* 
                     cudaStream_t st) {
     constexpr int per_block = 4 * (32 / H);
     dim3 grid((B + per_block - 1) / per_block, 2);
-    gru_scan_fwd_warp_kernel<H><<<grid, 128, 0, st>>>(gi, whh, bhh, out, gates, B, T);
+    launch_k(gru_scan_fwd_warp_kernel<H>, grid, 128, 0, st, gi, whh, bhh, out, gates, B, T);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }
@@ -1044,7 +1054,7 @@ int launch_warp_bwd(const float* dout, const float* out, const float* gates, con
                     float* dgh, float* part_w, float* part_b, int B, int T, cudaStream_t st) {
     constexpr int per_block = 4 * (32 / H);
     dim3 grid((B + per_block - 1) / per_block, 2);
-    gru_scan_bwd_warp_kernel<H><<<grid, 128, 0, st>>>(dout, out, gates, whh, dgi, dgh, part_w, part_b, B, T);
+    launch_k(gru_scan_bwd_warp_kernel<H>, grid, 128, 0, st, dout, out, gates, whh, dgi, dgh, part_w, part_b, B, T);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }
@@ -1059,7 +1069,7 @@ int gru_scan_forward(const float* gi, const float* whh, const float* bhh, float*
                      int H, cudaStream_t st, void* hprev_hi, void* hprev_lo) {
     SED_REQUIRE(!hprev_hi || gru_scan_emits_planes(H), SEDB200_ESHAPE, "gru_scan: h_prev planes need H = 32 (H = %d)", H);
     if (H == 32) {
-        gru_scan_fwd_bcast32_kernel<<<dim3((B + 3) / 4, 2), 256, 0, st>>>(
+        launch_k(gru_scan_fwd_bcast32_kernel, dim3((B + 3) / 4, 2), 256, 0, st,
             gi, whh, bhh, out, gates, B, T, reinterpret_cast<__nv_bfloat16*>(hprev_hi), reinterpret_cast<__nv_bfloat16*>(hprev_lo));
         SED_POST_LAUNCH();
         return SEDB200_OK;
@@ -1069,8 +1079,8 @@ int gru_scan_forward(const float* gi, const float* whh, const float* bhh, float*
     if (H == 128 || H == 64) {
         SED_REQUIRE((long)B * T * 2 * 4 * H < (1L << 31), SEDB200_ESHAPE, "gru_scan: B*T too large for H=%d (B=%d T=%d)", H, B, T);
         dim3 grid((B + kSplitBT - 1) / kSplitBT, 2);
-        if (H == 128) gru_scan_fwd_tile128_kernel<<<grid, 512, 0, st>>>(gi, whh, bhh, out, gates, B, T);
-        else gru_scan_fwd_split_kernel<64><<<grid, 256, 0, st>>>(gi, whh, bhh, out, gates, B, T);
+        if (H == 128) launch_k(gru_scan_fwd_tile128_kernel, grid, 512, 0, st, gi, whh, bhh, out, gates, B, T);
+        else launch_k(gru_scan_fwd_split_kernel<64>, grid, 256, 0, st, gi, whh, bhh, out, gates, B, T);
         SED_POST_LAUNCH();
         return SEDB200_OK;
     }
@@ -1080,7 +1090,7 @@ int gru_scan_forward(const float* gi, const float* whh, const float* bhh, float*
     { const int rc = ensure_dyn_smem((const void*)gru_scan_fwd_kernel, 227 * 1024); if (rc) return rc; }
     SED_REQUIRE(smem <= 227 * 1024, SEDB200_ESHAPE, "gru_scan: H=%d needs %zu B shared memory", H, smem);
     dim3 grid((B + kBT - 1) / kBT, 2);
-    gru_scan_fwd_kernel<<<grid, threads, smem, st>>>(gi, whh, bhh, out, gates, B, T, H);
+    launch_k(gru_scan_fwd_kernel, grid, threads, smem, st, gi, whh, bhh, out, gates, B, T, H);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }
@@ -1094,7 +1104,7 @@ int gru_scan_backward(const float* dout, const float* out, const float* gates, c
     if (H == 32) {
         __nv_bfloat16* pl[4] = {nullptr, nullptr, nullptr, nullptr};
         if (planes) for (int i = 0; i < 4; ++i) pl[i] = reinterpret_cast<__nv_bfloat16*>(planes[i]);
-        gru_scan_bwd_bcast32_kernel<<<dim3((B + 3) / 4, 2), 256, 0, st>>>(dout, out, gates, whh, dgi, dgh, part_b, B, T,
+        launch_k(gru_scan_bwd_bcast32_kernel, dim3((B + 3) / 4, 2), 256, 0, st, dout, out, gates, whh, dgi, dgh, part_b, B, T,
                                                                            pl[0], pl[1], pl[2], pl[3]);
         SED_POST_LAUNCH();
         return SEDB200_OK;
@@ -1104,8 +1114,8 @@ int gru_scan_backward(const float* dout, const float* out, const float* gates, c
     if (H == 128 || H == 64) {
         SED_REQUIRE((long)B * T * 2 * 4 * H < (1L << 31), SEDB200_ESHAPE, "gru_scan: B*T too large for H=%d (B=%d T=%d)", H, B, T);
         dim3 grid((B + kSplitBT - 1) / kSplitBT, 2);
-        if (H == 128) gru_scan_bwd_tile128_kernel<<<grid, 512, 0, st>>>(dout, out, gates, whh, dgi, dgh, part_b, B, T);
-        else gru_scan_bwd_split_kernel<64><<<grid, 256, 0, st>>>(dout, out, gates, whh, dgi, dgh, part_b, B, T);
+        if (H == 128) launch_k(gru_scan_bwd_tile128_kernel, grid, 512, 0, st, dout, out, gates, whh, dgi, dgh, part_b, B, T);
+        else launch_k(gru_scan_bwd_split_kernel<64>, grid, 256, 0, st, dout, out, gates, whh, dgi, dgh, part_b, B, T);
         SED_POST_LAUNCH();
         return SEDB200_OK;
     }
@@ -1115,7 +1125,7 @@ int gru_scan_backward(const float* dout, const float* out, const float* gates, c
     { const int rc = ensure_dyn_smem((const void*)gru_scan_bwd_kernel, 227 * 1024); if (rc) return rc; }
     SED_REQUIRE(smem <= 227 * 1024, SEDB200_ESHAPE, "gru_scan: H=%d needs %zu B shared memory", H, smem);
     dim3 grid((B + kBT - 1) / kBT, 2);
-    gru_scan_bwd_kernel<<<grid, threads, smem, st>>>(dout, out, gates, whh, dgi, dgh, B, T, H);
+    launch_k(gru_scan_bwd_kernel, grid, threads, smem, st, dout, out, gates, whh, dgi, dgh, B, T, H);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }

@@ -37,6 +37,7 @@ head_fused_kernel(const float* __restrict__ x, const float* __restrict__ w0, con
                   int rows, HeadDims hd, int loss_kind, float alpha, float gamma, float dl_scale,
                   float* __restrict__ logits, float* __restrict__ probs, float* __restrict__ dx,
                   float* __restrict__ part) {
+    pdl_wait();
     extern __shared__ __align__(16) float sm[];
     const int D = hd.D, N0 = hd.N0, N1 = hd.N1, Dp = x_pitch(D), Hp = N0 + 1, D4 = D >> 2;
     float* s_x = sm;                         // [128][D+4]
@@ -181,6 +182,7 @@ head_fused_kernel(const float* __restrict__ x, const float* __restrict__ w0, con
 __global__ void head_reduce_kernel(const float* __restrict__ part, int nblk, HeadDims hd, long n_elems,
                                    float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dw0,
                                    float* __restrict__ db0, float* __restrict__ loss) {
+    pdl_wait();
     const long stride = head_part_floats(hd.D, hd.N0, hd.N1);
     const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (o >= stride) return;
@@ -226,12 +228,12 @@ int head_fused_run(const Plan& P, const sedb200_crnn_desc* d, const float* param
         if (rc) return rc;
     }
     SED_PROF("head.fused", st);
-    head_fused_kernel<<<nblk, kThreads, smem, st>>>(x, params + P.dn_w[0], params + P.dn_b[0], params + P.dn_w[1],
+    launch_k(head_fused_kernel, nblk, kThreads, smem, st, x, params + P.dn_w[0], params + P.dn_b[0], params + P.dn_w[1],
                                                    params + P.dn_b[1], targets, rows, hd, loss_kind, alpha, gamma,
                                                    grad_scale / (float)n_elems, logits, probs, dx, part);
     SED_POST_LAUNCH();
     const long outs = head_part_floats(hd.D, hd.N0, hd.N1);
-    head_reduce_kernel<<<(int)((outs * 32 + 255) / 256), 256, 0, st>>>(part, nblk, hd, n_elems, grads + P.dn_w[1],
+    launch_k(head_reduce_kernel, (int)((outs * 32 + 255) / 256), 256, 0, st, part, nblk, hd, n_elems, grads + P.dn_w[1],
                                                                        grads + P.dn_b[1], grads + P.dn_w[0],
                                                                        grads + P.dn_b[0], loss);
     SED_POST_LAUNCH();

@@ -31,6 +31,7 @@ __device__ __forceinline__ float block_sum_256(float v, float* sh) {
 __global__ void __launch_bounds__(256)
 loss_kernel(int kind, float alpha, float gamma, const float* __restrict__ logits, const float* __restrict__ targets,
             long n, float gscale, float* __restrict__ probs, float* __restrict__ dlogits, float* __restrict__ part) {
+    pdl_wait();
     __shared__ float sh[8];
     float acc = 0.0f;
     const float inv_n = 1.0f / (float)n;
@@ -55,12 +56,14 @@ __device__ __forceinline__ double warp_total(const float* __restrict__ part, int
     return s;
 }
 __global__ void loss_final_kernel(const float* __restrict__ part, int nblk, long n, float* __restrict__ loss) {
+    pdl_wait();
     const double s = warp_total(part, nblk);
     if (threadIdx.x == 0) loss[0] = (float)(s / (double)n);
 }
 
 __global__ void __launch_bounds__(256)
 sumsq_kernel(const float* __restrict__ g, long n, float prescale, float* __restrict__ part) {
+    pdl_wait();
     __shared__ float sh[8];
     float acc = 0.0f;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -72,6 +75,7 @@ sumsq_kernel(const float* __restrict__ g, long n, float prescale, float* __restr
 }
 
 __global__ void gnorm_final_kernel(const float* __restrict__ part, int nblk, float* __restrict__ gnorm) {
+    pdl_wait();
     const double s = warp_total(part, nblk);
     if (threadIdx.x == 0) gnorm[0] = (float)sqrt(s);
 }
@@ -80,6 +84,7 @@ __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
             float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float max_norm,
             float prescale, const float* __restrict__ gnorm, const float* __restrict__ bc_dev) {
+    pdl_wait();
     if (bc_dev) { bc1 = __ldg(bc_dev); bc2_sqrt = __ldg(bc_dev + 1); }     // CUDA-graph steps: bias corrections of the device-side step
     float coef = prescale;
     if (max_norm > 0.0f) {
@@ -105,9 +110,11 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 struct StepState { unsigned long long seed; long long step; float bc1, bc2_sqrt; float pad[2]; };
 static_assert(sizeof(StepState) == 32, "sedb200_step_state is 32 bytes");
 __global__ void step_state_init_kernel(StepState* s, long long step) {
+    pdl_wait();
     s->seed = 0; s->step = step; s->bc1 = 1.0f; s->bc2_sqrt = 1.0f; s->pad[0] = s->pad[1] = 0.0f;
 }
 __global__ void step_advance_kernel(StepState* s, unsigned long long base_seed, float b1, float b2) {
+    pdl_wait();
     const long long step = s->step + 1;
     s->step = step;
     s->seed = base_seed + (unsigned long long)(step - 1);
@@ -119,6 +126,7 @@ __global__ void step_advance_kernel(StepState* s, unsigned long long base_seed, 
 __global__ void __launch_bounds__(256)
 frame_counts_kernel(const float* __restrict__ probs, const float* __restrict__ targets, long n_rows, int n_cls,
                     float thr, unsigned long long* __restrict__ counts) {
+    pdl_wait();
     unsigned long long tp = 0, nsys = 0, nref = 0, S = 0, D = 0, I = 0;
     for (long r = (long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (long)gridDim.x * blockDim.x) {
         int fp = 0, fn = 0;
@@ -137,6 +145,7 @@ frame_counts_kernel(const float* __restrict__ probs, const float* __restrict__ t
 __global__ void __launch_bounds__(256)
 block_counts_kernel(const float* __restrict__ probs, const float* __restrict__ targets, long n_rows, int n_cls,
                     int block, float thr, unsigned long long* __restrict__ counts) {
+    pdl_wait();
     const long n_ceil = (n_rows + block - 1) / block, n_floor = n_rows / block;
     unsigned long long tp = 0, nsys = 0, nref = 0, S = 0, D = 0, I = 0, nref_er = 0;
     for (long bi = (long)blockIdx.x * blockDim.x + threadIdx.x; bi < n_ceil; bi += (long)gridDim.x * blockDim.x) {
@@ -181,9 +190,9 @@ int sedb200_loss_fwd_bwd(int kind, float alpha, float gamma, const float* logits
     const int nb = red_blocks(n);
     float* part = reinterpret_cast<float*>(scratch);
     SED_PROF("loss", st);
-    loss_kernel<<<nb, 256, 0, st>>>(kind, alpha, gamma, logits, targets, n, grad_scale, probs, dlogits, part);
+    launch_k(loss_kernel, nb, 256, 0, st, kind, alpha, gamma, logits, targets, n, grad_scale, probs, dlogits, part);
     SED_POST_LAUNCH();
-    loss_final_kernel<<<1, 32, 0, st>>>(part, nb, n, loss);
+    launch_k(loss_final_kernel, 1, 32, 0, st, part, nb, n, loss);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }
@@ -202,14 +211,14 @@ static int clip_adam_impl(float* params, const float* grads, float* m, float* v,
     const int nb = red_blocks(n);
     float* part = reinterpret_cast<float*>(scratch);
     SED_PROF("clip_adam", st);
-    sumsq_kernel<<<nb, 256, 0, st>>>(grads, n, prescale, part);
+    launch_k(sumsq_kernel, nb, 256, 0, st, grads, n, prescale, part);
     SED_POST_LAUNCH();
-    gnorm_final_kernel<<<1, 32, 0, st>>>(part, nb, gnorm);
+    launch_k(gnorm_final_kernel, 1, 32, 0, st, part, nb, gnorm);
     SED_POST_LAUNCH();
     const double bc1 = step_state ? 1.0 : 1.0 - std::pow((double)b1, (double)step);
     const double bc2 = step_state ? 1.0 : 1.0 - std::pow((double)b2, (double)step);
     const float* bc_dev = step_state ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(step_state) + 16) : nullptr;
-    adam_kernel<<<nb, 256, 0, st>>>(params, grads, m, v, n, lr, b1, b2, eps, wd, (float)bc1, (float)std::sqrt(bc2),
+    launch_k(adam_kernel, nb, 256, 0, st, params, grads, m, v, n, lr, b1, b2, eps, wd, (float)bc1, (float)std::sqrt(bc2),
                                     max_norm, prescale, gnorm, bc_dev);
     SED_POST_LAUNCH();
     return SEDB200_OK;
@@ -234,7 +243,7 @@ int sedb200_step_state_init(void* step_state, long step, void* stream) {
     SED_REQUIRE(step_state && step >= 0, SEDB200_EINVAL, "step_state_init: bad argument");
     int rc = require_sm100();
     if (rc) return rc;
-    step_state_init_kernel<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<StepState*>(step_state), step);
+    launch_k(step_state_init_kernel, 1, 1, 0, as_stream(stream), reinterpret_cast<StepState*>(step_state), step);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }
@@ -242,7 +251,7 @@ int sedb200_step_advance(void* step_state, unsigned long long base_seed, float b
     SED_REQUIRE(step_state, SEDB200_EINVAL, "step_advance: null step state");
     int rc = require_sm100();
     if (rc) return rc;
-    step_advance_kernel<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<StepState*>(step_state), base_seed, b1, b2);
+    launch_k(step_advance_kernel, 1, 1, 0, as_stream(stream), reinterpret_cast<StepState*>(step_state), base_seed, b1, b2);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }
@@ -256,10 +265,10 @@ int sedb200_threshold_counts(const float* probs, const float* targets, long n_ro
     SED_CUDA_OK(cudaMemsetAsync(counts, 0, 13 * sizeof(unsigned long long), st));
     if (n_rows == 0) return SEDB200_OK;
     SED_REQUIRE(probs && targets, SEDB200_EINVAL, "threshold_counts: null buffer");
-    frame_counts_kernel<<<red_blocks(n_rows), 256, 0, st>>>(probs, targets, n_rows, n_cls, threshold, counts);
+    launch_k(frame_counts_kernel, red_blocks(n_rows), 256, 0, st, probs, targets, n_rows, n_cls, threshold, counts);
     SED_POST_LAUNCH();
     const long nblk = (n_rows + block - 1) / block;
-    block_counts_kernel<<<red_blocks(nblk), 256, 0, st>>>(probs, targets, n_rows, n_cls, block, threshold, counts);
+    launch_k(block_counts_kernel, red_blocks(nblk), 256, 0, st, probs, targets, n_rows, n_cls, block, threshold, counts);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }

@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const ConvTcParams p) {
+    pdl_wait();
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int n_stages = p.n_stages, stage_bytes = p.stage_bytes, n_epi_warps = p.n_epi_warps, tpi = p.tpi, planes = p.planes;
@@ -451,6 +452,7 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
 // fp32 [n] -> bf16 hi/lo planes
 __global__ void __launch_bounds__(256)
 split_planes_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long n4) {
+    pdl_wait();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
         __nv_bfloat16 h[4], l[4];
@@ -466,6 +468,7 @@ split_planes_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
 __global__ void __launch_bounds__(256)
 weight_planes_kernel(const float* __restrict__ w, int Cout, int Cin, int dgrad, int fmt, __nv_bfloat16* __restrict__ hi,
                      __nv_bfloat16* __restrict__ lo, const float* __restrict__ scale2) {
+    pdl_wait();
     const long n = 9L * Cout * Cin;
     const int N = dgrad ? Cin : Cout, K = dgrad ? Cout : Cin;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -525,6 +528,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
                 const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
                 const WgradTcParams p) {
+    pdl_wait();
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.n_stages * (p.terms == 1 ? kWgStageBytes / 2 : kWgStageBytes));
@@ -652,6 +656,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ part, int slices, int Cout, int Cin, float* __restrict__ dw,
                     const float* __restrict__ out_scale) {
+    pdl_wait();
     const long n = 9L * Cout * Cin;
     const float osc = out_scale ? __ldg(out_scale) : 1.0f;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -667,6 +672,7 @@ wgrad_reduce_kernel(const float* __restrict__ part, int slices, int Cout, int Ci
 // {2^b, 2^-(12 + b)}: 2^b places the largest |w| just below e4m3's 448 / 2 (the fp8 scale of a weight tensor)
 __global__ void __launch_bounds__(1024)
 weight_scale_kernel(const float* __restrict__ w, long n, float* __restrict__ out) {
+    pdl_wait();
     __shared__ float sm[32];
     float m = 0.0f;
     const long n4 = n >> 2;                                        // conv weights: 9 * Cout * Cin floats, 16-byte aligned
@@ -710,13 +716,13 @@ int conv_tc_weight_planes(const float* w, int Cin, int Cout, int dgrad, void* wp
     SED_REQUIRE(!scale2 || (fmt == kPlaneF16 && !dgrad && Cin % 64 == 0), SEDB200_EINVAL,
                 "conv_tc_weight_planes: the fp8 correction plane exists for the fp16 forward layout only");
     if (scale2) {
-        weight_scale_kernel<<<1, 1024, 0, st>>>(w, 9L * Cout * Cin, scale2);
+        launch_k(weight_scale_kernel, 1, 1024, 0, st, w, 9L * Cout * Cin, scale2);
         SED_POST_LAUNCH();
     }
     const size_t wp = ((size_t)9 * Cout * Cin * 2 + 1023) & ~(size_t)1023;
     __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(wplanes);
     __nv_bfloat16* w_lo = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(wplanes) + wp);
-    weight_planes_kernel<<<(int)std::min<long>((9L * Cout * Cin + 255) / 256, 1184), 256, 0, st>>>(w, Cout, Cin, dgrad, fmt, w_hi, w_lo, scale2);
+    launch_k(weight_planes_kernel, (int)std::min<long>((9L * Cout * Cin + 255) / 256, 1184), 256, 0, st, w, Cout, Cin, dgrad, fmt, w_hi, w_lo, scale2);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }
@@ -816,7 +822,7 @@ int conv_tc_planes_w(const void* a_hi, const void* a_lo, const void* wplanes, co
     { const int rc = ensure_dyn_smem((const void*)conv_tc_kernel, 227 * 1024); if (rc) return rc; }
     const int grid = std::min(p.total_items, sm_count());
     SED_REQUIRE(terms != 1 || !stats, SEDB200_EINVAL, "conv_tc: BatchNorm statistics need a forward mode");
-    conv_tc_kernel<<<grid, kConvThreads, smem_bytes, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+    launch_k(conv_tc_kernel, grid, kConvThreads, smem_bytes, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }
@@ -832,7 +838,7 @@ int conv_tc_forward(const float* in, const float* w, const float* bias, float* o
     const size_t act = ((size_t)B * H * W * Kc * 2 + 1023) & ~(size_t)1023;
     char* s = reinterpret_cast<char*>(scratch);
     const long n4 = (long)B * H * W * Kc / 4;
-    split_planes_kernel<<<(int)std::min<long>((n4 + 255) / 256, 148L * 8), 256, 0, st>>>(
+    launch_k(split_planes_kernel, (int)std::min<long>((n4 + 255) / 256, 148L * 8), 256, 0, st,
         in, reinterpret_cast<__nv_bfloat16*>(s), reinterpret_cast<__nv_bfloat16*>(s + act), n4);
     SED_POST_LAUNCH();
     return conv_tc_planes(s, s + act, w, bias, out, nullptr, B, H, W, Cin, Cout, dgrad, s + 2 * act, st);
@@ -900,9 +906,9 @@ int wgrad_tc_planes(const void* y_hi, const void* y_lo, const void* x_hi, const 
     const int smem_bytes = p.n_stages * (terms == 1 ? kWgStageBytes / 2 : kWgStageBytes) + 1024 + 256;
     { const int rc = ensure_dyn_smem((const void*)wgrad_tc_kernel, kWgSmemBytes); if (rc) return rc; }
     const int grid = p.n_mt * p.n_nt * 3 * p.slices;
-    wgrad_tc_kernel<<<grid, kThreads, smem_bytes, st>>>(tmY_hi, tmY_lo, tmX_hi, tmX_lo, p);
+    launch_k(wgrad_tc_kernel, grid, kThreads, smem_bytes, st, tmY_hi, tmY_lo, tmX_hi, tmX_lo, p);
     SED_POST_LAUNCH();
-    wgrad_reduce_kernel<<<(int)std::min<long>((9L * Cout * Cin + 255) / 256, 1184), 256, 0, st>>>(part, p.slices, Cout, Cin, dw, out_scale);
+    launch_k(wgrad_reduce_kernel, (int)std::min<long>((9L * Cout * Cin + 255) / 256, 1184), 256, 0, st, part, p.slices, Cout, Cin, dw, out_scale);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }
@@ -916,11 +922,11 @@ int wgrad_tc(const float* dy, const float* in, float* dw, int B, int H, int W, i
     const size_t ysz = (px * Cout * 2 + 1023) & ~(size_t)1023, xsz = (px * Cin * 2 + 1023) & ~(size_t)1023;
     char* s = reinterpret_cast<char*>(scratch);
     long n4 = (long)px * Cout / 4;
-    split_planes_kernel<<<(int)std::min<long>((n4 + 255) / 256, 148L * 8), 256, 0, st>>>(
+    launch_k(split_planes_kernel, (int)std::min<long>((n4 + 255) / 256, 148L * 8), 256, 0, st,
         dy, reinterpret_cast<__nv_bfloat16*>(s), reinterpret_cast<__nv_bfloat16*>(s + ysz), n4);
     SED_POST_LAUNCH();
     n4 = (long)px * Cin / 4;
-    split_planes_kernel<<<(int)std::min<long>((n4 + 255) / 256, 148L * 8), 256, 0, st>>>(
+    launch_k(split_planes_kernel, (int)std::min<long>((n4 + 255) / 256, 148L * 8), 256, 0, st,
         in, reinterpret_cast<__nv_bfloat16*>(s + 2 * ysz), reinterpret_cast<__nv_bfloat16*>(s + 2 * ysz + xsz), n4);
     SED_POST_LAUNCH();
     return wgrad_tc_planes(s, s + ysz, s + 2 * ysz, s + 2 * ysz + xsz, dw, B, H, W, Cin, Cout,

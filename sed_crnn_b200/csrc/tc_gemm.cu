@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const GemmTcParams p) {
+    pdl_wait();
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -205,6 +206,7 @@ __device__ __forceinline__ void split1(float x, __nv_bfloat16& hi, __nv_bfloat16
 }
 __global__ void __launch_bounds__(256)
 split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long n4) {
+    pdl_wait();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
         __nv_bfloat16 h[4], l[4];
@@ -218,6 +220,7 @@ split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_b
 __global__ void __launch_bounds__(256)
 hprev_planes_kernel(const float* __restrict__ out, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                     long n, int T, int H) {
+    pdl_wait();
     const int H2 = 2 * H;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
         const int c = (int)(i % H2);
@@ -236,7 +239,7 @@ int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& 
            const GemmTcParams& p, cudaStream_t st) {
     { const int rc = ensure_dyn_smem((const void*)gemm_tc_kernel<A_MN, B_MN>, kSmemBytes); if (rc) return rc; }
     const int grid = std::min(p.n_items, sm_count());
-    gemm_tc_kernel<A_MN, B_MN><<<grid, kThreads, kSmemBytes, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+    launch_k(gemm_tc_kernel<A_MN, B_MN>, grid, kThreads, kSmemBytes, st, a_hi, a_lo, b_hi, b_lo, p);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }
@@ -269,7 +272,7 @@ size_t gemm_tc_scratch_bytes(int M, int N, int K, int a_mn, int b_mn, int split_
 int split_planes(const float* x, void* hi, void* lo, long n, cudaStream_t st) {
     SED_REQUIRE(n % 4 == 0, SEDB200_ESHAPE, "split_planes: n %% 4 != 0");
     const long n4 = n / 4;
-    split_kernel<<<(int)std::min<long>((n4 + 255) / 256, 148L * 8), 256, 0, st>>>(
+    launch_k(split_kernel, (int)std::min<long>((n4 + 255) / 256, 148L * 8), 256, 0, st,
         x, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), n4);
     SED_POST_LAUNCH();
     return SEDB200_OK;
@@ -277,7 +280,7 @@ int split_planes(const float* x, void* hi, void* lo, long n, cudaStream_t st) {
 
 int hprev_planes(const float* out, void* hi, void* lo, long rows, int T, int H, cudaStream_t st) {
     const long n = rows * 2 * H;
-    hprev_planes_kernel<<<(int)std::min<long>((n + 255) / 256, 148L * 8), 256, 0, st>>>(
+    launch_k(hprev_planes_kernel, (int)std::min<long>((n + 255) / 256, 148L * 8), 256, 0, st,
         out, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), n, T, H);
     SED_POST_LAUNCH();
     return SEDB200_OK;

@@ -7,6 +7,7 @@ namespace sedb200 {
 
 __global__ void reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, long n,
                                        int splits) {
+    pdl_wait();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
         out[i] = ordered_sum<8, float>(part + i, n, splits);
     }
@@ -15,7 +16,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, float* __
 int reduce_partials(const float* part, float* out, long n, int splits, cudaStream_t st) {
     if (n <= 0) return SEDB200_OK;
     const int blocks = (int)std::min<long>((n + 255) / 256, 1184);
-    reduce_partials_kernel<<<blocks, 256, 0, st>>>(part, out, n, splits);
+    launch_k(reduce_partials_kernel, blocks, 256, 0, st, part, out, n, splits);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }
@@ -33,6 +34,7 @@ __host__ __device__ inline int col_width(int cols) {
 // part layout: [nblk][2][cols]  (0: sum x, 1: sum x^2)
 __global__ void __launch_bounds__(256)
 colsum2_kernel(const float* __restrict__ X, long rows, int cols, long rows_per_blk, float* __restrict__ part) {
+    pdl_wait();
     __shared__ float s1[256], s2[256];
     const int CW = col_width(cols), RY = 256 / CW;
     const int cx = threadIdx.x % CW, ry = threadIdx.x / CW;
@@ -66,6 +68,7 @@ colsum2_kernel(const float* __restrict__ X, long rows, int cols, long rows_per_b
 // one warp per column: fixed lane assignment + fixed shuffle tree (deterministic)
 __global__ void colsum_final_kernel(const float* __restrict__ part, int nblk, int cols, float* __restrict__ out,
                                     float* __restrict__ out_sq) {
+    pdl_wait();
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= cols) return;
     double a = 0.0, b = 0.0;
@@ -97,7 +100,7 @@ long colsum_scratch_floats(long rows, int cols) { return (long)colsum_blocks(row
 int colsum_partials(const float* X, long rows, int cols, float* part, int* nblk_out, cudaStream_t st) {
     const int nb = colsum_blocks(rows);
     const long rpb = (rows + nb - 1) / nb;
-    colsum2_kernel<<<nb, 256, 0, st>>>(X, rows, cols, rpb, part);
+    launch_k(colsum2_kernel, nb, 256, 0, st, X, rows, cols, rpb, part);
     SED_POST_LAUNCH();
     *nblk_out = nb;
     return SEDB200_OK;
@@ -107,7 +110,7 @@ int colsum(const float* X, long rows, int cols, float* out, float* scratch, cuda
     int nb = 0;
     int rc = colsum_partials(X, rows, cols, scratch, &nb, st);
     if (rc) return rc;
-    colsum_final_kernel<<<(cols * 32 + 255) / 256, 256, 0, st>>>(scratch, nb, cols, out, nullptr);
+    launch_k(colsum_final_kernel, (cols * 32 + 255) / 256, 256, 0, st, scratch, nb, cols, out, nullptr);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }
@@ -119,6 +122,7 @@ namespace {
 __global__ void standardize_final_kernel(const float* __restrict__ part, int nblk, int cols, long rows,
                                          double* __restrict__ mean, double* __restrict__ var,
                                          double* __restrict__ scale) {
+    pdl_wait();
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= cols) return;
     double a = 0.0, b = 0.0;
@@ -144,6 +148,7 @@ __global__ void standardize_final_kernel(const float* __restrict__ part, int nbl
 __global__ void __launch_bounds__(256)
 standardize_apply_kernel(const float* __restrict__ X, long n, int cols, const double* __restrict__ mean,
                          const double* __restrict__ scale, float* __restrict__ out) {
+    pdl_wait();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
         const int c = (int)(i % cols);
         out[i] = (float)((float)((double)__ldg(X + i) - mean[c]) / scale[c]);      // two roundings, like numpy in-place ops
@@ -170,7 +175,7 @@ int sedb200_standardize_fit(const float* x_dev, long rows, int cols, double* mea
     int nb = 0;
     rc = colsum_partials(x_dev, rows, cols, reinterpret_cast<float*>(scratch_dev), &nb, st);
     if (rc) return rc;
-    standardize_final_kernel<<<(cols * 32 + 255) / 256, 256, 0, st>>>(reinterpret_cast<float*>(scratch_dev), nb, cols, rows,
+    launch_k(standardize_final_kernel, (cols * 32 + 255) / 256, 256, 0, st, reinterpret_cast<float*>(scratch_dev), nb, cols, rows,
                                                                     mean_dev, var_dev, scale_dev);
     SED_POST_LAUNCH();
     return SEDB200_OK;
@@ -184,7 +189,7 @@ int sedb200_standardize_apply(const float* x_dev, long rows, int cols, const dou
     int rc = require_sm100();
     if (rc) return rc;
     const long n = rows * cols;
-    standardize_apply_kernel<<<(int)std::min<long>((n + 255) / 256, 148L * 16), 256, 0, as_stream(stream)>>>(
+    launch_k(standardize_apply_kernel, (int)std::min<long>((n + 255) / 256, 148L * 16), 256, 0, as_stream(stream),
         x_dev, n, cols, mean_dev, scale_dev, out_dev);
     SED_POST_LAUNCH();
     return SEDB200_OK;
