@@ -653,6 +653,12 @@ def dropin_e2e_leg(torch, steps=20):
     return out
 
 
+def pipe_floor(issued_flops, ms, sm_mhz=1965.0, n_sm=148):
+    """Tensor-pipe floor of a tcgen05 launch: issued fp16-pass FLOPs at 8192 dense FLOP / clk / SM."""
+    floor_ms = issued_flops / (n_sm * 8192.0 * sm_mhz * 1e6) * 1e3
+    return {"pipe_floor_ms": floor_ms, "frac_of_pipe_floor": floor_ms / ms if ms > 0 else None}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -799,15 +805,19 @@ def run_ours(args, rank, world, local_rank):
             for i in range(7):                          # eager first call + one graph per (batch, parity)
                 eng4.train_step(x4[i % 2], y4[i % 2])
             n4 = 10
-            barrier()
-            e0.record()
-            for i in range(n4):
-                eng4.train_step(x4[i % 2], y4[i % 2])
-            e1.record()
-            barrier()
-            t4 = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-            if world > 1:
-                dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+            blocks4 = []
+            for _ in range(3):                          # median of three timed blocks (max over ranks each)
+                barrier()
+                e0.record()
+                for i in range(n4):
+                    eng4.train_step(x4[i % 2], y4[i % 2])
+                e1.record()
+                barrier()
+                t4 = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+                if world > 1:
+                    dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+                blocks4.append(t4.item())
+            t4 = torch.tensor([sorted(blocks4)[1]], device="cuda")
             if eng4.xch is not None:
                 eng4.xch.raise_if_failed(wait=True)
                 eng4.xch.close()
@@ -913,7 +923,16 @@ def run_ours(args, rank, world, local_rank):
                 "peak_source": pk["src"] + " (sustained bf16)", "algorithmic_flops_per_launch": amount,
                 "mma_tflops_issued": issued, "frac_issued": issued / pk["tf_sustained"],
                 "per_phase": {k: {"ms": phases[k], "algorithmic_tflops": model[k][1] / (phases[k] * 1e-3) / 1e12,
-                                  "mma_passes": model[k][3] if len(model[k]) > 3 else 1} for k in dks},
+                                  "mma_passes": model[k][3] if len(model[k]) > 3 else 1,
+                                  **pipe_floor(model[k][1] * (model[k][3] if len(model[k]) > 3 else 1), phases[k])}
+                              for k in dks},
+                "tensor_pipe": {**pipe_floor(sum(model[k][1] * (model[k][3] if len(model[k]) > 3 else 1) for k in dks),
+                                             ms_kernel_step),
+                                "note": "a 128x128x16 fp16 (or 128x128x32 e4m3) tcgen05.mma occupies an SM's tensor pipe for 64 "
+                                "cycles (8192 dense FLOP per cycle and SM; ncu's sm__pipe_tensor_subpipe_hmma_cycles_active "
+                                "counts exactly that: profiles/README.md); floor_ms = issued pass-FLOPs / (148 SMs x 8192 x "
+                                "sm_max_mhz), frac_of_floor = floor_ms / measured ms = tensor-pipe busy fraction if the SM "
+                                "clock held its maximum inside the launch"},
                 "note": "frac = algorithmic FLOPs (2*M*K*N, SURVEY 8d) / measured sustained fp16/bf16 peak, pooled over this "
                 "kernel's launches in a step; the forward launches run one fp16 pass plus one e4m3 correction pass (twice the K "
                 "at twice the rate: 2 fp16-pass units per k-step), the data-gradient launches one pass; frac_issued counts "
