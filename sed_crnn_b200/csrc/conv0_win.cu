@@ -116,7 +116,7 @@ conv0_win_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
     uint64_t* bars = reinterpret_cast<uint64_t*>(a_base + 4 * kWinAPlane);
     uint64_t *a_full = bars, *a_empty = bars + 2, *t_full = bars + 4, *t_empty = bars + 6;     // t_*: one per channel group
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp-uniform by construction
     const int cg0 = blockIdx.y * (32 * D::kGroups);               // first channel of this CTA
 
     if (tid == 0) {
@@ -151,7 +151,7 @@ conv0_win_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const unsigned uWo = (unsigned)g.Wo, uH = (unsigned)g.H;
 
     if (warp < 4) {
@@ -190,28 +190,32 @@ conv0_win_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
     } else if (warp == 4) {
         // ================= MMA issuer: one accumulator per channel group, released by the epilogue as soon as it
         //                   sits in registers (a few hundred cycles), so a single buffer per group is enough =========
-        if (lane == 0) {
+        // (warp-wide control flow, one elected lane issues: tc_umma.cuh elect_one)
+        {
             constexpr uint32_t idesc = idesc_bf16(128, D::NB, 0, 0);
+            const uint64_t dbase = smem_desc_sw128(smem_u32(b_base), 16, 1024);          // b_base = start of the buffer
+            constexpr uint32_t apl_u = kWinAPlane >> 4, bpl_u = D::BPlane >> 4, a_off_u = (D::kGroups * 2 * D::BPlane) >> 4;
             int buf = 0; uint32_t phase = 0, tphase = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 mbar_wait(a_full + buf, phase);
-                const uint32_t ah = smem_u32(a_base + buf * 2 * kWinAPlane), al = ah + kWinAPlane;
+                const uint64_t dah0 = dbase + (uint64_t)(a_off_u + buf * 2 * apl_u), dal0 = dah0 + apl_u;
 #pragma unroll
                 for (int gq = 0; gq < D::kGroups; ++gq) {
                     mbar_wait(t_empty + gq, tphase ^ 1);         // the epilogue has drained this group's accumulator
                     tc_fence_after();
-                    const uint32_t bh2 = smem_u32(b_base + gq * 2 * D::BPlane), bl = bh2 + D::BPlane;
-                    const uint32_t d = tmem + gq * 256;
+                    if (elect_one()) {
+                        const uint64_t dbh0 = dbase + (uint64_t)(gq * 2 * bpl_u), dbl0 = dbh0 + bpl_u;
+                        const uint32_t d = tmem + gq * 256;
 #pragma unroll
-                    for (int k = 0; k < D::KSTEPS; ++k) {
-                        const uint64_t dah = smem_desc_sw128(ah + k * 32, 16, 1024), dal = smem_desc_sw128(al + k * 32, 16, 1024);
-                        const uint64_t dbh = smem_desc_sw128(bh2 + k * 32, 16, 1024), dbl = smem_desc_sw128(bl + k * 32, 16, 1024);
-                        mma_bf16(d, dah, dbh, idesc, k != 0);
-                        mma_bf16(d, dah, dbl, idesc, 1);
-                        mma_bf16(d, dal, dbh, idesc, 1);
+                        for (int k = 0; k < D::KSTEPS; ++k) {
+                            mma_bf16(d, dah0 + 2 * k, dbh0 + 2 * k, idesc, k != 0);
+                            mma_bf16(d, dah0 + 2 * k, dbl0 + 2 * k, idesc, 1);
+                            mma_bf16(d, dal0 + 2 * k, dbh0 + 2 * k, idesc, 1);
+                        }
+                        if (gq == D::kGroups - 1) mma_commit(a_empty + buf);
+                        mma_commit(t_full + gq);
                     }
-                    if (gq == D::kGroups - 1) mma_commit(a_empty + buf);
-                    mma_commit(t_full + gq);
+                    __syncwarp();
                 }
                 tphase ^= 1;
                 if (++buf == 2) { buf = 0; phase ^= 1; }

@@ -150,7 +150,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     float* stat_s = reinterpret_cast<float*>(smem + ring_bytes + 256);                // [4 warps][2][128]
     float* epi_stage = stat_s + 1024;                                                 // [epilogue warps][32][kEpiPitch]
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform by construction
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
     }
@@ -164,7 +164,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const int n_kb = 9 * p.kchunks;
     // work item -> (N tile, first M tile); an item covers M tiles mt0 .. mt0 + tpi - 1 (a tile past the end reads zeros
     // -- TMA fills boxes outside the tensor -- and is never stored)
@@ -203,7 +203,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 }
             }
         }
-    } else if (warp == 1 && lane == 0 && p.halo) {
+    } else if (warp == 1 && p.halo) {
         // ================= MMA issuer, halo mode: tap row r = descriptor start r * W rows into the A box =============
         const uint32_t idesc = p.idesc;
         const uint64_t dbase = smem_desc_sw128(smem_u32(smem), 16, 1024);
@@ -225,6 +225,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     tc_fence_after();
                     const uint64_t dbh0 = dbase + (uint64_t)(b_ring_u + bs * b_slot_u), dbl0 = dbh0 + tile_u;
                     const uint64_t dar = da + (uint64_t)(r * row_u);
+                    if (elect_one()) {
                     if (p.terms == 2) {
                         const uint32_t d1 = tmem_base + (buf * 2) * kTileN, d2 = d1 + kTileN;
                         const uint64_t dac = dar + a_plane_u;
@@ -252,14 +253,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                             mma_bf16(d, dal0 + 2 * k, dbh0 + 2 * k, idesc, 1);
                         }
                     }
-                    acc0 = 1;
                     mma_commit(empty + bs);
+                    if (r == 2) mma_commit(aempty + as);
+                    if (r == 2 && sc == 3 * p.kchunks - 1) mma_commit(tfull + buf);
+                    }
+                    __syncwarp();
+                    acc0 = 1;
                     if (++bs == n_stages) { bs = 0; bph ^= 1; }
                 }
-                mma_commit(aempty + as);
                 if (++as == p.n_a) { as = 0; aph ^= 1; }
             }
-            mma_commit(tfull + buf);
             if (++buf == 2) { buf = 0; bphase ^= 1; }
         }
     } else if (warp == 0) {
@@ -294,8 +297,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ================= MMA issuer =================
+    } else if (warp == 1) {
+        // ================= MMA issuer (warp-wide control flow, one elected lane issues: tc_umma.cuh elect_one) ====
         // The issuing thread is a serial instruction stream: with one MMA pass per k-step a stage holds only ~256 cycles
         // of tensor work, so descriptor construction must not cost more than that -- every descriptor is the
         // descriptor of the shared-memory base plus a (16-byte-unit) offset added to its low word.
@@ -313,6 +316,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 const uint64_t ds = dbase + (uint64_t)(stage * stage_u);
                 const uint64_t dbh0 = ds + b_u, dbl0 = dbh0 + tile_u;
                 const uint32_t acc0 = kb != 0;
+                if (elect_one()) {
                 if (p.terms == 2) {
                     // fp16 hi*hi into accumulator 0, the combined e4m3 correction tiles (128 fp8 along K) into accumulator 1
                     const uint32_t d1 = tmem_base + (buf * 2) * kTileN, d2 = d1 + kTileN;
@@ -347,9 +351,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     }
                 }
                 mma_commit(empty + stage);                 // smem slot reusable once these MMAs retire
+                if (kb == n_kb - 1) mma_commit(tfull + buf);   // accumulators complete
+                }
+                __syncwarp();
                 if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
-            mma_commit(tfull + buf);                       // accumulators complete
             if (++buf == 2) { buf = 0; bphase ^= 1; }
         }
     } else if (warp >= 4 && warp < 4 + n_epi_warps) {
@@ -541,7 +547,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
     // 1-term stage: {dY hi: 2 halves} + 3 x {In hi: 2 halves}; 3-term stage: each of those followed by its lo boxes
     const int a_bytes = p.terms == 1 ? kWgABytes / 2 : kWgABytes, b_bytes = p.terms == 1 ? kWgBBytes / 2 : kWgBBytes;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform by construction
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmY_hi); prefetch_tmap(&tmY_lo); prefetch_tmap(&tmX_hi); prefetch_tmap(&tmX_lo);
     }
@@ -554,7 +560,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     // work item of this CTA
     int w = blockIdx.x;
@@ -594,32 +600,38 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
             if (++hb == p.hblocks_per_img) { hb = 0; ++b; }
             if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
+        // warp-wide control flow, one elected lane issues (tc_umma.cuh: elect_one); the descriptors of a stage are the
+        // descriptor of its first box plus a 16-byte-unit offset added to the low word
         const uint32_t idesc = p.idesc;                             // both operands MN-major
+        const uint64_t dbase = smem_desc_sw128(smem_u32(smem), kWgBox, 1024);
+        const uint32_t stage_u = (uint32_t)stage_bytes >> 4, a_u = (uint32_t)a_bytes >> 4, b_u = (uint32_t)b_bytes >> 4;
+        constexpr uint32_t lo_u = (2 * kWgBox) >> 4, k_u = 2048 >> 4;
         int stage = 0; uint32_t phase = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(full + stage, phase);
             tc_fence_after();
-            const uint32_t a_hi = smem_u32(smem + stage * stage_bytes), a_lo = a_hi + 2 * kWgBox;
+            if (elect_one()) {
+                const uint64_t da_hi = dbase + (uint64_t)(stage * stage_u), da_lo = da_hi + lo_u;
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
-                const uint32_t b_hi = a_hi + a_bytes + s * b_bytes, b_lo = b_hi + 2 * kWgBox;
-                const uint32_t d = tmem_base + s * 128;
+                for (int s = 0; s < 3; ++s) {
+                    const uint64_t db_hi = da_hi + a_u + (uint64_t)(s * b_u), db_lo = db_hi + lo_u;
+                    const uint32_t d = tmem_base + s * 128;
 #pragma unroll
-                for (int k = 0; k < kWgKp / 16; ++k) {
-                    const uint64_t dah = smem_desc_sw128(a_hi + k * 2048, kWgBox, 1024), dbh = smem_desc_sw128(b_hi + k * 2048, kWgBox, 1024);
-                    mma_bf16(d, dah, dbh, idesc, (kb != kb0 || k != 0));
-                    if (p.terms != 1) {
-                        const uint64_t dal = smem_desc_sw128(a_lo + k * 2048, kWgBox, 1024), dbl = smem_desc_sw128(b_lo + k * 2048, kWgBox, 1024);
-                        mma_bf16(d, dah, dbl, idesc, 1);
-                        mma_bf16(d, dal, dbh, idesc, 1);
+                    for (int k = 0; k < kWgKp / 16; ++k) {
+                        mma_bf16(d, da_hi + k * k_u, db_hi + k * k_u, idesc, (kb != kb0 || k != 0));
+                        if (p.terms != 1) {
+                            mma_bf16(d, da_hi + k * k_u, db_lo + k * k_u, idesc, 1);
+                            mma_bf16(d, da_lo + k * k_u, db_hi + k * k_u, idesc, 1);
+                        }
                     }
                 }
+                mma_commit(empty + stage);
+                if (kb == kb1 - 1) mma_commit(tfull);
             }
-            mma_commit(empty + stage);
+            __syncwarp();
             if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
-        mma_commit(tfull);
     } else if (warp >= 4) {
         const int q = warp - 4;
         const int co = mt * 128 + q * 32 + lane;
@@ -757,12 +769,12 @@ int conv_tc_planes_w(const void* a_hi, const void* a_lo, const void* wplanes, co
     p.kchunks = Kc / kBlockK;
     p.n_total = Nc;
     p.terms = terms;
-    // halo mode (one A box per tap COLUMN, conv_halo_mode): possible whenever a tap-row offset is a whole number of
-    // swizzle atoms.  Measured (profiles/README.md, "r02 halo boxes"): 30-40 % fewer bytes into shared memory and NO
-    // gain -- the launches sit on the tensor pipe's 64 cycles per 128x128x16 MMA, not on L2 -- so it is opt-in
-    // (SEDB200_CONV_HALO=1; the parity tests run both settings).
+    // halo mode (one A box per tap COLUMN, conv_halo_mode) whenever a tap-row offset is a whole number of swizzle atoms.
+    // Measured (profiles/README.md, "r02 halo boxes"): no gain while the MMA-issuing thread was the bound, conv 2 forward
+    // 0.153 -> 0.134 ms and its data gradient 0.082 -> 0.073 ms once the issue stream was warp-uniform.
+    // SEDB200_CONV_HALO=0 turns it off (the parity tests run both settings).
     const char* e_halo = std::getenv("SEDB200_CONV_HALO");
-    bool halo = (W % 8 == 0) && e_halo && std::atoi(e_halo) != 0;
+    bool halo = (W % 8 == 0) && !(e_halo && std::atoi(e_halo) == 0);
     // two M tiles per work item when the CTAs stay balanced with half as many items (>= 5 per CTA)
     const char* e_tpi = std::getenv("SEDB200_CONV_TPI");
     const int force_tpi = e_tpi ? std::atoi(e_tpi) : 0;

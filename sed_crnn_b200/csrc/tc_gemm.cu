@@ -66,7 +66,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
     float* epi_stage = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform by construction
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
     }
@@ -79,7 +79,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const int kb_per = (p.kb_total + p.slices - 1) / p.slices;
 
     // item -> (slice, nt, mt)
@@ -108,8 +108,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
+        // warp-wide control flow, one elected lane issues (tc_umma.cuh: elect_one): descriptors in uniform registers
         constexpr uint32_t idesc = idesc_bf16(kTile, kTile, A_MN ? 1 : 0, B_MN ? 1 : 0);
+        const uint64_t da0 = operand_desc<A_MN>(smem_u32(smem), 0), db0 = operand_desc<B_MN>(smem_u32(smem), 0);
+        constexpr uint32_t stage_u = kStageBytes >> 4, tile_u = kTileBytes >> 4;
+        constexpr uint32_t ka_u = (A_MN ? 2048 : 32) >> 4, kb_u = (B_MN ? 2048 : 32) >> 4;
         int stage = 0; uint32_t phase = 0;
         int buf = 0; uint32_t bphase = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -122,20 +126,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(full + stage, phase);
                 tc_fence_after();
-                const uint32_t a_hi = smem_u32(smem + stage * kStageBytes);
-                const uint32_t a_lo = a_hi + kTileBytes, b_hi = a_hi + 2 * kTileBytes, b_lo = a_hi + 3 * kTileBytes;
+                if (elect_one()) {
+                    const uint64_t dah0 = da0 + (uint64_t)(stage * stage_u), dal0 = dah0 + tile_u;
+                    const uint64_t dbh0 = db0 + (uint64_t)(stage * stage_u + 2 * tile_u), dbl0 = dbh0 + tile_u;
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
-                    const uint64_t dah = operand_desc<A_MN>(a_hi, k), dal = operand_desc<A_MN>(a_lo, k);
-                    const uint64_t dbh = operand_desc<B_MN>(b_hi, k), dbl = operand_desc<B_MN>(b_lo, k);
-                    mma_bf16(d, dah, dbh, idesc, (kb != kb0 || k != 0));
-                    mma_bf16(d, dah, dbl, idesc, 1);
-                    mma_bf16(d, dal, dbh, idesc, 1);
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        mma_bf16(d, dah0 + k * ka_u, dbh0 + k * kb_u, idesc, (kb != kb0 || k != 0));
+                        mma_bf16(d, dah0 + k * ka_u, dbl0 + k * kb_u, idesc, 1);
+                        mma_bf16(d, dal0 + k * ka_u, dbh0 + k * kb_u, idesc, 1);
+                    }
+                    mma_commit(empty + stage);
+                    if (kb == kb1 - 1) mma_commit(tfull + buf);
                 }
-                mma_commit(empty + stage);
+                __syncwarp();
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
-            mma_commit(tfull + buf);
             if (++buf == 2) { buf = 0; bphase ^= 1; }
         }
     } else if (warp >= 4) {

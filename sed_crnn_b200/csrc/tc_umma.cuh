@@ -73,6 +73,23 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of a CONVERGED warp.  The MMA-issuing role runs warp-wide (uniform control flow, warp index obtained through
+// a shuffle so that the compiler knows it is warp-uniform) and issues under `if (elect_one())`: shared-memory
+// descriptors, TMEM addresses and loop state then live in uniform registers and every tcgen05.mma is ONE instruction.
+// Issued by `warp == 1 && lane == 0` instead, each MMA was wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall
+// loop (~80 cycles of dependent issue per MMA against the 64 the tensor pipe needs for a 128x128x16 one): the serial
+// issue stream, not L2 or the tensor pipe, bounded every tcgen05 kernel of this library (profiles/README.md).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, %1;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred)
+        : "r"(0xffffffffu));
+    return pred != 0;
+}
+
 // D[tmem] (+)= A[smem] * B[smem], bf16 operands, fp32 accumulate; issued by ONE thread
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                          uint32_t accumulate) {
