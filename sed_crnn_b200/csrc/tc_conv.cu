@@ -774,7 +774,7 @@ int conv_tc_planes_w(const void* a_hi, const void* a_lo, const void* wplanes, co
     // 0.153 -> 0.134 ms and its data gradient 0.082 -> 0.073 ms once the issue stream was warp-uniform.
     // SEDB200_CONV_HALO=0 turns it off (the parity tests run both settings).
     const char* e_halo = std::getenv("SEDB200_CONV_HALO");
-    bool halo = (W % 8 == 0) && !(e_halo && std::atoi(e_halo) == 0);
+    bool halo = (W % 4 == 0) && !(e_halo && std::atoi(e_halo) == 0);
     // two M tiles per work item when the CTAs stay balanced with half as many items (>= 5 per CTA)
     const char* e_tpi = std::getenv("SEDB200_CONV_TPI");
     const int force_tpi = e_tpi ? std::atoi(e_tpi) : 0;
