@@ -775,13 +775,15 @@ int conv_tc_planes_w(const void* a_hi, const void* a_lo, const void* wplanes, co
     // SEDB200_CONV_HALO=0 turns it off (the parity tests run both settings).
     const char* e_halo = std::getenv("SEDB200_CONV_HALO");
     bool halo = (W % 4 == 0) && !(e_halo && std::atoi(e_halo) == 0);
-    // two M tiles per work item when the CTAs stay balanced with half as many items (>= 5 per CTA)
+    // two M tiles per work item when the CTAs stay balanced with half as many items
     const char* e_tpi = std::getenv("SEDB200_CONV_TPI");
     const int force_tpi = e_tpi ? std::atoi(e_tpi) : 0;
     int tpi = 1;
     for (int pass = 0; pass < 2; ++pass) {
         const long pairs = halo ? (long)B * ((p.tiles_per_img + 1) / 2) * p.n_tiles_n : (long)((p.m_tiles + 1) / 2) * p.n_tiles_n;
-        tpi = pairs >= 5L * sm_count() ? 2 : 1;
+        // (>= 3 items per CTA: at 3.5 pairs per CTA -- conv 3's data gradient at C2 -- the pair form still wins, 0.055 ->
+        // 0.046 ms: half the weight bytes and half the per-tile hand-offs against one CTA round of imbalance)
+        tpi = pairs >= 3L * sm_count() ? 2 : 1;
         if (force_tpi == 1 || force_tpi == 2) tpi = force_tpi;
         if (terms == 2) tpi = 1;                                 // the tile's second accumulator slot holds the fp8 pass
         if (halo && terms == 3) tpi = 1;                         // two A slots of two planes of two tiles leave no room for B
