@@ -49,6 +49,17 @@ def test_c2_full_size_with_halo_boxes(pkg, monkeypatch):
     assert res["perr"] <= PU.PROB_TOL
 
 
+def test_ragged_tile_pairs_in_the_conv_blocks(pkg):
+    """seq_len 40 with 16 / 32 image rows per M tile: 3 / 2 tiles per image, so the last tile of an image is ragged and
+    the last PAIR of tiles of an image holds one tile only -- at a batch where the single-pass launches do run on tile
+    pairs (>= 3 pairs per CTA) and the halo boxes reach past the image on both sides."""
+    config, engine = pkg
+    rcfg, ref, cfg, eng = PU.make_pair(config, engine, "c2", {"seq_len": 40}, "bce", 1e-4, 1.0, seed=6)
+    x, y = R.synth_batch(rcfg, 256, seed=17)
+    res = PU.one_step_parity("c2_t40_b256_ragged_pairs", rcfg, ref, cfg, eng, x, y, "bce", 1e-4, 1.0)
+    assert res["perr"] <= PU.PROB_TOL
+
+
 def test_c5_long_context_t2048(pkg):
     """BASELINE configs[4] geometry at its real sequence length: T = 2048, 256 filters, 3 x BiGRU(128), 16 classes
     (batch 2: the recurrence length, not the batch, is what is new here -- 2,048 dependent fp32 steps per direction
