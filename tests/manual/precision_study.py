@@ -38,6 +38,10 @@ def r_e4m3(t, s):
     return (t * s).clamp(-448, 448).to(torch.float8_e4m3fn).float() / s
 
 
+def r_e5m2(t, s):
+    return (t * s).clamp(-57344, 57344).to(torch.float8_e5m2).float() / s
+
+
 def r_tf32(t):
     # round-to-nearest-even on the low 13 mantissa bits
     i = t.contiguous().view(torch.int32)
@@ -67,6 +71,10 @@ class Split:
             sw = pow2_scale(t, 224.0)
             self.hi8_w = r_e4m3(t, sw)
             self.lo8_w = r_e4m3(t - self.hi, sw * 2048.0)
+        elif scheme == "m2e":                                   # fp16 hi; e5m2 of x at its own scale and of the fp16 residual
+            self.hi = r_fp16(t, 1.0)                            # at the STATIC scale 2^8 (activations and weights alike):
+            self.hi8 = r_e5m2(t, 1.0)                           # both correction products carry 2^8, the same as the fp16
+            self.lo8 = r_e5m2(t - self.hi, 256.0)               # pass on weights pre-scaled by 2^8 -> ONE accumulator
         elif scheme == "x1":                                    # A (dY) bf16, B (weights / activations) fp16, one term
             self.hi = r_bf16(t)
             self.hi_b = r_fp16(t, pow2_scale(t, 2.0 ** 14))
@@ -79,7 +87,7 @@ class Split:
 
 
 COST = {"fp32": 0, "s3": 3, "b1": 1, "b2a": 2, "b2b": 2, "f1": 1, "f2a": 2, "f2b": 2, "f3": 3, "m2": 2, "m15a": 1.5,
-        "m15b": 1.5, "t1": 2, "bm2": 2, "x1": 1, "m2s": 2}
+        "m15b": 1.5, "t1": 2, "bm2": 2, "x1": 1, "m2s": 2, "m2e": 2}
 
 
 def contract(op, a, b, scheme):
@@ -98,7 +106,7 @@ def contract(op, a, b, scheme):
         return op(A.hi, B.hi) + op(A.lo, B.hi)
     if scheme in ("b2b", "f2b"):                                # truncated A, full B
         return op(A.hi, B.hi) + op(A.hi, B.lo)
-    if scheme in ("m2", "bm2"):                                 # 16-bit hi*hi + two fp8 correction terms
+    if scheme in ("m2", "bm2", "m2e"):                          # 16-bit hi*hi + two fp8 correction terms
         return op(A.hi, B.hi) + op(A.lo8, B.hi8) + op(A.hi8, B.lo8)
     if scheme == "m2s":                                         # a = activations (static scales), b = weights
         return op(A.hi, B.hi) + op(A.lo8_act, B.hi8_w) + op(A.hi8_act, B.lo8_w)
