@@ -74,21 +74,28 @@ sumsq_kernel(const float* __restrict__ g, long n, float prescale, float* __restr
     if (threadIdx.x == 0) part[blockIdx.x] = tot;
 }
 
-__global__ void gnorm_final_kernel(const float* __restrict__ part, int nblk, float* __restrict__ gnorm) {
-    pdl_wait();
-    const double s = warp_total(part, nblk);
-    if (threadIdx.x == 0) gnorm[0] = (float)sqrt(s);
-}
-
+// Every block folds the SAME per-block partials of the squared norm in the same order (one warp, fixed lane assignment
+// and shuffle tree: the fold p2p_reduce_clip_adam_kernel uses) -- the separate one-warp norm kernel between the two
+// passes is gone; block 0 publishes the norm.
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
             float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float max_norm,
-            float prescale, const float* __restrict__ gnorm, const float* __restrict__ bc_dev) {
+            float prescale, const float* __restrict__ part, int nblk, float* __restrict__ gnorm,
+            const float* __restrict__ bc_dev) {
     pdl_wait();
+    __shared__ float s_gn;
+    if (threadIdx.x < 32) {
+        const double s = warp_total(part, nblk);
+        if (threadIdx.x == 0) {
+            s_gn = (float)sqrt(s);
+            if (blockIdx.x == 0) gnorm[0] = s_gn;
+        }
+    }
+    __syncthreads();
     if (bc_dev) { bc1 = __ldg(bc_dev); bc2_sqrt = __ldg(bc_dev + 1); }     // CUDA-graph steps: bias corrections of the device-side step
     float coef = prescale;
     if (max_norm > 0.0f) {
-        const float c = max_norm / (gnorm[0] + 1e-6f);
+        const float c = max_norm / (s_gn + 1e-6f);
         coef *= fminf(c, 1.0f);
     }
     const float step_size = lr / bc1;
@@ -213,13 +220,11 @@ static int clip_adam_impl(float* params, const float* grads, float* m, float* v,
     SED_PROF("clip_adam", st);
     launch_k(sumsq_kernel, nb, 256, 0, st, grads, n, prescale, part);
     SED_POST_LAUNCH();
-    launch_k(gnorm_final_kernel, 1, 32, 0, st, part, nb, gnorm);
-    SED_POST_LAUNCH();
     const double bc1 = step_state ? 1.0 : 1.0 - std::pow((double)b1, (double)step);
     const double bc2 = step_state ? 1.0 : 1.0 - std::pow((double)b2, (double)step);
     const float* bc_dev = step_state ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(step_state) + 16) : nullptr;
     launch_k(adam_kernel, nb, 256, 0, st, params, grads, m, v, n, lr, b1, b2, eps, wd, (float)bc1, (float)std::sqrt(bc2),
-                                    max_norm, prescale, gnorm, bc_dev);
+                                    max_norm, prescale, part, nb, gnorm, bc_dev);
     SED_POST_LAUNCH();
     return SEDB200_OK;
 }

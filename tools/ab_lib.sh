@@ -1,6 +1,7 @@
 # same-box A/B of two builds of the library: sed_crnn_b200/libsedb200_prev.so (SEDB200_LIB_PATH) against the current one
-F="--steps 20 --warmup 5 --no-logmel --no-other-configs --no-cpu-baseline --no-library-baseline --no-dropin --no-fixed-global"
-for cfg in c2 c1 c5; do for lib in prev cur prev cur; do
+# usage: tools/ab_lib.sh "c2 c1 c5"
+F="--warmup 5 --no-logmel --no-other-configs --no-cpu-baseline --no-library-baseline --no-dropin --no-fixed-global"
+for cfg in ${1:-c2 c1 c5}; do for lib in prev cur prev cur; do
   if [ $lib = prev ]; then export SEDB200_LIB_PATH=$PWD/sed_crnn_b200/libsedb200_prev.so; else unset SEDB200_LIB_PATH; fi
   S=20; [ $cfg = c5 ] && S=5
   timeout 300 python bench.py --config $cfg $F --steps $S > gpurun_out/ablib.json 2> gpurun_out/ablib.err
