@@ -247,13 +247,16 @@ bn_relu_pool_fwd_t_kernel(const float* __restrict__ y, const float* __restrict__
     const float4 sh = *reinterpret_cast<const float4*>(stat + 3 * g.C + c);
     const float keep_scale = g.drop_p > 0.0f ? 1.0f / (1.0f - g.drop_p) : 1.0f;
     const unsigned Wo = (unsigned)g.Wo, H = (unsigned)g.H;
-    for (unsigned pix = blockIdx.x * rows + prow; pix < n_pix; pix += gridDim.x * rows) {
+    auto fetch = [&](unsigned pix, float4 (&v)[P]) {
         const unsigned t = pix / Wo, wo = pix - t * Wo;
         const unsigned b = t / H, h = t - b * H;
-        float4 v[P];
 #pragma unroll
         for (int j = 0; j < P; ++j)
             v[j] = __ldg(reinterpret_cast<const float4*>(y + ((((long)b * g.H + h) * g.W) + (long)wo * P + j) * g.C + c));
+    };
+    auto finish = [&](unsigned pix, const float4 (&v)[P]) {
+        const unsigned t = pix / Wo, wo = pix - t * Wo;
+        const unsigned b = t / H, h = t - b * H;
         float4 m = make_float4(0.0f, 0.0f, 0.0f, 0.0f);           // relu floor
 #pragma unroll
         for (int j = 0; j < P; ++j) {
@@ -279,6 +282,21 @@ bn_relu_pool_fwd_t_kernel(const float* __restrict__ y, const float* __restrict__
                 dst[0] = m.x; dst[g.oC] = m.y; dst[2 * g.oC] = m.z; dst[3 * g.oC] = m.w;
             }
         }
+    };
+    // two windows per trip: all 2 P loads are in flight before the first use
+    const unsigned stride = gridDim.x * rows;
+    unsigned pix = blockIdx.x * rows + prow;
+    for (; pix + stride < n_pix; pix += 2 * stride) {
+        float4 v0[P], v1[P];
+        fetch(pix, v0);
+        fetch(pix + stride, v1);
+        finish(pix, v0);
+        finish(pix + stride, v1);
+    }
+    if (pix < n_pix) {
+        float4 v0[P];
+        fetch(pix, v0);
+        finish(pix, v0);
     }
 }
 
