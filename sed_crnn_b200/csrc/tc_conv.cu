@@ -525,6 +525,10 @@ constexpr uint32_t kWgTmemCols = 512;
 
 struct WgradTcParams {
     int B, H, W, Hk, hblocks_per_img, total_kblocks, n_mt, n_nt, slices, terms, n_stages;
+    // halo mode (single pass, W % 4 == 0): a CTA owns a tap COLUMN s; ONE In box of Hk + 2 image rows per channel half
+    // serves the three tap rows as three descriptor start addresses (r * W * 128 B) -- 4 boxes and 8 + 2 * xh_bytes
+    // bytes per K-block instead of 8 boxes and 32 KB; tmX_lo then carries that box shape
+    int halo, xh_bytes, stage_bytes;
     uint32_t idesc;
     float* part;             // [slices][9][Cout][Cin]
     int Cout, Cin;
@@ -537,13 +541,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
     pdl_wait();
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.n_stages * (p.terms == 1 ? kWgStageBytes / 2 : kWgStageBytes));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.n_stages * p.stage_bytes);
     uint64_t* full = bars;
     uint64_t* empty = bars + kMaxStages;
     uint64_t* tfull = bars + 2 * kMaxStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
     const int n_stages = p.n_stages;
-    const int stage_bytes = p.terms == 1 ? kWgStageBytes / 2 : kWgStageBytes;
+    const int stage_bytes = p.stage_bytes;
     // 1-term stage: {dY hi: 2 halves} + 3 x {In hi: 2 halves}; 3-term stage: each of those followed by its lo boxes
     const int a_bytes = p.terms == 1 ? kWgABytes / 2 : kWgABytes, b_bytes = p.terms == 1 ? kWgBBytes / 2 : kWgBBytes;
 
@@ -565,12 +569,63 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
     // work item of this CTA
     int w = blockIdx.x;
     const int slice = w % p.slices; w /= p.slices;
-    const int r = w % 3; w /= 3;
+    const int r = w % 3; w /= 3;                                   // the CTA's tap row (halo mode: its tap COLUMN)
     const int nt = w % p.n_nt, mt = w / p.n_nt;
     const int kb_per = (p.total_kblocks + p.slices - 1) / p.slices;
     const int kb0 = slice * kb_per, kb1 = min(p.total_kblocks, kb0 + kb_per);
 
-    if (warp == 0) {
+    if (warp == 0 && p.halo) {
+        // halo mode: lanes 0-1 the dY halves, lanes 2-3 the In halves (Hk + 2 rows, shifted by the CTA's tap column)
+        int stage = 0; uint32_t phase = 0;
+        int b = kb0 / p.hblocks_per_img, hb = kb0 - b * p.hblocks_per_img;
+        const bool mine = lane < 4, is_y = lane < 2;
+        const int half = lane & 1;
+        const int c_first = (is_y ? mt : nt) * 128 + half * 64;
+        const int dst_off = is_y ? half * kWgBox : 2 * kWgBox + half * p.xh_bytes;
+        const CUtensorMap* tm = is_y ? &tmY_hi : &tmX_lo;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            const int h0 = hb * p.Hk;
+            if (lane == 0) {
+                mbar_wait(empty + stage, phase ^ 1);
+                mbar_expect_tx(full + stage, stage_bytes);
+            }
+            __syncwarp();
+            if (mine) {
+                unsigned char* st = smem + stage * stage_bytes;
+                if (is_y) tma_load_4d(st + dst_off, tm, full + stage, c_first, 0, h0, b);
+                else tma_load_4d(st + dst_off, tm, full + stage, c_first, r - 1, h0 - 1, b);
+            }
+            if (++hb == p.hblocks_per_img) { hb = 0; ++b; }
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1 && p.halo) {
+        // halo mode: tap row rr = descriptor start rr * W rows into the In box; the In halves are xh_bytes apart (LBO)
+        const uint32_t idesc = p.idesc;
+        const uint64_t dbase_a = smem_desc_sw128(smem_u32(smem), kWgBox, 1024);
+        const uint64_t dbase_b = smem_desc_sw128(smem_u32(smem), (uint32_t)p.xh_bytes, 1024);
+        const uint32_t stage_u = (uint32_t)stage_bytes >> 4, a_u = (2 * kWgBox) >> 4, row_u = (uint32_t)(p.W * 128) >> 4;
+        constexpr uint32_t k_u = 2048 >> 4;
+        int stage = 0; uint32_t phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(full + stage, phase);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t da = dbase_a + (uint64_t)(stage * stage_u);
+                const uint64_t db = dbase_b + (uint64_t)(stage * stage_u + a_u);
+#pragma unroll
+                for (int rr = 0; rr < 3; ++rr) {
+                    const uint32_t d = tmem_base + rr * 128;
+#pragma unroll
+                    for (int k = 0; k < kWgKp / 16; ++k)
+                        mma_bf16(d, da + k * k_u, db + (uint64_t)(rr * row_u) + k * k_u, idesc, (kb != kb0 || k != 0));
+                }
+                mma_commit(empty + stage);
+                if (kb == kb1 - 1) mma_commit(tfull);
+            }
+            __syncwarp();
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 0) {
         // The producer is a serial instruction stream too: per K-block it has 8 (single-pass) or 16 boxes to request,
         // ~40 cycles of issue each, against 384 cycles of MMA work -- so lane i requests box i (all lanes of the warp in
         // one instruction), lane 0 alone waits for the slot and posts the byte count, and (image, row) advance without
@@ -639,8 +694,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
             mbar_wait(tfull, 0);
             tc_fence_after();
         }
-        for (int s = 0; s < 3; ++s) {
-            float* dst = p.part + (((long)slice * 9 + (r * 3 + s)) * p.Cout + co) * p.Cin + nt * 128;
+        for (int s = 0; s < 3; ++s) {                              // accumulator s: tap (r, s), or (s, r) in halo mode
+            const int tap = p.halo ? s * 3 + r : r * 3 + s;
+            float* dst = p.part + (((long)slice * 9 + tap) * p.Cout + co) * p.Cin + nt * 128;
 #pragma unroll 1
             for (int cc = 0; cc < 4; ++cc) {
                 float v[32];
@@ -913,11 +969,26 @@ int wgrad_tc_planes(const void* y_hi, const void* y_lo, const void* x_hi, const 
     p.slices = std::min(wgrad_slices(Cin, Cout), p.total_kblocks);
     p.part = part; p.Cout = Cout; p.Cin = Cin; p.terms = terms;
     p.idesc = fmt == kPlaneF16 ? idesc_f16(128, 128, 1, 1) : idesc_bf16(128, 128, 1, 1);
+    const char* e_halo = std::getenv("SEDB200_WGRAD_HALO");
+    p.halo = (terms == 1 && W % 4 == 0 && !(e_halo && std::atoi(e_halo) == 0)) ? 1 : 0;
+    p.xh_bytes = (kWgKp + 2 * W) * 128;                             // one channel half of the In box: Hk + 2 image rows
+    p.stage_bytes = p.halo ? 2 * kWgBox + 2 * p.xh_bytes : (terms == 1 ? kWgStageBytes / 2 : kWgStageBytes);
+    if (p.halo) {                                                   // the In box of Hk + 2 rows (tmX_lo is free in this mode)
+        const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+        const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+        const uint32_t hbox[4] = {64, (uint32_t)W, (uint32_t)(Hk + 2), 1};
+        const int rc = encode_tmap_bf16(&tmX_lo, x_hi, 4, dims, strides, hbox);
+        if (rc) return rc;
+    }
     // pipeline depth: 6 half-size stages (single pass) / 3 (3-term) fill the SM; a caller that wants the kernel to
-    // share its SMs with another one (crnn_backward_impl: beside the BatchNorm / block-0 backward) asks for fewer
-    p.n_stages = terms == 1 ? kMaxStages : kStages;
-    if (max_stages >= 2 && max_stages < p.n_stages) p.n_stages = max_stages;
-    const int smem_bytes = p.n_stages * (terms == 1 ? kWgStageBytes / 2 : kWgStageBytes) + 1024 + 256;
+    // share its SMs with another one (crnn_backward_impl: beside the BatchNorm / block-0 backward) passes max_stages =
+    // the shared memory it may take in units of the 32 KB single-pass stage (the smaller halo stages: more of them)
+    const int full_stages = terms == 1 ? kMaxStages : kStages;
+    const int legacy_stage = terms == 1 ? kWgStageBytes / 2 : kWgStageBytes;
+    int budget = full_stages * legacy_stage;
+    if (max_stages >= 2 && max_stages < full_stages) budget = max_stages * legacy_stage;
+    p.n_stages = std::max(2, std::min(kMaxStages, budget / p.stage_bytes));
+    const int smem_bytes = p.n_stages * p.stage_bytes + 1024 + 256;
     { const int rc = ensure_dyn_smem((const void*)wgrad_tc_kernel, kWgSmemBytes); if (rc) return rc; }
     const int grid = p.n_mt * p.n_nt * 3 * p.slices;
     launch_k(wgrad_tc_kernel, grid, kThreads, smem_bytes, st, tmY_hi, tmY_lo, tmX_hi, tmX_lo, p);
