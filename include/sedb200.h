@@ -368,6 +368,18 @@ size_t sedb200_conv3x3_wgrad_tc_scratch_bytes(int B, int H, int W, int Cin, int 
 int    sedb200_conv3x3_wgrad_tc(const float* dy_dev, const float* in_dev, float* dw_dev, int B, int H, int W,
                                 int Cin, int Cout, void* scratch_dev, size_t scratch_bytes, void* stream);
 
+/* Test hook for the PLANE-NATIVE launches the CRNN flow uses (fp16 operand planes; forward = fp16 pass + e4m3
+ * correction pass, gradients = one fp16 pass, halo boxes, tile pairs): the planes are produced from the fp32 tensors
+ * given here with the helpers of the pool kernels, then exactly the launches of sedb200_crnn_forward / _backward run.
+ *   mode 0: out [B][H][W][Cout] = conv(in [B][H][W][Cin], weight)                       (in2 unused)
+ *   mode 1: out [B][H][W][Cin]  = conv_transposed(in = dY [B][H][W][Cout], weight)      (in2 unused)
+ *   mode 2: out [Cout][Cin][3][3] = wgrad(in = dY [B][H][W][Cout], in2 = x [B][H][W][Cin])   (weight unused)
+ * Reference call sites: nn.Conv2d(.., 3, padding=1) and its autograd backward, crnn_lightning.py:47 / sed.py:88. */
+size_t sedb200_conv3x3_planes_test_scratch_bytes(int B, int H, int W, int Cin, int Cout);
+int    sedb200_conv3x3_planes_test(const float* in_dev, const float* in2_dev, const float* weight_dev, float* out_dev,
+                                   int B, int H, int W, int Cin, int Cout, int mode, void* scratch_dev,
+                                   size_t scratch_bytes, void* stream);
+
 /* Small-channel direct 3x3 convolutions (<= 64 channels: the reference's shipped CONV_DEPTH = 16,
  * train_constants.py), exposed for unit tests.  `in` is read through strides (element b*sB + h*sH + w*sW + k*sC), so
  * NCHW user input and channels-last activations both work; outputs are channels-last.

@@ -90,6 +90,8 @@ SIGNATURES = {
     "sedb200_conv3x3_tc_scratch_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "sedb200_conv3x3_wgrad_tc_scratch_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "sedb200_conv3x3_wgrad_tc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _sz, _p]),
+    "sedb200_conv3x3_planes_test_scratch_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "sedb200_conv3x3_planes_test": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _sz, _p]),
     "sedb200_conv3x3_small_supported": (_i, [_i, _i, _i, _i]),
     "sedb200_conv3x3_small": (_i, [_p, _l, _l, _l, _l, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p]),
     "sedb200_conv3x3_small_wgrad_scratch_bytes": (_sz, [_i, _i, _i, _i]),

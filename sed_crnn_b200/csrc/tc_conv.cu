@@ -25,6 +25,7 @@
 #include <cuda_fp8.h>
 #include "tc_umma.cuh"
 #include "tc_conv.cuh"
+#include "crnn_block.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -1050,6 +1051,92 @@ int sedb200_conv3x3_wgrad_tc(const float* dy_dev, const float* in_dev, float* dw
     int rc = require_sm100();
     if (rc) return rc;
     return wgrad_tc(dy_dev, in_dev, dw_dev, B, H, W, Cin, Cout, scratch_dev, scratch_bytes, as_stream(stream));
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------- plane-native test hook
+// The CRNN flow never calls the fp32 entry points above: its conv blocks run conv_tc_planes_w / wgrad_tc_planes on fp16
+// planes (forward: fp16 pass + e4m3 correction pass; gradients: one fp16 pass; halo boxes; tile pairs).  This hook runs
+// exactly those launches on fp32 tensors -- the planes are produced here with the SAME helpers the pool kernels use
+// (crnn_block.cuh) -- so that tests can hold them against a float64 convolution tap by tap.
+namespace sedb200 {
+namespace {
+__global__ void __launch_bounds__(256)
+test_planes_kernel(const float* __restrict__ x, long n_pix, int C4, __nv_bfloat16* __restrict__ hi,
+                   __nv_bfloat16* __restrict__ c8, int with_c8) {
+    pdl_wait();
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pix * C4; i += (long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+        const long pix = i / C4;
+        const int c4 = (int)(i - pix * C4);
+        if (with_c8) store_planes4(hi, c8, pix, c4, C4, v);
+        else store_dy4(hi, i, v, 1.0f);
+    }
+}
+__global__ void test_one_kernel(float* p) { pdl_wait(); p[0] = 1.0f; p[1] = 1.0f; }
+}  // namespace
+}  // namespace sedb200
+
+extern "C" {
+
+size_t sedb200_conv3x3_planes_test_scratch_bytes(int B, int H, int W, int Cin, int Cout) {
+    const size_t px = (size_t)B * H * W, cmax = (size_t)std::max(Cin, Cout);
+    const size_t plane = (px * cmax * 2 + 1023) & ~(size_t)1023;
+    return 4 * plane + conv_tc_weight_scratch_bytes(Cin, Cout) + wgrad_tc_part_bytes(Cin, Cout) + 4096;
+}
+
+// mode 0: out [B][H][W][Cout] = conv(in [B][H][W][Cin], w)                        forward, fp16 + e4m3 passes
+// mode 1: out [B][H][W][Cin]  = conv_transposed(in = dY [B][H][W][Cout], w)       data gradient, one fp16 pass
+// mode 2: out [Cout][Cin][3][3] = wgrad(in = dY [B][H][W][Cout], in2 = x [B][H][W][Cin])   weight gradient, one pass
+int sedb200_conv3x3_planes_test(const float* in_dev, const float* in2_dev, const float* weight_dev, float* out_dev, int B,
+                                int H, int W, int Cin, int Cout, int mode, void* scratch_dev, size_t scratch_bytes,
+                                void* stream) {
+    SED_REQUIRE(in_dev && out_dev && scratch_dev && (mode == 2 ? in2_dev != nullptr : weight_dev != nullptr), SEDB200_EINVAL,
+                "conv3x3_planes_test: null buffer");
+    SED_REQUIRE(mode >= 0 && mode <= 2 && B >= 1, SEDB200_EINVAL, "conv3x3_planes_test: mode %d batch %d", mode, B);
+    SED_REQUIRE(scratch_bytes >= sedb200_conv3x3_planes_test_scratch_bytes(B, H, W, Cin, Cout), SEDB200_EWORKSPACE,
+                "conv3x3_planes_test: scratch too small");
+    int rc = require_sm100();
+    if (rc) return rc;
+    cudaStream_t st = as_stream(stream);
+    const long px = (long)B * H * W;
+    const size_t cmax = (size_t)std::max(Cin, Cout), plane = ((size_t)px * cmax * 2 + 1023) & ~(size_t)1023;
+    char* s = reinterpret_cast<char*>(scratch_dev);
+    __nv_bfloat16 *p0 = reinterpret_cast<__nv_bfloat16*>(s), *p1 = reinterpret_cast<__nv_bfloat16*>(s + plane);
+    __nv_bfloat16 *p2 = reinterpret_cast<__nv_bfloat16*>(s + 2 * plane), *p3 = reinterpret_cast<__nv_bfloat16*>(s + 3 * plane);
+    char* wpl = s + 4 * plane;
+    float* wpart = reinterpret_cast<float*>(wpl + conv_tc_weight_scratch_bytes(Cin, Cout));
+    float* one = reinterpret_cast<float*>(reinterpret_cast<char*>(wpart) + wgrad_tc_part_bytes(Cin, Cout));
+    launch_k(test_one_kernel, 1, 1, 0, st, one);
+    SED_POST_LAUNCH();
+    auto planes = [&](const float* x, int C, __nv_bfloat16* hi, __nv_bfloat16* c8, int with_c8) {
+        const long n = px * (C / 4);
+        launch_k(test_planes_kernel, (int)std::min<long>((n + 255) / 256, 148L * 8), 256, 0, st, x, px, C / 4, hi, c8, with_c8);
+    };
+    if (mode == 0) {
+        SED_REQUIRE(conv_tc_supported(H, W, Cin, Cout), SEDB200_ESHAPE, "conv3x3_planes_test: forward shape unsupported");
+        planes(in_dev, Cin, p0, p1, 1);
+        SED_POST_LAUNCH();
+        float* sc2 = one + 2;
+        rc = conv_tc_weight_planes(weight_dev, Cin, Cout, 0, wpl, st, kPlaneF16, sc2);
+        if (rc) return rc;
+        return conv_tc_planes_w(p0, p1, wpl, nullptr, out_dev, nullptr, B, H, W, Cin, Cout, 0, st, 2, kPlaneF16, nullptr, sc2 + 1);
+    }
+    if (mode == 1) {
+        SED_REQUIRE(conv_tc_supported(H, W, Cout, Cin), SEDB200_ESHAPE, "conv3x3_planes_test: data-gradient shape unsupported");
+        planes(in_dev, Cout, p0, nullptr, 0);
+        SED_POST_LAUNCH();
+        rc = conv_tc_weight_planes(weight_dev, Cin, Cout, 1, wpl, st, kPlaneF16);
+        if (rc) return rc;
+        return conv_tc_planes_w(p0, nullptr, wpl, nullptr, out_dev, nullptr, B, H, W, Cin, Cout, 1, st, 1, kPlaneF16, one);
+    }
+    SED_REQUIRE(wgrad_tc_supported(H, W, Cin, Cout), SEDB200_ESHAPE, "conv3x3_planes_test: weight-gradient shape unsupported");
+    planes(in_dev, Cout, p0, nullptr, 0);
+    SED_POST_LAUNCH();
+    planes(in2_dev, Cin, p2, p3, 1);
+    SED_POST_LAUNCH();
+    return wgrad_tc_planes(p0, nullptr, p2, nullptr, out_dev, B, H, W, Cin, Cout, wpart, st, 1, kPlaneF16, one);
 }
 
 }  // extern "C"

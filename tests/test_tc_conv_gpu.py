@@ -90,3 +90,87 @@ def test_wgrad_matches_autograd(L, B, H, W, Cin, Cout):
     torch.cuda.synchronize()
     err = (dw.cpu().double() - want).abs().max().item() / want.abs().max().item()
     assert err < 2e-5, err
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The PLANE-NATIVE launches the CRNN flow actually runs (fp16 planes: forward = fp16 pass + e4m3 correction pass on one
+# tile, gradients = one fp16 pass on tile pairs, halo boxes in all three kernels), through the test hook
+# sedb200_conv3x3_planes_test.  Two kinds of input: small dyadic values, for which every product and every fp32 partial
+# sum is exact -- so the result must EQUAL the float64 convolution and a wrong tap / row / channel shows up as an O(1)
+# error, not as something a gradient gate could absorb -- and random values with the tolerance of the operand format.
+def run_planes(L, mode, a, b, w, B, H, W, Cin, Cout):
+    from sed_crnn_b200 import _lib
+    shape = {0: (B, H, W, Cout), 1: (B, H, W, Cin), 2: (Cout, Cin, 3, 3)}[mode]
+    out = torch.empty(*shape, device="cuda")
+    nbytes = L.sedb200_conv3x3_planes_test_scratch_bytes(B, H, W, Cin, Cout)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    _lib.check(L.sedb200_conv3x3_planes_test(a.data_ptr(), b.data_ptr() if b is not None else None,
+                                             w.data_ptr() if w is not None else None, out.data_ptr(), B, H, W, Cin, Cout,
+                                             mode, scratch.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    return out.cpu().double()
+
+
+def dyadic(shape, g, levels, denom):
+    return torch.randint(-levels, levels + 1, shape, generator=g).float() / denom
+
+
+@pytest.fixture(params=[("1", "0"), ("1", "2"), ("0", "0")], ids=["halo", "halo-pairs", "boxes-per-tap"])
+def staging(request, monkeypatch):
+    halo, tpi = request.param
+    monkeypatch.setenv("SEDB200_CONV_HALO", halo)
+    monkeypatch.setenv("SEDB200_WGRAD_HALO", halo)
+    monkeypatch.setenv("SEDB200_CONV_TPI", tpi)
+    return request.param
+
+
+PLANE_SHAPES = [(2, 40, 16, 128, 128), (3, 24, 8, 128, 128), (2, 40, 4, 128, 128), (1, 40, 32, 128, 128),
+                (2, 9, 64, 128, 128), (3, 33, 8, 128, 256), (2, 16, 4, 256, 128)]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", PLANE_SHAPES)
+@pytest.mark.parametrize("exact", [True, False], ids=["dyadic", "random"])
+def test_plane_native_forward(L, staging, exact, B, H, W, Cin, Cout):
+    g = torch.Generator().manual_seed(31 * H + W + B)
+    if exact:
+        x, w = dyadic((B, Cin, H, W), g, 3, 4.0), dyadic((Cout, Cin, 3, 3), g, 4, 16.0)
+    else:
+        x, w = torch.randn(B, Cin, H, W, generator=g), torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)
+    want = F.conv2d(x.double(), w.double(), None, padding=1).permute(0, 2, 3, 1)
+    got = run_planes(L, 0, x.permute(0, 2, 3, 1).contiguous().cuda(), None, w.cuda(), B, H, W, Cin, Cout)
+    err = (got - want).abs().max().item() / want.abs().max().item()
+    assert err <= (1e-6 if exact else 1e-4), err          # fp16 x fp16 + e4m3 corrections: ~2^-15 per product
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", PLANE_SHAPES)
+@pytest.mark.parametrize("exact", [True, False], ids=["dyadic", "random"])
+def test_plane_native_data_gradient(L, staging, exact, B, H, W, Cin, Cout):
+    g = torch.Generator().manual_seed(17 * H + W + B)
+    if exact:
+        dy, w = dyadic((B, Cout, H, W), g, 3, 4.0), dyadic((Cout, Cin, 3, 3), g, 4, 16.0)
+    else:
+        dy, w = torch.randn(B, Cout, H, W, generator=g), torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)
+    x = torch.zeros(B, Cin, H, W, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x, w.double(), None, padding=1).backward(dy.double())
+    want = x.grad.permute(0, 2, 3, 1)
+    got = run_planes(L, 1, dy.permute(0, 2, 3, 1).contiguous().cuda(), None, w.cuda(), B, H, W, Cin, Cout)
+    err = (got - want).abs().max().item() / want.abs().max().item()
+    assert err <= (1e-6 if exact else 2e-3), err          # ONE fp16 pass: 2^-11 per operand
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 32, 8, 128, 128), (3, 10, 16, 128, 128), (2, 16, 4, 256, 128),
+                                            (1, 5, 32, 128, 256), (7, 64, 8, 128, 128), (2, 33, 4, 128, 128)])
+@pytest.mark.parametrize("exact", [True, False], ids=["dyadic", "random"])
+def test_plane_native_weight_gradient(L, staging, exact, B, H, W, Cin, Cout):
+    g = torch.Generator().manual_seed(13 * H + W + B)
+    if exact:
+        x, dy = dyadic((B, Cin, H, W), g, 3, 4.0), dyadic((B, Cout, H, W), g, 3, 4.0)
+    else:
+        x, dy = torch.randn(B, Cin, H, W, generator=g), torch.randn(B, Cout, H, W, generator=g)
+    w = torch.zeros(Cout, Cin, 3, 3, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.double(), w, None, padding=1).backward(dy.double())
+    want = w.grad
+    got = run_planes(L, 2, dy.permute(0, 2, 3, 1).contiguous().cuda(), x.permute(0, 2, 3, 1).contiguous().cuda(), None,
+                     B, H, W, Cin, Cout)
+    err = (got - want).abs().max().item() / want.abs().max().item()
+    assert err <= (1e-6 if exact else 2e-3), err
