@@ -246,17 +246,16 @@ bn_relu_pool_fwd_t_kernel(const float* __restrict__ y, const float* __restrict__
     const float4 sc = *reinterpret_cast<const float4*>(stat + 2 * g.C + c);
     const float4 sh = *reinterpret_cast<const float4*>(stat + 3 * g.C + c);
     const float keep_scale = g.drop_p > 0.0f ? 1.0f / (1.0f - g.drop_p) : 1.0f;
-    const unsigned Wo = (unsigned)g.Wo, H = (unsigned)g.H;
     auto fetch = [&](unsigned pix, float4 (&v)[P]) {
-        const unsigned t = pix / Wo, wo = pix - t * Wo;
-        const unsigned b = t / H, h = t - b * H;
+        unsigned b, h, wo;
+        pix_bhw(pix, g, b, h, wo);
 #pragma unroll
         for (int j = 0; j < P; ++j)
             v[j] = __ldg(reinterpret_cast<const float4*>(y + ((((long)b * g.H + h) * g.W) + (long)wo * P + j) * g.C + c));
     };
     auto finish = [&](unsigned pix, const float4 (&v)[P]) {
-        const unsigned t = pix / Wo, wo = pix - t * Wo;
-        const unsigned b = t / H, h = t - b * H;
+        unsigned b, h, wo;
+        pix_bhw(pix, g, b, h, wo);
         float4 m = make_float4(0.0f, 0.0f, 0.0f, 0.0f);           // relu floor
 #pragma unroll
         for (int j = 0; j < P; ++j) {
@@ -385,8 +384,8 @@ bn_pool_bwd_sums_t_kernel(const float* __restrict__ y, const float* __restrict__
     float a[4] = {0, 0, 0, 0}, bsum[4] = {0, 0, 0, 0};
     const unsigned Wo = (unsigned)g.Wo, H = (unsigned)g.H, npx = (unsigned)n_pix;     // n_pix < 2^31 (launcher)
     for (unsigned pix = blockIdx.x * rows + prow; pix < npx; pix += gridDim.x * rows) {
-        const unsigned t = pix / Wo, wo = pix - t * Wo;
-        const unsigned b = t / H, h = t - b * H;
+        unsigned b, h, wo;
+        pix_bhw(pix, g, b, h, wo);
         float4 v[P];
         float gq[4], dz[4], yarg[4];
         int arg[4];
@@ -439,13 +438,12 @@ bn_bwd_sums_act_kernel(const float* __restrict__ act, const __nv_bfloat16* __res
     const float mis[4] = {mu.x * is.x, mu.y * is.y, mu.z * is.z, mu.w * is.w};
     const float keep_scale = g.drop_p > 0.0f ? 1.0f / (1.0f - g.drop_p) : 1.0f;
     const float inv_keep = g.drop_p > 0.0f ? 1.0f - g.drop_p : 1.0f;
-    const unsigned Wo = (unsigned)g.Wo, H = (unsigned)g.H;
     float a[4] = {0, 0, 0, 0}, bsum[4] = {0, 0, 0, 0};
     float amax = 0.0f;                                                 // max |dz| this thread saw (-> dy_scale_kernel)
     // two pixels per trip: all six loads are issued before the first use
     auto fetch = [&](unsigned pix, float (&av)[4], float (&gq)[4]) {
-        const unsigned t = pix / Wo, wo = pix - t * Wo;
-        const unsigned b = t / H, h = t - b * H;
+        unsigned b, h, wo;
+        pix_bhw(pix, g, b, h, wo);
         const long off = (long)b * g.oB + (long)h * g.oH + (long)wo * g.oW + (long)c * g.oC;
         if (act) {
             load_dA(act + off, g.oC, av);
@@ -664,10 +662,9 @@ bn_pool_bwd_dy_t_kernel(const float* __restrict__ y, const float* __restrict__ s
     const float Bc[4] = {sc.x * is.x * k2.x, sc.y * is.y * k2.y, sc.z * is.z * k2.z, sc.w * is.w * k2.w};
     const float Ac[4] = {sc.x * k1.x - mu.x * Bc[0], sc.y * k1.y - mu.y * Bc[1], sc.z * k1.z - mu.z * Bc[2],
                          sc.w * k1.w - mu.w * Bc[3]};
-    const unsigned Wo = (unsigned)g.Wo, H = (unsigned)g.H;
     for (unsigned pix = blockIdx.x * rows + prow; pix < n_pix; pix += gridDim.x * rows) {
-        const unsigned t = pix / Wo, wo = pix - t * Wo;
-        const unsigned b = t / H, h = t - b * H;
+        unsigned b, h, wo;
+        pix_bhw(pix, g, b, h, wo);
         const long row = ((long)b * g.H + h) * g.W + (long)wo * P;
         float4 v[P];
         float gq[4], dz[4], yarg[4];
@@ -1119,6 +1116,9 @@ PoolGeom pool_geom(const Plan& P, const sedb200_crnn_desc* d, int i, int trainin
     const bool drop = training && d->dropout > 0.0f && (d->dropout_each_block || last);
     g.drop_p = drop ? d->dropout : 0.0f;
     g.seed = block_seed(seed, i);
+    auto lg = [](int v) { int l = 0; while ((1 << l) < v) ++l; return (1 << l) == v ? l : -1; };
+    g.lgWo = lg(g.Wo); g.lgH = lg(g.H);
+    if (g.lgWo < 0 || g.lgH < 0) g.lgWo = g.lgH = -1;
     return g;
 }
 

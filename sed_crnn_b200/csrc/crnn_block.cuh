@@ -118,7 +118,23 @@ struct PoolGeom {
     // captured step draws fresh masks at every replay; null = use `seed`
     const unsigned long long* seed_ptr;
     int block;
+    int lgWo, lgH;               // log2 of Wo and H when both are powers of two (every BASELINE config), else -1
 };
+// window index -> (image, row, window column).  The two divisions by run-time values were a fifth of the instructions
+// of the HBM-bound pool kernels (ncu: issue active 64-68 %); shifts when the geometry allows it.
+__device__ __forceinline__ void pix_bhw(unsigned pix, const PoolGeom& g, unsigned& b, unsigned& h, unsigned& wo) {
+    if (g.lgWo >= 0) {
+        wo = pix & ((unsigned)g.Wo - 1u);
+        const unsigned t = pix >> g.lgWo;
+        h = t & ((unsigned)g.H - 1u);
+        b = t >> g.lgH;
+    } else {
+        const unsigned t = pix / (unsigned)g.Wo;
+        wo = pix - t * (unsigned)g.Wo;
+        b = t / (unsigned)g.H;
+        h = t - b * (unsigned)g.H;
+    }
+}
 __device__ __forceinline__ unsigned long long pool_seed(const PoolGeom& g) {
     return g.seed_ptr ? block_seed(__ldg(g.seed_ptr), g.block) : g.seed;
 }
