@@ -118,7 +118,7 @@ inline HaloMode conv_halo_mode(int terms, int tpi, int W) {
 }
 
 struct ConvTcParams {
-    int B, H, W, Ht, tiles_per_img, n_tiles_n, m_tiles, total_items, kchunks, n_total;
+    int B, H, W, lgW, Ht, tiles_per_img, n_tiles_n, m_tiles, total_items, kchunks, n_total;   // W = 2^lgW (a divisor of 128)
     int terms, tpi, planes, stage_bytes, n_stages, n_epi_warps;
     // halo mode (conv_halo_mode): one A box per (tap column, channel chunk) carries the rows of all three tap rows
     int halo, groups_per_img, n_a, a_plane_bytes, a_slot_bytes, ring_bytes;
@@ -408,7 +408,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 for (int r = 0; r < 32; r += 4) {
                     float4 o = *reinterpret_cast<const float4*>(stg + (r + sub_r) * kEpiPitch + sub_c);
                     o.x = fmaf(o.x, osc, bb.x); o.y = fmaf(o.y, osc, bb.y); o.z = fmaf(o.z, osc, bb.z); o.w = fmaf(o.w, osc, bb.w);
-                    if ((h0 + (q * 32 + r + sub_r) / p.W) < p.H)
+                    if ((h0 + ((q * 32 + r + sub_r) >> p.lgW)) < p.H)
                         *reinterpret_cast<float4*>(dst0 + (long)(r + sub_r) * p.out_ld + cc * 32 + sub_c) = o;
                 }
                 if (p.stats) {
@@ -418,7 +418,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
                     for (int r = 0; r < 32; ++r) {
                         const float x = fmaf(stg[r * kEpiPitch + lane], osc, bl);
-                        if ((h0 + (q * 32 + r) / p.W) < p.H) { s1 += x; s2 = fmaf(x, x, s2); }
+                        if ((h0 + ((q * 32 + r) >> p.lgW)) < p.H) { s1 += x; s2 = fmaf(x, x, s2); }
                     }
                     stat_s[(q * 2 + 0) * 128 + cc * 32 + lane] = s1;
                     stat_s[(q * 2 + 1) * 128 + cc * 32 + lane] = s2;
@@ -820,6 +820,8 @@ int conv_tc_planes_w(const void* a_hi, const void* a_lo, const void* wplanes, co
     const int Ht = kTileM / W;
     ConvTcParams p;
     p.B = B; p.H = H; p.W = W; p.Ht = Ht;
+    p.lgW = 0;
+    while ((1 << p.lgW) < W) ++p.lgW;
     p.tiles_per_img = (H + Ht - 1) / Ht;
     p.n_tiles_n = Nc / kTileN;
     p.m_tiles = B * p.tiles_per_img;
