@@ -154,6 +154,253 @@ conv0_gram_kernel(const float* __restrict__ x, int H, int W, unsigned wmagic, in
         }
 }
 
+// ----------------------------------------------------------------------------- patch moments from autocorrelations
+// G[k][k'] = sum over the B*H*W output pixels of patch_k * patch_k', k = (c, r, s): 171 products per pixel when done
+// entry by entry (conv0_gram_kernel above).  But patch_k(h, w) = X[c][h + r - 1][w + s - 1], so over an output domain
+// EXTENDED by one ring of pixels (h in [-1, H], w in [-1, W]; X zero outside the image) every tap sees every image
+// pixel exactly once and the sum is a plain autocorrelation of the zero-padded input,
+//     A[c][c'](r' - r, s' - s) = sum_{u,v} X[c][u][v] * X[c'][u + r' - r][v + s' - s],
+// of which there are 13 (Cin = 1) or 51 (Cin = 2) distinct ones (A[c][c'](d) = A[c'][c](-d)).  What the ring adds is
+// subtracted again: in its top row only the taps r = 2 are non-zero (image row 0), in its bottom row the taps r = 0, in
+// its left / right columns the taps s = 2 / s = 0 -- four 1-D autocorrelations of the image's border rows / columns --
+// and the four corners, taken away twice, come back once:
+//     M G[(c,r,s)][(c',r',s')] = A - [r=r'=2] R_0(s'-s) - [r=r'=0] R_{H-1}(s'-s) - [s=s'=2] C_0(r'-r) - [s=s'=0] C_{W-1}(r'-r)
+//                                  + [both taps at the same corner] X[c][corner] X[c'][corner]
+// (same for the plain sums in column K).  51 + 2 products per pixel instead of 342, partials per block / per image,
+// one warp per entry folds them in a fixed order in double precision: same `gram` as before to rounding.
+template <int CIN>
+struct AcDims {
+    static constexpr int NA = CIN == 1 ? 13 : 51;        // distinct autocorrelation sums
+    static constexpr int NACC = NA + CIN;                // + the plain sums S_c
+    static constexpr int SEG = CIN * CIN * 5;            // one border row / column: [c][c'][d + 2]
+    static constexpr int B1 = 4 * SEG;                   // border row / column plain sums [seg][c]
+    static constexpr int B2 = B1 + 4 * CIN;              // corner values [corner][c]
+    static constexpr int B3 = B2 + 4 * CIN;              // corner products [corner][c][c']
+    static constexpr int NE = B3 + 4 * CIN * CIN;        // per-image edge partial
+};
+// index of A[c][c2](dr, ds) in a main partial (dr, ds in [-2, 2])
+template <int CIN>
+__host__ __device__ inline int ac_index(int c, int c2, int dr, int ds) {
+    if (c == c2) {
+        if (dr < 0 || (dr == 0 && ds < 0)) { dr = -dr; ds = -ds; }
+        const int i = dr == 0 ? ds : 3 + (dr - 1) * 5 + (ds + 2);
+        return c * 13 + i;
+    }
+    // c != c2 (CIN == 2): A01(dr >= 0) at 26 + dr*5 + ds+2 ; A10(dr > 0) = sum X1[u][v] X0[u+dr][v+ds] at 41 + (dr-1)*5 + ds+2
+    if (c == 0) return dr >= 0 ? 26 + dr * 5 + (ds + 2) : 41 + (-dr - 1) * 5 + (-ds + 2);
+    return dr > 0 ? 41 + (dr - 1) * 5 + (ds + 2) : 26 + (-dr) * 5 + (-ds + 2);
+}
+
+template <int CIN>
+__device__ __forceinline__ void ac_edge_block(const float* __restrict__ x, int H, int W, int b, float* __restrict__ partE) {
+    using D = AcDims<CIN>;
+    constexpr int NW = D::SEG + CIN;                      // per-warp accumulators: the segment's products + plain sums
+    __shared__ float sE[8][NW];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, seg = warp >> 1, half = warp & 1;
+    const bool is_row = seg < 2;
+    const int fixed = (seg == 0 || seg == 2) ? 0 : (is_row ? H - 1 : W - 1), len = is_row ? W : H;
+    const float* img = x + (long)b * CIN * H * W;
+    auto at = [&](int c, int t) -> float {                // element t of the border row / column of channel c, 0 outside
+        if (t < 0 || t >= len) return 0.0f;
+        return is_row ? __ldg(img + ((long)c * H + fixed) * W + t) : __ldg(img + ((long)c * H + t) * W + fixed);
+    };
+    float acc[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) acc[i] = 0.0f;
+    for (int t = half * 32 + lane; t < len; t += 64) {
+        float nb[CIN][5], own[CIN];
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+#pragma unroll
+            for (int d = 0; d < 5; ++d) nb[c][d] = at(c, t + d - 2);
+            own[c] = nb[c][2];
+        }
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+#pragma unroll
+            for (int c2 = 0; c2 < CIN; ++c2)
+#pragma unroll
+                for (int d = 0; d < 5; ++d) acc[(c * CIN + c2) * 5 + d] = fmaf(own[c], nb[c2][d], acc[(c * CIN + c2) * 5 + d]);
+            acc[D::SEG + c] += own[c];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        float v = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sE[warp][i] = v;
+    }
+    __syncthreads();
+    float* out = partE + (long)b * D::NE;
+    for (int i = threadIdx.x; i < 4 * NW; i += blockDim.x) {
+        const int sg = i / NW, e = i - sg * NW;
+        const float v = sE[2 * sg][e] + sE[2 * sg + 1][e];
+        if (e < D::SEG) out[sg * D::SEG + e] = v;
+        else out[D::B1 + sg * CIN + (e - D::SEG)] = v;
+    }
+    if (threadIdx.x < 4 * CIN) {                           // corner values, then their products
+        const int corner = threadIdx.x / CIN, c = threadIdx.x - corner * CIN;
+        const int u = (corner & 2) ? H - 1 : 0, v = (corner & 1) ? W - 1 : 0;
+        const float xc = __ldg(img + ((long)c * H + u) * W + v);
+        out[D::B2 + corner * CIN + c] = xc;
+#pragma unroll
+        for (int c2 = 0; c2 < CIN; ++c2) out[D::B3 + (corner * CIN + c) * CIN + c2] = xc * __ldg(img + ((long)c2 * H + u) * W + v);
+    }
+}
+
+// blocks [0, n_img): the border rows / columns / corners of image b (first, so that they run beside the main blocks);
+// blocks [n_img, n_img + n_main): persistent over row groups, 51 + 2 sums per thread.  The tile of the NEXT group is
+// fetched into registers before the current one is evaluated (every thread owns the same <= kAcStage tile slots in every
+// group, decoded once), so the global-load latency hides behind the products.
+constexpr int kAcStage = 4;
+template <int CIN>
+__global__ void __launch_bounds__(256, 3)
+conv0_ac_kernel(const float* __restrict__ x, int H, int W, unsigned wmagic, int groups_per_img, int n_groups, int n_img,
+                float* __restrict__ partA, float* __restrict__ partE) {
+    pdl_wait();
+    using D = AcDims<CIN>;
+    if ((int)blockIdx.x < n_img) { ac_edge_block<CIN>(x, H, W, (int)blockIdx.x, partE); return; }
+    const int blk = (int)blockIdx.x - n_img, n_main = (int)gridDim.x - n_img;
+    extern __shared__ float xs[];                          // [CIN][kC0Rows + 2][W + 4]: columns -2 .. W+1, zero outside
+    __shared__ float red[8][D::NACC];
+    const int Wp = W + 4, plane = (kC0Rows + 2) * Wp, n_slots = CIN * plane;
+    // this thread's tile slots: (channel, tile row, image column) or "always zero"
+    int s_off[kAcStage], s_rr[kAcStage];                   // offset inside the image of (ci, row 0, ww); -1: zero slot
+#pragma unroll
+    for (int j = 0; j < kAcStage; ++j) {
+        const int i = threadIdx.x + j * 256;
+        s_off[j] = -1; s_rr[j] = 0;
+        if (i < n_slots) {
+            const int ci = i / plane, rem = i - ci * plane, rr = rem / Wp, ww = rem - rr * Wp - 2;
+            s_rr[j] = rr;
+            if (ww >= 0 && ww < W) s_off[j] = ci * H * W + ww;
+        }
+    }
+    auto fetch = [&](int b, int h0, float (&v)[kAcStage]) {
+        const float* img = x + (long)b * CIN * H * W;
+#pragma unroll
+        for (int j = 0; j < kAcStage; ++j) {
+            const int hh = h0 + s_rr[j];
+            v[j] = (s_off[j] >= 0 && hh < H) ? __ldg(img + s_off[j] + hh * W) : 0.0f;
+        }
+    };
+    float acc[D::NACC];
+#pragma unroll
+    for (int i = 0; i < D::NACC; ++i) acc[i] = 0.0f;
+    GroupWalk gw(blk, n_main, groups_per_img);
+    float cur[kAcStage], nxt[kAcStage];
+    if (blk < n_groups) fetch(gw.b, gw.h0(), cur);
+    for (int grp = blk; grp < n_groups; grp += n_main) {
+        const int h0 = gw.h0();
+#pragma unroll
+        for (int j = 0; j < kAcStage; ++j)
+            if (threadIdx.x + j * 256 < n_slots) xs[threadIdx.x + j * 256] = cur[j];
+        gw.next();
+        if (grp + n_main < n_groups) fetch(gw.b, gw.h0(), nxt);
+        __syncthreads();
+        const int npix = min(kC0Rows, H - h0) * W;
+        for (int p = threadIdx.x; p < npix; p += blockDim.x) {
+            const int row = (int)__umulhi((unsigned)p, wmagic), col = p - row * W;
+            const float* b0 = xs + row * Wp + col + 2;     // channel 0 at (u, v); neighbours at [dr * Wp + ds]
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) {
+                const float* bc = b0 + c * plane;
+                const float xc = bc[0];
+                acc[D::NA + c] += xc;
+                // A[c][c]: (0, 0..2), (1..2, -2..2)
+#pragma unroll
+                for (int ds = 0; ds <= 2; ++ds) acc[c * 13 + ds] = fmaf(xc, bc[ds], acc[c * 13 + ds]);
+#pragma unroll
+                for (int dr = 1; dr <= 2; ++dr)
+#pragma unroll
+                    for (int ds = -2; ds <= 2; ++ds)
+                        acc[c * 13 + 3 + (dr - 1) * 5 + ds + 2] = fmaf(xc, bc[dr * Wp + ds], acc[c * 13 + 3 + (dr - 1) * 5 + ds + 2]);
+                if (CIN == 2) {
+                    const float* bo = b0 + (1 - c) * plane;   // the OTHER channel
+                    if (c == 0) {                          // A01(dr = 0..2, ds): X0[u][v] * X1[u + dr][v + ds]
+#pragma unroll
+                        for (int dr = 0; dr <= 2; ++dr)
+#pragma unroll
+                            for (int ds = -2; ds <= 2; ++ds)
+                                acc[26 + dr * 5 + ds + 2] = fmaf(xc, bo[dr * Wp + ds], acc[26 + dr * 5 + ds + 2]);
+                    } else {                               // A10(dr = 1..2, ds): X1[u][v] * X0[u + dr][v + ds]
+#pragma unroll
+                        for (int dr = 1; dr <= 2; ++dr)
+#pragma unroll
+                            for (int ds = -2; ds <= 2; ++ds)
+                                acc[41 + (dr - 1) * 5 + ds + 2] = fmaf(xc, bo[dr * Wp + ds], acc[41 + (dr - 1) * 5 + ds + 2]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kAcStage; ++j) cur[j] = nxt[j];
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < D::NACC; ++i) {
+        float v = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < D::NACC) {
+        float t = 0.0f;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) t += red[w8][threadIdx.x];
+        partA[(long)blk * D::NACC + threadIdx.x] = t;
+    }
+}
+
+// gram[k][k'] (k' <= K, doubles, divided by the pixel count) from the autocorrelation / border partials: one warp per
+// entry, every term folded over its blocks / images in a fixed order (lanes take every 32nd, fixed shuffle tree)
+template <int CIN>
+__global__ void __launch_bounds__(256)
+conv0_ac_gram_kernel(const float* __restrict__ partA, int n_main, const float* __restrict__ partE, int n_img, double inv_n,
+                     double* __restrict__ gram) {
+    pdl_wait();
+    using D = AcDims<CIN>;
+    constexpr int K = CIN * 9, NEnt = K * (K + 1);
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (e >= NEnt) return;
+    const int k = e / (K + 1), k2 = e - k * (K + 1);
+    const int c = k / 9, r = (k % 9) / 3, s = k % 3;
+    auto fold = [&](const float* part, int stride, int n, int idx) -> double {
+        const int mine = n > lane ? (n - lane + 31) / 32 : 0;
+        double a = ordered_sum<8, double>(part + (long)lane * stride + idx, 32L * stride, mine);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        return a;
+    };
+    auto foldA = [&](int idx) { return fold(partA, D::NACC, n_main, idx); };
+    auto foldE = [&](int idx) { return fold(partE, D::NE, n_img, idx); };
+    // corner index of a tap (r, s): (2,2) -> top-left 0, (2,0) -> top-right 1, (0,2) -> bottom-left 2, (0,0) -> bottom-right 3
+    auto corner_of = [](int rr, int ss) { return (rr == 1 || ss == 1) ? -1 : ((rr == 0 ? 2 : 0) + (ss == 0 ? 1 : 0)); };
+    double val;
+    if (k2 == K) {                                         // plain sum of patch_k
+        val = foldA(D::NA + c);
+        if (r == 2) val -= foldE(D::B1 + 0 * CIN + c);
+        if (r == 0) val -= foldE(D::B1 + 1 * CIN + c);
+        if (s == 2) val -= foldE(D::B1 + 2 * CIN + c);
+        if (s == 0) val -= foldE(D::B1 + 3 * CIN + c);
+        const int cr = corner_of(r, s);
+        if (cr >= 0) val += foldE(D::B2 + cr * CIN + c);
+    } else {
+        const int c2 = k2 / 9, r2 = (k2 % 9) / 3, s2 = k2 % 3, dr = r2 - r, ds = s2 - s;
+        val = foldA(ac_index<CIN>(c, c2, dr, ds));
+        if (r == 2 && r2 == 2) val -= foldE(0 * D::SEG + (c * CIN + c2) * 5 + ds + 2);
+        if (r == 0 && r2 == 0) val -= foldE(1 * D::SEG + (c * CIN + c2) * 5 + ds + 2);
+        if (s == 2 && s2 == 2) val -= foldE(2 * D::SEG + (c * CIN + c2) * 5 + dr + 2);
+        if (s == 0 && s2 == 0) val -= foldE(3 * D::SEG + (c * CIN + c2) * 5 + dr + 2);
+        const int cr = corner_of(r, s);
+        if (cr >= 0 && cr == corner_of(r2, s2)) val += foldE(D::B3 + (cr * CIN + c) * CIN + c2);
+    }
+    if (lane == 0) gram[e] = val * inv_n;
+}
+
 // gram[k][k'] (k' <= K, doubles, divided by the pixel count): one warp per entry, fixed order
 __global__ void conv0_gram_reduce_kernel(const float* __restrict__ part, int nblk, int cin, double inv_n,
                                          double* __restrict__ gram) {
@@ -739,15 +986,33 @@ int conv0_lean_stats(const float* x, int cin, int C, int H, int W, int batch, co
                      double* gram, float* part, cudaStream_t st) {
     const int gpi = (H + kC0Rows - 1) / kC0Rows, n_groups = gpi * batch, K0 = 9 * cin;
     const long M = (long)batch * H * W;
-    const int gblk = std::min(n_groups, (cin == 1 ? 5 : 3) * sm_count());
     const unsigned wmagic = (unsigned)(((1ull << 32) + (unsigned)W - 1) / (unsigned)W);
+    const int entries = K0 * (K0 + 1);
+    static const bool direct = [] { const char* e = std::getenv("SEDB200_GRAM_DIRECT"); return e && std::atoi(e) != 0; }();
+    if (!direct && kC0Rows * W < 65536 && (size_t)cin * (kC0Rows + 2) * (W + 4) <= (size_t)kAcStage * 256) {
+        // patch moments from the autocorrelations of the input (51 + 2 products per pixel instead of 342); one wave of
+        // three blocks per SM: the per-image border blocks first, the rest walks the row groups
+        const int n_main = std::min(n_groups, std::max(sm_count(), 3 * sm_count() - batch));
+        const int nacc = cin == 1 ? AcDims<1>::NACC : AcDims<2>::NACC, ne = cin == 1 ? AcDims<1>::NE : AcDims<2>::NE;
+        float* partA = part;
+        float* partE = part + (size_t)n_main * nacc;
+        const size_t asm_bytes = (size_t)cin * (kC0Rows + 2) * (W + 4) * 4;
+        if (cin == 1) launch_k(conv0_ac_kernel<1>, n_main + batch, 256, asm_bytes, st, x, H, W, wmagic, gpi, n_groups, batch, partA, partE);
+        else launch_k(conv0_ac_kernel<2>, n_main + batch, 256, asm_bytes, st, x, H, W, wmagic, gpi, n_groups, batch, partA, partE);
+        SED_POST_LAUNCH();
+        (void)ne;
+        if (cin == 1) launch_k(conv0_ac_gram_kernel<1>, (entries * 32 + 255) / 256, 256, 0, st, partA, n_main, partE, batch, 1.0 / (double)M, gram);
+        else launch_k(conv0_ac_gram_kernel<2>, (entries * 32 + 255) / 256, 256, 0, st, partA, n_main, partE, batch, 1.0 / (double)M, gram);
+        SED_POST_LAUNCH();
+    } else {
+    const int gblk = std::min(n_groups, (cin == 1 ? 5 : 3) * sm_count());
     const size_t gsm = 2 * (size_t)cin * (kC0Rows + 2) * (W + 32) * 4;
     if (cin == 1) launch_k(conv0_gram_kernel<1>, gblk, GramDims<1>::THREADS, gsm, st, x, H, W, wmagic, gpi, n_groups, part);
     else launch_k(conv0_gram_kernel<2>, gblk, GramDims<2>::THREADS, gsm, st, x, H, W, wmagic, gpi, n_groups, part);
     SED_POST_LAUNCH();
-    const int entries = K0 * (K0 + 1);
     launch_k(conv0_gram_reduce_kernel, (entries * 32 + 255) / 256, 256, 0, st, part, gblk, cin, 1.0 / (double)M, gram);
     SED_POST_LAUNCH();
+    }
     launch_k(conv0_bn_finalize_kernel, (C * 32 + 255) / 256, 256, 0, st, gram, cin, C, M, w, bias, gamma, beta, eps, momentum,
                                                                   running, stat);
     SED_POST_LAUNCH();
