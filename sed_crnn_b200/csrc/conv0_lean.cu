@@ -988,7 +988,8 @@ int conv0_lean_stats(const float* x, int cin, int C, int H, int W, int batch, co
     const long M = (long)batch * H * W;
     const unsigned wmagic = (unsigned)(((1ull << 32) + (unsigned)W - 1) / (unsigned)W);
     const int entries = K0 * (K0 + 1);
-    static const bool direct = [] { const char* e = std::getenv("SEDB200_GRAM_DIRECT"); return e && std::atoi(e) != 0; }();
+    const char* e_direct = std::getenv("SEDB200_GRAM_DIRECT");        // read at every call: the tests run both paths
+    const bool direct = e_direct && std::atoi(e_direct) != 0;
     if (!direct && kC0Rows * W < 65536 && (size_t)cin * (kC0Rows + 2) * (W + 4) <= (size_t)kAcStage * 256) {
         // patch moments from the autocorrelations of the input (51 + 2 products per pixel instead of 342); one wave of
         // three blocks per SM: the per-image border blocks first, the rest walks the row groups

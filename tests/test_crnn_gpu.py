@@ -373,3 +373,29 @@ def test_cuda_graph_steps_are_bit_identical_to_eager_steps(pkg):
     m0 = runs[False][5].dropout_masks(8)
     m1 = runs[True][5].dropout_masks(8)
     assert all(torch.equal(a, b) for a, b in zip(m0, m1))
+
+
+@pytest.mark.parametrize("preset,ov,batch", [("c2", {"seq_len": 40}, 5), ("c1", {"seq_len": 24}, 3), ("c2", {}, 16)])
+def test_block0_patch_moments_from_autocorrelations(pkg, monkeypatch, preset, ov, batch):
+    """Block 0's BatchNorm statistics (and its backward) come from the patch moments G = E[patch patch^T] of the input.
+    conv0_ac_kernel assembles G from autocorrelations of the zero-padded input minus border-ring terms (53 products per
+    pixel); conv0_gram_kernel accumulates it entry by entry (342).  Same numbers to rounding: logits, loss and every
+    gradient of one training step agree between the two (SEDB200_GRAM_DIRECT is read at every call)."""
+    import parity_util as PU
+    config, engine = pkg
+    outs = []
+    for direct in ("1", "0"):
+        monkeypatch.setenv("SEDB200_GRAM_DIRECT", direct)
+        rcfg, ref, cfg, eng = PU.make_pair(config, engine, preset, ov, "bce", 1e-4, 1.0, seed=11)
+        x, y = R.synth_batch(rcfg, batch, seed=41)
+        xd, yd = x.cuda(), y.cuda()
+        logits = eng.forward(xd, training=True).clone()
+        loss, _, dlog = eng.loss_and_grad(logits, yd)
+        eng.grads.zero_()
+        eng.backward(xd, dlog)
+        torch.cuda.synchronize()
+        outs.append((logits.cpu(), float(loss), eng.grads.clone().cpu()))
+    (l0, s0, g0), (l1, s1, g1) = outs
+    assert (l0 - l1).abs().max().item() <= 2e-6 * max(1.0, l0.abs().max().item())
+    assert abs(s0 - s1) <= 1e-6 * max(1.0, abs(s0))
+    assert (g0 - g1).abs().max().item() <= 5e-5 * g0.abs().max().item()
